@@ -1,0 +1,97 @@
+/* ORACLE / TEST INFRASTRUCTURE ONLY — never on the product path.
+ *
+ * Chain glue shared by both oracle libraries: compiled once with SLO_PREFIX=ref_ (every SLO(stage) call lands in
+ * the reference's CMSIS-DSP routine) and once with SLO_PREFIX=port_ (the plain-C restatement).
+ * THE COMPOSITION IS OURS: the reference firmware copies samples and contains no chain (dsp_if.c:367
+ * DSP_Set_Mode is empty). What the reference pins is each stage's arithmetic; the chain spec lives in DESIGN.md §3.
+ */
+#include <string.h>
+#include <stdlib.h>
+#include <pthread.h>
+#include "slo_api.h"
+
+/* RX-SSB-f32: see slo_api.h. Stage by stage this is what a firmware author would write inside
+ * DSP_In_Buff_Write (dsp_if.c:286-289) with arm_math.h. */
+void SLO (rx_ssb_f32) (const slo_rx_f32_params *p, slo_rx_f32_state *st, const int16_t *in_iq, int16_t *out_lr,
+                       float *audio_dbg, float *gain_dbg, uint32_t frames)
+{
+  const uint32_t N = p->fft_len, hop = p->hop, ovl = N - hop, B = p->agc_block;
+  int16_t *raw = (int16_t *) malloc (sizeof (int16_t) * 2 * N);
+  int16_t *mono = (int16_t *) malloc (sizeof (int16_t) * hop);
+  float *frame = (float *) malloc (sizeof (float) * 2 * N);
+  float *prod = (float *) malloc (sizeof (float) * 2 * N);
+  float *audio = (float *) malloc (sizeof (float) * hop);
+  float *scaled = (float *) malloc (sizeof (float) * hop);
+  float *absb = (float *) malloc (sizeof (float) * B);
+
+  for (uint32_t o = 0; o < frames; o += hop)
+  {
+    /* overlap-save frame = [previous ovl frames | hop new frames] */
+    memcpy (raw, st->ovl, sizeof (int16_t) * 2 * ovl);
+    memcpy (raw + 2 * ovl, in_iq + 2 * (size_t) o, sizeof (int16_t) * 2 * hop);
+    memcpy (st->ovl, raw + 2 * hop, sizeof (int16_t) * 2 * ovl);
+
+    SLO (q15_to_float) (raw, frame, 2 * N);
+    SLO (cfft_f32) (frame, N, 0, 1);
+    SLO (cmplx_mult_cmplx_f32) (frame, p->mask, prod, N);
+    SLO (cfft_f32) (prod, N, 1, 1);
+    for (uint32_t k = 0; k < hop; k++) audio[k] = prod[2 * (ovl + k)];   /* keep last hop, real part */
+
+    SLO (biquad_df2T_f32) (p->biquad, p->n_stages, st->bq, audio, audio, hop, B);
+    if (audio_dbg) memcpy (audio_dbg + o, audio, sizeof (float) * hop);
+
+    for (uint32_t b = 0; b < hop; b += B)
+    {
+      SLO (abs_f32) (audio + b, absb, B);
+      float peak = SLO (max_f32) (absb, B, 0);
+      /* AGC law (ours): instant attack, exponential release, bounded gain */
+      float rel = st->env * p->agc_decay;
+      float env = peak > rel ? peak : rel;
+      float den = env > p->agc_floor ? env : p->agc_floor;
+      float g = p->agc_target / den;
+      if (g > p->agc_gmax) g = p->agc_gmax;
+      st->env = env;
+      if (gain_dbg) gain_dbg[(o + b) / B] = g;
+      SLO (scale_f32) (audio + b, g, scaled + b, B);
+    }
+    SLO (float_to_q15) (scaled, mono, hop);
+    for (uint32_t k = 0; k < hop; k++)                                   /* USB IN endpoint is stereo: L = R */
+    {
+      out_lr[2 * (size_t) (o + k)] = mono[k];
+      out_lr[2 * (size_t) (o + k) + 1] = mono[k];
+    }
+  }
+  free (raw); free (mono); free (frame); free (prod); free (audio); free (scaled); free (absb);
+}
+
+typedef struct
+{
+  const slo_rx_f32_params *p; slo_rx_f32_state *st; const int16_t *in; int16_t *out;
+  uint32_t c0, c1, frames;
+} slo_rx_job;
+
+static void *slo_rx_worker (void *arg)
+{
+  slo_rx_job *j = (slo_rx_job *) arg;
+  for (uint32_t c = j->c0; c < j->c1; c++)
+    SLO (rx_ssb_f32) (j->p, j->st + c, j->in + 2 * (size_t) c * j->frames, j->out + 2 * (size_t) c * j->frames, 0, 0, j->frames);
+  return 0;
+}
+
+void SLO (rx_ssb_f32_batch) (const slo_rx_f32_params *p, slo_rx_f32_state *st, const int16_t *in_iq, int16_t *out_lr,
+                             uint32_t channels, uint32_t frames, uint32_t nthreads)
+{
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > channels) nthreads = channels;
+  pthread_t *th = (pthread_t *) malloc (sizeof (pthread_t) * nthreads);
+  slo_rx_job *jobs = (slo_rx_job *) malloc (sizeof (slo_rx_job) * nthreads);
+  for (uint32_t t = 0; t < nthreads; t++)
+  {
+    jobs[t].p = p; jobs[t].st = st; jobs[t].in = in_iq; jobs[t].out = out_lr; jobs[t].frames = frames;
+    jobs[t].c0 = (uint32_t) ((uint64_t) channels * t / nthreads);
+    jobs[t].c1 = (uint32_t) ((uint64_t) channels * (t + 1) / nthreads);
+    pthread_create (&th[t], 0, slo_rx_worker, &jobs[t]);
+  }
+  for (uint32_t t = 0; t < nthreads; t++) pthread_join (th[t], 0);
+  free (th); free (jobs);
+}

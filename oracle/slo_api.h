@@ -1,0 +1,136 @@
+/* ORACLE / TEST INFRASTRUCTURE ONLY.
+ *
+ * One C API, two implementations:
+ *   - oracle/_ref/libslo_ref.so   (prefix ref_)  : thin glue that CALLS the reference's own vendored
+ *       CMSIS-DSP V1.5.3 routines, compiled in place from /root/reference/Drivers/CMSIS/DSP/Source
+ *       (see oracle/Makefile). This is "the reference itself, run here".
+ *   - oracle/_port/libslo_port.so (prefix port_) : a plain-C restatement of the same routines
+ *       (oracle/port/*.c), each function citing the reference file:line it follows. It needs nothing
+ *       from /root/reference, so it can be rebuilt on the GPU box.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * either library; the product (selenite_lite_b200/) never does.
+ *
+ * All stage functions work on ONE channel and take plain arrays. `block` is the blockSize the CMSIS
+ * routine is invoked with (the firmware cadence is 48 frames at 48 kHz); `n` must be a
+ * multiple of `block`. State arrays follow the CMSIS layouts quoted next to each prototype.
+ */
+#ifndef SLO_API_H
+#define SLO_API_H
+#include <stdint.h>
+
+#ifndef SLO_PREFIX
+#error "define SLO_PREFIX to ref_ or port_"
+#endif
+#define SLO_CAT2(a, b) a##b
+#define SLO_CAT(a, b) SLO_CAT2 (a, b)
+#define SLO(name) SLO_CAT (SLO_PREFIX, name)
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- conversions (SupportFunctions/arm_q15_to_float.c:65, arm_float_to_q15.c:64) ---- */
+void SLO (q15_to_float) (const int16_t *src, float *dst, uint32_t n);
+void SLO (float_to_q15) (const float *src, int16_t *dst, uint32_t n);
+
+/* ---- FIR (FilteringFunctions/arm_fir_f32.c:553, arm_fir_q15.c:591, arm_fir_fast_q15.c:60, arm_fir_q31.c:60)
+ * coeffs are time-reversed {b[T-1]..b[0]}; state has ntaps+block-1 entries (q15: ntaps+block). */
+void SLO (fir_f32) (const float *coeffs, uint32_t ntaps, float *state, const float *src, float *dst, uint32_t n, uint32_t block);
+void SLO (fir_q15) (const int16_t *coeffs, uint32_t ntaps, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block);
+void SLO (fir_fast_q15) (const int16_t *coeffs, uint32_t ntaps, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block);
+void SLO (fir_q31) (const int32_t *coeffs, uint32_t ntaps, int32_t *state, const int32_t *src, int32_t *dst, uint32_t n, uint32_t block);
+/* decimator: state ntaps+block-1, one output per M inputs (arm_fir_decimate_f32.c:129) */
+void SLO (fir_decimate_f32) (const float *coeffs, uint32_t ntaps, uint32_t M, float *state, const float *src, float *dst, uint32_t n, uint32_t block);
+void SLO (fir_decimate_q15) (const int16_t *coeffs, uint32_t ntaps, uint32_t M, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block);
+/* interpolator: ntaps % L == 0, state block+ntaps/L-1, L outputs per input (arm_fir_interpolate_f32.c:470) */
+void SLO (fir_interpolate_f32) (const float *coeffs, uint32_t ntaps, uint32_t L, float *state, const float *src, float *dst, uint32_t n, uint32_t block);
+void SLO (fir_interpolate_q15) (const int16_t *coeffs, uint32_t ntaps, uint32_t L, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block);
+
+/* ---- biquad cascades: coeffs {b0,b1,b2,a1,a2} per stage, feedback sign +a1,+a2
+ * (arm_biquad_cascade_df1_f32.c:52). df2T state 2/stage, stereo df2T 4/stage, df1 4/stage.
+ * q15 coeffs are {b0,0,b1,b2,a1,a2} (arm_biquad_cascade_df1_q15.c:318). */
+void SLO (biquad_df2T_f32) (const float *coeffs, uint32_t nstages, float *state, const float *src, float *dst, uint32_t n, uint32_t block);
+void SLO (biquad_stereo_df2T_f32) (const float *coeffs, uint32_t nstages, float *state, const float *src, float *dst, uint32_t nframes, uint32_t block);
+void SLO (biquad_df1_f32) (const float *coeffs, uint32_t nstages, float *state, const float *src, float *dst, uint32_t n, uint32_t block);
+void SLO (biquad_df1_q15) (const int16_t *coeffs, uint32_t nstages, int32_t postshift, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block);
+void SLO (biquad_df1_q31) (const int32_t *coeffs, uint32_t nstages, int32_t postshift, int32_t *state, const int32_t *src, int32_t *dst, uint32_t n, uint32_t block);
+
+/* ---- transforms: in-place interleaved re/im (arm_cfft_f32.c:562, arm_cfft_q15.c:77, arm_cfft_q31.c:77,
+ * arm_rfft_fast_f32.c:288). N in {16..4096}. */
+void SLO (cfft_f32) (float *data, uint32_t N, int ifft, int bitrev);
+void SLO (cfft_q15) (int16_t *data, uint32_t N, int ifft, int bitrev);
+void SLO (cfft_q31) (int32_t *data, uint32_t N, int ifft, int bitrev);
+void SLO (rfft_fast_f32) (float *in_destroyed, float *out, uint32_t N, int ifft);
+
+/* ---- complex math (ComplexMathFunctions/arm_cmplx_*.c) ---- */
+void SLO (cmplx_mult_cmplx_f32) (const float *a, const float *b, float *dst, uint32_t n);
+void SLO (cmplx_mult_real_f32) (const float *a, const float *r, float *dst, uint32_t n);
+void SLO (cmplx_conj_f32) (const float *a, float *dst, uint32_t n);
+void SLO (cmplx_mag_f32) (const float *a, float *dst, uint32_t n);
+void SLO (cmplx_mag_squared_f32) (const float *a, float *dst, uint32_t n);
+void SLO (cmplx_mag_q15) (const int16_t *a, int16_t *dst, uint32_t n);
+
+/* ---- statistics (StatisticsFunctions/arm_max_f32.c:58, arm_rms_f32.c:64, arm_power_f32.c:64, ...) ---- */
+float SLO (max_f32) (const float *src, uint32_t n, uint32_t *idx);
+float SLO (rms_f32) (const float *src, uint32_t n);
+float SLO (power_f32) (const float *src, uint32_t n);
+float SLO (mean_f32) (const float *src, uint32_t n);
+int16_t SLO (max_q15) (const int16_t *src, uint32_t n, uint32_t *idx);
+int16_t SLO (rms_q15) (const int16_t *src, uint32_t n);
+
+/* ---- basic math (BasicMathFunctions/arm_scale_f32.c:77, arm_scale_q15.c:56, ...) ---- */
+void SLO (scale_f32) (const float *src, float scale, float *dst, uint32_t n);
+void SLO (mult_f32) (const float *a, const float *b, float *dst, uint32_t n);
+void SLO (add_f32) (const float *a, const float *b, float *dst, uint32_t n);
+void SLO (sub_f32) (const float *a, const float *b, float *dst, uint32_t n);
+void SLO (abs_f32) (const float *a, float *dst, uint32_t n);
+void SLO (scale_q15) (const int16_t *src, int16_t scale_fract, int32_t shift, int16_t *dst, uint32_t n);
+void SLO (add_q15) (const int16_t *a, const int16_t *b, int16_t *dst, uint32_t n);
+void SLO (sub_q15) (const int16_t *a, const int16_t *b, int16_t *dst, uint32_t n);
+void SLO (abs_q15) (const int16_t *a, int16_t *dst, uint32_t n);
+void SLO (shift_q15) (const int16_t *a, int32_t shift, int16_t *dst, uint32_t n);
+
+/* ---- NCO (FastMathFunctions/arm_sin_f32.c:72, arm_cos_f32.c) : element-wise over an array ---- */
+void SLO (sin_f32) (const float *x, float *dst, uint32_t n);
+void SLO (cos_f32) (const float *x, float *dst, uint32_t n);
+
+/* =====================================================================================
+ * Chains. The COMPOSITION is ours (the reference has no chain); every box is one of
+ * the stage routines above, so ref_ chains are straight-line CMSIS calls.
+ * ===================================================================================== */
+#define SLO_MAX_STAGES 4
+#define SLO_MAX_FFT 4096
+
+/* RX-SSB-f32: q15_to_float -> overlap-save [cfft fwd, cmplx_mult(mask), cfft inv, keep last
+ * `hop`, real part] -> biquad_df2T (mono audio) -> per-`agc_block` AGC [abs, max, env/gain recurrence,
+ * scale] -> float_to_q15, written L = R. */
+typedef struct
+{
+  uint32_t fft_len;   /* 512 */
+  uint32_t hop;       /* 384; overlap = fft_len - hop */
+  uint32_t agc_block; /* 48 */
+  uint32_t n_stages;  /* 2 */
+  float biquad[5 * SLO_MAX_STAGES];
+  float agc_target, agc_decay, agc_floor, agc_gmax;
+  const float *mask;  /* 2*fft_len, interleaved re/im, unscaled */
+} slo_rx_f32_params;
+
+typedef struct
+{
+  int16_t ovl[2 * SLO_MAX_FFT];       /* last (fft_len-hop) raw input frames, interleaved I,Q */
+  float bq[2 * SLO_MAX_STAGES];       /* df2T d1,d2 per stage */
+  float env;                          /* AGC envelope */
+} slo_rx_f32_state;
+
+/* frames % hop == 0. audio_dbg (optional) receives the post-biquad, pre-AGC float audio;
+ * gain_dbg (optional) the per-agc_block gain. */
+void SLO (rx_ssb_f32) (const slo_rx_f32_params *p, slo_rx_f32_state *st, const int16_t *in_iq, int16_t *out_lr,
+                       float *audio_dbg, float *gain_dbg, uint32_t frames);
+/* C channels, [C][frames][2] layouts, one state per channel, channels split over nthreads pthreads. */
+void SLO (rx_ssb_f32_batch) (const slo_rx_f32_params *p, slo_rx_f32_state *st, const int16_t *in_iq, int16_t *out_lr,
+                             uint32_t channels, uint32_t frames, uint32_t nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLO_API_H */
