@@ -1,0 +1,150 @@
+/* selenite_b200.h — C ABI of the B200-native batched I/Q block-processing library.
+ *
+ * Drop-in boundary for the sample path of the Selenite Lite firmware (reference tree = /root/reference):
+ * the functions of Core/Inc/dsp_if.h:42-51, (a) batched over independent channels with a context handle
+ * prepended and the channel index as the slowest axis ([channels][size], `size` in the SAME unit as the
+ * firmware function), and (b) as single-channel wrappers with the firmware's exact names and signatures so
+ * a dsp_if.h consumer (USB_DEVICE/App/usbd_audio_if.c:179-202, the I2S callbacks dsp_if.c:50-67) links
+ * unchanged. Plain pointers and sizes only; no CUDA or torch types appear in any signature (a CUDA stream is
+ * passed as an opaque void*).
+ *
+ * Sample format everywhere: interleaved little-endian int16 I,Q (= L,R) frames, as on the I2S bus
+ * (Core/Src/main.c:333-341) and the UAC1 endpoints (USB_DEVICE/Class/usbd_audio.c:329-334).
+ *
+ * There is no CPU fallback: every entry point that moves samples runs CUDA kernels on the context's device
+ * and returns SLB_ERR_CUDA if that fails.
+ */
+#ifndef SELENITE_B200_H
+#define SELENITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLB_OK               0
+#define SLB_ERR_ARG         (-1)   /* bad argument (null pointer, size not a whole number of blocks, ...) */
+#define SLB_ERR_CUDA        (-2)   /* CUDA runtime error; text in slb_last_error() */
+#define SLB_ERR_STATE       (-3)   /* call not valid in the current state */
+#define SLB_ERR_UNSUPPORTED (-4)   /* parameter combination this build has no kernel for */
+
+/* FT-817 mode bytes handed to DSP_Set_Mode (reference: Core/Inc/rxtx_if.h:33-43, call site rxtx_if.c:647) */
+#define SLB_MODE_LSB 0x00
+#define SLB_MODE_USB 0x01
+#define SLB_MODE_CW  0x02
+#define SLB_MODE_CWR 0x03
+#define SLB_MODE_AM  0x04
+#define SLB_MODE_FM  0x08
+#define SLB_MODE_DIG 0x0A
+#define SLB_MODE_PKT 0x0C
+
+/* What sits between pbuf and the ring store inside DSP_In_Buff_Write (dsp_if.c:286-289) */
+#define SLB_CHAIN_PASS        0    /* the firmware as shipped: bit-exact int16 copy */
+#define SLB_CHAIN_RX_SSB_F32  1    /* unpack -> FFT overlap-save SSB demod -> biquad cascade -> AGC -> pack */
+
+#define SLB_MAX_STAGES 4
+#define SLB_MAX_MASKS  8
+
+typedef struct slb_ctx slb_ctx;
+
+typedef struct
+{
+  uint32_t channels;     /* independent I/Q streams handled by this context (this GPU's shard) */
+  uint32_t fs;           /* USBD_AUDIO_FREQ: 48000, 96000 or 192000 (usbd_audio.h:46, dsp_if.h:55-57) */
+  int32_t  device;       /* CUDA device ordinal */
+  uint32_t chain;        /* SLB_CHAIN_* */
+} slb_config;
+
+/* RX-SSB-f32 chain parameters. Oracle stage for each field in brackets. */
+typedef struct
+{
+  uint32_t fft_len;                      /* overlap-save FFT length [arm_cfft_f32]; this build: 512 */
+  uint32_t hop;                          /* new frames per FFT frame; this build: 384 (= DSP_BUFF_SIZE at 48 kHz) */
+  uint32_t agc_block;                    /* AGC detector block = firmware block, fs/1000 frames; this build: 48 */
+  uint32_t n_stages;                     /* audio biquad stages [arm_biquad_cascade_df2T_f32]; this build: 2 */
+  float    biquad[5 * SLB_MAX_STAGES];   /* {b0,b1,b2,a1,a2} per stage, CMSIS sign (+a1,+a2 feedback) */
+  float    agc_target, agc_decay, agc_floor, agc_gmax;
+} slb_rx_f32_params;
+
+/* ---- life cycle ---- */
+int  slb_create (const slb_config *cfg, slb_ctx **out);
+void slb_destroy (slb_ctx *ctx);
+const char *slb_last_error (const slb_ctx *ctx);           /* ctx may be NULL: last create() failure */
+const char *slb_version (void);
+
+/* ---- frozen default design (there are no taps or constants in the reference) ---- */
+int slb_default_rx_f32_params (uint32_t fs, slb_rx_f32_params *out);
+/* frequency response of the frozen 129-tap complex band-pass for `mode`, 2*fft_len floats re/im, UNSCALED */
+int slb_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out);
+int slb_set_rx_f32_params (slb_ctx *ctx, const slb_rx_f32_params *p);
+int slb_get_rx_f32_params (const slb_ctx *ctx, slb_rx_f32_params *p);
+int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask);   /* host, 2*fft_len floats */
+int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask);
+
+/* ---- the firmware API, batched (reference: Core/Inc/dsp_if.h:42-51; bodies Core/Src/dsp_if.c) ----
+ * pbuf is HOST memory laid out [channels][size]; `size` means what it means in the firmware. */
+int SLB_DSP_Init (slb_ctx *ctx);                                                   /* dsp_if.c:377 */
+int SLB_DSP_Set_RX (slb_ctx *ctx);                                                 /* dsp_if.c:347 */
+int SLB_DSP_Set_TX (slb_ctx *ctx);                                                 /* dsp_if.c:357 */
+int SLB_DSP_Set_Mode (slb_ctx *ctx, uint8_t mode);                                 /* dsp_if.c:367, all channels */
+int SLB_DSP_Set_Mode_Channel (slb_ctx *ctx, uint32_t channel, uint8_t mode);
+int SLB_DSP_In_Buff_Write (slb_ctx *ctx, const uint16_t *pbuf, uint16_t size);     /* dsp_if.c:250, size = half-words */
+int SLB_DSP_In_Buff_Read (slb_ctx *ctx, uint8_t *pbuf, uint32_t size);             /* dsp_if.c:310, size = bytes */
+int SLB_DSP_Out_Buff_Write (slb_ctx *ctx, const uint8_t *pbuf, uint32_t size);     /* dsp_if.c:116, size = bytes */
+int SLB_DSP_Out_Buff_Read (slb_ctx *ctx, uint16_t *pbuf, uint16_t size);           /* dsp_if.c:204, size = half-words */
+int SLB_DSP_Out_Buff_Mute (slb_ctx *ctx);                                          /* dsp_if.c:188 */
+/* ring introspection (tests): which 0 = RX ring (dsp_in_buff), 1 = TX ring (dsp_out_buff); out = {enable, rd, wr} */
+int slb_ring_get_ptrs (const slb_ctx *ctx, int which, uint32_t out[3]);
+/* copies the de-interleaved ring contents to host: i, q each [channels][DSP_BUFF_SIZE] */
+int slb_ring_get_iq (slb_ctx *ctx, int which, int16_t *i, int16_t *q);
+
+/* ---- bulk path: many firmware blocks per call, ring bypassed ----
+ * in/out: [channels][frames][2] int16; frames must be a multiple of hop (PASS: any).
+ * *_device: device pointers, asynchronous on `stream` (a cudaStream_t passed as void*, NULL = default stream).
+ * *_host: host pointers; stages through pinned memory with chunked H2D / kernel / D2H overlap, synchronous. */
+int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream);
+int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames);
+/* optional float tap: post-biquad, pre-AGC audio [channels][frames] f32 and per-block gains [channels][frames/agc_block]
+ * are written by the next slb_rx_process_device call(s) when non-NULL (device pointers) */
+int slb_rx_set_debug_taps (slb_ctx *ctx, float *d_audio, float *d_gain);
+
+/* ---- carried state = the checkpoint: overlap tail, biquad d1/d2, AGC envelope, ring ---- */
+int slb_state_size (const slb_ctx *ctx, size_t *bytes);
+int slb_state_save (slb_ctx *ctx, void *host_buf, size_t bytes);
+int slb_state_load (slb_ctx *ctx, const void *host_buf, size_t bytes);
+
+/* ---- host-only logic, callable without a GPU (unit tests of the index arithmetic and the scan tables) ----
+ * One firmware ring's pointer logic, Core/Src/dsp_if.c:116-180, :204-219, :250-301, :310-340. state = {enable, rd, wr}
+ * is updated in place; the return value is the ring slot of the first frame moved (a write stores frames+1 slots:
+ * the block, then its last frame once more, dsp_if.c:291-300). */
+uint32_t slb_ring_plan_write (uint32_t ring_frames, int is_out, uint32_t state[3], uint32_t frames);
+uint32_t slb_ring_plan_read (uint32_t ring_frames, int is_out, uint32_t state[3], uint32_t frames);
+/* tables of the time-parallel 2-stage df2T evaluation: Mpow[5][16], Cresp[48][4] */
+int slb_biquad_scan_tables (const float coef10[10], float *Mpow80, float *Cresp192);
+
+/* ---- accounting ---- */
+uint64_t slb_kernel_launches (const slb_ctx *ctx);   /* kernels this context has launched since create */
+int slb_sync (slb_ctx *ctx);
+
+/* ---- single-channel drop-in with the firmware's own names and signatures (Core/Inc/dsp_if.h:42-51).
+ * They drive one process-global 1-channel context on device 0 (env SELENITE_B200_DEVICE, SELENITE_B200_FS,
+ * SELENITE_B200_CHAIN=pass|rx_ssb_f32; default pass at 48000 = the firmware's behaviour). Like the firmware
+ * they return void; failures are reported through slb_dropin_status(). ---- */
+void DSP_Init (void);
+void DSP_Set_RX (void);
+void DSP_Set_TX (void);
+void DSP_Set_Mode (uint8_t mode);
+void DSP_In_Buff_Write (uint16_t *pbuf, uint16_t size);
+void DSP_In_Buff_Read (uint8_t *pbuf, uint32_t size);
+void DSP_Out_Buff_Write (uint8_t *pbuf, uint32_t size);
+void DSP_Out_Buff_Read (uint16_t *pbuf, uint16_t size);
+void DSP_Out_Buff_Mute (void);
+int  slb_dropin_status (void);
+slb_ctx *slb_dropin_ctx (void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELENITE_B200_H */

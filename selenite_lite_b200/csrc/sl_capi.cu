@@ -1,0 +1,587 @@
+// Host library + C ABI (include/selenite_b200.h). Mirrors the reference module Core/Src/dsp_if.c: same entry points,
+// same argument meaning, ring index arithmetic identical; the sample movement and the inserted chain run on the GPU.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "sl_internal.h"
+
+using namespace sl;
+
+namespace {
+std::string g_create_error;
+constexpr int kBulkSlots = 3;          // pipeline depth of the host bulk path
+}  // namespace
+
+struct slb_ctx
+{
+  slb_config cfg{};
+  Geometry geo{ 48000 };
+  int sm_count = 148;
+  std::string err;
+  uint64_t launches = 0;
+  cudaStream_t stream = nullptr;
+
+  // chain configuration
+  slb_rx_f32_params rx{};
+  BiquadScanTables tables{};
+  std::vector<float> masks_host;       // [SLB_MAX_MASKS][2*fft_len], unscaled, as set
+  std::vector<uint8_t> slot_host;      // [C]
+  std::vector<uint8_t> mode_host;      // [C]
+  bool tx_mode = false;
+
+  // device: chain constants + carried state
+  float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
+  int16_t *d_ovl[2] = { nullptr, nullptr }; int ovl_parity = 0;
+  float *d_state = nullptr; unsigned *d_flag = nullptr; unsigned *d_queue = nullptr; int queue_rr = 0;
+  unsigned flag_base = 0;
+  float *dbg_audio = nullptr, *dbg_gain = nullptr;
+
+  // device: firmware rings (de-interleaved planes) + per-call block staging
+  RingPtrs ring_in, ring_out;
+  int16_t *d_ring[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [which][i|q]
+  int16_t *d_blk = nullptr; size_t blk_frames = 0;                           // [C][blk_frames][2]
+  // chain at the 1 ms cadence: accumulate `hop` frames, process, feed the ring from the previous super-block
+  int16_t *d_acc = nullptr; int16_t *d_proc[2] = { nullptr, nullptr }; uint32_t acc_fill = 0; int proc_cur = 0;
+
+  // host bulk path
+  int16_t *d_bulk_in[kBulkSlots] = {}; int16_t *d_bulk_out[kBulkSlots] = {}; size_t bulk_bytes = 0;
+  cudaStream_t bulk_stream[kBulkSlots] = {}; cudaEvent_t bulk_done[kBulkSlots] = {};
+};
+
+#define CK(ctx, call)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (cudaError_t) (call);                                                         \
+    if (e_ != cudaSuccess) {                                                                       \
+      char b_[512]; std::snprintf (b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString (e_)); \
+      (ctx)->err = b_; return SLB_ERR_CUDA;                                                        \
+    }                                                                                              \
+  } while (0)
+
+static int fail (slb_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; else g_create_error = msg; return code; }
+
+static int upload_chain_constants (slb_ctx *ctx)
+{
+  const uint32_t N = ctx->rx.fft_len;
+  std::vector<float> scaled (ctx->masks_host.size ());
+  const float inv = 1.0f / (float) N;                      // arm_cfft_f32.c:604-614 scales by 1/L after the transform;
+  for (size_t i = 0; i < scaled.size (); i++) scaled[i] = ctx->masks_host[i] * inv;   // power of two: exact either way
+  CK (ctx, cudaMemcpyAsync (ctx->d_masks, scaled.data (), scaled.size () * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
+  CK (ctx, cudaMemcpyAsync (ctx->d_slot, ctx->slot_host.data (), ctx->slot_host.size (), cudaMemcpyHostToDevice, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  design_biquad_scan_tables (ctx->rx.biquad, &ctx->tables);
+  return SLB_OK;
+}
+
+static int reset_state (slb_ctx *ctx)
+{
+  const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop;
+  for (int p = 0; p < 2; p++) CK (ctx, cudaMemsetAsync (ctx->d_ovl[p], 0, (size_t) C * ovl * 4, ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_state, 0, (size_t) C * 8 * sizeof (float), ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_flag, 0, (size_t) C * sizeof (unsigned), ctx->stream));
+  for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) CK (ctx, cudaMemsetAsync (ctx->d_ring[w][k], 0, (size_t) C * R * 2, ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_acc, 0, (size_t) C * hop * 4, ctx->stream));
+  for (int p = 0; p < 2; p++) CK (ctx, cudaMemsetAsync (ctx->d_proc[p], 0, (size_t) C * hop * 4, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  ctx->flag_base = 0; ctx->ovl_parity = 0; ctx->acc_fill = 0; ctx->proc_cur = 0;
+  ctx->ring_in.reset (R); ctx->ring_out.reset (R);
+  return SLB_OK;
+}
+
+extern "C" {
+
+const char *slb_version (void) { return "selenite-b200 0.1 (sm_100a)"; }
+const char *slb_last_error (const slb_ctx *ctx) { return ctx ? ctx->err.c_str () : g_create_error.c_str (); }
+uint64_t slb_kernel_launches (const slb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int slb_default_rx_f32_params (uint32_t fs, slb_rx_f32_params *out) { return design_default_rx_f32 (fs, out); }
+int slb_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out) { return design_default_mask (fs, fft_len, mode, mask_out); }
+
+int slb_create (const slb_config *cfg, slb_ctx **out)
+{
+  if (!cfg || !out) return fail (nullptr, SLB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->channels == 0) return fail (nullptr, SLB_ERR_ARG, "channels must be > 0");
+  if (cfg->fs != 48000u && cfg->fs != 96000u && cfg->fs != 192000u) return fail (nullptr, SLB_ERR_ARG, "fs must be 48000, 96000 or 192000");
+  if (cfg->chain != SLB_CHAIN_PASS && cfg->chain != SLB_CHAIN_RX_SSB_F32) return fail (nullptr, SLB_ERR_ARG, "unknown chain");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount (&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail (nullptr, SLB_ERR_CUDA, "no CUDA device: selenite-b200 has no CPU fallback (cudaGetDeviceCount failed or returned 0)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail (nullptr, SLB_ERR_ARG, "device ordinal out of range");
+  if ((e = cudaSetDevice (cfg->device)) != cudaSuccess) return fail (nullptr, SLB_ERR_CUDA, cudaGetErrorString (e));
+
+  slb_ctx *ctx = new slb_ctx ();
+  ctx->cfg = *cfg; ctx->geo = Geometry (cfg->fs);
+  cudaDeviceGetAttribute (&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  design_default_rx_f32 (cfg->fs, &ctx->rx);
+  ctx->rx.agc_block = ctx->geo.block_frames;
+  const uint32_t C = cfg->channels, N = ctx->rx.fft_len, hop = ctx->rx.hop, ovl = N - hop, R = ctx->geo.ring_frames;
+
+  ctx->masks_host.assign ((size_t) SLB_MAX_MASKS * 2 * N, 0.0f);
+  const uint8_t modes[6] = { SLB_MODE_LSB, SLB_MODE_USB, SLB_MODE_CW, SLB_MODE_CWR, SLB_MODE_DIG, SLB_MODE_PKT };
+  for (uint8_t m : modes) design_default_mask (cfg->fs, N, m, ctx->masks_host.data () + (size_t) mode_to_mask_slot (m) * 2 * N);
+  ctx->mode_host.assign (C, SLB_MODE_USB);
+  ctx->slot_host.assign (C, (uint8_t) mode_to_mask_slot (SLB_MODE_USB));
+
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string (#call) + " -> " + cudaGetErrorString (e_); slb_destroy (ctx); return SLB_ERR_CUDA; } } while (0)
+  CKC (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
+  CKC (cudaMalloc (&ctx->d_masks, (size_t) SLB_MAX_MASKS * 2 * N * sizeof (float)));
+  CKC (cudaMalloc (&ctx->d_slot, C));
+  CKC (cudaMalloc (&ctx->d_twiddle, (size_t) 2 * N * sizeof (float)));
+  for (int p = 0; p < 2; p++) CKC (cudaMalloc (&ctx->d_ovl[p], (size_t) C * ovl * 4));
+  CKC (cudaMalloc (&ctx->d_state, (size_t) C * 8 * sizeof (float)));
+  CKC (cudaMalloc (&ctx->d_flag, (size_t) C * sizeof (unsigned)));
+  CKC (cudaMalloc (&ctx->d_queue, 64 * sizeof (unsigned)));
+  for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) CKC (cudaMalloc (&ctx->d_ring[w][k], (size_t) C * R * 2));
+  ctx->blk_frames = R;
+  CKC (cudaMalloc (&ctx->d_blk, (size_t) C * ctx->blk_frames * 4));
+  CKC (cudaMalloc (&ctx->d_acc, (size_t) C * hop * 4));
+  for (int p = 0; p < 2; p++) CKC (cudaMalloc (&ctx->d_proc[p], (size_t) C * hop * 4));
+  {
+    std::vector<float> tw (2 * N);
+    for (uint32_t k = 0; k < N; k++)
+    {
+      const double a = -2.0 * 3.14159265358979323846 * (double) k / (double) N;
+      tw[2 * k] = (float) std::cos (a); tw[2 * k + 1] = (float) std::sin (a);
+    }
+    CKC (cudaMemcpy (ctx->d_twiddle, tw.data (), tw.size () * sizeof (float), cudaMemcpyHostToDevice));
+  }
+#undef CKC
+  int rc = upload_chain_constants (ctx);
+  if (rc == SLB_OK) rc = reset_state (ctx);
+  if (rc != SLB_OK) { g_create_error = ctx->err; slb_destroy (ctx); return rc; }
+  *out = ctx;
+  return SLB_OK;
+}
+
+void slb_destroy (slb_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice (ctx->cfg.device);
+  cudaDeviceSynchronize ();
+  cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle);
+  for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
+  cudaFree (ctx->d_state); cudaFree (ctx->d_flag); cudaFree (ctx->d_queue);
+  for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
+  cudaFree (ctx->d_blk); cudaFree (ctx->d_acc);
+  for (int s = 0; s < kBulkSlots; s++)
+  {
+    cudaFree (ctx->d_bulk_in[s]); cudaFree (ctx->d_bulk_out[s]);
+    if (ctx->bulk_stream[s]) cudaStreamDestroy (ctx->bulk_stream[s]);
+    if (ctx->bulk_done[s]) cudaEventDestroy (ctx->bulk_done[s]);
+  }
+  if (ctx->stream) cudaStreamDestroy (ctx->stream);
+  delete ctx;
+}
+
+int slb_sync (slb_ctx *ctx)
+{
+  if (!ctx) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  return SLB_OK;
+}
+
+int slb_set_rx_f32_params (slb_ctx *ctx, const slb_rx_f32_params *p)
+{
+  if (!ctx || !p) return SLB_ERR_ARG;
+  if (p->fft_len != 512 || p->hop != 384 || p->n_stages != 2 || p->agc_block != (uint32_t) kRun)
+    return fail (ctx, SLB_ERR_UNSUPPORTED, "this build has kernels for fft_len=512, hop=384, n_stages=2, agc_block=48 only");
+  if (!(p->agc_decay > 0.f && p->agc_decay <= 1.f) || !(p->agc_floor > 0.f) || !(p->agc_gmax > 0.f) || !(p->agc_target > 0.f))
+    return fail (ctx, SLB_ERR_ARG, "AGC constants out of range");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  ctx->rx = *p;
+  return upload_chain_constants (ctx);
+}
+int slb_get_rx_f32_params (const slb_ctx *ctx, slb_rx_f32_params *p) { if (!ctx || !p) return SLB_ERR_ARG; *p = ctx->rx; return SLB_OK; }
+
+int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask)
+{
+  if (!ctx || !mask) return SLB_ERR_ARG;
+  const int slot = mode_to_mask_slot (mode);
+  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "mode has no spectral mask (AM/FM are not SSB-style demodulators)");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  std::memcpy (ctx->masks_host.data () + (size_t) slot * 2 * ctx->rx.fft_len, mask, (size_t) 2 * ctx->rx.fft_len * sizeof (float));
+  return upload_chain_constants (ctx);
+}
+int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask)
+{
+  if (!ctx || !mask) return SLB_ERR_ARG;
+  const int slot = mode_to_mask_slot (mode);
+  if (slot < 0) return SLB_ERR_UNSUPPORTED;
+  std::memcpy (mask, ctx->masks_host.data () + (size_t) slot * 2 * ctx->rx.fft_len, (size_t) 2 * ctx->rx.fft_len * sizeof (float));
+  return SLB_OK;
+}
+
+int slb_rx_set_debug_taps (slb_ctx *ctx, float *d_audio, float *d_gain)
+{
+  if (!ctx) return SLB_ERR_ARG;
+  ctx->dbg_audio = d_audio; ctx->dbg_gain = d_gain;
+  return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Firmware API, batched
+// ------------------------------------------------------------------------------------------------------------------
+int SLB_DSP_Init (slb_ctx *ctx)                       // dsp_if.c:377-383 (+ i2s_buff_init :74-83: zero the buffers)
+{
+  if (!ctx) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  ctx->tx_mode = false;
+  return reset_state (ctx);
+}
+int SLB_DSP_Set_RX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; ctx->tx_mode = false; return SLB_OK; }   // dsp_if.c:347 (codec routing is out of scope)
+int SLB_DSP_Set_TX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; ctx->tx_mode = true; return SLB_OK; }    // dsp_if.c:357
+
+int SLB_DSP_Set_Mode_Channel (slb_ctx *ctx, uint32_t ch, uint8_t mode)
+{
+  if (!ctx || ch >= ctx->cfg.channels) return SLB_ERR_ARG;
+  const int slot = mode_to_mask_slot (mode);
+  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "AM/FM demodulators are not built yet (DESIGN.md: next)");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  ctx->mode_host[ch] = mode; ctx->slot_host[ch] = (uint8_t) slot;
+  CK (ctx, cudaMemcpyAsync (ctx->d_slot + ch, &ctx->slot_host[ch], 1, cudaMemcpyHostToDevice, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  return SLB_OK;
+}
+int SLB_DSP_Set_Mode (slb_ctx *ctx, uint8_t mode)     // dsp_if.c:367-370 is the empty hook this fills
+{
+  if (!ctx) return SLB_ERR_ARG;
+  const int slot = mode_to_mask_slot (mode);
+  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "AM/FM demodulators are not built yet (DESIGN.md: next)");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  std::fill (ctx->mode_host.begin (), ctx->mode_host.end (), mode);
+  std::fill (ctx->slot_host.begin (), ctx->slot_host.end (), (uint8_t) slot);
+  CK (ctx, cudaMemcpyAsync (ctx->d_slot, ctx->slot_host.data (), ctx->slot_host.size (), cudaMemcpyHostToDevice, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  return SLB_OK;
+}
+
+static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
+                          float *dbg_audio, float *dbg_gain, cudaStream_t stream)
+{
+  const uint32_t ovl = ctx->rx.fft_len - ctx->rx.hop;
+  RxF32Launch L{};
+  L.in = d_in; L.out = d_out; L.audio_dbg = dbg_audio; L.gain_dbg = dbg_gain;
+  L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
+  L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
+  L.queue = ctx->d_queue + (ctx->queue_rr++ % 64);
+  L.masks = ctx->d_masks; L.mask_slot = ctx->d_slot + ch0; L.twiddle = ctx->d_twiddle;
+  L.flag_base = ctx->flag_base; L.channels = nch; L.frames = frames;
+  L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;
+  L.tables = &ctx->tables;
+  CK (ctx, launch_rx_ssb_f32 (L, ctx->sm_count, stream));
+  ctx->launches += rx_ssb_f32_launches_per_call ();
+  return SLB_OK;
+}
+// after ALL channels have been advanced by `frames`
+static void rx_advance (slb_ctx *ctx, uint32_t frames) { ctx->flag_base += rx_ssb_f32_tiles (frames); ctx->ovl_parity ^= 1; }
+
+static int ensure_blk (slb_ctx *ctx, size_t frames)
+{
+  if (frames <= ctx->blk_frames) return SLB_OK;
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  CK (ctx, cudaFree (ctx->d_blk)); ctx->d_blk = nullptr;
+  CK (ctx, cudaMalloc (&ctx->d_blk, (size_t) ctx->cfg.channels * frames * 4));
+  ctx->blk_frames = frames;
+  return SLB_OK;
+}
+
+static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_t frames)
+{
+  const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames;
+  if (!pbuf || frames == 0 || frames + 1 > R) return fail (ctx, SLB_ERR_ARG, "block must hold 1..DSP_BUFF_SIZE-1 frames");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
+  const bool chain = (which == 0 && ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32);
+  if (!chain)
+  {
+    int rc = ensure_blk (ctx, frames); if (rc) return rc;
+    CK (ctx, cudaMemcpyAsync (ctx->d_blk, pbuf, (size_t) C * frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t wr0 = rp.plan_write (which != 0, frames);
+    CK (ctx, launch_ring_write (ctx->d_blk, frames, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, wr0, frames, ctx->stream));
+    ctx->launches++;
+  }
+  else
+  {
+    const uint32_t hop = ctx->rx.hop;
+    if (hop % frames != 0 || ctx->acc_fill % frames != 0) return fail (ctx, SLB_ERR_ARG, "with a chain the block size must divide the hop (384)");
+    // 1. this block joins the super-block being accumulated
+    CK (ctx, cudaMemcpy2DAsync (ctx->d_acc + (size_t) ctx->acc_fill * 2, (size_t) hop * 4, pbuf, (size_t) frames * 4, (size_t) frames * 4, C,
+                                cudaMemcpyHostToDevice, ctx->stream));
+    // 2. the ring is fed, at the same cadence, from the previously processed super-block (chain latency = hop frames)
+    const uint32_t wr0 = rp.plan_write (false, frames);
+    CK (ctx, launch_ring_write (ctx->d_proc[ctx->proc_cur] + (size_t) ctx->acc_fill * 2, hop, ctx->d_ring[0][0], ctx->d_ring[0][1], C, R, wr0,
+                                frames, ctx->stream));
+    ctx->launches++;
+    ctx->acc_fill += frames;
+    // 3. a full super-block runs through the fused chain
+    if (ctx->acc_fill == hop)
+    {
+      int rc = run_rx_kernel (ctx, ctx->d_acc, ctx->d_proc[ctx->proc_cur ^ 1], 0, C, hop, nullptr, nullptr, ctx->stream);
+      if (rc) return rc;
+      rx_advance (ctx, hop);
+      ctx->proc_cur ^= 1; ctx->acc_fill = 0;
+    }
+  }
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  return SLB_OK;
+}
+
+static int ring_read_common (slb_ctx *ctx, int which, void *pbuf, uint32_t frames)
+{
+  const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames;
+  if (!pbuf || frames == 0) return fail (ctx, SLB_ERR_ARG, "empty read");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  int rc = ensure_blk (ctx, frames); if (rc) return rc;
+  RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
+  const uint32_t rd0 = rp.plan_read (which != 0, frames);
+  CK (ctx, launch_ring_read (ctx->d_blk, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, rd0, frames, ctx->stream));
+  ctx->launches++;
+  CK (ctx, cudaMemcpyAsync (pbuf, ctx->d_blk, (size_t) C * frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  return SLB_OK;
+}
+
+int SLB_DSP_In_Buff_Write (slb_ctx *ctx, const uint16_t *pbuf, uint16_t size)      // size in half-words
+{ if (!ctx) return SLB_ERR_ARG; if (size < 2 || (size & 1)) return fail (ctx, SLB_ERR_ARG, "size must be an even number of half-words >= 2"); return ring_write_common (ctx, 0, pbuf, size / 2u); }
+int SLB_DSP_In_Buff_Read (slb_ctx *ctx, uint8_t *pbuf, uint32_t size)              // size in bytes
+{ if (!ctx) return SLB_ERR_ARG; if (size < 4 || (size & 3)) return fail (ctx, SLB_ERR_ARG, "size must be a multiple of 4 bytes"); return ring_read_common (ctx, 0, pbuf, size / 4u); }
+int SLB_DSP_Out_Buff_Write (slb_ctx *ctx, const uint8_t *pbuf, uint32_t size)      // size in bytes
+{ if (!ctx) return SLB_ERR_ARG; if (size < 4 || (size & 3)) return fail (ctx, SLB_ERR_ARG, "size must be a multiple of 4 bytes"); return ring_write_common (ctx, 1, pbuf, size / 4u); }
+int SLB_DSP_Out_Buff_Read (slb_ctx *ctx, uint16_t *pbuf, uint16_t size)            // size in half-words
+{ if (!ctx) return SLB_ERR_ARG; if (size < 2 || (size & 1)) return fail (ctx, SLB_ERR_ARG, "size must be an even number of half-words >= 2"); return ring_read_common (ctx, 1, pbuf, size / 2u); }
+
+int SLB_DSP_Out_Buff_Mute (slb_ctx *ctx)                                           // dsp_if.c:188-195: zero the samples, keep the pointers
+{
+  if (!ctx) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const size_t bytes = (size_t) ctx->cfg.channels * ctx->geo.ring_frames * 2;
+  CK (ctx, cudaMemsetAsync (ctx->d_ring[1][0], 0, bytes, ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_ring[1][1], 0, bytes, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  return SLB_OK;
+}
+
+int slb_ring_get_ptrs (const slb_ctx *ctx, int which, uint32_t out[3])
+{
+  if (!ctx || !out || which < 0 || which > 1) return SLB_ERR_ARG;
+  const RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
+  out[0] = rp.enable; out[1] = rp.rd; out[2] = rp.wr;
+  return SLB_OK;
+}
+int slb_ring_get_iq (slb_ctx *ctx, int which, int16_t *i, int16_t *q)
+{
+  if (!ctx || !i || !q || which < 0 || which > 1) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const size_t bytes = (size_t) ctx->cfg.channels * ctx->geo.ring_frames * 2;
+  CK (ctx, cudaMemcpy (i, ctx->d_ring[which][0], bytes, cudaMemcpyDeviceToHost));
+  CK (ctx, cudaMemcpy (q, ctx->d_ring[which][1], bytes, cudaMemcpyDeviceToHost));
+  return SLB_OK;
+}
+
+uint32_t slb_ring_plan_write (uint32_t ring_frames, int is_out, uint32_t state[3], uint32_t frames)
+{
+  RingPtrs rp; rp.size = ring_frames; rp.enable = state[0]; rp.rd = state[1]; rp.wr = state[2];
+  const uint32_t first = rp.plan_write (is_out != 0, frames);
+  state[0] = rp.enable; state[1] = rp.rd; state[2] = rp.wr;
+  return first;
+}
+uint32_t slb_ring_plan_read (uint32_t ring_frames, int is_out, uint32_t state[3], uint32_t frames)
+{
+  RingPtrs rp; rp.size = ring_frames; rp.enable = state[0]; rp.rd = state[1]; rp.wr = state[2];
+  const uint32_t first = rp.plan_read (is_out != 0, frames);
+  state[0] = rp.enable; state[1] = rp.rd; state[2] = rp.wr;
+  return first;
+}
+int slb_biquad_scan_tables (const float coef10[10], float *Mpow80, float *Cresp192)
+{
+  if (!coef10 || !Mpow80 || !Cresp192) return SLB_ERR_ARG;
+  BiquadScanTables t; design_biquad_scan_tables (coef10, &t);
+  std::memcpy (Mpow80, t.Mpow, sizeof t.Mpow); std::memcpy (Cresp192, t.Cresp, sizeof t.Cresp);
+  return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Bulk path
+// ------------------------------------------------------------------------------------------------------------------
+int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream)
+{
+  if (!ctx || !d_in || !d_out || frames == 0) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  if (ctx->cfg.chain == SLB_CHAIN_PASS)
+  {
+    CK (ctx, launch_copy_iq (d_in, d_out, (size_t) ctx->cfg.channels * frames, stream));
+    ctx->launches++;
+    return SLB_OK;
+  }
+  if (frames % ctx->rx.hop != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the hop (384)");
+  int rc = run_rx_kernel (ctx, d_in, d_out, 0, ctx->cfg.channels, frames, ctx->dbg_audio, ctx->dbg_gain, (cudaStream_t) stream);
+  if (rc) return rc;
+  rx_advance (ctx, frames);
+  return SLB_OK;
+}
+
+int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames)
+{
+  if (!ctx || !h_in || !h_out || frames == 0) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const bool chain = ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32;
+  if (chain && frames % ctx->rx.hop != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the hop (384)");
+  const uint32_t C = ctx->cfg.channels;
+  const size_t ch_bytes = (size_t) frames * 4;
+  // channels are independent, so the batch is cut into channel groups and H2D / kernel / D2H of consecutive groups overlap
+  uint32_t group = (uint32_t) ((size_t) (48u << 20) / ch_bytes);
+  if (group < 1) group = 1;
+  if (group > C) group = C;
+  const size_t need = (size_t) group * ch_bytes;
+  if (need > ctx->bulk_bytes)
+  {
+    for (int s = 0; s < kBulkSlots; s++)
+    {
+      if (ctx->bulk_stream[s]) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
+      CK (ctx, cudaFree (ctx->d_bulk_in[s])); CK (ctx, cudaFree (ctx->d_bulk_out[s]));
+      ctx->d_bulk_in[s] = ctx->d_bulk_out[s] = nullptr;
+      CK (ctx, cudaMalloc (&ctx->d_bulk_in[s], need)); CK (ctx, cudaMalloc (&ctx->d_bulk_out[s], need));
+      if (!ctx->bulk_stream[s]) CK (ctx, cudaStreamCreateWithFlags (&ctx->bulk_stream[s], cudaStreamNonBlocking));
+      if (!ctx->bulk_done[s]) CK (ctx, cudaEventCreateWithFlags (&ctx->bulk_done[s], cudaEventDisableTiming));
+    }
+    ctx->bulk_bytes = need;
+  }
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  int slot = 0;
+  for (uint32_t c0 = 0; c0 < C; c0 += group, slot = (slot + 1) % kBulkSlots)
+  {
+    const uint32_t n = (C - c0 < group) ? C - c0 : group;
+    cudaStream_t st = ctx->bulk_stream[slot];
+    const size_t bytes = (size_t) n * ch_bytes;
+    CK (ctx, cudaMemcpyAsync (ctx->d_bulk_in[slot], reinterpret_cast<const char *> (h_in) + (size_t) c0 * ch_bytes, bytes, cudaMemcpyHostToDevice, st));
+    if (chain)
+    {
+      int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], c0, n, frames, nullptr, nullptr, st);
+      if (rc) return rc;
+    }
+    else
+    {
+      CK (ctx, launch_copy_iq (ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], (size_t) n * frames, st));
+      ctx->launches++;
+    }
+    CK (ctx, cudaMemcpyAsync (reinterpret_cast<char *> (h_out) + (size_t) c0 * ch_bytes, ctx->d_bulk_out[slot], bytes, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kBulkSlots; s++) if (ctx->bulk_stream[s]) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
+  if (chain) rx_advance (ctx, frames);
+  return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Checkpoint: everything a later call depends on
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+struct StateHeader
+{
+  uint32_t magic, channels, fs, chain, fft_len, hop;
+  uint32_t flag_base, ovl_parity, acc_fill, proc_cur, tx_mode;
+  uint32_t ring[2][4];
+};
+constexpr uint32_t kMagic = 0x534C4232u;   // 'SLB2'
+}
+static size_t state_bytes (const slb_ctx *ctx)
+{
+  const size_t C = ctx->cfg.channels, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop, R = ctx->geo.ring_frames;
+  return sizeof (StateHeader) + C /*modes*/ + C * ovl * 4 + C * 8 * 4 + 4 * C * R * 2 + C * hop * 4 * 2;
+}
+int slb_state_size (const slb_ctx *ctx, size_t *bytes) { if (!ctx || !bytes) return SLB_ERR_ARG; *bytes = state_bytes (ctx); return SLB_OK; }
+
+int slb_state_save (slb_ctx *ctx, void *buf, size_t bytes)
+{
+  if (!ctx || !buf || bytes < state_bytes (ctx)) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  const size_t C = ctx->cfg.channels, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop, R = ctx->geo.ring_frames;
+  char *p = static_cast<char *> (buf);
+  StateHeader h{};
+  h.magic = kMagic; h.channels = (uint32_t) C; h.fs = ctx->cfg.fs; h.chain = ctx->cfg.chain; h.fft_len = ctx->rx.fft_len; h.hop = ctx->rx.hop;
+  h.flag_base = ctx->flag_base; h.ovl_parity = (uint32_t) ctx->ovl_parity; h.acc_fill = ctx->acc_fill; h.proc_cur = (uint32_t) ctx->proc_cur; h.tx_mode = ctx->tx_mode;
+  const RingPtrs *rp[2] = { &ctx->ring_in, &ctx->ring_out };
+  for (int w = 0; w < 2; w++) { h.ring[w][0] = rp[w]->size; h.ring[w][1] = rp[w]->enable; h.ring[w][2] = rp[w]->rd; h.ring[w][3] = rp[w]->wr; }
+  std::memcpy (p, &h, sizeof h); p += sizeof h;
+  std::memcpy (p, ctx->mode_host.data (), C); p += C;
+  CK (ctx, cudaMemcpy (p, ctx->d_ovl[ctx->ovl_parity], C * ovl * 4, cudaMemcpyDeviceToHost)); p += C * ovl * 4;
+  CK (ctx, cudaMemcpy (p, ctx->d_state, C * 8 * 4, cudaMemcpyDeviceToHost)); p += C * 8 * 4;
+  for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) { CK (ctx, cudaMemcpy (p, ctx->d_ring[w][k], C * R * 2, cudaMemcpyDeviceToHost)); p += C * R * 2; }
+  CK (ctx, cudaMemcpy (p, ctx->d_acc, C * hop * 4, cudaMemcpyDeviceToHost)); p += C * hop * 4;
+  CK (ctx, cudaMemcpy (p, ctx->d_proc[ctx->proc_cur], C * hop * 4, cudaMemcpyDeviceToHost));
+  return SLB_OK;
+}
+
+int slb_state_load (slb_ctx *ctx, const void *buf, size_t bytes)
+{
+  if (!ctx || !buf || bytes < state_bytes (ctx)) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const size_t C = ctx->cfg.channels, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop, R = ctx->geo.ring_frames;
+  const char *p = static_cast<const char *> (buf);
+  StateHeader h; std::memcpy (&h, p, sizeof h); p += sizeof h;
+  if (h.magic != kMagic || h.channels != C || h.fs != ctx->cfg.fs || h.chain != ctx->cfg.chain || h.fft_len != ctx->rx.fft_len || h.hop != ctx->rx.hop)
+    return fail (ctx, SLB_ERR_STATE, "checkpoint does not match this context");
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  for (size_t c = 0; c < C; c++) { ctx->mode_host[c] = (uint8_t) p[c]; int s = mode_to_mask_slot (ctx->mode_host[c]); ctx->slot_host[c] = (uint8_t) (s < 0 ? 1 : s); }
+  p += C;
+  CK (ctx, cudaMemcpy (ctx->d_slot, ctx->slot_host.data (), C, cudaMemcpyHostToDevice));
+  ctx->ovl_parity = 0; ctx->proc_cur = 0;
+  CK (ctx, cudaMemcpy (ctx->d_ovl[0], p, C * ovl * 4, cudaMemcpyHostToDevice)); p += C * ovl * 4;
+  CK (ctx, cudaMemcpy (ctx->d_state, p, C * 8 * 4, cudaMemcpyHostToDevice)); p += C * 8 * 4;
+  for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) { CK (ctx, cudaMemcpy (ctx->d_ring[w][k], p, C * R * 2, cudaMemcpyHostToDevice)); p += C * R * 2; }
+  CK (ctx, cudaMemcpy (ctx->d_acc, p, C * hop * 4, cudaMemcpyHostToDevice)); p += C * hop * 4;
+  CK (ctx, cudaMemcpy (ctx->d_proc[0], p, C * hop * 4, cudaMemcpyHostToDevice));
+  // per-channel tile counters restart from zero on this context
+  CK (ctx, cudaMemset (ctx->d_flag, 0, C * sizeof (unsigned)));
+  ctx->flag_base = 0; ctx->acc_fill = h.acc_fill; ctx->tx_mode = h.tx_mode != 0;
+  RingPtrs *rp[2] = { &ctx->ring_in, &ctx->ring_out };
+  for (int w = 0; w < 2; w++) { rp[w]->size = h.ring[w][0]; rp[w]->enable = h.ring[w][1]; rp[w]->rd = h.ring[w][2]; rp[w]->wr = h.ring[w][3]; }
+  return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Single-channel drop-in with the firmware's names (Core/Inc/dsp_if.h:42-51)
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+slb_ctx *g_dropin = nullptr;
+int g_dropin_status = SLB_OK;
+std::mutex g_dropin_mu;
+slb_ctx *dropin ()
+{
+  std::lock_guard<std::mutex> lk (g_dropin_mu);
+  if (!g_dropin)
+  {
+    slb_config cfg{};
+    cfg.channels = 1;
+    const char *fs = std::getenv ("SELENITE_B200_FS"), *dev = std::getenv ("SELENITE_B200_DEVICE"), *ch = std::getenv ("SELENITE_B200_CHAIN");
+    cfg.fs = fs ? (uint32_t) std::atoi (fs) : 48000u;
+    cfg.device = dev ? std::atoi (dev) : 0;
+    cfg.chain = (ch && std::strcmp (ch, "rx_ssb_f32") == 0) ? SLB_CHAIN_RX_SSB_F32 : SLB_CHAIN_PASS;
+    g_dropin_status = slb_create (&cfg, &g_dropin);
+    if (g_dropin_status != SLB_OK) std::fprintf (stderr, "selenite-b200: drop-in context failed: %s\n", slb_last_error (nullptr));
+  }
+  return g_dropin;
+}
+}  // namespace
+
+int slb_dropin_status (void) { return g_dropin_status; }
+slb_ctx *slb_dropin_ctx (void) { return dropin (); }
+#define DROPIN(call) do { slb_ctx *c_ = dropin (); if (c_) g_dropin_status = (call); } while (0)
+void DSP_Init (void) { DROPIN (SLB_DSP_Init (c_)); }
+void DSP_Set_RX (void) { DROPIN (SLB_DSP_Set_RX (c_)); }
+void DSP_Set_TX (void) { DROPIN (SLB_DSP_Set_TX (c_)); }
+void DSP_Set_Mode (uint8_t mode) { DROPIN (SLB_DSP_Set_Mode (c_, mode)); }
+void DSP_In_Buff_Write (uint16_t *pbuf, uint16_t size) { DROPIN (SLB_DSP_In_Buff_Write (c_, pbuf, size)); }
+void DSP_In_Buff_Read (uint8_t *pbuf, uint32_t size) { DROPIN (SLB_DSP_In_Buff_Read (c_, pbuf, size)); }
+void DSP_Out_Buff_Write (uint8_t *pbuf, uint32_t size) { DROPIN (SLB_DSP_Out_Buff_Write (c_, pbuf, size)); }
+void DSP_Out_Buff_Read (uint16_t *pbuf, uint16_t size) { DROPIN (SLB_DSP_Out_Buff_Read (c_, pbuf, size)); }
+void DSP_Out_Buff_Mute (void) { DROPIN (SLB_DSP_Out_Buff_Mute (c_)); }
+
+}  // extern "C"

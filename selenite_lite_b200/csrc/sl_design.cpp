@@ -1,0 +1,183 @@
+// Frozen default design of the RX-SSB-f32 chain. NOTHING here comes from the reference: the firmware has no filter
+// taps, no AGC constants and no demodulator (DSP_Set_Mode is empty, Core/Src/dsp_if.c:367-370).
+// The designs are closed-form and evaluated in double so that every consumer (product, oracle, tests) gets the same
+// numbers from slb_default_*().
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "sl_internal.h"
+
+namespace sl {
+
+static const double kPi = 3.14159265358979323846;
+
+// RBJ-style 2nd-order sections by bilinear transform with pre-warping; returned in the CMSIS layout
+// {b0,b1,b2,a1,a2} with the +a1,+a2 feedback sign (arm_biquad_cascade_df1_f32.c:52).
+static void biquad_lp (double fc, double q, double fs, float *c)
+{
+  double w0 = 2.0 * kPi * fc / fs, cw = std::cos (w0), al = std::sin (w0) / (2.0 * q), a0 = 1.0 + al;
+  c[0] = (float) ((1.0 - cw) / 2.0 / a0); c[1] = (float) ((1.0 - cw) / a0); c[2] = (float) ((1.0 - cw) / 2.0 / a0);
+  c[3] = (float) (2.0 * cw / a0); c[4] = (float) (-(1.0 - al) / a0);
+}
+
+int design_default_rx_f32 (uint32_t fs, slb_rx_f32_params *p)
+{
+  if (!p || (fs != 48000u && fs != 96000u && fs != 192000u)) return SLB_ERR_ARG;
+  std::memset (p, 0, sizeof *p);
+  p->fft_len = 512; p->hop = 384; p->agc_block = 48; p->n_stages = 2;
+  // 4th-order Butterworth audio low-pass at 3 kHz as two sections. (A 200 Hz high-pass section was tried first and
+  // dropped: in float32 df2T its poles at r = 0.98 amplify a 1-ulp input perturbation ~30x, which makes ANY two
+  // implementations — even the reference against its own restatement — disagree at the 1e-5 level. The mask already
+  // removes everything below 300 Hz.)
+  biquad_lp (3000.0, 0.54119610014619698, (double) fs, p->biquad);
+  biquad_lp (3000.0, 1.30656296487637653, (double) fs, p->biquad + 5);
+  p->agc_target = 0.25f;                                                 // -12 dBFS
+  p->agc_decay = (float) std::exp (-1.0 / 300.0);                        // 300 ms release at the 1 ms block cadence
+  p->agc_floor = 1.0e-4f;
+  p->agc_gmax = 100.0f;                                                  // +40 dB
+  return SLB_OK;
+}
+
+int mode_to_mask_slot (uint8_t mode)
+{
+  switch (mode)
+  {
+    case SLB_MODE_LSB: return 0; case SLB_MODE_USB: return 1; case SLB_MODE_CW: return 2; case SLB_MODE_CWR: return 3;
+    case SLB_MODE_DIG: return 4; case SLB_MODE_PKT: return 5;
+    default: return -1;                                                  // AM / FM need a different demodulator
+  }
+}
+
+static double bessel_i0 (double x)
+{
+  double s = 1.0, t = 1.0;
+  for (int k = 1; k < 64; k++) { t *= (x / (2.0 * k)) * (x / (2.0 * k)); s += t; if (t < 1e-18 * s) break; }
+  return s;
+}
+
+// 129-tap (fft_len/4 + 1) Kaiser-windowed-sinc low-pass, heterodyned to the wanted sideband, then its fft_len-point
+// DFT. Overlap-save with fft_len - hop = 128 = taps - 1 makes the FFT filter identical to that linear FIR.
+int design_default_mask (uint32_t fs, uint32_t N, uint8_t mode, float *out)
+{
+  if (!out || N < 16 || N > 4096 || (N & (N - 1))) return SLB_ERR_ARG;
+  double lo, hi;
+  switch (mode)
+  {
+    case SLB_MODE_USB: lo = 300.0; hi = 2700.0; break;
+    case SLB_MODE_LSB: lo = -2700.0; hi = -300.0; break;
+    case SLB_MODE_CW:  lo = 450.0; hi = 950.0; break;
+    case SLB_MODE_CWR: lo = -950.0; hi = -450.0; break;
+    case SLB_MODE_DIG: case SLB_MODE_PKT: lo = 300.0; hi = 3300.0; break;
+    default: return SLB_ERR_UNSUPPORTED;
+  }
+  const int taps = (int) N / 4 + 1, mid = (taps - 1) / 2;
+  const double fcut = (hi - lo) / 2.0 / (double) fs, fcen = (hi + lo) / 2.0 / (double) fs, beta = 8.0;
+  std::vector<double> hr (taps), hi_ (taps);
+  double dc = 0.0;
+  for (int n = 0; n < taps; n++)
+  {
+    double m = n - mid, x = 2.0 * fcut * m;
+    double sinc = (m == 0) ? 1.0 : std::sin (kPi * x) / (kPi * x);
+    double r = (double) m / (double) mid;
+    double w = bessel_i0 (beta * std::sqrt (1.0 - r * r)) / bessel_i0 (beta);
+    hr[n] = 2.0 * fcut * sinc * w; dc += hr[n];
+  }
+  for (int n = 0; n < taps; n++)
+  {
+    double g = hr[n] / dc;                                               // unit pass-band gain for a complex (I/Q) tone
+    double ph = 2.0 * kPi * fcen * (n - mid);
+    hr[n] = g * std::cos (ph); hi_[n] = g * std::sin (ph);
+  }
+  for (uint32_t k = 0; k < N; k++)
+  {
+    double re = 0.0, im = 0.0;
+    for (int n = 0; n < taps; n++)
+    {
+      double ph = -2.0 * kPi * (double) ((uint64_t) k * (uint64_t) n % N) / (double) N, c = std::cos (ph), s = std::sin (ph);
+      re += hr[n] * c - hi_[n] * s; im += hr[n] * s + hi_[n] * c;
+    }
+    out[2 * k] = (float) re; out[2 * k + 1] = (float) im;
+  }
+  return SLB_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// Time-parallel evaluation of the 2-stage df2T cascade (arm_biquad_cascade_df2T_f32.c:551-562 per sample):
+// with x = 0 the 4-vector s = {d1_0,d2_0,d1_1,d2_1} evolves linearly, s' = A s, and the cascade output is c.s.
+// A lane filters its run of kRun samples from a zero state; the true start state s_k of run k then adds
+// Cresp[n].s_k to sample n, and run end states chain through M = A^kRun (scan with M, M^2, M^4, ...).
+// -----------------------------------------------------------------------------------------------------------
+void design_biquad_scan_tables (const float *cf, BiquadScanTables *t)
+{
+  for (int i = 0; i < 10; i++) t->coef[i] = cf[i];
+  const double b0 = cf[5], b1 = cf[6], b2 = cf[7];
+  const double a1[2] = { cf[3], cf[8] }, a2[2] = { cf[4], cf[9] };
+  double M[4][4];
+  for (int col = 0; col < 4; col++)
+  {
+    double s[4] = { 0, 0, 0, 0 }; s[col] = 1.0;
+    for (int n = 0; n < kRun; n++)
+    {
+      double y0 = s[0];                                  // stage 0, x = 0
+      double n0 = a1[0] * y0 + s[1], n1 = a2[0] * y0;
+      double y1 = b0 * y0 + s[2];                        // stage 1, x = y0
+      double n2 = (b1 * y0 + a1[1] * y1) + s[3], n3 = b2 * y0 + a2[1] * y1;
+      t->Cresp[n][col] = (float) y1;
+      s[0] = n0; s[1] = n1; s[2] = n2; s[3] = n3;
+    }
+    for (int r = 0; r < 4; r++) M[r][col] = s[r];
+  }
+  for (int k = 0; k < 5; k++)
+  {
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) t->Mpow[k][4 * r + c] = (float) M[r][c];
+    double P[4][4];
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { double a = 0; for (int j = 0; j < 4; j++) a += M[r][j] * M[j][c]; P[r][c] = a; }
+    std::memcpy (M, P, sizeof M);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// Ring index logic — follows Core/Src/dsp_if.c line by line (cited), with the sample stores left to the kernels.
+// -----------------------------------------------------------------------------------------------------------
+uint32_t RingPtrs::plan_write (bool is_out, uint32_t frames)
+{
+  const uint32_t N = size;
+  uint32_t gap = 0;
+  if (is_out)
+  {
+    if (!enable)                                   // dsp_if.c:124-134: writer arms the TX ring half a ring ahead
+    {
+      wr = rd + N / 2; if (wr >= N) wr -= N;
+      enable = 1;
+    }
+    gap = wr; if (rd > wr) gap += N; gap -= rd;    // dsp_if.c:136-143
+  }
+  else if (enable)                                 // dsp_if.c:254-264: RX gap only once the reader armed the ring
+  {
+    gap = wr; if (rd > wr) gap += N; gap -= rd;
+  }
+  gap &= 0xFFFFu;                                  // uint16_t gap
+  if (gap > 3u * N / 4u) { if (wr < 1u) wr += N; wr--; }          // dsp_if.c:145-153 / :266-274
+  if (gap < N / 4u) { wr++; if (wr >= N) wr -= N; }               // dsp_if.c:155-163 / :276-284
+  const uint32_t first = wr;
+  // `frames` stores, the duplicate of the last frame, then one step back (dsp_if.c:165-179 / :286-300)
+  wr = (wr + frames + 1u) % N;
+  if (wr < 1u) wr += N;
+  wr--;
+  return first;
+}
+
+uint32_t RingPtrs::plan_read (bool is_out, uint32_t frames)
+{
+  const uint32_t N = size;
+  if (!is_out && !enable)                          // dsp_if.c:316-326: first read arms; overflow case RESETS TO 0
+  {
+    rd = wr + N / 2; if (rd >= N) rd = 0;
+    enable = 1;
+  }
+  const uint32_t first = rd;
+  rd = (rd + frames) % N;                          // dsp_if.c:206-217 / :328-339
+  return first;
+}
+
+}  // namespace sl

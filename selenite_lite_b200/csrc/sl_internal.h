@@ -1,0 +1,84 @@
+// Internal declarations shared by the host library and the CUDA translation units.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/selenite_b200.h"
+
+namespace sl {
+
+// ---------------------------------------------------------------------------------------------------------
+// Geometry of the firmware buffers, Core/Inc/dsp_if.h:69-85 with AUDIO_OUT_PACKET_NUM = 2 (usbd_audio.h:53).
+// ---------------------------------------------------------------------------------------------------------
+struct Geometry
+{
+  uint32_t fs;
+  uint32_t block_frames;     // DSP_BUFF_PACKET_SIZE      = fs / 1000          (48)
+  uint32_t i2s_half_hw;      // I2S_BUFF_HALF_SIZE        = 2 * fs / 1000      (96 half-words)
+  uint32_t ring_frames;      // DSP_BUFF_SIZE             = 8 * fs / 1000      (384)
+  explicit Geometry (uint32_t fs_) : fs (fs_), block_frames (fs_ / 1000u), i2s_half_hw (2u * fs_ / 1000u), ring_frames (8u * fs_ / 1000u) {}
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-side index logic of one firmware ring (DSP_Buff_TypeDef, dsp_if.h:87-94). Sample storage is on the GPU;
+// all channels of a context share one cadence, hence one set of pointers. plan_*() advance the pointers exactly
+// as Core/Src/dsp_if.c does and return where the kernel must put / fetch the frames.
+// ---------------------------------------------------------------------------------------------------------
+struct RingPtrs
+{
+  uint32_t size = 0, enable = 0, rd = 0, wr = 0;
+  void reset (uint32_t n) { size = n; enable = 0; rd = 0; wr = 0; }
+  // returns the ring index the first frame of the block is stored at; `frames`+1 slots get written (last frame twice)
+  uint32_t plan_write (bool is_out, uint32_t frames);
+  // returns the ring index the first frame is read from
+  uint32_t plan_read (bool is_out, uint32_t frames);
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Frozen default design (sl_design.cpp)
+// ---------------------------------------------------------------------------------------------------------
+int design_default_rx_f32 (uint32_t fs, slb_rx_f32_params *out);
+int design_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out);
+int mode_to_mask_slot (uint8_t mode);   // -1 when the mode has no SSB-style mask (AM, FM)
+
+// Tables the time-parallel biquad needs, derived in double from the 2-stage df2T coefficients (sl_design.cpp).
+constexpr int kRun = 48;                // samples per lane run = AGC block
+struct BiquadScanTables
+{
+  float coef[10];                       // stage 0 {b0,b1,b2,a1,a2}, stage 1 {...}
+  float Mpow[5][16];                    // (A^kRun)^(2^k), k = 0..4, row-major 4x4, state order {d1_0,d2_0,d1_1,d2_1}
+  float Cresp[kRun][4];                 // zero-input response of the cascade output at sample n of a run per unit state
+};
+void design_biquad_scan_tables (const float *coef10, BiquadScanTables *t);
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel launchers (sl_ring.cu, sl_rx_ssb_f32.cu). All return cudaError_t as int.
+// ---------------------------------------------------------------------------------------------------------
+int launch_ring_write (const int16_t *d_blocks, uint32_t block_stride_frames, int16_t *d_ring_i, int16_t *d_ring_q,
+                       uint32_t channels, uint32_t ring_frames, uint32_t wr0, uint32_t frames, void *stream);
+int launch_ring_read (int16_t *d_blocks, const int16_t *d_ring_i, const int16_t *d_ring_q, uint32_t channels,
+                      uint32_t ring_frames, uint32_t rd0, uint32_t frames, void *stream);
+int launch_copy_iq (const int16_t *d_in, int16_t *d_out, size_t n_frames_total, void *stream);
+
+struct RxF32Launch
+{
+  const int16_t *in; int16_t *out;         // [C][T][2]
+  float *audio_dbg; float *gain_dbg;       // optional taps
+  const int16_t *ovl_in; int16_t *ovl_out; // [C][ovl][2] carried raw-input tail (ping-pong between calls)
+  float *state;                            // [C][8] {d1_0,d2_0,d1_1,d2_1,env,-,-,-}
+  unsigned *flag;                          // [C] tiles completed, monotonically increasing across calls
+  unsigned *queue;                         // [1] work counter, zeroed before launch
+  const float *masks;                      // [SLB_MAX_MASKS][fft_len][2] pre-scaled by 1/fft_len
+  const uint8_t *mask_slot;                // [C]
+  const float *twiddle;                    // [fft_len][2]  W_N^k = exp(-2 pi i k / N)
+  unsigned flag_base;                      // tiles each channel had completed before this launch
+  uint32_t channels, frames;
+  float agc_target, agc_decay, agc_floor, agc_gmax;
+  const BiquadScanTables *tables;          // host pointer, copied into the kernel parameter block
+};
+int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream);
+uint32_t rx_ssb_f32_launches_per_call ();
+uint32_t rx_ssb_f32_tiles (uint32_t frames);   // tiles per channel a call of `frames` advances the per-channel flag by
+
+}  // namespace sl

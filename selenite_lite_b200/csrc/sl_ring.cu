@@ -1,0 +1,70 @@
+// Firmware ring on the GPU: DSP_Buff_TypeDef (Core/Inc/dsp_if.h:87-94) keeps i[] and q[] de-interleaved; here they
+// are [channels][ring_frames] int16 planes in HBM. The index arithmetic lives on the host (sl::RingPtrs); these
+// kernels only move samples, one thread per (channel, frame).
+#include <cuda_runtime.h>
+#include "sl_internal.h"
+
+namespace sl {
+
+// DSP_In_Buff_Write / DSP_Out_Buff_Write sample stores (dsp_if.c:286-293 / :165-172): frames 0..n-1, then the
+// last frame once more in the following slot.
+__global__ void ring_write_kernel (const int16_t *__restrict__ blocks, uint32_t block_stride_frames, int16_t *__restrict__ ring_i,
+                                   int16_t *__restrict__ ring_q, uint32_t ring_frames, uint32_t wr0, uint32_t frames)
+{
+  const uint32_t c = blockIdx.y;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > frames) return;
+  const uint32_t src = (k < frames) ? k : frames - 1u;
+  const uint32_t iq = reinterpret_cast<const uint32_t *> (blocks)[(size_t) c * block_stride_frames + src];
+  const uint32_t slot = (wr0 + k) % ring_frames;
+  ring_i[(size_t) c * ring_frames + slot] = (int16_t) (iq & 0xFFFFu);
+  ring_q[(size_t) c * ring_frames + slot] = (int16_t) (iq >> 16);
+}
+
+// DSP_In_Buff_Read / DSP_Out_Buff_Read (dsp_if.c:328-339 / :206-217): re-interleave from the ring
+__global__ void ring_read_kernel (int16_t *__restrict__ blocks, const int16_t *__restrict__ ring_i, const int16_t *__restrict__ ring_q,
+                                  uint32_t ring_frames, uint32_t rd0, uint32_t frames)
+{
+  const uint32_t c = blockIdx.y;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= frames) return;
+  const uint32_t slot = (rd0 + k) % ring_frames;
+  const uint32_t i = (uint16_t) ring_i[(size_t) c * ring_frames + slot], q = (uint16_t) ring_q[(size_t) c * ring_frames + slot];
+  reinterpret_cast<uint32_t *> (blocks)[(size_t) c * frames + k] = i | (q << 16);
+}
+
+// PASS chain, bulk path: the firmware's steady-state behaviour is the identity on int16 frames.
+__global__ void copy_iq_kernel (const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n16, const uint32_t *__restrict__ in_tail,
+                                uint32_t *__restrict__ out_tail, size_t ntail)
+{
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t k = i; k < n16; k += stride) out[k] = __ldcs (in + k);
+  for (size_t k = i; k < ntail; k += stride) out_tail[k] = in_tail[k];
+}
+
+int launch_ring_write (const int16_t *d_blocks, uint32_t stride, int16_t *ri, int16_t *rq, uint32_t channels, uint32_t ring_frames,
+                       uint32_t wr0, uint32_t frames, void *stream)
+{
+  dim3 grid ((frames + 1 + 127) / 128, channels);
+  ring_write_kernel<<<grid, 128, 0, (cudaStream_t) stream>>> (d_blocks, stride, ri, rq, ring_frames, wr0, frames);
+  return (int) cudaGetLastError ();
+}
+int launch_ring_read (int16_t *d_blocks, const int16_t *ri, const int16_t *rq, uint32_t channels, uint32_t ring_frames, uint32_t rd0,
+                      uint32_t frames, void *stream)
+{
+  dim3 grid ((frames + 127) / 128, channels);
+  ring_read_kernel<<<grid, 128, 0, (cudaStream_t) stream>>> (d_blocks, ri, rq, ring_frames, rd0, frames);
+  return (int) cudaGetLastError ();
+}
+int launch_copy_iq (const int16_t *d_in, int16_t *d_out, size_t n_frames, void *stream)
+{
+  const size_t n16 = n_frames / 4, ntail = n_frames % 4;
+  const uint32_t *tin = reinterpret_cast<const uint32_t *> (d_in) + n16 * 4;
+  uint32_t *tout = reinterpret_cast<uint32_t *> (d_out) + n16 * 4;
+  size_t want = (n16 + 255) / 256; if (want < 1) want = 1;
+  int blocks = (int) (want < 148u * 16u ? want : 148u * 16u);
+  copy_iq_kernel<<<blocks, 256, 0, (cudaStream_t) stream>>> (reinterpret_cast<const uint4 *> (d_in), reinterpret_cast<uint4 *> (d_out), n16, tin, tout, ntail);
+  return (int) cudaGetLastError ();
+}
+
+}  // namespace sl

@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference module Core/Src/dsp_if.c, batched over channels.
+
+Method names, argument order and the unit of `size` are the firmware's (Core/Inc/dsp_if.h:42-51); every method is
+one call into the C ABI (include/selenite_b200.h). numpy arrays are host buffers ([channels][size] as in the C ABI),
+torch CUDA tensors go through the device bulk path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+CHAIN_PASS, CHAIN_RX_SSB_F32 = 0, 1
+MODE_LSB, MODE_USB, MODE_CW, MODE_CWR, MODE_AM, MODE_FM, MODE_DIG, MODE_PKT = 0x00, 0x01, 0x02, 0x03, 0x04, 0x08, 0x0A, 0x0C
+
+
+class SeleniteError(RuntimeError):
+    pass
+
+
+def default_rx_f32_params(fs=48000):
+    p = _lib.RxF32Params()
+    rc = _lib.load().slb_default_rx_f32_params(fs, C.byref(p))
+    if rc:
+        raise SeleniteError("slb_default_rx_f32_params -> %d" % rc)
+    return p
+
+
+def default_mask(fs=48000, fft_len=512, mode=MODE_USB):
+    m = np.zeros(2 * fft_len, np.float32)
+    rc = _lib.load().slb_default_mask(fs, fft_len, mode, m.ctypes.data)
+    if rc:
+        raise SeleniteError("slb_default_mask -> %d" % rc)
+    return m.view(np.complex64)
+
+
+def params_to_dict(p, mask):
+    """The chain parameters as plain data (what a test hands to the oracle)."""
+    return dict(fft_len=p.fft_len, hop=p.hop, agc_block=p.agc_block,
+                biquad=np.array(p.biquad[:5 * p.n_stages], np.float32).reshape(-1, 5),
+                agc_target=p.agc_target, agc_decay=p.agc_decay, agc_floor=p.agc_floor, agc_gmax=p.agc_gmax, mask=mask)
+
+
+class DspIf:
+    """One context = one GPU's shard of channels."""
+
+    def __init__(self, channels, fs=48000, chain=CHAIN_PASS, device=0):
+        self.lib = _lib.load()
+        self.channels, self.fs, self.chain, self.device = int(channels), int(fs), int(chain), int(device)
+        cfg = _lib.Config(self.channels, self.fs, self.device, self.chain)
+        h = C.c_void_p()
+        rc = self.lib.slb_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise SeleniteError("slb_create -> %d: %s" % (rc, self.lib.slb_last_error(None).decode()))
+        self.h = h
+        self.block_frames = self.fs // 1000
+        self.ring_frames = 8 * self.block_frames
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.slb_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc, what):
+        if rc:
+            raise SeleniteError("%s -> %d: %s" % (what, rc, self.lib.slb_last_error(self.h).decode()))
+
+    # ---- firmware API (dsp_if.h:42-51) ----
+    def DSP_Init(self): self._ck(self.lib.SLB_DSP_Init(self.h), "DSP_Init")
+    def DSP_Set_RX(self): self._ck(self.lib.SLB_DSP_Set_RX(self.h), "DSP_Set_RX")
+    def DSP_Set_TX(self): self._ck(self.lib.SLB_DSP_Set_TX(self.h), "DSP_Set_TX")
+
+    def DSP_Set_Mode(self, mode, channel=None):
+        if channel is None:
+            self._ck(self.lib.SLB_DSP_Set_Mode(self.h, mode), "DSP_Set_Mode")
+        else:
+            self._ck(self.lib.SLB_DSP_Set_Mode_Channel(self.h, channel, mode), "DSP_Set_Mode_Channel")
+
+    def DSP_In_Buff_Write(self, pbuf, size=None):
+        """pbuf int16/uint16 [channels][size]; size = half-words per channel (2 per frame)."""
+        a = np.ascontiguousarray(pbuf).view(np.int16).reshape(self.channels, -1)
+        size = a.shape[1] if size is None else size
+        self._ck(self.lib.SLB_DSP_In_Buff_Write(self.h, a.ctypes.data, size), "DSP_In_Buff_Write")
+
+    def DSP_In_Buff_Read(self, size):
+        """size = bytes per channel (4 per frame). Returns int16 [channels][size/2]."""
+        out = np.zeros((self.channels, size // 2), np.int16)
+        self._ck(self.lib.SLB_DSP_In_Buff_Read(self.h, out.ctypes.data, size), "DSP_In_Buff_Read")
+        return out
+
+    def DSP_Out_Buff_Write(self, pbuf, size=None):
+        """pbuf int16 [channels][n]; size = BYTES per channel."""
+        a = np.ascontiguousarray(pbuf).view(np.int16).reshape(self.channels, -1)
+        size = a.shape[1] * 2 if size is None else size
+        self._ck(self.lib.SLB_DSP_Out_Buff_Write(self.h, a.ctypes.data, size), "DSP_Out_Buff_Write")
+
+    def DSP_Out_Buff_Read(self, size):
+        """size = half-words per channel. Returns int16 [channels][size]."""
+        out = np.zeros((self.channels, size), np.int16)
+        self._ck(self.lib.SLB_DSP_Out_Buff_Read(self.h, out.ctypes.data, size), "DSP_Out_Buff_Read")
+        return out
+
+    def DSP_Out_Buff_Mute(self): self._ck(self.lib.SLB_DSP_Out_Buff_Mute(self.h), "DSP_Out_Buff_Mute")
+
+    def ring_ptrs(self, which=0):
+        o = (C.c_uint32 * 3)()
+        self._ck(self.lib.slb_ring_get_ptrs(self.h, which, C.byref(o)), "ring_get_ptrs")
+        return tuple(o)
+
+    def ring_iq(self, which=0):
+        i = np.zeros((self.channels, self.ring_frames), np.int16); q = np.zeros_like(i)
+        self._ck(self.lib.slb_ring_get_iq(self.h, which, i.ctypes.data, q.ctypes.data), "ring_get_iq")
+        return i, q
+
+    # ---- chain parameters ----
+    def rx_params(self):
+        p = _lib.RxF32Params()
+        self._ck(self.lib.slb_get_rx_f32_params(self.h, C.byref(p)), "get_rx_f32_params")
+        return p
+
+    def set_rx_params(self, p): self._ck(self.lib.slb_set_rx_f32_params(self.h, C.byref(p)), "set_rx_f32_params")
+
+    def mask(self, mode=MODE_USB):
+        m = np.zeros(2 * self.rx_params().fft_len, np.float32)
+        self._ck(self.lib.slb_get_mask(self.h, mode, m.ctypes.data), "get_mask")
+        return m.view(np.complex64)
+
+    def set_mask(self, mode, mask):
+        m = np.ascontiguousarray(np.asarray(mask, np.complex64)).view(np.float32)
+        self._ck(self.lib.slb_set_mask(self.h, mode, m.ctypes.data), "set_mask")
+
+    def oracle_params(self, mode=MODE_USB):
+        return params_to_dict(self.rx_params(), self.mask(mode))
+
+    # ---- bulk path ----
+    def rx_process(self, x, out=None, stream=None):
+        """x: torch CUDA int16 tensor [channels][frames][2] (device path, async on `stream`/current stream) or
+        numpy int16 array of that shape (host path, synchronous). Returns `out`."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, np.int16)
+            frames = x.shape[1]
+            out = np.empty_like(x) if out is None else out
+            self._ck(self.lib.slb_rx_process_host(self.h, x.ctypes.data, out.ctypes.data, frames), "rx_process_host")
+            return out
+        import torch
+        assert x.is_cuda and x.dtype == torch.int16 and x.is_contiguous() and x.shape[0] == self.channels
+        frames = x.shape[1]
+        out = torch.empty_like(x) if out is None else out
+        s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+        self._ck(self.lib.slb_rx_process_device(self.h, x.data_ptr(), out.data_ptr(), frames, s), "rx_process_device")
+        return out
+
+    def rx_process_pinned(self, x_pinned, out_pinned):
+        """torch pinned host tensors [channels][frames][2]; chunked H2D / kernel / D2H overlap inside the library."""
+        frames = x_pinned.shape[1]
+        self._ck(self.lib.slb_rx_process_host(self.h, x_pinned.data_ptr(), out_pinned.data_ptr(), frames), "rx_process_host")
+        return out_pinned
+
+    def set_debug_taps(self, audio=None, gain=None):
+        self._keep_taps = (audio, gain)
+        self._ck(self.lib.slb_rx_set_debug_taps(self.h, audio.data_ptr() if audio is not None else None,
+                                                gain.data_ptr() if gain is not None else None), "set_debug_taps")
+
+    # ---- checkpoint ----
+    def state_save(self):
+        n = C.c_size_t()
+        self._ck(self.lib.slb_state_size(self.h, C.byref(n)), "state_size")
+        buf = np.zeros(n.value, np.uint8)
+        self._ck(self.lib.slb_state_save(self.h, buf.ctypes.data, n.value), "state_save")
+        return buf
+
+    def state_load(self, buf):
+        buf = np.ascontiguousarray(buf, np.uint8)
+        self._ck(self.lib.slb_state_load(self.h, buf.ctypes.data, buf.size), "state_load")
+
+    def kernel_launches(self): return int(self.lib.slb_kernel_launches(self.h))
+    def sync(self): self._ck(self.lib.slb_sync(self.h), "sync")

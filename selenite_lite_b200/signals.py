@@ -1,0 +1,25 @@
+"""Synthetic inputs frozen by SURVEY.md §8(d): complex tone + complex white Gaussian noise, int16 I/Q."""
+import numpy as np
+
+SEED = 0x5E1E217E
+
+
+def channel_tone_hz(c):
+    """Config 2/5 tone placement: f0 = 300 + 2400 * ((c * 2654435761 mod 2^32) / 2^32) Hz."""
+    return 300.0 + 2400.0 * (((int(c) * 2654435761) % (1 << 32)) / float(1 << 32))
+
+
+def synth_iq(channels, frames, fs=48000, f0=None, amp=0.25, sigma=0.01, seed=SEED, sideband=+1, first_channel=0):
+    """int16[channels][frames][2]. Channel c uses PCG64(seed + c); config 1 is channels=1, f0=1000."""
+    out = np.empty((channels, frames, 2), np.int16)
+    n = np.arange(frames, dtype=np.float64)
+    for k in range(channels):
+        c = first_channel + k
+        rng = np.random.Generator(np.random.PCG64(seed + c))
+        f = channel_tone_hz(c) if f0 is None else float(f0)
+        ph = 2.0 * np.pi * sideband * f * n / fs
+        i = amp * np.cos(ph) + sigma * rng.standard_normal(frames)
+        q = amp * np.sin(ph) + sigma * rng.standard_normal(frames)
+        out[k, :, 0] = np.clip(np.rint(i * 32768.0), -32768, 32767).astype(np.int16)
+        out[k, :, 1] = np.clip(np.rint(q * 32768.0), -32768, 32767).astype(np.int16)
+    return out

@@ -1,0 +1,79 @@
+"""Generates tests/golden/*.npz by RUNNING THE REFERENCE here (oracle/_ref = /root/reference's CMSIS-DSP V1.5.3 and
+dsp_if.c compiled for x86). The reference owns no golden vectors, so these are its outputs on frozen
+seeded inputs. Re-run only in a container where /root/reference is mounted:  python tests/golden/make_golden.py
+Chain parameters come from the product's frozen default design (pure data: slb_default_*), inputs from
+selenite_lite_b200.signals."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE)); sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import oracle_lib  # noqa: E402
+import selenite_lite_b200 as slb  # noqa: E402
+from selenite_lite_b200.dsp_if import params_to_dict  # noqa: E402
+
+
+def main():
+    oracle_lib.build_oracles()
+    ref = oracle_lib.Oracle("ref")
+    rng = np.random.Generator(np.random.PCG64(slb.signals.SEED))
+
+    # ---- RX-SSB-f32, config-1 style: one channel, tone +1000 Hz + noise, 20 hops; and an LSB tone at -1700 Hz
+    p = slb.default_rx_f32_params(48000)
+    out = {}
+    for name, mode, f0, sb in (("usb", slb.MODE_USB, 1000.0, +1), ("lsb", slb.MODE_LSB, 1700.0, -1)):
+        mask = slb.default_mask(48000, p.fft_len, mode)
+        x = slb.synth_iq(1, 20 * 384, f0=f0, sideband=sb)[0]
+        y, audio, gain, _ = ref.rx_ssb_f32(params_to_dict(p, mask), x)
+        out["rx_%s_in" % name] = x; out["rx_%s_out" % name] = y; out["rx_%s_audio" % name] = audio; out["rx_%s_gain" % name] = gain
+        out["rx_%s_mask" % name] = mask
+    out["rx_biquad"] = np.array(p.biquad[:10], np.float32)
+    out["rx_agc"] = np.array([p.agc_target, p.agc_decay, p.agc_floor, p.agc_gmax], np.float32)
+    np.savez_compressed(os.path.join(HERE, "rx_ssb_f32.npz"), **out)
+
+    # ---- the firmware ring (unmodified dsp_if.c): ramp through In_Buff_Write/In_Buff_Read and Out_Buff_Write/Out_Buff_Read
+    ring = {}
+    for fs in (48000, 96000):
+        r = oracle_lib.RefRing(fs)
+        nb = 40; hw = r.half_hw
+        ramp = (np.arange(nb * hw // 2, dtype=np.int64) % 30000).astype(np.int16)
+        blocks = np.stack([ramp, -ramp], 1).reshape(nb, hw)            # I = n, Q = -n
+        rx_out, tx_out, ptrs = [], [], []
+        for b in range(nb):
+            r.in_write(blocks[b]); rx_out.append(r.in_read(hw * 2))
+            r.out_write(blocks[b]); tx_out.append(r.out_read(hw))
+            ptrs.append(r.ptrs(0) + r.ptrs(1))
+        ring["in_%d" % fs] = blocks; ring["rx_%d" % fs] = np.stack(rx_out); ring["tx_%d" % fs] = np.stack(tx_out)
+        ring["ptrs_%d" % fs] = np.array(ptrs, np.uint32)
+    np.savez_compressed(os.path.join(HERE, "ring.npz"), **ring)
+
+    # ---- stage known-answer vectors (integer stages: bit-exact pins)
+    st = {}
+    x15 = rng.integers(-32768, 32768, 48 * 6).astype(np.int16)
+    c15 = rng.integers(-6000, 6000, 64).astype(np.int16)
+    st["q15_x"] = x15; st["q15_c"] = c15
+    st["fir_q15"] = ref.fir_q15(c15, np.zeros(64 + 48, np.int16), x15, 48)[0]
+    st["fir_fast_q15"] = ref.fir_fast_q15(c15, np.zeros(64 + 48, np.int16), x15, 48)[0]
+    bq15 = np.array([8000, 0, -16000, 8000, 15000, -7000, 4000, 0, 8000, 4000, 9000, -3000], np.int16)
+    st["bq15_c"] = bq15
+    st["biquad_df1_q15"] = ref.biquad_df1_q15(bq15, 2, 1, np.zeros(8, np.int16), x15, 48)[0]
+    st["scale_q15"] = ref.scale_q15(x15, 23170, 1)
+    st["cmplx_mag_q15"] = ref.cmplx_mag_q15(x15)
+    xf = (rng.standard_normal(48 * 6) * 0.4).astype(np.float32)
+    st["f32_x"] = xf
+    st["float_to_q15"] = ref.float_to_q15(xf * 3)
+    st["cfft_f32_512"] = ref.cfft_f32(rng.standard_normal(1024).astype(np.float32))
+    st["cfft_in_512"] = np.random.Generator(np.random.PCG64(slb.signals.SEED)).standard_normal(1)  # placeholder, replaced below
+    z = np.random.Generator(np.random.PCG64(7)).standard_normal(1024).astype(np.float32)
+    st["cfft_in_512"] = z; st["cfft_f32_512"] = ref.cfft_f32(z); st["icfft_f32_512"] = ref.cfft_f32(z, 1, 1)
+    cbq = np.array(p.biquad[:10], np.float32)
+    st["biquad_df2T_f32"] = ref.biquad_df2T_f32(cbq, 2, np.zeros(4, np.float32), xf, 48)[0]
+    np.savez_compressed(os.path.join(HERE, "stages.npz"), **st)
+    for f in ("rx_ssb_f32.npz", "ring.npz", "stages.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol include/selenite_b200.h
+declares, and refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import selenite_lite_b200 as slb
+from selenite_lite_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "selenite_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", src)
+    return sorted(set(n for n in names if n not in ("defined",)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), "declared in include/selenite_b200.h but not exported: " + n
+    # and the Python binding table covers the header, so a signature drift is caught here
+    assert set(names) == set(_lib.SYMBOLS), set(names) ^ set(_lib.SYMBOLS)
+
+
+def test_firmware_names_present():
+    lib = _lib.load()
+    for n in ("DSP_Init", "DSP_Set_RX", "DSP_Set_TX", "DSP_Set_Mode", "DSP_In_Buff_Write", "DSP_In_Buff_Read",
+              "DSP_Out_Buff_Write", "DSP_Out_Buff_Read", "DSP_Out_Buff_Mute"):        # Core/Inc/dsp_if.h:42-51
+        assert hasattr(lib, n) and hasattr(lib, "SLB_" + n)
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(slb.SeleniteError, match="no CPU fallback"):
+        slb.DspIf(4, chain=slb.CHAIN_RX_SSB_F32)
+
+
+def test_bad_config_rejected():
+    lib = _lib.load()
+    h = C.c_void_p()
+    for cfg in (_lib.Config(0, 48000, 0, 0), _lib.Config(4, 44100, 0, 0), _lib.Config(4, 48000, 0, 9)):
+        assert lib.slb_create(C.byref(cfg), C.byref(h)) == -1
+        assert not h.value
+
+
+def test_product_never_touches_oracle():
+    """Parity claims are void if the shipped path can reach the checker (or the reference tree)."""
+    pk = os.path.join(ROOT, "selenite_lite_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle_lib" not in text and "libslo_" not in text and "oracle/" not in text.replace("oracle/_ref", "").replace("the oracle", ""), f
+                assert "/root/reference" not in text or f in ("sl_rx_ssb_f32.cu", "__init__.py", "dsp_if.py"), f
+
+
+def test_default_design_is_sane():
+    p = slb.default_rx_f32_params(48000)
+    assert (p.fft_len, p.hop, p.agc_block, p.n_stages) == (512, 384, 48, 2)
+    import numpy as np
+    usb = slb.default_mask(48000, 512, slb.MODE_USB); lsb = slb.default_mask(48000, 512, slb.MODE_LSB)
+    f = np.fft.fftfreq(512, 1 / 48000.0)
+    assert abs(abs(usb[np.argmin(abs(f - 1500))]) - 1.0) < 1e-3          # unit pass-band gain
+    assert abs(usb[np.argmin(abs(f + 4000))]) < 1e-3                     # other sideband rejected
+    assert np.allclose(abs(lsb), abs(usb[(-np.arange(512)) % 512]), atol=1e-6)   # mirror image
+    # time response is 129 taps: overlap-save with 128 carried frames is exact linear filtering
+    h = np.fft.ifft(usb.astype(np.complex128))
+    assert np.max(abs(h[129:])) < 1e-6

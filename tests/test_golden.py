@@ -1,0 +1,65 @@
+"""Oracle vs the committed golden vectors (outputs of the reference itself, tests/golden/make_golden.py).
+Runs on the CPU; on a box without /root/reference this is what pins the port."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rx_params(g, name):
+    return dict(fft_len=512, hop=384, agc_block=48, biquad=g["rx_biquad"].reshape(2, 5), agc_target=g["rx_agc"][0],
+                agc_decay=g["rx_agc"][1], agc_floor=g["rx_agc"][2], agc_gmax=g["rx_agc"][3], mask=g["rx_%s_mask" % name])
+
+
+def audio_tolerance(ref_audio, block=48):
+    """1e-5 relative per sample, made well-defined at zero crossings: 1e-5 * max(|ref|, block rms)."""
+    r = ref_audio.astype(np.float64).reshape(-1, block)
+    rms = np.sqrt(np.mean(r ** 2, axis=1, keepdims=True))
+    return (1e-5 * np.maximum(np.abs(r), rms)).reshape(-1)
+
+
+@pytest.mark.parametrize("name", ["usb", "lsb"])
+def test_port_chain_vs_golden(port, name):
+    g = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))
+    out, audio, gain, _ = port.rx_ssb_f32(rx_params(g, name), g["rx_%s_in" % name])
+    assert np.all(np.abs(audio - g["rx_%s_audio" % name]) <= audio_tolerance(g["rx_%s_audio" % name]) + 1e-9)
+    assert np.allclose(gain, g["rx_%s_gain" % name], rtol=1e-5)
+    d = np.abs(out.astype(np.int32) - g["rx_%s_out" % name].astype(np.int32))
+    assert d.max() <= 1 and np.mean(d > 0) < 0.02           # a 1e-7 float difference can flip the truncating pack by one LSB
+
+
+@pytest.mark.parametrize("name", ["usb", "lsb"])
+def test_ref_chain_reproduces_golden(ref, name):
+    g = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))
+    out, audio, gain, _ = ref.rx_ssb_f32(rx_params(g, name), g["rx_%s_in" % name])
+    assert np.array_equal(out, g["rx_%s_out" % name]) and np.array_equal(audio, g["rx_%s_audio" % name])
+
+
+def test_chain_blocking_independence(port):
+    """Carried state: 20 hops in one call == 20 calls of one hop (the firmware cadence accumulates 8 x 48 frames)."""
+    g = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))
+    prm = rx_params(g, "usb"); x = g["rx_usb_in"]
+    whole, _, _, _ = port.rx_ssb_f32(prm, x)
+    st = None; parts = []
+    for h in range(20):
+        o, _, _, st = port.rx_ssb_f32(prm, x[384 * h:384 * (h + 1)], st)
+        parts.append(o)
+    assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_port_stages_vs_golden(port):
+    s = np.load(os.path.join(GOLD, "stages.npz"))
+    x, c = s["q15_x"], s["q15_c"]
+    assert np.array_equal(port.fir_q15(c, np.zeros(112, np.int16), x, 48)[0], s["fir_q15"])
+    assert np.array_equal(port.fir_fast_q15(c, np.zeros(112, np.int16), x, 48)[0], s["fir_fast_q15"])
+    assert np.array_equal(port.biquad_df1_q15(s["bq15_c"], 2, 1, np.zeros(8, np.int16), x, 48)[0], s["biquad_df1_q15"])
+    assert np.array_equal(port.scale_q15(x, 23170, 1), s["scale_q15"])
+    assert np.array_equal(port.cmplx_mag_q15(x), s["cmplx_mag_q15"])
+    assert np.array_equal(port.float_to_q15(s["f32_x"] * 3), s["float_to_q15"])
+    rms = np.sqrt(np.mean(s["cfft_f32_512"].astype(np.float64) ** 2))
+    assert np.max(np.abs(port.cfft_f32(s["cfft_in_512"]) - s["cfft_f32_512"])) < 2e-6 * rms
+    assert np.max(np.abs(port.cfft_f32(s["cfft_in_512"], 1, 1) - s["icfft_f32_512"])) < 2e-6 * rms / 512 * 30
+    bq = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))["rx_biquad"]
+    assert np.array_equal(port.biquad_df2T_f32(bq, 2, np.zeros(4, np.float32), s["f32_x"], 48)[0], s["biquad_df2T_f32"])
