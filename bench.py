@@ -164,7 +164,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    C, T = CHANNELS_PER_GPU, FRAMES
+    C, T = CHANNELS_PER_GPU, FS * args.seconds
     d = slb.DspIf(C, fs=FS, chain=slb.CHAIN_RX_SSB_F32, device=local)
     x = synth_on_gpu(torch, C, T, dev, first_channel=rank * C)
     y = torch.empty_like(x)
@@ -258,6 +258,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--seconds", type=int, default=SECONDS, help="signal seconds per channel per step (profiling runs only; the headline uses the default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -252,7 +252,14 @@ class RefRing:
         path = os.path.join(ORACLE_DIR, "_ref", "libdspif_%d.so" % fs)
         if not os.path.exists(path):
             raise FileNotFoundError(path)
-        self.lib = C.CDLL(path)
+        # dsp_if.c keeps its rings in file-scope globals (dsp_if.c:32-35): one loaded image = one channel. Each RefRing
+        # therefore loads its own private copy of the library.
+        import shutil
+        import tempfile
+        tmp = tempfile.NamedTemporaryFile(prefix="dspif_", suffix=".so", delete=False)
+        tmp.close(); shutil.copyfile(path, tmp.name)
+        self.lib = C.CDLL(tmp.name)
+        os.unlink(tmp.name)
         L = self.lib
         for n in ("refring_fs", "refring_i2s_buff_size", "refring_i2s_half_size", "refring_dsp_buff_size", "refring_dsp_half_size"):
             getattr(L, n).restype = u32
