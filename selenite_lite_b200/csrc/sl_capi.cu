@@ -37,7 +37,7 @@ struct slb_ctx
   // device: chain constants + carried state
   float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
   int16_t *d_ovl[2] = { nullptr, nullptr }; int ovl_parity = 0;
-  float *d_state = nullptr; unsigned *d_flag = nullptr; unsigned *d_queue = nullptr; int queue_rr = 0;
+  float *d_state = nullptr; unsigned *d_flag = nullptr;
   unsigned flag_base = 0;
   float *dbg_audio = nullptr, *dbg_gain = nullptr;
 
@@ -68,8 +68,11 @@ static int upload_chain_constants (slb_ctx *ctx)
 {
   const uint32_t N = ctx->rx.fft_len;
   std::vector<float> scaled (ctx->masks_host.size ());
-  const float inv = 1.0f / (float) N;                      // arm_cfft_f32.c:604-614 scales by 1/L after the transform;
-  for (size_t i = 0; i < scaled.size (); i++) scaled[i] = ctx->masks_host[i] * inv;   // power of two: exact either way
+  // arm_cfft_f32.c:604-614 scales by 1/L after the inverse transform and arm_q15_to_float.c:87 by 1/32768 before the
+  // forward one; both are powers of two, so folding them into the mask changes no bit of the result
+  const float inv = 1.0f / ((float) N * 32768.0f);
+  for (int m = 0; m < SLB_MAX_MASKS; m++)
+    rx_ssb_f32_pack_mask (ctx->masks_host.data () + (size_t) m * 2 * N, inv, scaled.data () + (size_t) m * 2 * N);
   CK (ctx, cudaMemcpyAsync (ctx->d_masks, scaled.data (), scaled.size () * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
   CK (ctx, cudaMemcpyAsync (ctx->d_slot, ctx->slot_host.data (), ctx->slot_host.size (), cudaMemcpyHostToDevice, ctx->stream));
   CK (ctx, cudaStreamSynchronize (ctx->stream));
@@ -132,23 +135,18 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   CKC (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
   CKC (cudaMalloc (&ctx->d_masks, (size_t) SLB_MAX_MASKS * 2 * N * sizeof (float)));
   CKC (cudaMalloc (&ctx->d_slot, C));
-  CKC (cudaMalloc (&ctx->d_twiddle, (size_t) 2 * N * sizeof (float)));
+  CKC (cudaMalloc (&ctx->d_twiddle, kTwiddleFloats * sizeof (float)));
   for (int p = 0; p < 2; p++) CKC (cudaMalloc (&ctx->d_ovl[p], (size_t) C * ovl * 4));
   CKC (cudaMalloc (&ctx->d_state, (size_t) C * 8 * sizeof (float)));
   CKC (cudaMalloc (&ctx->d_flag, (size_t) C * sizeof (unsigned)));
-  CKC (cudaMalloc (&ctx->d_queue, 64 * sizeof (unsigned)));
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) CKC (cudaMalloc (&ctx->d_ring[w][k], (size_t) C * R * 2));
   ctx->blk_frames = R;
   CKC (cudaMalloc (&ctx->d_blk, (size_t) C * ctx->blk_frames * 4));
   CKC (cudaMalloc (&ctx->d_acc, (size_t) C * hop * 4));
   for (int p = 0; p < 2; p++) CKC (cudaMalloc (&ctx->d_proc[p], (size_t) C * hop * 4));
   {
-    std::vector<float> tw (2 * N);
-    for (uint32_t k = 0; k < N; k++)
-    {
-      const double a = -2.0 * 3.14159265358979323846 * (double) k / (double) N;
-      tw[2 * k] = (float) std::cos (a); tw[2 * k + 1] = (float) std::sin (a);
-    }
+    std::vector<float> tw (kTwiddleFloats);
+    rx_ssb_f32_pack_twiddles (tw.data ());
     CKC (cudaMemcpy (ctx->d_twiddle, tw.data (), tw.size () * sizeof (float), cudaMemcpyHostToDevice));
   }
 #undef CKC
@@ -166,7 +164,7 @@ void slb_destroy (slb_ctx *ctx)
   cudaDeviceSynchronize ();
   cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
-  cudaFree (ctx->d_state); cudaFree (ctx->d_flag); cudaFree (ctx->d_queue);
+  cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
   cudaFree (ctx->d_blk); cudaFree (ctx->d_acc);
   for (int s = 0; s < kBulkSlots; s++)
@@ -270,7 +268,6 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
   L.in = d_in; L.out = d_out; L.audio_dbg = dbg_audio; L.gain_dbg = dbg_gain;
   L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
   L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
-  L.queue = ctx->d_queue + (ctx->queue_rr++ % 64);
   L.masks = ctx->d_masks; L.mask_slot = ctx->d_slot + ch0; L.twiddle = ctx->d_twiddle;
   L.flag_base = ctx->flag_base; L.channels = nch; L.frames = frames;
   L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;

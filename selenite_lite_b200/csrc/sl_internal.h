@@ -68,10 +68,9 @@ struct RxF32Launch
   const int16_t *ovl_in; int16_t *ovl_out; // [C][ovl][2] carried raw-input tail (ping-pong between calls)
   float *state;                            // [C][8] {d1_0,d2_0,d1_1,d2_1,env,-,-,-}
   unsigned *flag;                          // [C] tiles completed, monotonically increasing across calls
-  unsigned *queue;                         // [1] work counter, zeroed before launch
-  const float *masks;                      // [SLB_MAX_MASKS][fft_len][2] pre-scaled by 1/fft_len
+  const float *masks;                      // [SLB_MAX_MASKS][2*fft_len] in the kernel's packed layout (rx_ssb_f32_pack_mask)
   const uint8_t *mask_slot;                // [C]
-  const float *twiddle;                    // [fft_len][2]  W_N^k = exp(-2 pi i k / N)
+  const float *twiddle;                    // kTwiddleFloats, packed per lane (rx_ssb_f32_pack_twiddles)
   unsigned flag_base;                      // tiles each channel had completed before this launch
   uint32_t channels, frames;
   float agc_target, agc_decay, agc_floor, agc_gmax;
@@ -79,6 +78,9 @@ struct RxF32Launch
 };
 int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream);
 uint32_t rx_ssb_f32_launches_per_call ();
-uint32_t rx_ssb_f32_tiles (uint32_t frames);   // tiles per channel a call of `frames` advances the per-channel flag by
+uint32_t rx_ssb_f32_tiles (uint32_t frames);   // how far a call of `frames` advances the per-channel hand-over flag
+void rx_ssb_f32_pack_twiddles (float *out /* kTwiddleFloats */);
+void rx_ssb_f32_pack_mask (const float *mask_re_im, float scale, float *out /* 2 * fft_len floats */);
+constexpr size_t kTwiddleFloats = 14 * 32 * 4;
 
 }  // namespace sl

@@ -8,11 +8,22 @@
 //     pack     SupportFunctions/arm_float_to_q15.c:64 (truncating)
 //   and it sits where the firmware would call it: between pbuf and the ring store in DSP_In_Buff_Write (Core/Src/dsp_if.c:286-289).
 //
-// Work decomposition: a work item is (channel, tile of 4 hops = 1536 frames). Persistent CTAs pull
-// items from an atomic queue ordered tile-major, so the only cross-tile dependency — 5 floats of biquad/AGC state per
-// channel — is almost always already published when a CTA reaches the recurrence phase; it is handed over through
-// global memory with a release/acquire flag per channel. The FFT phases never wait.
+// Structure. The chain is bound by the FP32 pipe, not by HBM (~130 FP32 lane-ops per complex sample
+// for two 512-point FFTs per 384 samples), so the kernel is organised around instruction count and issue slots:
+//   * warp-specialised CTA of 5 warps. Warps 0..3 each own one overlap-save frame of a 4-frame tile: load, unpack,
+//     forward FFT, mask, inverse FFT — entirely warp-local (private shared-memory scratch, __syncwarp only, no CTA
+//     barrier). Warp 4 runs the time recurrences (biquad cascade, AGC) of the PREVIOUS tile, packs and stores it.
+//     The two sides meet through a double-buffered audio tile in shared memory and four named barriers.
+//   * every FFT lane carries TWO radix-8 butterflies and evaluates them together with packed FP32x2 instructions
+//     (FADD2 / FMUL2 / FFMA2, new on sm_100): half the FP32 issue slots of scalar code.
+//   * the biquad recurrence is evaluated time-parallel: lane k filters its own 48-sample run from a zero state, run end
+//     states are chained with a 5-step warp scan over 4x4 transition matrices, and the true start state is added back
+//     through the cascade's zero-input response (tables from sl_design.cpp).
+//   * a CTA owns (channel, segment of 8 tiles); segments of one channel are chained through 5 floats in global memory
+//     with a release/acquire flag. Items are dealt round-robin in segment-major order, so the flag is already set
+//     whenever at least as many channels as resident CTAs are in flight.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <cstdint>
 #include "sl_internal.h"
 
@@ -20,72 +31,75 @@ namespace sl {
 
 namespace {
 
-constexpr int kN = 512;               // FFT length
-constexpr int kHop = 384;             // new frames per FFT frame
-constexpr int kOvl = kN - kHop;       // 128 carried frames
-constexpr int kHopsPerTile = 4;
-constexpr int kTile = kHop * kHopsPerTile;      // 1536 frames
-constexpr int kThreads = 256;                   // 64 threads per FFT frame, radix-8
-constexpr int kRunsPerTile = kTile / kRun;      // 32 lanes x 48 samples in the recurrence phase
-constexpr int kRunPad = kRun + 1;               // 49: lane stride in shared memory, conflict-free
-constexpr int kFramePad = kN + kN / 8;          // 576: phys(i) = i + (i >> 3)
+constexpr int kN = 512;                          // FFT length
+constexpr int kHop = 384;                        // new frames per FFT frame
+constexpr int kOvl = kN - kHop;                  // 128 carried frames
+constexpr int kFftWarps = 4;                     // = frames per tile
+constexpr int kTile = kHop * kFftWarps;          // 1536 frames
+constexpr int kThreads = 32 * (kFftWarps + 1);   // + the recurrence warp
+constexpr int kRunsPerTile = kTile / kRun;       // 32 lanes x 48 samples
+constexpr int kRunPad = kRun + 1;                // lane stride 49 words: conflict-free both ways
+constexpr int kTilesPerItem = 8;                 // tiles a CTA processes with the recurrence state in registers
+constexpr int kPlane = 544;                      // floats per re / im scratch plane: phys(511) + 1 = 542, rounded up
+
+// shared-memory index of FFT point i inside a plane: pairs (2k, 2k+1) stay adjacent and 8-byte aligned; gathers are
+// conflict-free, the pass-0 and pass-1 scatters are 2-way (best of the family searched)
+__device__ __forceinline__ int phys (int i) { return i + 2 * (i >> 5); }
+
+// ---- packed FP32x2: one 64-bit register pair holds the same quantity for butterfly A (lo) and butterfly B (hi) ----
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk (float lo, float hi) { u64 r; asm ("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo_of (u64 a) { float x, y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return x; }
+__device__ __forceinline__ float hi_of (u64 a) { float x, y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return y; }
+__device__ __forceinline__ u64 add2 (u64 a, u64 b) { u64 r; asm ("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2 (u64 a, u64 b) { u64 r; asm ("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2 (u64 a, u64 b) { u64 r; asm ("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2 (u64 a, u64 b, u64 c) { u64 r; asm ("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// 8-point forward DFT of two butterflies at once, natural order in and out; re[] / im[] are packed (A,B).
+// 52 packed instructions (26 per butterfly): the W8 rotations are folded into FMAs with +-1/sqrt2.
+__device__ __forceinline__ void dft8x2 (u64 *re, u64 *im)
+{
+  const u64 H = pk (0.70710678118654752f, 0.70710678118654752f), NH = pk (-0.70710678118654752f, -0.70710678118654752f);
+  const u64 a0r = add2 (re[0], re[4]), a0i = add2 (im[0], im[4]), t0r = sub2 (re[0], re[4]), t0i = sub2 (im[0], im[4]);
+  const u64 a1r = add2 (re[1], re[5]), a1i = add2 (im[1], im[5]), t1r = sub2 (re[1], re[5]), t1i = sub2 (im[1], im[5]);
+  const u64 a2r = add2 (re[2], re[6]), a2i = add2 (im[2], im[6]), t2r = sub2 (re[2], re[6]), t2i = sub2 (im[2], im[6]);
+  const u64 a3r = add2 (re[3], re[7]), a3i = add2 (im[3], im[7]), t3r = sub2 (re[3], re[7]), t3i = sub2 (im[3], im[7]);
+  // even outputs: DFT4 of a
+  {
+    const u64 s0r = add2 (a0r, a2r), s0i = add2 (a0i, a2i), s1r = sub2 (a0r, a2r), s1i = sub2 (a0i, a2i);
+    const u64 s2r = add2 (a1r, a3r), s2i = add2 (a1i, a3i), dr = sub2 (a1r, a3r), di = sub2 (a1i, a3i);
+    re[0] = add2 (s0r, s2r); im[0] = add2 (s0i, s2i);
+    re[4] = sub2 (s0r, s2r); im[4] = sub2 (s0i, s2i);
+    re[2] = add2 (s1r, di); im[2] = sub2 (s1i, dr);        // s1 + (-i) d
+    re[6] = sub2 (s1r, di); im[6] = add2 (s1i, dr);        // s1 - (-i) d
+  }
+  // odd outputs: DFT4 of b, b0 = t0, b1 = t1 W8, b2 = -i t2, b3 = t3 W8^3
+  {
+    const u64 s0r = add2 (t0r, t2i), s0i = sub2 (t0i, t2r), s1r = sub2 (t0r, t2i), s1i = add2 (t0i, t2r);
+    const u64 p = add2 (t1r, t1i), q = sub2 (t1i, t1r), u = sub2 (t3i, t3r), v = add2 (t3r, t3i);
+    const u64 pu = add2 (p, u), qv = sub2 (q, v), pmu = sub2 (p, u), qpv = add2 (q, v);   // s2 = h (pu, qv), d = h (pmu, qpv)
+    re[1] = fma2 (H, pu, s0r); im[1] = fma2 (H, qv, s0i);
+    re[5] = fma2 (NH, pu, s0r); im[5] = fma2 (NH, qv, s0i);
+    re[3] = fma2 (H, qpv, s1r); im[3] = fma2 (NH, pmu, s1i);
+    re[7] = fma2 (NH, qpv, s1r); im[7] = fma2 (H, pmu, s1i);
+  }
+}
 
 struct KParams
 {
   const uint32_t *in; uint32_t *out;            // one u32 = one I/Q (or L/R) frame
   float *audio_dbg; float *gain_dbg;
   const uint32_t *ovl_in; uint32_t *ovl_out;
-  float *state; unsigned *flag; unsigned *queue;
-  const float2 *masks; const uint8_t *mask_slot; const float2 *twiddle;
+  float *state; unsigned *flag;
+  const float4 *masks;                          // [slot][r][lane] = (HrA, HrB, HiA, HiB) * 1/(512*32768)
+  const uint8_t *mask_slot;
+  const float4 *twiddle;                        // [pass 1|2][r-1][lane] = (WrA, WrB, WiA, WiB)
   unsigned flag_base;
-  uint32_t channels, frames, tiles_per_channel;
+  uint32_t channels, frames, tiles_per_channel, items_per_channel;
   float agc_target, agc_decay, agc_floor, agc_gmax;
   BiquadScanTables tab;
 };
-
-__device__ __forceinline__ int phys (int i) { return i + (i >> 3); }
-
-__device__ __forceinline__ float2 cmul (float2 a, float2 b) { return make_float2 (a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-__device__ __forceinline__ float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 mul_mi (float2 a) { return make_float2 (a.y, -a.x); }      // a * (-i)
-
-// 4-point forward DFT, natural order in and out
-__device__ __forceinline__ void dft4 (float2 &u0, float2 &u1, float2 &u2, float2 &u3)
-{
-  float2 s0 = cadd (u0, u2), s1 = csub (u0, u2), s2 = cadd (u1, u3), s3 = mul_mi (csub (u1, u3));
-  u0 = cadd (s0, s2); u2 = csub (s0, s2); u1 = cadd (s1, s3); u3 = csub (s1, s3);
-}
-
-// 8-point forward DFT, natural order in and out (decimation in frequency, outputs renamed at compile time)
-__device__ __forceinline__ void dft8 (float2 *v)
-{
-  const float h = 0.70710678118654752f;
-  float2 a0 = cadd (v[0], v[4]), a1 = cadd (v[1], v[5]), a2 = cadd (v[2], v[6]), a3 = cadd (v[3], v[7]);
-  float2 b0 = csub (v[0], v[4]), t1 = csub (v[1], v[5]), t2 = csub (v[2], v[6]), t3 = csub (v[3], v[7]);
-  float2 b1 = make_float2 ((t1.x + t1.y) * h, (t1.y - t1.x) * h);       // * W8^1 = (1 - i)/sqrt2
-  float2 b2 = mul_mi (t2);                                              // * W8^2 = -i
-  float2 b3 = make_float2 ((t3.y - t3.x) * h, -(t3.x + t3.y) * h);      // * W8^3 = (-1 - i)/sqrt2
-  dft4 (a0, a1, a2, a3);
-  dft4 (b0, b1, b2, b3);
-  v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
-  v[1] = b0; v[3] = b1; v[5] = b2; v[7] = b3;
-}
-
-// One Stockham radix-8 pass for the 64 threads of a frame: v[] already holds x[j + 64 r] (twiddled by the caller's
-// choice); scatter to idxD + r*Ns with idxD = (j / Ns) * Ns * 8 + (j % Ns).
-template <int Ns>
-__device__ __forceinline__ void twiddle8 (float2 *v, int j, const float2 *tw)
-{
-  if (Ns == 1) return;
-  const int kk = j & (Ns - 1);
-  const int step = kk * (kN / (Ns * 8));          // W_{8 Ns}^{kk} = W_512^{step}
-#pragma unroll
-  for (int r = 1; r < 8; r++) v[r] = cmul (v[r], tw[(r * step) & (kN - 1)]);
-}
-
-template <int Ns>
-__device__ __forceinline__ int scatter_base (int j) { return (j / Ns) * Ns * 8 + (j & (Ns - 1)); }
 
 __device__ __forceinline__ unsigned ld_acquire (const unsigned *p)
 {
@@ -97,111 +111,201 @@ __device__ __forceinline__ void st_release (unsigned *p, unsigned v)
 {
   asm volatile ("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// named barriers: 1,2 = audio buffer 0/1 full; 3,4 = audio buffer 0/1 empty. All 160 threads take part in each.
+__device__ __forceinline__ void bar_sync (int id) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive (int id) { asm volatile ("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
+
+// int16 pair -> two exact floats without the conversion pipe: (v ^ 0x8000) dropped into the mantissa of 2^23.
+// The 1/32768 of arm_q15_to_float is a power of two and is folded into the mask.
+__device__ __forceinline__ void unpack_iq (uint32_t iq, float &i, float &q)
+{
+  const uint32_t u = iq ^ 0x80008000u;
+  i = __uint_as_float (__byte_perm (u, 0x4B000000u, 0x7610)) - 8421376.0f;
+  q = __uint_as_float (__byte_perm (u, 0x4B000000u, 0x7632)) - 8421376.0f;
+}
 
 __device__ __forceinline__ uint32_t pack_lr (float x)
 {
-  // arm_float_to_q15.c:147 : (q15_t) __SSAT((q31_t)(x * 32768.0f), 16) — cast truncates toward zero
+  // arm_float_to_q15.c:147 : (q15_t) __SSAT((q31_t)(x * 32768.0f), 16) — the cast truncates toward zero
   int v = __float2int_rz (x * 32768.0f);
   v = max (-32768, min (32767, v));
-  const uint32_t u = (uint32_t) v & 0xFFFFu;
-  return u | (u << 16);                            // stereo endpoint, L = R
+  return __byte_perm ((uint32_t) v, 0u, 0x1010);   // stereo endpoint, L = R
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FFT warp: one overlap-save frame. re/im planes are this warp's private scratch.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, float *sim, const float4 *tw, int lane)
+{
+  // entry: xr/xi hold the pass-0 butterfly outputs of j = 2*lane (lo) and 2*lane+1 (hi). Ns = 1 scatter: idx = 8 j + r.
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+  {
+    const int ia = phys (16 * lane + r), ib = phys (16 * lane + 8 + r);
+    sre[ia] = lo_of (xr[r]); sim[ia] = lo_of (xi[r]);
+    sre[ib] = hi_of (xr[r]); sim[ib] = hi_of (xi[r]);
+  }
+  __syncwarp ();
+  // pass 1 (Ns = 8): gather x[j + 64 r], twiddle W_64^{r (j & 7)}, butterfly, scatter to (j / 8) * 64 + (j & 7) + 8 r
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+  {
+    const int i = phys (2 * lane + 64 * r);
+    xr[r] = *reinterpret_cast<const u64 *> (sre + i); xi[r] = *reinterpret_cast<const u64 *> (sim + i);
+  }
+#pragma unroll
+  for (int r = 1; r < 8; r++)
+  {
+    const float4 w = tw[(r - 1) * 32 + lane];
+    const u64 wr = pk (w.x, w.y), wi = pk (w.z, w.w);
+    const u64 nr = fma2 (xr[r], wr, mul2 (sub2 (0ull, xi[r]), wi));     // xr wr - xi wi
+    xi[r] = fma2 (xr[r], wi, mul2 (xi[r], wr));                         // xr wi + xi wr
+    xr[r] = nr;
+  }
+  dft8x2 (xr, xi);
+  __syncwarp ();
+  {
+    const int base = (lane >> 2) * 64 + 2 * (lane & 3);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+    {
+      const int i = phys (base + 8 * r);
+      *reinterpret_cast<u64 *> (sre + i) = xr[r]; *reinterpret_cast<u64 *> (sim + i) = xi[r];
+    }
+  }
+  __syncwarp ();
+  // pass 2 (Ns = 64): gather x[j + 64 r], twiddle W_512^{r j}, butterfly; result index j + 64 r stays in registers
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+  {
+    const int i = phys (2 * lane + 64 * r);
+    xr[r] = *reinterpret_cast<const u64 *> (sre + i); xi[r] = *reinterpret_cast<const u64 *> (sim + i);
+  }
+#pragma unroll
+  for (int r = 1; r < 8; r++)
+  {
+    const float4 w = tw[(7 + r - 1) * 32 + lane];
+    const u64 wr = pk (w.x, w.y), wi = pk (w.z, w.w);
+    const u64 nr = fma2 (xr[r], wr, mul2 (sub2 (0ull, xi[r]), wi));
+    xi[r] = fma2 (xr[r], wi, mul2 (xi[r], wr));
+    xr[r] = nr;
+  }
+  dft8x2 (xr, xi);
+  __syncwarp ();
 }
 
 __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_constant__ KParams P)
 {
-  __shared__ float2 sX[kHopsPerTile][kFramePad];
-  __shared__ float sAudio[kRunsPerTile * kRunPad];
-  __shared__ float sGain[kRunsPerTile];
-  __shared__ float2 sTw[kN];
-  __shared__ unsigned sItem;
+  __shared__ __align__ (16) float sScratch[kFftWarps][2][kPlane];
+  __shared__ __align__ (16) float sAudio[2][kRunsPerTile * kRunPad];
+  __shared__ __align__ (16) float4 sTw[14 * 32];
 
-  const int tid = threadIdx.x;
-  const int fid = tid >> 6;                        // which of the 4 FFT frames of the tile this thread works on
-  const int j = tid & 63;                          // its index inside the 64-thread FFT group
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 14 * 32; i += kThreads) sTw[i] = P.twiddle[i];
+  __syncthreads ();
 
-  for (int i = tid; i < kN; i += kThreads) sTw[i] = P.twiddle[i];
+  const unsigned total_items = P.channels * P.items_per_channel;
+  unsigned tile_seq = 0;                          // tiles this CTA has pushed through the audio double buffer
 
-  const unsigned total_items = P.channels * P.tiles_per_channel;
-
-  while (true)
+  if (warp < kFftWarps)
   {
-    __syncthreads ();                              // also covers sTw on the first trip and smem reuse afterwards
-    if (tid == 0) sItem = atomicAdd (P.queue, 1u);
-    __syncthreads ();
-    const unsigned item = sItem;
-    if (item >= total_items) break;
-    const uint32_t tile = item / P.channels, c = item % P.channels;      // tile-major order
-    const uint32_t t0 = tile * kTile;
-    const int hops = min ((uint32_t) kHopsPerTile, (P.frames - t0) / kHop);
-    const int nsamp = hops * kHop;
-    const uint32_t *in_c = P.in + (size_t) c * P.frames;
-    const float2 *mask = P.masks + (size_t) P.mask_slot[c] * kN;
-
-    // ---- P1: load + unpack (arm_q15_to_float: x / 32768). Frame f covers stream samples [t0 + 384 f - 128, +512).
-    for (int f = 0; f < hops; f++)
+    // =========================================== FFT warps ===========================================
+    float *sre = sScratch[warp][0], *sim = sScratch[warp][1];
+    for (unsigned item = blockIdx.x; item < total_items; item += gridDim.x)
     {
-#pragma unroll
-      for (int i = tid; i < kN; i += kThreads)
+      const uint32_t seg = item / P.channels, c = item % P.channels;              // segment-major order
+      const uint32_t tile0 = seg * kTilesPerItem;
+      const uint32_t ntiles = min ((uint32_t) kTilesPerItem, P.tiles_per_channel - tile0);
+      const uint32_t *in_c = P.in + (size_t) c * P.frames;
+      const float4 *mask = P.masks + (size_t) P.mask_slot[c] * 256;
+      for (uint32_t tl = 0; tl < ntiles; tl++, tile_seq++)
       {
-        const int64_t t = (int64_t) t0 + (int64_t) f * kHop - kOvl + i;
-        const uint32_t iq = (t >= 0) ? __ldg (in_c + t) : __ldg (P.ovl_in + (size_t) c * kOvl + (t + kOvl));
-        const float re = (float) (int16_t) (iq & 0xFFFFu) * (1.0f / 32768.0f);
-        const float im = (float) (int16_t) (iq >> 16) * (1.0f / 32768.0f);
-        sX[f][phys (i)] = make_float2 (re, im);
+        const uint32_t t0 = (tile0 + tl) * kTile;
+        const int hops = min ((uint32_t) kFftWarps, (P.frames - t0) / kHop);
+        const int buf = tile_seq & 1;
+        u64 xr[8], xi[8];
+        if (warp < hops)
+        {
+          // ---- load + unpack (arm_q15_to_float): frame covers stream samples [ts, ts + 512), ts = t0 + 384 w - 128;
+          // lane takes the adjacent pair 2*lane, 2*lane+1 of every 64-sample row: one coalesced 8-byte load per row
+          const int64_t ts = (int64_t) t0 + (int64_t) warp * kHop - kOvl;
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+          {
+            const int64_t t = ts + 2 * lane + 64 * r;
+            const uint2 raw = (t >= 0) ? __ldg (reinterpret_cast<const uint2 *> (in_c + t))
+                                       : __ldg (reinterpret_cast<const uint2 *> (P.ovl_in + (size_t) c * kOvl + (t + kOvl)));
+            float ia, qa, ib, qb;
+            unpack_iq (raw.x, ia, qa); unpack_iq (raw.y, ib, qb);
+            xr[r] = pk (ia, ib); xi[r] = pk (qa, qb);
+          }
+          // carry the raw tail of the stream for the next call (this launch reads ovl_in and writes ovl_out)
+          if (t0 + (warp + 1) * kHop == P.frames)
+          {
+            const uint2 *src = reinterpret_cast<const uint2 *> (in_c + P.frames - kOvl);
+            uint2 *dst = reinterpret_cast<uint2 *> (P.ovl_out + (size_t) c * kOvl);
+            dst[lane] = __ldg (src + lane); dst[lane + 32] = __ldg (src + lane + 32);
+          }
+          // ---- forward FFT (arm_cfft_f32 forward): pass 0 needs no twiddles
+          dft8x2 (xr, xi);
+          fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
+          // ---- spectral mask (arm_cmplx_mult_cmplx_f32), then the inverse transform as a forward transform of the
+          // re/im-swapped spectrum: N ifft(Y) = swap(fft(swap(Y))), so Re ifft(Y) = Im fft(swap Y) / N (1/N is in the mask)
+#pragma unroll
+          for (int r = 0; r < 8; r++)
+          {
+            const float4 h = __ldg (mask + r * 32 + lane);
+            const u64 hr = pk (h.x, h.y), hi = pk (h.z, h.w);
+            const u64 yr = fma2 (xr[r], hr, mul2 (sub2 (0ull, xi[r]), hi));
+            const u64 yi = fma2 (xr[r], hi, mul2 (xi[r], hr));
+            xr[r] = yi; xi[r] = yr;                                                // swap
+          }
+          dft8x2 (xr, xi);
+          fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
+        }
+        // ---- hand the audio of this frame to the recurrence warp: keep the last 384 outputs (rows r >= 2)
+        if (tile_seq >= 2) bar_sync (3 + buf);                                     // wait until the buffer was drained
+        if (warp < hops)
+        {
+          float *a = sAudio[buf];
+#pragma unroll
+          for (int r = 2; r < 8; r++)
+          {
+            const int n = warp * kHop + 2 * lane + 64 * (r - 2);                   // even; n and n+1 lie in the same run
+            const int pos = (n / kRun) * kRunPad + (n % kRun);
+            // (xr, xi) now hold fft(swap Y): the wanted real part is the imaginary component
+            // of that transform, which after fft_passes_1_2 lives in xi
+            a[pos] = lo_of (xi[r]); a[pos + 1] = hi_of (xi[r]);
+          }
+        }
+        bar_arrive (1 + buf);
       }
     }
-    // carry the raw tail for the next call (ping-pong buffer: this launch reads ovl_in, writes ovl_out)
-    if (t0 + nsamp == P.frames)
-      for (int i = tid; i < kOvl; i += kThreads) P.ovl_out[(size_t) c * kOvl + i] = __ldg (in_c + P.frames - kOvl + i);
-    __syncthreads ();
-
-    float2 v[8];
-    const bool active = fid < hops;
-
-    // ---- P2: forward FFT, three Stockham radix-8 passes (Ns = 1, 8, 64), in place with a barrier between gather and scatter
-#define SL_PASS(NS, LOAD_EXPR, STORE_STMT)                                                  \
-    if (active) {                                                                            \
-      _Pragma ("unroll") for (int r = 0; r < 8; r++) { const int idx = j + 64 * r; v[r] = LOAD_EXPR; } \
-      twiddle8<NS> (v, j, sTw);                                                              \
-      dft8 (v);                                                                              \
-    }                                                                                        \
-    __syncthreads ();                                                                        \
-    if (active) {                                                                            \
-      const int base = scatter_base<NS> (j);                                                 \
-      _Pragma ("unroll") for (int r = 0; r < 8; r++) { const int idx = base + r * NS; STORE_STMT; } \
-    }                                                                                        \
-    __syncthreads ();
-
-    SL_PASS (1, sX[fid][phys (idx)], sX[fid][phys (idx)] = v[r])
-    SL_PASS (8, sX[fid][phys (idx)], sX[fid][phys (idx)] = v[r])
-    SL_PASS (64, sX[fid][phys (idx)], sX[fid][phys (idx)] = v[r])
-
-    // ---- P3+P4: spectral mask (arm_cmplx_mult_cmplx_f32) and inverse FFT. arm_cfft_f32 inverse = conj in, forward
-    // transform, conj and 1/N out (arm_cfft_f32.c:571-580, :604-614); the 1/N is folded into the mask (power of two,
-    // exact) and the final conj disappears because only the real part is kept.
+  }
+  else
+  {
+    // ======================================= recurrence warp =======================================
+    const float *cf = P.tab.coef;
+    for (unsigned item = blockIdx.x; item < total_items; item += gridDim.x)
     {
-      auto load_masked = [&] (int idx) {
-        const float2 y = cmul (sX[fid][phys (idx)], __ldg (mask + idx));
-        return make_float2 (y.x, -y.y);
-      };
-      SL_PASS (1, load_masked (idx), sX[fid][phys (idx)] = v[r])
-    }
-    SL_PASS (8, sX[fid][phys (idx)], sX[fid][phys (idx)] = v[r])
-    // last pass: keep the last 384 outputs of the frame, real part only -> audio in lane-run layout
-    SL_PASS (64, sX[fid][phys (idx)], if (idx >= kOvl) { const int n = fid * kHop + idx - kOvl; sAudio[(n / kRun) * kRunPad + (n % kRun)] = v[r].x; })
-#undef SL_PASS
-
-    // ---- P5: recurrences, warp 0. Lane k owns run k (48 samples = one AGC block).
-    if (tid < 32)
-    {
-      const int lane = tid, nruns = nsamp / kRun;
-      float *run = sAudio + lane * kRunPad;
-      const float *cf = P.tab.coef;
-      float d1a = 0.f, d2a = 0.f, d1b = 0.f, d2b = 0.f;
-      if (lane < nruns)
+      const uint32_t seg = item / P.channels, c = item % P.channels;
+      const uint32_t tile0 = seg * kTilesPerItem;
+      const uint32_t ntiles = min ((uint32_t) kTilesPerItem, P.tiles_per_channel - tile0);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, env = 0.f;                     // carried state (uniform across lanes)
+      for (uint32_t tl = 0; tl < ntiles; tl++, tile_seq++)
       {
-        // zero-state response of the cascade; per-sample recurrences as arm_biquad_cascade_df2T_f32.c:551-562
-#pragma unroll 4
+        const uint32_t t0 = (tile0 + tl) * kTile;
+        const int hops = min ((uint32_t) kFftWarps, (P.frames - t0) / kHop);
+        const int nruns = hops * (kHop / kRun);
+        const int buf = tile_seq & 1;
+        float *run = sAudio[buf] + lane * kRunPad;
+        bar_sync (1 + buf);                                                        // audio tile is complete
+
+        // zero-state response of the cascade over this lane's run; per-sample recurrences exactly as
+        // arm_biquad_cascade_df2T_f32.c:551-562:  y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
+        float y[kRun];
+        float d1a = 0.f, d2a = 0.f, d1b = 0.f, d2b = 0.f;
+#pragma unroll
         for (int n = 0; n < kRun; n++)
         {
           const float x = run[n];
@@ -211,90 +315,100 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
           const float y1 = cf[5] * y0 + d1b;
           d1b = (cf[6] * y0 + cf[8] * y1) + d2b;
           d2b = cf[7] * y0 + cf[9] * y1;
-          run[n] = y1;
+          y[n] = y1;
         }
-      }
-      // wait for the previous tile of this channel (tile-major queue order makes this a formality)
-      if (lane == 0) { const unsigned want = P.flag_base + tile; while (ld_acquire (P.flag + c) != want) __nanosleep (64); }
-      __syncwarp ();
-      const float *stc = P.state + (size_t) c * 8;
-      const float s0 = __ldcg (stc + 0), s1 = __ldcg (stc + 1), s2 = __ldcg (stc + 2), s3 = __ldcg (stc + 3);
-      const float env0 = __ldcg (stc + 4);
-
-      // end state of run k given all earlier runs: z_k = zs_k + M z_{k-1}; lane 0 folds the carried state in
-      float z0 = d1a, z1 = d2a, z2 = d1b, z3 = d2b;
-      if (lane == 0)
-      {
-        const float *M = P.tab.Mpow[0];
-        z0 += M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
-        z1 += M[4] * s0 + M[5] * s1 + M[6] * s2 + M[7] * s3;
-        z2 += M[8] * s0 + M[9] * s1 + M[10] * s2 + M[11] * s3;
-        z3 += M[12] * s0 + M[13] * s1 + M[14] * s2 + M[15] * s3;
-      }
-#pragma unroll
-      for (int k = 0; k < 5; k++)
-      {
-        const int d = 1 << k;
-        const float *M = P.tab.Mpow[k];
-        const float p0 = __shfl_up_sync (0xffffffffu, z0, d), p1 = __shfl_up_sync (0xffffffffu, z1, d);
-        const float p2 = __shfl_up_sync (0xffffffffu, z2, d), p3 = __shfl_up_sync (0xffffffffu, z3, d);
-        if (lane >= d)
+        if (tl == 0)
         {
-          z0 += M[0] * p0 + M[1] * p1 + M[2] * p2 + M[3] * p3;
-          z1 += M[4] * p0 + M[5] * p1 + M[6] * p2 + M[7] * p3;
-          z2 += M[8] * p0 + M[9] * p1 + M[10] * p2 + M[11] * p3;
-          z3 += M[12] * p0 + M[13] * p1 + M[14] * p2 + M[15] * p3;
+          // state of the previous segment of this channel (segment-major dealing makes the wait a formality)
+          if (lane == 0) { const unsigned want = P.flag_base + seg; while (ld_acquire (P.flag + c) != want) __nanosleep (64); }
+          __syncwarp ();
+          const float *stc = P.state + (size_t) c * 8;
+          s0 = __ldcg (stc + 0); s1 = __ldcg (stc + 1); s2 = __ldcg (stc + 2); s3 = __ldcg (stc + 3); env = __ldcg (stc + 4);
         }
-      }
-      // start state of this lane's run = end state of the previous run
-      float b0 = __shfl_up_sync (0xffffffffu, z0, 1), b1 = __shfl_up_sync (0xffffffffu, z1, 1);
-      float b2 = __shfl_up_sync (0xffffffffu, z2, 1), b3 = __shfl_up_sync (0xffffffffu, z3, 1);
-      if (lane == 0) { b0 = s0; b1 = s1; b2 = s2; b3 = s3; }
+        // end state of run k given all earlier runs: z_k = zs_k + M z_{k-1}; lane 0 folds the carried state in
+        float z0 = d1a, z1 = d2a, z2 = d1b, z3 = d2b;
+        if (lane == 0)
+        {
+          const float *M = P.tab.Mpow[0];
+          z0 += M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
+          z1 += M[4] * s0 + M[5] * s1 + M[6] * s2 + M[7] * s3;
+          z2 += M[8] * s0 + M[9] * s1 + M[10] * s2 + M[11] * s3;
+          z3 += M[12] * s0 + M[13] * s1 + M[14] * s2 + M[15] * s3;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+        {
+          const int d = 1 << k;
+          const float *M = P.tab.Mpow[k];
+          const float p0 = __shfl_up_sync (0xffffffffu, z0, d), p1 = __shfl_up_sync (0xffffffffu, z1, d);
+          const float p2 = __shfl_up_sync (0xffffffffu, z2, d), p3 = __shfl_up_sync (0xffffffffu, z3, d);
+          if (lane >= d)
+          {
+            z0 += M[0] * p0 + M[1] * p1 + M[2] * p2 + M[3] * p3;
+            z1 += M[4] * p0 + M[5] * p1 + M[6] * p2 + M[7] * p3;
+            z2 += M[8] * p0 + M[9] * p1 + M[10] * p2 + M[11] * p3;
+            z3 += M[12] * p0 + M[13] * p1 + M[14] * p2 + M[15] * p3;
+          }
+        }
+        // start state of this lane's run = end state of the previous run
+        float b0 = __shfl_up_sync (0xffffffffu, z0, 1), b1 = __shfl_up_sync (0xffffffffu, z1, 1);
+        float b2 = __shfl_up_sync (0xffffffffu, z2, 1), b3 = __shfl_up_sync (0xffffffffu, z3, 1);
+        if (lane == 0) { b0 = s0; b1 = s1; b2 = s2; b3 = s3; }
+        // carried state for the next tile = end state of the last run
+        s0 = __shfl_sync (0xffffffffu, z0, nruns - 1); s1 = __shfl_sync (0xffffffffu, z1, nruns - 1);
+        s2 = __shfl_sync (0xffffffffu, z2, nruns - 1); s3 = __shfl_sync (0xffffffffu, z3, nruns - 1);
 
-      float peak = 0.f;
-      if (lane < nruns)
-      {
-        float *adbg = P.audio_dbg ? P.audio_dbg + (size_t) c * P.frames + t0 + lane * kRun : nullptr;
-#pragma unroll 4
+        float peak = 0.f;
+#pragma unroll
         for (int n = 0; n < kRun; n++)
         {
-          const float *C = P.tab.Cresp[n];
-          const float y = run[n] + (C[0] * b0 + C[1] * b1 + C[2] * b2 + C[3] * b3);
-          run[n] = y;
-          peak = fmaxf (peak, fabsf (y));                                   // arm_abs_f32 + arm_max_f32
-          if (adbg) adbg[n] = y;
+          y[n] += P.tab.Cresp[n][0] * b0 + P.tab.Cresp[n][1] * b1 + P.tab.Cresp[n][2] * b2 + P.tab.Cresp[n][3] * b3;
+          peak = fmaxf (peak, fabsf (y[n]));                                       // arm_abs_f32 + arm_max_f32
+        }
+        // AGC envelope: sequential over blocks, exactly the oracle's order
+        float my_env = 0.f;
+        for (int i = 0; i < nruns; i++)
+        {
+          const float pi = __shfl_sync (0xffffffffu, peak, i);
+          env = fmaxf (pi, env * P.agc_decay);
+          if (lane == i) my_env = env;
+        }
+        const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (my_env, P.agc_floor)), P.agc_gmax);
+        if (lane < nruns)
+        {
+          if (P.audio_dbg)
+          {
+            float *adbg = P.audio_dbg + (size_t) c * P.frames + t0 + lane * kRun;
+#pragma unroll
+            for (int n = 0; n < kRun; n++) adbg[n] = y[n];
+          }
+          if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kRun) + t0 / kRun + lane] = g;
+          // gain (arm_scale_f32) and pack (arm_float_to_q15), in place in the run
+          uint32_t *runu = reinterpret_cast<uint32_t *> (run);
+#pragma unroll
+          for (int n = 0; n < kRun; n++) runu[n] = pack_lr (y[n] * g);
+        }
+        __syncwarp ();
+        // coalesced store, 128 B per warp instruction
+        {
+          const uint32_t *au = reinterpret_cast<const uint32_t *> (sAudio[buf]);
+          uint32_t *out_c = P.out + (size_t) c * P.frames + t0;
+          const int nsamp = nruns * kRun;
+          for (int n = lane; n < nsamp; n += 32)
+          {
+            const int r = n / kRun;
+            out_c[n] = au[r * kRunPad + (n - r * kRun)];
+          }
+        }
+        bar_arrive (3 + buf);                                                      // buffer drained
+        if (tl == ntiles - 1 && lane == 0)
+        {
+          float *stw = P.state + (size_t) c * 8;
+          __stcg (stw + 0, s0); __stcg (stw + 1, s1); __stcg (stw + 2, s2); __stcg (stw + 3, s3); __stcg (stw + 4, env);
+          __threadfence ();
+          st_release (P.flag + c, P.flag_base + seg + 1u);
         }
       }
-      // AGC envelope: sequential over blocks, exactly the oracle's order
-      float env = env0, my_env = 0.f;
-      for (int i = 0; i < nruns; i++)
-      {
-        const float pi = __shfl_sync (0xffffffffu, peak, i);
-        env = fmaxf (pi, env * P.agc_decay);
-        if (lane == i) my_env = env;
-      }
-      if (lane < nruns)
-      {
-        const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (my_env, P.agc_floor)), P.agc_gmax);
-        sGain[lane] = g;
-        if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kRun) + t0 / kRun + lane] = g;
-      }
-      if (lane == nruns - 1)
-      {
-        float *stw = P.state + (size_t) c * 8;
-        __stcg (stw + 0, z0); __stcg (stw + 1, z1); __stcg (stw + 2, z2); __stcg (stw + 3, z3); __stcg (stw + 4, env);
-        __threadfence ();
-        st_release (P.flag + c, P.flag_base + tile + 1u);
-      }
-    }
-    __syncthreads ();
-
-    // ---- P6: gain (arm_scale_f32), pack (arm_float_to_q15), coalesced store L = R
-    uint32_t *out_c = P.out + (size_t) c * P.frames + t0;
-    for (int n = tid; n < nsamp; n += kThreads)
-    {
-      const int r = n / kRun;
-      out_c[n] = pack_lr (sAudio[r * kRunPad + (n - r * kRun)] * sGain[r]);
     }
   }
 }
@@ -302,6 +416,44 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
 }  // namespace
 
 uint32_t rx_ssb_f32_launches_per_call () { return 1u; }
+// the per-channel flag advances by one per segment (= kTilesPerItem tiles)
+uint32_t rx_ssb_f32_tiles (uint32_t frames)
+{
+  const uint32_t tiles = (frames + kTile - 1) / kTile;
+  return (tiles + kTilesPerItem - 1) / kTilesPerItem;
+}
+
+// twiddles in the per-lane packed layout the kernel reads with one 16-byte load: [pass][r-1][lane] = (WrA, WrB, WiA, WiB)
+// for the lane's butterflies jA = 2 lane, jB = 2 lane + 1; pass 1: W_64^{r (j & 7)}, pass 2: W_512^{r j}
+void rx_ssb_f32_pack_twiddles (float *out /* 14*32*4 */)
+{
+  const double two_pi = 6.283185307179586476925286766559;
+  for (int pass = 0; pass < 2; pass++)
+    for (int r = 1; r < 8; r++)
+      for (int lane = 0; lane < 32; lane++)
+      {
+        float *o = out + ((pass * 7 + (r - 1)) * 32 + lane) * 4;
+        for (int b = 0; b < 2; b++)
+        {
+          const int j = 2 * lane + b;
+          const int e = (pass == 0) ? (r * (j & 7) * 8) % kN : (r * j) % kN;
+          const double a = -two_pi * (double) e / (double) kN;
+          o[b] = (float) std::cos (a); o[2 + b] = (float) std::sin (a);
+        }
+      }
+}
+// mask (already scaled by the caller) in the packed layout: [r][lane] = (HrA, HrB, HiA, HiB), k = 2 lane + b + 64 r
+void rx_ssb_f32_pack_mask (const float *mask_re_im /* 2*512 */, float scale, float *out /* 8*32*4 */)
+{
+  for (int r = 0; r < 8; r++)
+    for (int lane = 0; lane < 32; lane++)
+      for (int b = 0; b < 2; b++)
+      {
+        const int k = 2 * lane + b + 64 * r;
+        out[(r * 32 + lane) * 4 + b] = mask_re_im[2 * k] * scale;
+        out[(r * 32 + lane) * 4 + 2 + b] = mask_re_im[2 * k + 1] * scale;
+      }
+}
 
 int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream_)
 {
@@ -311,27 +463,24 @@ int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream_)
   P.in = reinterpret_cast<const uint32_t *> (L.in); P.out = reinterpret_cast<uint32_t *> (L.out);
   P.audio_dbg = L.audio_dbg; P.gain_dbg = L.gain_dbg;
   P.ovl_in = reinterpret_cast<const uint32_t *> (L.ovl_in); P.ovl_out = reinterpret_cast<uint32_t *> (L.ovl_out);
-  P.state = L.state; P.flag = L.flag; P.queue = L.queue;
-  P.masks = reinterpret_cast<const float2 *> (L.masks); P.mask_slot = L.mask_slot;
-  P.twiddle = reinterpret_cast<const float2 *> (L.twiddle);
+  P.state = L.state; P.flag = L.flag;
+  P.masks = reinterpret_cast<const float4 *> (L.masks); P.mask_slot = L.mask_slot;
+  P.twiddle = reinterpret_cast<const float4 *> (L.twiddle);
   P.flag_base = L.flag_base; P.channels = L.channels; P.frames = L.frames;
   P.tiles_per_channel = (L.frames + kTile - 1) / kTile;
+  P.items_per_channel = (P.tiles_per_channel + kTilesPerItem - 1) / kTilesPerItem;
   P.agc_target = L.agc_target; P.agc_decay = L.agc_decay; P.agc_floor = L.agc_floor; P.agc_gmax = L.agc_gmax;
   P.tab = *L.tables;
 
-  cudaError_t e = cudaMemsetAsync (L.queue, 0, sizeof (unsigned), stream);
-  if (e != cudaSuccess) return (int) e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, rx_ssb_f32_kernel, kThreads, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, rx_ssb_f32_kernel, kThreads, 0);
   if (e != cudaSuccess) return (int) e;
   if (per_sm < 1) per_sm = 1;
-  const uint64_t items = (uint64_t) L.channels * P.tiles_per_channel;
-  uint64_t grid = (uint64_t) sm_count * per_sm;
+  const uint64_t items = (uint64_t) L.channels * P.items_per_channel;
+  uint64_t grid = (uint64_t) sm_count * per_sm;      // all CTAs co-resident: the segment hand-over may spin
   if (grid > items) grid = items;
   rx_ssb_f32_kernel<<<(unsigned) grid, kThreads, 0, stream>>> (P);
   return (int) cudaGetLastError ();
 }
-
-uint32_t rx_ssb_f32_tiles (uint32_t frames) { return (frames + kTile - 1) / kTile; }
 
 }  // namespace sl
