@@ -124,12 +124,61 @@ __device__ __forceinline__ void unpack_iq (uint32_t iq, float &i, float &q)
   q = __uint_as_float (__byte_perm (u, 0x4B000000u, 0x7632)) - 8421376.0f;
 }
 
-__device__ __forceinline__ uint32_t pack_lr (float x)
+__device__ __forceinline__ uint32_t pack_lr (float x_times_32768)
 {
-  // arm_float_to_q15.c:147 : (q15_t) __SSAT((q31_t)(x * 32768.0f), 16) — the cast truncates toward zero
-  int v = __float2int_rz (x * 32768.0f);
-  v = max (-32768, min (32767, v));
-  return __byte_perm ((uint32_t) v, 0u, 0x1010);   // stereo endpoint, L = R
+  // arm_float_to_q15.c:147 : (q15_t) __SSAT((q31_t)(x * 32768.0f), 16) — the cast truncates toward zero, then saturates.
+  // F2I.S16.TRUNC does both; the caller has already multiplied by 32768 (a power of two, folded into the gain).
+  short v;
+  asm ("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(v) : "f"(x_times_32768));
+  return __byte_perm ((uint32_t) (uint16_t) v, 0u, 0x1010);   // stereo endpoint, L = R
+}
+
+// work-list walk shared by both roles: CTA b takes items b, b + grid, ... (segment-major), each item = up to
+// kTilesPerItem consecutive tiles of one channel
+struct TileIter
+{
+  unsigned item, total_items, stride;
+  uint32_t seg, c, tl, ntiles, t0;
+  int hops;
+  bool valid;
+  __device__ __forceinline__ void set_item (const KParams &P)
+  {
+    valid = item < total_items;
+    if (!valid) return;
+    seg = item / P.channels; c = item % P.channels;
+    const uint32_t tile0 = seg * kTilesPerItem;
+    ntiles = min ((uint32_t) kTilesPerItem, P.tiles_per_channel - tile0);
+    tl = 0; set_tile (P);
+  }
+  __device__ __forceinline__ void set_tile (const KParams &P)
+  {
+    t0 = (seg * kTilesPerItem + tl) * kTile;
+    hops = min ((uint32_t) kFftWarps, (P.frames - t0) / kHop);
+  }
+  __device__ __forceinline__ void start (const KParams &P)
+  {
+    total_items = P.channels * P.items_per_channel; stride = gridDim.x; item = blockIdx.x; set_item (P);
+  }
+  __device__ __forceinline__ void next (const KParams &P)
+  {
+    if (++tl < ntiles) { set_tile (P); return; }
+    item += stride; set_item (P);
+  }
+};
+
+__device__ __forceinline__ void load_frame_raw (const KParams &P, const TileIter &it, int warp, int lane, uint2 *raw)
+{
+  // frame covers stream samples [ts, ts + 512), ts = t0 + 384 w - 128; the lane takes the adjacent pair 2*lane,
+  // 2*lane+1 of every 64-sample row: one coalesced 8-byte load per row
+  const uint32_t *in_c = P.in + (size_t) it.c * P.frames;
+  const int64_t ts = (int64_t) it.t0 + (int64_t) warp * kHop - kOvl;
+#pragma unroll
+  for (int r = 0; r < 8; r++)
+  {
+    const int64_t t = ts + 2 * lane + 64 * r;
+    raw[r] = (t >= 0) ? __ldg (reinterpret_cast<const uint2 *> (in_c + t))
+                      : __ldg (reinterpret_cast<const uint2 *> (P.ovl_in + (size_t) it.c * kOvl + (t + kOvl)));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -158,7 +207,7 @@ __device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, fl
   {
     const float4 w = tw[(r - 1) * 32 + lane];
     const u64 wr = pk (w.x, w.y), wi = pk (w.z, w.w);
-    const u64 nr = fma2 (xr[r], wr, mul2 (sub2 (0ull, xi[r]), wi));     // xr wr - xi wi
+    const u64 nr = sub2 (mul2 (xr[r], wr), mul2 (xi[r], wi));           // xr wr - xi wi
     xi[r] = fma2 (xr[r], wi, mul2 (xi[r], wr));                         // xr wi + xi wr
     xr[r] = nr;
   }
@@ -186,7 +235,7 @@ __device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, fl
   {
     const float4 w = tw[(7 + r - 1) * 32 + lane];
     const u64 wr = pk (w.x, w.y), wi = pk (w.z, w.w);
-    const u64 nr = fma2 (xr[r], wr, mul2 (sub2 (0ull, xi[r]), wi));
+    const u64 nr = sub2 (mul2 (xr[r], wr), mul2 (xi[r], wi));
     xi[r] = fma2 (xr[r], wi, mul2 (xi[r], wr));
     xr[r] = nr;
   }
@@ -199,215 +248,204 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
   __shared__ __align__ (16) float sScratch[kFftWarps][2][kPlane];
   __shared__ __align__ (16) float sAudio[2][kRunsPerTile * kRunPad];
   __shared__ __align__ (16) float4 sTw[14 * 32];
+  __shared__ __align__ (16) float sPeak[32];
+  __shared__ float sEnv[32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < 14 * 32; i += kThreads) sTw[i] = P.twiddle[i];
   __syncthreads ();
 
-  const unsigned total_items = P.channels * P.items_per_channel;
   unsigned tile_seq = 0;                          // tiles this CTA has pushed through the audio double buffer
 
   if (warp < kFftWarps)
   {
     // =========================================== FFT warps ===========================================
     float *sre = sScratch[warp][0], *sim = sScratch[warp][1];
-    for (unsigned item = blockIdx.x; item < total_items; item += gridDim.x)
+    TileIter it; it.start (P);
+    uint2 raw[8];
+    if (it.valid && warp < it.hops) load_frame_raw (P, it, warp, lane, raw);
+    for (; it.valid; tile_seq++)
     {
-      const uint32_t seg = item / P.channels, c = item % P.channels;              // segment-major order
-      const uint32_t tile0 = seg * kTilesPerItem;
-      const uint32_t ntiles = min ((uint32_t) kTilesPerItem, P.tiles_per_channel - tile0);
-      const uint32_t *in_c = P.in + (size_t) c * P.frames;
-      const float4 *mask = P.masks + (size_t) P.mask_slot[c] * 256;
-      for (uint32_t tl = 0; tl < ntiles; tl++, tile_seq++)
+      const int buf = tile_seq & 1;
+      const bool mine = warp < it.hops;
+      const uint32_t c = it.c, t0 = it.t0;
+      u64 xr[8], xi[8];
+      if (mine)
       {
-        const uint32_t t0 = (tile0 + tl) * kTile;
-        const int hops = min ((uint32_t) kFftWarps, (P.frames - t0) / kHop);
-        const int buf = tile_seq & 1;
-        u64 xr[8], xi[8];
-        if (warp < hops)
+        // ---- unpack (arm_q15_to_float)
+#pragma unroll
+        for (int r = 0; r < 8; r++)
         {
-          // ---- load + unpack (arm_q15_to_float): frame covers stream samples [ts, ts + 512), ts = t0 + 384 w - 128;
-          // lane takes the adjacent pair 2*lane, 2*lane+1 of every 64-sample row: one coalesced 8-byte load per row
-          const int64_t ts = (int64_t) t0 + (int64_t) warp * kHop - kOvl;
-#pragma unroll
-          for (int r = 0; r < 8; r++)
-          {
-            const int64_t t = ts + 2 * lane + 64 * r;
-            const uint2 raw = (t >= 0) ? __ldg (reinterpret_cast<const uint2 *> (in_c + t))
-                                       : __ldg (reinterpret_cast<const uint2 *> (P.ovl_in + (size_t) c * kOvl + (t + kOvl)));
-            float ia, qa, ib, qb;
-            unpack_iq (raw.x, ia, qa); unpack_iq (raw.y, ib, qb);
-            xr[r] = pk (ia, ib); xi[r] = pk (qa, qb);
-          }
-          // carry the raw tail of the stream for the next call (this launch reads ovl_in and writes ovl_out)
-          if (t0 + (warp + 1) * kHop == P.frames)
-          {
-            const uint2 *src = reinterpret_cast<const uint2 *> (in_c + P.frames - kOvl);
-            uint2 *dst = reinterpret_cast<uint2 *> (P.ovl_out + (size_t) c * kOvl);
-            dst[lane] = __ldg (src + lane); dst[lane + 32] = __ldg (src + lane + 32);
-          }
-          // ---- forward FFT (arm_cfft_f32 forward): pass 0 needs no twiddles
-          dft8x2 (xr, xi);
-          fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
-          // ---- spectral mask (arm_cmplx_mult_cmplx_f32), then the inverse transform as a forward transform of the
-          // re/im-swapped spectrum: N ifft(Y) = swap(fft(swap(Y))), so Re ifft(Y) = Im fft(swap Y) / N (1/N is in the mask)
-#pragma unroll
-          for (int r = 0; r < 8; r++)
-          {
-            const float4 h = __ldg (mask + r * 32 + lane);
-            const u64 hr = pk (h.x, h.y), hi = pk (h.z, h.w);
-            const u64 yr = fma2 (xr[r], hr, mul2 (sub2 (0ull, xi[r]), hi));
-            const u64 yi = fma2 (xr[r], hi, mul2 (xi[r], hr));
-            xr[r] = yi; xi[r] = yr;                                                // swap
-          }
-          dft8x2 (xr, xi);
-          fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
+          float ia, qa, ib, qb;
+          unpack_iq (raw[r].x, ia, qa); unpack_iq (raw[r].y, ib, qb);
+          xr[r] = pk (ia, ib); xi[r] = pk (qa, qb);
         }
-        // ---- hand the audio of this frame to the recurrence warp: keep the last 384 outputs (rows r >= 2)
-        if (tile_seq >= 2) bar_sync (3 + buf);                                     // wait until the buffer was drained
-        if (warp < hops)
+        // carry the raw tail of the stream for the next call (this launch reads ovl_in and writes ovl_out)
+        if (t0 + (warp + 1) * kHop == P.frames)
         {
-          float *a = sAudio[buf];
-#pragma unroll
-          for (int r = 2; r < 8; r++)
-          {
-            const int n = warp * kHop + 2 * lane + 64 * (r - 2);                   // even; n and n+1 lie in the same run
-            const int pos = (n / kRun) * kRunPad + (n % kRun);
-            // (xr, xi) now hold fft(swap Y): the wanted real part is the imaginary component
-            // of that transform, which after fft_passes_1_2 lives in xi
-            a[pos] = lo_of (xi[r]); a[pos + 1] = hi_of (xi[r]);
-          }
+          uint2 *dst = reinterpret_cast<uint2 *> (P.ovl_out + (size_t) c * kOvl);
+          dst[lane] = raw[6]; dst[lane + 32] = raw[7];                            // rows 6, 7 = the last 128 frames
         }
-        bar_arrive (1 + buf);
       }
+      const float4 *mask = P.masks + (size_t) P.mask_slot[c] * 256;
+      // ---- software prefetch: the next tile's frame is requested now and consumed after two FFTs
+      it.next (P);
+      if (it.valid && warp < it.hops) load_frame_raw (P, it, warp, lane, raw);
+      if (mine)
+      {
+        // ---- forward FFT (arm_cfft_f32 forward): pass 0 needs no twiddles
+        dft8x2 (xr, xi);
+        fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
+        // ---- spectral mask (arm_cmplx_mult_cmplx_f32), then the inverse transform as a forward transform of the
+        // re/im-swapped spectrum: N ifft(Y) = swap(fft(swap(Y))), so Re ifft(Y) = Im fft(swap Y) / N (1/N is in the mask)
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+        {
+          const float4 h = __ldg (mask + r * 32 + lane);
+          const u64 hr = pk (h.x, h.y), hi = pk (h.z, h.w);
+          const u64 yr = sub2 (mul2 (xr[r], hr), mul2 (xi[r], hi));
+          const u64 yi = fma2 (xr[r], hi, mul2 (xi[r], hr));
+          xr[r] = yi; xi[r] = yr;                                                  // swap
+        }
+        dft8x2 (xr, xi);
+        fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
+      }
+      // ---- hand the audio of this frame to the recurrence warp: keep the last 384 outputs (rows r >= 2)
+      if (tile_seq >= 2) bar_sync (3 + buf);                                       // wait until the buffer was drained
+      if (mine)
+      {
+        float *a = sAudio[buf];
+#pragma unroll
+        for (int r = 2; r < 8; r++)
+        {
+          const int n = warp * kHop + 2 * lane + 64 * (r - 2);                     // even; n and n+1 lie in the same run
+          const int pos = (n / kRun) * kRunPad + (n % kRun);
+          // (xr, xi) hold fft(swap Y): the wanted real part of the inverse transform is its imaginary component
+          a[pos] = lo_of (xi[r]); a[pos + 1] = hi_of (xi[r]);
+        }
+      }
+      bar_arrive (1 + buf);
     }
   }
   else
   {
     // ======================================= recurrence warp =======================================
     const float *cf = P.tab.coef;
-    for (unsigned item = blockIdx.x; item < total_items; item += gridDim.x)
+    const float decay = P.agc_decay;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, env = 0.f;                       // carried state (uniform across lanes)
+    TileIter it; it.start (P);
+    for (; it.valid; it.next (P), tile_seq++)
     {
-      const uint32_t seg = item / P.channels, c = item % P.channels;
-      const uint32_t tile0 = seg * kTilesPerItem;
-      const uint32_t ntiles = min ((uint32_t) kTilesPerItem, P.tiles_per_channel - tile0);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, env = 0.f;                     // carried state (uniform across lanes)
-      for (uint32_t tl = 0; tl < ntiles; tl++, tile_seq++)
+      const uint32_t c = it.c, t0 = it.t0;
+      const int nruns = it.hops * (kHop / kRun);
+      const int buf = tile_seq & 1;
+      const float *run = sAudio[buf] + lane * kRunPad;
+      bar_sync (1 + buf);                                                          // audio tile is complete
+
+      // zero-state response of the cascade over this lane's run; per-sample recurrences exactly as
+      // arm_biquad_cascade_df2T_f32.c:551-562:  y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
+      float y[kRun];
+      float d1a = 0.f, d2a = 0.f, d1b = 0.f, d2b = 0.f;
+#pragma unroll
+      for (int n = 0; n < kRun; n++)
       {
-        const uint32_t t0 = (tile0 + tl) * kTile;
-        const int hops = min ((uint32_t) kFftWarps, (P.frames - t0) / kHop);
-        const int nruns = hops * (kHop / kRun);
-        const int buf = tile_seq & 1;
-        float *run = sAudio[buf] + lane * kRunPad;
-        bar_sync (1 + buf);                                                        // audio tile is complete
-
-        // zero-state response of the cascade over this lane's run; per-sample recurrences exactly as
-        // arm_biquad_cascade_df2T_f32.c:551-562:  y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
-        float y[kRun];
-        float d1a = 0.f, d2a = 0.f, d1b = 0.f, d2b = 0.f;
-#pragma unroll
-        for (int n = 0; n < kRun; n++)
-        {
-          const float x = run[n];
-          const float y0 = cf[0] * x + d1a;
-          d1a = (cf[1] * x + cf[3] * y0) + d2a;
-          d2a = cf[2] * x + cf[4] * y0;
-          const float y1 = cf[5] * y0 + d1b;
-          d1b = (cf[6] * y0 + cf[8] * y1) + d2b;
-          d2b = cf[7] * y0 + cf[9] * y1;
-          y[n] = y1;
-        }
-        if (tl == 0)
-        {
-          // state of the previous segment of this channel (segment-major dealing makes the wait a formality)
-          if (lane == 0) { const unsigned want = P.flag_base + seg; while (ld_acquire (P.flag + c) != want) __nanosleep (64); }
-          __syncwarp ();
-          const float *stc = P.state + (size_t) c * 8;
-          s0 = __ldcg (stc + 0); s1 = __ldcg (stc + 1); s2 = __ldcg (stc + 2); s3 = __ldcg (stc + 3); env = __ldcg (stc + 4);
-        }
-        // end state of run k given all earlier runs: z_k = zs_k + M z_{k-1}; lane 0 folds the carried state in
-        float z0 = d1a, z1 = d2a, z2 = d1b, z3 = d2b;
-        if (lane == 0)
-        {
-          const float *M = P.tab.Mpow[0];
-          z0 += M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
-          z1 += M[4] * s0 + M[5] * s1 + M[6] * s2 + M[7] * s3;
-          z2 += M[8] * s0 + M[9] * s1 + M[10] * s2 + M[11] * s3;
-          z3 += M[12] * s0 + M[13] * s1 + M[14] * s2 + M[15] * s3;
-        }
-#pragma unroll
-        for (int k = 0; k < 5; k++)
-        {
-          const int d = 1 << k;
-          const float *M = P.tab.Mpow[k];
-          const float p0 = __shfl_up_sync (0xffffffffu, z0, d), p1 = __shfl_up_sync (0xffffffffu, z1, d);
-          const float p2 = __shfl_up_sync (0xffffffffu, z2, d), p3 = __shfl_up_sync (0xffffffffu, z3, d);
-          if (lane >= d)
-          {
-            z0 += M[0] * p0 + M[1] * p1 + M[2] * p2 + M[3] * p3;
-            z1 += M[4] * p0 + M[5] * p1 + M[6] * p2 + M[7] * p3;
-            z2 += M[8] * p0 + M[9] * p1 + M[10] * p2 + M[11] * p3;
-            z3 += M[12] * p0 + M[13] * p1 + M[14] * p2 + M[15] * p3;
-          }
-        }
-        // start state of this lane's run = end state of the previous run
-        float b0 = __shfl_up_sync (0xffffffffu, z0, 1), b1 = __shfl_up_sync (0xffffffffu, z1, 1);
-        float b2 = __shfl_up_sync (0xffffffffu, z2, 1), b3 = __shfl_up_sync (0xffffffffu, z3, 1);
-        if (lane == 0) { b0 = s0; b1 = s1; b2 = s2; b3 = s3; }
-        // carried state for the next tile = end state of the last run
-        s0 = __shfl_sync (0xffffffffu, z0, nruns - 1); s1 = __shfl_sync (0xffffffffu, z1, nruns - 1);
-        s2 = __shfl_sync (0xffffffffu, z2, nruns - 1); s3 = __shfl_sync (0xffffffffu, z3, nruns - 1);
-
-        float peak = 0.f;
-#pragma unroll
-        for (int n = 0; n < kRun; n++)
-        {
-          y[n] += P.tab.Cresp[n][0] * b0 + P.tab.Cresp[n][1] * b1 + P.tab.Cresp[n][2] * b2 + P.tab.Cresp[n][3] * b3;
-          peak = fmaxf (peak, fabsf (y[n]));                                       // arm_abs_f32 + arm_max_f32
-        }
-        // AGC envelope: sequential over blocks, exactly the oracle's order
-        float my_env = 0.f;
-        for (int i = 0; i < nruns; i++)
-        {
-          const float pi = __shfl_sync (0xffffffffu, peak, i);
-          env = fmaxf (pi, env * P.agc_decay);
-          if (lane == i) my_env = env;
-        }
-        const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (my_env, P.agc_floor)), P.agc_gmax);
-        if (lane < nruns)
-        {
-          if (P.audio_dbg)
-          {
-            float *adbg = P.audio_dbg + (size_t) c * P.frames + t0 + lane * kRun;
-#pragma unroll
-            for (int n = 0; n < kRun; n++) adbg[n] = y[n];
-          }
-          if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kRun) + t0 / kRun + lane] = g;
-          // gain (arm_scale_f32) and pack (arm_float_to_q15), in place in the run
-          uint32_t *runu = reinterpret_cast<uint32_t *> (run);
-#pragma unroll
-          for (int n = 0; n < kRun; n++) runu[n] = pack_lr (y[n] * g);
-        }
+        const float x = run[n];
+        // (b1 x + d2) is formed before y is known, so each stage costs two dependent FMAs per sample
+        const float y0 = fmaf (cf[0], x, d1a);
+        d1a = fmaf (cf[3], y0, fmaf (cf[1], x, d2a));
+        d2a = fmaf (cf[4], y0, cf[2] * x);
+        const float y1 = fmaf (cf[5], y0, d1b);
+        d1b = fmaf (cf[8], y1, fmaf (cf[6], y0, d2b));
+        d2b = fmaf (cf[9], y1, cf[7] * y0);
+        y[n] = y1;
+      }
+      __syncwarp ();
+      bar_arrive (3 + buf);                                                        // the audio tile now lives in registers
+      if (it.tl == 0)
+      {
+        // state of the previous segment of this channel (segment-major dealing makes the wait a formality)
+        if (lane == 0) { const unsigned want = P.flag_base + it.seg; while (ld_acquire (P.flag + c) != want) __nanosleep (64); }
         __syncwarp ();
-        // coalesced store, 128 B per warp instruction
+        const float *stc = P.state + (size_t) c * 8;
+        s0 = __ldcg (stc + 0); s1 = __ldcg (stc + 1); s2 = __ldcg (stc + 2); s3 = __ldcg (stc + 3); env = __ldcg (stc + 4);
+      }
+      // end state of run k given all earlier runs: z_k = zs_k + M z_{k-1}; lane 0 folds the carried state in
+      float z0 = d1a, z1 = d2a, z2 = d1b, z3 = d2b;
+      if (lane == 0)
+      {
+        const float *M = P.tab.Mpow[0];
+        z0 += M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
+        z1 += M[4] * s0 + M[5] * s1 + M[6] * s2 + M[7] * s3;
+        z2 += M[8] * s0 + M[9] * s1 + M[10] * s2 + M[11] * s3;
+        z3 += M[12] * s0 + M[13] * s1 + M[14] * s2 + M[15] * s3;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+      {
+        const int d = 1 << k;
+        const float *M = P.tab.Mpow[k];
+        const float p0 = __shfl_up_sync (0xffffffffu, z0, d), p1 = __shfl_up_sync (0xffffffffu, z1, d);
+        const float p2 = __shfl_up_sync (0xffffffffu, z2, d), p3 = __shfl_up_sync (0xffffffffu, z3, d);
+        if (lane >= d)
         {
-          const uint32_t *au = reinterpret_cast<const uint32_t *> (sAudio[buf]);
-          uint32_t *out_c = P.out + (size_t) c * P.frames + t0;
-          const int nsamp = nruns * kRun;
-          for (int n = lane; n < nsamp; n += 32)
-          {
-            const int r = n / kRun;
-            out_c[n] = au[r * kRunPad + (n - r * kRun)];
-          }
+          z0 += M[0] * p0 + M[1] * p1 + M[2] * p2 + M[3] * p3;
+          z1 += M[4] * p0 + M[5] * p1 + M[6] * p2 + M[7] * p3;
+          z2 += M[8] * p0 + M[9] * p1 + M[10] * p2 + M[11] * p3;
+          z3 += M[12] * p0 + M[13] * p1 + M[14] * p2 + M[15] * p3;
         }
-        bar_arrive (3 + buf);                                                      // buffer drained
-        if (tl == ntiles - 1 && lane == 0)
+      }
+      // start state of this lane's run = end state of the previous run
+      float b0 = __shfl_up_sync (0xffffffffu, z0, 1), b1 = __shfl_up_sync (0xffffffffu, z1, 1);
+      float b2 = __shfl_up_sync (0xffffffffu, z2, 1), b3 = __shfl_up_sync (0xffffffffu, z3, 1);
+      if (lane == 0) { b0 = s0; b1 = s1; b2 = s2; b3 = s3; }
+      // carried state for the next tile = end state of the last run
+      s0 = __shfl_sync (0xffffffffu, z0, nruns - 1); s1 = __shfl_sync (0xffffffffu, z1, nruns - 1);
+      s2 = __shfl_sync (0xffffffffu, z2, nruns - 1); s3 = __shfl_sync (0xffffffffu, z3, nruns - 1);
+
+      float peak = 0.f;
+#pragma unroll
+      for (int n = 0; n < kRun; n++)
+      {
+        y[n] += P.tab.Cresp[n][0] * b0 + P.tab.Cresp[n][1] * b1 + P.tab.Cresp[n][2] * b2 + P.tab.Cresp[n][3] * b3;
+        peak = fmaxf (peak, fabsf (y[n]));                                         // arm_abs_f32 + arm_max_f32
+      }
+      // AGC envelope: sequential over blocks in exactly the oracle's order. Every lane walks the same
+      // chain from the block peaks (shared memory, broadcast reads) and drops each step where its owner picks it up.
+      sPeak[lane] = peak;
+      __syncwarp ();
+      for (int q = 0; q < nruns; q += 4)
+      {
+        const float4 p4 = *reinterpret_cast<const float4 *> (&sPeak[q]);
+        env = fmaxf (p4.x, env * decay); sEnv[q] = env;
+        env = fmaxf (p4.y, env * decay); sEnv[q + 1] = env;
+        env = fmaxf (p4.z, env * decay); sEnv[q + 2] = env;
+        env = fmaxf (p4.w, env * decay); sEnv[q + 3] = env;
+      }
+      __syncwarp ();
+      const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (sEnv[lane], P.agc_floor)), P.agc_gmax);
+      __syncwarp ();
+      if (lane < nruns)
+      {
+        if (P.audio_dbg)
         {
-          float *stw = P.state + (size_t) c * 8;
-          __stcg (stw + 0, s0); __stcg (stw + 1, s1); __stcg (stw + 2, s2); __stcg (stw + 3, s3); __stcg (stw + 4, env);
-          __threadfence ();
-          st_release (P.flag + c, P.flag_base + seg + 1u);
+          float *adbg = P.audio_dbg + (size_t) c * P.frames + t0 + lane * kRun;
+#pragma unroll
+          for (int n = 0; n < kRun; n++) adbg[n] = y[n];
         }
+        if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kRun) + t0 / kRun + lane] = g;
+        // gain (arm_scale_f32), pack (arm_float_to_q15) and store: the lane's run is 192 contiguous bytes
+        const float g15 = g * 32768.0f;                                           // exact: power of two
+        uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + t0 + lane * kRun);
+#pragma unroll
+        for (int n = 0; n < kRun; n += 4)
+          dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
+      }
+      if (it.tl == it.ntiles - 1 && lane == 0)
+      {
+        float *stw = P.state + (size_t) c * 8;
+        __stcg (stw + 0, s0); __stcg (stw + 1, s1); __stcg (stw + 2, s2); __stcg (stw + 3, s3); __stcg (stw + 4, env);
+        __threadfence ();
+        st_release (P.flag + c, P.flag_base + it.seg + 1u);
       }
     }
   }
