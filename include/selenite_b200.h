@@ -121,8 +121,9 @@ int slb_state_load (slb_ctx *ctx, const void *host_buf, size_t bytes);
  * the block, then its last frame once more, dsp_if.c:291-300). */
 uint32_t slb_ring_plan_write (uint32_t ring_frames, int is_out, uint32_t state[3], uint32_t frames);
 uint32_t slb_ring_plan_read (uint32_t ring_frames, int is_out, uint32_t state[3], uint32_t frames);
-/* tables of the time-parallel 2-stage df2T evaluation: Mpow[5][16], Cresp[48][4] */
-int slb_biquad_scan_tables (const float coef10[10], float *Mpow80, float *Cresp192);
+/* tables of the time-parallel 2-stage df2T evaluation for runs of 24 samples: Mpow[6][16] =
+ * (A^24)^(2^k), Cresp[24][4] */
+int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp96);
 
 /* ---- accounting ---- */
 uint64_t slb_kernel_launches (const slb_ctx *ctx);   /* kernels this context has launched since create */

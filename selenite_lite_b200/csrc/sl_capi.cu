@@ -188,7 +188,7 @@ int slb_sync (slb_ctx *ctx)
 int slb_set_rx_f32_params (slb_ctx *ctx, const slb_rx_f32_params *p)
 {
   if (!ctx || !p) return SLB_ERR_ARG;
-  if (p->fft_len != 512 || p->hop != 384 || p->n_stages != 2 || p->agc_block != (uint32_t) kRun)
+  if (p->fft_len != 512 || p->hop != 384 || p->n_stages != 2 || p->agc_block != (uint32_t) kAgcBlock)
     return fail (ctx, SLB_ERR_UNSUPPORTED, "this build has kernels for fft_len=512, hop=384, n_stages=2, agc_block=48 only");
   if (!(p->agc_decay > 0.f && p->agc_decay <= 1.f) || !(p->agc_floor > 0.f) || !(p->agc_gmax > 0.f) || !(p->agc_target > 0.f))
     return fail (ctx, SLB_ERR_ARG, "AGC constants out of range");
@@ -396,11 +396,11 @@ uint32_t slb_ring_plan_read (uint32_t ring_frames, int is_out, uint32_t state[3]
   state[0] = rp.enable; state[1] = rp.rd; state[2] = rp.wr;
   return first;
 }
-int slb_biquad_scan_tables (const float coef10[10], float *Mpow80, float *Cresp192)
+int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp96)
 {
-  if (!coef10 || !Mpow80 || !Cresp192) return SLB_ERR_ARG;
+  if (!coef10 || !Mpow96 || !Cresp96) return SLB_ERR_ARG;
   BiquadScanTables t; design_biquad_scan_tables (coef10, &t);
-  std::memcpy (Mpow80, t.Mpow, sizeof t.Mpow); std::memcpy (Cresp192, t.Cresp, sizeof t.Cresp);
+  std::memcpy (Mpow96, t.Mpow, sizeof t.Mpow); std::memcpy (Cresp96, t.Cresp, sizeof t.Cresp);
   return SLB_OK;
 }
 

@@ -127,7 +127,7 @@ void design_biquad_scan_tables (const float *cf, BiquadScanTables *t)
     }
     for (int r = 0; r < 4; r++) M[r][col] = s[r];
   }
-  for (int k = 0; k < 5; k++)
+  for (int k = 0; k < 6; k++)
   {
     for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) t->Mpow[k][4 * r + c] = (float) M[r][c];
     double P[4][4];

@@ -43,11 +43,12 @@ int design_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mas
 int mode_to_mask_slot (uint8_t mode);   // -1 when the mode has no SSB-style mask (AM, FM)
 
 // Tables the time-parallel biquad needs, derived in double from the 2-stage df2T coefficients (sl_design.cpp).
-constexpr int kRun = 48;                // samples per lane run = AGC block
+constexpr int kRun = 24;                // samples per run; a lane of the recurrence warp carries two runs = one AGC block
+constexpr int kAgcBlock = 2 * kRun;     // 48 frames = the firmware block at 48 kHz
 struct BiquadScanTables
 {
   float coef[10];                       // stage 0 {b0,b1,b2,a1,a2}, stage 1 {...}
-  float Mpow[5][16];                    // (A^kRun)^(2^k), k = 0..4, row-major 4x4, state order {d1_0,d2_0,d1_1,d2_1}
+  float Mpow[6][16];                    // (A^kRun)^(2^k), k = 0..5, row-major 4x4, state order {d1_0,d2_0,d1_1,d2_1}
   float Cresp[kRun][4];                 // zero-input response of the cascade output at sample n of a run per unit state
 };
 void design_biquad_scan_tables (const float *coef10, BiquadScanTables *t);
@@ -81,6 +82,6 @@ uint32_t rx_ssb_f32_launches_per_call ();
 uint32_t rx_ssb_f32_tiles (uint32_t frames);   // how far a call of `frames` advances the per-channel hand-over flag
 void rx_ssb_f32_pack_twiddles (float *out /* kTwiddleFloats */);
 void rx_ssb_f32_pack_mask (const float *mask_re_im, float scale, float *out /* 2 * fft_len floats */);
-constexpr size_t kTwiddleFloats = 14 * 32 * 4;
+constexpr size_t kTwiddleFloats = 6 * 32 * 4;
 
 }  // namespace sl

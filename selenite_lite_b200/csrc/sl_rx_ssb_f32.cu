@@ -16,9 +16,10 @@
 //     The two sides meet through a double-buffered audio tile in shared memory and four named barriers.
 //   * every FFT lane carries TWO radix-8 butterflies and evaluates them together with packed FP32x2 instructions
 //     (FADD2 / FMUL2 / FFMA2, new on sm_100): half the FP32 issue slots of scalar code.
-//   * the biquad recurrence is evaluated time-parallel: lane k filters its own 48-sample run from a zero state, run end
-//     states are chained with a 5-step warp scan over 4x4 transition matrices, and the true start state is added back
-//     through the cascade's zero-input response (tables from sl_design.cpp).
+//   * the biquad recurrence is evaluated time-parallel: lane k filters the two 24-sample runs of its 48-sample AGC block
+//     from a zero state (both runs at once, packed FP32x2), block end states are chained with a 5-step warp scan over
+//     4x4 transition matrices, and the true start states are added back through the cascade's zero-input response
+//     (tables from sl_design.cpp).
 //   * a CTA owns (channel, segment of 8 tiles); segments of one channel are chained through 5 floats in global memory
 //     with a release/acquire flag. Items are dealt round-robin in segment-major order, so the flag is already set
 //     whenever at least as many channels as resident CTAs are in flight.
@@ -37,20 +38,25 @@ constexpr int kOvl = kN - kHop;                  // 128 carried frames
 constexpr int kFftWarps = 4;                     // = frames per tile
 constexpr int kTile = kHop * kFftWarps;          // 1536 frames
 constexpr int kThreads = 32 * (kFftWarps + 1);   // + the recurrence warp
-constexpr int kRunsPerTile = kTile / kRun;       // 32 lanes x 48 samples
-constexpr int kRunPad = kRun + 1;                // lane stride 49 words: conflict-free both ways
-constexpr int kTilesPerItem = 8;                 // tiles a CTA processes with the recurrence state in registers
-constexpr int kPlane = 544;                      // floats per re / im scratch plane: phys(511) + 1 = 542, rounded up
+constexpr int kBlocksPerTile = kTile / kAgcBlock; // 32 AGC blocks of 48 samples = one per recurrence lane
+constexpr int kBlkStride = 50;                   // words per block in the audio tile: 8-byte aligned, conflict-free for
+                                                 // the lane-per-block 64-bit reads (18 l mod 32 hits 16 distinct even banks)
+constexpr int kTilesPerItem = 16;                // tiles a CTA processes with the recurrence state in registers
+constexpr int kPlane = kN;                       // floats per re / im scratch plane (XOR swizzle: no padding)
 
-// shared-memory index of FFT point i inside a plane: pairs (2k, 2k+1) stay adjacent and 8-byte aligned; gathers are
-// conflict-free, the pass-0 and pass-1 scatters are 2-way (best of the family searched)
-__device__ __forceinline__ int phys (int i) { return i + 2 * (i >> 5); }
+// shared-memory index of FFT point i inside a plane. The LSU data pipe is the busiest unit of this kernel (ncu:
+// l1tex__data_pipe_lsu_wavefronts 84 % before this swizzle, half of all store wavefronts were bank conflicts), so the
+// layout is chosen to make every access pattern of the three passes conflict-free with 64-bit accesses: bits [4:1]
+// of the word index are XORed with bits [7:4]. Pairs (2k, 2k+1) stay adjacent and 8-byte aligned.
+__device__ __forceinline__ int phys (int i) { return i ^ (((i >> 4) & 15) << 1); }
 
 // ---- packed FP32x2: one 64-bit register pair holds the same quantity for butterfly A (lo) and butterfly B (hi) ----
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk (float lo, float hi) { u64 r; asm ("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ float lo_of (u64 a) { float x, y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return x; }
 __device__ __forceinline__ float hi_of (u64 a) { float x, y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return y; }
+__device__ __forceinline__ u64 pair_lo (u64 a, u64 b) { return pk (lo_of (a), lo_of (b)); }   // 2x2 transpose helpers
+__device__ __forceinline__ u64 pair_hi (u64 a, u64 b) { return pk (hi_of (a), hi_of (b)); }
 __device__ __forceinline__ u64 add2 (u64 a, u64 b) { u64 r; asm ("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 sub2 (u64 a, u64 b) { u64 r; asm ("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2 (u64 a, u64 b) { u64 r; asm ("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -94,7 +100,7 @@ struct KParams
   float *state; unsigned *flag;
   const float4 *masks;                          // [slot][r][lane] = (HrA, HrB, HiA, HiB) * 1/(512*32768)
   const uint8_t *mask_slot;
-  const float4 *twiddle;                        // [pass 1|2][r-1][lane] = (WrA, WrB, WiA, WiB)
+  const float4 *twiddle;                        // [pass 1|2][w, w^2, w^4][lane] = (WrA, WrB, WiA, WiB)
   unsigned flag_base;
   uint32_t channels, frames, tiles_per_channel, items_per_channel;
   float agc_target, agc_decay, agc_floor, agc_gmax;
@@ -105,6 +111,14 @@ __device__ __forceinline__ unsigned ld_acquire (const unsigned *p)
 {
   unsigned v;
   asm volatile ("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// polling load for the hand-over spin: coherent at GPU scope but WITHOUT acquire semantics, so the loop does not
+// invalidate the SM's L1 on every iteration (ld.acquire compiles to LDG.STRONG + CCTL.IVALL); one acquire follows.
+__device__ __forceinline__ unsigned ld_relaxed (const unsigned *p)
+{
+  unsigned v;
+  asm volatile ("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_release (unsigned *p, unsigned v)
@@ -131,6 +145,14 @@ __device__ __forceinline__ uint32_t pack_lr (float x_times_32768)
   short v;
   asm ("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(v) : "f"(x_times_32768));
   return __byte_perm ((uint32_t) (uint16_t) v, 0u, 0x1010);   // stereo endpoint, L = R
+}
+
+// streaming 8-byte load: read-only path, no L1 allocation (the 2 GB input must not evict masks and twiddles)
+__device__ __forceinline__ uint2 ld_stream (const uint2 *p)
+{
+  uint2 v;
+  asm volatile ("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
 }
 
 // work-list walk shared by both roles: CTA b takes items b, b + grid, ... (segment-major), each item = up to
@@ -176,23 +198,51 @@ __device__ __forceinline__ void load_frame_raw (const KParams &P, const TileIter
   for (int r = 0; r < 8; r++)
   {
     const int64_t t = ts + 2 * lane + 64 * r;
-    raw[r] = (t >= 0) ? __ldg (reinterpret_cast<const uint2 *> (in_c + t))
-                      : __ldg (reinterpret_cast<const uint2 *> (P.ovl_in + (size_t) it.c * kOvl + (t + kOvl)));
+    raw[r] = ld_stream (reinterpret_cast<const uint2 *> ((t >= 0) ? in_c + t : P.ovl_in + (size_t) it.c * kOvl + (t + kOvl)));
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // FFT warp: one overlap-save frame. re/im planes are this warp's private scratch.
 // ---------------------------------------------------------------------------------------------------------------
+// complex multiply of packed pairs, 4 packed instructions (ptxas folds the subtraction into an FFMA2 with a negated addend)
+__device__ __forceinline__ void cmul2 (u64 ar, u64 ai, u64 br, u64 bi, u64 &cr, u64 &ci)
+{
+  cr = sub2 (mul2 (ar, br), mul2 (ai, bi));
+  ci = fma2 (ar, bi, mul2 (ai, br));
+}
+
+// twiddle x[r] *= w^r, r = 1..7, from the three table entries w, w^2, w^4 (3 x 16-byte loads instead of 7: the
+// shared-memory pipe is the scarce resource, the FP32 pipe has room for the 4 extra complex products)
+__device__ __forceinline__ void twiddle8x2 (u64 *xr, u64 *xi, const float4 *tw3, int lane)
+{
+  const float4 t1 = tw3[lane], t2 = tw3[32 + lane], t4 = tw3[64 + lane];
+  const u64 w1r = pk (t1.x, t1.y), w1i = pk (t1.z, t1.w), w2r = pk (t2.x, t2.y), w2i = pk (t2.z, t2.w);
+  const u64 w4r = pk (t4.x, t4.y), w4i = pk (t4.z, t4.w);
+  u64 w3r, w3i, w5r, w5i, w6r, w6i, w7r, w7i;
+  cmul2 (w1r, w1i, w2r, w2i, w3r, w3i);
+  cmul2 (w1r, w1i, w4r, w4i, w5r, w5i);
+  cmul2 (w2r, w2i, w4r, w4i, w6r, w6i);
+  cmul2 (w3r, w3i, w4r, w4i, w7r, w7i);
+  cmul2 (xr[1], xi[1], w1r, w1i, xr[1], xi[1]);
+  cmul2 (xr[2], xi[2], w2r, w2i, xr[2], xi[2]);
+  cmul2 (xr[3], xi[3], w3r, w3i, xr[3], xi[3]);
+  cmul2 (xr[4], xi[4], w4r, w4i, xr[4], xi[4]);
+  cmul2 (xr[5], xi[5], w5r, w5i, xr[5], xi[5]);
+  cmul2 (xr[6], xi[6], w6r, w6i, xr[6], xi[6]);
+  cmul2 (xr[7], xi[7], w7r, w7i, xr[7], xi[7]);
+}
+
 __device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, float *sim, const float4 *tw, int lane)
 {
-  // entry: xr/xi hold the pass-0 butterfly outputs of j = 2*lane (lo) and 2*lane+1 (hi). Ns = 1 scatter: idx = 8 j + r.
+  // entry: xr/xi hold the pass-0 butterfly outputs of j = 2*lane (lo) and 2*lane+1 (hi). Ns = 1 scatter: idx = 8 j + r,
+  // i.e. outputs r, r+1 of ONE butterfly are neighbours: transpose 2x2 in registers and store 64 bits at a time
 #pragma unroll
-  for (int r = 0; r < 8; r++)
+  for (int r = 0; r < 8; r += 2)
   {
     const int ia = phys (16 * lane + r), ib = phys (16 * lane + 8 + r);
-    sre[ia] = lo_of (xr[r]); sim[ia] = lo_of (xi[r]);
-    sre[ib] = hi_of (xr[r]); sim[ib] = hi_of (xi[r]);
+    *reinterpret_cast<u64 *> (sre + ia) = pair_lo (xr[r], xr[r + 1]); *reinterpret_cast<u64 *> (sim + ia) = pair_lo (xi[r], xi[r + 1]);
+    *reinterpret_cast<u64 *> (sre + ib) = pair_hi (xr[r], xr[r + 1]); *reinterpret_cast<u64 *> (sim + ib) = pair_hi (xi[r], xi[r + 1]);
   }
   __syncwarp ();
   // pass 1 (Ns = 8): gather x[j + 64 r], twiddle W_64^{r (j & 7)}, butterfly, scatter to (j / 8) * 64 + (j & 7) + 8 r
@@ -202,15 +252,7 @@ __device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, fl
     const int i = phys (2 * lane + 64 * r);
     xr[r] = *reinterpret_cast<const u64 *> (sre + i); xi[r] = *reinterpret_cast<const u64 *> (sim + i);
   }
-#pragma unroll
-  for (int r = 1; r < 8; r++)
-  {
-    const float4 w = tw[(r - 1) * 32 + lane];
-    const u64 wr = pk (w.x, w.y), wi = pk (w.z, w.w);
-    const u64 nr = sub2 (mul2 (xr[r], wr), mul2 (xi[r], wi));           // xr wr - xi wi
-    xi[r] = fma2 (xr[r], wi, mul2 (xi[r], wr));                         // xr wi + xi wr
-    xr[r] = nr;
-  }
+  twiddle8x2 (xr, xi, tw, lane);
   dft8x2 (xr, xi);
   __syncwarp ();
   {
@@ -230,29 +272,26 @@ __device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, fl
     const int i = phys (2 * lane + 64 * r);
     xr[r] = *reinterpret_cast<const u64 *> (sre + i); xi[r] = *reinterpret_cast<const u64 *> (sim + i);
   }
-#pragma unroll
-  for (int r = 1; r < 8; r++)
-  {
-    const float4 w = tw[(7 + r - 1) * 32 + lane];
-    const u64 wr = pk (w.x, w.y), wi = pk (w.z, w.w);
-    const u64 nr = sub2 (mul2 (xr[r], wr), mul2 (xi[r], wi));
-    xi[r] = fma2 (xr[r], wi, mul2 (xi[r], wr));
-    xr[r] = nr;
-  }
+  twiddle8x2 (xr, xi, tw + 96, lane);
   dft8x2 (xr, xi);
   __syncwarp ();
 }
 
-__global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_constant__ KParams P)
+__global__ void __launch_bounds__ (kThreads, 4) rx_ssb_f32_kernel (const __grid_constant__ KParams P)
 {
   __shared__ __align__ (16) float sScratch[kFftWarps][2][kPlane];
-  __shared__ __align__ (16) float sAudio[2][kRunsPerTile * kRunPad];
-  __shared__ __align__ (16) float4 sTw[14 * 32];
+  __shared__ __align__ (16) float sAudio[2][kBlocksPerTile * kBlkStride];
+  __shared__ __align__ (16) float4 sTw[6 * 32];
   __shared__ __align__ (16) float sPeak[32];
   __shared__ float sEnv[32];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 14 * 32; i += kThreads) sTw[i] = P.twiddle[i];
+  const int tid = threadIdx.x, lane = tid & 31;
+  // Warp w of a CTA runs on scheduler (SMSP) w % 4, so a fixed "warp 4 = recurrence warp" would stack the recurrence
+  // warps of all resident CTAs on SMSP 0 (measured: that scheduler became the bottleneck). The role rotates with the
+  // CTA index instead; `warp` below is the FFT frame index (0..3) or kFftWarps for the recurrence role.
+  const int hw_warp = tid >> 5, rec_warp = (blockIdx.x + blockIdx.x / 148u) % (kFftWarps + 1);
+  const int warp = (hw_warp == rec_warp) ? kFftWarps : (hw_warp < rec_warp ? hw_warp : hw_warp - 1);
+  for (int i = tid; i < 6 * 32; i += kThreads) sTw[i] = P.twiddle[i];
   __syncthreads ();
 
   unsigned tile_seq = 0;                          // tiles this CTA has pushed through the audio double buffer
@@ -318,10 +357,11 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
 #pragma unroll
         for (int r = 2; r < 8; r++)
         {
-          const int n = warp * kHop + 2 * lane + 64 * (r - 2);                     // even; n and n+1 lie in the same run
-          const int pos = (n / kRun) * kRunPad + (n % kRun);
+          const int n = warp * kHop + 2 * lane + 64 * (r - 2);                     // even: n and n+1 share run and block
+          const int blk = n / kAgcBlock, i = n - blk * kAgcBlock, half = i / kRun, k = i - half * kRun;
+          const int pos = blk * kBlkStride + 2 * k + half;                         // runs A/B of a block are interleaved
           // (xr, xi) hold fft(swap Y): the wanted real part of the inverse transform is its imaginary component
-          a[pos] = lo_of (xi[r]); a[pos + 1] = hi_of (xi[r]);
+          a[pos] = lo_of (xi[r]); a[pos + 2] = hi_of (xi[r]);
         }
       }
       bar_arrive (1 + buf);
@@ -330,50 +370,69 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
   else
   {
     // ======================================= recurrence warp =======================================
+    // Lane l owns AGC block l of the tile (48 samples) as TWO runs of 24 evaluated together in packed FP32x2:
+    // lo = run A (samples 0..23 of the block), hi = run B (24..47).
     const float *cf = P.tab.coef;
+    u64 c2[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) c2[i] = pk (cf[i], cf[i]);
     const float decay = P.agc_decay;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, env = 0.f;                       // carried state (uniform across lanes)
     TileIter it; it.start (P);
     for (; it.valid; it.next (P), tile_seq++)
     {
       const uint32_t c = it.c, t0 = it.t0;
-      const int nruns = it.hops * (kHop / kRun);
+      const int nblk = it.hops * (kHop / kAgcBlock);
       const int buf = tile_seq & 1;
-      const float *run = sAudio[buf] + lane * kRunPad;
+      const float *blk = sAudio[buf] + lane * kBlkStride;
       bar_sync (1 + buf);                                                          // audio tile is complete
 
-      // zero-state response of the cascade over this lane's run; per-sample recurrences exactly as
+      // zero-state response of the cascade over both runs; per-sample recurrences as
       // arm_biquad_cascade_df2T_f32.c:551-562:  y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
-      float y[kRun];
-      float d1a = 0.f, d2a = 0.f, d1b = 0.f, d2b = 0.f;
+      // ((b1 x + d2) is formed before y is known, so each stage costs two dependent FMAs per sample)
+      u64 y[kRun];
+      u64 d1a = 0ull, d2a = 0ull, d1b = 0ull, d2b = 0ull;
 #pragma unroll
-      for (int n = 0; n < kRun; n++)
+      for (int k = 0; k < kRun; k++)
       {
-        const float x = run[n];
-        // (b1 x + d2) is formed before y is known, so each stage costs two dependent FMAs per sample
-        const float y0 = fmaf (cf[0], x, d1a);
-        d1a = fmaf (cf[3], y0, fmaf (cf[1], x, d2a));
-        d2a = fmaf (cf[4], y0, cf[2] * x);
-        const float y1 = fmaf (cf[5], y0, d1b);
-        d1b = fmaf (cf[8], y1, fmaf (cf[6], y0, d2b));
-        d2b = fmaf (cf[9], y1, cf[7] * y0);
-        y[n] = y1;
+        const u64 x = *reinterpret_cast<const u64 *> (blk + 2 * k);
+        const u64 y0 = fma2 (c2[0], x, d1a);
+        d1a = fma2 (c2[3], y0, fma2 (c2[1], x, d2a));
+        d2a = fma2 (c2[4], y0, mul2 (c2[2], x));
+        const u64 y1 = fma2 (c2[5], y0, d1b);
+        d1b = fma2 (c2[8], y1, fma2 (c2[6], y0, d2b));
+        d2b = fma2 (c2[9], y1, mul2 (c2[7], y0));
+        y[k] = y1;
       }
       __syncwarp ();
       bar_arrive (3 + buf);                                                        // the audio tile now lives in registers
       if (it.tl == 0)
       {
         // state of the previous segment of this channel (segment-major dealing makes the wait a formality)
-        if (lane == 0) { const unsigned want = P.flag_base + it.seg; while (ld_acquire (P.flag + c) != want) __nanosleep (64); }
+        if (lane == 0)
+        {
+          const unsigned want = P.flag_base + it.seg;
+          while (ld_relaxed (P.flag + c) != want) __nanosleep (32);
+          (void) ld_acquire (P.flag + c);
+        }
         __syncwarp ();
         const float *stc = P.state + (size_t) c * 8;
         s0 = __ldcg (stc + 0); s1 = __ldcg (stc + 1); s2 = __ldcg (stc + 2); s3 = __ldcg (stc + 3); env = __ldcg (stc + 4);
       }
-      // end state of run k given all earlier runs: z_k = zs_k + M z_{k-1}; lane 0 folds the carried state in
-      float z0 = d1a, z1 = d2a, z2 = d1b, z3 = d2b;
-      if (lane == 0)
+      // zero-start end state of the whole block: zB + M24 zA
+      const float a0 = lo_of (d1a), a1 = lo_of (d2a), a2 = lo_of (d1b), a3 = lo_of (d2b);
+      float z0, z1, z2, z3;
       {
         const float *M = P.tab.Mpow[0];
+        z0 = hi_of (d1a) + (M[0] * a0 + M[1] * a1 + M[2] * a2 + M[3] * a3);
+        z1 = hi_of (d2a) + (M[4] * a0 + M[5] * a1 + M[6] * a2 + M[7] * a3);
+        z2 = hi_of (d1b) + (M[8] * a0 + M[9] * a1 + M[10] * a2 + M[11] * a3);
+        z3 = hi_of (d2b) + (M[12] * a0 + M[13] * a1 + M[14] * a2 + M[15] * a3);
+      }
+      // end state of block l given all earlier blocks: z_l = zs_l + M48 z_{l-1}; lane 0 folds the carried state in
+      if (lane == 0)
+      {
+        const float *M = P.tab.Mpow[1];
         z0 += M[0] * s0 + M[1] * s1 + M[2] * s2 + M[3] * s3;
         z1 += M[4] * s0 + M[5] * s1 + M[6] * s2 + M[7] * s3;
         z2 += M[8] * s0 + M[9] * s1 + M[10] * s2 + M[11] * s3;
@@ -383,7 +442,7 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
       for (int k = 0; k < 5; k++)
       {
         const int d = 1 << k;
-        const float *M = P.tab.Mpow[k];
+        const float *M = P.tab.Mpow[k + 1];
         const float p0 = __shfl_up_sync (0xffffffffu, z0, d), p1 = __shfl_up_sync (0xffffffffu, z1, d);
         const float p2 = __shfl_up_sync (0xffffffffu, z2, d), p3 = __shfl_up_sync (0xffffffffu, z3, d);
         if (lane >= d)
@@ -394,26 +453,36 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
           z3 += M[12] * p0 + M[13] * p1 + M[14] * p2 + M[15] * p3;
         }
       }
-      // start state of this lane's run = end state of the previous run
+      // start state of run A = end state of the previous block; of run B = zA + M24 (start of A)
       float b0 = __shfl_up_sync (0xffffffffu, z0, 1), b1 = __shfl_up_sync (0xffffffffu, z1, 1);
       float b2 = __shfl_up_sync (0xffffffffu, z2, 1), b3 = __shfl_up_sync (0xffffffffu, z3, 1);
       if (lane == 0) { b0 = s0; b1 = s1; b2 = s2; b3 = s3; }
-      // carried state for the next tile = end state of the last run
-      s0 = __shfl_sync (0xffffffffu, z0, nruns - 1); s1 = __shfl_sync (0xffffffffu, z1, nruns - 1);
-      s2 = __shfl_sync (0xffffffffu, z2, nruns - 1); s3 = __shfl_sync (0xffffffffu, z3, nruns - 1);
-
-      float peak = 0.f;
-#pragma unroll
-      for (int n = 0; n < kRun; n++)
+      u64 q0, q1, q2, q3;
       {
-        y[n] += P.tab.Cresp[n][0] * b0 + P.tab.Cresp[n][1] * b1 + P.tab.Cresp[n][2] * b2 + P.tab.Cresp[n][3] * b3;
-        peak = fmaxf (peak, fabsf (y[n]));                                         // arm_abs_f32 + arm_max_f32
+        const float *M = P.tab.Mpow[0];
+        q0 = pk (b0, a0 + (M[0] * b0 + M[1] * b1 + M[2] * b2 + M[3] * b3));
+        q1 = pk (b1, a1 + (M[4] * b0 + M[5] * b1 + M[6] * b2 + M[7] * b3));
+        q2 = pk (b2, a2 + (M[8] * b0 + M[9] * b1 + M[10] * b2 + M[11] * b3));
+        q3 = pk (b3, a3 + (M[12] * b0 + M[13] * b1 + M[14] * b2 + M[15] * b3));
+      }
+      // carried state for the next tile = end state of the last block
+      s0 = __shfl_sync (0xffffffffu, z0, nblk - 1); s1 = __shfl_sync (0xffffffffu, z1, nblk - 1);
+      s2 = __shfl_sync (0xffffffffu, z2, nblk - 1); s3 = __shfl_sync (0xffffffffu, z3, nblk - 1);
+
+      // add the zero-input response of the true start states; block peak (arm_abs_f32 + arm_max_f32)
+      float pk0 = 0.f, pk1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRun; k++)
+      {
+        const float *C = P.tab.Cresp[k];
+        y[k] = fma2 (pk (C[0], C[0]), q0, fma2 (pk (C[1], C[1]), q1, fma2 (pk (C[2], C[2]), q2, fma2 (pk (C[3], C[3]), q3, y[k]))));
+        pk0 = fmaxf (pk0, fabsf (lo_of (y[k]))); pk1 = fmaxf (pk1, fabsf (hi_of (y[k])));
       }
       // AGC envelope: sequential over blocks in exactly the oracle's order. Every lane walks the same
       // chain from the block peaks (shared memory, broadcast reads) and drops each step where its owner picks it up.
-      sPeak[lane] = peak;
+      sPeak[lane] = fmaxf (pk0, pk1);
       __syncwarp ();
-      for (int q = 0; q < nruns; q += 4)
+      for (int q = 0; q < nblk; q += 4)
       {
         const float4 p4 = *reinterpret_cast<const float4 *> (&sPeak[q]);
         env = fmaxf (p4.x, env * decay); sEnv[q] = env;
@@ -424,21 +493,24 @@ __global__ void __launch_bounds__ (kThreads) rx_ssb_f32_kernel (const __grid_con
       __syncwarp ();
       const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (sEnv[lane], P.agc_floor)), P.agc_gmax);
       __syncwarp ();
-      if (lane < nruns)
+      if (lane < nblk)
       {
         if (P.audio_dbg)
         {
-          float *adbg = P.audio_dbg + (size_t) c * P.frames + t0 + lane * kRun;
+          float *adbg = P.audio_dbg + (size_t) c * P.frames + t0 + lane * kAgcBlock;
 #pragma unroll
-          for (int n = 0; n < kRun; n++) adbg[n] = y[n];
+          for (int k = 0; k < kRun; k++) { adbg[k] = lo_of (y[k]); adbg[kRun + k] = hi_of (y[k]); }
         }
-        if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kRun) + t0 / kRun + lane] = g;
-        // gain (arm_scale_f32), pack (arm_float_to_q15) and store: the lane's run is 192 contiguous bytes
+        if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kAgcBlock) + t0 / kAgcBlock + lane] = g;
+        // gain (arm_scale_f32), pack (arm_float_to_q15) and store: the lane's block is 192 contiguous bytes
         const float g15 = g * 32768.0f;                                           // exact: power of two
-        uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + t0 + lane * kRun);
+        uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + t0 + lane * kAgcBlock);
 #pragma unroll
-        for (int n = 0; n < kRun; n += 4)
-          dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
+        for (int k = 0; k < kRun; k += 4)
+        {
+          dst[k / 4] = make_uint4 (pack_lr (lo_of (y[k]) * g15), pack_lr (lo_of (y[k + 1]) * g15), pack_lr (lo_of (y[k + 2]) * g15), pack_lr (lo_of (y[k + 3]) * g15));
+          dst[(kRun + k) / 4] = make_uint4 (pack_lr (hi_of (y[k]) * g15), pack_lr (hi_of (y[k + 1]) * g15), pack_lr (hi_of (y[k + 2]) * g15), pack_lr (hi_of (y[k + 3]) * g15));
+        }
       }
       if (it.tl == it.ntiles - 1 && lane == 0)
       {
@@ -461,21 +533,22 @@ uint32_t rx_ssb_f32_tiles (uint32_t frames)
   return (tiles + kTilesPerItem - 1) / kTilesPerItem;
 }
 
-// twiddles in the per-lane packed layout the kernel reads with one 16-byte load: [pass][r-1][lane] = (WrA, WrB, WiA, WiB)
-// for the lane's butterflies jA = 2 lane, jB = 2 lane + 1; pass 1: W_64^{r (j & 7)}, pass 2: W_512^{r j}
-void rx_ssb_f32_pack_twiddles (float *out /* 14*32*4 */)
+// twiddles in the per-lane packed layout the kernel reads with one 16-byte load: [pass][e][lane] = (WrA, WrB, WiA, WiB)
+// for the lane's butterflies jA = 2 lane, jB = 2 lane + 1 and the powers w^1, w^2, w^4 (e = 0, 1, 2) of the
+// butterfly's base twiddle; pass 1: w = W_64^{j & 7}, pass 2: w = W_512^{j}
+void rx_ssb_f32_pack_twiddles (float *out /* kTwiddleFloats */)
 {
   const double two_pi = 6.283185307179586476925286766559;
   for (int pass = 0; pass < 2; pass++)
-    for (int r = 1; r < 8; r++)
+    for (int e = 0; e < 3; e++)
       for (int lane = 0; lane < 32; lane++)
       {
-        float *o = out + ((pass * 7 + (r - 1)) * 32 + lane) * 4;
+        float *o = out + ((pass * 3 + e) * 32 + lane) * 4;
         for (int b = 0; b < 2; b++)
         {
-          const int j = 2 * lane + b;
-          const int e = (pass == 0) ? (r * (j & 7) * 8) % kN : (r * j) % kN;
-          const double a = -two_pi * (double) e / (double) kN;
+          const int j = 2 * lane + b, r = 1 << e;
+          const int ex = (pass == 0) ? (r * (j & 7) * 8) % kN : (r * j) % kN;
+          const double a = -two_pi * (double) ex / (double) kN;
           o[b] = (float) std::cos (a); o[2 + b] = (float) std::sin (a);
         }
       }
