@@ -115,6 +115,55 @@ int slb_state_size (const slb_ctx *ctx, size_t *bytes);
 int slb_state_save (slb_ctx *ctx, void *host_buf, size_t bytes);
 int slb_state_load (slb_ctx *ctx, const void *host_buf, size_t bytes);
 
+/* ---- stage library: the CMSIS-DSP routines SURVEY.md §8(a) lists as stages of the path, batched, unfused ----
+ * Array pointers are DEVICE pointers laid out [channels][n] (complex: interleaved re,im, n = complex count); coefficient
+ * pointers are HOST pointers; `hist` / `state` are caller-owned DEVICE buffers that carry what the CMSIS instance would:
+ * FIR hist = the first ntaps-1 state entries (interpolator: ntaps/L - 1) per channel; biquad state = the CMSIS layout
+ * per channel (df2T 2/stage, stereo df2T 4/stage, df1 4/stage). `stream` is a cudaStream_t or NULL. Reference for each
+ * name: Drivers/CMSIS/DSP/Source/<group>/arm_<name>.c. Integer routines are bit-exact; so are the sequential float ones. */
+int slb_st_q15_to_float (slb_ctx *ctx, const int16_t *src, float *dst, uint32_t n, void *stream);
+int slb_st_float_to_q15 (slb_ctx *ctx, const float *src, int16_t *dst, uint32_t n, void *stream);
+int slb_st_scale_f32 (slb_ctx *ctx, const float *src, float scale, float *dst, uint32_t n, void *stream);
+int slb_st_mult_f32 (slb_ctx *ctx, const float *a, const float *b, float *dst, uint32_t n, void *stream);
+int slb_st_add_f32 (slb_ctx *ctx, const float *a, const float *b, float *dst, uint32_t n, void *stream);
+int slb_st_sub_f32 (slb_ctx *ctx, const float *a, const float *b, float *dst, uint32_t n, void *stream);
+int slb_st_abs_f32 (slb_ctx *ctx, const float *a, float *dst, uint32_t n, void *stream);
+int slb_st_scale_q15 (slb_ctx *ctx, const int16_t *src, int16_t scale_fract, int32_t shift, int16_t *dst, uint32_t n, void *stream);
+int slb_st_add_q15 (slb_ctx *ctx, const int16_t *a, const int16_t *b, int16_t *dst, uint32_t n, void *stream);
+int slb_st_sub_q15 (slb_ctx *ctx, const int16_t *a, const int16_t *b, int16_t *dst, uint32_t n, void *stream);
+int slb_st_abs_q15 (slb_ctx *ctx, const int16_t *a, int16_t *dst, uint32_t n, void *stream);
+int slb_st_shift_q15 (slb_ctx *ctx, const int16_t *a, int32_t shift, int16_t *dst, uint32_t n, void *stream);
+int slb_st_cmplx_mult_cmplx_f32 (slb_ctx *ctx, const float *a, const float *b, float *dst, uint32_t n, void *stream);
+int slb_st_cmplx_mult_real_f32 (slb_ctx *ctx, const float *a, const float *r, float *dst, uint32_t n, void *stream);
+int slb_st_cmplx_conj_f32 (slb_ctx *ctx, const float *a, float *dst, uint32_t n, void *stream);
+int slb_st_cmplx_mag_f32 (slb_ctx *ctx, const float *a, float *dst, uint32_t n, void *stream);
+int slb_st_cmplx_mag_squared_f32 (slb_ctx *ctx, const float *a, float *dst, uint32_t n, void *stream);
+int slb_st_cmplx_mag_q15 (slb_ctx *ctx, const int16_t *a, int16_t *dst, uint32_t n, void *stream);
+int slb_st_sin_f32 (slb_ctx *ctx, const float *x, float *dst, uint32_t n, void *stream);
+int slb_st_cos_f32 (slb_ctx *ctx, const float *x, float *dst, uint32_t n, void *stream);
+int slb_st_fir_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ntaps, float *hist, const float *src, float *dst, uint32_t n, void *stream);
+int slb_st_fir_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream);
+int slb_st_fir_fast_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream);
+int slb_st_fir_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t ntaps, int32_t *hist, const int32_t *src, int32_t *dst, uint32_t n, void *stream);
+int slb_st_fir_decimate_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ntaps, uint32_t M, float *hist, const float *src, float *dst, uint32_t n, void *stream);
+int slb_st_fir_decimate_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, uint32_t M, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream);
+int slb_st_fir_interpolate_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ntaps, uint32_t L, float *hist, const float *src, float *dst, uint32_t n, void *stream);
+int slb_st_fir_interpolate_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, uint32_t L, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream);
+int slb_st_biquad_df2T_f32 (slb_ctx *ctx, const float *coeffs, uint32_t n_stages, float *state, const float *src, float *dst, uint32_t n, void *stream);
+int slb_st_biquad_stereo_df2T_f32 (slb_ctx *ctx, const float *coeffs, uint32_t n_stages, float *state, const float *src, float *dst, uint32_t nframes, void *stream);
+int slb_st_biquad_df1_f32 (slb_ctx *ctx, const float *coeffs, uint32_t n_stages, float *state, const float *src, float *dst, uint32_t n, void *stream);
+int slb_st_biquad_df1_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t n_stages, int32_t postshift, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, void *stream);
+int slb_st_biquad_df1_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t n_stages, int32_t postshift, int32_t *state, const int32_t *src, int32_t *dst, uint32_t n, void *stream);
+/* per-block statistics: out is [channels][n / block]; idx (may be NULL) receives the position of the maximum */
+int slb_st_max_f32 (slb_ctx *ctx, const float *src, uint32_t n, uint32_t block, float *out, uint32_t *idx, void *stream);
+int slb_st_rms_f32 (slb_ctx *ctx, const float *src, uint32_t n, uint32_t block, float *out, void *stream);
+int slb_st_power_f32 (slb_ctx *ctx, const float *src, uint32_t n, uint32_t block, float *out, void *stream);
+int slb_st_mean_f32 (slb_ctx *ctx, const float *src, uint32_t n, uint32_t block, float *out, void *stream);
+int slb_st_max_q15 (slb_ctx *ctx, const int16_t *src, uint32_t n, uint32_t block, int16_t *out, uint32_t *idx, void *stream);
+int slb_st_rms_q15 (slb_ctx *ctx, const int16_t *src, uint32_t n, uint32_t block, int16_t *out, void *stream);
+/* batched arm_cfft_f32 (bit-reversed output order is not offered): data [channels][count][2*N] floats, in place */
+int slb_st_cfft_f32 (slb_ctx *ctx, float *data, uint32_t N, uint32_t count, int ifft, void *stream);
+
 /* ---- host-only logic, callable without a GPU (unit tests of the index arithmetic and the scan tables) ----
  * One firmware ring's pointer logic, Core/Src/dsp_if.c:116-180, :204-219, :250-301, :310-340. state = {enable, rd, wr}
  * is updated in place; the return value is the ring slot of the first frame moved (a write stores frames+1 slots:

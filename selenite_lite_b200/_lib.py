@@ -1,6 +1,7 @@
 """ctypes binding of include/selenite_b200.h. Loading fails loudly: there is no Python or CPU fallback."""
 import ctypes as C
 import os
+import re
 
 from . import build as _build
 
@@ -18,54 +19,38 @@ class RxF32Params(C.Structure):
                 ("agc_target", C.c_float), ("agc_decay", C.c_float), ("agc_floor", C.c_float), ("agc_gmax", C.c_float)]
 
 
-# every symbol include/selenite_b200.h declares: name -> (restype, argtypes)
+# every symbol include/selenite_b200.h declares: name -> (restype, argtypes), derived from the header text so the
+# binding cannot drift from the ABI
 _P = C.c_void_p
-SYMBOLS = {
-    "slb_create": (C.c_int, [C.POINTER(Config), C.POINTER(_P)]),
-    "slb_destroy": (None, [_P]),
-    "slb_last_error": (C.c_char_p, [_P]),
-    "slb_version": (C.c_char_p, []),
-    "slb_default_rx_f32_params": (C.c_int, [C.c_uint32, C.POINTER(RxF32Params)]),
-    "slb_default_mask": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint8, _P]),
-    "slb_set_rx_f32_params": (C.c_int, [_P, C.POINTER(RxF32Params)]),
-    "slb_get_rx_f32_params": (C.c_int, [_P, C.POINTER(RxF32Params)]),
-    "slb_set_mask": (C.c_int, [_P, C.c_uint8, _P]),
-    "slb_get_mask": (C.c_int, [_P, C.c_uint8, _P]),
-    "SLB_DSP_Init": (C.c_int, [_P]),
-    "SLB_DSP_Set_RX": (C.c_int, [_P]),
-    "SLB_DSP_Set_TX": (C.c_int, [_P]),
-    "SLB_DSP_Set_Mode": (C.c_int, [_P, C.c_uint8]),
-    "SLB_DSP_Set_Mode_Channel": (C.c_int, [_P, C.c_uint32, C.c_uint8]),
-    "SLB_DSP_In_Buff_Write": (C.c_int, [_P, _P, C.c_uint16]),
-    "SLB_DSP_In_Buff_Read": (C.c_int, [_P, _P, C.c_uint32]),
-    "SLB_DSP_Out_Buff_Write": (C.c_int, [_P, _P, C.c_uint32]),
-    "SLB_DSP_Out_Buff_Read": (C.c_int, [_P, _P, C.c_uint16]),
-    "SLB_DSP_Out_Buff_Mute": (C.c_int, [_P]),
-    "slb_ring_get_ptrs": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint32 * 3)]),
-    "slb_ring_get_iq": (C.c_int, [_P, C.c_int, _P, _P]),
-    "slb_rx_process_device": (C.c_int, [_P, _P, _P, C.c_uint32, _P]),
-    "slb_rx_process_host": (C.c_int, [_P, _P, _P, C.c_uint32]),
-    "slb_rx_set_debug_taps": (C.c_int, [_P, _P, _P]),
-    "slb_state_size": (C.c_int, [_P, C.POINTER(C.c_size_t)]),
-    "slb_state_save": (C.c_int, [_P, _P, C.c_size_t]),
-    "slb_state_load": (C.c_int, [_P, _P, C.c_size_t]),
-    "slb_ring_plan_write": (C.c_uint32, [C.c_uint32, C.c_int, C.POINTER(C.c_uint32 * 3), C.c_uint32]),
-    "slb_ring_plan_read": (C.c_uint32, [C.c_uint32, C.c_int, C.POINTER(C.c_uint32 * 3), C.c_uint32]),
-    "slb_biquad_scan_tables": (C.c_int, [_P, _P, _P]),
-    "slb_kernel_launches": (C.c_uint64, [_P]),
-    "slb_sync": (C.c_int, [_P]),
-    "DSP_Init": (None, []),
-    "DSP_Set_RX": (None, []),
-    "DSP_Set_TX": (None, []),
-    "DSP_Set_Mode": (None, [C.c_uint8]),
-    "DSP_In_Buff_Write": (None, [_P, C.c_uint16]),
-    "DSP_In_Buff_Read": (None, [_P, C.c_uint32]),
-    "DSP_Out_Buff_Write": (None, [_P, C.c_uint32]),
-    "DSP_Out_Buff_Read": (None, [_P, C.c_uint16]),
-    "DSP_Out_Buff_Mute": (None, []),
-    "slb_dropin_status": (C.c_int, []),
-    "slb_dropin_ctx": (_P, []),
-}
+_SCALARS = {"int": C.c_int, "int8_t": C.c_int8, "uint8_t": C.c_uint8, "int16_t": C.c_int16, "uint16_t": C.c_uint16,
+            "int32_t": C.c_int32, "uint32_t": C.c_uint32, "uint64_t": C.c_uint64, "size_t": C.c_size_t, "float": C.c_float}
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "selenite_b200.h")
+
+
+def _ctype(decl, is_return=False):
+    decl = decl.strip()
+    if decl in ("void", ""):
+        return None
+    if "*" in decl or "[" in decl:
+        return C.c_char_p if (is_return and "char" in decl) else _P
+    base = decl.replace("const", "").split()[0]
+    return _SCALARS[base]
+
+
+def _parse_header():
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ ]*?[ \*]+)([A-Za-z_][A-Za-z0-9_]*)\s*\(([^;{}()]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        if "typedef" in ret:
+            continue
+        argt = [] if args.strip() in ("void", "") else [_ctype(a) for a in args.split(",")]
+        out[name] = (_ctype(ret, True), argt)
+    return out
+
+
+SYMBOLS = _parse_header()
 
 
 def lib_path():

@@ -48,6 +48,9 @@ struct slb_ctx
   // chain at the 1 ms cadence: accumulate `hop` frames, process, feed the ring from the previous super-block
   int16_t *d_acc = nullptr; int16_t *d_proc[2] = { nullptr, nullptr }; uint32_t acc_fill = 0; int proc_cur = 0;
 
+  // scratch for the stage library (coefficients, FIR history double buffer)
+  void *d_scratch = nullptr; size_t scratch_bytes = 0;
+
   // host bulk path
   int16_t *d_bulk_in[kBulkSlots] = {}; int16_t *d_bulk_out[kBulkSlots] = {}; size_t bulk_bytes = 0;
   cudaStream_t bulk_stream[kBulkSlots] = {}; cudaEvent_t bulk_done[kBulkSlots] = {};
@@ -63,6 +66,23 @@ struct slb_ctx
   } while (0)
 
 static int fail (slb_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; else g_create_error = msg; return code; }
+
+namespace sl {
+int ctx_device (const slb_ctx *ctx) { return ctx->cfg.device; }
+size_t ctx_channels (const slb_ctx *ctx) { return ctx->cfg.channels; }
+int ctx_fail (slb_ctx *ctx, int code, const char *msg) { return fail (ctx, code, msg); }
+void ctx_count_launch (slb_ctx *ctx, unsigned n) { ctx->launches += n; }
+void *ctx_scratch (slb_ctx *ctx, size_t bytes)
+{
+  if (bytes <= ctx->scratch_bytes) return ctx->d_scratch;
+  cudaDeviceSynchronize ();
+  cudaFree (ctx->d_scratch); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0;
+  const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+  if (cudaMalloc (&ctx->d_scratch, want) != cudaSuccess) { ctx->err = "scratch allocation failed"; return nullptr; }
+  ctx->scratch_bytes = want;
+  return ctx->d_scratch;
+}
+}  // namespace sl
 
 static int upload_chain_constants (slb_ctx *ctx)
 {
@@ -166,7 +186,7 @@ void slb_destroy (slb_ctx *ctx)
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
-  cudaFree (ctx->d_blk); cudaFree (ctx->d_acc);
+  cudaFree (ctx->d_blk); cudaFree (ctx->d_acc); cudaFree (ctx->d_scratch);
   for (int s = 0; s < kBulkSlots; s++)
   {
     cudaFree (ctx->d_bulk_in[s]); cudaFree (ctx->d_bulk_out[s]);

@@ -84,4 +84,11 @@ void rx_ssb_f32_pack_twiddles (float *out /* kTwiddleFloats */);
 void rx_ssb_f32_pack_mask (const float *mask_re_im, float scale, float *out /* 2 * fft_len floats */);
 constexpr size_t kTwiddleFloats = 6 * 32 * 4;
 
+// ---- context accessors for translation units that do not see the struct (sl_stages.cu, sl_chains.cu) ----
+int ctx_device (const slb_ctx *ctx);
+size_t ctx_channels (const slb_ctx *ctx);
+int ctx_fail (slb_ctx *ctx, int code, const char *msg);
+void ctx_count_launch (slb_ctx *ctx, unsigned n = 1);
+void *ctx_scratch (slb_ctx *ctx, size_t bytes);     // device scratch owned by the context, grown on demand (nullptr + error on failure)
+
 }  // namespace sl

@@ -163,6 +163,18 @@ class DspIf:
         self._ck(self.lib.slb_rx_set_debug_taps(self.h, audio.data_ptr() if audio is not None else None,
                                                 gain.data_ptr() if gain is not None else None), "set_debug_taps")
 
+    # ---- stage library (slb_st_*): torch CUDA tensors = device arrays [channels][n], numpy arrays = host coefficients ----
+    def st(self, name, *args, stream=None):
+        conv, keep = [], []
+        for a in args:
+            if isinstance(a, np.ndarray):
+                a = np.ascontiguousarray(a); keep.append(a); conv.append(a.ctypes.data)
+            elif hasattr(a, "data_ptr"):
+                assert a.is_cuda and a.is_contiguous(); conv.append(a.data_ptr())
+            else:
+                conv.append(a)
+        self._ck(getattr(self.lib, "slb_st_" + name)(self.h, *conv, stream), "slb_st_" + name)
+
     # ---- checkpoint ----
     def state_save(self):
         n = C.c_size_t()

@@ -1,0 +1,212 @@
+"""GPU parity of the batched stage library (slb_st_*) against the oracle, routine by routine, through the C ABI.
+Integer routines and the sequential float routines: bit-exact. FFT: 2e-6 of output RMS."""
+import numpy as np
+import pytest
+
+import selenite_lite_b200 as slb
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+C, B, NB = 3, 48, 7
+N = B * NB
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return slb.DspIf(C, chain=slb.CHAIN_PASS)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def q15(rng, *shape, amp=32767):
+    return rng.integers(-amp, amp + 1, shape).astype(np.int16)
+
+
+def f32(rng, *shape, amp=1.0):
+    return (rng.standard_normal(shape) * amp).astype(np.float32)
+
+
+def test_elementwise_float(ctx, best_oracle, rng):
+    a, b = f32(rng, C, N), f32(rng, C, N)
+    o = best_oracle
+    for name, args, exp in (
+        ("scale_f32", (dev(a), 0.37), lambda: np.stack([o.scale_f32(a[c], 0.37) for c in range(C)])),
+        ("mult_f32", (dev(a), dev(b)), lambda: np.stack([o.mult_f32(a[c], b[c]) for c in range(C)])),
+        ("add_f32", (dev(a), dev(b)), lambda: np.stack([o.add_f32(a[c], b[c]) for c in range(C)])),
+        ("sub_f32", (dev(a), dev(b)), lambda: np.stack([o.sub_f32(a[c], b[c]) for c in range(C)])),
+        ("abs_f32", (dev(a),), lambda: np.stack([o.abs_f32(a[c]) for c in range(C)])),
+    ):
+        d = torch.zeros((C, N), dtype=torch.float32, device="cuda")
+        ctx.st(name, *args, d, N)
+        assert np.array_equal(d.cpu().numpy(), exp()), name
+
+
+def test_conversions(ctx, best_oracle, rng):
+    x = q15(rng, C, N); x[0, :4] = [-32768, 32767, 0, -1]
+    d = torch.zeros((C, N), dtype=torch.float32, device="cuda")
+    ctx.st("q15_to_float", dev(x), d, N)
+    assert np.array_equal(d.cpu().numpy(), best_oracle.q15_to_float(x))
+    f = f32(rng, C, N, amp=0.6); f[1, :6] = [1.5, -1.5, 0.99999, -1.0, 3.05e-5, -3.05e-5]
+    q = torch.zeros((C, N), dtype=torch.int16, device="cuda")
+    ctx.st("float_to_q15", dev(f), q, N)
+    assert np.array_equal(q.cpu().numpy(), best_oracle.float_to_q15(f))
+
+
+def test_elementwise_q15(ctx, best_oracle, rng):
+    a, b = q15(rng, C, N), q15(rng, C, N); a[0, :4] = [-32768, 32767, 0, -1]
+    o = best_oracle
+    d = torch.zeros((C, N), dtype=torch.int16, device="cuda")
+    for k, sh in ((12345, 0), (-32768, 1), (32767, 3), (700, -2)):
+        ctx.st("scale_q15", dev(a), k, sh, d, N)
+        assert np.array_equal(d.cpu().numpy(), np.stack([o.scale_q15(a[c], k, sh) for c in range(C)])), (k, sh)
+    for name in ("add_q15", "sub_q15"):
+        ctx.st(name, dev(a), dev(b), d, N)
+        assert np.array_equal(d.cpu().numpy(), np.stack([getattr(o, name)(a[c], b[c]) for c in range(C)])), name
+    ctx.st("abs_q15", dev(a), d, N)
+    assert np.array_equal(d.cpu().numpy(), np.stack([o.abs_q15(a[c]) for c in range(C)]))
+    for sh in (-3, 0, 2):
+        ctx.st("shift_q15", dev(a), sh, d, N)
+        assert np.array_equal(d.cpu().numpy(), np.stack([o.shift_q15(a[c], sh) for c in range(C)])), sh
+
+
+def test_complex_math(ctx, best_oracle, rng):
+    a, b = f32(rng, C, 2 * N), f32(rng, C, 2 * N); r = f32(rng, C, N)
+    o = best_oracle
+    d2 = torch.zeros((C, 2 * N), dtype=torch.float32, device="cuda"); d1 = torch.zeros((C, N), dtype=torch.float32, device="cuda")
+    ctx.st("cmplx_mult_cmplx_f32", dev(a), dev(b), d2, N)
+    assert np.array_equal(d2.cpu().numpy(), np.stack([o.cmplx_mult_cmplx_f32(a[c], b[c]) for c in range(C)]))
+    ctx.st("cmplx_mult_real_f32", dev(a), dev(r), d2, N)
+    assert np.array_equal(d2.cpu().numpy(), np.stack([o.cmplx_mult_real_f32(a[c], r[c]) for c in range(C)]))
+    ctx.st("cmplx_conj_f32", dev(a), d2, N)
+    assert np.array_equal(d2.cpu().numpy(), np.stack([o.cmplx_conj_f32(a[c]) for c in range(C)]))
+    for name in ("cmplx_mag_f32", "cmplx_mag_squared_f32"):
+        ctx.st(name, dev(a), d1, N)
+        assert np.array_equal(d1.cpu().numpy(), np.stack([getattr(o, name)(a[c]) for c in range(C)])), name
+    q = q15(rng, C, 2 * N); dq = torch.zeros((C, N), dtype=torch.int16, device="cuda")
+    ctx.st("cmplx_mag_q15", dev(q), dq, N)
+    assert np.array_equal(dq.cpu().numpy(), np.stack([o.cmplx_mag_q15(q[c]) for c in range(C)]))
+
+
+def test_sin_cos_table(ctx, best_oracle, rng):
+    x = (rng.random((C, N)) * 40 - 20).astype(np.float32); x[0, :3] = [0, -1e-7, 6.2831855]
+    d = torch.zeros((C, N), dtype=torch.float32, device="cuda")
+    ctx.st("sin_f32", dev(x), d, N)
+    assert np.array_equal(d.cpu().numpy(), best_oracle.sin_f32(x.reshape(-1)).reshape(C, N))
+    ctx.st("cos_f32", dev(x), d, N)
+    assert np.array_equal(d.cpu().numpy(), best_oracle.cos_f32(x.reshape(-1)).reshape(C, N))
+
+
+@pytest.mark.parametrize("name,dt,ntaps", [("fir_f32", np.float32, 64), ("fir_f32", np.float32, 129), ("fir_q15", np.int16, 64),
+                                           ("fir_fast_q15", np.int16, 64), ("fir_q31", np.int32, 32)])
+def test_fir_family_bit_exact_with_carried_state(ctx, best_oracle, rng, name, dt, ntaps):
+    if dt == np.float32:
+        c, x = f32(rng, ntaps, amp=0.1), f32(rng, C, 2 * N)
+    elif dt == np.int16:
+        c, x = q15(rng, ntaps, amp=6000), q15(rng, C, 2 * N)
+    else:
+        c = rng.integers(-2**28, 2**28, ntaps).astype(np.int32); x = rng.integers(-2**31, 2**31 - 1, (C, 2 * N)).astype(np.int32)
+    tdt = {np.float32: torch.float32, np.int16: torch.int16, np.int32: torch.int32}[dt]
+    hist = torch.zeros((C, ntaps - 1), dtype=tdt, device="cuda")
+    outs = []
+    for part in (x[:, :N], x[:, N:]):                       # two calls: the history must carry
+        d = torch.zeros((C, N), dtype=tdt, device="cuda")
+        ctx.st(name, c, ntaps, hist, dev(part), d, N)
+        outs.append(d.cpu().numpy())
+    got = np.concatenate(outs, 1)
+    for ch in range(C):
+        exp, _ = getattr(best_oracle, name)(c, np.zeros(ntaps + B, dt), x[ch], B)
+        assert np.array_equal(got[ch], exp), (name, ch)
+
+
+def test_fir_decimate_interpolate(ctx, best_oracle, rng):
+    c, x = f32(rng, 64, amp=0.1), f32(rng, C, 2 * N)
+    cq, xq = q15(rng, 64, amp=4000), q15(rng, C, 2 * N)
+    for name, cc, xx, tdt, dt in (("f32", c, x, torch.float32, np.float32), ("q15", cq, xq, torch.int16, np.int16)):
+        hist = torch.zeros((C, 63), dtype=tdt, device="cuda"); outs = []
+        for part in (xx[:, :N], xx[:, N:]):
+            d = torch.zeros((C, N // 4), dtype=tdt, device="cuda")
+            ctx.st("fir_decimate_" + name, cc, 64, 4, hist, dev(part), d, N); outs.append(d.cpu().numpy())
+        got = np.concatenate(outs, 1)
+        for ch in range(C):
+            assert np.array_equal(got[ch], getattr(best_oracle, "fir_decimate_" + name)(cc, 4, np.zeros(64 + B, dt), xx[ch], B)[0]), ("dec", name, ch)
+        hist = torch.zeros((C, 15), dtype=tdt, device="cuda"); outs = []
+        for part in (xx[:, :N], xx[:, N:]):
+            d = torch.zeros((C, N * 4), dtype=tdt, device="cuda")
+            ctx.st("fir_interpolate_" + name, cc, 64, 4, hist, dev(part), d, N); outs.append(d.cpu().numpy())
+        got = np.concatenate(outs, 1)
+        for ch in range(C):
+            assert np.array_equal(got[ch], getattr(best_oracle, "fir_interpolate_" + name)(cc, 4, np.zeros(64 + B, dt), xx[ch], B)[0]), ("int", name, ch)
+
+
+def test_biquads_bit_exact_with_carried_state(ctx, best_oracle, rng):
+    p = slb.default_rx_f32_params(48000)
+    cf = np.array(p.biquad[:10], np.float32)
+    x = f32(rng, C, 2 * N, amp=0.3)
+    for name, per_stage in (("biquad_df2T_f32", 2), ("biquad_df1_f32", 4)):
+        st = torch.zeros((C, per_stage * 2), dtype=torch.float32, device="cuda"); outs = []
+        for part in (x[:, :N], x[:, N:]):
+            d = torch.zeros((C, N), dtype=torch.float32, device="cuda")
+            ctx.st(name, cf, 2, st, dev(part), d, N); outs.append(d.cpu().numpy())
+        got = np.concatenate(outs, 1)
+        for ch in range(C):
+            exp, est = getattr(best_oracle, name)(cf, 2, np.zeros(per_stage * 2, np.float32), x[ch], B)
+            assert np.array_equal(got[ch], exp), (name, ch)
+            assert np.array_equal(st[ch].cpu().numpy(), est), (name, "state", ch)
+    xs = f32(rng, C, 2 * N, amp=0.3)                         # N stereo frames
+    st = torch.zeros((C, 8), dtype=torch.float32, device="cuda"); d = torch.zeros((C, 2 * N), dtype=torch.float32, device="cuda")
+    ctx.st("biquad_stereo_df2T_f32", cf, 2, st, dev(xs), d, N)
+    for ch in range(C):
+        exp, est = best_oracle.biquad_stereo_df2T_f32(cf, 2, np.zeros(8, np.float32), xs[ch], B)
+        assert np.array_equal(d[ch].cpu().numpy(), exp) and np.array_equal(st[ch].cpu().numpy(), est)
+    c15 = np.array([8000, 0, -16000, 8000, 15000, -7000, 4000, 0, 8000, 4000, 9000, -3000], np.int16)
+    xq = q15(rng, C, N, amp=20000)
+    st = torch.zeros((C, 8), dtype=torch.int16, device="cuda"); d = torch.zeros((C, N), dtype=torch.int16, device="cuda")
+    ctx.st("biquad_df1_q15", c15, 2, 1, st, dev(xq), d, N)
+    for ch in range(C):
+        exp, est = best_oracle.biquad_df1_q15(c15, 2, 1, np.zeros(8, np.int16), xq[ch], B)
+        assert np.array_equal(d[ch].cpu().numpy(), exp) and np.array_equal(st[ch].cpu().numpy(), est)
+    c31 = (np.array([0.25, -0.5, 0.25, 0.45, -0.2, 0.12, 0.24, 0.12, 0.27, -0.09]) * 2**31).astype(np.int64).astype(np.int32)
+    x31 = rng.integers(-2**30, 2**30, (C, N)).astype(np.int32)
+    st = torch.zeros((C, 8), dtype=torch.int32, device="cuda"); d = torch.zeros((C, N), dtype=torch.int32, device="cuda")
+    ctx.st("biquad_df1_q31", c31, 2, 1, st, dev(x31), d, N)
+    for ch in range(C):
+        exp, est = best_oracle.biquad_df1_q31(c31, 2, 1, np.zeros(8, np.int32), x31[ch], B)
+        assert np.array_equal(d[ch].cpu().numpy(), exp) and np.array_equal(st[ch].cpu().numpy(), est)
+
+
+def test_block_statistics(ctx, best_oracle, rng):
+    x = f32(rng, C, N); o = best_oracle
+    out = torch.zeros((C, NB), dtype=torch.float32, device="cuda"); idx = torch.zeros((C, NB), dtype=torch.int32, device="cuda")
+    ctx.st("max_f32", dev(x), N, B, out, idx)
+    for c in range(C):
+        for b in range(NB):
+            v, i = o.max_f32(x[c, b * B:(b + 1) * B])
+            assert out[c, b].item() == v and idx[c, b].item() == i
+    for name in ("rms_f32", "power_f32", "mean_f32"):
+        ctx.st(name, dev(x), N, B, out)
+        exp = np.array([[getattr(o, name)(x[c, b * B:(b + 1) * B]) for b in range(NB)] for c in range(C)], np.float32)
+        assert np.array_equal(out.cpu().numpy(), exp), name
+    q = q15(rng, C, N)
+    outq = torch.zeros((C, NB), dtype=torch.int16, device="cuda")
+    ctx.st("max_q15", dev(q), N, B, outq, idx)
+    assert np.array_equal(outq.cpu().numpy(), np.array([[o.max_q15(q[c, b * B:(b + 1) * B])[0] for b in range(NB)] for c in range(C)]))
+    ctx.st("rms_q15", dev(q), N, B, outq)
+    assert np.array_equal(outq.cpu().numpy(), np.array([[o.rms_q15(q[c, b * B:(b + 1) * B]) for b in range(NB)] for c in range(C)]))
+
+
+@pytest.mark.parametrize("nfft", [16, 64, 256, 512, 1024, 4096])
+def test_batched_cfft(ctx, best_oracle, rng, nfft):
+    cnt = 2
+    x = f32(rng, C, cnt, 2 * nfft)
+    for ifft in (0, 1):
+        d = dev(x)
+        ctx.st("cfft_f32", d, nfft, cnt, ifft)
+        got = d.cpu().numpy()
+        for c in range(C):
+            for k in range(cnt):
+                exp = best_oracle.cfft_f32(x[c, k], ifft, 1)
+                rms = np.sqrt(np.mean(exp.astype(np.float64) ** 2))
+                assert np.max(np.abs(got[c, k] - exp)) <= 3e-6 * rms, (nfft, ifft)
