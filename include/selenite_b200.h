@@ -43,6 +43,7 @@ extern "C" {
 /* What sits between pbuf and the ring store inside DSP_In_Buff_Write (dsp_if.c:286-289) */
 #define SLB_CHAIN_PASS        0    /* the firmware as shipped: bit-exact int16 copy */
 #define SLB_CHAIN_RX_SSB_F32  1    /* unpack -> FFT overlap-save SSB demod -> biquad cascade -> AGC -> pack */
+#define SLB_CHAIN_TX_SSB_F32  2    /* mic (L of L=R) -> FFT overlap-save SSB modulator (band-pass + Hilbert) -> ALC -> I/Q pack */
 
 #define SLB_MAX_STAGES 4
 #define SLB_MAX_MASKS  8
@@ -68,6 +69,15 @@ typedef struct
   float    agc_target, agc_decay, agc_floor, agc_gmax;
 } slb_rx_f32_params;
 
+/* TX-SSB-f32 chain parameters: the spectral masks are shared with RX (slb_set_mask). */
+typedef struct
+{
+  uint32_t fft_len;                      /* this build: 512 */
+  uint32_t hop;                          /* this build: 384 */
+  uint32_t alc_block;                    /* ALC detector block [arm_cmplx_mag_f32 + arm_max_f32] = firmware block; this build: 48 */
+  float    alc_target, alc_decay, alc_floor, alc_gmax;
+} slb_tx_f32_params;
+
 /* ---- life cycle ---- */
 int  slb_create (const slb_config *cfg, slb_ctx **out);
 void slb_destroy (slb_ctx *ctx);
@@ -80,6 +90,9 @@ int slb_default_rx_f32_params (uint32_t fs, slb_rx_f32_params *out);
 int slb_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out);
 int slb_set_rx_f32_params (slb_ctx *ctx, const slb_rx_f32_params *p);
 int slb_get_rx_f32_params (const slb_ctx *ctx, slb_rx_f32_params *p);
+int slb_default_tx_f32_params (uint32_t fs, slb_tx_f32_params *out);
+int slb_set_tx_f32_params (slb_ctx *ctx, const slb_tx_f32_params *p);
+int slb_get_tx_f32_params (const slb_ctx *ctx, slb_tx_f32_params *p);
 int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask);   /* host, 2*fft_len floats */
 int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask);
 
@@ -106,8 +119,14 @@ int slb_ring_get_iq (slb_ctx *ctx, int which, int16_t *i, int16_t *q);
  * *_host: host pointers; stages through pinned memory with chunked H2D / kernel / D2H overlap, synchronous. */
 int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream);
 int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames);
+/* TX direction (context created with SLB_CHAIN_TX_SSB_F32): in = mic frames (L = R as the codec delivers them in TX,
+ * Core/Src/codec_if.c:304-306; L is used), out = modulated I/Q frames. Same shapes and rules as the RX calls. With this
+ * chain SLB_DSP_In_Buff_Write runs the modulator at the 1 ms cadence exactly as it runs the demodulator for RX. */
+int slb_tx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream);
+int slb_tx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames);
 /* optional float tap: post-biquad, pre-AGC audio [channels][frames] f32 and per-block gains [channels][frames/agc_block]
- * are written by the next slb_rx_process_device call(s) when non-NULL (device pointers) */
+ * are written by the next slb_rx_process_device call(s) when non-NULL (device pointers). TX chain: d_audio receives
+ * the pre-ALC complex baseband [channels][frames][2] f32. */
 int slb_rx_set_debug_taps (slb_ctx *ctx, float *d_audio, float *d_gain);
 
 /* ---- carried state = the checkpoint: overlap tail, biquad d1/d2, AGC envelope, ring ---- */

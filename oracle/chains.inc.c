@@ -95,3 +95,49 @@ void SLO (rx_ssb_f32_batch) (const slo_rx_f32_params *p, slo_rx_f32_state *st, c
   for (uint32_t t = 0; t < nthreads; t++) pthread_join (th[t], 0);
   free (th); free (jobs);
 }
+
+/* TX-SSB-f32: see slo_api.h. What a firmware author would write for the transmit direction with arm_math.h: the
+ * codec delivers the microphone on both ADC channels (codec_if.c:304-306), the modulated I/Q goes to the DAC. */
+void SLO (tx_ssb_f32) (const slo_tx_f32_params *p, slo_tx_f32_state *st, const int16_t *in_lr, int16_t *out_iq,
+                       float *iq_dbg, float *gain_dbg, uint32_t frames)
+{
+  const uint32_t N = p->fft_len, hop = p->hop, ovl = N - hop, B = p->alc_block;
+  int16_t *raw = (int16_t *) malloc (sizeof (int16_t) * N);
+  float *mic = (float *) malloc (sizeof (float) * N);
+  float *frame = (float *) malloc (sizeof (float) * 2 * N);
+  float *prod = (float *) malloc (sizeof (float) * 2 * N);
+  float *scaled = (float *) malloc (sizeof (float) * 2 * hop);
+  float *mag = (float *) malloc (sizeof (float) * B);
+
+  for (uint32_t o = 0; o < frames; o += hop)
+  {
+    memcpy (raw, st->ovl, sizeof (int16_t) * ovl);
+    for (uint32_t k = 0; k < hop; k++) raw[ovl + k] = in_lr[2 * (size_t) (o + k)];   /* L channel */
+    memcpy (st->ovl, raw + hop, sizeof (int16_t) * ovl);
+
+    SLO (q15_to_float) (raw, mic, N);
+    for (uint32_t k = 0; k < N; k++) { frame[2 * k] = mic[k]; frame[2 * k + 1] = 0.0f; }
+    SLO (cfft_f32) (frame, N, 0, 1);
+    SLO (cmplx_mult_cmplx_f32) (frame, p->mask, prod, N);
+    SLO (cfft_f32) (prod, N, 1, 1);
+    const float *iq = prod + 2 * ovl;                                      /* keep last hop */
+    if (iq_dbg) memcpy (iq_dbg + 2 * (size_t) o, iq, sizeof (float) * 2 * hop);
+
+    for (uint32_t b = 0; b < hop; b += B)
+    {
+      SLO (cmplx_mag_f32) (iq + 2 * b, mag, B);
+      float peak = SLO (max_f32) (mag, B, 0);
+      /* same gain law as the RX AGC (ours) */
+      float rel = st->env * p->alc_decay;
+      float env = peak > rel ? peak : rel;
+      float den = env > p->alc_floor ? env : p->alc_floor;
+      float g = p->alc_target / den;
+      if (g > p->alc_gmax) g = p->alc_gmax;
+      st->env = env;
+      if (gain_dbg) gain_dbg[(o + b) / B] = g;
+      SLO (scale_f32) (iq + 2 * b, g, scaled + 2 * b, 2 * B);
+    }
+    SLO (float_to_q15) (scaled, out_iq + 2 * (size_t) o, 2 * hop);
+  }
+  free (raw); free (mic); free (frame); free (prod); free (scaled); free (mag);
+}

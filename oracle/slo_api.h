@@ -130,6 +130,26 @@ void SLO (rx_ssb_f32) (const slo_rx_f32_params *p, slo_rx_f32_state *st, const i
 void SLO (rx_ssb_f32_batch) (const slo_rx_f32_params *p, slo_rx_f32_state *st, const int16_t *in_iq, int16_t *out_lr,
                              uint32_t channels, uint32_t frames, uint32_t nthreads);
 
+/* TX-SSB-f32: mic = L of each L=R frame -> q15_to_float -> overlap-save [cfft fwd of (mic, 0),
+ * cmplx_mult(mask), cfft inv, keep last `hop`] -> per-`alc_block` ALC [cmplx_mag, max, env/gain recurrence, scale]
+ * -> float_to_q15, written interleaved I,Q. The one-sided mask is band-pass and Hilbert pair in one. */
+typedef struct
+{
+  uint32_t fft_len, hop, alc_block;
+  float alc_target, alc_decay, alc_floor, alc_gmax;
+  const float *mask;
+} slo_tx_f32_params;
+
+typedef struct
+{
+  int16_t ovl[SLO_MAX_FFT];           /* last (fft_len-hop) mic samples */
+  float env;
+} slo_tx_f32_state;
+
+/* frames % hop == 0. iq_dbg (optional) receives the pre-ALC complex baseband [frames][2]; gain_dbg the per-block gain. */
+void SLO (tx_ssb_f32) (const slo_tx_f32_params *p, slo_tx_f32_state *st, const int16_t *in_lr, int16_t *out_iq,
+                       float *iq_dbg, float *gain_dbg, uint32_t frames);
+
 #ifdef __cplusplus
 }
 #endif

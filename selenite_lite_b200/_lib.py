@@ -19,6 +19,11 @@ class RxF32Params(C.Structure):
                 ("agc_target", C.c_float), ("agc_decay", C.c_float), ("agc_floor", C.c_float), ("agc_gmax", C.c_float)]
 
 
+class TxF32Params(C.Structure):
+    _fields_ = [("fft_len", C.c_uint32), ("hop", C.c_uint32), ("alc_block", C.c_uint32),
+                ("alc_target", C.c_float), ("alc_decay", C.c_float), ("alc_floor", C.c_float), ("alc_gmax", C.c_float)]
+
+
 # every symbol include/selenite_b200.h declares: name -> (restype, argtypes), derived from the header text so the
 # binding cannot drift from the ABI
 _P = C.c_void_p

@@ -28,6 +28,7 @@ struct slb_ctx
 
   // chain configuration
   slb_rx_f32_params rx{};
+  slb_tx_f32_params tx{};
   BiquadScanTables tables{};
   std::vector<float> masks_host;       // [SLB_MAX_MASKS][2*fft_len], unscaled, as set
   std::vector<uint8_t> slot_host;      // [C]
@@ -64,6 +65,8 @@ struct slb_ctx
       (ctx)->err = b_; return SLB_ERR_CUDA;                                                        \
     }                                                                                              \
   } while (0)
+
+static inline bool is_ssb_chain (uint32_t chain) { return chain == SLB_CHAIN_RX_SSB_F32 || chain == SLB_CHAIN_TX_SSB_F32; }
 
 static int fail (slb_ctx *ctx, int code, const char *msg) { if (ctx) ctx->err = msg; else g_create_error = msg; return code; }
 
@@ -122,6 +125,7 @@ const char *slb_last_error (const slb_ctx *ctx) { return ctx ? ctx->err.c_str ()
 uint64_t slb_kernel_launches (const slb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int slb_default_rx_f32_params (uint32_t fs, slb_rx_f32_params *out) { return design_default_rx_f32 (fs, out); }
+int slb_default_tx_f32_params (uint32_t fs, slb_tx_f32_params *out) { return design_default_tx_f32 (fs, out); }
 int slb_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out) { return design_default_mask (fs, fft_len, mode, mask_out); }
 
 int slb_create (const slb_config *cfg, slb_ctx **out)
@@ -130,7 +134,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   *out = nullptr;
   if (cfg->channels == 0) return fail (nullptr, SLB_ERR_ARG, "channels must be > 0");
   if (cfg->fs != 48000u && cfg->fs != 96000u && cfg->fs != 192000u) return fail (nullptr, SLB_ERR_ARG, "fs must be 48000, 96000 or 192000");
-  if (cfg->chain != SLB_CHAIN_PASS && cfg->chain != SLB_CHAIN_RX_SSB_F32) return fail (nullptr, SLB_ERR_ARG, "unknown chain");
+  if (cfg->chain != SLB_CHAIN_PASS && !is_ssb_chain (cfg->chain)) return fail (nullptr, SLB_ERR_ARG, "unknown chain");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -143,6 +147,8 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   cudaDeviceGetAttribute (&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   design_default_rx_f32 (cfg->fs, &ctx->rx);
   ctx->rx.agc_block = ctx->geo.block_frames;
+  design_default_tx_f32 (cfg->fs, &ctx->tx);
+  ctx->tx.alc_block = ctx->geo.block_frames;
   const uint32_t C = cfg->channels, N = ctx->rx.fft_len, hop = ctx->rx.hop, ovl = N - hop, R = ctx->geo.ring_frames;
 
   ctx->masks_host.assign ((size_t) SLB_MAX_MASKS * 2 * N, 0.0f);
@@ -218,6 +224,18 @@ int slb_set_rx_f32_params (slb_ctx *ctx, const slb_rx_f32_params *p)
 }
 int slb_get_rx_f32_params (const slb_ctx *ctx, slb_rx_f32_params *p) { if (!ctx || !p) return SLB_ERR_ARG; *p = ctx->rx; return SLB_OK; }
 
+int slb_set_tx_f32_params (slb_ctx *ctx, const slb_tx_f32_params *p)
+{
+  if (!ctx || !p) return SLB_ERR_ARG;
+  if (p->fft_len != 512 || p->hop != 384 || p->alc_block != (uint32_t) kAgcBlock)
+    return fail (ctx, SLB_ERR_UNSUPPORTED, "this build has kernels for fft_len=512, hop=384, alc_block=48 only");
+  if (!(p->alc_decay > 0.f && p->alc_decay <= 1.f) || !(p->alc_floor > 0.f) || !(p->alc_gmax > 0.f) || !(p->alc_target > 0.f))
+    return fail (ctx, SLB_ERR_ARG, "ALC constants out of range");
+  ctx->tx = *p;
+  return SLB_OK;
+}
+int slb_get_tx_f32_params (const slb_ctx *ctx, slb_tx_f32_params *p) { if (!ctx || !p) return SLB_ERR_ARG; *p = ctx->tx; return SLB_OK; }
+
 int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask)
 {
   if (!ctx || !mask) return SLB_ERR_ARG;
@@ -290,7 +308,9 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
   L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
   L.masks = ctx->d_masks; L.mask_slot = ctx->d_slot + ch0; L.twiddle = ctx->d_twiddle;
   L.flag_base = ctx->flag_base; L.channels = nch; L.frames = frames;
-  L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;
+  L.tx = ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32;
+  if (L.tx) { L.agc_target = ctx->tx.alc_target; L.agc_decay = ctx->tx.alc_decay; L.agc_floor = ctx->tx.alc_floor; L.agc_gmax = ctx->tx.alc_gmax; }
+  else { L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax; }
   L.tables = &ctx->tables;
   CK (ctx, launch_rx_ssb_f32 (L, ctx->sm_count, stream));
   ctx->launches += rx_ssb_f32_launches_per_call ();
@@ -315,7 +335,7 @@ static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_
   if (!pbuf || frames == 0 || frames + 1 > R) return fail (ctx, SLB_ERR_ARG, "block must hold 1..DSP_BUFF_SIZE-1 frames");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
-  const bool chain = (which == 0 && ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32);
+  const bool chain = (which == 0 && is_ssb_chain (ctx->cfg.chain));
   if (!chain)
   {
     int rc = ensure_blk (ctx, frames); if (rc) return rc;
@@ -427,9 +447,10 @@ int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp9
 // ------------------------------------------------------------------------------------------------------------------
 // Bulk path
 // ------------------------------------------------------------------------------------------------------------------
-int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream)
+static int process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream, bool want_tx)
 {
   if (!ctx || !d_in || !d_out || frames == 0) return SLB_ERR_ARG;
+  if (want_tx != (ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32)) return fail (ctx, SLB_ERR_STATE, "context was created for the other direction (cfg.chain)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   if (ctx->cfg.chain == SLB_CHAIN_PASS)
   {
@@ -444,11 +465,15 @@ int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, ui
   return SLB_OK;
 }
 
-int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames)
+int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream) { return process_device (ctx, d_in, d_out, frames, stream, false); }
+int slb_tx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream) { return process_device (ctx, d_in, d_out, frames, stream, true); }
+
+static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames, bool want_tx)
 {
   if (!ctx || !h_in || !h_out || frames == 0) return SLB_ERR_ARG;
+  if (want_tx != (ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32)) return fail (ctx, SLB_ERR_STATE, "context was created for the other direction (cfg.chain)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
-  const bool chain = ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32;
+  const bool chain = is_ssb_chain (ctx->cfg.chain);
   if (chain && frames % ctx->rx.hop != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the hop (384)");
   const uint32_t C = ctx->cfg.channels;
   const size_t ch_bytes = (size_t) frames * 4;
@@ -494,6 +519,8 @@ int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
   if (chain) rx_advance (ctx, frames);
   return SLB_OK;
 }
+int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames) { return process_host (ctx, h_in, h_out, frames, false); }
+int slb_tx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames) { return process_host (ctx, h_in, h_out, frames, true); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // Checkpoint: everything a later call depends on
@@ -580,7 +607,7 @@ slb_ctx *dropin ()
     const char *fs = std::getenv ("SELENITE_B200_FS"), *dev = std::getenv ("SELENITE_B200_DEVICE"), *ch = std::getenv ("SELENITE_B200_CHAIN");
     cfg.fs = fs ? (uint32_t) std::atoi (fs) : 48000u;
     cfg.device = dev ? std::atoi (dev) : 0;
-    cfg.chain = (ch && std::strcmp (ch, "rx_ssb_f32") == 0) ? SLB_CHAIN_RX_SSB_F32 : SLB_CHAIN_PASS;
+    cfg.chain = (ch && std::strcmp (ch, "rx_ssb_f32") == 0) ? SLB_CHAIN_RX_SSB_F32 : (ch && std::strcmp (ch, "tx_ssb_f32") == 0) ? SLB_CHAIN_TX_SSB_F32 : SLB_CHAIN_PASS;
     g_dropin_status = slb_create (&cfg, &g_dropin);
     if (g_dropin_status != SLB_OK) std::fprintf (stderr, "selenite-b200: drop-in context failed: %s\n", slb_last_error (nullptr));
   }

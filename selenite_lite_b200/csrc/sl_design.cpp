@@ -38,6 +38,19 @@ int design_default_rx_f32 (uint32_t fs, slb_rx_f32_params *p)
   return SLB_OK;
 }
 
+// TX-SSB-f32: the mode's one-sided mask is band-pass and Hilbert pair in one; what is left to freeze is the ALC.
+int design_default_tx_f32 (uint32_t fs, slb_tx_f32_params *p)
+{
+  if (!p || (fs != 48000u && fs != 96000u && fs != 192000u)) return SLB_ERR_ARG;
+  std::memset (p, 0, sizeof *p);
+  p->fft_len = 512; p->hop = 384; p->alc_block = 48;
+  p->alc_target = 0.5f;                                                  // -6 dBFS peak envelope of I + jQ
+  p->alc_decay = (float) std::exp (-1.0 / 100.0);                        // 100 ms release at the 1 ms block cadence
+  p->alc_floor = 1.0e-3f;
+  p->alc_gmax = 16.0f;                                                   // +24 dB
+  return SLB_OK;
+}
+
 int mode_to_mask_slot (uint8_t mode)
 {
   switch (mode)

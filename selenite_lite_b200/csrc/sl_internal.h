@@ -39,6 +39,7 @@ struct RingPtrs
 // Frozen default design (sl_design.cpp)
 // ---------------------------------------------------------------------------------------------------------
 int design_default_rx_f32 (uint32_t fs, slb_rx_f32_params *out);
+int design_default_tx_f32 (uint32_t fs, slb_tx_f32_params *out);
 int design_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out);
 int mode_to_mask_slot (uint8_t mode);   // -1 when the mode has no SSB-style mask (AM, FM)
 
@@ -76,6 +77,7 @@ struct RxF32Launch
   uint32_t channels, frames;
   float agc_target, agc_decay, agc_floor, agc_gmax;
   const BiquadScanTables *tables;          // host pointer, copied into the kernel parameter block
+  bool tx;                                 // TX-SSB-f32: mic (L) in, I/Q out through the ALC; audio_dbg is then [C][T][2]
 };
 int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream);
 uint32_t rx_ssb_f32_launches_per_call ();

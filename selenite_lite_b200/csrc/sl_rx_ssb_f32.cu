@@ -41,6 +41,8 @@ constexpr int kThreads = 32 * (kFftWarps + 1);   // + the recurrence warp
 constexpr int kBlocksPerTile = kTile / kAgcBlock; // 32 AGC blocks of 48 samples = one per recurrence lane
 constexpr int kBlkStride = 50;                   // words per block in the audio tile: 8-byte aligned, conflict-free for
                                                  // the lane-per-block 64-bit reads (18 l mod 32 hits 16 distinct even banks)
+constexpr int kTxBlkStride = 100;                // TX tile: 48 complex per block + pad; 16-byte aligned, the lane-per-block
+                                                 // 128-bit reads (100 l mod 32 = 4 l) cover all banks once per 8 lanes
 constexpr int kTilesPerItem = 16;                // tiles a CTA processes with the recurrence state in registers
 constexpr int kPlane = kN;                       // floats per re / im scratch plane (XOR swizzle: no padding)
 
@@ -145,6 +147,14 @@ __device__ __forceinline__ uint32_t pack_lr (float x_times_32768)
   short v;
   asm ("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(v) : "f"(x_times_32768));
   return __byte_perm ((uint32_t) (uint16_t) v, 0u, 0x1010);   // stereo endpoint, L = R
+}
+
+__device__ __forceinline__ uint32_t pack_iq (float i_times_32768, float q_times_32768)
+{
+  short a, b;
+  asm ("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(a) : "f"(i_times_32768));
+  asm ("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(b) : "f"(q_times_32768));
+  return (uint32_t) (uint16_t) a | ((uint32_t) (uint16_t) b << 16);              // interleaved I,Q as on the I2S bus (main.c:333-341)
 }
 
 // streaming 8-byte load: read-only path, no L1 allocation (the 2 GB input must not evict masks and twiddles)
@@ -277,10 +287,15 @@ __device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, fl
   __syncwarp ();
 }
 
-__global__ void __launch_bounds__ (kThreads, 4) rx_ssb_f32_kernel (const __grid_constant__ KParams P)
+// kTx = false: RX-SSB-f32 (complex I/Q in, real audio out through biquad + AGC, written L = R).
+// kTx = true : TX-SSB-f32 (mic audio = L of the L = R frames in, complex I/Q out through the ALC): same overlap-save
+//              filter with the mode's one-sided mask acting as band-pass + Hilbert pair, no biquad; the post warp measures
+//              |I + jQ| per firmware block (arm_cmplx_mag_f32 + arm_max_f32) and applies the same gain law.
+template <bool kTx>
+__global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_constant__ KParams P)
 {
   __shared__ __align__ (16) float sScratch[kFftWarps][2][kPlane];
-  __shared__ __align__ (16) float sAudio[2][kBlocksPerTile * kBlkStride];
+  __shared__ __align__ (16) float sAudio[2][kBlocksPerTile * (kTx ? kTxBlkStride : kBlkStride)];
   __shared__ __align__ (16) float4 sTw[6 * 32];
   __shared__ __align__ (16) float sPeak[32];
   __shared__ float sEnv[32];
@@ -317,7 +332,7 @@ __global__ void __launch_bounds__ (kThreads, 4) rx_ssb_f32_kernel (const __grid_
         {
           float ia, qa, ib, qb;
           unpack_iq (raw[r].x, ia, qa); unpack_iq (raw[r].y, ib, qb);
-          xr[r] = pk (ia, ib); xi[r] = pk (qa, qb);
+          xr[r] = pk (ia, ib); xi[r] = kTx ? 0ull : pk (qa, qb);                   // TX: the mic is the L half of an L = R frame
         }
         // carry the raw tail of the stream for the next call (this launch reads ovl_in and writes ovl_out)
         if (t0 + (warp + 1) * kHop == P.frames)
@@ -358,13 +373,95 @@ __global__ void __launch_bounds__ (kThreads, 4) rx_ssb_f32_kernel (const __grid_
         for (int r = 2; r < 8; r++)
         {
           const int n = warp * kHop + 2 * lane + 64 * (r - 2);                     // even: n and n+1 share run and block
-          const int blk = n / kAgcBlock, i = n - blk * kAgcBlock, half = i / kRun, k = i - half * kRun;
-          const int pos = blk * kBlkStride + 2 * k + half;                         // runs A/B of a block are interleaved
-          // (xr, xi) hold fft(swap Y): the wanted real part of the inverse transform is its imaginary component
-          a[pos] = lo_of (xi[r]); a[pos + 2] = hi_of (xi[r]);
+          const int blk = n / kAgcBlock, i = n - blk * kAgcBlock;
+          // (xr, xi) hold fft(swap Y) = swap(N ifft(Y)): real part of the inverse transform in xi, imaginary part in xr
+          if (kTx)
+            *reinterpret_cast<float4 *> (a + blk * kTxBlkStride + 2 * i) = make_float4 (lo_of (xi[r]), lo_of (xr[r]), hi_of (xi[r]), hi_of (xr[r]));
+          else
+          {
+            const int half = i / kRun, k = i - half * kRun;
+            const int pos = blk * kBlkStride + 2 * k + half;                       // runs A/B of a block are interleaved
+            a[pos] = lo_of (xi[r]); a[pos + 2] = hi_of (xi[r]);
+          }
         }
       }
       bar_arrive (1 + buf);
+    }
+  }
+  else if constexpr (kTx)
+  {
+    // ===================================== TX post warp: ALC =====================================
+    // Lane l owns firmware block l of the tile (48 complex samples = 192 output bytes). Pass 1 finds the block peak of
+    // |I + jQ|, the envelope walk is the AGC's, pass 2 re-reads the tile, scales, packs and stores.
+    const float decay = P.agc_decay;
+    float env = 0.f;
+    TileIter it; it.start (P);
+    for (; it.valid; it.next (P), tile_seq++)
+    {
+      const uint32_t c = it.c, t0 = it.t0;
+      const int nblk = it.hops * (kHop / kAgcBlock);
+      const int buf = tile_seq & 1;
+      const float4 *blk = reinterpret_cast<const float4 *> (sAudio[buf] + lane * kTxBlkStride);
+      bar_sync (1 + buf);                                                          // I/Q tile is complete
+      // arm_cmplx_mag_f32.c:72 : sqrt(re*re + im*im), each product rounded (no contraction in the oracle build);
+      // arm_max_f32 over the block. sqrt is monotonic and correctly rounded, so max(sqrt) = sqrt(max).
+      float m2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < kAgcBlock / 2; k++)
+      {
+        const float4 v = blk[k];
+        m2 = fmaxf (m2, fmaxf (__fadd_rn (__fmul_rn (v.x, v.x), __fmul_rn (v.y, v.y)), __fadd_rn (__fmul_rn (v.z, v.z), __fmul_rn (v.w, v.w))));
+      }
+      if (it.tl == 0)
+      {
+        if (lane == 0)
+        {
+          const unsigned want = P.flag_base + it.seg;
+          while (ld_relaxed (P.flag + c) != want) __nanosleep (32);
+          (void) ld_acquire (P.flag + c);
+        }
+        __syncwarp ();
+        env = __ldcg (P.state + (size_t) c * 8 + 4);
+      }
+      sPeak[lane] = __fsqrt_rn (m2);
+      __syncwarp ();
+      for (int q = 0; q < nblk; q += 4)
+      {
+        const float4 p4 = *reinterpret_cast<const float4 *> (&sPeak[q]);
+        env = fmaxf (p4.x, env * decay); sEnv[q] = env;
+        env = fmaxf (p4.y, env * decay); sEnv[q + 1] = env;
+        env = fmaxf (p4.z, env * decay); sEnv[q + 2] = env;
+        env = fmaxf (p4.w, env * decay); sEnv[q + 3] = env;
+      }
+      __syncwarp ();
+      const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (sEnv[lane], P.agc_floor)), P.agc_gmax);
+      __syncwarp ();
+      if (lane < nblk)
+      {
+        if (P.audio_dbg)
+        {
+          float4 *adbg = reinterpret_cast<float4 *> (P.audio_dbg + 2 * ((size_t) c * P.frames + t0 + lane * kAgcBlock));
+#pragma unroll
+          for (int k = 0; k < kAgcBlock / 2; k++) adbg[k] = blk[k];
+        }
+        if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kAgcBlock) + t0 / kAgcBlock + lane] = g;
+        const float g15 = g * 32768.0f;                                           // arm_scale_f32 then arm_float_to_q15: exact fold
+        uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + t0 + lane * kAgcBlock);
+#pragma unroll
+        for (int k = 0; k < kAgcBlock / 4; k++)
+        {
+          const float4 u = blk[2 * k], v = blk[2 * k + 1];
+          dst[k] = make_uint4 (pack_iq (u.x * g15, u.y * g15), pack_iq (u.z * g15, u.w * g15), pack_iq (v.x * g15, v.y * g15), pack_iq (v.z * g15, v.w * g15));
+        }
+      }
+      __syncwarp ();
+      bar_arrive (3 + buf);                                                        // the tile has been consumed
+      if (it.tl == it.ntiles - 1 && lane == 0)
+      {
+        __stcg (P.state + (size_t) c * 8 + 4, env);
+        __threadfence ();
+        st_release (P.flag + c, P.flag_base + it.seg + 1u);
+      }
     }
   }
   else
@@ -584,13 +681,15 @@ int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream_)
   P.tab = *L.tables;
 
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, rx_ssb_f32_kernel, kThreads, 0);
+  cudaError_t e = L.tx ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, ssb_f32_kernel<true>, kThreads, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, ssb_f32_kernel<false>, kThreads, 0);
   if (e != cudaSuccess) return (int) e;
   if (per_sm < 1) per_sm = 1;
   const uint64_t items = (uint64_t) L.channels * P.items_per_channel;
   uint64_t grid = (uint64_t) sm_count * per_sm;      // all CTAs co-resident: the segment hand-over may spin
   if (grid > items) grid = items;
-  rx_ssb_f32_kernel<<<(unsigned) grid, kThreads, 0, stream>>> (P);
+  if (L.tx) ssb_f32_kernel<true><<<(unsigned) grid, kThreads, 0, stream>>> (P);
+  else ssb_f32_kernel<false><<<(unsigned) grid, kThreads, 0, stream>>> (P);
   return (int) cudaGetLastError ();
 }
 

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 
-CHAIN_PASS, CHAIN_RX_SSB_F32 = 0, 1
+CHAIN_PASS, CHAIN_RX_SSB_F32, CHAIN_TX_SSB_F32 = 0, 1, 2
 MODE_LSB, MODE_USB, MODE_CW, MODE_CWR, MODE_AM, MODE_FM, MODE_DIG, MODE_PKT = 0x00, 0x01, 0x02, 0x03, 0x04, 0x08, 0x0A, 0x0C
 
 
@@ -24,6 +24,19 @@ def default_rx_f32_params(fs=48000):
     if rc:
         raise SeleniteError("slb_default_rx_f32_params -> %d" % rc)
     return p
+
+
+def default_tx_f32_params(fs=48000):
+    p = _lib.TxF32Params()
+    rc = _lib.load().slb_default_tx_f32_params(fs, C.byref(p))
+    if rc:
+        raise SeleniteError("slb_default_tx_f32_params -> %d" % rc)
+    return p
+
+
+def tx_params_to_dict(p, mask):
+    return dict(fft_len=p.fft_len, hop=p.hop, alc_block=p.alc_block, alc_target=p.alc_target, alc_decay=p.alc_decay,
+                alc_floor=p.alc_floor, alc_gmax=p.alc_gmax, mask=mask)
 
 
 def default_mask(fs=48000, fft_len=512, mode=MODE_USB):
@@ -131,26 +144,39 @@ class DspIf:
         m = np.ascontiguousarray(np.asarray(mask, np.complex64)).view(np.float32)
         self._ck(self.lib.slb_set_mask(self.h, mode, m.ctypes.data), "set_mask")
 
+    def tx_params(self):
+        p = _lib.TxF32Params()
+        self._ck(self.lib.slb_get_tx_f32_params(self.h, C.byref(p)), "get_tx_f32_params")
+        return p
+
+    def set_tx_params(self, p): self._ck(self.lib.slb_set_tx_f32_params(self.h, C.byref(p)), "set_tx_f32_params")
+
     def oracle_params(self, mode=MODE_USB):
+        if self.chain == CHAIN_TX_SSB_F32:
+            return tx_params_to_dict(self.tx_params(), self.mask(mode))
         return params_to_dict(self.rx_params(), self.mask(mode))
 
     # ---- bulk path ----
-    def rx_process(self, x, out=None, stream=None):
+    def rx_process(self, x, out=None, stream=None, _dir="rx"):
         """x: torch CUDA int16 tensor [channels][frames][2] (device path, async on `stream`/current stream) or
         numpy int16 array of that shape (host path, synchronous). Returns `out`."""
         if isinstance(x, np.ndarray):
             x = np.ascontiguousarray(x, np.int16)
             frames = x.shape[1]
             out = np.empty_like(x) if out is None else out
-            self._ck(self.lib.slb_rx_process_host(self.h, x.ctypes.data, out.ctypes.data, frames), "rx_process_host")
+            self._ck(getattr(self.lib, "slb_%s_process_host" % _dir)(self.h, x.ctypes.data, out.ctypes.data, frames), _dir + "_process_host")
             return out
         import torch
         assert x.is_cuda and x.dtype == torch.int16 and x.is_contiguous() and x.shape[0] == self.channels
         frames = x.shape[1]
         out = torch.empty_like(x) if out is None else out
         s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
-        self._ck(self.lib.slb_rx_process_device(self.h, x.data_ptr(), out.data_ptr(), frames, s), "rx_process_device")
+        self._ck(getattr(self.lib, "slb_%s_process_device" % _dir)(self.h, x.data_ptr(), out.data_ptr(), frames, s), _dir + "_process_device")
         return out
+
+    def tx_process(self, x, out=None, stream=None):
+        """TX direction (context created with CHAIN_TX_SSB_F32): mic frames (L = R) in, modulated I/Q frames out."""
+        return self.rx_process(x, out, stream, _dir="tx")
 
     def rx_process_pinned(self, x_pinned, out_pinned):
         """torch pinned host tensors [channels][frames][2]; chunked H2D / kernel / D2H overlap inside the library."""

@@ -23,3 +23,19 @@ def synth_iq(channels, frames, fs=48000, f0=None, amp=0.25, sigma=0.01, seed=SEE
         out[k, :, 0] = np.clip(np.rint(i * 32768.0), -32768, 32767).astype(np.int16)
         out[k, :, 1] = np.clip(np.rint(q * 32768.0), -32768, 32767).astype(np.int16)
     return out
+
+
+def synth_mic(channels, frames, fs=48000, tones=(700.0, 1900.0), amp=0.2, sigma=0.005, seed=SEED, first_channel=0):
+    """Config 3 input: int16[channels][frames][2] with L = R (what the codec delivers in TX,
+    Core/Src/codec_if.c:304-306): two-tone 700 Hz + 1900 Hz at 0.2 FS each + noise; channel c detunes the pair by c Hz."""
+    out = np.empty((channels, frames, 2), np.int16)
+    n = np.arange(frames, dtype=np.float64)
+    for k in range(channels):
+        c = first_channel + k
+        rng = np.random.Generator(np.random.PCG64(seed + 0x7A + c))
+        m = sigma * rng.standard_normal(frames)
+        for f in tones:
+            m = m + amp * np.cos(2.0 * np.pi * (f + (c % 97)) * n / fs + 0.1 * c)
+        v = np.clip(np.rint(m * 32768.0), -32768, 32767).astype(np.int16)
+        out[k, :, 0] = v; out[k, :, 1] = v
+    return out

@@ -33,6 +33,18 @@ def main():
     out["rx_agc"] = np.array([p.agc_target, p.agc_decay, p.agc_floor, p.agc_gmax], np.float32)
     np.savez_compressed(os.path.join(HERE, "rx_ssb_f32.npz"), **out)
 
+    # ---- TX-SSB-f32, config-3 style: one mic channel (L = R), two-tone + noise, 20 hops, USB and LSB
+    tp = slb.default_tx_f32_params(48000)
+    tx = {}
+    for name, mode in (("usb", slb.MODE_USB), ("lsb", slb.MODE_LSB)):
+        mask = slb.default_mask(48000, tp.fft_len, mode)
+        x = slb.synth_mic(1, 20 * 384)[0]
+        y, iq, gain, _ = ref.tx_ssb_f32(slb.dsp_if.tx_params_to_dict(tp, mask), x)
+        tx["tx_%s_in" % name] = x; tx["tx_%s_out" % name] = y; tx["tx_%s_iq" % name] = iq; tx["tx_%s_gain" % name] = gain
+        tx["tx_%s_mask" % name] = mask
+    tx["tx_alc"] = np.array([tp.alc_target, tp.alc_decay, tp.alc_floor, tp.alc_gmax], np.float32)
+    np.savez_compressed(os.path.join(HERE, "tx_ssb_f32.npz"), **tx)
+
     # ---- the firmware ring (unmodified dsp_if.c): ramp through In_Buff_Write/In_Buff_Read and Out_Buff_Write/Out_Buff_Read
     ring = {}
     for fs in (48000, 96000):
@@ -71,7 +83,7 @@ def main():
     cbq = np.array(p.biquad[:10], np.float32)
     st["biquad_df2T_f32"] = ref.biquad_df2T_f32(cbq, 2, np.zeros(4, np.float32), xf, 48)[0]
     np.savez_compressed(os.path.join(HERE, "stages.npz"), **st)
-    for f in ("rx_ssb_f32.npz", "ring.npz", "stages.npz"):
+    for f in ("rx_ssb_f32.npz", "tx_ssb_f32.npz", "ring.npz", "stages.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

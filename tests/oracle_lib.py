@@ -35,6 +35,16 @@ class RxF32State(C.Structure):
     _fields_ = [("ovl", C.c_int16 * (2 * MAX_FFT)), ("bq", C.c_float * (2 * MAX_STAGES)), ("env", C.c_float)]
 
 
+class TxF32Params(C.Structure):
+    _fields_ = [("fft_len", u32), ("hop", u32), ("alc_block", u32),
+                ("alc_target", C.c_float), ("alc_decay", C.c_float), ("alc_floor", C.c_float), ("alc_gmax", C.c_float),
+                ("mask", C.POINTER(C.c_float))]
+
+
+class TxF32State(C.Structure):
+    _fields_ = [("ovl", C.c_int16 * MAX_FFT), ("env", C.c_float)]
+
+
 def build_oracles(want_ref=True):
     """Build the port (always) and, when the reference tree is mounted, the reference build."""
     subprocess.run(["make", "-s", "-C", ORACLE_DIR, "port"], check=True)
@@ -243,6 +253,25 @@ class Oracle:
         fn = self._f("rx_ssb_f32_batch", [C.POINTER(RxF32Params), C.POINTER(RxF32State), i16p, i16p, u32, u32, u32])
         fn(C.byref(p), st, x.reshape(-1), out.reshape(-1), Cn, frames, nthreads)
         return out, st
+
+
+    def tx_ssb_f32(self, prm, in_lr, state=None):
+        """in_lr int16[frames][2] (L = R mic) one channel. Returns out int16[frames][2] I/Q, iq f32[frames][2] (pre-ALC),
+        gain f32[frames/alc_block], state."""
+        p = TxF32Params()
+        p.fft_len, p.hop, p.alc_block = prm["fft_len"], prm["hop"], prm["alc_block"]
+        p.alc_target, p.alc_decay = float(prm["alc_target"]), float(prm["alc_decay"])
+        p.alc_floor, p.alc_gmax = float(prm["alc_floor"]), float(prm["alc_gmax"])
+        mask = np.ascontiguousarray(np.asarray(prm["mask"], np.complex64).view(np.float32))
+        p.mask = mask.ctypes.data_as(C.POINTER(C.c_float))
+        st = state if state is not None else TxF32State()
+        x = np.ascontiguousarray(in_lr, np.int16).reshape(-1)
+        frames = x.size // 2
+        out = np.zeros(2 * frames, np.int16); iq = np.zeros(2 * frames, np.float32)
+        gain = np.zeros(frames // prm["alc_block"], np.float32)
+        fn = self._f("tx_ssb_f32", [C.POINTER(TxF32Params), C.POINTER(TxF32State), i16p, i16p, f32p, f32p, u32])
+        fn(C.byref(p), C.byref(st), x, out, iq, gain, frames)
+        return out.reshape(frames, 2), iq.reshape(frames, 2), gain, st
 
 
 class RefRing:

@@ -40,6 +40,47 @@ def test_ref_chain_reproduces_golden(ref, name):
     assert np.array_equal(out, g["rx_%s_out" % name]) and np.array_equal(audio, g["rx_%s_audio" % name])
 
 
+def tx_params(g, name):
+    return dict(fft_len=512, hop=384, alc_block=48, alc_target=g["tx_alc"][0], alc_decay=g["tx_alc"][1],
+                alc_floor=g["tx_alc"][2], alc_gmax=g["tx_alc"][3], mask=g["tx_%s_mask" % name])
+
+
+def iq_tolerance(ref_iq, block=384):
+    """audio_tolerance for a complex stream [frames][2]: 1e-5 * max(|z[n]|, rms of |z| over the super-block)."""
+    z = ref_iq.astype(np.float64); mag = np.hypot(z[:, 0], z[:, 1]).reshape(-1, block)
+    rms = np.sqrt(np.mean(mag ** 2, axis=1, keepdims=True))
+    return np.repeat((1e-5 * np.maximum(mag, rms)).reshape(-1, 1), 2, axis=1)
+
+
+@pytest.mark.parametrize("name", ["usb", "lsb"])
+def test_port_tx_chain_vs_golden(port, name):
+    g = np.load(os.path.join(GOLD, "tx_ssb_f32.npz"))
+    out, iq, gain, _ = port.tx_ssb_f32(tx_params(g, name), g["tx_%s_in" % name])
+    assert np.all(np.abs(iq - g["tx_%s_iq" % name]) <= iq_tolerance(g["tx_%s_iq" % name]) + 1e-9)
+    assert np.allclose(gain, g["tx_%s_gain" % name], rtol=1e-5)
+    d = np.abs(out.astype(np.int32) - g["tx_%s_out" % name].astype(np.int32))
+    assert d.max() <= 1 and np.mean(d > 0) < 0.02
+
+
+@pytest.mark.parametrize("name", ["usb", "lsb"])
+def test_ref_tx_chain_reproduces_golden(ref, name):
+    g = np.load(os.path.join(GOLD, "tx_ssb_f32.npz"))
+    out, iq, gain, _ = ref.tx_ssb_f32(tx_params(g, name), g["tx_%s_in" % name])
+    assert np.array_equal(out, g["tx_%s_out" % name]) and np.array_equal(iq, g["tx_%s_iq" % name])
+
+
+def test_tx_chain_is_a_single_sideband_modulator(port):
+    """Domain property, independent of any implementation: a real two-tone through the USB chain comes out with its
+    energy on the positive-frequency side only (opposite sideband suppressed by the mask's stop band), and LSB mirrors."""
+    g = np.load(os.path.join(GOLD, "tx_ssb_f32.npz"))
+    for name, sign in (("usb", +1), ("lsb", -1)):
+        z = g["tx_%s_iq" % name].astype(np.float64); z = (z[:, 0] + 1j * z[:, 1])[1536:]
+        spec = np.abs(np.fft.fft(z * np.hanning(z.size))) ** 2
+        f = np.fft.fftfreq(z.size, 1 / 48000.0)
+        wanted = spec[(sign * f > 250) & (sign * f < 2800)].sum(); other = spec[(sign * f < -250) & (sign * f > -2800)].sum()
+        assert 10 * np.log10(wanted / other) > 60.0
+
+
 def test_chain_blocking_independence(port):
     """Carried state: 20 hops in one call == 20 calls of one hop (the firmware cadence accumulates 8 x 48 frames)."""
     g = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))
