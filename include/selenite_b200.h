@@ -45,6 +45,8 @@ extern "C" {
 #define SLB_CHAIN_RX_SSB_F32  1    /* unpack -> FFT overlap-save SSB demod -> biquad cascade -> AGC -> pack */
 #define SLB_CHAIN_TX_SSB_F32  2    /* mic (L of L=R) -> FFT overlap-save SSB modulator (band-pass + Hilbert) -> ALC -> I/Q pack */
 
+#define SLB_CHAIN_CHAN64_F32  3    /* wideband stream -> 64-branch polyphase FFT channelizer -> per-bin demod + AGC -> pack */
+
 #define SLB_MAX_STAGES 4
 #define SLB_MAX_MASKS  8
 
@@ -77,6 +79,20 @@ typedef struct
   uint32_t alc_block;                    /* ALC detector block [arm_cmplx_mag_f32 + arm_max_f32] = firmware block; this build: 48 */
   float    alc_target, alc_decay, alc_floor, alc_gmax;
 } slb_tx_f32_params;
+
+/* CHAN-64-f32 chain parameters (BASELINE config 4). The context's `channels` are WIDEBAND streams; each
+ * yields `bins` narrowband channels at fs/bins. Oracle stage for each field in brackets. */
+#define SLB_CHAN_BINS 64
+#define SLB_CHAN_TAPS 8
+typedef struct
+{
+  uint32_t bins;                         /* branches = FFT length = decimation [arm_cfft_f32]; this build: 64 */
+  uint32_t taps_per_branch;              /* [arm_fir_f32 numTaps per branch]; this build: 8 */
+  uint32_t agc_block;                    /* narrowband samples per AGC block = one firmware block (1 ms); this build: 3 */
+  uint32_t envelope;                     /* demodulator per bin: 0 = product detector (real part), 1 = envelope [arm_cmplx_mag_f32] */
+  float    agc_target, agc_decay, agc_floor, agc_gmax;
+  float    proto[SLB_CHAN_BINS * SLB_CHAN_TAPS];   /* prototype low-pass h[n]; branch r uses e_r[p] = h[bins*p + bins-1-r] */
+} slb_chan_params;
 
 /* ---- life cycle ---- */
 int  slb_create (const slb_config *cfg, slb_ctx **out);
@@ -124,6 +140,16 @@ int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
  * chain SLB_DSP_In_Buff_Write runs the modulator at the 1 ms cadence exactly as it runs the demodulator for RX. */
 int slb_tx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream);
 int slb_tx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames);
+/* Channelizer (context created with SLB_CHAIN_CHAN64_F32): in = wideband I/Q [streams][frames][2] int16, out =
+ * demodulated narrowband audio, channel-major [streams][64 bins][frames/64][2] int16 (L = R). frames % 768 == 0
+ * (4 firmware blocks of 192 frames). Debug taps (slb_rx_set_debug_taps): d_audio [streams][64][frames/64] f32 pre-AGC,
+ * d_gain [streams][64][frames/192]. The firmware ring API is not offered for this chain (one ring holds one I/Q stream,
+ * dsp_if.c:32-35); SLB_DSP_Set_Mode(AM) selects the envelope detector, any other mode the product detector. */
+int slb_default_chan_params (uint32_t fs, slb_chan_params *out);
+int slb_set_chan_params (slb_ctx *ctx, const slb_chan_params *p);
+int slb_get_chan_params (const slb_ctx *ctx, slb_chan_params *p);
+int slb_chan_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream);
+int slb_chan_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames);
 /* optional float tap: post-biquad, pre-AGC audio [channels][frames] f32 and per-block gains [channels][frames/agc_block]
  * are written by the next slb_rx_process_device call(s) when non-NULL (device pointers). TX chain: d_audio receives
  * the pre-ALC complex baseband [channels][frames][2] f32. */

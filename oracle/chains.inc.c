@@ -141,3 +141,60 @@ void SLO (tx_ssb_f32) (const slo_tx_f32_params *p, slo_tx_f32_state *st, const i
   }
   free (raw); free (mic); free (frame); free (prod); free (scaled); free (mag);
 }
+
+/* CHAN-64-f32: see slo_api.h. Straight-line CMSIS calls: one arm_fir_f32 instance per branch and rail over the whole
+ * call, one arm_cfft_f32 per hop, then the per-bin detector and AGC at the firmware's 1 ms cadence. */
+void SLO (chan_f32) (const slo_chan_params *p, slo_chan_state *st, const int16_t *in_iq, int16_t *out_lr,
+                     float *audio_dbg, float *gain_dbg, uint32_t frames)
+{
+  const uint32_t M = p->bins, P = p->taps_per_branch, B = p->agc_block, hops = frames / M;
+  float *xf = (float *) malloc (sizeof (float) * 2 * (size_t) frames);
+  float *bi = (float *) malloc (sizeof (float) * hops), *bq = (float *) malloc (sizeof (float) * hops);
+  float *vi = (float *) malloc (sizeof (float) * (size_t) M * hops), *vq = (float *) malloc (sizeof (float) * (size_t) M * hops);
+  float *fstate = (float *) malloc (sizeof (float) * (P + hops));
+  float *coef = (float *) malloc (sizeof (float) * P);
+  float *spec = (float *) malloc (sizeof (float) * 2 * M), *magb = (float *) malloc (sizeof (float) * M);
+  float *audio = (float *) malloc (sizeof (float) * (size_t) M * hops);
+  float *absb = (float *) malloc (sizeof (float) * B), *scaled = (float *) malloc (sizeof (float) * B);
+  int16_t *mono = (int16_t *) malloc (sizeof (int16_t) * B);
+
+  SLO (q15_to_float) (in_iq, xf, 2 * frames);
+  for (uint32_t r = 0; r < M; r++)
+  {
+    /* branch taps e_r[p] = h[M p + M-1-r], handed to CMSIS time-reversed (arm_fir_f32.c:54-66) */
+    for (uint32_t k = 0; k < P; k++) coef[k] = p->proto[M * (P - 1 - k) + (M - 1 - r)];
+    for (uint32_t m = 0; m < hops; m++) { bi[m] = xf[2 * ((size_t) M * m + r)]; bq[m] = xf[2 * ((size_t) M * m + r) + 1]; }
+    memset (fstate, 0, sizeof (float) * (P + hops)); memcpy (fstate, st->fir_i[r], sizeof (float) * (P - 1));
+    SLO (fir_f32) (coef, P, fstate, bi, vi + (size_t) r * hops, hops, B);
+    memcpy (st->fir_i[r], fstate, sizeof (float) * (P - 1));
+    memset (fstate, 0, sizeof (float) * (P + hops)); memcpy (fstate, st->fir_q[r], sizeof (float) * (P - 1));
+    SLO (fir_f32) (coef, P, fstate, bq, vq + (size_t) r * hops, hops, B);
+    memcpy (st->fir_q[r], fstate, sizeof (float) * (P - 1));
+  }
+  for (uint32_t m = 0; m < hops; m++)
+  {
+    for (uint32_t r = 0; r < M; r++) { spec[2 * r] = vi[(size_t) r * hops + m]; spec[2 * r + 1] = vq[(size_t) r * hops + m]; }
+    SLO (cfft_f32) (spec, M, 0, 1);
+    if (p->envelope) { SLO (cmplx_mag_f32) (spec, magb, M); for (uint32_t k = 0; k < M; k++) audio[(size_t) k * hops + m] = magb[k]; }
+    else for (uint32_t k = 0; k < M; k++) audio[(size_t) k * hops + m] = spec[2 * k];
+  }
+  if (audio_dbg) memcpy (audio_dbg, audio, sizeof (float) * (size_t) M * hops);
+  for (uint32_t k = 0; k < M; k++)
+    for (uint32_t b = 0; b < hops; b += B)
+    {
+      const float *a = audio + (size_t) k * hops + b;
+      SLO (abs_f32) (a, absb, B);
+      float peak = SLO (max_f32) (absb, B, 0);
+      float rel = st->env[k] * p->agc_decay;
+      float env = peak > rel ? peak : rel;
+      float den = env > p->agc_floor ? env : p->agc_floor;
+      float g = p->agc_target / den;
+      if (g > p->agc_gmax) g = p->agc_gmax;
+      st->env[k] = env;
+      if (gain_dbg) gain_dbg[(size_t) k * (hops / B) + b / B] = g;
+      SLO (scale_f32) (a, g, scaled, B);
+      SLO (float_to_q15) (scaled, mono, B);
+      for (uint32_t i = 0; i < B; i++) { out_lr[2 * ((size_t) k * hops + b + i)] = mono[i]; out_lr[2 * ((size_t) k * hops + b + i) + 1] = mono[i]; }
+    }
+  free (xf); free (bi); free (bq); free (vi); free (vq); free (fstate); free (coef); free (spec); free (magb); free (audio); free (absb); free (scaled); free (mono);
+}

@@ -150,6 +150,31 @@ typedef struct
 void SLO (tx_ssb_f32) (const slo_tx_f32_params *p, slo_tx_f32_state *st, const int16_t *in_lr, int16_t *out_iq,
                        float *iq_dbg, float *gain_dbg, uint32_t frames);
 
+/* CHAN-64-f32 (BASELINE config 4): one wideband stream -> q15_to_float -> `bins`-branch polyphase
+ * filter [branch r = fir_f32 with taps e_r[p] = proto[bins*p + bins-1-r] on the commutated input x[bins*m + r], I and Q
+ * separately] -> cfft_f32(len bins, forward) per hop -> per bin: real part (or cmplx_mag when `envelope`) ->
+ * per-`agc_block` AGC [abs, max, gain law, scale] -> float_to_q15, written channel-major [bin][hop] L = R. */
+#define SLO_CHAN_MAX_BINS 64
+#define SLO_CHAN_MAX_TAPS 8
+typedef struct
+{
+  uint32_t bins, taps_per_branch, agc_block, envelope;
+  float agc_target, agc_decay, agc_floor, agc_gmax;
+  const float *proto;                                   /* bins * taps_per_branch */
+} slo_chan_params;
+
+typedef struct
+{
+  float fir_i[SLO_CHAN_MAX_BINS][SLO_CHAN_MAX_TAPS];    /* arm_fir_f32 history per branch (numTaps-1 used) */
+  float fir_q[SLO_CHAN_MAX_BINS][SLO_CHAN_MAX_TAPS];
+  float env[SLO_CHAN_MAX_BINS];
+} slo_chan_state;
+
+/* frames % (bins * agc_block) == 0. out_lr: [bins][frames/bins][2]; audio_dbg (optional): [bins][frames/bins];
+ * gain_dbg (optional): [bins][frames/bins/agc_block]. */
+void SLO (chan_f32) (const slo_chan_params *p, slo_chan_state *st, const int16_t *in_iq, int16_t *out_lr,
+                     float *audio_dbg, float *gain_dbg, uint32_t frames);
+
 #ifdef __cplusplus
 }
 #endif

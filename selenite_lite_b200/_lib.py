@@ -24,6 +24,12 @@ class TxF32Params(C.Structure):
                 ("alc_target", C.c_float), ("alc_decay", C.c_float), ("alc_floor", C.c_float), ("alc_gmax", C.c_float)]
 
 
+class ChanParams(C.Structure):
+    _fields_ = [("bins", C.c_uint32), ("taps_per_branch", C.c_uint32), ("agc_block", C.c_uint32), ("envelope", C.c_uint32),
+                ("agc_target", C.c_float), ("agc_decay", C.c_float), ("agc_floor", C.c_float), ("agc_gmax", C.c_float),
+                ("proto", C.c_float * 512)]
+
+
 # every symbol include/selenite_b200.h declares: name -> (restype, argtypes), derived from the header text so the
 # binding cannot drift from the ABI
 _P = C.c_void_p

@@ -34,6 +34,7 @@ struct slb_ctx
   std::vector<uint8_t> slot_host;      // [C]
   std::vector<uint8_t> mode_host;      // [C]
   bool tx_mode = false;
+  Chan64State *chan = nullptr;         // SLB_CHAIN_CHAN64_F32 only
 
   // device: chain constants + carried state
   float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
@@ -115,6 +116,7 @@ static int reset_state (slb_ctx *ctx)
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   ctx->flag_base = 0; ctx->ovl_parity = 0; ctx->acc_fill = 0; ctx->proc_cur = 0;
   ctx->ring_in.reset (R); ctx->ring_out.reset (R);
+  if (ctx->chan) return chan64_reset (ctx, ctx->chan);
   return SLB_OK;
 }
 
@@ -134,7 +136,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   *out = nullptr;
   if (cfg->channels == 0) return fail (nullptr, SLB_ERR_ARG, "channels must be > 0");
   if (cfg->fs != 48000u && cfg->fs != 96000u && cfg->fs != 192000u) return fail (nullptr, SLB_ERR_ARG, "fs must be 48000, 96000 or 192000");
-  if (cfg->chain != SLB_CHAIN_PASS && !is_ssb_chain (cfg->chain)) return fail (nullptr, SLB_ERR_ARG, "unknown chain");
+  if (cfg->chain != SLB_CHAIN_PASS && !is_ssb_chain (cfg->chain) && cfg->chain != SLB_CHAIN_CHAN64_F32) return fail (nullptr, SLB_ERR_ARG, "unknown chain");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -178,6 +180,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
 #undef CKC
   int rc = upload_chain_constants (ctx);
   if (rc == SLB_OK) rc = reset_state (ctx);
+  if (rc == SLB_OK && cfg->chain == SLB_CHAIN_CHAN64_F32) rc = chan64_create (ctx, C, cfg->fs, &ctx->chan);
   if (rc != SLB_OK) { g_create_error = ctx->err; slb_destroy (ctx); return rc; }
   *out = ctx;
   return SLB_OK;
@@ -188,6 +191,7 @@ void slb_destroy (slb_ctx *ctx)
   if (!ctx) return;
   cudaSetDevice (ctx->cfg.device);
   cudaDeviceSynchronize ();
+  chan64_destroy (ctx->chan);
   cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
@@ -258,6 +262,7 @@ int slb_rx_set_debug_taps (slb_ctx *ctx, float *d_audio, float *d_gain)
 {
   if (!ctx) return SLB_ERR_ARG;
   ctx->dbg_audio = d_audio; ctx->dbg_gain = d_gain;
+  if (ctx->chan) chan64_set_debug (ctx->chan, d_audio, d_gain);
   return SLB_OK;
 }
 
@@ -288,6 +293,14 @@ int SLB_DSP_Set_Mode_Channel (slb_ctx *ctx, uint32_t ch, uint8_t mode)
 int SLB_DSP_Set_Mode (slb_ctx *ctx, uint8_t mode)     // dsp_if.c:367-370 is the empty hook this fills
 {
   if (!ctx) return SLB_ERR_ARG;
+  if (ctx->chan)                                       // channelizer: the mode picks the per-bin detector
+  {
+    if (mode == SLB_MODE_FM) return fail (ctx, SLB_ERR_UNSUPPORTED, "no FM discriminator in the channelizer chain");
+    slb_chan_params p = *chan64_params (ctx->chan);
+    p.envelope = (mode == SLB_MODE_AM) ? 1u : 0u;
+    CK (ctx, cudaSetDevice (ctx->cfg.device));
+    return chan64_set_params (ctx, ctx->chan, &p);
+  }
   const int slot = mode_to_mask_slot (mode);
   if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "AM/FM demodulators are not built yet (DESIGN.md: next)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
@@ -331,6 +344,7 @@ static int ensure_blk (slb_ctx *ctx, size_t frames)
 
 static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_t frames)
 {
+  if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
   const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames;
   if (!pbuf || frames == 0 || frames + 1 > R) return fail (ctx, SLB_ERR_ARG, "block must hold 1..DSP_BUFF_SIZE-1 frames");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
@@ -372,6 +386,7 @@ static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_
 
 static int ring_read_common (slb_ctx *ctx, int which, void *pbuf, uint32_t frames)
 {
+  if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
   const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames;
   if (!pbuf || frames == 0) return fail (ctx, SLB_ERR_ARG, "empty read");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
@@ -450,6 +465,7 @@ int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp9
 static int process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream, bool want_tx)
 {
   if (!ctx || !d_in || !d_out || frames == 0) return SLB_ERR_ARG;
+  if (ctx->chan) return fail (ctx, SLB_ERR_STATE, "channelizer context: use slb_chan_process_*");
   if (want_tx != (ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32)) return fail (ctx, SLB_ERR_STATE, "context was created for the other direction (cfg.chain)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   if (ctx->cfg.chain == SLB_CHAIN_PASS)
@@ -471,6 +487,7 @@ int slb_tx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, ui
 static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames, bool want_tx)
 {
   if (!ctx || !h_in || !h_out || frames == 0) return SLB_ERR_ARG;
+  if (ctx->chan) return fail (ctx, SLB_ERR_STATE, "channelizer context: use slb_chan_process_*");
   if (want_tx != (ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32)) return fail (ctx, SLB_ERR_STATE, "context was created for the other direction (cfg.chain)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   const bool chain = is_ssb_chain (ctx->cfg.chain);
@@ -523,6 +540,75 @@ int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
 int slb_tx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames) { return process_host (ctx, h_in, h_out, frames, true); }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Channelizer bulk path (SLB_CHAIN_CHAN64_F32)
+// ------------------------------------------------------------------------------------------------------------------
+int slb_default_chan_params (uint32_t fs, slb_chan_params *out) { return design_default_chan (fs, out); }
+int slb_set_chan_params (slb_ctx *ctx, const slb_chan_params *p)
+{
+  if (!ctx || !p) return SLB_ERR_ARG;
+  if (!ctx->chan) return fail (ctx, SLB_ERR_STATE, "not a channelizer context");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  CK (ctx, cudaDeviceSynchronize ());
+  return chan64_set_params (ctx, ctx->chan, p);
+}
+int slb_get_chan_params (const slb_ctx *ctx, slb_chan_params *p)
+{
+  if (!ctx || !p || !ctx->chan) return SLB_ERR_ARG;
+  *p = *chan64_params (ctx->chan);
+  return SLB_OK;
+}
+int slb_chan_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream)
+{
+  if (!ctx || !d_in || !d_out || frames == 0) return SLB_ERR_ARG;
+  if (!ctx->chan) return fail (ctx, SLB_ERR_STATE, "not a channelizer context (cfg.chain)");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  int rc = chan64_launch (ctx, ctx->chan, d_in, d_out, 0, ctx->cfg.channels, frames, ctx->sm_count, stream, true);
+  if (rc) return rc;
+  chan64_advance (ctx->chan);
+  return SLB_OK;
+}
+int slb_chan_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames)
+{
+  if (!ctx || !h_in || !h_out || frames == 0) return SLB_ERR_ARG;
+  if (!ctx->chan) return fail (ctx, SLB_ERR_STATE, "not a channelizer context (cfg.chain)");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const uint32_t S = ctx->cfg.channels;
+  const size_t st_bytes = (size_t) frames * 4;          // per stream, in and out alike (64 bins x frames/64 x 4 B)
+  uint32_t group = (uint32_t) ((size_t) (48u << 20) / st_bytes);
+  if (group < 1) group = 1;
+  if (group > S) group = S;
+  const size_t need = (size_t) group * st_bytes;
+  if (need > ctx->bulk_bytes)
+  {
+    for (int s = 0; s < kBulkSlots; s++)
+    {
+      if (ctx->bulk_stream[s]) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
+      CK (ctx, cudaFree (ctx->d_bulk_in[s])); CK (ctx, cudaFree (ctx->d_bulk_out[s]));
+      ctx->d_bulk_in[s] = ctx->d_bulk_out[s] = nullptr;
+      CK (ctx, cudaMalloc (&ctx->d_bulk_in[s], need)); CK (ctx, cudaMalloc (&ctx->d_bulk_out[s], need));
+      if (!ctx->bulk_stream[s]) CK (ctx, cudaStreamCreateWithFlags (&ctx->bulk_stream[s], cudaStreamNonBlocking));
+      if (!ctx->bulk_done[s]) CK (ctx, cudaEventCreateWithFlags (&ctx->bulk_done[s], cudaEventDisableTiming));
+    }
+    ctx->bulk_bytes = need;
+  }
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  int slot = 0;
+  for (uint32_t s0 = 0; s0 < S; s0 += group, slot = (slot + 1) % kBulkSlots)
+  {
+    const uint32_t n = (S - s0 < group) ? S - s0 : group;
+    cudaStream_t st = ctx->bulk_stream[slot];
+    const size_t bytes = (size_t) n * st_bytes;
+    CK (ctx, cudaMemcpyAsync (ctx->d_bulk_in[slot], reinterpret_cast<const char *> (h_in) + (size_t) s0 * st_bytes, bytes, cudaMemcpyHostToDevice, st));
+    int rc = chan64_launch (ctx, ctx->chan, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], s0, n, frames, ctx->sm_count, st, false);
+    if (rc) return rc;
+    CK (ctx, cudaMemcpyAsync (reinterpret_cast<char *> (h_out) + (size_t) s0 * st_bytes, ctx->d_bulk_out[slot], bytes, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kBulkSlots; s++) if (ctx->bulk_stream[s]) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
+  chan64_advance (ctx->chan);
+  return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Checkpoint: everything a later call depends on
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
@@ -537,7 +623,7 @@ constexpr uint32_t kMagic = 0x534C4232u;   // 'SLB2'
 static size_t state_bytes (const slb_ctx *ctx)
 {
   const size_t C = ctx->cfg.channels, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop, R = ctx->geo.ring_frames;
-  return sizeof (StateHeader) + C /*modes*/ + C * ovl * 4 + C * 8 * 4 + 4 * C * R * 2 + C * hop * 4 * 2;
+  return sizeof (StateHeader) + C /*modes*/ + C * ovl * 4 + C * 8 * 4 + 4 * C * R * 2 + C * hop * 4 * 2 + (ctx->chan ? chan64_state_bytes (ctx->chan) : 0);
 }
 int slb_state_size (const slb_ctx *ctx, size_t *bytes) { if (!ctx || !bytes) return SLB_ERR_ARG; *bytes = state_bytes (ctx); return SLB_OK; }
 
@@ -559,7 +645,8 @@ int slb_state_save (slb_ctx *ctx, void *buf, size_t bytes)
   CK (ctx, cudaMemcpy (p, ctx->d_state, C * 8 * 4, cudaMemcpyDeviceToHost)); p += C * 8 * 4;
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) { CK (ctx, cudaMemcpy (p, ctx->d_ring[w][k], C * R * 2, cudaMemcpyDeviceToHost)); p += C * R * 2; }
   CK (ctx, cudaMemcpy (p, ctx->d_acc, C * hop * 4, cudaMemcpyDeviceToHost)); p += C * hop * 4;
-  CK (ctx, cudaMemcpy (p, ctx->d_proc[ctx->proc_cur], C * hop * 4, cudaMemcpyDeviceToHost));
+  CK (ctx, cudaMemcpy (p, ctx->d_proc[ctx->proc_cur], C * hop * 4, cudaMemcpyDeviceToHost)); p += C * hop * 4;
+  if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_save (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state save failed"); }
   return SLB_OK;
 }
 
@@ -581,7 +668,8 @@ int slb_state_load (slb_ctx *ctx, const void *buf, size_t bytes)
   CK (ctx, cudaMemcpy (ctx->d_state, p, C * 8 * 4, cudaMemcpyHostToDevice)); p += C * 8 * 4;
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) { CK (ctx, cudaMemcpy (ctx->d_ring[w][k], p, C * R * 2, cudaMemcpyHostToDevice)); p += C * R * 2; }
   CK (ctx, cudaMemcpy (ctx->d_acc, p, C * hop * 4, cudaMemcpyHostToDevice)); p += C * hop * 4;
-  CK (ctx, cudaMemcpy (ctx->d_proc[0], p, C * hop * 4, cudaMemcpyHostToDevice));
+  CK (ctx, cudaMemcpy (ctx->d_proc[0], p, C * hop * 4, cudaMemcpyHostToDevice)); p += C * hop * 4;
+  if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_load (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state load failed"); }
   // per-channel tile counters restart from zero on this context
   CK (ctx, cudaMemset (ctx->d_flag, 0, C * sizeof (unsigned)));
   ctx->flag_base = 0; ctx->acc_fill = h.acc_fill; ctx->tx_mode = h.tx_mode != 0;
@@ -607,7 +695,7 @@ slb_ctx *dropin ()
     const char *fs = std::getenv ("SELENITE_B200_FS"), *dev = std::getenv ("SELENITE_B200_DEVICE"), *ch = std::getenv ("SELENITE_B200_CHAIN");
     cfg.fs = fs ? (uint32_t) std::atoi (fs) : 48000u;
     cfg.device = dev ? std::atoi (dev) : 0;
-    cfg.chain = (ch && std::strcmp (ch, "rx_ssb_f32") == 0) ? SLB_CHAIN_RX_SSB_F32 : (ch && std::strcmp (ch, "tx_ssb_f32") == 0) ? SLB_CHAIN_TX_SSB_F32 : SLB_CHAIN_PASS;
+    cfg.chain = (ch && std::strcmp (ch, "rx_ssb_f32") == 0) ? SLB_CHAIN_RX_SSB_F32 : (ch && std::strcmp (ch, "tx_ssb_f32") == 0) ? SLB_CHAIN_TX_SSB_F32 : SLB_CHAIN_PASS;   // (the channelizer has no single-channel drop-in)
     g_dropin_status = slb_create (&cfg, &g_dropin);
     if (g_dropin_status != SLB_OK) std::fprintf (stderr, "selenite-b200: drop-in context failed: %s\n", slb_last_error (nullptr));
   }

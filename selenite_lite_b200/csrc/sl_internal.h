@@ -86,6 +86,22 @@ void rx_ssb_f32_pack_twiddles (float *out /* kTwiddleFloats */);
 void rx_ssb_f32_pack_mask (const float *mask_re_im, float scale, float *out /* 2 * fft_len floats */);
 constexpr size_t kTwiddleFloats = 6 * 32 * 4;
 
+// ---- CHAN-64-f32 (sl_chan64.cu): state object owned by the context ----
+struct Chan64State;
+int design_default_chan (uint32_t fs, slb_chan_params *p);
+int chan64_create (slb_ctx *ctx, uint32_t streams, uint32_t fs, Chan64State **out);
+void chan64_destroy (Chan64State *st);
+int chan64_reset (slb_ctx *ctx, Chan64State *st);
+int chan64_set_params (slb_ctx *ctx, Chan64State *st, const slb_chan_params *p);
+const slb_chan_params *chan64_params (const Chan64State *st);
+void chan64_set_debug (Chan64State *st, float *audio, float *gain);
+size_t chan64_state_bytes (const Chan64State *st);
+int chan64_state_save (Chan64State *st, char *dst);
+int chan64_state_load (Chan64State *st, const char *src);
+int chan64_launch (slb_ctx *ctx, Chan64State *st, const int16_t *d_in, int16_t *d_out, uint32_t s0, uint32_t ns, uint32_t frames,
+                   int sm_count, void *stream, bool with_debug);
+void chan64_advance (Chan64State *st);
+
 // ---- context accessors for translation units that do not see the struct (sl_stages.cu, sl_chains.cu) ----
 int ctx_device (const slb_ctx *ctx);
 size_t ctx_channels (const slb_ctx *ctx);

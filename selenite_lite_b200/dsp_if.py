@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 
-CHAIN_PASS, CHAIN_RX_SSB_F32, CHAIN_TX_SSB_F32 = 0, 1, 2
+CHAIN_PASS, CHAIN_RX_SSB_F32, CHAIN_TX_SSB_F32, CHAIN_CHAN64_F32 = 0, 1, 2, 3
 MODE_LSB, MODE_USB, MODE_CW, MODE_CWR, MODE_AM, MODE_FM, MODE_DIG, MODE_PKT = 0x00, 0x01, 0x02, 0x03, 0x04, 0x08, 0x0A, 0x0C
 
 
@@ -37,6 +37,20 @@ def default_tx_f32_params(fs=48000):
 def tx_params_to_dict(p, mask):
     return dict(fft_len=p.fft_len, hop=p.hop, alc_block=p.alc_block, alc_target=p.alc_target, alc_decay=p.alc_decay,
                 alc_floor=p.alc_floor, alc_gmax=p.alc_gmax, mask=mask)
+
+
+def default_chan_params(fs=192000):
+    p = _lib.ChanParams()
+    rc = _lib.load().slb_default_chan_params(fs, C.byref(p))
+    if rc:
+        raise SeleniteError("slb_default_chan_params -> %d" % rc)
+    return p
+
+
+def chan_params_to_dict(p):
+    return dict(bins=p.bins, taps_per_branch=p.taps_per_branch, agc_block=p.agc_block, envelope=p.envelope,
+                agc_target=p.agc_target, agc_decay=p.agc_decay, agc_floor=p.agc_floor, agc_gmax=p.agc_gmax,
+                proto=np.array(p.proto[:p.bins * p.taps_per_branch], np.float32))
 
 
 def default_mask(fs=48000, fft_len=512, mode=MODE_USB):
@@ -151,7 +165,16 @@ class DspIf:
 
     def set_tx_params(self, p): self._ck(self.lib.slb_set_tx_f32_params(self.h, C.byref(p)), "set_tx_f32_params")
 
+    def chan_params(self):
+        p = _lib.ChanParams()
+        self._ck(self.lib.slb_get_chan_params(self.h, C.byref(p)), "get_chan_params")
+        return p
+
+    def set_chan_params(self, p): self._ck(self.lib.slb_set_chan_params(self.h, C.byref(p)), "set_chan_params")
+
     def oracle_params(self, mode=MODE_USB):
+        if self.chain == CHAIN_CHAN64_F32:
+            return chan_params_to_dict(self.chan_params())
         if self.chain == CHAIN_TX_SSB_F32:
             return tx_params_to_dict(self.tx_params(), self.mask(mode))
         return params_to_dict(self.rx_params(), self.mask(mode))
@@ -177,6 +200,27 @@ class DspIf:
     def tx_process(self, x, out=None, stream=None):
         """TX direction (context created with CHAIN_TX_SSB_F32): mic frames (L = R) in, modulated I/Q frames out."""
         return self.rx_process(x, out, stream, _dir="tx")
+
+    def chan_process(self, x, out=None, stream=None):
+        """Channelizer (context created with CHAIN_CHAN64_F32): x int16 [streams][frames][2] wideband I/Q ->
+        int16 [streams][64][frames/64][2] demodulated narrowband audio (L = R), channel-major."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, np.int16)
+            frames = x.shape[1]
+            out = np.empty((x.shape[0], 64, frames // 64, 2), np.int16) if out is None else out
+            self._ck(self.lib.slb_chan_process_host(self.h, x.ctypes.data, out.ctypes.data, frames), "chan_process_host")
+            return out
+        import torch
+        assert x.is_cuda and x.dtype == torch.int16 and x.is_contiguous() and x.shape[0] == self.channels
+        frames = x.shape[1]
+        out = torch.empty((x.shape[0], 64, frames // 64, 2), dtype=torch.int16, device=x.device) if out is None else out
+        s = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+        self._ck(self.lib.slb_chan_process_device(self.h, x.data_ptr(), out.data_ptr(), frames, s), "chan_process_device")
+        return out
+
+    def chan_process_pinned(self, x_pinned, out_pinned):
+        self._ck(self.lib.slb_chan_process_host(self.h, x_pinned.data_ptr(), out_pinned.data_ptr(), x_pinned.shape[1]), "chan_process_host")
+        return out_pinned
 
     def rx_process_pinned(self, x_pinned, out_pinned):
         """torch pinned host tensors [channels][frames][2]; chunked H2D / kernel / D2H overlap inside the library."""

@@ -39,3 +39,27 @@ def synth_mic(channels, frames, fs=48000, tones=(700.0, 1900.0), amp=0.2, sigma=
         v = np.clip(np.rint(m * 32768.0), -32768, 32767).astype(np.int16)
         out[k, :, 0] = v; out[k, :, 1] = v
     return out
+
+
+def wideband_occupancy(stream, bins=64, seed=SEED):
+    """Config 4: which bins of wideband stream `stream` carry a tone (random half of the bins)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 0xC4A7 + int(stream)))
+    return rng.random(bins) < 0.5
+
+
+def synth_wideband(streams, frames, fs=192000, bins=64, amp=0.02, sigma=0.01, offset_hz=500.0, seed=SEED, first_stream=0):
+    """Config 4 input: int16[streams][frames][2]; one complex tone at bin-centre + 500 Hz in every occupied
+    bin (bin k is centred on k * fs/bins, k >= bins/2 meaning negative frequencies), plus complex white noise."""
+    out = np.empty((streams, frames, 2), np.int16)
+    n = np.arange(frames, dtype=np.float64)
+    for k in range(streams):
+        s = first_stream + k
+        rng = np.random.Generator(np.random.PCG64(seed + 0x1D00 + s))
+        z = sigma * (rng.standard_normal(frames) + 1j * rng.standard_normal(frames))
+        occ = wideband_occupancy(s, bins, seed)
+        for b in np.nonzero(occ)[0]:
+            fb = (b if b < bins // 2 else b - bins) * fs / bins + offset_hz
+            z = z + amp * np.exp(1j * (2.0 * np.pi * fb * n / fs + 0.37 * b + 0.11 * s))
+        out[k, :, 0] = np.clip(np.rint(z.real * 32768.0), -32768, 32767).astype(np.int16)
+        out[k, :, 1] = np.clip(np.rint(z.imag * 32768.0), -32768, 32767).astype(np.int16)
+    return out

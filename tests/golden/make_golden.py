@@ -45,6 +45,19 @@ def main():
     tx["tx_alc"] = np.array([tp.alc_target, tp.alc_decay, tp.alc_floor, tp.alc_gmax], np.float32)
     np.savez_compressed(os.path.join(HERE, "tx_ssb_f32.npz"), **tx)
 
+    # ---- CHAN-64-f32, config-4 style: one 192 kHz wideband stream, tones in a random half of the bins, 36 hops;
+    #      product detector and envelope detector
+    cp = slb.default_chan_params(192000)
+    ch = {}
+    xw = slb.synth_wideband(1, 768 * 3)[0]
+    ch["chan_in"] = xw; ch["chan_proto"] = np.array(cp.proto[:512], np.float32)
+    ch["chan_agc"] = np.array([cp.agc_target, cp.agc_decay, cp.agc_floor, cp.agc_gmax], np.float32)
+    for name, envl in (("prod", 0), ("env", 1)):
+        prm = slb.dsp_if.chan_params_to_dict(cp); prm["envelope"] = envl
+        y, audio, gain, _ = ref.chan_f32(prm, xw)
+        ch["chan_%s_out" % name] = y; ch["chan_%s_audio" % name] = audio; ch["chan_%s_gain" % name] = gain
+    np.savez_compressed(os.path.join(HERE, "chan64_f32.npz"), **ch)
+
     # ---- the firmware ring (unmodified dsp_if.c): ramp through In_Buff_Write/In_Buff_Read and Out_Buff_Write/Out_Buff_Read
     ring = {}
     for fs in (48000, 96000):
@@ -83,7 +96,7 @@ def main():
     cbq = np.array(p.biquad[:10], np.float32)
     st["biquad_df2T_f32"] = ref.biquad_df2T_f32(cbq, 2, np.zeros(4, np.float32), xf, 48)[0]
     np.savez_compressed(os.path.join(HERE, "stages.npz"), **st)
-    for f in ("rx_ssb_f32.npz", "tx_ssb_f32.npz", "ring.npz", "stages.npz"):
+    for f in ("rx_ssb_f32.npz", "tx_ssb_f32.npz", "chan64_f32.npz", "ring.npz", "stages.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 

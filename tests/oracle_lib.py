@@ -45,6 +45,16 @@ class TxF32State(C.Structure):
     _fields_ = [("ovl", C.c_int16 * MAX_FFT), ("env", C.c_float)]
 
 
+class ChanParams(C.Structure):
+    _fields_ = [("bins", u32), ("taps_per_branch", u32), ("agc_block", u32), ("envelope", u32),
+                ("agc_target", C.c_float), ("agc_decay", C.c_float), ("agc_floor", C.c_float), ("agc_gmax", C.c_float),
+                ("proto", C.POINTER(C.c_float))]
+
+
+class ChanState(C.Structure):
+    _fields_ = [("fir_i", C.c_float * (64 * 8)), ("fir_q", C.c_float * (64 * 8)), ("env", C.c_float * 64)]
+
+
 def build_oracles(want_ref=True):
     """Build the port (always) and, when the reference tree is mounted, the reference build."""
     subprocess.run(["make", "-s", "-C", ORACLE_DIR, "port"], check=True)
@@ -272,6 +282,25 @@ class Oracle:
         fn = self._f("tx_ssb_f32", [C.POINTER(TxF32Params), C.POINTER(TxF32State), i16p, i16p, f32p, f32p, u32])
         fn(C.byref(p), C.byref(st), x, out, iq, gain, frames)
         return out.reshape(frames, 2), iq.reshape(frames, 2), gain, st
+
+
+    def chan_f32(self, prm, in_iq, state=None, want_debug=True):
+        """One wideband stream int16[frames][2]. Returns out int16[bins][frames/bins][2], audio f32[bins][hops],
+        gain f32[bins][hops/agc_block], state."""
+        p = ChanParams()
+        p.bins, p.taps_per_branch, p.agc_block, p.envelope = prm["bins"], prm["taps_per_branch"], prm["agc_block"], int(prm["envelope"])
+        p.agc_target, p.agc_decay = float(prm["agc_target"]), float(prm["agc_decay"])
+        p.agc_floor, p.agc_gmax = float(prm["agc_floor"]), float(prm["agc_gmax"])
+        proto = np.ascontiguousarray(prm["proto"], np.float32)
+        p.proto = proto.ctypes.data_as(C.POINTER(C.c_float))
+        st = state if state is not None else ChanState()
+        x = np.ascontiguousarray(in_iq, np.int16).reshape(-1)
+        frames = x.size // 2; bins = prm["bins"]; hops = frames // bins
+        out = np.zeros(2 * bins * hops, np.int16)
+        audio = np.zeros(bins * hops, np.float32); gain = np.zeros(bins * hops // prm["agc_block"], np.float32)
+        fn = self._f("chan_f32", [C.POINTER(ChanParams), C.POINTER(ChanState), i16p, i16p, C.c_void_p, C.c_void_p, u32])
+        fn(C.byref(p), C.byref(st), x, out, audio.ctypes.data if want_debug else None, gain.ctypes.data if want_debug else None, frames)
+        return out.reshape(bins, hops, 2), audio.reshape(bins, hops), gain.reshape(bins, -1), st
 
 
 class RefRing:

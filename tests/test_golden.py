@@ -81,6 +81,65 @@ def test_tx_chain_is_a_single_sideband_modulator(port):
         assert 10 * np.log10(wanted / other) > 60.0
 
 
+def chan_params(g, envelope=0):
+    return dict(bins=64, taps_per_branch=8, agc_block=3, envelope=envelope, agc_target=g["chan_agc"][0], agc_decay=g["chan_agc"][1],
+                agc_floor=g["chan_agc"][2], agc_gmax=g["chan_agc"][3], proto=g["chan_proto"])
+
+
+def chan_tolerance(ref_audio, window=12):
+    """Channelizer audio [bins][hops]: 1e-5 * max(|ref|, rms over ALL bins of the same 12-hop (4 ms) window) - the
+    64-point FFT mixes every branch into every bin, so its float32 rounding noise scales with the whole spectrum frame."""
+    r = ref_audio.astype(np.float64)
+    bins, hops = r.shape
+    w = r.reshape(bins, hops // window, window)
+    rms = np.sqrt(np.mean(w ** 2, axis=(0, 2), keepdims=True))
+    return (1e-5 * np.maximum(np.abs(w), rms)).reshape(bins, hops)
+
+
+@pytest.mark.parametrize("name,envelope", [("prod", 0), ("env", 1)])
+def test_port_chan_chain_vs_golden(port, name, envelope):
+    g = np.load(os.path.join(GOLD, "chan64_f32.npz"))
+    out, audio, gain, _ = port.chan_f32(chan_params(g, envelope), g["chan_in"])
+    assert np.all(np.abs(audio - g["chan_%s_audio" % name]) <= chan_tolerance(g["chan_%s_audio" % name]) + 1e-9)
+    assert np.allclose(gain, g["chan_%s_gain" % name], rtol=2e-5)
+    d = np.abs(out.astype(np.int32) - g["chan_%s_out" % name].astype(np.int32))
+    assert d.max() <= 1 and np.mean(d > 0) < 0.02
+
+
+@pytest.mark.parametrize("name,envelope", [("prod", 0), ("env", 1)])
+def test_ref_chan_chain_reproduces_golden(ref, name, envelope):
+    g = np.load(os.path.join(GOLD, "chan64_f32.npz"))
+    out, audio, gain, _ = ref.chan_f32(chan_params(g, envelope), g["chan_in"])
+    assert np.array_equal(out, g["chan_%s_out" % name]) and np.array_equal(audio, g["chan_%s_audio" % name])
+
+
+def test_chan_chain_is_a_channelizer(port):
+    """Domain property: a tone at bin-centre + 500 Hz appears in its own bin as a 500 Hz tone at the 3 kHz narrowband
+    rate, and empty bins stay at the noise floor (> 20 dB below)."""
+    import selenite_lite_b200 as slb
+    g = np.load(os.path.join(GOLD, "chan64_f32.npz"))
+    occ = slb.signals.wideband_occupancy(0)
+    a = g["chan_prod_audio"].astype(np.float64)[:, 12:]
+    rms = np.sqrt(np.mean(a ** 2, axis=1))
+    assert 20 * np.log10(rms[occ].min() / rms[~occ].max()) > 15.0
+    k = int(np.nonzero(occ)[0][0]); n = np.arange(a.shape[1])
+    basis = np.stack([np.cos(2 * np.pi * 500 * n / 3000.0), np.sin(2 * np.pi * 500 * n / 3000.0)], 1)
+    coef, *_ = np.linalg.lstsq(basis, a[k], rcond=None)
+    assert np.sum((a[k] - basis @ coef) ** 2) < 0.05 * np.sum(a[k] ** 2)
+
+
+def test_chan_blocking_independence(port):
+    """Carried state (branch FIR histories, per-bin envelope): 3 calls of 768 frames == one call of 2304."""
+    g = np.load(os.path.join(GOLD, "chan64_f32.npz"))
+    prm = chan_params(g); x = g["chan_in"]
+    whole, _, _, _ = port.chan_f32(prm, x)
+    st = None; parts = []
+    for h in range(3):
+        o, _, _, st = port.chan_f32(prm, x[768 * h:768 * (h + 1)], st)
+        parts.append(o)
+    assert np.array_equal(np.concatenate(parts, 1), whole)
+
+
 def test_chain_blocking_independence(port):
     """Carried state: 20 hops in one call == 20 calls of one hop (the firmware cadence accumulates 8 x 48 frames)."""
     g = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))
