@@ -14,21 +14,24 @@
 // Work per wideband sample: 16 FMA (polyphase) + ~20 (FFT-64 as 8 x 8) + ~5 (AGC, pack): ~43 FP32 lane-ops, i.e. the
 // FP32 pipe (35 T lane-ops/s) and the HBM roof (6.5 TB/s / 8 B) are about equal for this chain.
 //
-// Structure. Work item = (stream, tile of 96 hops = 6144 wideband frames). Items are dealt tile-major to a persistent,
-// co-resident grid. Per item:
-//   A  one thread stages the tile's raw int16 frames (plus the 7 hops of FIR history that precede it) into shared memory
-//      with ONE bulk asynchronous copy (cp.async.bulk + mbarrier, SASS UBLKCP) - issued for item i+1 while the AGC phase
-//      of item i runs.
-//   B  six warps, 16 hops each, in two rounds of 8 hops. Polyphase: lane r owns branches r and r+32 with their 8+8
-//      coefficients in registers and a sliding window of 8 complex inputs per branch, so each input sample is read from
-//      shared memory once per round and each tap is one FMA in the oracle's accumulation order. The 8 x 64 branch
-//      outputs go through a warp-private scratch; the 64-point FFTs run as 8 x 8 on groups of 8 lanes, two hops per lane
-//      packed in FP32x2 registers (FADD2/FMUL2/FFMA2), with a skewed 8 x 8 exchange that is bank-conflict-free both ways.
-//   C  64 threads (one per bin) run the AGC over the tile's 32 blocks. The envelope recurrence env = max(peak, env*decay)
-//      is a max-plus scan whose carry-in comes from the previous tile of the same stream, which another CTA processes
-//      concurrently: tiles are chained with a DECOUPLED LOOK-BACK (publish the zero-start envelope at once, then the
-//      inclusive one) so that no tile waits for a predecessor's full AGC pass, and because fl(max(a,b)*d) =
-//      max(fl(a*d), fl(b*d)) the folded result is bit-identical to the oracle's sequential walk.
+// Structure. Work item = (stream, tile of 48 hops = 3072 wideband frames). Items are dealt tile-major to a persistent,
+// co-resident grid of warp-specialised CTAs (3 producer warps + 2 AGC warps, 3 CTAs per SM); nothing in the steady state
+// is a CTA-wide barrier:
+//   * one thread stages each tile's raw int16 frames (plus the 7 hops of FIR history that precede it) into a
+//     double-buffered shared-memory tile with ONE bulk asynchronous copy (cp.async.bulk + mbarrier, SASS UBLKCP), two
+//     items ahead of the compute.
+//   * producer warps, 16 hops each, in two rounds of 8 hops. Polyphase: lane r owns branches r and r+32 with their 8+8
+//     coefficients in registers and a sliding window of 8 complex inputs per branch, so each input sample is read from
+//     shared memory once per round and each tap is one FMA in the oracle's accumulation order. The 8 x 64 branch
+//     outputs go through a warp-private scratch; the 64-point FFTs run as 8 x 8 on groups of 8 lanes, two hops per lane
+//     packed in FP32x2 registers (FADD2/FMUL2/FFMA2), with a skewed 8 x 8 exchange that is bank-conflict-free both ways.
+//     The detector output goes to a double-buffered audio tile [bin][hop]; named barriers (full / empty per buffer)
+//     connect the two sides as in the RX kernel.
+//   * 64 AGC threads (one per bin) work one tile behind. The envelope recurrence env = max(peak, env*decay) is a
+//     max-plus scan whose carry-in comes from the previous tile of the same stream, which another CTA processes
+//     concurrently: tiles are chained with a DECOUPLED LOOK-BACK (publish the zero-start envelope at once, then the
+//     inclusive one) so that no tile waits for a predecessor's full AGC pass, and because fl(max(a,b)*d) =
+//     max(fl(a*d), fl(b*d)) the folded result is bit-identical to the oracle's sequential walk.
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
@@ -43,20 +46,24 @@ namespace {
 constexpr int kBins = 64;                        // branches = FFT length = decimation
 constexpr int kTaps = 8;                         // taps per branch (prototype = 512 taps)
 constexpr int kHistHops = kTaps - 1;             // hops of input history a tile needs
-constexpr int kTileHops = 96;                    // hops per tile = 32 AGC blocks of 3
+constexpr int kTileHops = 48;                    // hops per tile = 16 AGC blocks of 3
 constexpr int kBlk = 3;                          // AGC block: 1 ms = 192 wideband frames = 3 narrowband samples
 constexpr int kTileBlocks = kTileHops / kBlk;
-constexpr int kWarps = 6, kThreads = 32 * kWarps;
-constexpr int kHopsPerWarp = kTileHops / kWarps; // 16 = two rounds of 8
+constexpr int kFftWarps = 3, kAgcWarps = 2;
+constexpr int kFftThreads = 32 * kFftWarps, kAgcThreads = 32 * kAgcWarps, kThreads = kFftThreads + kAgcThreads;
+constexpr int kHopsPerWarp = kTileHops / kFftWarps;  // 16 = two rounds of 8
 constexpr int kRowUnits = 72;                    // 64-bit units per hop-pair row of the FFT scratch (64 + 8: rows of the two
                                                  // hop pairs a half-warp touches land in different bank halves)
-constexpr int kAudioStride = 100;                // floats per bin row of the audio tile (= 4 mod 32, 16-byte aligned rows)
+constexpr int kAudioStride = 52;                 // floats per bin row of the audio tile: 16-byte aligned rows, and 52 c mod 32
+                                                 // runs through all multiples of 4 for c = 0..7 (conflict-free both ways)
 constexpr int kLookBackMax = 8;                  // deepest fold before a tile insists on an inclusive predecessor
 
-constexpr size_t kRawBytes = (size_t) (kTileHops + kHistHops) * kBins * 4;
-constexpr size_t kScratchBytes = (size_t) kWarps * 2 * 4 * kRowUnits * 8;
-constexpr size_t kAudioBytes = (size_t) kBins * kAudioStride * 4;
-constexpr size_t kSmemBytes = kRawBytes + kScratchBytes + kAudioBytes + 64 * 8 /* twiddles */ + 16 /* mbarrier */;
+constexpr size_t kRawWords = (size_t) (kTileHops + kHistHops) * kBins;
+constexpr size_t kRawBytes = 2 * kRawWords * 4;                                  // double-buffered
+constexpr size_t kScratchBytes = (size_t) kFftWarps * 2 * 4 * kRowUnits * 8;
+constexpr size_t kAudioWords = (size_t) kBins * kAudioStride;
+constexpr size_t kAudioBytes = 2 * kAudioWords * 4;                              // double-buffered
+constexpr size_t kSmemBytes = kRawBytes + kScratchBytes + kAudioBytes + 64 * 8 /* twiddles */ + 32 /* mbarriers */;
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk (float lo, float hi) { u64 r; asm ("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -138,8 +145,10 @@ __device__ __forceinline__ unsigned ld_relaxed (const unsigned *p)
   unsigned v; asm volatile ("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void st_release (unsigned *p, unsigned v) { asm volatile ("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-// named barrier 1: the 64 AGC threads only
-__device__ __forceinline__ void agc_bar () { asm volatile ("bar.sync 1, 64;" ::: "memory"); }
+// named barriers (like the RX kernel): 1,2 = audio buffer 0/1 full; 3,4 = audio buffer 0/1 empty (all 160 threads take
+// part in each, one side syncs, the other arrives); 5 = the FFT warps among themselves; 6 = the AGC warps
+__device__ __forceinline__ void bar_sync (int id, int n) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive (int id, int n) { asm volatile ("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct KParams
 {
@@ -154,69 +163,77 @@ struct KParams
   float target, decay, floor, gmax;
 };
 
-// ns steps of the oracle's release walk from a zero peak history: x <- fl(x * decay), exactly as chains.inc.c does per block
+// n steps of the oracle's release walk from a zero peak history: x <- fl(x * decay), exactly as chains.inc.c does per block
 __device__ __forceinline__ float decay_n (float x, float decay, int n)
 {
   for (int i = 0; i < n; i++) x = x * decay;
   return x;
 }
 
-__global__ void __launch_bounds__ (kThreads, 2) chan64_f32_kernel (const __grid_constant__ KParams P)
+__global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_constant__ KParams P)
 {
   extern __shared__ __align__ (128) unsigned char smem[];
   uint32_t *sRaw = reinterpret_cast<uint32_t *> (smem);
   u64 *sScr = reinterpret_cast<u64 *> (smem + kRawBytes);
   float *sAudio = reinterpret_cast<float *> (smem + kRawBytes + kScratchBytes);
   float2 *sTw = reinterpret_cast<float2 *> (smem + kRawBytes + kScratchBytes + kAudioBytes);
-  uint64_t *sBar = reinterpret_cast<uint64_t *> (smem + kRawBytes + kScratchBytes + kAudioBytes + 64 * 8);
+  uint64_t *sBar = reinterpret_cast<uint64_t *> (smem + kRawBytes + kScratchBytes + kAudioBytes + 64 * 8);   // [2]: raw buffer full
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned total = P.streams * P.tiles;
 
-  // issue the bulk copy of item `it` (thread 0 only): history rows + the tile's hops, contiguous in the stream except
-  // for tile 0, whose history comes from the carried state
-  auto issue_load = [&] (unsigned it) {
-    const uint32_t tile = it / P.streams, s = it % P.streams;
-    const uint32_t hops_here = min ((uint32_t) kTileHops, P.hops - tile * kTileHops);
-    const uint32_t *src = P.in + (size_t) s * P.hops * kBins + (size_t) tile * kTileHops * kBins;
-    mbar_expect_tx (sBar, (hops_here + kHistHops) * kBins * 4);
-    if (tile == 0)
-    {
-      bulk_g2s (sRaw, P.hist_in + (size_t) s * kHistHops * kBins, kHistHops * kBins * 4, sBar);
-      bulk_g2s (sRaw + kHistHops * kBins, src, hops_here * kBins * 4, sBar);
-    }
-    else
-      bulk_g2s (sRaw, src - kHistHops * kBins, (hops_here + kHistHops) * kBins * 4, sBar);
-  };
-
-  if (tid == 0) { mbar_init (sBar, 1); }
+  if (tid == 0) { mbar_init (sBar, 1); mbar_init (sBar + 1, 1); }
   if (tid < 64) sTw[tid] = P.tw[tid];
-  // branch coefficients of this lane: branches r = lane and lane + 32
-  float c0[kTaps], c1[kTaps];
-#pragma unroll
-  for (int p = 0; p < kTaps; p++) { c0[p] = P.coef[lane * kTaps + p]; c1[p] = P.coef[(lane + 32) * kTaps + p]; }
   __syncthreads ();
-  unsigned item = blockIdx.x;
-  if (tid == 0 && item < total) issue_load (item);
-  unsigned phase = 0;
 
-  u64 *scr_re = sScr + (size_t) warp * 2 * 4 * kRowUnits, *scr_im = scr_re + 4 * kRowUnits;
-  const int g = lane >> 3, b = lane & 7;
-
-  for (; item < total; item += gridDim.x)
+  if (warp < kFftWarps)
   {
-    const uint32_t tile = item / P.streams, s = item % P.streams;
-    const uint32_t hops_here = min ((uint32_t) kTileHops, P.hops - tile * kTileHops);
-    mbar_wait (sBar, phase); phase ^= 1;
-
-    // ================================ phase B: polyphase + FFT, 16 hops per warp ================================
+    // =============================== producer side: staging, polyphase, FFT, detector ===============================
+    // bulk copy of item `it` into raw buffer `buf` (thread 0 only): history rows + the tile's hops, contiguous in the
+    // stream except for tile 0, whose history comes from the carried state
+    auto issue_load = [&] (unsigned it, int buf) {
+      const uint32_t tile = it / P.streams, s = it % P.streams;
+      const uint32_t hops_here = min ((uint32_t) kTileHops, P.hops - tile * kTileHops);
+      const uint32_t *src = P.in + (size_t) s * P.hops * kBins + (size_t) tile * kTileHops * kBins;
+      uint32_t *dst = sRaw + (size_t) buf * kRawWords;
+      mbar_expect_tx (sBar + buf, (hops_here + kHistHops) * kBins * 4);
+      if (tile == 0)
+      {
+        bulk_g2s (dst, P.hist_in + (size_t) s * kHistHops * kBins, kHistHops * kBins * 4, sBar + buf);
+        bulk_g2s (dst + kHistHops * kBins, src, hops_here * kBins * 4, sBar + buf);
+      }
+      else
+        bulk_g2s (dst, src - kHistHops * kBins, (hops_here + kHistHops) * kBins * 4, sBar + buf);
+    };
+    if (tid == 0)
     {
-      const int h_base = warp * kHopsPerWarp;                      // first hop of this warp inside the tile
+      if (blockIdx.x < total) issue_load (blockIdx.x, 0);
+      if (blockIdx.x + gridDim.x < total) issue_load (blockIdx.x + gridDim.x, 1);
+    }
+    // branch coefficients of this lane: branches r = lane and lane + 32
+    float c0[kTaps], c1[kTaps];
+#pragma unroll
+    for (int p = 0; p < kTaps; p++) { c0[p] = P.coef[lane * kTaps + p]; c1[p] = P.coef[(lane + 32) * kTaps + p]; }
+    u64 *scr_re = sScr + (size_t) warp * 2 * 4 * kRowUnits, *scr_im = scr_re + 4 * kRowUnits;
+    const int g = lane >> 3, b = lane & 7;
+    unsigned seq = 0;
+
+    for (unsigned item = blockIdx.x; item < total; item += gridDim.x, seq++)
+    {
+      const int buf = seq & 1;
+      const uint32_t tile = item / P.streams, s = item % P.streams;
+      const uint32_t hops_here = min ((uint32_t) kTileHops, P.hops - tile * kTileHops);
+      const uint32_t *raw = sRaw + (size_t) buf * kRawWords;
+      float *audio = sAudio + (size_t) buf * kAudioWords;
+      mbar_wait (sBar + buf, (seq >> 1) & 1);                        // raw tile has landed
+      if (seq >= 2) bar_sync (3 + buf, kThreads);                    // the AGC warps have drained this audio buffer
+
+      const int h_base = warp * kHopsPerWarp;                        // first hop of this warp inside the tile
       if ((uint32_t) h_base < hops_here)
       {
-        // sliding windows: w?[j] holds x_r[m - 7 + j] at the time hop m is evaluated (static rotation by unrolling)
+        // sliding windows: at hop m the oldest sample x_r[m-7] sits in slot (m+1)&7, the newest in slot m&7
         float w0r[kTaps], w0i[kTaps], w1r[kTaps], w1i[kTaps];
-        const uint32_t *rawp = sRaw + (size_t) h_base * kBins + lane;   // row (hop_local + 7) holds hop hop_local
+        const uint32_t *rawp = raw + (size_t) h_base * kBins + lane;  // row (hop_local + 7) holds hop hop_local
 #pragma unroll
         for (int j = 0; j < kHistHops; j++)
         {
@@ -228,37 +245,41 @@ __global__ void __launch_bounds__ (kThreads, 2) chan64_f32_kernel (const __grid_
         {
           const int h0 = h_base + 8 * rd;
           // ---- polyphase branch FIRs (arm_fir_f32.c: acc = sum_k state[n+k] * pCoeffs[k], oldest sample first,
-          //      pCoeffs[k] = e_r[7-k]) for 8 hops; results of hop pairs are stored packed
+          //      pCoeffs[k] = e_r[7-k]) for 8 hops; the two hops of a pair are stored together
 #pragma unroll
-          for (int m = 0; m < 8; m++)
+          for (int m = 0; m < 8; m += 2)
           {
-            // slot (m & 7) is the oldest entry: it is replaced by the newest sample x_r[h0 + m]
-            // window order at hop m: oldest = slot (m+1)&7, ..., newest = slot m&7
-            unpack_iq (rawp[(8 * rd + m + kHistHops) * kBins], w0r[m & 7], w0i[m & 7]);
-            unpack_iq (rawp[(8 * rd + m + kHistHops) * kBins + 32], w1r[m & 7], w1i[m & 7]);
-            float a0r = 0.f, a0i = 0.f, a1r = 0.f, a1i = 0.f;
+            float a0r[2], a0i[2], a1r[2], a1i[2];
 #pragma unroll
-            for (int k = 0; k < kTaps; k++)
+            for (int e = 0; e < 2; e++)
             {
-              const int slot = (m + 1 + k) & 7;                     // x_r[m - 7 + k]
-              a0r = fmaf (w0r[slot], c0[kTaps - 1 - k], a0r); a0i = fmaf (w0i[slot], c0[kTaps - 1 - k], a0i);
-              a1r = fmaf (w1r[slot], c1[kTaps - 1 - k], a1r); a1i = fmaf (w1i[slot], c1[kTaps - 1 - k], a1i);
+              const int mm = m + e;
+              unpack_iq (rawp[(8 * rd + mm + kHistHops) * kBins], w0r[mm & 7], w0i[mm & 7]);
+              unpack_iq (rawp[(8 * rd + mm + kHistHops) * kBins + 32], w1r[mm & 7], w1i[mm & 7]);
+              float p0r = 0.f, p0i = 0.f, p1r = 0.f, p1i = 0.f;
+#pragma unroll
+              for (int k = 0; k < kTaps; k++)
+              {
+                const int slot = (mm + 1 + k) & 7;                   // x_r[m - 7 + k]
+                p0r = fmaf (w0r[slot], c0[kTaps - 1 - k], p0r); p0i = fmaf (w0i[slot], c0[kTaps - 1 - k], p0i);
+                p1r = fmaf (w1r[slot], c1[kTaps - 1 - k], p1r); p1i = fmaf (w1i[slot], c1[kTaps - 1 - k], p1i);
+              }
+              a0r[e] = p0r; a0i[e] = p0i; a1r[e] = p1r; a1i[e] = p1i;
             }
             // scratch row = hop pair, unit = branch; lo/hi = even/odd hop of the pair
-            float *re = reinterpret_cast<float *> (scr_re + (m >> 1) * kRowUnits), *im = reinterpret_cast<float *> (scr_im + (m >> 1) * kRowUnits);
-            re[2 * lane + (m & 1)] = a0r; im[2 * lane + (m & 1)] = a0i;
-            re[2 * (lane + 32) + (m & 1)] = a1r; im[2 * (lane + 32) + (m & 1)] = a1i;
+            scr_re[(m >> 1) * kRowUnits + lane] = pk (a0r[0], a0r[1]); scr_im[(m >> 1) * kRowUnits + lane] = pk (a0i[0], a0i[1]);
+            scr_re[(m >> 1) * kRowUnits + lane + 32] = pk (a1r[0], a1r[1]); scr_im[(m >> 1) * kRowUnits + lane + 32] = pk (a1i[0], a1i[1]);
           }
           __syncwarp ();
           // ---- 64-point FFT (arm_cfft_f32 len 64, forward) of 8 hops: lane (g, b) = hop pair g, column b
           u64 xr[8], xi[8];
 #pragma unroll
           for (int a = 0; a < 8; a++) { xr[a] = scr_re[g * kRowUnits + 8 * a + b]; xi[a] = scr_im[g * kRowUnits + 8 * a + b]; }
-          dft8x2 (xr, xi);                                          // over a: index k1
+          dft8x2 (xr, xi);                                           // over a: index k1
 #pragma unroll
           for (int k1 = 1; k1 < 8; k1++)
           {
-            const float2 w = sTw[k1 * 8 + b];                       // W_64^(k1 b)
+            const float2 w = sTw[k1 * 8 + b];                        // W_64^(k1 b)
             const u64 wr = pk (w.x, w.x), wi = pk (w.y, w.y);
             const u64 tr = sub2 (mul2 (xr[k1], wr), mul2 (xi[k1], wi));
             xi[k1] = fma2 (xr[k1], wi, mul2 (xi[k1], wr)); xr[k1] = tr;
@@ -275,12 +296,12 @@ __global__ void __launch_bounds__ (kThreads, 2) chan64_f32_kernel (const __grid_
 #pragma unroll
           for (int bb = 0; bb < 8; bb++)
           {
-            const int u = g * kRowUnits + 8 * b + ((bb + b) & 7);   // this lane is k1 = b now
+            const int u = g * kRowUnits + 8 * b + ((bb + b) & 7);    // this lane is k1 = b now
             xr[bb] = scr_re[u]; xi[bb] = scr_im[u];
           }
-          dft8x2 (xr, xi);                                          // over b: index k2, bin = k1 + 8 k2
+          dft8x2 (xr, xi);                                           // over b: index k2, bin = k1 + 8 k2
           __syncwarp ();
-          // ---- demodulator: product detector (real part) or envelope (arm_cmplx_mag_f32); audio tile [bin][hop]
+          // ---- detector: product (real part) or envelope (arm_cmplx_mag_f32); audio tile [bin][hop]
 #pragma unroll
           for (int k2 = 0; k2 < 8; k2++)
           {
@@ -292,28 +313,33 @@ __global__ void __launch_bounds__ (kThreads, 2) chan64_f32_kernel (const __grid_
               hi = __fsqrt_rn (__fadd_rn (__fmul_rn (rh, rh), __fmul_rn (ih, ih)));
             }
             else { lo = lo_of (xr[k2]); hi = hi_of (xr[k2]); }
-            *reinterpret_cast<float2 *> (sAudio + (b + 8 * k2) * kAudioStride + h0 + 2 * g) = make_float2 (lo, hi);
+            *reinterpret_cast<float2 *> (audio + (b + 8 * k2) * kAudioStride + h0 + 2 * g) = make_float2 (lo, hi);
           }
         }
       }
+      // carried FIR history for the next call: the last 7 hops of the stream (rows hops_here .. hops_here + 6)
+      if (tile == P.tiles - 1)
+        for (int i = tid; i < kHistHops * kBins; i += kFftThreads) P.hist_out[(size_t) s * kHistHops * kBins + i] = raw[hops_here * kBins + i];
+      bar_sync (5, kFftThreads);                                     // every FFT warp is done with raw[buf]; audio[buf] complete
+      const unsigned refill = item + 2 * gridDim.x;
+      if (tid == 0 && refill < total) { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); issue_load (refill, buf); }
+      bar_arrive (1 + buf, kThreads);
     }
-    __syncthreads ();                                               // audio tile complete, raw tile consumed
-
-    // carried FIR history for the next call: the last 7 hops of the stream (rows hops_here .. hops_here + 6)
-    if (tile == P.tiles - 1)
-      for (int i = tid; i < kHistHops * kBins; i += kThreads) P.hist_out[(size_t) s * kHistHops * kBins + i] = sRaw[hops_here * kBins + i];
-    __syncthreads ();
-    // the raw buffer is free: start the next item's copy now, it lands while the AGC phase runs
-    const unsigned next = item + gridDim.x;
-    if (tid == 0 && next < total) { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); issue_load (next); }
-
-    // ================================ phase C: AGC, one thread per bin ================================
-    if (tid < kBins)
+  }
+  else
+  {
+    // ================================ consumer side: AGC, one thread per bin ================================
+    const int k = tid - kFftThreads;
+    const float decay = P.decay;
+    unsigned seq = 0;
+    for (unsigned item = blockIdx.x; item < total; item += gridDim.x, seq++)
     {
-      const int k = tid;
+      const int buf = seq & 1;
+      const uint32_t tile = item / P.streams, s = item % P.streams;
+      const uint32_t hops_here = min ((uint32_t) kTileHops, P.hops - tile * kTileHops);
       const int nblk = hops_here / kBlk;
-      const float decay = P.decay;
-      const float4 *row = reinterpret_cast<const float4 *> (sAudio + k * kAudioStride);
+      const float4 *row = reinterpret_cast<const float4 *> (sAudio + (size_t) buf * kAudioWords + k * kAudioStride);
+      bar_sync (1 + buf, kThreads);                                  // audio tile complete
       // block peaks (arm_abs_f32 + arm_max_f32 over 3 samples); 4 blocks = 12 samples = 3 float4
       float pkv[kTileBlocks];
 #pragma unroll
@@ -332,33 +358,50 @@ __global__ void __launch_bounds__ (kThreads, 2) chan64_f32_kernel (const __grid_
       for (int q = 0; q < kTileBlocks; q++) if (q < nblk) e0 = fmaxf (pkv[q], e0 * decay);
       const size_t slot = ((size_t) s * P.tiles + tile) * kBins + k;
       __stcg (P.agg + slot, e0);
-      __threadfence ();
-      agc_bar ();
+      // publish: the CTA-scope barrier orders the 64 stores before thread 0's release at GPU scope (release is cumulative),
+      // so no per-thread __threadfence (MEMBAR.SC + L1 invalidate) is needed
+      bar_sync (6, kAgcThreads);
       if (k == 0) st_release (P.status + (size_t) s * P.tiles + tile, 1u);
 
-      // carry-in by look-back over the predecessors of this stream
+      // carry-in by look-back over the predecessors of this stream. The statuses of the last kLookBackMax tiles are
+      // polled TOGETHER and the values then fetched together, so a look-back costs two global round trips whatever its
+      // depth. Virtual tile -1 is the call's carried state (always inclusive).
       float env;
-      if (tile == 0) env = __ldcg (P.env_state + (size_t) s * kBins + k);
-      else
       {
-        float stack[kLookBackMax];
-        int depth = 0;
-        int j = (int) tile - 1;
+        const unsigned *stp = P.status + (size_t) s * P.tiles;
+        int dstar;
         for (;;)
         {
-          const unsigned *stp = P.status + (size_t) s * P.tiles + j;
-          unsigned st;
-          const unsigned need = (depth == kLookBackMax - 1) ? 2u : 1u;     // bound the fold depth
-          while ((st = ld_relaxed (stp)) < need) __nanosleep (20);
-          (void) ld_acquire (stp);
-          const size_t sj = ((size_t) s * P.tiles + j) * kBins + k;
-          if (st >= 2u) { env = __ldcg (P.incl + sj); break; }
-          stack[depth++] = __ldcg (P.agg + sj);
-          if (j == 0) { env = __ldcg (P.env_state + (size_t) s * kBins + k); break; }   // tile 0's carry-in is the call's state
-          j--;
+          unsigned st[kLookBackMax];
+#pragma unroll
+          for (int d = 0; d < kLookBackMax; d++) { const int j = (int) tile - 1 - d; st[d] = (j >= 0) ? ld_relaxed (stp + j) : 2u; }
+          dstar = -1;
+          bool ok = true;
+#pragma unroll
+          for (int d = kLookBackMax - 1; d >= 0; d--) { if (st[d] >= 2u) dstar = d; }      // nearest inclusive predecessor
+          if (dstar < 0) ok = false;
+#pragma unroll
+          for (int d = 0; d < kLookBackMax; d++) if (d < dstar && st[d] < 1u) ok = false;   // everything nearer has an aggregate
+          if (ok) break;
+          __nanosleep (64);
         }
-        // fold forward: env_end(i) = max(E0(i), decay^32(env_end(i-1))), every predecessor tile is a full one
-        while (depth > 0) env = fmaxf (stack[--depth], decay_n (env, decay, kTileBlocks));
+        asm volatile ("fence.acq_rel.gpu;" ::: "memory");
+        float val[kLookBackMax];
+#pragma unroll
+        for (int d = 0; d < kLookBackMax; d++)
+        {
+          const int j = (int) tile - 1 - d;
+          val[d] = 0.f;
+          if (d <= dstar)
+            val[d] = (j < 0) ? __ldcg (P.env_state + (size_t) s * kBins + k)
+                             : __ldcg ((d == dstar ? P.incl : P.agg) + ((size_t) s * P.tiles + j) * kBins + k);
+        }
+        // fold forward: env_end(i) = max(E0(i), decay^16(env_end(i-1))), every predecessor tile is a full one
+        env = 0.f;
+#pragma unroll
+        for (int d = kLookBackMax - 1; d >= 0; d--)
+          if (d == dstar) env = val[d];
+          else if (d < dstar) env = fmaxf (val[d], decay_n (env, decay, kTileBlocks));
       }
       // the real walk (oracle order), gains per block
       float gain[kTileBlocks];
@@ -367,12 +410,17 @@ __global__ void __launch_bounds__ (kThreads, 2) chan64_f32_kernel (const __grid_
         if (q < nblk)
         {
           env = fmaxf (pkv[q], env * decay);
-          gain[q] = fminf (__fdiv_rn (P.target, fmaxf (env, P.floor)), P.gmax);
+          // g = target / max(env, floor): reciprocal + one Newton step (<= 1 ulp from the oracle's IEEE division, far inside
+          // the 1e-5 float tolerance; the envelope itself stays bit-exact)
+          const float den = fmaxf (env, P.floor);
+          float rc; asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(den));
+          rc = fmaf (rc, fmaf (-den, rc, 1.0f), rc);
+          const float gq = P.target * rc;
+          gain[q] = fminf (fmaf (rc, fmaf (-den, gq, P.target), gq), P.gmax);
         }
       __stcg (P.incl + slot, env);
       if (tile == P.tiles - 1) __stcg (P.env_state + (size_t) s * kBins + k, env);
-      __threadfence ();
-      agc_bar ();
+      bar_sync (6, kAgcThreads);
       if (k == 0) st_release (P.status + (size_t) s * P.tiles + tile, 2u);
 
       // scale (arm_scale_f32), pack (arm_float_to_q15), store channel-major: 12 samples = 3 float4 in, 3 uint4 out
@@ -398,8 +446,8 @@ __global__ void __launch_bounds__ (kThreads, 2) chan64_f32_kernel (const __grid_
             ad[0] = v0; ad[1] = v1; ad[2] = v2;
           }
         }
+      bar_arrive (3 + buf, kThreads);                                // audio buffer drained
     }
-    __syncthreads ();                                               // audio tile consumed
   }
 }
 
