@@ -154,7 +154,8 @@ struct KParams
 {
   const uint32_t *in; uint32_t *out;            // in [S][frames] u32 I/Q; out [S][64][hops] u32 L=R
   const uint32_t *hist_in; uint32_t *hist_out;  // [S][7*64] raw frames carried between calls (ping-pong)
-  float *env_state;                             // [S][64]
+  const float *env_in; float *env_out;          // [S][64] carried envelope (ping-pong: a late tile may finish before an
+                                                // early one has read its carry-in)
   float *agg, *incl; unsigned *status;          // look-back: [S][tiles][64], [S][tiles][64], [S][tiles]
   const float *coef;                            // [64][8]: e_r[p] = h[64 p + 63 - r] / 32768
   const float2 *tw;                             // [8][8]: W_64^(k1*b)
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
           const int j = (int) tile - 1 - d;
           val[d] = 0.f;
           if (d <= dstar)
-            val[d] = (j < 0) ? __ldcg (P.env_state + (size_t) s * kBins + k)
+            val[d] = (j < 0) ? __ldcg (P.env_in + (size_t) s * kBins + k)
                              : __ldcg ((d == dstar ? P.incl : P.agg) + ((size_t) s * P.tiles + j) * kBins + k);
         }
         // fold forward: env_end(i) = max(E0(i), decay^16(env_end(i-1))), every predecessor tile is a full one
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
           gain[q] = fminf (fmaf (rc, fmaf (-den, gq, P.target), gq), P.gmax);
         }
       __stcg (P.incl + slot, env);
-      if (tile == P.tiles - 1) __stcg (P.env_state + (size_t) s * kBins + k, env);
+      if (tile == P.tiles - 1) __stcg (P.env_out + (size_t) s * kBins + k, env);
       bar_sync (6, kAgcThreads);
       if (k == 0) st_release (P.status + (size_t) s * P.tiles + tile, 2u);
 
@@ -462,7 +463,7 @@ struct Chan64State
   slb_chan_params prm{};
   float *d_coef = nullptr; float2 *d_tw = nullptr;
   uint32_t *d_hist[2] = { nullptr, nullptr }; int parity = 0;
-  float *d_env = nullptr;
+  float *d_env[2] = { nullptr, nullptr };
   float *dbg_audio = nullptr, *dbg_gain = nullptr;
   bool attr_set = false;
 };
@@ -519,7 +520,7 @@ static int chan_upload (slb_ctx *ctx, Chan64State *st)
 void chan64_destroy (Chan64State *st)
 {
   if (!st) return;
-  cudaFree (st->d_coef); cudaFree (st->d_tw); cudaFree (st->d_hist[0]); cudaFree (st->d_hist[1]); cudaFree (st->d_env);
+  cudaFree (st->d_coef); cudaFree (st->d_tw); cudaFree (st->d_hist[0]); cudaFree (st->d_hist[1]); cudaFree (st->d_env[0]); cudaFree (st->d_env[1]);
   delete st;
 }
 
@@ -527,7 +528,7 @@ int chan64_reset (slb_ctx *ctx, Chan64State *st)
 {
   const size_t hb = (size_t) st->streams * kHistHops * kBins * 4;
   if (cudaMemset (st->d_hist[0], 0, hb) != cudaSuccess || cudaMemset (st->d_hist[1], 0, hb) != cudaSuccess ||
-      cudaMemset (st->d_env, 0, (size_t) st->streams * kBins * 4) != cudaSuccess)
+      cudaMemset (st->d_env[0], 0, (size_t) st->streams * kBins * 4) != cudaSuccess || cudaMemset (st->d_env[1], 0, (size_t) st->streams * kBins * 4) != cudaSuccess)
     return ctx_fail (ctx, SLB_ERR_CUDA, "chan64: state reset failed");
   st->parity = 0;
   return SLB_OK;
@@ -541,7 +542,7 @@ int chan64_create (slb_ctx *ctx, uint32_t streams, uint32_t fs, Chan64State **ou
   const size_t hb = (size_t) streams * kHistHops * kBins * 4;
   if (cudaMalloc (&st->d_coef, (size_t) kBins * kTaps * 4) != cudaSuccess || cudaMalloc (&st->d_tw, 64 * sizeof (float2)) != cudaSuccess ||
       cudaMalloc (&st->d_hist[0], hb) != cudaSuccess || cudaMalloc (&st->d_hist[1], hb) != cudaSuccess ||
-      cudaMalloc (&st->d_env, (size_t) streams * kBins * 4) != cudaSuccess)
+      cudaMalloc (&st->d_env[0], (size_t) streams * kBins * 4) != cudaSuccess || cudaMalloc (&st->d_env[1], (size_t) streams * kBins * 4) != cudaSuccess)
   { chan64_destroy (st); return ctx_fail (ctx, SLB_ERR_CUDA, "chan64: allocation failed"); }
   int rc = chan_upload (ctx, st);
   if (rc == SLB_OK) rc = chan64_reset (ctx, st);
@@ -566,7 +567,7 @@ int chan64_state_save (Chan64State *st, char *dst)
 {
   const size_t hb = (size_t) st->streams * kHistHops * kBins * 4;
   if (cudaMemcpy (dst, st->d_hist[st->parity], hb, cudaMemcpyDeviceToHost) != cudaSuccess) return SLB_ERR_CUDA;
-  if (cudaMemcpy (dst + hb, st->d_env, (size_t) st->streams * kBins * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return SLB_ERR_CUDA;
+  if (cudaMemcpy (dst + hb, st->d_env[st->parity], (size_t) st->streams * kBins * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return SLB_ERR_CUDA;
   return SLB_OK;
 }
 int chan64_state_load (Chan64State *st, const char *src)
@@ -574,7 +575,7 @@ int chan64_state_load (Chan64State *st, const char *src)
   const size_t hb = (size_t) st->streams * kHistHops * kBins * 4;
   st->parity = 0;
   if (cudaMemcpy (st->d_hist[0], src, hb, cudaMemcpyHostToDevice) != cudaSuccess) return SLB_ERR_CUDA;
-  if (cudaMemcpy (st->d_env, src + hb, (size_t) st->streams * kBins * 4, cudaMemcpyHostToDevice) != cudaSuccess) return SLB_ERR_CUDA;
+  if (cudaMemcpy (st->d_env[0], src + hb, (size_t) st->streams * kBins * 4, cudaMemcpyHostToDevice) != cudaSuccess) return SLB_ERR_CUDA;
   return SLB_OK;
 }
 
@@ -596,7 +597,7 @@ int chan64_launch (slb_ctx *ctx, Chan64State *st, const int16_t *d_in, int16_t *
   if (cudaMemsetAsync (P.status, 0, (size_t) ns * P.tiles * 4, stream) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "chan64: status reset failed");
   P.in = reinterpret_cast<const uint32_t *> (d_in); P.out = reinterpret_cast<uint32_t *> (d_out);
   P.hist_in = st->d_hist[st->parity] + (size_t) s0 * kHistHops * kBins; P.hist_out = st->d_hist[st->parity ^ 1] + (size_t) s0 * kHistHops * kBins;
-  P.env_state = st->d_env + (size_t) s0 * kBins;
+  P.env_in = st->d_env[st->parity] + (size_t) s0 * kBins; P.env_out = st->d_env[st->parity ^ 1] + (size_t) s0 * kBins;
   P.coef = st->d_coef; P.tw = st->d_tw;
   P.audio_dbg = with_debug ? st->dbg_audio : nullptr; P.gain_dbg = with_debug ? st->dbg_gain : nullptr;
   P.envelope = st->prm.envelope;
