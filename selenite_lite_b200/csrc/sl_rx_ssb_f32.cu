@@ -45,6 +45,31 @@ constexpr int kTxBlkStride = 100;                // TX tile: 48 complex per bloc
                                                  // 128-bit reads (100 l mod 32 = 4 l) cover all banks once per 8 lanes
 constexpr int kTilesPerItem = 16;                // tiles a CTA processes with the recurrence state in registers
 constexpr int kPlane = kN;                       // floats per re / im scratch plane (XOR swizzle: no padding)
+constexpr int kRawWords = kTile + kOvl;          // raw frames (one u32 each) a tile needs: its 1536 + the 128 before it
+#ifndef SL_RX_RAWBUFS
+#define SL_RX_RAWBUFS 2
+#endif
+#ifndef SL_RX_AUDIOBUFS
+#define SL_RX_AUDIOBUFS 3
+#endif
+#ifndef SL_RX_CTAS
+#define SL_RX_CTAS 4
+#endif
+constexpr int kRawBufs = SL_RX_RAWBUFS;          // raw staging: filled by bulk asynchronous copies kRawBufs tiles ahead
+
+// dynamic shared memory layout (bytes). RX keeps three audio tiles in flight so that the FFT warps and the recurrence
+// warp only meet when one side is a whole tile late; the TX tile is twice as large (complex) and stays double-buffered.
+template <bool kTx> struct Smem
+{
+  static constexpr int kAudioBufs = kTx ? 2 : SL_RX_AUDIOBUFS;
+  static constexpr int kAudioWords = kBlocksPerTile * (kTx ? kTxBlkStride : kBlkStride);
+  static constexpr size_t scratch = 0;
+  static constexpr size_t audio = scratch + (size_t) kFftWarps * 2 * kPlane * 4;
+  static constexpr size_t raw = audio + (size_t) kAudioBufs * kAudioWords * 4;
+  static constexpr size_t tw = raw + (size_t) kRawBufs * kRawWords * 4;
+  static constexpr size_t bars = tw + 6 * 32 * 16;
+  static constexpr size_t bytes = bars + (2 * kRawBufs + 2 * kAudioBufs) * 8;
+};
 
 // shared-memory index of FFT point i inside a plane. The LSU data pipe is the busiest unit of this kernel (ncu:
 // l1tex__data_pipe_lsu_wavefronts 84 % before this swizzle, half of all store wavefronts were bank conflicts), so the
@@ -127,19 +152,6 @@ __device__ __forceinline__ void st_release (unsigned *p, unsigned v)
 {
   asm volatile ("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// named barriers: 1,2 = audio buffer 0/1 full; 3,4 = audio buffer 0/1 empty. All 160 threads take part in each.
-__device__ __forceinline__ void bar_sync (int id) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
-__device__ __forceinline__ void bar_arrive (int id) { asm volatile ("bar.arrive %0, %1;" ::"r"(id), "n"(kThreads) : "memory"); }
-
-// int16 pair -> two exact floats without the conversion pipe: (v ^ 0x8000) dropped into the mantissa of 2^23.
-// The 1/32768 of arm_q15_to_float is a power of two and is folded into the mask.
-__device__ __forceinline__ void unpack_iq (uint32_t iq, float &i, float &q)
-{
-  const uint32_t u = iq ^ 0x80008000u;
-  i = __uint_as_float (__byte_perm (u, 0x4B000000u, 0x7610)) - 8421376.0f;
-  q = __uint_as_float (__byte_perm (u, 0x4B000000u, 0x7632)) - 8421376.0f;
-}
-
 __device__ __forceinline__ uint32_t pack_lr (float x_times_32768)
 {
   // arm_float_to_q15.c:147 : (q15_t) __SSAT((q31_t)(x * 32768.0f), 16) — the cast truncates toward zero, then saturates.
@@ -157,59 +169,96 @@ __device__ __forceinline__ uint32_t pack_iq (float i_times_32768, float q_times_
   return (uint32_t) (uint16_t) a | ((uint32_t) (uint16_t) b << 16);              // interleaved I,Q as on the I2S bus (main.c:333-341)
 }
 
-// streaming 8-byte load: read-only path, no L1 allocation (the 2 GB input must not evict masks and twiddles)
-__device__ __forceinline__ uint2 ld_stream (const uint2 *p)
+// ---- bulk asynchronous copy (TMA engine, SASS UBLKCP) + mbarrier: raw tiles are staged global -> shared without
+// passing through registers, two tiles ahead of the FFTs ----
+__device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared (p); }
+__device__ __forceinline__ void mbar_init (uint64_t *bar, unsigned count)
 {
-  uint2 v;
-  asm volatile ("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
+  asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32 (bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, unsigned bytes)
+{
+  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32 (bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive (uint64_t *bar)
+{
+  asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32 (bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
+{
+  asm volatile (
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+      ::"r"(smem_u32 (bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
 }
 
-// work-list walk shared by both roles: CTA b takes items b, b + grid, ... (segment-major), each item = up to
+// work-list walk shared by all roles: CTA b takes items b, b + grid, ... (segment-major), each item = up to
 // kTilesPerItem consecutive tiles of one channel
 struct TileIter
 {
-  unsigned item, total_items, stride;
-  uint32_t seg, c, tl, ntiles, t0;
-  int hops;
-  bool valid;
+  unsigned item;
+  uint32_t c, tile, tiles_left;                   // channel, tile index inside the channel, tiles left in the item (incl. this)
+  __device__ __forceinline__ bool valid () const { return tiles_left != 0; }
   __device__ __forceinline__ void set_item (const KParams &P)
   {
-    valid = item < total_items;
-    if (!valid) return;
-    seg = item / P.channels; c = item % P.channels;
-    const uint32_t tile0 = seg * kTilesPerItem;
-    ntiles = min ((uint32_t) kTilesPerItem, P.tiles_per_channel - tile0);
-    tl = 0; set_tile (P);
+    if (item >= P.channels * P.items_per_channel) { tiles_left = 0; return; }
+    const uint32_t seg = item / P.channels;
+    c = item - seg * P.channels;
+    tile = seg * kTilesPerItem;
+    tiles_left = min ((uint32_t) kTilesPerItem, P.tiles_per_channel - tile);
   }
-  __device__ __forceinline__ void set_tile (const KParams &P)
-  {
-    t0 = (seg * kTilesPerItem + tl) * kTile;
-    hops = min ((uint32_t) kFftWarps, (P.frames - t0) / kHop);
-  }
-  __device__ __forceinline__ void start (const KParams &P)
-  {
-    total_items = P.channels * P.items_per_channel; stride = gridDim.x; item = blockIdx.x; set_item (P);
-  }
+  __device__ __forceinline__ void start (const KParams &P) { item = blockIdx.x; set_item (P); }
   __device__ __forceinline__ void next (const KParams &P)
   {
-    if (++tl < ntiles) { set_tile (P); return; }
-    item += stride; set_item (P);
+    tile++;
+    if (--tiles_left != 0) return;
+    item += gridDim.x; set_item (P);
   }
+  __device__ __forceinline__ uint32_t t0 () const { return tile * kTile; }
+  __device__ __forceinline__ int hops (const KParams &P) const { return (int) min ((uint32_t) kFftWarps, (P.frames - tile * kTile) / kHop); }
+  __device__ __forceinline__ bool first_of_item () const { return tile % kTilesPerItem == 0; }
+  __device__ __forceinline__ bool last_of_item () const { return tiles_left == 1; }
+  __device__ __forceinline__ uint32_t seg () const { return tile / kTilesPerItem; }
 };
 
-__device__ __forceinline__ void load_frame_raw (const KParams &P, const TileIter &it, int warp, int lane, uint2 *raw)
+// stage the raw frames of tile `it` (its hops * 384 frames and the 128 before them) into `dst`; one thread
+__device__ __forceinline__ void issue_raw_tile (const KParams &P, const TileIter &it, uint32_t *dst, uint64_t *bar)
 {
-  // frame covers stream samples [ts, ts + 512), ts = t0 + 384 w - 128; the lane takes the adjacent pair 2*lane,
-  // 2*lane+1 of every 64-sample row: one coalesced 8-byte load per row
+  const uint32_t t0 = it.t0 ();
+  const unsigned body = (unsigned) it.hops (P) * kHop * 4u;
   const uint32_t *in_c = P.in + (size_t) it.c * P.frames;
-  const int64_t ts = (int64_t) it.t0 + (int64_t) warp * kHop - kOvl;
-#pragma unroll
-  for (int r = 0; r < 8; r++)
+  mbar_expect_tx (bar, body + kOvl * 4u);
+  if (t0 == 0)
   {
-    const int64_t t = ts + 2 * lane + 64 * r;
-    raw[r] = ld_stream (reinterpret_cast<const uint2 *> ((t >= 0) ? in_c + t : P.ovl_in + (size_t) it.c * kOvl + (t + kOvl)));
+    // the stream starts here: the 128 frames before it are the carried tail of the previous call
+    bulk_g2s (dst, P.ovl_in + (size_t) it.c * kOvl, kOvl * 4u, bar);
+    bulk_g2s (dst + kOvl, in_c, body, bar);
   }
+  else
+    bulk_g2s (dst, in_c + t0 - kOvl, body + kOvl * 4u, bar);
+}
+
+// exact parallel form of the oracle's release walk env_k = max(peak_k, fl(env_{k-1} * decay)) over the 32 blocks of a tile
+// (lane = block). Because x -> fl(x * decay) is monotonic, fl(max(a, b) * decay) = max(fl(a * decay), fl(b * decay)):
+// a Kogge-Stone max-scan whose step of distance d applies the rounded multiply d times gives bit-for-bit the value
+// the sequential walk produces (31 dependent multiplies per lane instead of 32 round trips through shared memory).
+__device__ __forceinline__ float env_scan (float peak, float carry, float decay, int lane)
+{
+  float v = (lane == 0) ? fmaxf (peak, carry * decay) : peak;
+#pragma unroll
+  for (int s = 0; s < 5; s++)
+  {
+    float w = v;
+#pragma unroll
+    for (int i = 0; i < (1 << s); i++) w = w * decay;
+    w = __shfl_up_sync (0xffffffffu, w, 1 << s);
+    if (lane >= (1 << s)) v = fmaxf (v, w);
+  }
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -243,48 +292,57 @@ __device__ __forceinline__ void twiddle8x2 (u64 *xr, u64 *xi, const float4 *tw3,
   cmul2 (xr[7], xi[7], w7r, w7i, xr[7], xi[7]);
 }
 
-__device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, float *sim, const float4 *tw, int lane)
+// One 512-point forward transform of the lane's 16 points (two radix-8 butterflies per pass, packed), Stockham
+// autosort, three radix-8 passes. Entry: xr/xi[r] = x[j + 64 r] for j = 2*lane (lo) and 2*lane+1 (hi); exit: the same
+// indexing of the spectrum. The passes run through ONE copy of the butterfly / twiddle / gather code (rolled loop): the
+// kernel is sensitive to its instruction footprint (see the note at the call site). The XOR swizzle `phys` is folded
+// into per-lane bases so that every access is base-register + immediate (gathers) or one LOP3 away from it (scatters).
+__device__ __forceinline__ void fft512x2 (u64 *xr, u64 *xi, float *sre, const float4 *tw, int lane)
 {
-  // entry: xr/xi hold the pass-0 butterfly outputs of j = 2*lane (lo) and 2*lane+1 (hi). Ns = 1 scatter: idx = 8 j + r,
-  // i.e. outputs r, r+1 of ONE butterfly are neighbours: transpose 2x2 in registers and store 64 bits at a time
-#pragma unroll
-  for (int r = 0; r < 8; r += 2)
+  // gather x[2 lane + 64 r]: phys = ((2 lane ^ 2 (lane >> 3)) ^ 8 (r & 3)) + 64 r
+  const int gl = (2 * lane) ^ (2 * (lane >> 3));
+  // pass-0 scatter, Ns = 1: idx = 8 j + r, outputs r, r+1 of ONE butterfly are neighbours (transposed 2x2 in registers
+  // and stored 64 bits at a time): phys (16 lane + r + 8 h) = (16 lane ^ 2 (lane & 15)) ^ (r + 8 h)
+  const int sa = (16 * lane) ^ (2 * (lane & 15));
+  // pass-1 scatter, Ns = 8: idx = (j / 8) * 64 + (j & 7) + 8 r: phys = (base ^ (8 (r & 3) + 2 (r >> 1))) + 32 (r >> 2)
+  const int sc = 64 * (lane >> 2) + 8 * ((lane >> 2) & 3) + 2 * (lane & 3);
+#pragma unroll 1
+  for (int p = 0; p < 3; p++)
   {
-    const int ia = phys (16 * lane + r), ib = phys (16 * lane + 8 + r);
-    *reinterpret_cast<u64 *> (sre + ia) = pair_lo (xr[r], xr[r + 1]); *reinterpret_cast<u64 *> (sim + ia) = pair_lo (xi[r], xi[r + 1]);
-    *reinterpret_cast<u64 *> (sre + ib) = pair_hi (xr[r], xr[r + 1]); *reinterpret_cast<u64 *> (sim + ib) = pair_hi (xi[r], xi[r + 1]);
-  }
-  __syncwarp ();
-  // pass 1 (Ns = 8): gather x[j + 64 r], twiddle W_64^{r (j & 7)}, butterfly, scatter to (j / 8) * 64 + (j & 7) + 8 r
-#pragma unroll
-  for (int r = 0; r < 8; r++)
-  {
-    const int i = phys (2 * lane + 64 * r);
-    xr[r] = *reinterpret_cast<const u64 *> (sre + i); xi[r] = *reinterpret_cast<const u64 *> (sim + i);
-  }
-  twiddle8x2 (xr, xi, tw, lane);
-  dft8x2 (xr, xi);
-  __syncwarp ();
-  {
-    const int base = (lane >> 2) * 64 + 2 * (lane & 3);
-#pragma unroll
-    for (int r = 0; r < 8; r++)
+    if (p != 0)
     {
-      const int i = phys (base + 8 * r);
-      *reinterpret_cast<u64 *> (sre + i) = xr[r]; *reinterpret_cast<u64 *> (sim + i) = xi[r];
-    }
-  }
-  __syncwarp ();
-  // pass 2 (Ns = 64): gather x[j + 64 r], twiddle W_512^{r j}, butterfly; result index j + 64 r stays in registers
+      if (p == 1)
+      {
 #pragma unroll
-  for (int r = 0; r < 8; r++)
-  {
-    const int i = phys (2 * lane + 64 * r);
-    xr[r] = *reinterpret_cast<const u64 *> (sre + i); xi[r] = *reinterpret_cast<const u64 *> (sim + i);
+        for (int r = 0; r < 8; r += 2)
+        {
+          float *qa = sre + (sa ^ r), *qb = sre + (sa ^ (r + 8));
+          *reinterpret_cast<u64 *> (qa) = pair_lo (xr[r], xr[r + 1]); *reinterpret_cast<u64 *> (qa + kPlane) = pair_lo (xi[r], xi[r + 1]);
+          *reinterpret_cast<u64 *> (qb) = pair_hi (xr[r], xr[r + 1]); *reinterpret_cast<u64 *> (qb + kPlane) = pair_hi (xi[r], xi[r + 1]);
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+        {
+          float *q = sre + (sc ^ (8 * (r & 3) + 2 * (r >> 1))) + 32 * (r >> 2);
+          *reinterpret_cast<u64 *> (q) = xr[r]; *reinterpret_cast<u64 *> (q + kPlane) = xi[r];
+        }
+      }
+      __syncwarp ();
+#pragma unroll
+      for (int r = 0; r < 8; r++)
+      {
+        const float *q = sre + (gl ^ (8 * (r & 3))) + 64 * r;
+        xr[r] = *reinterpret_cast<const u64 *> (q); xi[r] = *reinterpret_cast<const u64 *> (q + kPlane);
+      }
+      // twiddles: pass 1 W_64^{r (j & 7)}, pass 2 W_512^{r j}
+      twiddle8x2 (xr, xi, tw + 96 * (p - 1), lane);
+    }
+    dft8x2 (xr, xi);
+    __syncwarp ();
   }
-  twiddle8x2 (xr, xi, tw + 96, lane);
-  dft8x2 (xr, xi);
-  __syncwarp ();
 }
 
 // kTx = false: RX-SSB-f32 (complex I/Q in, real audio out through biquad + AGC, written L = R).
@@ -292,13 +350,25 @@ __device__ __forceinline__ void fft_passes_1_2 (u64 *xr, u64 *xi, float *sre, fl
 //              filter with the mode's one-sided mask acting as band-pass + Hilbert pair, no biquad; the post warp measures
 //              |I + jQ| per firmware block (arm_cmplx_mag_f32 + arm_max_f32) and applies the same gain law.
 template <bool kTx>
-__global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_constant__ KParams P)
+#ifdef SL_RX_MAXNREG
+__global__ void __maxnreg__ (SL_RX_MAXNREG) ssb_f32_kernel
+#else
+__global__ void __launch_bounds__ (kThreads, SL_RX_CTAS) ssb_f32_kernel
+#endif
+ (const __grid_constant__ KParams P)
 {
-  __shared__ __align__ (16) float sScratch[kFftWarps][2][kPlane];
-  __shared__ __align__ (16) float sAudio[2][kBlocksPerTile * (kTx ? kTxBlkStride : kBlkStride)];
-  __shared__ __align__ (16) float4 sTw[6 * 32];
-  __shared__ __align__ (16) float sPeak[32];
-  __shared__ float sEnv[32];
+  typedef Smem<kTx> S;
+  constexpr int kAB = S::kAudioBufs;
+  extern __shared__ __align__ (128) unsigned char smem[];
+  float *sScratch = reinterpret_cast<float *> (smem + S::scratch);
+  float *sAudio = reinterpret_cast<float *> (smem + S::audio);
+  uint32_t *sRaw = reinterpret_cast<uint32_t *> (smem + S::raw);
+  float4 *sTw = reinterpret_cast<float4 *> (smem + S::tw);
+  uint64_t *sFull = reinterpret_cast<uint64_t *> (smem + S::bars), *sEmpty = sFull + kRawBufs;
+  // audio tiles: aFull[b] completes when the four FFT warps have each stored their frame, aEmpty[b] when the recurrence
+  // warp has taken the tile into registers. mbarriers, not named barriers: a named barrier would also make the four FFT
+  // warps rendezvous with EACH OTHER once per tile (ncu: 23 % of their time), although they only depend on the consumer.
+  uint64_t *aFull = sEmpty + kRawBufs, *aEmpty = aFull + kAB;
 
   const int tid = threadIdx.x, lane = tid & 31;
   // Warp w of a CTA runs on scheduler (SMSP) w % 4, so a fixed "warp 4 = recurrence warp" would stack the recurrence
@@ -307,68 +377,119 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
   const int hw_warp = tid >> 5, rec_warp = (blockIdx.x + blockIdx.x / 148u) % (kFftWarps + 1);
   const int warp = (hw_warp == rec_warp) ? kFftWarps : (hw_warp < rec_warp ? hw_warp : hw_warp - 1);
   for (int i = tid; i < 6 * 32; i += kThreads) sTw[i] = P.twiddle[i];
+  if (tid == 0)
+  {
+#pragma unroll
+    for (int b = 0; b < kRawBufs; b++) { mbar_init (sFull + b, 1); mbar_init (sEmpty + b, kFftWarps); }
+#pragma unroll
+    for (int b = 0; b < kAB; b++) { mbar_init (aFull + b, kFftWarps); mbar_init (aEmpty + b, 1); }
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads ();
 
-  unsigned tile_seq = 0;                          // tiles this CTA has pushed through the audio double buffer
+  unsigned tile_seq = 0;                          // tiles this CTA has pushed through the audio buffers
+  int abuf = 0;                                   // = tile_seq % kAB
+  unsigned ause = 0;                              // = tile_seq / kAB: how often audio buffer `abuf` has been used before
 
   if (warp < kFftWarps)
   {
     // =========================================== FFT warps ===========================================
-    float *sre = sScratch[warp][0], *sim = sScratch[warp][1];
+    float *sre = sScratch + warp * 2 * kPlane;              // re plane; the im plane follows it
+    const u64 NB = pk (-8421376.0f, -8421376.0f);
     TileIter it; it.start (P);
-    uint2 raw[8];
-    if (it.valid && warp < it.hops) load_frame_raw (P, it, warp, lane, raw);
-    for (; it.valid; tile_seq++)
+    TileIter itl = it;                            // warp 0 is also the loader: its second iterator runs kRawBufs tiles ahead
+    if (warp == 0)
     {
-      const int buf = tile_seq & 1;
-      const bool mine = warp < it.hops;
-      const uint32_t c = it.c, t0 = it.t0;
+#pragma unroll
+      for (int b = 0; b < kRawBufs; b++)
+        if (itl.valid ())
+        {
+          if (lane == 0) issue_raw_tile (P, itl, sRaw + b * kRawWords, sFull + b);
+          itl.next (P);
+        }
+    }
+    for (; it.valid (); tile_seq++)
+    {
+      const int rbuf = (kRawBufs == 1) ? 0 : (int) (tile_seq & 1);
+      const unsigned rpar = (kRawBufs == 1) ? (tile_seq & 1) : ((tile_seq >> 1) & 1);
+      const bool mine = warp < it.hops (P);
+      const uint32_t c = it.c, t0 = it.t0 ();
       u64 xr[8], xi[8];
+      mbar_wait (sFull + rbuf, rpar);                                              // the raw tile has landed
       if (mine)
       {
-        // ---- unpack (arm_q15_to_float)
+        // ---- unpack (arm_q15_to_float): the frame covers stream samples [ts, ts + 512), ts = t0 + 384 w - 128; the lane
+        // takes the adjacent pair 2*lane, 2*lane+1 of every 64-sample row. int16 -> float exactly through the mantissa of
+        // 2^23 (no conversion pipe); the 1/32768 of arm_q15_to_float is a power of two and is folded into the mask.
+        const uint2 *rawp = reinterpret_cast<const uint2 *> (sRaw + rbuf * kRawWords + warp * kHop) + lane;
+        uint2 tail6 = make_uint2 (0u, 0u), tail7 = tail6;
 #pragma unroll
         for (int r = 0; r < 8; r++)
         {
-          float ia, qa, ib, qb;
-          unpack_iq (raw[r].x, ia, qa); unpack_iq (raw[r].y, ib, qb);
-          xr[r] = pk (ia, ib); xi[r] = kTx ? 0ull : pk (qa, qb);                   // TX: the mic is the L half of an L = R frame
+          const uint2 v = rawp[32 * r];
+          if (r == 6) tail6 = v;
+          if (r == 7) tail7 = v;
+          const uint32_t a = v.x ^ 0x80008000u, b = v.y ^ 0x80008000u;
+          xr[r] = add2 (pk (__uint_as_float (__byte_perm (a, 0x4B000000u, 0x7610)), __uint_as_float (__byte_perm (b, 0x4B000000u, 0x7610))), NB);
+          // TX: the mic is the L half of an L = R frame
+          xi[r] = kTx ? 0ull : add2 (pk (__uint_as_float (__byte_perm (a, 0x4B000000u, 0x7632)), __uint_as_float (__byte_perm (b, 0x4B000000u, 0x7632))), NB);
         }
         // carry the raw tail of the stream for the next call (this launch reads ovl_in and writes ovl_out)
         if (t0 + (warp + 1) * kHop == P.frames)
         {
           uint2 *dst = reinterpret_cast<uint2 *> (P.ovl_out + (size_t) c * kOvl);
-          dst[lane] = raw[6]; dst[lane + 32] = raw[7];                            // rows 6, 7 = the last 128 frames
+          dst[lane] = tail6; dst[lane + 32] = tail7;                              // rows 6, 7 = the last 128 frames
         }
       }
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (sEmpty + rbuf);                                  // this warp no longer needs raw[rbuf]
       const float4 *mask = P.masks + (size_t) P.mask_slot[c] * 256;
-      // ---- software prefetch: the next tile's frame is requested now and consumed after two FFTs
       it.next (P);
-      if (it.valid && warp < it.hops) load_frame_raw (P, it, warp, lane, raw);
-      if (mine)
+      // ---- forward FFT (arm_cfft_f32 forward; pass 0 needs no twiddles), spectral mask (arm_cmplx_mult_cmplx_f32), then
+      // the inverse transform as a forward transform of the re/im-swapped spectrum: N ifft(Y) = swap(fft(swap(Y))), so
+      // Re ifft(Y) = Im fft(swap Y) / N (1/N is in the mask). Both transforms run through ONE copy of the FFT code (a
+      // rolled two-trip loop): the unrolled kernel was bound by instruction fetch, not by any execution pipe (ncu:
+      // gcc__cache_requests_type_instruction at 93 % of peak with a 64 KB body against the 32 KB L1.5 instruction cache).
+#pragma unroll 1
+      for (int dir = 0; dir < 2; dir++)
       {
-        // ---- forward FFT (arm_cfft_f32 forward): pass 0 needs no twiddles
-        dft8x2 (xr, xi);
-        fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
-        // ---- spectral mask (arm_cmplx_mult_cmplx_f32), then the inverse transform as a forward transform of the
-        // re/im-swapped spectrum: N ifft(Y) = swap(fft(swap(Y))), so Re ifft(Y) = Im fft(swap Y) / N (1/N is in the mask)
-#pragma unroll
-        for (int r = 0; r < 8; r++)
+        if (mine)
         {
-          const float4 h = __ldg (mask + r * 32 + lane);
-          const u64 hr = pk (h.x, h.y), hi = pk (h.z, h.w);
-          const u64 yr = sub2 (mul2 (xr[r], hr), mul2 (xi[r], hi));
-          const u64 yi = fma2 (xr[r], hi, mul2 (xi[r], hr));
-          xr[r] = yi; xi[r] = yr;                                                  // swap
+          fft512x2 (xr, xi, sre, sTw, lane);
         }
-        dft8x2 (xr, xi);
-        fft_passes_1_2 (xr, xi, sre, sim, sTw, lane);
+        if (dir == 0)
+        {
+          if (warp == 0 && itl.valid ())
+          {
+            // ---- refill raw[rbuf] with a later tile, as soon as the four warps have unpacked the current one
+            if (lane == 0)
+            {
+              mbar_wait (sEmpty + rbuf, rpar);
+              asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+              issue_raw_tile (P, itl, sRaw + rbuf * kRawWords, sFull + rbuf);
+            }
+            itl.next (P);
+            __syncwarp ();
+          }
+          if (mine)
+          {
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+            {
+              const float4 h = __ldg (mask + r * 32 + lane);
+              const u64 hr = pk (h.x, h.y), hi = pk (h.z, h.w);
+              const u64 yr = sub2 (mul2 (xr[r], hr), mul2 (xi[r], hi));
+              const u64 yi = fma2 (xr[r], hi, mul2 (xi[r], hr));
+              xr[r] = yi; xi[r] = yr;                                              // swap
+            }
+          }
+        }
       }
       // ---- hand the audio of this frame to the recurrence warp: keep the last 384 outputs (rows r >= 2)
-      if (tile_seq >= 2) bar_sync (3 + buf);                                       // wait until the buffer was drained
+      if (ause != 0) mbar_wait (aEmpty + abuf, (ause - 1) & 1);                    // wait until the buffer was drained
       if (mine)
       {
-        float *a = sAudio[buf];
+        float *a = sAudio + abuf * S::kAudioWords;
 #pragma unroll
         for (int r = 2; r < 8; r++)
         {
@@ -385,7 +506,9 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
           }
         }
       }
-      bar_arrive (1 + buf);
+      __syncwarp ();
+      if (lane == 0) mbar_arrive (aFull + abuf);
+      if (++abuf == kAB) { abuf = 0; ause++; }
     }
   }
   else if constexpr (kTx)
@@ -396,13 +519,12 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
     const float decay = P.agc_decay;
     float env = 0.f;
     TileIter it; it.start (P);
-    for (; it.valid; it.next (P), tile_seq++)
+    for (; it.valid (); it.next (P), tile_seq++)
     {
-      const uint32_t c = it.c, t0 = it.t0;
-      const int nblk = it.hops * (kHop / kAgcBlock);
-      const int buf = tile_seq & 1;
-      const float4 *blk = reinterpret_cast<const float4 *> (sAudio[buf] + lane * kTxBlkStride);
-      bar_sync (1 + buf);                                                          // I/Q tile is complete
+      const uint32_t c = it.c, t0 = it.t0 ();
+      const int nblk = it.hops (P) * (kHop / kAgcBlock);
+      const float4 *blk = reinterpret_cast<const float4 *> (sAudio + abuf * S::kAudioWords + lane * kTxBlkStride);
+      mbar_wait (aFull + abuf, ause & 1);                                          // I/Q tile is complete
       // arm_cmplx_mag_f32.c:72 : sqrt(re*re + im*im), each product rounded (no contraction in the oracle build);
       // arm_max_f32 over the block. sqrt is monotonic and correctly rounded, so max(sqrt) = sqrt(max).
       float m2 = 0.f;
@@ -412,30 +534,20 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
         const float4 v = blk[k];
         m2 = fmaxf (m2, fmaxf (__fadd_rn (__fmul_rn (v.x, v.x), __fmul_rn (v.y, v.y)), __fadd_rn (__fmul_rn (v.z, v.z), __fmul_rn (v.w, v.w))));
       }
-      if (it.tl == 0)
+      if (it.first_of_item ())
       {
         if (lane == 0)
         {
-          const unsigned want = P.flag_base + it.seg;
+          const unsigned want = P.flag_base + it.seg ();
           while (ld_relaxed (P.flag + c) != want) __nanosleep (32);
           (void) ld_acquire (P.flag + c);
         }
         __syncwarp ();
         env = __ldcg (P.state + (size_t) c * 8 + 4);
       }
-      sPeak[lane] = __fsqrt_rn (m2);
-      __syncwarp ();
-      for (int q = 0; q < nblk; q += 4)
-      {
-        const float4 p4 = *reinterpret_cast<const float4 *> (&sPeak[q]);
-        env = fmaxf (p4.x, env * decay); sEnv[q] = env;
-        env = fmaxf (p4.y, env * decay); sEnv[q + 1] = env;
-        env = fmaxf (p4.z, env * decay); sEnv[q + 2] = env;
-        env = fmaxf (p4.w, env * decay); sEnv[q + 3] = env;
-      }
-      __syncwarp ();
-      const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (sEnv[lane], P.agc_floor)), P.agc_gmax);
-      __syncwarp ();
+      const float e = env_scan (__fsqrt_rn (m2), env, decay, lane);
+      env = __shfl_sync (0xffffffffu, e, nblk - 1);
+      const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (e, P.agc_floor)), P.agc_gmax);
       if (lane < nblk)
       {
         if (P.audio_dbg)
@@ -455,12 +567,13 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
         }
       }
       __syncwarp ();
-      bar_arrive (3 + buf);                                                        // the tile has been consumed
-      if (it.tl == it.ntiles - 1 && lane == 0)
+      if (lane == 0) mbar_arrive (aEmpty + abuf);                                  // the tile has been consumed
+      if (++abuf == kAB) { abuf = 0; ause++; }
+      if (it.last_of_item () && lane == 0)
       {
         __stcg (P.state + (size_t) c * 8 + 4, env);
         __threadfence ();
-        st_release (P.flag + c, P.flag_base + it.seg + 1u);
+        st_release (P.flag + c, P.flag_base + it.seg () + 1u);
       }
     }
   }
@@ -476,13 +589,12 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
     const float decay = P.agc_decay;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, env = 0.f;                       // carried state (uniform across lanes)
     TileIter it; it.start (P);
-    for (; it.valid; it.next (P), tile_seq++)
+    for (; it.valid (); it.next (P), tile_seq++)
     {
-      const uint32_t c = it.c, t0 = it.t0;
-      const int nblk = it.hops * (kHop / kAgcBlock);
-      const int buf = tile_seq & 1;
-      const float *blk = sAudio[buf] + lane * kBlkStride;
-      bar_sync (1 + buf);                                                          // audio tile is complete
+      const uint32_t c = it.c, t0 = it.t0 ();
+      const int nblk = it.hops (P) * (kHop / kAgcBlock);
+      const float *blk = sAudio + abuf * S::kAudioWords + lane * kBlkStride;
+      mbar_wait (aFull + abuf, ause & 1);                                          // audio tile is complete
 
       // zero-state response of the cascade over both runs; per-sample recurrences as
       // arm_biquad_cascade_df2T_f32.c:551-562:  y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
@@ -502,13 +614,14 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
         y[k] = y1;
       }
       __syncwarp ();
-      bar_arrive (3 + buf);                                                        // the audio tile now lives in registers
-      if (it.tl == 0)
+      if (lane == 0) mbar_arrive (aEmpty + abuf);                                  // the audio tile now lives in registers
+      if (++abuf == kAB) { abuf = 0; ause++; }
+      if (it.first_of_item ())
       {
         // state of the previous segment of this channel (segment-major dealing makes the wait a formality)
         if (lane == 0)
         {
-          const unsigned want = P.flag_base + it.seg;
+          const unsigned want = P.flag_base + it.seg ();
           while (ld_relaxed (P.flag + c) != want) __nanosleep (32);
           (void) ld_acquire (P.flag + c);
         }
@@ -575,21 +688,10 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
         y[k] = fma2 (pk (C[0], C[0]), q0, fma2 (pk (C[1], C[1]), q1, fma2 (pk (C[2], C[2]), q2, fma2 (pk (C[3], C[3]), q3, y[k]))));
         pk0 = fmaxf (pk0, fabsf (lo_of (y[k]))); pk1 = fmaxf (pk1, fabsf (hi_of (y[k])));
       }
-      // AGC envelope: sequential over blocks in exactly the oracle's order. Every lane walks the same
-      // chain from the block peaks (shared memory, broadcast reads) and drops each step where its owner picks it up.
-      sPeak[lane] = fmaxf (pk0, pk1);
-      __syncwarp ();
-      for (int q = 0; q < nblk; q += 4)
-      {
-        const float4 p4 = *reinterpret_cast<const float4 *> (&sPeak[q]);
-        env = fmaxf (p4.x, env * decay); sEnv[q] = env;
-        env = fmaxf (p4.y, env * decay); sEnv[q + 1] = env;
-        env = fmaxf (p4.z, env * decay); sEnv[q + 2] = env;
-        env = fmaxf (p4.w, env * decay); sEnv[q + 3] = env;
-      }
-      __syncwarp ();
-      const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (sEnv[lane], P.agc_floor)), P.agc_gmax);
-      __syncwarp ();
+      // AGC envelope: the oracle's sequential walk over the blocks, evaluated as an exact max-scan (env_scan above)
+      const float e = env_scan (fmaxf (pk0, pk1), env, decay, lane);
+      env = __shfl_sync (0xffffffffu, e, nblk - 1);
+      const float g = fminf (__fdiv_rn (P.agc_target, fmaxf (e, P.agc_floor)), P.agc_gmax);
       if (lane < nblk)
       {
         if (P.audio_dbg)
@@ -609,12 +711,12 @@ __global__ void __launch_bounds__ (kThreads, 4) ssb_f32_kernel (const __grid_con
           dst[(kRun + k) / 4] = make_uint4 (pack_lr (hi_of (y[k]) * g15), pack_lr (hi_of (y[k + 1]) * g15), pack_lr (hi_of (y[k + 2]) * g15), pack_lr (hi_of (y[k + 3]) * g15));
         }
       }
-      if (it.tl == it.ntiles - 1 && lane == 0)
+      if (it.last_of_item () && lane == 0)
       {
         float *stw = P.state + (size_t) c * 8;
         __stcg (stw + 0, s0); __stcg (stw + 1, s1); __stcg (stw + 2, s2); __stcg (stw + 3, s3); __stcg (stw + 4, env);
         __threadfence ();
-        st_release (P.flag + c, P.flag_base + it.seg + 1u);
+        st_release (P.flag + c, P.flag_base + it.seg () + 1u);
       }
     }
   }
@@ -680,16 +782,21 @@ int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream_)
   P.agc_target = L.agc_target; P.agc_decay = L.agc_decay; P.agc_floor = L.agc_floor; P.agc_gmax = L.agc_gmax;
   P.tab = *L.tables;
 
+  // the bulk copies need 16-byte aligned sources: frames % 384 == 0 keeps every channel row and every tile start aligned
+  if ((reinterpret_cast<uintptr_t> (L.in) | reinterpret_cast<uintptr_t> (L.ovl_in)) & 15u) return (int) cudaErrorMisalignedAddress;
+  const size_t smem = L.tx ? Smem<true>::bytes : Smem<false>::bytes;
+  const void *fn = L.tx ? (const void *) ssb_f32_kernel<true> : (const void *) ssb_f32_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return (int) e;
   int per_sm = 0;
-  cudaError_t e = L.tx ? cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, ssb_f32_kernel<true>, kThreads, 0)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, ssb_f32_kernel<false>, kThreads, 0);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, fn, kThreads, smem);
   if (e != cudaSuccess) return (int) e;
   if (per_sm < 1) per_sm = 1;
   const uint64_t items = (uint64_t) L.channels * P.items_per_channel;
   uint64_t grid = (uint64_t) sm_count * per_sm;      // all CTAs co-resident: the segment hand-over may spin
   if (grid > items) grid = items;
-  if (L.tx) ssb_f32_kernel<true><<<(unsigned) grid, kThreads, 0, stream>>> (P);
-  else ssb_f32_kernel<false><<<(unsigned) grid, kThreads, 0, stream>>> (P);
+  if (L.tx) ssb_f32_kernel<true><<<(unsigned) grid, kThreads, smem, stream>>> (P);
+  else ssb_f32_kernel<false><<<(unsigned) grid, kThreads, smem, stream>>> (P);
   return (int) cudaGetLastError ();
 }
 
