@@ -47,6 +47,8 @@ extern "C" {
 
 #define SLB_CHAIN_CHAN64_F32  3    /* wideband stream -> 64-branch polyphase FFT channelizer -> per-bin demod + AGC -> pack */
 
+#define SLB_CHAIN_RX_SSB_Q15  4    /* all-integer phasing SSB demodulator: fir_q15 Hilbert pair -> add/sub -> q15 AGC (bit-exact) */
+
 #define SLB_MAX_STAGES 4
 #define SLB_MAX_MASKS  8
 
@@ -94,6 +96,23 @@ typedef struct
   float    proto[SLB_CHAN_BINS * SLB_CHAN_TAPS];   /* prototype low-pass h[n]; branch r uses e_r[p] = h[bins*p + bins-1-r] */
 } slb_chan_params;
 
+/* RX-SSB-q15 chain parameters: every stage is an integer CMSIS-DSP routine, results are bit-exact.
+ * Oracle stage for each field in brackets. The sideband follows the channel's mode (SLB_DSP_Set_Mode: LSB / CW-R
+ * subtract the quadrature rail, every other SSB-style mode adds it). */
+#define SLB_Q15_TAPS 64
+#define SLB_Q15_WIN  32
+typedef struct
+{
+  uint32_t ntaps;                        /* taps per rail [arm_fir_q15 numTaps, even]; this build: 64 */
+  uint32_t agc_block;                    /* AGC detector block [arm_abs_q15 + arm_max_q15] = firmware block; this build: 48 */
+  uint32_t agc_window;                   /* blocks of peak history the envelope sees (finite release), 1..SLB_Q15_WIN */
+  int16_t  taps_i[SLB_Q15_TAPS];         /* b[0..ntaps-1] of the in-phase rail, q15, natural order */
+  int16_t  taps_q[SLB_Q15_TAPS];         /* quadrature rail: same magnitude response, +90 degrees */
+  int16_t  rel[SLB_Q15_WIN];             /* q15 release weight of a block peak by age in blocks; rel[0] unused */
+  int16_t  agc_target, agc_floor;        /* q15 */
+  uint32_t agc_gmax_q15;                 /* gain limit in Q15 (1.0 = 32768) [arm_scale_q15 scaleFract << shift] */
+} slb_rx_q15_params;
+
 /* ---- life cycle ---- */
 int  slb_create (const slb_config *cfg, slb_ctx **out);
 void slb_destroy (slb_ctx *ctx);
@@ -109,6 +128,9 @@ int slb_get_rx_f32_params (const slb_ctx *ctx, slb_rx_f32_params *p);
 int slb_default_tx_f32_params (uint32_t fs, slb_tx_f32_params *out);
 int slb_set_tx_f32_params (slb_ctx *ctx, const slb_tx_f32_params *p);
 int slb_get_tx_f32_params (const slb_ctx *ctx, slb_tx_f32_params *p);
+int slb_default_rx_q15_params (uint32_t fs, slb_rx_q15_params *out);
+int slb_set_rx_q15_params (slb_ctx *ctx, const slb_rx_q15_params *p);
+int slb_get_rx_q15_params (const slb_ctx *ctx, slb_rx_q15_params *p);
 int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask);   /* host, 2*fft_len floats */
 int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask);
 
@@ -154,6 +176,8 @@ int slb_chan_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, ui
  * are written by the next slb_rx_process_device call(s) when non-NULL (device pointers). TX chain: d_audio receives
  * the pre-ALC complex baseband [channels][frames][2] f32. */
 int slb_rx_set_debug_taps (slb_ctx *ctx, float *d_audio, float *d_gain);
+/* RX-SSB-q15: pre-AGC q15 audio int16[channels][frames] and the per-block gain q (Q15) uint32[channels][frames/48] */
+int slb_rx_q15_set_debug_taps (slb_ctx *ctx, int16_t *d_audio, uint32_t *d_gain);
 
 /* ---- carried state = the checkpoint: overlap tail, biquad d1/d2, AGC envelope, ring ---- */
 int slb_state_size (const slb_ctx *ctx, size_t *bytes);

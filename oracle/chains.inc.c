@@ -198,3 +198,43 @@ void SLO (chan_f32) (const slo_chan_params *p, slo_chan_state *st, const int16_t
     }
   free (xf); free (bi); free (bq); free (vi); free (vq); free (fstate); free (coef); free (spec); free (magb); free (audio); free (absb); free (scaled); free (mono);
 }
+
+/* RX-SSB-q15: see slo_api.h. All-integer phasing demodulator, one firmware block per iteration — what a firmware
+ * author would write inside DSP_In_Buff_Write (dsp_if.c:286-289) with the q15 half of arm_math.h. */
+void SLO (rx_ssb_q15) (const slo_rx_q15_params *p, slo_rx_q15_state *st, const int16_t *in_iq, int16_t *out_lr,
+                       int16_t *audio_dbg, uint32_t *gain_dbg, uint32_t frames)
+{
+  const uint32_t T = p->ntaps, B = p->agc_block, K = p->agc_window;
+  int16_t ci[SLO_Q15_TAPS], cq[SLO_Q15_TAPS];
+  int16_t xi[SLO_Q15_MAX_BLOCK], xq[SLO_Q15_MAX_BLOCK], fi[SLO_Q15_MAX_BLOCK], fq[SLO_Q15_MAX_BLOCK];
+  int16_t a[SLO_Q15_MAX_BLOCK], ab[SLO_Q15_MAX_BLOCK], y[SLO_Q15_MAX_BLOCK];
+  for (uint32_t k = 0; k < T; k++) { ci[k] = p->taps_i[T - 1 - k]; cq[k] = p->taps_q[T - 1 - k]; }   /* arm_fir_q15.c: pCoeffs time-reversed */
+
+  for (uint32_t o = 0; o < frames; o += B)
+  {
+    for (uint32_t k = 0; k < B; k++) { xi[k] = in_iq[2 * (size_t) (o + k)]; xq[k] = in_iq[2 * (size_t) (o + k) + 1]; }   /* dsp_if.c:227-238 */
+    SLO (fir_q15) (ci, T, st->fir_i, xi, fi, B, B);
+    SLO (fir_q15) (cq, T, st->fir_q, xq, fq, B, B);
+    if (p->lsb) SLO (sub_q15) (fi, fq, a, B); else SLO (add_q15) (fi, fq, a, B);
+    if (audio_dbg) memcpy (audio_dbg + o, a, sizeof (int16_t) * B);
+    SLO (abs_q15) (a, ab, B);
+    const int32_t peak = SLO (max_q15) (ab, B, 0);
+    /* AGC law (ours): finite-window peak hold with a q15 release table */
+    int32_t env = peak;
+    for (uint32_t j = 1; j < K; j++)
+    {
+      const int32_t v = ((int32_t) st->peaks[j - 1] * (int32_t) p->rel[j]) >> 15;
+      if (v > env) env = v;
+    }
+    for (uint32_t j = SLO_Q15_WIN - 1; j > 0; j--) st->peaks[j] = st->peaks[j - 1];
+    st->peaks[0] = (int16_t) peak;
+    const uint32_t den = (uint32_t) (env > p->agc_floor ? env : p->agc_floor);
+    uint32_t q = ((uint32_t) p->agc_target << 15) / den;
+    if (q > p->agc_gmax_q15) q = p->agc_gmax_q15;
+    uint32_t s = 0;
+    while ((q >> s) > 32767u) s++;
+    if (gain_dbg) gain_dbg[o / B] = q;
+    SLO (scale_q15) (a, (int16_t) (q >> s), (int32_t) s, y, B);
+    for (uint32_t k = 0; k < B; k++) { out_lr[2 * (size_t) (o + k)] = y[k]; out_lr[2 * (size_t) (o + k) + 1] = y[k]; }   /* L = R */
+  }
+}

@@ -175,6 +175,39 @@ typedef struct
 void SLO (chan_f32) (const slo_chan_params *p, slo_chan_state *st, const int16_t *in_iq, int16_t *out_lr,
                      float *audio_dbg, float *gain_dbg, uint32_t frames);
 
+/* RX-SSB-q15 (SURVEY.md Appendix B "the fully-integer variant"): phasing-method SSB demodulator, every
+ * box an integer CMSIS routine, so the GPU must match bit for bit. Per `agc_block` (the firmware block):
+ * de-interleave I, Q -> fir_q15(I, taps_i), fir_q15(Q, taps_q) [a +-45 degree band-pass Hilbert pair]
+ * -> add_q15 (USB) or sub_q15 (LSB), saturating -> abs_q15 + max_q15 = block peak p_b
+ * -> AGC law (ours): env_b = max(p_b, max_{j=1..agc_window-1} (p_{b-j} * rel[j]) >> 15)   [finite release window]
+ *    q = min((agc_target << 15) / max(env_b, agc_floor), agc_gmax_q15)                     [gain in Q15, integer divide]
+ *    shift s = smallest s >= 0 with (q >> s) <= 32767, scaleFract = q >> s
+ * -> scale_q15(audio, scaleFract, s) -> written L = R. */
+#define SLO_Q15_TAPS 64
+#define SLO_Q15_WIN 32
+#define SLO_Q15_MAX_BLOCK 192
+typedef struct
+{
+  uint32_t ntaps;                                        /* even (arm_fir_init_q15.c:88-128), <= SLO_Q15_TAPS */
+  uint32_t agc_block;                                    /* 48 */
+  uint32_t agc_window;                                   /* blocks of peak history the envelope sees, 1..SLO_Q15_WIN */
+  uint32_t lsb;                                          /* 0: I' + Q' (upper sideband), 1: I' - Q' */
+  int16_t taps_i[SLO_Q15_TAPS], taps_q[SLO_Q15_TAPS];    /* b[0..ntaps-1] in natural order */
+  int16_t rel[SLO_Q15_WIN];                              /* q15 release weight by block age; rel[0] unused */
+  int16_t agc_target, agc_floor;                         /* q15; floor >= 1 */
+  uint32_t agc_gmax_q15;                                 /* gain limit in Q15 (1.0 = 32768) */
+} slo_rx_q15_params;
+
+typedef struct
+{
+  int16_t fir_i[SLO_Q15_TAPS + SLO_Q15_MAX_BLOCK], fir_q[SLO_Q15_TAPS + SLO_Q15_MAX_BLOCK];   /* arm_fir_q15 pState */
+  int16_t peaks[SLO_Q15_WIN];                            /* peaks[j] = block peak j+1 blocks ago */
+} slo_rx_q15_state;
+
+/* frames % agc_block == 0. audio_dbg (optional): the pre-AGC q15 audio [frames]; gain_dbg (optional): q per block. */
+void SLO (rx_ssb_q15) (const slo_rx_q15_params *p, slo_rx_q15_state *st, const int16_t *in_iq, int16_t *out_lr,
+                       int16_t *audio_dbg, uint32_t *gain_dbg, uint32_t frames);
+
 #ifdef __cplusplus
 }
 #endif

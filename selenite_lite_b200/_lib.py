@@ -24,6 +24,12 @@ class TxF32Params(C.Structure):
                 ("alc_target", C.c_float), ("alc_decay", C.c_float), ("alc_floor", C.c_float), ("alc_gmax", C.c_float)]
 
 
+class RxQ15Params(C.Structure):
+    _fields_ = [("ntaps", C.c_uint32), ("agc_block", C.c_uint32), ("agc_window", C.c_uint32),
+                ("taps_i", C.c_int16 * 64), ("taps_q", C.c_int16 * 64), ("rel", C.c_int16 * 32),
+                ("agc_target", C.c_int16), ("agc_floor", C.c_int16), ("agc_gmax_q15", C.c_uint32)]
+
+
 class ChanParams(C.Structure):
     _fields_ = [("bins", C.c_uint32), ("taps_per_branch", C.c_uint32), ("agc_block", C.c_uint32), ("envelope", C.c_uint32),
                 ("agc_target", C.c_float), ("agc_decay", C.c_float), ("agc_floor", C.c_float), ("agc_gmax", C.c_float),

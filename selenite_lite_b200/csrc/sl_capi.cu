@@ -35,6 +35,7 @@ struct slb_ctx
   std::vector<uint8_t> mode_host;      // [C]
   bool tx_mode = false;
   Chan64State *chan = nullptr;         // SLB_CHAIN_CHAN64_F32 only
+  RxQ15State *q15 = nullptr;           // SLB_CHAIN_RX_SSB_Q15 only
 
   // device: chain constants + carried state
   float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
@@ -117,6 +118,7 @@ static int reset_state (slb_ctx *ctx)
   ctx->flag_base = 0; ctx->ovl_parity = 0; ctx->acc_fill = 0; ctx->proc_cur = 0;
   ctx->ring_in.reset (R); ctx->ring_out.reset (R);
   if (ctx->chan) return chan64_reset (ctx, ctx->chan);
+  if (ctx->q15) return rxq15_reset (ctx, ctx->q15);
   return SLB_OK;
 }
 
@@ -136,7 +138,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   *out = nullptr;
   if (cfg->channels == 0) return fail (nullptr, SLB_ERR_ARG, "channels must be > 0");
   if (cfg->fs != 48000u && cfg->fs != 96000u && cfg->fs != 192000u) return fail (nullptr, SLB_ERR_ARG, "fs must be 48000, 96000 or 192000");
-  if (cfg->chain != SLB_CHAIN_PASS && !is_ssb_chain (cfg->chain) && cfg->chain != SLB_CHAIN_CHAN64_F32) return fail (nullptr, SLB_ERR_ARG, "unknown chain");
+  if (cfg->chain != SLB_CHAIN_PASS && !is_ssb_chain (cfg->chain) && cfg->chain != SLB_CHAIN_CHAN64_F32 && cfg->chain != SLB_CHAIN_RX_SSB_Q15) return fail (nullptr, SLB_ERR_ARG, "unknown chain");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount (&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -181,6 +183,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   int rc = upload_chain_constants (ctx);
   if (rc == SLB_OK) rc = reset_state (ctx);
   if (rc == SLB_OK && cfg->chain == SLB_CHAIN_CHAN64_F32) rc = chan64_create (ctx, C, cfg->fs, &ctx->chan);
+  if (rc == SLB_OK && cfg->chain == SLB_CHAIN_RX_SSB_Q15) rc = rxq15_create (ctx, C, cfg->fs, &ctx->q15);
   if (rc != SLB_OK) { g_create_error = ctx->err; slb_destroy (ctx); return rc; }
   *out = ctx;
   return SLB_OK;
@@ -192,6 +195,7 @@ void slb_destroy (slb_ctx *ctx)
   cudaSetDevice (ctx->cfg.device);
   cudaDeviceSynchronize ();
   chan64_destroy (ctx->chan);
+  rxq15_destroy (ctx->q15);
   cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
@@ -258,6 +262,39 @@ int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask)
   return SLB_OK;
 }
 
+int slb_default_rx_q15_params (uint32_t fs, slb_rx_q15_params *out) { return design_default_rx_q15 (fs, out); }
+int slb_set_rx_q15_params (slb_ctx *ctx, const slb_rx_q15_params *p)
+{
+  if (!ctx || !p) return SLB_ERR_ARG;
+  if (!ctx->q15) return fail (ctx, SLB_ERR_STATE, "not an RX-SSB-q15 context");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  return rxq15_set_params (ctx, ctx->q15, p);
+}
+int slb_get_rx_q15_params (const slb_ctx *ctx, slb_rx_q15_params *p)
+{
+  if (!ctx || !p || !ctx->q15) return SLB_ERR_ARG;
+  *p = *rxq15_params (ctx->q15);
+  return SLB_OK;
+}
+int slb_rx_q15_set_debug_taps (slb_ctx *ctx, int16_t *d_audio, uint32_t *d_gain)
+{
+  if (!ctx || !ctx->q15) return SLB_ERR_ARG;
+  rxq15_set_debug (ctx->q15, d_audio, d_gain);
+  return SLB_OK;
+}
+
+// LSB and CW-R take the lower sideband (subtract the quadrature rail); AM / FM are not SSB-style demodulators
+static int mode_to_lsb (uint8_t mode)
+{
+  switch (mode)
+  {
+    case SLB_MODE_LSB: case SLB_MODE_CWR: return 1;
+    case SLB_MODE_USB: case SLB_MODE_CW: case SLB_MODE_DIG: case SLB_MODE_PKT: return 0;
+    default: return -1;
+  }
+}
+
 int slb_rx_set_debug_taps (slb_ctx *ctx, float *d_audio, float *d_gain)
 {
   if (!ctx) return SLB_ERR_ARG;
@@ -285,6 +322,12 @@ int SLB_DSP_Set_Mode_Channel (slb_ctx *ctx, uint32_t ch, uint8_t mode)
   const int slot = mode_to_mask_slot (mode);
   if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "AM/FM demodulators are not built yet (DESIGN.md: next)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
+  if (ctx->q15)
+  {
+    CK (ctx, cudaStreamSynchronize (ctx->stream));
+    ctx->mode_host[ch] = mode;
+    return rxq15_set_sideband (ctx, ctx->q15, ch, 1, mode_to_lsb (mode));
+  }
   ctx->mode_host[ch] = mode; ctx->slot_host[ch] = (uint8_t) slot;
   CK (ctx, cudaMemcpyAsync (ctx->d_slot + ch, &ctx->slot_host[ch], 1, cudaMemcpyHostToDevice, ctx->stream));
   CK (ctx, cudaStreamSynchronize (ctx->stream));
@@ -305,6 +348,11 @@ int SLB_DSP_Set_Mode (slb_ctx *ctx, uint8_t mode)     // dsp_if.c:367-370 is the
   if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "AM/FM demodulators are not built yet (DESIGN.md: next)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   std::fill (ctx->mode_host.begin (), ctx->mode_host.end (), mode);
+  if (ctx->q15)
+  {
+    CK (ctx, cudaStreamSynchronize (ctx->stream));
+    return rxq15_set_sideband (ctx, ctx->q15, 0, ctx->cfg.channels, mode_to_lsb (mode));
+  }
   std::fill (ctx->slot_host.begin (), ctx->slot_host.end (), (uint8_t) slot);
   CK (ctx, cudaMemcpyAsync (ctx->d_slot, ctx->slot_host.data (), ctx->slot_host.size (), cudaMemcpyHostToDevice, ctx->stream));
   CK (ctx, cudaStreamSynchronize (ctx->stream));
@@ -350,7 +398,21 @@ static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
   const bool chain = (which == 0 && is_ssb_chain (ctx->cfg.chain));
-  if (!chain)
+  if (which == 0 && ctx->q15)
+  {
+    // the integer chain works at the firmware's own block size: the block is demodulated and enters the ring in the same
+    // call, where the firmware would have called it (dsp_if.c:286-289), with no added latency
+    if (frames % ctx->geo.block_frames != 0) return fail (ctx, SLB_ERR_ARG, "with the RX-SSB-q15 chain the block must be a whole number of 48-frame firmware blocks");
+    int rc = ensure_blk (ctx, frames); if (rc) return rc;
+    CK (ctx, cudaMemcpyAsync (ctx->d_blk, pbuf, (size_t) C * frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = rxq15_launch (ctx, ctx->q15, ctx->d_blk, ctx->d_proc[0], 0, C, frames, ctx->sm_count, ctx->stream, false);
+    if (rc) return rc;
+    rxq15_advance (ctx->q15);
+    const uint32_t wr0 = rp.plan_write (false, frames);
+    CK (ctx, launch_ring_write (ctx->d_proc[0], frames, ctx->d_ring[0][0], ctx->d_ring[0][1], C, R, wr0, frames, ctx->stream));
+    ctx->launches++;
+  }
+  else if (!chain)
   {
     int rc = ensure_blk (ctx, frames); if (rc) return rc;
     CK (ctx, cudaMemcpyAsync (ctx->d_blk, pbuf, (size_t) C * frames * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -474,6 +536,13 @@ static int process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, ui
     ctx->launches++;
     return SLB_OK;
   }
+  if (ctx->q15)
+  {
+    int rc = rxq15_launch (ctx, ctx->q15, d_in, d_out, 0, ctx->cfg.channels, frames, ctx->sm_count, stream, true);
+    if (rc) return rc;
+    rxq15_advance (ctx->q15);
+    return SLB_OK;
+  }
   if (frames % ctx->rx.hop != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the hop (384)");
   int rc = run_rx_kernel (ctx, d_in, d_out, 0, ctx->cfg.channels, frames, ctx->dbg_audio, ctx->dbg_gain, (cudaStream_t) stream);
   if (rc) return rc;
@@ -492,6 +561,7 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   const bool chain = is_ssb_chain (ctx->cfg.chain);
   if (chain && frames % ctx->rx.hop != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the hop (384)");
+  if (ctx->q15 && frames % ctx->geo.block_frames != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the 48-frame firmware block");
   const uint32_t C = ctx->cfg.channels;
   const size_t ch_bytes = (size_t) frames * 4;
   // channels are independent, so the batch is cut into channel groups and H2D / kernel / D2H of consecutive groups overlap
@@ -525,6 +595,11 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
       int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], c0, n, frames, nullptr, nullptr, st);
       if (rc) return rc;
     }
+    else if (ctx->q15)
+    {
+      int rc = rxq15_launch (ctx, ctx->q15, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], c0, n, frames, ctx->sm_count, st, false);
+      if (rc) return rc;
+    }
     else
     {
       CK (ctx, launch_copy_iq (ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], (size_t) n * frames, st));
@@ -534,6 +609,7 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
   }
   for (int s = 0; s < kBulkSlots; s++) if (ctx->bulk_stream[s]) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
   if (chain) rx_advance (ctx, frames);
+  if (ctx->q15) rxq15_advance (ctx->q15);
   return SLB_OK;
 }
 int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames) { return process_host (ctx, h_in, h_out, frames, false); }
@@ -623,7 +699,7 @@ constexpr uint32_t kMagic = 0x534C4232u;   // 'SLB2'
 static size_t state_bytes (const slb_ctx *ctx)
 {
   const size_t C = ctx->cfg.channels, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop, R = ctx->geo.ring_frames;
-  return sizeof (StateHeader) + C /*modes*/ + C * ovl * 4 + C * 8 * 4 + 4 * C * R * 2 + C * hop * 4 * 2 + (ctx->chan ? chan64_state_bytes (ctx->chan) : 0);
+  return sizeof (StateHeader) + C /*modes*/ + C * ovl * 4 + C * 8 * 4 + 4 * C * R * 2 + C * hop * 4 * 2 + (ctx->chan ? chan64_state_bytes (ctx->chan) : 0) + (ctx->q15 ? rxq15_state_bytes (ctx->q15) : 0);
 }
 int slb_state_size (const slb_ctx *ctx, size_t *bytes) { if (!ctx || !bytes) return SLB_ERR_ARG; *bytes = state_bytes (ctx); return SLB_OK; }
 
@@ -646,7 +722,8 @@ int slb_state_save (slb_ctx *ctx, void *buf, size_t bytes)
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) { CK (ctx, cudaMemcpy (p, ctx->d_ring[w][k], C * R * 2, cudaMemcpyDeviceToHost)); p += C * R * 2; }
   CK (ctx, cudaMemcpy (p, ctx->d_acc, C * hop * 4, cudaMemcpyDeviceToHost)); p += C * hop * 4;
   CK (ctx, cudaMemcpy (p, ctx->d_proc[ctx->proc_cur], C * hop * 4, cudaMemcpyDeviceToHost)); p += C * hop * 4;
-  if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_save (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state save failed"); }
+  if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_save (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state save failed"); p += chan64_state_bytes (ctx->chan); }
+  if (ctx->q15) { CK (ctx, cudaDeviceSynchronize ()); if (rxq15_state_save (ctx->q15, p)) return fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state save failed"); }
   return SLB_OK;
 }
 
@@ -669,7 +746,8 @@ int slb_state_load (slb_ctx *ctx, const void *buf, size_t bytes)
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) { CK (ctx, cudaMemcpy (ctx->d_ring[w][k], p, C * R * 2, cudaMemcpyHostToDevice)); p += C * R * 2; }
   CK (ctx, cudaMemcpy (ctx->d_acc, p, C * hop * 4, cudaMemcpyHostToDevice)); p += C * hop * 4;
   CK (ctx, cudaMemcpy (ctx->d_proc[0], p, C * hop * 4, cudaMemcpyHostToDevice)); p += C * hop * 4;
-  if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_load (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state load failed"); }
+  if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_load (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state load failed"); p += chan64_state_bytes (ctx->chan); }
+  if (ctx->q15) { CK (ctx, cudaDeviceSynchronize ()); if (rxq15_state_load (ctx->q15, p)) return fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state load failed"); }
   // per-channel tile counters restart from zero on this context
   CK (ctx, cudaMemset (ctx->d_flag, 0, C * sizeof (unsigned)));
   ctx->flag_base = 0; ctx->acc_fill = h.acc_fill; ctx->tx_mode = h.tx_mode != 0;

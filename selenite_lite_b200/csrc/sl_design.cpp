@@ -114,6 +114,37 @@ int design_default_mask (uint32_t fs, uint32_t N, uint8_t mode, float *out)
   return SLB_OK;
 }
 
+// RX-SSB-q15: 64-tap band-pass Hilbert pair (Kaiser-windowed low-pass of half the audio bandwidth, heterodyned to the
+// audio centre with 0 / +90 degrees), each rail at half gain so that the wanted sideband sums to unity and the other
+// cancels; finite-window AGC. Quantised to q15 by round-to-nearest.
+int design_default_rx_q15 (uint32_t fs, slb_rx_q15_params *p)
+{
+  if (!p || fs != 48000u) return p ? SLB_ERR_UNSUPPORTED : SLB_ERR_ARG;
+  std::memset (p, 0, sizeof *p);
+  p->ntaps = SLB_Q15_TAPS; p->agc_block = fs / 1000u; p->agc_window = 16;
+  const int T = SLB_Q15_TAPS;
+  const double lo = 300.0, hi = 2700.0, fcut = (hi - lo) / 2.0 / (double) fs, fcen = (hi + lo) / 2.0 / (double) fs, beta = 6.0, mid = (T - 1) / 2.0;
+  double g[SLB_Q15_TAPS], dc = 0.0;
+  for (int n = 0; n < T; n++)
+  {
+    const double m = n - mid, x = 2.0 * fcut * m, r = m / mid;
+    g[n] = 2.0 * fcut * (std::sin (kPi * x) / (kPi * x)) * bessel_i0 (beta * std::sqrt (1.0 - r * r)) / bessel_i0 (beta);
+    dc += g[n];
+  }
+  for (int n = 0; n < T; n++)
+  {
+    const double ph = 2.0 * kPi * fcen * (n - mid), a = g[n] / dc;
+    p->taps_i[n] = (int16_t) std::lrint (32768.0 * a * std::cos (ph));
+    p->taps_q[n] = (int16_t) std::lrint (-32768.0 * a * std::sin (ph));
+  }
+  p->rel[0] = 32767;
+  for (int j = 1; j < SLB_Q15_WIN; j++) p->rel[j] = (int16_t) std::lrint (32767.0 * std::exp (-(double) j / 6.0));   // ~6 ms time constant
+  p->agc_target = 8192;                                                  // -12 dBFS
+  p->agc_floor = 16;
+  p->agc_gmax_q15 = 64u << 15;                                           // +36 dB
+  return SLB_OK;
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // Time-parallel evaluation of the 2-stage df2T cascade (arm_biquad_cascade_df2T_f32.c:551-562 per sample):
 // with x = 0 the 4-vector s = {d1_0,d2_0,d1_1,d2_1} evolves linearly, s' = A s, and the cascade output is c.s.

@@ -102,6 +102,23 @@ int chan64_launch (slb_ctx *ctx, Chan64State *st, const int16_t *d_in, int16_t *
                    int sm_count, void *stream, bool with_debug);
 void chan64_advance (Chan64State *st);
 
+// ---- RX-SSB-q15 (sl_rx_ssb_q15.cu): state object owned by the context ----
+struct RxQ15State;
+int design_default_rx_q15 (uint32_t fs, slb_rx_q15_params *p);
+int rxq15_create (slb_ctx *ctx, uint32_t channels, uint32_t fs, RxQ15State **out);
+void rxq15_destroy (RxQ15State *st);
+int rxq15_reset (slb_ctx *ctx, RxQ15State *st);
+int rxq15_set_params (slb_ctx *ctx, RxQ15State *st, const slb_rx_q15_params *p);
+const slb_rx_q15_params *rxq15_params (const RxQ15State *st);
+void rxq15_set_debug (RxQ15State *st, int16_t *audio, uint32_t *gain);
+int rxq15_set_sideband (slb_ctx *ctx, RxQ15State *st, uint32_t ch0, uint32_t n, int lsb);
+int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
+                  int sm_count, void *stream, bool with_debug);
+void rxq15_advance (RxQ15State *st);
+size_t rxq15_state_bytes (const RxQ15State *st);
+int rxq15_state_save (RxQ15State *st, char *dst);
+int rxq15_state_load (RxQ15State *st, const char *src);
+
 // ---- context accessors for translation units that do not see the struct (sl_stages.cu, sl_chains.cu) ----
 int ctx_device (const slb_ctx *ctx);
 size_t ctx_channels (const slb_ctx *ctx);

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _lib
 
-CHAIN_PASS, CHAIN_RX_SSB_F32, CHAIN_TX_SSB_F32, CHAIN_CHAN64_F32 = 0, 1, 2, 3
+CHAIN_PASS, CHAIN_RX_SSB_F32, CHAIN_TX_SSB_F32, CHAIN_CHAN64_F32, CHAIN_RX_SSB_Q15 = 0, 1, 2, 3, 4
 MODE_LSB, MODE_USB, MODE_CW, MODE_CWR, MODE_AM, MODE_FM, MODE_DIG, MODE_PKT = 0x00, 0x01, 0x02, 0x03, 0x04, 0x08, 0x0A, 0x0C
 
 
@@ -51,6 +51,20 @@ def chan_params_to_dict(p):
     return dict(bins=p.bins, taps_per_branch=p.taps_per_branch, agc_block=p.agc_block, envelope=p.envelope,
                 agc_target=p.agc_target, agc_decay=p.agc_decay, agc_floor=p.agc_floor, agc_gmax=p.agc_gmax,
                 proto=np.array(p.proto[:p.bins * p.taps_per_branch], np.float32))
+
+
+def default_rx_q15_params(fs=48000):
+    p = _lib.RxQ15Params()
+    rc = _lib.load().slb_default_rx_q15_params(fs, C.byref(p))
+    if rc:
+        raise SeleniteError("slb_default_rx_q15_params -> %d" % rc)
+    return p
+
+
+def q15_params_to_dict(p, lsb=0):
+    return dict(ntaps=p.ntaps, agc_block=p.agc_block, agc_window=p.agc_window, lsb=int(lsb),
+                taps_i=np.array(p.taps_i[:], np.int16), taps_q=np.array(p.taps_q[:], np.int16), rel=np.array(p.rel[:], np.int16),
+                agc_target=p.agc_target, agc_floor=p.agc_floor, agc_gmax_q15=p.agc_gmax_q15)
 
 
 def default_mask(fs=48000, fft_len=512, mode=MODE_USB):
@@ -172,7 +186,22 @@ class DspIf:
 
     def set_chan_params(self, p): self._ck(self.lib.slb_set_chan_params(self.h, C.byref(p)), "set_chan_params")
 
+    def rx_q15_params(self):
+        p = _lib.RxQ15Params()
+        self._ck(self.lib.slb_get_rx_q15_params(self.h, C.byref(p)), "get_rx_q15_params")
+        return p
+
+    def set_rx_q15_params(self, p): self._ck(self.lib.slb_set_rx_q15_params(self.h, C.byref(p)), "set_rx_q15_params")
+
+    def set_q15_debug_taps(self, audio=None, gain=None):
+        """audio: torch CUDA int16 [channels][frames]; gain: torch CUDA int32 [channels][frames/48] (Q15 gain per block)."""
+        self._keep_taps = (audio, gain)
+        self._ck(self.lib.slb_rx_q15_set_debug_taps(self.h, audio.data_ptr() if audio is not None else None,
+                                                    gain.data_ptr() if gain is not None else None), "rx_q15_set_debug_taps")
+
     def oracle_params(self, mode=MODE_USB):
+        if self.chain == CHAIN_RX_SSB_Q15:
+            return q15_params_to_dict(self.rx_q15_params(), lsb=mode in (MODE_LSB, MODE_CWR))
         if self.chain == CHAIN_CHAN64_F32:
             return chan_params_to_dict(self.chan_params())
         if self.chain == CHAIN_TX_SSB_F32:

@@ -15,9 +15,30 @@ import selenite_lite_b200 as slb  # noqa: E402
 from selenite_lite_b200.dsp_if import params_to_dict  # noqa: E402
 
 
+def golden_q15(ref):
+    """RX-SSB-q15 (all-integer chain): tone + noise on the wanted sideband, USB and LSB, and a full-scale random input
+    that drives every saturation point (FIR __SSAT, arm_add_q15, arm_abs_q15 of -32768, arm_scale_q15)."""
+    qp = slb.default_rx_q15_params(48000)
+    q = {"q15_taps_i": np.array(qp.taps_i[:], np.int16), "q15_taps_q": np.array(qp.taps_q[:], np.int16), "q15_rel": np.array(qp.rel[:], np.int16),
+         "q15_agc": np.array([qp.agc_window, qp.agc_target, qp.agc_floor, qp.agc_gmax_q15], np.int64)}
+    rng = np.random.Generator(np.random.PCG64(slb.signals.SEED + 15))
+    for name, lsb, f0, sb in (("usb", 0, 1000.0, +1), ("lsb", 1, 1700.0, -1)):
+        x = slb.synth_iq(1, 20 * 384, f0=f0, sideband=sb)[0]
+        y, audio, gain, _ = ref.rx_ssb_q15(slb.dsp_if.q15_params_to_dict(qp, lsb), x)
+        q["q15_%s_in" % name] = x; q["q15_%s_out" % name] = y; q["q15_%s_audio" % name] = audio; q["q15_%s_gain" % name] = gain
+    x = rng.integers(-32768, 32768, (10 * 384, 2)).astype(np.int16)
+    x[100:164] = -32768; x[500:564, 0] = 32767; x[500:564, 1] = -32768
+    y, audio, gain, _ = ref.rx_ssb_q15(slb.dsp_if.q15_params_to_dict(qp, 0), x)
+    q["q15_sat_in"] = x; q["q15_sat_out"] = y; q["q15_sat_audio"] = audio; q["q15_sat_gain"] = gain
+    np.savez_compressed(os.path.join(HERE, "rx_ssb_q15.npz"), **q)
+    print("rx_ssb_q15.npz", os.path.getsize(os.path.join(HERE, "rx_ssb_q15.npz")), "bytes")
+
+
 def main():
     oracle_lib.build_oracles()
     ref = oracle_lib.Oracle("ref")
+    if len(sys.argv) > 1 and sys.argv[1] == "q15":      # later additions regenerate alone: the older fixtures stay untouched
+        return golden_q15(ref)
     rng = np.random.Generator(np.random.PCG64(slb.signals.SEED))
 
     # ---- RX-SSB-f32, config-1 style: one channel, tone +1000 Hz + noise, 20 hops; and an LSB tone at -1700 Hz
@@ -96,6 +117,7 @@ def main():
     cbq = np.array(p.biquad[:10], np.float32)
     st["biquad_df2T_f32"] = ref.biquad_df2T_f32(cbq, 2, np.zeros(4, np.float32), xf, 48)[0]
     np.savez_compressed(os.path.join(HERE, "stages.npz"), **st)
+    golden_q15(ref)
     for f in ("rx_ssb_f32.npz", "tx_ssb_f32.npz", "chan64_f32.npz", "ring.npz", "stages.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 

@@ -55,6 +55,16 @@ class ChanState(C.Structure):
     _fields_ = [("fir_i", C.c_float * (64 * 8)), ("fir_q", C.c_float * (64 * 8)), ("env", C.c_float * 64)]
 
 
+class RxQ15Params(C.Structure):
+    _fields_ = [("ntaps", u32), ("agc_block", u32), ("agc_window", u32), ("lsb", u32),
+                ("taps_i", C.c_int16 * 64), ("taps_q", C.c_int16 * 64), ("rel", C.c_int16 * 32),
+                ("agc_target", C.c_int16), ("agc_floor", C.c_int16), ("agc_gmax_q15", u32)]
+
+
+class RxQ15State(C.Structure):
+    _fields_ = [("fir_i", C.c_int16 * (64 + 192)), ("fir_q", C.c_int16 * (64 + 192)), ("peaks", C.c_int16 * 32)]
+
+
 def build_oracles(want_ref=True):
     """Build the port (always) and, when the reference tree is mounted, the reference build."""
     subprocess.run(["make", "-s", "-C", ORACLE_DIR, "port"], check=True)
@@ -283,6 +293,24 @@ class Oracle:
         fn(C.byref(p), C.byref(st), x, out, iq, gain, frames)
         return out.reshape(frames, 2), iq.reshape(frames, 2), gain, st
 
+
+    def rx_ssb_q15(self, prm, in_iq, state=None):
+        """in_iq int16[frames][2] one channel. Returns out int16[frames][2], audio int16[frames] (pre-AGC),
+        gain uint32[frames/agc_block] (Q15), state."""
+        p = RxQ15Params()
+        p.ntaps, p.agc_block, p.agc_window, p.lsb = prm["ntaps"], prm["agc_block"], prm["agc_window"], int(prm["lsb"])
+        for k in range(64):
+            p.taps_i[k] = int(prm["taps_i"][k]); p.taps_q[k] = int(prm["taps_q"][k])
+        for k in range(32):
+            p.rel[k] = int(prm["rel"][k])
+        p.agc_target, p.agc_floor, p.agc_gmax_q15 = int(prm["agc_target"]), int(prm["agc_floor"]), int(prm["agc_gmax_q15"])
+        st = state if state is not None else RxQ15State()
+        x = np.ascontiguousarray(in_iq, np.int16).reshape(-1)
+        frames = x.size // 2
+        out = np.zeros(2 * frames, np.int16); audio = np.zeros(frames, np.int16); gain = np.zeros(frames // prm["agc_block"], np.uint32)
+        fn = self._f("rx_ssb_q15", [C.POINTER(RxQ15Params), C.POINTER(RxQ15State), i16p, i16p, i16p, np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), u32])
+        fn(C.byref(p), C.byref(st), x, out, audio, gain, frames)
+        return out.reshape(frames, 2), audio, gain, st
 
     def chan_f32(self, prm, in_iq, state=None, want_debug=True):
         """One wideband stream int16[frames][2]. Returns out int16[bins][frames/bins][2], audio f32[bins][hops],

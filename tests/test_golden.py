@@ -166,3 +166,55 @@ def test_port_stages_vs_golden(port):
     assert np.max(np.abs(port.cfft_f32(s["cfft_in_512"], 1, 1) - s["icfft_f32_512"])) < 2e-6 * rms / 512 * 30
     bq = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))["rx_biquad"]
     assert np.array_equal(port.biquad_df2T_f32(bq, 2, np.zeros(4, np.float32), s["f32_x"], 48)[0], s["biquad_df2T_f32"])
+
+
+# ---- RX-SSB-q15 (all-integer chain): every comparison is bit-exact ----
+def q15_params(g, lsb=0):
+    w, target, floor, gmax = [int(v) for v in g["q15_agc"]]
+    return dict(ntaps=64, agc_block=48, agc_window=w, lsb=lsb, taps_i=g["q15_taps_i"], taps_q=g["q15_taps_q"], rel=g["q15_rel"],
+                agc_target=target, agc_floor=floor, agc_gmax_q15=gmax)
+
+
+@pytest.mark.parametrize("name,lsb", [("usb", 0), ("lsb", 1), ("sat", 0)])
+def test_port_q15_chain_vs_golden(port, name, lsb):
+    g = np.load(os.path.join(GOLD, "rx_ssb_q15.npz"))
+    y, audio, gain, _ = port.rx_ssb_q15(q15_params(g, lsb), g["q15_%s_in" % name])
+    assert np.array_equal(audio, g["q15_%s_audio" % name])
+    assert np.array_equal(gain, g["q15_%s_gain" % name])
+    assert np.array_equal(y, g["q15_%s_out" % name])
+
+
+@pytest.mark.parametrize("name,lsb", [("usb", 0), ("lsb", 1), ("sat", 0)])
+def test_ref_q15_chain_reproduces_golden(ref, name, lsb):
+    g = np.load(os.path.join(GOLD, "rx_ssb_q15.npz"))
+    y, audio, gain, _ = ref.rx_ssb_q15(q15_params(g, lsb), g["q15_%s_in" % name])
+    assert np.array_equal(y, g["q15_%s_out" % name]) and np.array_equal(audio, g["q15_%s_audio" % name]) and np.array_equal(gain, g["q15_%s_gain" % name])
+
+
+def test_q15_chain_is_a_single_sideband_demodulator(port):
+    """Mid-band, the wanted sideband comes through at about unity and the other is suppressed by the Hilbert pair by
+    > 40 dB. (64 taps at 48 kHz make a wide transition: the band edges 300 / 2700 Hz sit at -6 dB.)"""
+    g = np.load(os.path.join(GOLD, "rx_ssb_q15.npz"))
+    n = np.arange(4800)
+    for f0 in (1000.0, 1500.0, 2000.0):
+        ph = 2 * np.pi * f0 * n / 48000.0
+        up = np.stack([np.round(8000 * np.cos(ph)), np.round(8000 * np.sin(ph))], 1).astype(np.int16)     # +f0: upper sideband
+        lo = np.stack([np.round(8000 * np.cos(ph)), np.round(-8000 * np.sin(ph))], 1).astype(np.int16)    # -f0
+        a_uu = port.rx_ssb_q15(q15_params(g, 0), up)[1][200:].astype(np.float64)
+        a_ul = port.rx_ssb_q15(q15_params(g, 0), lo)[1][200:].astype(np.float64)
+        a_ll = port.rx_ssb_q15(q15_params(g, 1), lo)[1][200:].astype(np.float64)
+        assert 0.9 * 8000 / np.sqrt(2) < a_uu.std() < 1.02 * 8000 / np.sqrt(2)
+        assert abs(a_ll.std() - a_uu.std()) < 0.02 * a_uu.std()
+        assert 20 * np.log10(a_uu.std() / max(a_ul.std(), 1e-9)) > 40.0
+
+
+def test_q15_chain_blocking_independence(port):
+    """One call over the stream == the same stream fed in pieces (the carried FIR state and peak window are the whole state)."""
+    g = np.load(os.path.join(GOLD, "rx_ssb_q15.npz"))
+    x = g["q15_usb_in"]; prm = q15_params(g, 0)
+    whole = port.rx_ssb_q15(prm, x)[0]
+    st, parts = None, []
+    for a, b in ((0, 48), (48, 480), (480, 4800), (4800, 7680)):
+        y, _, _, st = port.rx_ssb_q15(prm, x[a:b], st)
+        parts.append(y)
+    assert np.array_equal(np.concatenate(parts), whole)

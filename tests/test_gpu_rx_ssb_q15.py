@@ -1,0 +1,128 @@
+"""GPU parity of the fused RX-SSB-q15 chain (the all-integer receive chain: fir_q15 Hilbert pair on the integer tensor
+cores -> saturating add/sub -> q15 AGC), called through the C ABI, against the oracle and the committed golden vectors.
+Every stage is integer arithmetic, so every comparison is BIT-EXACT: pre-AGC audio, per-block gain word and output."""
+import os
+
+import numpy as np
+import pytest
+
+import selenite_lite_b200 as slb
+from test_golden import GOLD, q15_params
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(d, x, want_dbg=True):
+    C, T = x.shape[0], x.shape[1]
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    audio = torch.zeros((C, T), dtype=torch.int16, device="cuda") if want_dbg else None
+    gain = torch.zeros((C, T // 48), dtype=torch.int32, device="cuda") if want_dbg else None
+    d.set_q15_debug_taps(audio, gain)
+    y = d.rx_process(xd)
+    torch.cuda.synchronize()
+    d.set_q15_debug_taps(None, None)
+    return y.cpu().numpy(), (audio.cpu().numpy() if want_dbg else None), (gain.cpu().numpy().view(np.uint32) if want_dbg else None)
+
+
+@pytest.mark.parametrize("name,mode", [("usb", slb.MODE_USB), ("lsb", slb.MODE_LSB), ("sat", slb.MODE_USB)])
+def test_golden_vectors(name, mode):
+    g = np.load(os.path.join(GOLD, "rx_ssb_q15.npz"))
+    d = slb.DspIf(1, chain=slb.CHAIN_RX_SSB_Q15)
+    d.DSP_Set_Mode(mode)
+    p = d.rx_q15_params()
+    assert np.array_equal(np.array(p.taps_i[:], np.int16), g["q15_taps_i"]) and np.array_equal(np.array(p.taps_q[:], np.int16), g["q15_taps_q"])
+    y, audio, gain = run_gpu(d, g["q15_%s_in" % name][None])
+    assert np.array_equal(audio[0], g["q15_%s_audio" % name])
+    assert np.array_equal(gain[0], g["q15_%s_gain" % name])
+    assert np.array_equal(y[0], g["q15_%s_out" % name])
+
+
+@pytest.mark.parametrize("channels,frames", [(1, 48), (3, 96), (8, 1488), (9, 4800), (33, 9600), (130, 3072)])
+def test_vs_oracle_ragged_shapes(best_oracle, channels, frames):
+    x = slb.synth_iq(channels, frames)
+    d = slb.DspIf(channels, chain=slb.CHAIN_RX_SSB_Q15)
+    modes = [slb.MODE_USB, slb.MODE_LSB, slb.MODE_CW, slb.MODE_CWR, slb.MODE_DIG]
+    for c in range(channels):
+        d.DSP_Set_Mode(modes[c % len(modes)], channel=c)
+    y, audio, gain = run_gpu(d, x)
+    for c in range(channels):
+        exp, a, g_, _ = best_oracle.rx_ssb_q15(d.oracle_params(modes[c % len(modes)]), x[c])
+        assert np.array_equal(audio[c], a), (c, int(np.argmax(audio[c] != a)))
+        assert np.array_equal(gain[c], g_), c
+        assert np.array_equal(y[c], exp), c
+
+
+def test_every_saturation_point(best_oracle, rng):
+    """Hot taps (4x, clipped) and full-scale input: the FIR's __SSAT, arm_add_q15's saturation, arm_abs_q15(-32768) and
+    arm_scale_q15's saturation all fire; the split-byte tensor-core FIR must still equal the 64-bit accumulator."""
+    C, T = 16, 4800
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    p = d.rx_q15_params()
+    for k in range(64):
+        p.taps_i[k] = int(np.clip(4 * p.taps_i[k], -32768, 32767)); p.taps_q[k] = int(np.clip(4 * p.taps_q[k], -32768, 32767))
+    p.taps_i[0] = -32768; p.taps_q[63] = 32767; p.taps_i[31] = 32767; p.taps_q[32] = -32768
+    p.agc_window = 32; p.agc_floor = 1; p.agc_gmax_q15 = 255 << 15
+    d.set_rx_q15_params(p)
+    x = rng.integers(-32768, 32768, (C, T, 2)).astype(np.int16)
+    x[0, 100:300] = -32768; x[1, 100:300] = 32767; x[2, 100:300, 0] = -32768; x[2, 100:300, 1] = 32767; x[3, 1000:2000] = 0
+    x[4] = (x[4] // 4096).astype(np.int16)                   # a quiet channel: the gain limit and the floor come into play
+    y, audio, gain = run_gpu(d, x)
+    sat_seen = 0
+    for c in range(C):
+        exp, a, g_, _ = best_oracle.rx_ssb_q15(d.oracle_params(slb.MODE_USB), x[c])
+        assert np.array_equal(audio[c], a), c
+        assert np.array_equal(gain[c], g_), c
+        assert np.array_equal(y[c], exp), c
+        sat_seen += int(np.sum(np.abs(a.astype(np.int32)) >= 32767))
+    assert sat_seen > 100
+
+
+def test_streaming_state_across_calls(best_oracle):
+    """Two bulk calls == one: the carried raw tail and peak window are the whole state. Long enough (and enough channels
+    few) that the launch is cut into several time segments, each re-deriving its peak window."""
+    C, T = 2, 48 * 2000
+    x = slb.synth_iq(C, T)
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    y1, _, _ = run_gpu(d, x[:, :48 * 700], want_dbg=False)
+    y2, _, _ = run_gpu(d, x[:, 48 * 700:], want_dbg=False)
+    whole = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    yw, _, _ = run_gpu(whole, x, want_dbg=False)
+    assert np.array_equal(np.concatenate([y1, y2], 1), yw)
+    exp = best_oracle.rx_ssb_q15(d.oracle_params(slb.MODE_USB), x[1])[0]
+    assert np.array_equal(yw[1], exp)
+
+
+def test_host_path_checkpoint_and_ring(best_oracle):
+    C = 5
+    x = slb.synth_iq(C, 48 * 40)
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    y = d.rx_process(x[:, :48 * 20])                          # numpy -> slb_rx_process_host
+    snap = d.state_save()
+    y2 = d.rx_process(x[:, 48 * 20:])
+    exp = np.stack([best_oracle.rx_ssb_q15(d.oracle_params(slb.MODE_USB), x[c])[0] for c in range(C)])
+    assert np.array_equal(np.concatenate([y, y2], 1), exp)
+    e = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    e.state_load(snap)
+    assert np.array_equal(e.rx_process(x[:, 48 * 20:]), y2)
+    # behind the firmware's 1 ms cadence: each 48-frame block is demodulated in the call that delivers it, then rides the ring
+    f = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    p = slb.DspIf(C, chain=slb.CHAIN_PASS)
+    for b in range(40):
+        f.DSP_In_Buff_Write(x[:, 48 * b:48 * (b + 1)].reshape(C, -1))
+        p.DSP_In_Buff_Write(exp[:, 48 * b:48 * (b + 1)].reshape(C, -1))
+        assert np.array_equal(f.DSP_In_Buff_Read(192), p.DSP_In_Buff_Read(192))
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] width (1024 channels): shards equal the whole, and the output is L = R everywhere."""
+    C, T = 1024, 48 * 500
+    x = slb.synth_iq(8, T)
+    x = np.ascontiguousarray(np.tile(x, (C // 8, 1, 1)))
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    y, _, _ = run_gpu(d, x, want_dbg=False)
+    assert np.array_equal(y[..., 0], y[..., 1])
+    assert np.array_equal(y[:8], y[8:16]) and np.array_equal(y[:8], y[-8:])
+    h = slb.DspIf(C // 2, chain=slb.CHAIN_RX_SSB_Q15)
+    yh, _, _ = run_gpu(h, x[C // 2:], want_dbg=False)
+    assert np.array_equal(yh, y[C // 2:])

@@ -27,7 +27,7 @@ def timeit(fn, steps, warmup=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--which", default="tx,chan,rx")
+    ap.add_argument("--which", default="tx,chan,rx,q15")
     ap.add_argument("--seconds", type=int, default=10)
     ap.add_argument("--rx-channels", type=int, default=1024)
     args = ap.parse_args()
@@ -49,6 +49,11 @@ def main():
             x = torch.randint(-3000, 3000, (S, T, 2), dtype=torch.int16, device=dev, generator=g)
             d = slb.DspIf(S, fs=192000, chain=slb.CHAIN_CHAN64_F32); y = torch.empty((S, 64, T // 64, 2), dtype=torch.int16, device=dev)
             ms = timeit(lambda: d.chan_process(x, y), args.steps); n = S * T; name = "chan64_f32 (config 4: 64 x 192 kHz streams -> 4096 channels, %d s)" % args.seconds
+        elif which == "q15":
+            C, T = args.rx_channels, 48000 * args.seconds
+            x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
+            d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15); y = torch.empty_like(x)
+            ms = timeit(lambda: d.rx_process(x, y), args.steps); n = C * T; name = "rx_ssb_q15 (%d channels x %d s)" % (C, args.seconds)
         else:
             C, T = args.rx_channels, 48000 * args.seconds // 384 * 384
             x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
