@@ -37,9 +37,12 @@ namespace {
 constexpr int kTaps = SLB_Q15_TAPS;              // 64
 constexpr int kWin = SLB_Q15_WIN;                // peak ring length (>= agc_window)
 constexpr int kBlk = 48;                         // AGC block = firmware block at 48 kHz = 3 MMA blocks of 16 frames
-constexpr int kChunkBlocks = 2;                  // AGC blocks per staged chunk
+#ifndef SL_Q15_CHUNK
+#define SL_Q15_CHUNK 2
+#endif
+constexpr int kChunkBlocks = SL_Q15_CHUNK;       // AGC blocks per staged chunk
 constexpr int kChunk = kChunkBlocks * kBlk;      // 96 frames
-constexpr int kRowWords = 176;                   // words per channel row of a raw stage: 64 history + 96 new + 16 pad;
+constexpr int kRowWords = kTaps + kChunk + 16;   // words per channel row of a raw stage: 64 history + 96 new + 16 pad;
                                                  // 704 B = 64 mod 128, so the 16-byte loads of lanes (ch, tig), (ch+1, tig)
                                                  // fall into different bank halves
 constexpr int kWarps = 4;
@@ -423,13 +426,8 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
   P.channels = nch; P.frames = frames; P.blocks = frames / kBlk; P.groups = (nch + 7) / 8; P.window = st->prm.agc_window;
   P.target = st->prm.agc_target; P.floor_ = st->prm.agc_floor; P.gmax = st->prm.agc_gmax_q15;
 
-  static bool attr_set = false;
-  if (!attr_set)
-  {
-    if (cudaFuncSetAttribute (rx_ssb_q15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes) != cudaSuccess)
-      return ctx_fail (ctx, SLB_ERR_CUDA, "cudaFuncSetAttribute failed");
-    attr_set = true;
-  }
+  if (cudaFuncSetAttribute (rx_ssb_q15_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes) != cudaSuccess)
+    return ctx_fail (ctx, SLB_ERR_CUDA, "cudaFuncSetAttribute failed");
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, rx_ssb_q15_kernel, kThreads, kSmemBytes) != cudaSuccess || per_sm < 1) per_sm = 1;
   // segments: independent given the input (finite AGC window), each pays window-1 blocks of re-derived peaks. Aim at two
@@ -440,7 +438,7 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
   if (segs > P.blocks / min_seg) segs = P.blocks / min_seg;
   if (segs < 1) segs = 1;
   uint32_t seg_blocks = (P.blocks + segs - 1) / segs;
-  seg_blocks += seg_blocks % kChunkBlocks;                                       // whole chunks
+  seg_blocks = (seg_blocks + kChunkBlocks - 1) / kChunkBlocks * kChunkBlocks;    // whole chunks
   P.seg_blocks = seg_blocks; P.segs = (P.blocks + seg_blocks - 1) / seg_blocks;
   const uint64_t items = (uint64_t) P.groups * P.segs;
   uint64_t grid = ((uint64_t) items + kWarps - 1) / kWarps;
