@@ -35,7 +35,8 @@ void SLO (rx_ssb_f32) (const slo_rx_f32_params *p, slo_rx_f32_state *st, const i
     SLO (cfft_f32) (frame, N, 0, 1);
     SLO (cmplx_mult_cmplx_f32) (frame, p->mask, prod, N);
     SLO (cfft_f32) (prod, N, 1, 1);
-    for (uint32_t k = 0; k < hop; k++) audio[k] = prod[2 * (ovl + k)];   /* keep last hop, real part */
+    if (p->envelope) SLO (cmplx_mag_f32) (prod + 2 * ovl, audio, hop);   /* AM: keep last hop, envelope */
+    else for (uint32_t k = 0; k < hop; k++) audio[k] = prod[2 * (ovl + k)];   /* keep last hop, real part */
 
     SLO (biquad_df2T_f32) (p->biquad, p->n_stages, st->bq, audio, audio, hop, B);
     if (audio_dbg) memcpy (audio_dbg + o, audio, sizeof (float) * hop);

@@ -113,6 +113,7 @@ typedef struct
   float biquad[5 * SLO_MAX_STAGES];
   float agc_target, agc_decay, agc_floor, agc_gmax;
   const float *mask;  /* 2*fft_len, interleaved re/im, unscaled */
+  uint32_t envelope;  /* 0: product detector (real part), 1: AM envelope detector [cmplx_mag_f32] */
 } slo_rx_f32_params;
 
 typedef struct

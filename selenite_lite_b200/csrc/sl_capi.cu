@@ -156,7 +156,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   const uint32_t C = cfg->channels, N = ctx->rx.fft_len, hop = ctx->rx.hop, ovl = N - hop, R = ctx->geo.ring_frames;
 
   ctx->masks_host.assign ((size_t) SLB_MAX_MASKS * 2 * N, 0.0f);
-  const uint8_t modes[6] = { SLB_MODE_LSB, SLB_MODE_USB, SLB_MODE_CW, SLB_MODE_CWR, SLB_MODE_DIG, SLB_MODE_PKT };
+  const uint8_t modes[7] = { SLB_MODE_LSB, SLB_MODE_USB, SLB_MODE_CW, SLB_MODE_CWR, SLB_MODE_DIG, SLB_MODE_PKT, SLB_MODE_AM };
   for (uint8_t m : modes) design_default_mask (cfg->fs, N, m, ctx->masks_host.data () + (size_t) mode_to_mask_slot (m) * 2 * N);
   ctx->mode_host.assign (C, SLB_MODE_USB);
   ctx->slot_host.assign (C, (uint8_t) mode_to_mask_slot (SLB_MODE_USB));
@@ -248,7 +248,7 @@ int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask)
 {
   if (!ctx || !mask) return SLB_ERR_ARG;
   const int slot = mode_to_mask_slot (mode);
-  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "mode has no spectral mask (AM/FM are not SSB-style demodulators)");
+  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "mode has no spectral mask (FM)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   std::memcpy (ctx->masks_host.data () + (size_t) slot * 2 * ctx->rx.fft_len, mask, (size_t) 2 * ctx->rx.fft_len * sizeof (float));
   return upload_chain_constants (ctx);
@@ -316,11 +316,20 @@ int SLB_DSP_Init (slb_ctx *ctx)                       // dsp_if.c:377-383 (+ i2s
 int SLB_DSP_Set_RX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; ctx->tx_mode = false; return SLB_OK; }   // dsp_if.c:347 (codec routing is out of scope)
 int SLB_DSP_Set_TX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; ctx->tx_mode = true; return SLB_OK; }    // dsp_if.c:357
 
+// which FT-817 mode bytes (rxtx_if.h:33-43) a chain has a demodulator / modulator for
+static int check_mode (slb_ctx *ctx, uint8_t mode)
+{
+  if (mode_to_mask_slot (mode) < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "no FM discriminator in this build (AM, LSB, USB, CW, CW-R, DIG, PKT are served)");
+  if (mode == SLB_MODE_AM && ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 && ctx->cfg.chain != SLB_CHAIN_PASS)
+    return fail (ctx, SLB_ERR_UNSUPPORTED, "AM is served by the RX-SSB-f32 chain (envelope detector) and the channelizer only");
+  return SLB_OK;
+}
+
 int SLB_DSP_Set_Mode_Channel (slb_ctx *ctx, uint32_t ch, uint8_t mode)
 {
   if (!ctx || ch >= ctx->cfg.channels) return SLB_ERR_ARG;
   const int slot = mode_to_mask_slot (mode);
-  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "AM/FM demodulators are not built yet (DESIGN.md: next)");
+  { const int rc = check_mode (ctx, mode); if (rc) return rc; }
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   if (ctx->q15)
   {
@@ -345,7 +354,7 @@ int SLB_DSP_Set_Mode (slb_ctx *ctx, uint8_t mode)     // dsp_if.c:367-370 is the
     return chan64_set_params (ctx, ctx->chan, &p);
   }
   const int slot = mode_to_mask_slot (mode);
-  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "AM/FM demodulators are not built yet (DESIGN.md: next)");
+  { const int rc = check_mode (ctx, mode); if (rc) return rc; }
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   std::fill (ctx->mode_host.begin (), ctx->mode_host.end (), mode);
   if (ctx->q15)

@@ -41,7 +41,8 @@ struct RingPtrs
 int design_default_rx_f32 (uint32_t fs, slb_rx_f32_params *out);
 int design_default_tx_f32 (uint32_t fs, slb_tx_f32_params *out);
 int design_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out);
-int mode_to_mask_slot (uint8_t mode);   // -1 when the mode has no SSB-style mask (AM, FM)
+int mode_to_mask_slot (uint8_t mode);   // -1 when the mode has no spectral mask (FM)
+constexpr int kAmMaskSlot = 6;          // channels on this slot use the envelope detector (arm_cmplx_mag_f32) instead of Re
 
 // Tables the time-parallel biquad needs, derived in double from the 2-stage df2T coefficients (sl_design.cpp).
 constexpr int kRun = 24;                // samples per run; a lane of the recurrence warp carries two runs = one AGC block

@@ -443,7 +443,9 @@ __global__ void __launch_bounds__ (kThreads, SL_RX_CTAS) ssb_f32_kernel
       }
       __syncwarp ();
       if (lane == 0) mbar_arrive (sEmpty + rbuf);                                  // this warp no longer needs raw[rbuf]
-      const float4 *mask = P.masks + (size_t) P.mask_slot[c] * 256;
+      const int slot = P.mask_slot[c];
+      const float4 *mask = P.masks + (size_t) slot * 256;
+      const bool envelope = !kTx && slot == kAmMaskSlot;                           // AM: |z| instead of Re z
       it.next (P);
       // ---- forward FFT (arm_cfft_f32 forward; pass 0 needs no twiddles), spectral mask (arm_cmplx_mult_cmplx_f32), then
       // the inverse transform as a forward transform of the re/im-swapped spectrum: N ifft(Y) = swap(fft(swap(Y))), so
@@ -502,7 +504,15 @@ __global__ void __launch_bounds__ (kThreads, SL_RX_CTAS) ssb_f32_kernel
           {
             const int half = i / kRun, k = i - half * kRun;
             const int pos = blk * kBlkStride + 2 * k + half;                       // runs A/B of a block are interleaved
-            a[pos] = lo_of (xi[r]); a[pos + 2] = hi_of (xi[r]);
+            float v0 = lo_of (xi[r]), v1 = hi_of (xi[r]);
+            if (envelope)
+            {
+              // arm_cmplx_mag_f32.c:72: sqrt (re * re + im * im), each product rounded (the oracle build does not contract)
+              const float u0 = lo_of (xr[r]), u1 = hi_of (xr[r]);
+              v0 = __fsqrt_rn (__fadd_rn (__fmul_rn (v0, v0), __fmul_rn (u0, u0)));
+              v1 = __fsqrt_rn (__fadd_rn (__fmul_rn (v1, v1), __fmul_rn (u1, u1)));
+            }
+            a[pos] = v0; a[pos + 2] = v1;
           }
         }
       }

@@ -206,7 +206,9 @@ class DspIf:
             return chan_params_to_dict(self.chan_params())
         if self.chain == CHAIN_TX_SSB_F32:
             return tx_params_to_dict(self.tx_params(), self.mask(mode))
-        return params_to_dict(self.rx_params(), self.mask(mode))
+        prm = params_to_dict(self.rx_params(), self.mask(mode))
+        prm["envelope"] = int(mode == MODE_AM)
+        return prm
 
     # ---- bulk path ----
     def rx_process(self, x, out=None, stream=None, _dir="rx"):

@@ -28,7 +28,7 @@ class RxF32Params(C.Structure):
     _fields_ = [("fft_len", u32), ("hop", u32), ("agc_block", u32), ("n_stages", u32),
                 ("biquad", C.c_float * (5 * MAX_STAGES)),
                 ("agc_target", C.c_float), ("agc_decay", C.c_float), ("agc_floor", C.c_float), ("agc_gmax", C.c_float),
-                ("mask", C.POINTER(C.c_float))]
+                ("mask", C.POINTER(C.c_float)), ("envelope", u32)]
 
 
 class RxF32State(C.Structure):
@@ -249,6 +249,7 @@ class Oracle:
         mask = np.ascontiguousarray(np.asarray(prm["mask"], np.complex64).view(np.float32))
         p.mask = mask.ctypes.data_as(C.POINTER(C.c_float))
         p._keep = mask
+        p.envelope = int(prm.get("envelope", 0))
         return p
 
     def rx_ssb_f32(self, prm, in_iq, state=None, want_debug=True):
