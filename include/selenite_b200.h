@@ -148,6 +148,17 @@ int SLB_DSP_Out_Buff_Read (slb_ctx *ctx, uint16_t *pbuf, uint16_t size);        
 int SLB_DSP_Out_Buff_Mute (slb_ctx *ctx);                                          /* dsp_if.c:188 */
 /* ring introspection (tests): which 0 = RX ring (dsp_in_buff), 1 = TX ring (dsp_out_buff); out = {enable, rd, wr} */
 int slb_ring_get_ptrs (const slb_ctx *ctx, int which, uint32_t out[3]);
+/* ---- per-channel cadence (the ring's drift compensation as a batched primitive; dsp_if.c:136-179, :252-300) ----
+ * `active` is a HOST array [channels] (NULL = all): a channel with active[c] == 0 is skipped by this call, exactly as if
+ * its producer / consumer had not fired this millisecond. From the first such call on every channel carries its own
+ * {enable, rd, wr} on the device, fill levels drift apart, and the firmware's own +-1 slip / repeat logic re-centres each
+ * channel independently. A skipped channel's part of a read buffer is zero-filled. The producer side of the RX ring
+ * accepts a mask with the PASS chain only (a chain's filter state has one cadence). */
+int SLB_DSP_In_Buff_Write_Ch (slb_ctx *ctx, const uint16_t *pbuf, uint16_t size, const uint8_t *active);
+int SLB_DSP_In_Buff_Read_Ch (slb_ctx *ctx, uint8_t *pbuf, uint32_t size, const uint8_t *active);
+int SLB_DSP_Out_Buff_Write_Ch (slb_ctx *ctx, const uint8_t *pbuf, uint32_t size, const uint8_t *active);
+int SLB_DSP_Out_Buff_Read_Ch (slb_ctx *ctx, uint16_t *pbuf, uint16_t size, const uint8_t *active);
+int slb_ring_get_ptrs_channel (slb_ctx *ctx, int which, uint32_t channel, uint32_t out[3]);
 /* copies the de-interleaved ring contents to host: i, q each [channels][DSP_BUFF_SIZE] */
 int slb_ring_get_iq (slb_ctx *ctx, int which, int16_t *i, int16_t *q);
 

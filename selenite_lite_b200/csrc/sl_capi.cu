@@ -46,6 +46,8 @@ struct slb_ctx
 
   // device: firmware rings (de-interleaved planes) + per-call block staging
   RingPtrs ring_in, ring_out;
+  // per-channel cadence (SLB_DSP_*_Ch): once switched on, the pointers of every channel live on the device
+  bool ring_pc = false; uint32_t *d_rptr[2] = { nullptr, nullptr }; uint8_t *d_active = nullptr;
   int16_t *d_ring[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [which][i|q]
   int16_t *d_blk = nullptr; size_t blk_frames = 0;                           // [C][blk_frames][2]
   // chain at the 1 ms cadence: accumulate `hop` frames, process, feed the ring from the previous super-block
@@ -117,6 +119,7 @@ static int reset_state (slb_ctx *ctx)
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   ctx->flag_base = 0; ctx->ovl_parity = 0; ctx->acc_fill = 0; ctx->proc_cur = 0;
   ctx->ring_in.reset (R); ctx->ring_out.reset (R);
+  ctx->ring_pc = false;
   if (ctx->chan) return chan64_reset (ctx, ctx->chan);
   if (ctx->q15) return rxq15_reset (ctx, ctx->q15);
   return SLB_OK;
@@ -201,6 +204,7 @@ void slb_destroy (slb_ctx *ctx)
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
   cudaFree (ctx->d_blk); cudaFree (ctx->d_acc); cudaFree (ctx->d_scratch);
+  cudaFree (ctx->d_rptr[0]); cudaFree (ctx->d_rptr[1]); cudaFree (ctx->d_active);
   for (int s = 0; s < kBulkSlots; s++)
   {
     cudaFree (ctx->d_bulk_in[s]); cudaFree (ctx->d_bulk_out[s]);
@@ -399,7 +403,35 @@ static int ensure_blk (slb_ctx *ctx, size_t frames)
   return SLB_OK;
 }
 
-static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_t frames)
+// switch to per-channel pointers: every channel starts from the shared host-side state
+static int ring_pc_enable (slb_ctx *ctx)
+{
+  if (ctx->ring_pc) return SLB_OK;
+  const uint32_t C = ctx->cfg.channels;
+  for (int w = 0; w < 2; w++) if (!ctx->d_rptr[w]) CK (ctx, cudaMalloc (&ctx->d_rptr[w], (size_t) C * 4 * sizeof (uint32_t)));
+  if (!ctx->d_active) CK (ctx, cudaMalloc (&ctx->d_active, C));
+  const RingPtrs *rp[2] = { &ctx->ring_in, &ctx->ring_out };
+  std::vector<uint32_t> h ((size_t) C * 4);
+  for (int w = 0; w < 2; w++)
+  {
+    for (uint32_t c = 0; c < C; c++) { h[4 * c] = rp[w]->enable; h[4 * c + 1] = rp[w]->rd; h[4 * c + 2] = rp[w]->wr; h[4 * c + 3] = 0; }
+    CK (ctx, cudaMemcpyAsync (ctx->d_rptr[w], h.data (), h.size () * sizeof (uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK (ctx, cudaStreamSynchronize (ctx->stream));
+  }
+  ctx->ring_pc = true;
+  return SLB_OK;
+}
+// device copy of the activity mask of this call (nullptr = all channels)
+static int ring_pc_mask (slb_ctx *ctx, const uint8_t *active, const uint8_t **d_out)
+{
+  *d_out = nullptr;
+  if (!active) return SLB_OK;
+  CK (ctx, cudaMemcpyAsync (ctx->d_active, active, ctx->cfg.channels, cudaMemcpyHostToDevice, ctx->stream));
+  *d_out = ctx->d_active;
+  return SLB_OK;
+}
+
+static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_t frames, const uint8_t *active = nullptr, bool per_channel = false)
 {
   if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
   const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames;
@@ -407,6 +439,23 @@ static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
   const bool chain = (which == 0 && is_ssb_chain (ctx->cfg.chain));
+  if (per_channel || ctx->ring_pc)
+  {
+    if (which == 0 && active && ctx->cfg.chain != SLB_CHAIN_PASS)
+      return fail (ctx, SLB_ERR_UNSUPPORTED, "a per-channel producer mask on the RX ring needs the PASS chain (a chain's filter state has one cadence)");
+    if (which == 0 && ctx->cfg.chain != SLB_CHAIN_PASS)
+      return fail (ctx, SLB_ERR_UNSUPPORTED, "per-channel cadence with a chain behind the RX ring is not built: use the PASS chain or the bulk calls");
+    int rc = ring_pc_enable (ctx); if (rc) return rc;
+    const uint8_t *d_act = nullptr;
+    rc = ring_pc_mask (ctx, active, &d_act); if (rc) return rc;
+    rc = ensure_blk (ctx, frames); if (rc) return rc;
+    CK (ctx, cudaMemcpyAsync (ctx->d_blk, pbuf, (size_t) C * frames * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK (ctx, launch_ring_plan (ctx->d_rptr[which], d_act, C, R, true, which != 0, frames, ctx->stream));
+    CK (ctx, launch_ring_write_pc (ctx->d_blk, frames, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, ctx->d_rptr[which], frames, ctx->stream));
+    ctx->launches += 2;
+    CK (ctx, cudaStreamSynchronize (ctx->stream));
+    return SLB_OK;
+  }
   if (which == 0 && ctx->q15)
   {
     // the integer chain works at the firmware's own block size: the block is demodulated and enters the ring in the same
@@ -455,13 +504,27 @@ static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_
   return SLB_OK;
 }
 
-static int ring_read_common (slb_ctx *ctx, int which, void *pbuf, uint32_t frames)
+static int ring_read_common (slb_ctx *ctx, int which, void *pbuf, uint32_t frames, const uint8_t *active = nullptr, bool per_channel = false)
 {
   if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
   const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames;
   if (!pbuf || frames == 0) return fail (ctx, SLB_ERR_ARG, "empty read");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   int rc = ensure_blk (ctx, frames); if (rc) return rc;
+  if (per_channel || ctx->ring_pc)
+  {
+    if (which == 0 && !ctx->ring_pc && ctx->cfg.chain != SLB_CHAIN_PASS && ctx->acc_fill != 0)
+      return fail (ctx, SLB_ERR_STATE, "switch to per-channel cadence on a super-block boundary");
+    rc = ring_pc_enable (ctx); if (rc) return rc;
+    const uint8_t *d_act = nullptr;
+    rc = ring_pc_mask (ctx, active, &d_act); if (rc) return rc;
+    CK (ctx, launch_ring_plan (ctx->d_rptr[which], d_act, C, R, false, which != 0, frames, ctx->stream));
+    CK (ctx, launch_ring_read_pc (ctx->d_blk, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, ctx->d_rptr[which], frames, ctx->stream));
+    ctx->launches += 2;
+    CK (ctx, cudaMemcpyAsync (pbuf, ctx->d_blk, (size_t) C * frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK (ctx, cudaStreamSynchronize (ctx->stream));
+    return SLB_OK;
+  }
   RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
   const uint32_t rd0 = rp.plan_read (which != 0, frames);
   CK (ctx, launch_ring_read (ctx->d_blk, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, rd0, frames, ctx->stream));
@@ -479,6 +542,23 @@ int SLB_DSP_Out_Buff_Write (slb_ctx *ctx, const uint8_t *pbuf, uint32_t size)   
 { if (!ctx) return SLB_ERR_ARG; if (size < 4 || (size & 3)) return fail (ctx, SLB_ERR_ARG, "size must be a multiple of 4 bytes"); return ring_write_common (ctx, 1, pbuf, size / 4u); }
 int SLB_DSP_Out_Buff_Read (slb_ctx *ctx, uint16_t *pbuf, uint16_t size)            // size in half-words
 { if (!ctx) return SLB_ERR_ARG; if (size < 2 || (size & 1)) return fail (ctx, SLB_ERR_ARG, "size must be an even number of half-words >= 2"); return ring_read_common (ctx, 1, pbuf, size / 2u); }
+
+int SLB_DSP_In_Buff_Write_Ch (slb_ctx *ctx, const uint16_t *pbuf, uint16_t size, const uint8_t *active)
+{ if (!ctx) return SLB_ERR_ARG; if (size < 2 || (size & 1)) return fail (ctx, SLB_ERR_ARG, "size must be an even number of half-words >= 2"); return ring_write_common (ctx, 0, pbuf, size / 2u, active, true); }
+int SLB_DSP_In_Buff_Read_Ch (slb_ctx *ctx, uint8_t *pbuf, uint32_t size, const uint8_t *active)
+{ if (!ctx) return SLB_ERR_ARG; if (size < 4 || (size & 3)) return fail (ctx, SLB_ERR_ARG, "size must be a multiple of 4 bytes"); return ring_read_common (ctx, 0, pbuf, size / 4u, active, true); }
+int SLB_DSP_Out_Buff_Write_Ch (slb_ctx *ctx, const uint8_t *pbuf, uint32_t size, const uint8_t *active)
+{ if (!ctx) return SLB_ERR_ARG; if (size < 4 || (size & 3)) return fail (ctx, SLB_ERR_ARG, "size must be a multiple of 4 bytes"); return ring_write_common (ctx, 1, pbuf, size / 4u, active, true); }
+int SLB_DSP_Out_Buff_Read_Ch (slb_ctx *ctx, uint16_t *pbuf, uint16_t size, const uint8_t *active)
+{ if (!ctx) return SLB_ERR_ARG; if (size < 2 || (size & 1)) return fail (ctx, SLB_ERR_ARG, "size must be an even number of half-words >= 2"); return ring_read_common (ctx, 1, pbuf, size / 2u, active, true); }
+int slb_ring_get_ptrs_channel (slb_ctx *ctx, int which, uint32_t channel, uint32_t out[3])
+{
+  if (!ctx || !out || which < 0 || which > 1 || channel >= ctx->cfg.channels) return SLB_ERR_ARG;
+  if (!ctx->ring_pc) return slb_ring_get_ptrs (ctx, which, out);
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  CK (ctx, cudaMemcpy (out, ctx->d_rptr[which] + 4 * (size_t) channel, 3 * sizeof (uint32_t), cudaMemcpyDeviceToHost));
+  return SLB_OK;
+}
 
 int SLB_DSP_Out_Buff_Mute (slb_ctx *ctx)                                           // dsp_if.c:188-195: zero the samples, keep the pointers
 {
@@ -702,13 +782,14 @@ struct StateHeader
   uint32_t magic, channels, fs, chain, fft_len, hop;
   uint32_t flag_base, ovl_parity, acc_fill, proc_cur, tx_mode;
   uint32_t ring[2][4];
+  uint32_t ring_pc;                          // 1: the per-channel pointer tables at the end of the blob are live
 };
-constexpr uint32_t kMagic = 0x534C4232u;   // 'SLB2'
+constexpr uint32_t kMagic = 0x534C4233u;   // 'SLB3'
 }
 static size_t state_bytes (const slb_ctx *ctx)
 {
   const size_t C = ctx->cfg.channels, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop, R = ctx->geo.ring_frames;
-  return sizeof (StateHeader) + C /*modes*/ + C * ovl * 4 + C * 8 * 4 + 4 * C * R * 2 + C * hop * 4 * 2 + (ctx->chan ? chan64_state_bytes (ctx->chan) : 0) + (ctx->q15 ? rxq15_state_bytes (ctx->q15) : 0);
+  return sizeof (StateHeader) + C /*modes*/ + C * ovl * 4 + C * 8 * 4 + 4 * C * R * 2 + C * hop * 4 * 2 + (ctx->chan ? chan64_state_bytes (ctx->chan) : 0) + (ctx->q15 ? rxq15_state_bytes (ctx->q15) : 0) + 2 * C * 4 * sizeof (uint32_t) /* per-channel ring pointers */;
 }
 int slb_state_size (const slb_ctx *ctx, size_t *bytes) { if (!ctx || !bytes) return SLB_ERR_ARG; *bytes = state_bytes (ctx); return SLB_OK; }
 
@@ -724,6 +805,7 @@ int slb_state_save (slb_ctx *ctx, void *buf, size_t bytes)
   h.flag_base = ctx->flag_base; h.ovl_parity = (uint32_t) ctx->ovl_parity; h.acc_fill = ctx->acc_fill; h.proc_cur = (uint32_t) ctx->proc_cur; h.tx_mode = ctx->tx_mode;
   const RingPtrs *rp[2] = { &ctx->ring_in, &ctx->ring_out };
   for (int w = 0; w < 2; w++) { h.ring[w][0] = rp[w]->size; h.ring[w][1] = rp[w]->enable; h.ring[w][2] = rp[w]->rd; h.ring[w][3] = rp[w]->wr; }
+  h.ring_pc = ctx->ring_pc ? 1u : 0u;
   std::memcpy (p, &h, sizeof h); p += sizeof h;
   std::memcpy (p, ctx->mode_host.data (), C); p += C;
   CK (ctx, cudaMemcpy (p, ctx->d_ovl[ctx->ovl_parity], C * ovl * 4, cudaMemcpyDeviceToHost)); p += C * ovl * 4;
@@ -732,7 +814,13 @@ int slb_state_save (slb_ctx *ctx, void *buf, size_t bytes)
   CK (ctx, cudaMemcpy (p, ctx->d_acc, C * hop * 4, cudaMemcpyDeviceToHost)); p += C * hop * 4;
   CK (ctx, cudaMemcpy (p, ctx->d_proc[ctx->proc_cur], C * hop * 4, cudaMemcpyDeviceToHost)); p += C * hop * 4;
   if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_save (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state save failed"); p += chan64_state_bytes (ctx->chan); }
-  if (ctx->q15) { CK (ctx, cudaDeviceSynchronize ()); if (rxq15_state_save (ctx->q15, p)) return fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state save failed"); }
+  if (ctx->q15) { CK (ctx, cudaDeviceSynchronize ()); if (rxq15_state_save (ctx->q15, p)) return fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state save failed"); p += rxq15_state_bytes (ctx->q15); }
+  for (int w = 0; w < 2; w++)
+  {
+    if (ctx->ring_pc) CK (ctx, cudaMemcpy (p, ctx->d_rptr[w], C * 4 * sizeof (uint32_t), cudaMemcpyDeviceToHost));
+    else std::memset (p, 0, C * 4 * sizeof (uint32_t));
+    p += C * 4 * sizeof (uint32_t);
+  }
   return SLB_OK;
 }
 
@@ -756,7 +844,13 @@ int slb_state_load (slb_ctx *ctx, const void *buf, size_t bytes)
   CK (ctx, cudaMemcpy (ctx->d_acc, p, C * hop * 4, cudaMemcpyHostToDevice)); p += C * hop * 4;
   CK (ctx, cudaMemcpy (ctx->d_proc[0], p, C * hop * 4, cudaMemcpyHostToDevice)); p += C * hop * 4;
   if (ctx->chan) { CK (ctx, cudaDeviceSynchronize ()); if (chan64_state_load (ctx->chan, p)) return fail (ctx, SLB_ERR_CUDA, "chan64 state load failed"); p += chan64_state_bytes (ctx->chan); }
-  if (ctx->q15) { CK (ctx, cudaDeviceSynchronize ()); if (rxq15_state_load (ctx->q15, p)) return fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state load failed"); }
+  if (ctx->q15) { CK (ctx, cudaDeviceSynchronize ()); if (rxq15_state_load (ctx->q15, p)) return fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state load failed"); p += rxq15_state_bytes (ctx->q15); }
+  ctx->ring_pc = false;
+  if (h.ring_pc)
+  {
+    int rc = ring_pc_enable (ctx); if (rc) return rc;
+    for (int w = 0; w < 2; w++) { CK (ctx, cudaMemcpy (ctx->d_rptr[w], p, C * 4 * sizeof (uint32_t), cudaMemcpyHostToDevice)); p += C * 4 * sizeof (uint32_t); }
+  }
   // per-channel tile counters restart from zero on this context
   CK (ctx, cudaMemset (ctx->d_flag, 0, C * sizeof (unsigned)));
   ctx->flag_base = 0; ctx->acc_fill = h.acc_fill; ctx->tx_mode = h.tx_mode != 0;

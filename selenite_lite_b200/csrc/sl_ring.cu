@@ -33,6 +33,98 @@ __global__ void ring_read_kernel (int16_t *__restrict__ blocks, const int16_t *_
   reinterpret_cast<uint32_t *> (blocks)[(size_t) c * frames + k] = i | (q << 16);
 }
 
+// ---- per-channel cadence -------------------------------------------------------------------------
+// Every channel carries its own {enable, rd, wr}; a call serves the channels whose producer / consumer fired this tick
+// (active[c] != 0, or all). One thread per channel runs the firmware's pointer arithmetic — the same statements as
+// sl::RingPtrs (Core/Src/dsp_if.c:116-180, :204-219, :250-301, :310-340) — and leaves the first slot in ptr[c][3]
+// (kRingSkip for a skipped channel); the move kernels then read it per channel.
+constexpr uint32_t kRingSkip = 0xFFFFFFFFu;
+
+__global__ void ring_plan_kernel (uint32_t *__restrict__ ptr /* [C][4] */, const uint8_t *__restrict__ active, uint32_t channels, uint32_t N,
+                                  int is_write, int is_out, uint32_t frames)
+{
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= channels) return;
+  uint32_t *p = ptr + 4 * (size_t) c;
+  if (active && !active[c]) { p[3] = kRingSkip; return; }
+  uint32_t enable = p[0], rd = p[1], wr = p[2], first;
+  if (is_write)
+  {
+    uint32_t gap = 0;
+    if (is_out)
+    {
+      if (!enable) { wr = rd + N / 2; if (wr >= N) wr -= N; enable = 1; }       // dsp_if.c:124-134
+      gap = wr; if (rd > wr) gap += N; gap -= rd;                                // dsp_if.c:136-143
+    }
+    else if (enable) { gap = wr; if (rd > wr) gap += N; gap -= rd; }             // dsp_if.c:254-264
+    gap &= 0xFFFFu;
+    if (gap > 3u * N / 4u) { if (wr < 1u) wr += N; wr--; }                       // dsp_if.c:145-153 / :266-274
+    if (gap < N / 4u) { wr++; if (wr >= N) wr -= N; }                            // dsp_if.c:155-163 / :276-284
+    first = wr;
+    wr = (wr + frames + 1u) % N;                                                 // dsp_if.c:165-179 / :286-300
+    if (wr < 1u) wr += N;
+    wr--;
+  }
+  else
+  {
+    if (!is_out && !enable) { rd = wr + N / 2; if (rd >= N) rd = 0; enable = 1; }   // dsp_if.c:316-326
+    first = rd;
+    rd = (rd + frames) % N;                                                      // dsp_if.c:206-217 / :328-339
+  }
+  p[0] = enable; p[1] = rd; p[2] = wr; p[3] = first;
+}
+
+__global__ void ring_write_pc_kernel (const int16_t *__restrict__ blocks, uint32_t block_stride_frames, int16_t *__restrict__ ring_i,
+                                      int16_t *__restrict__ ring_q, uint32_t ring_frames, const uint32_t *__restrict__ ptr, uint32_t frames)
+{
+  const uint32_t c = blockIdx.y;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t wr0 = ptr[4 * (size_t) c + 3];
+  if (k > frames || wr0 == kRingSkip) return;
+  const uint32_t src = (k < frames) ? k : frames - 1u;
+  const uint32_t iq = reinterpret_cast<const uint32_t *> (blocks)[(size_t) c * block_stride_frames + src];
+  const uint32_t slot = (wr0 + k) % ring_frames;
+  ring_i[(size_t) c * ring_frames + slot] = (int16_t) (iq & 0xFFFFu);
+  ring_q[(size_t) c * ring_frames + slot] = (int16_t) (iq >> 16);
+}
+
+__global__ void ring_read_pc_kernel (int16_t *__restrict__ blocks, const int16_t *__restrict__ ring_i, const int16_t *__restrict__ ring_q,
+                                     uint32_t ring_frames, const uint32_t *__restrict__ ptr, uint32_t frames)
+{
+  const uint32_t c = blockIdx.y;
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t rd0 = ptr[4 * (size_t) c + 3];
+  if (k >= frames) return;
+  uint32_t v = 0u;                                                               // a skipped channel's block reads as zeros
+  if (rd0 != kRingSkip)
+  {
+    const uint32_t slot = (rd0 + k) % ring_frames;
+    v = (uint32_t) (uint16_t) ring_i[(size_t) c * ring_frames + slot] | ((uint32_t) (uint16_t) ring_q[(size_t) c * ring_frames + slot] << 16);
+  }
+  reinterpret_cast<uint32_t *> (blocks)[(size_t) c * frames + k] = v;
+}
+
+int launch_ring_plan (uint32_t *d_ptr, const uint8_t *d_active, uint32_t channels, uint32_t ring_frames, bool is_write, bool is_out,
+                      uint32_t frames, void *stream)
+{
+  ring_plan_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t) stream>>> (d_ptr, d_active, channels, ring_frames, is_write, is_out, frames);
+  return (int) cudaGetLastError ();
+}
+int launch_ring_write_pc (const int16_t *d_blocks, uint32_t stride, int16_t *ri, int16_t *rq, uint32_t channels, uint32_t ring_frames,
+                          const uint32_t *d_ptr, uint32_t frames, void *stream)
+{
+  dim3 grid ((frames + 1 + 127) / 128, channels);
+  ring_write_pc_kernel<<<grid, 128, 0, (cudaStream_t) stream>>> (d_blocks, stride, ri, rq, ring_frames, d_ptr, frames);
+  return (int) cudaGetLastError ();
+}
+int launch_ring_read_pc (int16_t *d_blocks, const int16_t *ri, const int16_t *rq, uint32_t channels, uint32_t ring_frames,
+                         const uint32_t *d_ptr, uint32_t frames, void *stream)
+{
+  dim3 grid ((frames + 127) / 128, channels);
+  ring_read_pc_kernel<<<grid, 128, 0, (cudaStream_t) stream>>> (d_blocks, ri, rq, ring_frames, d_ptr, frames);
+  return (int) cudaGetLastError ();
+}
+
 // PASS chain, bulk path: the firmware's steady-state behaviour is the identity on int16 frames.
 __global__ void copy_iq_kernel (const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n16, const uint32_t *__restrict__ in_tail,
                                 uint32_t *__restrict__ out_tail, size_t ntail)

@@ -145,6 +145,37 @@ class DspIf:
 
     def DSP_Out_Buff_Mute(self): self._ck(self.lib.SLB_DSP_Out_Buff_Mute(self.h), "DSP_Out_Buff_Mute")
 
+    # ---- per-channel cadence (SLB_DSP_*_Ch): `active` uint8[channels], 0 = this channel's producer / consumer did not fire
+    @staticmethod
+    def _mask(active):
+        if active is None:
+            return None, None
+        a = np.ascontiguousarray(active, np.uint8)
+        return a, a.ctypes.data
+
+    def DSP_In_Buff_Write_Ch(self, pbuf, active=None):
+        a = np.ascontiguousarray(pbuf).view(np.int16).reshape(self.channels, -1); keep, m = self._mask(active)
+        self._ck(self.lib.SLB_DSP_In_Buff_Write_Ch(self.h, a.ctypes.data, a.shape[1], m), "DSP_In_Buff_Write_Ch")
+
+    def DSP_In_Buff_Read_Ch(self, size, active=None):
+        out = np.zeros((self.channels, size // 2), np.int16); keep, m = self._mask(active)
+        self._ck(self.lib.SLB_DSP_In_Buff_Read_Ch(self.h, out.ctypes.data, size, m), "DSP_In_Buff_Read_Ch")
+        return out
+
+    def DSP_Out_Buff_Write_Ch(self, pbuf, active=None):
+        a = np.ascontiguousarray(pbuf).view(np.int16).reshape(self.channels, -1); keep, m = self._mask(active)
+        self._ck(self.lib.SLB_DSP_Out_Buff_Write_Ch(self.h, a.ctypes.data, a.shape[1] * 2, m), "DSP_Out_Buff_Write_Ch")
+
+    def DSP_Out_Buff_Read_Ch(self, size, active=None):
+        out = np.zeros((self.channels, size), np.int16); keep, m = self._mask(active)
+        self._ck(self.lib.SLB_DSP_Out_Buff_Read_Ch(self.h, out.ctypes.data, size, m), "DSP_Out_Buff_Read_Ch")
+        return out
+
+    def ring_ptrs_channel(self, channel, which=0):
+        o = (C.c_uint32 * 3)()
+        self._ck(self.lib.slb_ring_get_ptrs_channel(self.h, which, channel, C.byref(o)), "ring_get_ptrs_channel")
+        return tuple(o)
+
     def ring_ptrs(self, which=0):
         o = (C.c_uint32 * 3)()
         self._ck(self.lib.slb_ring_get_ptrs(self.h, which, C.byref(o)), "ring_get_ptrs")

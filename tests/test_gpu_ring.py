@@ -85,3 +85,62 @@ def test_chain_behind_the_1ms_cadence(best_oracle):
             e = rings[c][1](192)
             worst = max(worst, int(np.max(np.abs(got[c].astype(np.int32) - e.astype(np.int32)))))
     assert worst <= 1
+
+
+def _oracle_rings(n, fs=48000):
+    try:
+        return [oracle_lib.RefRing(fs) for _ in range(n)]
+    except FileNotFoundError:
+        return [oracle_lib.PortRing(fs) for _ in range(n)]
+
+
+def test_per_channel_drift_compensation():
+    """producers and consumers of different channels tick at different rates. Every channel carries its
+    own pointers on the device and must follow its own instance of the firmware ring (one unmodified dsp_if.c image per
+    channel) through both slip branches: frames delivered, pointers and ring contents, bit for bit."""
+    C, ticks, hw = 6, 700, 96
+    d = slb.DspIf(C, chain=slb.CHAIN_PASS)
+    rings = _oracle_rings(C)
+    rng = np.random.Generator(np.random.PCG64(11))
+    # channel 0: nominal; 1: producer drops every 37th tick; 2: consumer drops every 41st; 3: producer drops often;
+    # 4: consumer drops often; 5: both irregular
+    def fires(c, t):
+        w = not ((c == 1 and t % 37 == 36) or (c == 3 and t % 9 == 8) or (c == 5 and rng.random() < 0.04))
+        r = not ((c == 2 and t % 41 == 40) or (c == 4 and t % 11 == 10) or (c == 5 and rng.random() < 0.04))
+        return w, r
+    def ptrs_of(r, which):
+        return tuple(r.ptrs(which)) if isinstance(r, oracle_lib.RefRing) else tuple(r.ptrs())
+    slips = np.zeros(C, np.int64)
+    for t in range(ticks):
+        blk = rng.integers(-30000, 30000, (C, hw)).astype(np.int16)
+        act = np.array([fires(c, t) for c in range(C)])
+        d.DSP_In_Buff_Write_Ch(blk, act[:, 0].astype(np.uint8))
+        got = d.DSP_In_Buff_Read_Ch(2 * hw, act[:, 1].astype(np.uint8))
+        for c in range(C):
+            wr_before = ptrs_of(rings[c], 0)[2]
+            if act[c, 0]:
+                rings[c].in_write(blk[c])
+                slips[c] += int((ptrs_of(rings[c], 0)[2] - wr_before) % 384 != 48)
+            exp = rings[c].in_read(2 * hw) if act[c, 1] else np.zeros(hw, np.int16)
+            assert np.array_equal(got[c], exp), (t, c)
+            assert d.ring_ptrs_channel(c, 0) == ptrs_of(rings[c], 0), (t, c)
+    assert slips[0] <= 3 and slips[3] > 5 and slips[4] > 5            # the nominal channel only slips while arming; drifting ones keep slipping
+    # TX ring with per-channel consumers
+    e = slb.DspIf(C, chain=slb.CHAIN_PASS)
+    rings = _oracle_rings(C)
+    for t in range(200):
+        blk = rng.integers(-30000, 30000, (C, hw)).astype(np.int16)
+        act = np.array([(t % (7 + c)) != 0 for c in range(C)])
+        e.DSP_Out_Buff_Write_Ch(blk)
+        got = e.DSP_Out_Buff_Read_Ch(hw, act.astype(np.uint8))
+        for c in range(C):
+            rings[c].out_write(blk[c])
+            exp = rings[c].out_read(hw) if act[c] else np.zeros(hw, np.int16)
+            assert np.array_equal(got[c], exp), (t, c)
+    # checkpoint carries the per-channel pointers
+    snap = e.state_save()
+    f = slb.DspIf(C, chain=slb.CHAIN_PASS); f.state_load(snap)
+    blk = rng.integers(-30000, 30000, (C, hw)).astype(np.int16)
+    e.DSP_Out_Buff_Write_Ch(blk); f.DSP_Out_Buff_Write_Ch(blk)
+    assert np.array_equal(e.DSP_Out_Buff_Read_Ch(hw), f.DSP_Out_Buff_Read_Ch(hw))
+    assert all(e.ring_ptrs_channel(c, 1) == f.ring_ptrs_channel(c, 1) for c in range(C))
