@@ -206,8 +206,8 @@ def run_ours(args):
     kern_ms = sum(step_ms) / len(step_ms)
     achieved = C * T * BYTES_PER_SAMPLE / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "rx_ssb_f32_kernel", "algorithmic_bytes_per_launch": C * T * BYTES_PER_SAMPLE,
-                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f" % (achieved / 8000.0)}
+                "peak_source": peak_src, "kernel": "ssb_f32_kernel<false> (sl_rx_ssb_f32.cu)", "algorithmic_bytes_per_launch": C * T * BYTES_PER_SAMPLE,
+                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f; the chain is bound by instruction issue, not HBM (DESIGN.md §4.2)" % (achieved / 8000.0)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
     if os.path.exists(traffic_file):
         try:
@@ -236,6 +236,41 @@ def run_ours(args):
                "steps": n_e2e, "path": "slb_rx_process_host: pinned host -> H2D -> rx_ssb_f32_kernel -> D2H, 48 MB channel groups on 3 streams"}
         del xh, yh, d2
 
+    # the other chains of the library at the same width, device-resident, for context (not the headline metric)
+    other = None
+    if rank == 0 and world == 1 and not args.no_other:
+        other = {}
+        del x, y
+        torch.cuda.empty_cache()
+        g = torch.Generator(device=dev); g.manual_seed(1)
+
+        def timed(fn, n=5):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        xi = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g); yo = torch.empty_like(xi)
+        for name, chain, call in (("rx_ssb_q15", slb.CHAIN_RX_SSB_Q15, "rx_process"), ("tx_ssb_f32", slb.CHAIN_TX_SSB_F32, "tx_process")):
+            dd = slb.DspIf(C, fs=FS, chain=chain, device=local)
+            ms = timed(lambda: getattr(dd, call)(xi, yo))
+            other[name] = {"Msamples_per_s": C * T / (ms * 1e-3) / 1e6, "hbm_frac": C * T * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / peak,
+                           "note": "bit-exact integer chain, FIR on the integer tensor cores" if name == "rx_ssb_q15" else "config 3"}
+            del dd
+        del xi, yo
+        S, Tw = 64, 192000 * args.seconds // 768 * 768
+        xw = torch.randint(-3000, 3000, (S, Tw, 2), dtype=torch.int16, device=dev, generator=g)
+        yw = torch.empty((S, 64, Tw // 64, 2), dtype=torch.int16, device=dev)
+        dd = slb.DspIf(S, fs=192000, chain=slb.CHAIN_CHAN64_F32, device=local)
+        ms = timed(lambda: dd.chan_process(xw, yw))
+        other["chan64_f32"] = {"Msamples_per_s": S * Tw / (ms * 1e-3) / 1e6, "hbm_frac": S * Tw * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / peak,
+                               "note": "config 4: 64 x 192 kHz wideband streams -> 4096 narrowband channels"}
+        del dd, xw, yw
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_baseline = cpu_reference_run(os.cpu_count() or 1, budget_s=12.0)[0]
@@ -249,7 +284,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "channels_per_gpu": C, "frames_per_step": T, "fs": FS, "chain": "rx_ssb_f32",
                    "l2_policy": "inputs larger than L2 (3.9 GB touched per step per GPU vs 126 MB L2)", "parallelism": "channels sharded, no collective"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}))
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "other_chains": other}))
 
 
 def main():
@@ -260,6 +295,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the context measurements of the other chains")
     ap.add_argument("--seconds", type=int, default=SECONDS, help="signal seconds per channel per step (profiling runs only; the headline uses the default)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -244,6 +244,29 @@ int slb_st_rms_q15 (slb_ctx *ctx, const int16_t *src, uint32_t n, uint32_t block
 /* batched arm_cfft_f32 (bit-reversed output order is not offered): data [channels][count][2*N] floats, in place */
 int slb_st_cfft_f32 (slb_ctx *ctx, float *data, uint32_t N, uint32_t count, int ifft, void *stream);
 
+/* ---- host stream feeder: the stand-in for HAL DMA + UAC1 that replays the firmware's cadence ----
+ * One tick = 1 ms = fs/1000 frames per channel, in this order (the I2S completion callback, dsp_if.c:50-67, then the two
+ * USB class commands, usbd_audio_if.c:179-202):
+ *     DSP_Out_Buff_Read (dac block t); DSP_In_Buff_Write (adc block t); DSP_Out_Buff_Write (usb_out packet t);
+ *     DSP_In_Buff_Read (usb_in packet t)
+ * slb_feeder_run() is equivalent to `ticks` rounds of those four batched calls, but moves whole streams: one H2D copy,
+ * the context's chain over all ticks in one launch, the ring traffic of all ticks replayed by one kernel per ring (the
+ * pointer evolution, including the start-up slips, is planned on the host with the firmware's own arithmetic), one
+ * D2H copy. Buffers are HOST memory [channels][ticks * fs/1000][2]; a NULL pair skips that direction. With the
+ * RX-SSB-f32 chain `ticks` must be a multiple of 8 (the 384-frame super-block). Not available while per-channel
+ * cadence (SLB_DSP_*_Ch) is on. */
+typedef struct
+{
+  const int16_t *adc;       /* RX in : what the codec ADC delivers on the I2S bus */
+  int16_t *usb_in;          /* RX out: what AUDIO_CMD_RECORD hands to the USB IN endpoint */
+  const int16_t *usb_out;   /* TX in : what AUDIO_CMD_PLAY receives from the USB OUT endpoint */
+  int16_t *dac;             /* TX out: what the I2S TX half carries to the codec DAC */
+} slb_feeder_io;
+int slb_feeder_run (slb_ctx *ctx, const slb_feeder_io *io, uint32_t ticks);
+/* USBD_AUDIO_ItfTypeDef.AudioCmd, batched (usbd_audio_if.c:179-202): cmd = 1 START (no-op), 2 PLAY -> DSP_Out_Buff_Write,
+ * 3 STOP -> DSP_Out_Buff_Mute, 4 RECORD -> DSP_In_Buff_Read; pbuf is [channels][size] host memory, size in bytes */
+int SLB_AUDIO_AudioCmd (slb_ctx *ctx, uint8_t *pbuf, uint32_t size, uint8_t cmd);
+
 /* ---- host-only logic, callable without a GPU (unit tests of the index arithmetic and the scan tables) ----
  * One firmware ring's pointer logic, Core/Src/dsp_if.c:116-180, :204-219, :250-301, :310-340. state = {enable, rd, wr}
  * is updated in place; the return value is the ring slot of the first frame moved (a write stores frames+1 slots:
@@ -260,7 +283,7 @@ int slb_sync (slb_ctx *ctx);
 
 /* ---- single-channel drop-in with the firmware's own names and signatures (Core/Inc/dsp_if.h:42-51).
  * They drive one process-global 1-channel context on device 0 (env SELENITE_B200_DEVICE, SELENITE_B200_FS,
- * SELENITE_B200_CHAIN=pass|rx_ssb_f32; default pass at 48000 = the firmware's behaviour). Like the firmware
+ * SELENITE_B200_CHAIN=pass|rx_ssb_f32|tx_ssb_f32|rx_ssb_q15; default pass at 48000 = the firmware's behaviour). Like the firmware
  * they return void; failures are reported through slb_dropin_status(). ---- */
 void DSP_Init (void);
 void DSP_Set_RX (void);
@@ -271,6 +294,13 @@ void DSP_In_Buff_Read (uint8_t *pbuf, uint32_t size);
 void DSP_Out_Buff_Write (uint8_t *pbuf, uint32_t size);
 void DSP_Out_Buff_Read (uint16_t *pbuf, uint16_t size);
 void DSP_Out_Buff_Mute (void);
+/* the rest of the firmware's sample-path surface, single channel: the I2S DMA double buffer and its two completion
+ * callbacks (dsp_if.c:32, :50-67; hi2s is ignored) and the USB class dispatcher (usbd_audio_if.c:179-202) */
+typedef struct { uint16_t rx[768]; uint16_t tx[768]; } SLB_I2S_Buff_TypeDef;   /* I2S_BUFF_SIZE = 4 fs/1000 entries are used */
+extern SLB_I2S_Buff_TypeDef i2s_buff;
+void HAL_I2SEx_TxRxHalfCpltCallback (void *hi2s);
+void HAL_I2SEx_TxRxCpltCallback (void *hi2s);
+int8_t AUDIO_AudioCmd_FS (uint8_t *pbuf, uint32_t size, uint8_t cmd);
 int  slb_dropin_status (void);
 slb_ctx *slb_dropin_ctx (void);
 

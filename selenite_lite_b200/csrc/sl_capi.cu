@@ -560,6 +560,88 @@ int slb_ring_get_ptrs_channel (slb_ctx *ctx, int which, uint32_t channel, uint32
   return SLB_OK;
 }
 
+int SLB_AUDIO_AudioCmd (slb_ctx *ctx, uint8_t *pbuf, uint32_t size, uint8_t cmd)     // usbd_audio_if.c:179-202
+{
+  if (!ctx) return SLB_ERR_ARG;
+  switch (cmd)
+  {
+    case 1: return SLB_OK;                                                             // AUDIO_CMD_START
+    case 2: return SLB_DSP_Out_Buff_Write (ctx, pbuf, size);                           // AUDIO_CMD_PLAY
+    case 3: return SLB_DSP_Out_Buff_Mute (ctx);                                        // AUDIO_CMD_STOP
+    case 4: return SLB_DSP_In_Buff_Read (ctx, pbuf, size);                             // AUDIO_CMD_RECORD
+    default: return SLB_OK;                                                            // the firmware ignores unknown opcodes
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Host stream feeder
+// ------------------------------------------------------------------------------------------------------------------
+int slb_feeder_run (slb_ctx *ctx, const slb_feeder_io *io, uint32_t ticks)
+{
+  if (!ctx || !io || ticks == 0) return SLB_ERR_ARG;
+  if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
+  if (ctx->ring_pc) return fail (ctx, SLB_ERR_STATE, "the feeder replays one shared cadence; per-channel cadence is on");
+  if ((io->adc == nullptr) != (io->usb_in == nullptr) || (io->usb_out == nullptr) != (io->dac == nullptr)) return fail (ctx, SLB_ERR_ARG, "give both buffers of a direction or neither");
+  const bool f32 = ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32;
+  const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames, B = ctx->geo.block_frames, hop = ctx->rx.hop, per_hop = hop / B;
+  if (io->adc && f32 && (ticks % per_hop != 0 || ctx->acc_fill != 0)) return fail (ctx, SLB_ERR_ARG, "with the RX-SSB-f32 chain the feeder moves whole 384-frame super-blocks (ticks % 8 == 0)");
+  if (io->adc && ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32) return fail (ctx, SLB_ERR_STATE, "a TX-SSB-f32 context has no RX chain behind the ring");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const size_t frames = (size_t) ticks * B, bytes = (size_t) C * frames * 4;
+  // scratch: raw stream, processed stream, ring output, plan
+  char *scr = static_cast<char *> (ctx_scratch (ctx, 3 * bytes + (size_t) ticks * 8 + 256));
+  if (!scr) return SLB_ERR_CUDA;
+  int16_t *d_raw = reinterpret_cast<int16_t *> (scr), *d_prc = reinterpret_cast<int16_t *> (scr + bytes), *d_out = reinterpret_cast<int16_t *> (scr + 2 * bytes);
+  uint32_t *d_plan = reinterpret_cast<uint32_t *> (scr + 3 * bytes);
+  std::vector<uint32_t> plan ((size_t) ticks * 2);
+  cudaStream_t st = ctx->stream;
+
+  if (io->usb_out)                                                                     // ---- TX ring: read, then write, per tick
+  {
+    for (uint32_t t = 0; t < ticks; t++) { plan[2 * t + 1] = ctx->ring_out.plan_read (true, B); plan[2 * t] = ctx->ring_out.plan_write (true, B); }
+    CK (ctx, cudaMemcpyAsync (d_plan, plan.data (), plan.size () * 4, cudaMemcpyHostToDevice, st));
+    CK (ctx, cudaMemcpyAsync (d_raw, io->usb_out, bytes, cudaMemcpyHostToDevice, st));
+    CK (ctx, launch_ring_replay (false, nullptr, 0, 0, d_raw, (uint32_t) frames, d_out, ctx->d_ring[1][0], ctx->d_ring[1][1], C, R, d_plan, ticks, B, st));
+    ctx->launches++;
+    CK (ctx, cudaMemcpyAsync (io->dac, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    CK (ctx, cudaStreamSynchronize (st));
+  }
+  if (io->adc)                                                                         // ---- RX ring: write, then read, per tick
+  {
+    for (uint32_t t = 0; t < ticks; t++) { plan[2 * t] = ctx->ring_in.plan_write (false, B); plan[2 * t + 1] = ctx->ring_in.plan_read (false, B); }
+    CK (ctx, cudaMemcpyAsync (d_plan, plan.data (), plan.size () * 4, cudaMemcpyHostToDevice, st));
+    CK (ctx, cudaMemcpyAsync (d_raw, io->adc, bytes, cudaMemcpyHostToDevice, st));
+    const int16_t *src_a = nullptr, *src_b = d_raw; uint32_t stride_a = 0, ticks_a = 0;
+    if (ctx->q15)
+    {
+      int rc = rxq15_launch (ctx, ctx->q15, d_raw, d_prc, 0, C, (uint32_t) frames, ctx->sm_count, st, false);
+      if (rc) return rc;
+      rxq15_advance (ctx->q15);
+      src_b = d_prc;
+    }
+    else if (f32)
+    {
+      // the ring is fed from the PREVIOUS processed super-block (the chain's 384 frames of latency, as behind the per-call
+      // API): the first 8 ticks come from the carried super-block, the last super-block of this run becomes the carry
+      int rc = run_rx_kernel (ctx, d_raw, d_prc, 0, C, (uint32_t) frames, nullptr, nullptr, st);
+      if (rc) return rc;
+      rx_advance (ctx, (uint32_t) frames);
+      src_a = ctx->d_proc[ctx->proc_cur]; stride_a = hop; ticks_a = per_hop; src_b = d_prc;
+    }
+    CK (ctx, launch_ring_replay (true, src_a, stride_a, ticks_a, src_b, (uint32_t) frames, d_out, ctx->d_ring[0][0], ctx->d_ring[0][1], C, R, d_plan, ticks, B, st));
+    ctx->launches++;
+    if (f32)
+    {
+      CK (ctx, cudaMemcpy2DAsync (ctx->d_proc[ctx->proc_cur ^ 1], (size_t) hop * 4, reinterpret_cast<const char *> (d_prc) + (frames - hop) * 4, frames * 4,
+                                  (size_t) hop * 4, C, cudaMemcpyDeviceToDevice, st));
+      ctx->proc_cur ^= 1;
+    }
+    CK (ctx, cudaMemcpyAsync (io->usb_in, d_out, bytes, cudaMemcpyDeviceToHost, st));
+    CK (ctx, cudaStreamSynchronize (st));
+  }
+  return SLB_OK;
+}
+
 int SLB_DSP_Out_Buff_Mute (slb_ctx *ctx)                                           // dsp_if.c:188-195: zero the samples, keep the pointers
 {
   if (!ctx) return SLB_ERR_ARG;
@@ -876,7 +958,8 @@ slb_ctx *dropin ()
     const char *fs = std::getenv ("SELENITE_B200_FS"), *dev = std::getenv ("SELENITE_B200_DEVICE"), *ch = std::getenv ("SELENITE_B200_CHAIN");
     cfg.fs = fs ? (uint32_t) std::atoi (fs) : 48000u;
     cfg.device = dev ? std::atoi (dev) : 0;
-    cfg.chain = (ch && std::strcmp (ch, "rx_ssb_f32") == 0) ? SLB_CHAIN_RX_SSB_F32 : (ch && std::strcmp (ch, "tx_ssb_f32") == 0) ? SLB_CHAIN_TX_SSB_F32 : SLB_CHAIN_PASS;   // (the channelizer has no single-channel drop-in)
+    cfg.chain = (ch && std::strcmp (ch, "rx_ssb_f32") == 0) ? SLB_CHAIN_RX_SSB_F32 : (ch && std::strcmp (ch, "tx_ssb_f32") == 0) ? SLB_CHAIN_TX_SSB_F32
+              : (ch && std::strcmp (ch, "rx_ssb_q15") == 0) ? SLB_CHAIN_RX_SSB_Q15 : SLB_CHAIN_PASS;   // (the channelizer has no single-channel drop-in)
     g_dropin_status = slb_create (&cfg, &g_dropin);
     if (g_dropin_status != SLB_OK) std::fprintf (stderr, "selenite-b200: drop-in context failed: %s\n", slb_last_error (nullptr));
   }
@@ -896,5 +979,23 @@ void DSP_In_Buff_Read (uint8_t *pbuf, uint32_t size) { DROPIN (SLB_DSP_In_Buff_R
 void DSP_Out_Buff_Write (uint8_t *pbuf, uint32_t size) { DROPIN (SLB_DSP_Out_Buff_Write (c_, pbuf, size)); }
 void DSP_Out_Buff_Read (uint16_t *pbuf, uint16_t size) { DROPIN (SLB_DSP_Out_Buff_Read (c_, pbuf, size)); }
 void DSP_Out_Buff_Mute (void) { DROPIN (SLB_DSP_Out_Buff_Mute (c_)); }
+
+// the I2S DMA double buffer and its completion callbacks (dsp_if.c:32, :50-67) and the USB class dispatcher
+SLB_I2S_Buff_TypeDef i2s_buff;
+void HAL_I2SEx_TxRxHalfCpltCallback (void *)
+{
+  slb_ctx *c = dropin (); if (!c) return;
+  const uint16_t half = (uint16_t) c->geo.i2s_half_hw;
+  DSP_Out_Buff_Read (i2s_buff.tx, half);
+  DSP_In_Buff_Write (i2s_buff.rx, half);
+}
+void HAL_I2SEx_TxRxCpltCallback (void *)
+{
+  slb_ctx *c = dropin (); if (!c) return;
+  const uint16_t half = (uint16_t) c->geo.i2s_half_hw;
+  DSP_Out_Buff_Read (&i2s_buff.tx[half], half);
+  DSP_In_Buff_Write (&i2s_buff.rx[half], half);
+}
+int8_t AUDIO_AudioCmd_FS (uint8_t *pbuf, uint32_t size, uint8_t cmd) { DROPIN (SLB_AUDIO_AudioCmd (c_, pbuf, size, cmd)); return 0; /* USBD_OK, unconditionally (usbd_audio_if.c:200) */ }
 
 }  // extern "C"

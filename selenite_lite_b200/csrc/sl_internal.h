@@ -63,6 +63,10 @@ int launch_ring_write (const int16_t *d_blocks, uint32_t block_stride_frames, in
 int launch_ring_read (int16_t *d_blocks, const int16_t *d_ring_i, const int16_t *d_ring_q, uint32_t channels,
                       uint32_t ring_frames, uint32_t rd0, uint32_t frames, void *stream);
 int launch_copy_iq (const int16_t *d_in, int16_t *d_out, size_t n_frames_total, void *stream);
+// stream feeder: `ticks` firmware ticks of one ring in one launch; d_plan = [ticks][2] {first slot written, first slot read}
+int launch_ring_replay (bool write_first, const int16_t *src_a, uint32_t stride_a_frames, uint32_t ticks_a, const int16_t *src_b,
+                        uint32_t stride_b_frames, int16_t *dst, int16_t *d_ring_i, int16_t *d_ring_q, uint32_t channels, uint32_t ring_frames,
+                        const uint32_t *d_plan, uint32_t ticks, uint32_t block_frames, void *stream);
 // per-channel cadence: d_ptr = [C][4] {enable, rd, wr, first slot of this call | 0xFFFFFFFF when skipped}
 int launch_ring_plan (uint32_t *d_ptr, const uint8_t *d_active, uint32_t channels, uint32_t ring_frames, bool is_write, bool is_out,
                       uint32_t frames, void *stream);

@@ -125,6 +125,65 @@ int launch_ring_read_pc (int16_t *d_blocks, const int16_t *ri, const int16_t *rq
   return (int) cudaGetLastError ();
 }
 
+// ---- stream feeder: many 1 ms ticks of one ring in ONE launch --------------------------------------
+// The pointer evolution of a ring depends on the call sequence only, never on the samples, so the host plans every tick
+// (plan[2 t] = first slot written, plan[2 t + 1] = first slot read, both from sl::RingPtrs) and this kernel replays the
+// sample movement: one CTA per channel keeps the ring (DSP_BUFF_SIZE frames, one u32 per frame) in shared memory and
+// walks the ticks in order. kWriteFirst = true : RX ring, a tick is DSP_In_Buff_Write then DSP_In_Buff_Read
+//                          kWriteFirst = false: TX ring, a tick is DSP_Out_Buff_Read (the I2S callback's first statement,
+//                                               dsp_if.c:52) then DSP_Out_Buff_Write.
+// The block written at tick t comes from `src_a` while t < ticks_a (the chain's carried super-block) and from `src_b`
+// afterwards (PASS: ticks_a = 0).
+template <bool kWriteFirst>
+__global__ void ring_replay_kernel (const uint32_t *__restrict__ src_a, uint32_t stride_a, uint32_t ticks_a, const uint32_t *__restrict__ src_b,
+                                    uint32_t stride_b, uint32_t *__restrict__ dst, int16_t *__restrict__ ring_i, int16_t *__restrict__ ring_q,
+                                    uint32_t R, const uint32_t *__restrict__ plan, uint32_t ticks, uint32_t B)
+{
+  extern __shared__ uint32_t sRing[];
+  const uint32_t c = blockIdx.x, k = threadIdx.x;
+  for (uint32_t i = k; i < R; i += blockDim.x)
+    sRing[i] = (uint32_t) (uint16_t) ring_i[(size_t) c * R + i] | ((uint32_t) (uint16_t) ring_q[(size_t) c * R + i] << 16);
+  __syncthreads ();
+  for (uint32_t t = 0; t < ticks; t++)
+  {
+    const uint32_t wr0 = plan[2 * t], rd0 = plan[2 * t + 1];
+    const uint32_t *src = (t < ticks_a) ? src_a + (size_t) c * stride_a + (size_t) t * B : src_b + (size_t) c * stride_b + (size_t) (t - ticks_a) * B;
+    if (kWriteFirst)
+    {
+      for (uint32_t j = k; j <= B; j += blockDim.x) sRing[(wr0 + j) % R] = src[j < B ? j : B - 1u];   // dsp_if.c:286-300
+      __syncthreads ();
+      for (uint32_t j = k; j < B; j += blockDim.x) dst[((size_t) c * ticks + t) * B + j] = sRing[(rd0 + j) % R];   // dsp_if.c:328-339
+      __syncthreads ();
+    }
+    else
+    {
+      for (uint32_t j = k; j < B; j += blockDim.x) dst[((size_t) c * ticks + t) * B + j] = sRing[(rd0 + j) % R];   // dsp_if.c:206-217
+      __syncthreads ();
+      for (uint32_t j = k; j <= B; j += blockDim.x) sRing[(wr0 + j) % R] = src[j < B ? j : B - 1u];   // dsp_if.c:165-179
+      __syncthreads ();
+    }
+  }
+  for (uint32_t i = k; i < R; i += blockDim.x)
+  {
+    ring_i[(size_t) c * R + i] = (int16_t) (sRing[i] & 0xFFFFu);
+    ring_q[(size_t) c * R + i] = (int16_t) (sRing[i] >> 16);
+  }
+}
+
+int launch_ring_replay (bool write_first, const int16_t *src_a, uint32_t stride_a, uint32_t ticks_a, const int16_t *src_b, uint32_t stride_b,
+                        int16_t *dst, int16_t *ri, int16_t *rq, uint32_t channels, uint32_t ring_frames, const uint32_t *d_plan, uint32_t ticks,
+                        uint32_t block_frames, void *stream)
+{
+  const unsigned threads = block_frames + 1 <= 64 ? 64 : (block_frames + 1 <= 128 ? 128 : 256);
+  const size_t smem = (size_t) ring_frames * 4;
+  const uint32_t *a = reinterpret_cast<const uint32_t *> (src_a), *b = reinterpret_cast<const uint32_t *> (src_b);
+  if (write_first)
+    ring_replay_kernel<true><<<channels, threads, smem, (cudaStream_t) stream>>> (a, stride_a, ticks_a, b, stride_b, reinterpret_cast<uint32_t *> (dst), ri, rq, ring_frames, d_plan, ticks, block_frames);
+  else
+    ring_replay_kernel<false><<<channels, threads, smem, (cudaStream_t) stream>>> (a, stride_a, ticks_a, b, stride_b, reinterpret_cast<uint32_t *> (dst), ri, rq, ring_frames, d_plan, ticks, block_frames);
+  return (int) cudaGetLastError ();
+}
+
 // PASS chain, bulk path: the firmware's steady-state behaviour is the identity on int16 frames.
 __global__ void copy_iq_kernel (const uint4 *__restrict__ in, uint4 *__restrict__ out, size_t n16, const uint32_t *__restrict__ in_tail,
                                 uint32_t *__restrict__ out_tail, size_t ntail)

@@ -171,6 +171,26 @@ class DspIf:
         self._ck(self.lib.SLB_DSP_Out_Buff_Read_Ch(self.h, out.ctypes.data, size, m), "DSP_Out_Buff_Read_Ch")
         return out
 
+    def feeder_run(self, adc=None, usb_out=None):
+        """Replay `ticks` firmware milliseconds in one call (slb_feeder_run): adc / usb_out int16 [channels][ticks*block][2]
+        host streams (either may be None). Returns (usb_in, dac) of the same shape (None for a skipped direction)."""
+        io = _lib.FeederIo(); keep = []
+        ticks = None
+        usb_in = dac = None
+        if adc is not None:
+            adc = np.ascontiguousarray(adc, np.int16); usb_in = np.zeros_like(adc); keep += [adc, usb_in]
+            io.adc, io.usb_in = adc.ctypes.data, usb_in.ctypes.data; ticks = adc.shape[1] // self.block_frames
+        if usb_out is not None:
+            usb_out = np.ascontiguousarray(usb_out, np.int16); dac = np.zeros_like(usb_out); keep += [usb_out, dac]
+            io.usb_out, io.dac = usb_out.ctypes.data, dac.ctypes.data; ticks = usb_out.shape[1] // self.block_frames
+        self._ck(self.lib.slb_feeder_run(self.h, C.byref(io), ticks), "feeder_run")
+        return usb_in, dac
+
+    def AUDIO_AudioCmd(self, pbuf, size, cmd):
+        a = np.ascontiguousarray(pbuf)
+        self._ck(self.lib.SLB_AUDIO_AudioCmd(self.h, a.ctypes.data, size, cmd), "AUDIO_AudioCmd")
+        return a
+
     def ring_ptrs_channel(self, channel, which=0):
         o = (C.c_uint32 * 3)()
         self._ck(self.lib.slb_ring_get_ptrs_channel(self.h, which, channel, C.byref(o)), "ring_get_ptrs_channel")

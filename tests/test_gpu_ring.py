@@ -144,3 +144,58 @@ def test_per_channel_drift_compensation():
     e.DSP_Out_Buff_Write_Ch(blk); f.DSP_Out_Buff_Write_Ch(blk)
     assert np.array_equal(e.DSP_Out_Buff_Read_Ch(hw), f.DSP_Out_Buff_Read_Ch(hw))
     assert all(e.ring_ptrs_channel(c, 1) == f.ring_ptrs_channel(c, 1) for c in range(C))
+
+
+@pytest.mark.parametrize("chain,ticks", [(slb.CHAIN_PASS, 61), (slb.CHAIN_RX_SSB_Q15, 50), (slb.CHAIN_RX_SSB_F32, 48)])
+def test_stream_feeder_equals_the_per_tick_calls(chain, ticks, rng):
+    """SURVEY.md §8f.1: slb_feeder_run == `ticks` rounds of {Out_Buff_Read, In_Buff_Write, Out_Buff_Write, In_Buff_Read}
+    (the I2S callback, then AUDIO_CMD_PLAY / AUDIO_CMD_RECORD), including the start-up slips, chain latency and every
+    piece of carried state: two feeder runs back to back, then per-tick calls on both contexts must keep agreeing."""
+    C, B = 7, 48
+    adc = slb.synth_iq(C, 2 * ticks * B + 16 * B)
+    pc = rng.integers(-20000, 20000, (C, 2 * ticks * B + 16 * B, 2)).astype(np.int16)
+    a = slb.DspIf(C, chain=chain); b = slb.DspIf(C, chain=chain)
+    # reference run on `a`: one call per event
+    exp_in, exp_dac = [], []
+    for t in range(2 * ticks):
+        blk = slice(t * B, (t + 1) * B)
+        exp_dac.append(a.DSP_Out_Buff_Read(2 * B))
+        a.DSP_In_Buff_Write(adc[:, blk].reshape(C, -1))
+        a.AUDIO_AudioCmd(pc[:, blk].reshape(C, -1), 4 * B, 2)                                   # AUDIO_CMD_PLAY
+        exp_in.append(a.AUDIO_AudioCmd(np.zeros((C, 2 * B), np.int16), 4 * B, 4))                # AUDIO_CMD_RECORD
+    exp_in = np.stack(exp_in, 1).reshape(C, -1, 2); exp_dac = np.stack(exp_dac, 1).reshape(C, -1, 2)
+    n = ticks * B
+    in1, dac1 = b.feeder_run(adc[:, :n], pc[:, :n])
+    in2, dac2 = b.feeder_run(adc[:, n:2 * n], pc[:, n:2 * n])
+    assert np.array_equal(np.concatenate([dac1, dac2], 1), exp_dac)
+    assert np.array_equal(np.concatenate([in1, in2], 1), exp_in)
+    assert a.ring_ptrs(0) == b.ring_ptrs(0) and a.ring_ptrs(1) == b.ring_ptrs(1)
+    for t in range(2 * ticks, 2 * ticks + 16):                                                   # and the two contexts stay in step
+        blk = slice(t * B, (t + 1) * B)
+        for d in (a, b):
+            d.DSP_In_Buff_Write(adc[:, blk].reshape(C, -1))
+        assert np.array_equal(a.DSP_In_Buff_Read(4 * B), b.DSP_In_Buff_Read(4 * B))
+
+
+def test_firmware_names_i2s_callbacks_and_audiocmd():
+    """The single-channel drop-in surface beyond dsp_if.h: i2s_buff + HAL_I2SEx_TxRx{Half,}CpltCallback (dsp_if.c:32, :50-67)
+    and AUDIO_AudioCmd_FS (usbd_audio_if.c:179-202) drive the same global context as DSP_*."""
+    lib = _lib.load()
+    lib.DSP_Init()
+    buf_t = (C.c_uint16 * 768) * 2
+    i2s = buf_t.in_dll(lib, "i2s_buff")
+    ring, fns = oracle_ring(48000)
+    in_write, in_read, out_write, out_read, ptrs, mute = fns
+    rng = np.random.Generator(np.random.PCG64(3))
+    for t in range(30):
+        half = t & 1
+        rx = rng.integers(-30000, 30000, 96).astype(np.int16); pkt = rng.integers(-30000, 30000, 96).astype(np.int16)
+        C.memmove(C.addressof(i2s[0]) + half * 192, rx.ctypes.data, 192)
+        (lib.HAL_I2SEx_TxRxCpltCallback if half else lib.HAL_I2SEx_TxRxHalfCpltCallback)(None)
+        tx = np.frombuffer(bytes(i2s[1]), np.int16)[half * 96:(half + 1) * 96]
+        exp_tx = out_read(96); in_write(rx)
+        assert np.array_equal(tx, exp_tx), t
+        lib.AUDIO_AudioCmd_FS(pkt.ctypes.data, 192, 2); out_write(pkt)
+        got = np.zeros(96, np.int16); lib.AUDIO_AudioCmd_FS(got.ctypes.data, 192, 4)
+        assert np.array_equal(got, in_read(192)), t
+    assert lib.slb_dropin_status() == 0
