@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include "sl_internal.h"
 
 namespace sl {
@@ -35,7 +36,10 @@ namespace {
 constexpr int kN = 512;                          // FFT length
 constexpr int kHop = 384;                        // new frames per FFT frame
 constexpr int kOvl = kN - kHop;                  // 128 carried frames
-constexpr int kFftWarps = 4;                     // = frames per tile
+#ifndef SL_RX_FFTWARPS
+#define SL_RX_FFTWARPS 4
+#endif
+constexpr int kFftWarps = SL_RX_FFTWARPS;        // = frames per tile
 constexpr int kTile = kHop * kFftWarps;          // 1536 frames
 constexpr int kThreads = 32 * (kFftWarps + 1);   // + the recurrence warp
 constexpr int kBlocksPerTile = kTile / kAgcBlock; // 32 AGC blocks of 48 samples = one per recurrence lane
@@ -187,8 +191,14 @@ __device__ __forceinline__ void mbar_arrive (uint64_t *bar)
 __device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
 {
   asm volatile (
+#ifdef SL_RX_WAIT_HINT
+      // the time hint lets the hardware park the warp until the phase flips instead of spinning through issue slots
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+      ::"r"(smem_u32 (bar)), "r"(parity), "r"(SL_RX_WAIT_HINT) : "memory");
+#else
       "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
       ::"r"(smem_u32 (bar)), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {
@@ -457,7 +467,9 @@ __global__ void __launch_bounds__ (kThreads, SL_RX_CTAS) ssb_f32_kernel
       {
         if (mine)
         {
+#ifndef SL_RX_ABLATE_FFT                                                            // (profiling aid: time the recurrence side alone)
           fft512x2 (xr, xi, sre, sTw, lane);
+#endif
         }
         if (dir == 0)
         {
@@ -805,6 +817,10 @@ int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream_)
   const uint64_t items = (uint64_t) L.channels * P.items_per_channel;
   uint64_t grid = (uint64_t) sm_count * per_sm;      // all CTAs co-resident: the segment hand-over may spin
   if (grid > items) grid = items;
+  // (Measured, profiles/r01_summary.md: throughput is proportional to the number of resident CTAs — 592: 155, 512: 132,
+  // 448: 117 Gsamples/s — i.e. every CTA is an internally latency-bound pipeline; shrinking the grid to make the segment
+  // hand-over trivially satisfied costs more than the polling it removes.)
+  if (const char *g = std::getenv ("SELENITE_B200_RX_GRID")) { const long v = std::atol (g); if (v > 0 && (uint64_t) v <= (uint64_t) sm_count * per_sm) grid = (uint64_t) v; }   // profiling aid
   if (L.tx) ssb_f32_kernel<true><<<(unsigned) grid, kThreads, smem, stream>>> (P);
   else ssb_f32_kernel<false><<<(unsigned) grid, kThreads, smem, stream>>> (P);
   return (int) cudaGetLastError ();
