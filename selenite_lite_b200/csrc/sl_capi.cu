@@ -438,11 +438,11 @@ static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_
   if (!pbuf || frames == 0 || frames + 1 > R) return fail (ctx, SLB_ERR_ARG, "block must hold 1..DSP_BUFF_SIZE-1 frames");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   RingPtrs &rp = which ? ctx->ring_out : ctx->ring_in;
+  // every chain sits where the codec's I2S half enters (dsp_if.c:286-289): RX chains demodulate the I/Q there, the TX
+  // modulator takes the microphone the codec delivers on both ADC channels in TX (codec_if.c:304-306); the TX ring passes
   const bool chain = (which == 0 && is_ssb_chain (ctx->cfg.chain));
   if (per_channel || ctx->ring_pc)
   {
-    if (which == 0 && active && ctx->cfg.chain != SLB_CHAIN_PASS)
-      return fail (ctx, SLB_ERR_UNSUPPORTED, "a per-channel producer mask on the RX ring needs the PASS chain (a chain's filter state has one cadence)");
     if (which == 0 && ctx->cfg.chain != SLB_CHAIN_PASS)
       return fail (ctx, SLB_ERR_UNSUPPORTED, "per-channel cadence with a chain behind the RX ring is not built: use the PASS chain or the bulk calls");
     int rc = ring_pc_enable (ctx); if (rc) return rc;
@@ -582,10 +582,10 @@ int slb_feeder_run (slb_ctx *ctx, const slb_feeder_io *io, uint32_t ticks)
   if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
   if (ctx->ring_pc) return fail (ctx, SLB_ERR_STATE, "the feeder replays one shared cadence; per-channel cadence is on");
   if ((io->adc == nullptr) != (io->usb_in == nullptr) || (io->usb_out == nullptr) != (io->dac == nullptr)) return fail (ctx, SLB_ERR_ARG, "give both buffers of a direction or neither");
-  const bool f32 = ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32;
+  const bool f32 = is_ssb_chain (ctx->cfg.chain);        // RX demodulator or TX modulator: both sit where the I2S half enters
   const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames, B = ctx->geo.block_frames, hop = ctx->rx.hop, per_hop = hop / B;
-  if (io->adc && f32 && (ticks % per_hop != 0 || ctx->acc_fill != 0)) return fail (ctx, SLB_ERR_ARG, "with the RX-SSB-f32 chain the feeder moves whole 384-frame super-blocks (ticks % 8 == 0)");
-  if (io->adc && ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32) return fail (ctx, SLB_ERR_STATE, "a TX-SSB-f32 context has no RX chain behind the ring");
+  if (io->adc && f32 && (ticks % per_hop != 0 || ctx->acc_fill != 0))
+    return fail (ctx, SLB_ERR_ARG, "with an FFT chain the feeder moves whole 384-frame super-blocks (ticks % 8 == 0)");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   const size_t frames = (size_t) ticks * B, bytes = (size_t) C * frames * 4;
   // scratch: raw stream, processed stream, ring output, plan

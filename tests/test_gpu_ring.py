@@ -146,7 +146,7 @@ def test_per_channel_drift_compensation():
     assert all(e.ring_ptrs_channel(c, 1) == f.ring_ptrs_channel(c, 1) for c in range(C))
 
 
-@pytest.mark.parametrize("chain,ticks", [(slb.CHAIN_PASS, 61), (slb.CHAIN_RX_SSB_Q15, 50), (slb.CHAIN_RX_SSB_F32, 48)])
+@pytest.mark.parametrize("chain,ticks", [(slb.CHAIN_PASS, 61), (slb.CHAIN_RX_SSB_Q15, 50), (slb.CHAIN_RX_SSB_F32, 48), (slb.CHAIN_TX_SSB_F32, 40)])
 def test_stream_feeder_equals_the_per_tick_calls(chain, ticks, rng):
     """SURVEY.md §8f.1: slb_feeder_run == `ticks` rounds of {Out_Buff_Read, In_Buff_Write, Out_Buff_Write, In_Buff_Read}
     (the I2S callback, then AUDIO_CMD_PLAY / AUDIO_CMD_RECORD), including the start-up slips, chain latency and every
