@@ -178,7 +178,9 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         d.rx_process(x, y)
     barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler = ClockSampler(local)
+    if not os.environ.get("BENCH_NO_SAMPLER"):
+        sampler.start()
     time.sleep(0.3)
     launches0 = d.kernel_launches()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -193,6 +195,8 @@ def run_ours(args):
     clocks = sampler.stop()
     launches = d.kernel_launches() - launches0
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    if os.environ.get("BENCH_DEBUG"):
+        print("step_ms", [round(v, 3) for v in step_ms], file=sys.stderr)
     total_ms = evs[0].elapsed_time(evs[-1])
     if dist is not None:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)

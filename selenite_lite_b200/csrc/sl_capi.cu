@@ -1,10 +1,12 @@
 // Host library + C ABI (include/selenite_b200.h). Mirrors the reference module Core/Src/dsp_if.c: same entry points,
 // same argument meaning, ring index arithmetic identical; the sample movement and the inserted chain run on the GPU.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -39,6 +41,12 @@ struct slb_ctx
 
   // device: chain constants + carried state
   float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
+  // tensor-core path of the RX-SSB-f32 chain (sl_rx_ssb_tc.cu): tap planes per mask slot, which slots it can serve
+  uint8_t *d_planes = nullptr; bool tc_ok[SLB_MAX_MASKS] = {}; float tc_s0[SLB_MAX_MASKS] = {}; TcBiquadTables tc_tables{};
+  // channel lists of the tensor-core launches, cached per channel range (the bulk paths cut the batch the same way every
+  // call) and rebuilt when a mode or a mask changes (mode_version)
+  struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
+  std::map<uint64_t, TcLists> tc_lists; uint64_t mode_version = 0;
   int16_t *d_ovl[2] = { nullptr, nullptr }; int ovl_parity = 0;
   float *d_state = nullptr; unsigned *d_flag = nullptr;
   unsigned flag_base = 0;
@@ -93,6 +101,7 @@ void *ctx_scratch (slb_ctx *ctx, size_t bytes)
 
 static int upload_chain_constants (slb_ctx *ctx)
 {
+  ctx->mode_version++;
   const uint32_t N = ctx->rx.fft_len;
   std::vector<float> scaled (ctx->masks_host.size ());
   // arm_cfft_f32.c:604-614 scales by 1/L after the inverse transform and arm_q15_to_float.c:87 by 1/32768 before the
@@ -102,8 +111,17 @@ static int upload_chain_constants (slb_ctx *ctx)
     rx_ssb_f32_pack_mask (ctx->masks_host.data () + (size_t) m * 2 * N, inv, scaled.data () + (size_t) m * 2 * N);
   CK (ctx, cudaMemcpyAsync (ctx->d_masks, scaled.data (), scaled.size () * sizeof (float), cudaMemcpyHostToDevice, ctx->stream));
   CK (ctx, cudaMemcpyAsync (ctx->d_slot, ctx->slot_host.data (), ctx->slot_host.size (), cudaMemcpyHostToDevice, ctx->stream));
+  // the same masks as 24-bit FIR taps in tensor-core layout; a mask whose impulse response does not fit 129 taps (a
+  // caller-supplied one may not) and the AM slot (two outputs per sample) stay on the FFT kernel
+  {
+    std::vector<uint8_t> planes ((size_t) SLB_MAX_MASKS * kTcPlaneBytes, 0);
+    for (int m = 0; m < SLB_MAX_MASKS; m++)
+      ctx->tc_ok[m] = N == 512 && m != kAmMaskSlot && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m]);
+    CK (ctx, cudaMemcpyAsync (ctx->d_planes, planes.data (), planes.size (), cudaMemcpyHostToDevice, ctx->stream));
+  }
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   design_biquad_scan_tables (ctx->rx.biquad, &ctx->tables);
+  design_biquad_tc_tables (ctx->rx.biquad, &ctx->tc_tables);
   return SLB_OK;
 }
 
@@ -167,6 +185,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_create_error = std::string (#call) + " -> " + cudaGetErrorString (e_); slb_destroy (ctx); return SLB_ERR_CUDA; } } while (0)
   CKC (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
   CKC (cudaMalloc (&ctx->d_masks, (size_t) SLB_MAX_MASKS * 2 * N * sizeof (float)));
+  CKC (cudaMalloc (&ctx->d_planes, (size_t) SLB_MAX_MASKS * kTcPlaneBytes));
   CKC (cudaMalloc (&ctx->d_slot, C));
   CKC (cudaMalloc (&ctx->d_twiddle, kTwiddleFloats * sizeof (float)));
   for (int p = 0; p < 2; p++) CKC (cudaMalloc (&ctx->d_ovl[p], (size_t) C * ovl * 4));
@@ -199,7 +218,8 @@ void slb_destroy (slb_ctx *ctx)
   cudaDeviceSynchronize ();
   chan64_destroy (ctx->chan);
   rxq15_destroy (ctx->q15);
-  cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle);
+  cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle); cudaFree (ctx->d_planes);
+  for (auto &kv : ctx->tc_lists) cudaFree (kv.second.d);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
@@ -341,7 +361,7 @@ int SLB_DSP_Set_Mode_Channel (slb_ctx *ctx, uint32_t ch, uint8_t mode)
     ctx->mode_host[ch] = mode;
     return rxq15_set_sideband (ctx, ctx->q15, ch, 1, mode_to_lsb (mode));
   }
-  ctx->mode_host[ch] = mode; ctx->slot_host[ch] = (uint8_t) slot;
+  ctx->mode_host[ch] = mode; ctx->slot_host[ch] = (uint8_t) slot; ctx->mode_version++;
   CK (ctx, cudaMemcpyAsync (ctx->d_slot + ch, &ctx->slot_host[ch], 1, cudaMemcpyHostToDevice, ctx->stream));
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   return SLB_OK;
@@ -366,14 +386,15 @@ int SLB_DSP_Set_Mode (slb_ctx *ctx, uint8_t mode)     // dsp_if.c:367-370 is the
     CK (ctx, cudaStreamSynchronize (ctx->stream));
     return rxq15_set_sideband (ctx, ctx->q15, 0, ctx->cfg.channels, mode_to_lsb (mode));
   }
-  std::fill (ctx->slot_host.begin (), ctx->slot_host.end (), (uint8_t) slot);
+  std::fill (ctx->slot_host.begin (), ctx->slot_host.end (), (uint8_t) slot); ctx->mode_version++;
   CK (ctx, cudaMemcpyAsync (ctx->d_slot, ctx->slot_host.data (), ctx->slot_host.size (), cudaMemcpyHostToDevice, ctx->stream));
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   return SLB_OK;
 }
 
-static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
-                          float *dbg_audio, float *dbg_gain, cudaStream_t stream)
+// The FFT kernel over the contiguous channel range [ch0, ch0 + nch)
+static int run_rx_fft_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
+                              float *dbg_audio, float *dbg_gain, cudaStream_t stream)
 {
   const uint32_t ovl = ctx->rx.fft_len - ctx->rx.hop;
   RxF32Launch L{};
@@ -388,6 +409,89 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
   L.tables = &ctx->tables;
   CK (ctx, launch_rx_ssb_f32 (L, ctx->sm_count, stream));
   ctx->launches += rx_ssb_f32_launches_per_call ();
+  return SLB_OK;
+}
+
+// SELENITE_B200_RX_PATH=fft keeps every channel on the FFT kernel (A/B measurements, tests of that kernel)
+static bool tc_path_enabled ()
+{
+  static const bool on = [] { const char *e = std::getenv ("SELENITE_B200_RX_PATH"); return !(e && std::strcmp (e, "fft") == 0); } ();
+  return on;
+}
+
+// One pass of the SSB chain over channels [ch0, ch0 + nch); d_in / d_out / debug taps point at channel ch0.
+// RX: every channel whose mask is a 129-tap FIR goes to the tensor-core kernel — in groups of up to 8 channels of one
+// mask slot; which kernel serves a channel depends on its mode only, never on how the batch is cut, so shards and
+// channel groups reproduce the whole bit for bit. AM channels, caller-supplied masks that are no FIR, and TX stay on
+// the FFT kernel (contiguous runs).
+static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
+                          float *dbg_audio, float *dbg_gain, cudaStream_t stream)
+{
+  if (ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 || !tc_path_enabled ())
+    return run_rx_fft_kernel (ctx, d_in, d_out, ch0, nch, frames, dbg_audio, dbg_gain, stream);
+  slb_ctx::TcLists &tl = ctx->tc_lists[((uint64_t) ch0 << 32) | nch];
+  if (tl.version != ctx->mode_version)
+  {
+    std::vector<uint32_t> by_slot[SLB_MAX_MASKS];
+    tl.on_tc.assign (nch, 0);
+    size_t n_tc = 0;
+    for (uint32_t i = 0; i < nch; i++)
+    {
+      const uint8_t slot = ctx->slot_host[ch0 + i];
+      if (slot < SLB_MAX_MASKS && ctx->tc_ok[slot]) { by_slot[slot].push_back (i); tl.on_tc[i] = 1; n_tc++; }
+    }
+    std::vector<uint32_t> chan, gstart, ginfo;
+    chan.reserve (n_tc);
+    // a group fills the 8 channel rows of one CTA; with fewer than 8 channels per SM the groups are made smaller (rows of
+    // a short group repeat its last channel and are not stored), so that every SM has one: 1024 channels -> 147 groups of 7
+    const size_t gsz = std::min<size_t> (kTcChannels, std::max<size_t> (1, (n_tc + (size_t) ctx->sm_count - 1) / (size_t) ctx->sm_count));
+    for (uint32_t slot = 0; slot < SLB_MAX_MASKS; slot++)
+      for (size_t i = 0; i < by_slot[slot].size (); i += gsz)
+      {
+        const uint32_t n = (uint32_t) std::min<size_t> (gsz, by_slot[slot].size () - i);
+        gstart.push_back ((uint32_t) chan.size ()); ginfo.push_back (slot | (n << 8));
+        chan.insert (chan.end (), by_slot[slot].begin () + i, by_slot[slot].begin () + i + n);
+      }
+    const uint32_t G = (uint32_t) gstart.size ();
+    if (G != 0)
+    {
+      std::vector<uint32_t> pack (2 * (size_t) G + chan.size ());
+      std::memcpy (pack.data (), gstart.data (), G * 4); std::memcpy (pack.data () + G, ginfo.data (), G * 4);
+      std::memcpy (pack.data () + 2 * (size_t) G, chan.data (), chan.size () * 4);
+      // a kernel of an earlier call may still be reading the old lists (any stream): modes change rarely, so wait
+      CK (ctx, cudaDeviceSynchronize ());
+      if (pack.size () > tl.cap) { CK (ctx, cudaFree (tl.d)); tl.d = nullptr; CK (ctx, cudaMalloc (&tl.d, pack.size () * 4)); tl.cap = pack.size (); }
+      CK (ctx, cudaMemcpy (tl.d, pack.data (), pack.size () * 4, cudaMemcpyHostToDevice));
+    }
+    tl.groups = G; tl.version = ctx->mode_version;
+  }
+  const std::vector<uint8_t> &on_tc = tl.on_tc;
+  if (tl.groups != 0)
+  {
+    const uint32_t G = tl.groups;
+    const uint32_t ovl = ctx->rx.fft_len - ctx->rx.hop;
+    RxTcLaunch L{};
+    L.in = d_in; L.out = d_out; L.audio_dbg = dbg_audio; L.gain_dbg = dbg_gain;
+    L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
+    L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
+    L.gstart = tl.d; L.ginfo = tl.d + G; L.chan = tl.d + 2 * (size_t) G;
+    L.planes = ctx->d_planes; L.s0 = ctx->tc_s0;
+    L.flag_final = ctx->flag_base + rx_ssb_f32_tiles (frames);
+    L.n_groups = G; L.frames = frames;
+    L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;
+    L.tables = &ctx->tc_tables;
+    CK (ctx, launch_rx_ssb_tc (L, ctx->sm_count, stream));
+    ctx->launches++;
+  }
+  for (uint32_t i = 0; i < nch;)
+  {
+    if (on_tc[i]) { i++; continue; }
+    uint32_t e = i; while (e < nch && !on_tc[e]) e++;
+    const int rc = run_rx_fft_kernel (ctx, d_in + (size_t) i * frames * 2, d_out + (size_t) i * frames * 2, ch0 + i, e - i, frames,
+                                      dbg_audio ? dbg_audio + (size_t) i * frames : nullptr, dbg_gain ? dbg_gain + (size_t) i * (frames / kAgcBlock) : nullptr, stream);
+    if (rc) return rc;
+    i = e;
+  }
   return SLB_OK;
 }
 // after ALL channels have been advanced by `frames`
@@ -692,6 +796,39 @@ int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp9
   return SLB_OK;
 }
 
+int slb_design_tc_taps (const float *mask_re_im, int32_t taps_re[129], int32_t taps_im[129], float *unit)
+{
+  if (!mask_re_im || !taps_re || !taps_im || !unit) return SLB_ERR_ARG;
+  std::vector<uint8_t> planes (kTcPlaneBytes);
+  if (!tc_build_planes (mask_re_im, planes.data (), unit)) return SLB_ERR_UNSUPPORTED;
+  // read the taps back out of the operand layout: output n = 0 of the block meets tap d at window frame 128 - d
+  for (int d = 0; d < kTcTaps; d++)
+    for (int rail = 0; rail < 2; rail++)
+    {
+      const int m = 2 * (128 - d) + rail, ks = m / 32, kk = m % 32;
+      int32_t v = 0;
+      for (int g = 0; g < 3; g++)
+      {
+        const int row = g * 48;
+        v = v * 256 + (int8_t) planes[(size_t) ks * 18 * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)];
+      }
+      if (rail) taps_im[d] = -v; else taps_re[d] = v;
+    }
+  return SLB_OK;
+}
+int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im)
+{
+  if (!mask_re_im) return SLB_ERR_ARG;
+  return design_default_mask (fs, 512, mode, mask_re_im) == 0 ? SLB_OK : SLB_ERR_UNSUPPORTED;
+}
+int slb_biquad_tc_tables (const float coef10[10], float *Mp64, float *M192, float *Cresp192)
+{
+  if (!coef10 || !Mp64 || !M192 || !Cresp192) return SLB_ERR_ARG;
+  TcBiquadTables t; design_biquad_tc_tables (coef10, &t);
+  std::memcpy (Mp64, t.Mp, sizeof t.Mp); std::memcpy (M192, t.M192, sizeof t.M192); std::memcpy (Cresp192, t.Cresp, sizeof t.Cresp);
+  return SLB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Bulk path
 // ------------------------------------------------------------------------------------------------------------------
@@ -917,6 +1054,7 @@ int slb_state_load (slb_ctx *ctx, const void *buf, size_t bytes)
     return fail (ctx, SLB_ERR_STATE, "checkpoint does not match this context");
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   for (size_t c = 0; c < C; c++) { ctx->mode_host[c] = (uint8_t) p[c]; int s = mode_to_mask_slot (ctx->mode_host[c]); ctx->slot_host[c] = (uint8_t) (s < 0 ? 1 : s); }
+  ctx->mode_version++;
   p += C;
   CK (ctx, cudaMemcpy (ctx->d_slot, ctx->slot_host.data (), C, cudaMemcpyHostToDevice));
   ctx->ovl_parity = 0; ctx->proc_cur = 0;

@@ -183,6 +183,101 @@ void design_biquad_scan_tables (const float *cf, BiquadScanTables *t)
 }
 
 // -----------------------------------------------------------------------------------------------------------
+// Tables of the tensor-core RX-SSB-f32 kernel (sl_rx_ssb_tc.cu)
+// -----------------------------------------------------------------------------------------------------------
+// One zero-input step of the 2-stage df2T cascade (arm_biquad_cascade_df2T_f32.c:551-562 with x = 0), in double.
+static void cascade_zero_input_step (const float *cf, double *s, double *y_out)
+{
+  const double b0 = cf[5], b1 = cf[6], b2 = cf[7];
+  const double y0 = s[0];
+  const double n0 = (double) cf[3] * y0 + s[1], n1 = (double) cf[4] * y0;
+  const double y1 = b0 * y0 + s[2];
+  const double n2 = (b1 * y0 + (double) cf[8] * y1) + s[3], n3 = b2 * y0 + (double) cf[9] * y1;
+  s[0] = n0; s[1] = n1; s[2] = n2; s[3] = n3;
+  *y_out = y1;
+}
+void design_biquad_tc_tables (const float *cf, TcBiquadTables *t)
+{
+  for (int i = 0; i < 10; i++) t->coef[i] = cf[i];
+  double M[4][4];
+  for (int col = 0; col < 4; col++)
+  {
+    double s[4] = { 0, 0, 0, 0 }; s[col] = 1.0;
+    for (int n = 0; n < 48; n++) { double y; cascade_zero_input_step (cf, s, &y); t->Cresp[n][col] = (float) y; }
+    for (int r = 0; r < 4; r++) M[r][col] = s[r];
+  }
+  double P[4][4];
+  for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) P[r][c] = (r == c) ? 1.0 : 0.0;
+  for (int k = 0; k <= 4; k++)
+  {
+    float *dst = (k < 4) ? t->Mp[k] : t->M192;
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) dst[4 * r + c] = (float) P[r][c];
+    double Q[4][4];
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { double a = 0; for (int j = 0; j < 4; j++) a += M[r][j] * P[j][c]; Q[r][c] = a; }
+    std::memcpy (P, Q, sizeof P);
+  }
+}
+
+// The mask of a mode is the DFT of a filter of fft_len - hop + 1 = 129 taps, so overlap-save with it IS a 129-tap FIR.
+// Recover the taps (inverse DFT in double, 1/N as arm_cfft_f32.c:604-614), quantise them to 24 bits and lay them out
+// as the B operand of tcgen05.mma kind::i8: for k-step ks and window byte m = 32 ks + kk (frame m / 2 counted from
+// 128 frames before the block, rail m & 1), output n of the block takes tap d = 128 + n - m / 2:
+//   Re y[n] = sum_d hr[d] I[n - d] - hi[d] Q[n - d]   ->   B[n][m] = rail ? -hi[d] : hr[d]
+// split into three balanced base-256 digits (rows digit * 48 + n), K-major no-swizzle core matrices of 8 rows x 16 bytes.
+bool tc_build_planes (const float *mask, uint8_t *planes, float *s0)
+{
+  const int N = 512;
+  const double two_pi = 6.283185307179586476925286766559;
+  std::vector<double> cs (N), sn (N), hr (N), hi (N);
+  for (int i = 0; i < N; i++) { cs[i] = std::cos (two_pi * i / N); sn[i] = std::sin (two_pi * i / N); }
+  double main_e = 0, tail_e = 0, mx = 0;
+  for (int d = 0; d < N; d++)
+  {
+    double ar = 0, ai = 0;
+    for (int k = 0; k < N; k++)
+    {
+      const int ph = (k * d) & (N - 1);
+      const double Hr = mask[2 * k], Hi = mask[2 * k + 1];
+      ar += Hr * cs[ph] - Hi * sn[ph]; ai += Hr * sn[ph] + Hi * cs[ph];
+    }
+    hr[d] = ar / N; hi[d] = ai / N;
+    const double e = hr[d] * hr[d] + hi[d] * hi[d];
+    if (d < kTcTaps) { main_e += e; mx = std::fmax (mx, std::fmax (std::fabs (hr[d]), std::fabs (hi[d]))); } else tail_e += e;
+  }
+  if (!(main_e > 0.0) || !std::isfinite (main_e) || tail_e > 1e-13 * main_e) return false;
+  const double lim = 8323071.0;                      // 2^23 - 2^16 - 1: the top balanced digit stays inside int8
+  // scale: the largest tap takes the full 24 bits. The float unit of the integer output is fixed first and the tap
+  // scale derived from it, so that unit * 32768 * scale == 1 holds exactly for the float32 value the kernel multiplies by.
+  const float unit = (float) (mx / (lim * 32768.0));
+  if (!(unit > 0.0f) || !std::isfinite (unit) || unit < 1e-30f) return false;
+  const double scale = 1.0 / ((double) unit * 32768.0);
+  std::vector<int32_t> qr (kTcTaps), qi (kTcTaps);
+  for (int d = 0; d < kTcTaps; d++)
+  {
+    qr[d] = (int32_t) std::llround (hr[d] * scale); qi[d] = (int32_t) std::llround (hi[d] * scale);
+    if (std::abs (qr[d]) > (int32_t) lim + 1 || std::abs (qi[d]) > (int32_t) lim + 1) return false;
+  }
+  *s0 = unit;                                        // 1/32768 of arm_q15_to_float.c:87 folded in
+  std::memset (planes, 0, kTcPlaneBytes);
+  for (int ks = 0; ks < 11; ks++)
+    for (int n = 0; n < 48; n++)
+      for (int kk = 0; kk < 32; kk++)
+      {
+        const int m = 32 * ks + kk, f = m / 2, rail = m & 1, d = 128 + n - f;
+        if (d < 0 || d >= kTcTaps) continue;
+        const int32_t h = rail ? -qi[d] : qr[d];
+        const int32_t l0 = ((h + 128) & 255) - 128, r1 = (h - l0) >> 8, l1 = ((r1 + 128) & 255) - 128, l2 = (r1 - l1) >> 8;
+        const int32_t dg[3] = { l2, l1, l0 };          // most significant first: accumulator columns 0..47 carry 2^24
+        for (int g = 0; g < 3; g++)
+        {
+          const int row = g * 48 + n;
+          planes[(size_t) ks * 18 * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)] = (uint8_t) (int8_t) dg[g];
+        }
+      }
+  return true;
+}
+
+// -----------------------------------------------------------------------------------------------------------
 // Ring index logic — follows Core/Src/dsp_if.c line by line (cited), with the sample stores left to the kernels.
 // -----------------------------------------------------------------------------------------------------------
 uint32_t RingPtrs::plan_write (bool is_out, uint32_t frames)

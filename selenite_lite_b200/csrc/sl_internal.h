@@ -98,6 +98,40 @@ void rx_ssb_f32_pack_twiddles (float *out /* kTwiddleFloats */);
 void rx_ssb_f32_pack_mask (const float *mask_re_im, float scale, float *out /* 2 * fft_len floats */);
 constexpr size_t kTwiddleFloats = 6 * 32 * 4;
 
+// ---- RX-SSB-f32 on the tensor cores (sl_rx_ssb_tc.cu): the overlap-save filter restated as the exact integer FIR it
+// is (the mask is the DFT of a 129-tap filter), evaluated by tcgen05.mma kind::i8 on byte planes of samples and taps ----
+constexpr int kTcTaps = 129;                       // fft_len - hop + 1
+constexpr int kTcChannels = 8;                     // channels of one group = the 8 rows of a shared-memory core matrix
+constexpr size_t kTcPlaneBytes = 11 * 18 * 256;    // Toeplitz tap planes of one mask: [k-step][digit*48+n][32 bytes] in UMMA layout
+struct TcBiquadTables
+{
+  float coef[10];                       // stage 0 {b0,b1,b2,a1,a2}, stage 1 {...}
+  float Mp[4][16];                      // A^(48 k), k = 0..3 (k = 0: identity), row-major 4x4, state order {d1_0,d2_0,d1_1,d2_1}
+  float M192[16];                       // A^192: one warp of the epilogue = four blocks
+  float Cresp[48][4];                   // zero-input response of the cascade output at sample n of a block per unit state
+};
+void design_biquad_tc_tables (const float *coef10, TcBiquadTables *t);
+// taps = IDFT of the (unscaled) mask in double; returns false when the impulse response does not fit 129 taps (then the
+// FFT kernel serves the slot). *s0 = 2^-(e+15): the float value of one unit of the integer FIR output.
+bool tc_build_planes (const float *mask_re_im /* [512][2] */, uint8_t *planes /* kTcPlaneBytes */, float *s0);
+struct RxTcLaunch
+{
+  const int16_t *in; int16_t *out;         // [C][T][2]
+  float *audio_dbg; float *gain_dbg;
+  const int16_t *ovl_in; int16_t *ovl_out; // [C][128][2]
+  float *state; unsigned *flag;            // as RxF32Launch; flag[c] is left at flag_final so the FFT kernel can take over
+  const uint32_t *chan;                    // channels served by this launch, grouped by mask slot
+  const uint32_t *gstart;                  // [n_groups] index of the group's first channel in chan[]
+  const uint32_t *ginfo;                   // [n_groups] mask slot | channels in the group (1..8) << 8
+  const uint8_t *planes;                   // [SLB_MAX_MASKS][kTcPlaneBytes]
+  const float *s0;                         // host, [SLB_MAX_MASKS]
+  unsigned flag_final;
+  uint32_t n_groups, frames;
+  float agc_target, agc_decay, agc_floor, agc_gmax;
+  const TcBiquadTables *tables;
+};
+int launch_rx_ssb_tc (const RxTcLaunch &L, int sm_count, void *stream);
+
 // ---- CHAN-64-f32 (sl_chan64.cu): state object owned by the context ----
 struct Chan64State;
 int design_default_chan (uint32_t fs, slb_chan_params *p);
