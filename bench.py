@@ -210,8 +210,8 @@ def run_ours(args):
     kern_ms = sum(step_ms) / len(step_ms)
     achieved = C * T * BYTES_PER_SAMPLE / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "ssb_f32_kernel<false> (sl_rx_ssb_f32.cu)", "algorithmic_bytes_per_launch": C * T * BYTES_PER_SAMPLE,
-                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f; the chain is bound by instruction issue, not HBM (DESIGN.md §4.2)" % (achieved / 8000.0)}
+                "peak_source": peak_src, "kernel": "rx_ssb_tc_kernel (sl_rx_ssb_tc.cu: tcgen05.mma kind::i8 FIR + biquad/AGC epilogue)", "algorithmic_bytes_per_launch": C * T * BYTES_PER_SAMPLE,
+                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f; bound by the A-operand fetch of the SS-mode MMAs and by the epilogue's FP32 work, not by HBM (DESIGN.md §4A)" % (achieved / 8000.0)}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
     if os.path.exists(traffic_file):
         try:
@@ -237,7 +237,7 @@ def run_ours(args):
         if dist is not None:
             t = torch.tensor([dt], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         e2e = {"value": samples_per_step * n_e2e / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": C * T * 4 * world, "d2h_bytes_per_step": C * T * 4 * world,
-               "steps": n_e2e, "path": "slb_rx_process_host: pinned host -> H2D -> rx_ssb_f32_kernel -> D2H, 48 MB channel groups on 3 streams"}
+               "steps": n_e2e, "path": "slb_rx_process_host: pinned host -> H2D -> rx_ssb_tc_kernel -> D2H, channel chunks (>= 1 channel per SM) on 3 streams"}
         del xh, yh, d2
 
     # the other chains of the library at the same width, device-resident, for context (not the headline metric)

@@ -875,6 +875,13 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
   // channels are independent, so the batch is cut into channel groups and H2D / kernel / D2H of consecutive groups overlap
   uint32_t group = (uint32_t) ((size_t) (48u << 20) / ch_bytes);
   if (group < 1) group = 1;
+  if (ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32 && tc_path_enabled ())
+  {
+    // the tensor-core kernel runs one CTA per group of up to 8 channels: a chunk should bring at least one channel
+    // per SM (staging buffers capped at 1 GB each)
+    const uint32_t want = (uint32_t) ctx->sm_count, cap = (uint32_t) std::max<size_t> (1, ((size_t) 1 << 30) / ch_bytes);
+    if (group < want) group = std::min (want, std::max (group, cap));
+  }
   if (group > C) group = C;
   const size_t need = (size_t) group * ch_bytes;
   if (need > ctx->bulk_bytes)

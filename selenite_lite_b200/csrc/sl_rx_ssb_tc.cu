@@ -23,6 +23,7 @@
 // Oracle stage per box as in sl_rx_ssb_f32.cu; the chain sits where the firmware would call it (Core/Src/dsp_if.c:286-289).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include "sl_internal.h"
@@ -44,26 +45,37 @@ constexpr int kKSteps = 11;              // (128 + 48) frames * 2 bytes / 32
 constexpr int kBStep = 18 * 256;         // B bytes per K-step: 18 row groups (3 digits x 48 outputs) x 2 chunks x 128 B
 constexpr int kRawRow = kSuper * 4 + 16; // raw stage row (one channel), padded: conflict-free 16-byte reads across channels
 constexpr int kHistRow = kHist * 4 + 16;
-constexpr int kSets = 2;                 // epilogue warp sets, alternating supertiles
+#ifndef SL_TC_SETS
+#define SL_TC_SETS 2
+#endif
+#ifndef SL_TC_RAWSTAGES
+#define SL_TC_RAWSTAGES 3
+#endif
+#ifndef SL_TC_REGSPLIT
+#define SL_TC_REGSPLIT 0
+#endif
+constexpr int kSets = SL_TC_SETS;                 // epilogue warp sets (warpgroups), taking supertiles in turn
+constexpr int kRawStages = SL_TC_RAWSTAGES;            // raw stages: a bulk copy takes ~4400 clocks to land (measured), a supertile ~3000
 constexpr int kEpiWarps = 4 * kSets;
 constexpr int kConvWarps = 2;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
-constexpr int kThreads = 32 * (kProdWarp + 1);   // 12 warps: 384 threads x 170 registers
+constexpr int kThreads = 32 * (kProdWarp + 1);   // 16 warps = 4 warpgroups: 3 epilogue sets + {2 converters, MMA issuer, producer}
+static_assert (!SL_TC_REGSPLIT || kThreads == 512, "register split below assumes 4 warpgroups");
 constexpr int kTmemCols = 512;           // two accumulator buffers of 192 columns at 0 and 256
 
 struct Smem
 {
   static constexpr size_t a = 0;                                        // [2 buffers][hi plane | lo plane]
   static constexpr size_t b = a + 2 * 2 * kPlaneBytes;                  // tap planes of the current mask
-  static constexpr size_t raw = b + kTcPlaneBytes;                      // [2 stages][8 rows]
-  static constexpr size_t hist = raw + 2 * kJ * kRawRow;                // [2 stages][8 rows] carried tail of the previous call
-  static constexpr size_t wsum = hist + 2 * kJ * kHistRow;              // [sets][4 warps][8][4] floats
+  static constexpr size_t raw = b + kTcPlaneBytes;                      // [stages][8 rows]
+  static constexpr size_t hist = raw + kRawStages * kJ * kRawRow;       // [stages][8 rows] carried tail of the previous call
+  static constexpr size_t wsum = hist + kRawStages * kJ * kHistRow;              // [sets][4 warps][8][4] floats
   static constexpr size_t pk = wsum + kSets * 4 * kJ * 4 * 4;           // [sets][16][8] floats
   static constexpr size_t carry_s = pk + kSets * kQ * kJ * 4;           // [2][8][4] floats
   static constexpr size_t carry_e = carry_s + 2 * kJ * 4 * 4;           // [2][8] floats
   static constexpr size_t mp = carry_e + 2 * kJ * 4;                    // [4][20] floats: A^(48 a), rows padded to 20 (bank spread)
   static constexpr size_t bars = mp + 4 * 20 * 4;
-  static constexpr int n_bars = 18;
+  static constexpr int n_bars = 22;
   static constexpr size_t tmem_ptr = bars + n_bars * 8;
   static constexpr size_t bytes = tmem_ptr + 16;
 };
@@ -77,6 +89,7 @@ struct KParams
   const uint32_t *chan; const uint32_t *gstart; const uint32_t *ginfo;
   const uint8_t *planes;
   float s0[SLB_MAX_MASKS];
+  long long *trace;                            // profiling aid (SELENITE_B200_TC_TRACE): [supertile][16] clock64 stamps of CTA 0
   unsigned flag_final;
   uint32_t n_groups, frames, supers;
   float agc_target, agc_decay, agc_floor, agc_gmax;
@@ -126,6 +139,12 @@ __device__ __forceinline__ void umma_i8 (uint32_t tmem_d, uint64_t da, uint64_t 
   asm volatile ("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ bool elect_one ()
+{
+  uint32_t pred;
+  asm volatile ("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit (uint64_t *bar)
 {
   asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32 (bar)) : "memory");
@@ -137,6 +156,11 @@ __device__ __forceinline__ void tmem_ld16 (uint32_t addr, uint32_t *v)
   asm volatile ("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld8 (uint32_t addr, uint32_t *v)
+{
+  asm volatile ("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr));
 }
 __device__ __forceinline__ void tmem_ld_wait () { asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -155,6 +179,13 @@ __device__ __forceinline__ void matvec4 (const float *M, const float *x, const f
   for (int r = 0; r < 4; r++) y[r] = add[r] + (M[4 * r] * x[0] + M[4 * r + 1] * x[1] + M[4 * r + 2] * x[2] + M[4 * r + 3] * x[3]);
 }
 
+// pipeline trace (tools/tc_trace.py): build with -DSL_TC_TRACE; the stamps cost 7 % even when no buffer is attached
+#ifndef SL_TC_TRACE
+#define TC_STAMP(slot) do { } while (0)
+#else
+#define TC_STAMP(slot) do { if (P.trace && blockIdx.x == 0 && lane == 0) P.trace[(size_t) kk * 16 + (slot)] = clock64 (); } while (0)
+#endif
+
 __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_constant__ KParams P)
 {
   extern __shared__ __align__ (1024) unsigned char smem[];
@@ -163,17 +194,20 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   float *sCarryS = reinterpret_cast<float *> (smem + Smem::carry_s), *sCarryE = reinterpret_cast<float *> (smem + Smem::carry_e);
   float *sMp = reinterpret_cast<float *> (smem + Smem::mp);
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
-  uint64_t *raw_full = bars, *raw_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 6, *t_full = bars + 8, *t_empty = bars + 10;
-  uint64_t *s_bar = bars + 12, *e_bar = bars + 14, *b_full = bars + 16, *drain = bars + 17;
+  uint64_t *raw_full = bars, *raw_empty = bars + 3, *a_full = bars + 6, *a_empty = bars + 8, *t_empty = bars + 10;
+  uint64_t *s_bar = bars + 12, *e_bar = bars + 14, *b_full = bars + 16, *drain = bars + 17, *t_full = bars + 18;
+  // t_full has FOUR slots although there are two accumulator buffers: an epilogue set may start waiting for supertile
+  // kk + 2 while kk is still in flight, and on a two-slot barrier that wait would alias the phase before kk's and pass at once
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *> (smem + Smem::tmem_ptr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0)
   {
+    for (int i = 0; i < kRawStages; i++) { mbar_init (raw_full + i, 1); mbar_init (raw_empty + i, kConvWarps); }
     for (int i = 0; i < 2; i++)
     {
-      mbar_init (raw_full + i, 1); mbar_init (raw_empty + i, kConvWarps); mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
-      mbar_init (t_full + i, 1); mbar_init (t_empty + i, 4); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
+      mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
+      mbar_init (t_full + i, 1); mbar_init (t_full + 2 + i, 1); mbar_init (t_empty + i, 4); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
     }
     mbar_init (b_full, 1); mbar_init (drain, 1);
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -189,6 +223,13 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   tc_fence_after ();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t supers = P.supers;
+  // register split between the warpgroups (the launch gives every thread 128): the epilogue holds a 48-sample block plus
+  // 64 accumulator words per thread, the copy / convert / issue roles need little
+  // (the whole warpgroup executes ONE setmaxnreg: the three small roles share warpgroup 3 and release together, as a
+  // .sync.aligned instruction requires; the epilogue warpgroups acquire at the head of their branch)
+#if SL_TC_REGSPLIT
+  if (warp >= kEpiWarps) asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
+#endif
 
   if (warp == kProdWarp)
   {
@@ -199,9 +240,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
         for (uint32_t k = 0; k < supers; k++, kk++)
         {
-          const int rb = kk & 1;
+          const int rb = kk % kRawStages;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
-          mbar_wait (raw_empty + rb, ((kk >> 1) & 1) ^ 1);
+          mbar_wait (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
+          TC_STAMP (0);
           mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
 #pragma unroll 1
@@ -220,7 +262,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // ========================================== converters ==========================================
     // int16 I/Q frames -> the two byte planes of the A operand: chunk = 8 frames, 16 bytes (I, Q) per channel,
     // 8 channels contiguous (one core matrix). Two PRMTs per pair of frames and plane; no arithmetic. A lane keeps its
-    // channel (lane & 7) and walks the chunks lane >> 3, + 4, + 8, ...: constant strides, six chunks in flight.
+    // channel (lane & 7) and walks the chunks lane >> 3, + 4, + 8, ...: constant strides, three chunks in flight (the role runs on 56 registers).
     const int cw = warp - kEpiWarps, j = lane & 7, c4 = lane >> 3;
     unsigned kk = 0;
     for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
@@ -228,11 +270,13 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       const uint32_t nvalid = P.ginfo[g] >> 8, gs = P.gstart[g];
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
-        const int rb = kk & 1, ab = kk & 1;
+        const int rb = kk % kRawStages, ab = kk & 1;
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
-        unsigned char *Ahi = sA + ab * 2 * kPlaneBytes, *Alo = Ahi + kPlaneBytes;
-        mbar_wait (raw_full + rb, (kk >> 1) & 1);
+        unsigned char *Ahi = sA + ab * 2 * kPlaneBytes;
+        mbar_wait (raw_full + rb, (kk / kRawStages) & 1);
+        if (cw == 0) TC_STAMP (1);
         mbar_wait (a_empty + ab, ((kk >> 1) & 1) ^ 1);                         // the MMAs of supertile kk - 2 have read this buffer
+        if (cw == 0) TC_STAMP (2);
         if (cw == 0 && k == 0)
         {
           // history = the carried raw tail of the previous call (this launch reads ovl_in and writes ovl_out)
@@ -264,13 +308,14 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           const int per = (int) (nfr / 32) / kConvWarps;                          // 12 (or 6 for the half supertile at the end of a stream)
           const unsigned char *src = sRaw + (rb * kJ + j) * kRawRow + (c4 + 4 * cw * per) * 32;
           unsigned char *dst = Ahi + (kChunksHist + c4 + 4 * cw * per) * kChunkBytes + j * 16;
-          for (int t0 = 0; t0 < per; t0 += 6)
+          constexpr int kB = SL_TC_REGSPLIT ? 3 : 6;                             // chunks in flight (the role runs on 56 registers under the split)
+          for (int t0 = 0; t0 < per; t0 += kB)
           {
-            uint4 v[12];
+            uint4 v[2 * kB];
 #pragma unroll
-            for (int t = 0; t < 6; t++) { v[2 * t] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * 128); v[2 * t + 1] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * 128 + 16); }
+            for (int t = 0; t < kB; t++) { v[2 * t] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * 128); v[2 * t + 1] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * 128 + 16); }
 #pragma unroll
-            for (int t = 0; t < 6; t++)
+            for (int t = 0; t < kB; t++)
             {
               const uint4 v0 = v[2 * t], v1 = v[2 * t + 1];
               *reinterpret_cast<uint4 *> (dst + (t0 + t) * 4 * kChunkBytes) =
@@ -296,6 +341,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         }
         asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp ();
+        if (cw == 0) TC_STAMP (3);
         if (lane == 0) { mbar_arrive (a_full + ab); mbar_arrive (raw_empty + rb); }
       }
     }
@@ -303,61 +349,72 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   else if (warp == kMmaWarp)
   {
     // ========================================== MMA issuer ==========================================
-    if (lane == 0)
+    // The whole warp walks the loop converged and ONE elected lane issues: with `if (lane == 0)` around the loop the
+    // compiler cannot keep descriptors in uniform registers and wraps every tcgen05.mma in a vote / broadcast loop —
+    // measured 128 clocks of issue per MMA against 72 of execution (N = 144), i.e. the tensor pipe sat idle 2/3 of the time.
+    constexpr uint32_t id_ss48 = umma_idesc (48, 1, 1), id_ss96 = umma_idesc (96, 1, 1), id_ss144 = umma_idesc (144, 1, 1), id_us144 = umma_idesc (144, 0, 1);
+    const uint32_t aBase = smem_u32 (sA), bBase = smem_u32 (sB);
+    // constant upper halves of the descriptors: LBO = 128 (A and B), SBO = 768 (A, aliased row groups) / 256 (B), version 1
+    constexpr uint64_t kDescA = ((uint64_t) (kChunkBytes >> 4) << 16) | ((uint64_t) ((6 * kChunkBytes) >> 4) << 32) | (1ull << 46);
+    constexpr uint64_t kDescB = ((uint64_t) (128 >> 4) << 16) | ((uint64_t) (256 >> 4) << 32) | (1ull << 46);
+    unsigned kk = 0, b_loads = 0, drains = 0;
+    int cur_slot = -1;
+    for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
     {
-      constexpr uint32_t id_ss48 = umma_idesc (48, 1, 1), id_ss96 = umma_idesc (96, 1, 1), id_ss144 = umma_idesc (144, 1, 1), id_us144 = umma_idesc (144, 0, 1);
-      const uint32_t aBase = smem_u32 (sA), bBase = smem_u32 (sB);
-      unsigned kk = 0, b_loads = 0, drains = 0;
-      int cur_slot = -1;
-      for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
+      const int slot = (int) (P.ginfo[g] & 0xFFu);
+      if (slot != cur_slot)
       {
-        const int slot = (int) (P.ginfo[g] & 0xFFu);
-        if (slot != cur_slot)
+        // (re)load the tap planes of this mask; earlier MMAs may still be reading the old ones
+        if (kk != 0) { if (elect_one ()) umma_commit (drain); __syncwarp (); mbar_wait (drain, drains & 1); drains++; }
+        if (elect_one ())
         {
-          // (re)load the tap planes of this mask; earlier MMAs may still be reading the old ones
-          if (kk != 0) { umma_commit (drain); mbar_wait (drain, drains & 1); drains++; }
           mbar_expect_tx (b_full, (unsigned) kTcPlaneBytes);
           bulk_g2s (sB, P.planes + (size_t) slot * kTcPlaneBytes, (unsigned) kTcPlaneBytes, b_full);
-          mbar_wait (b_full, b_loads & 1); b_loads++;
-          cur_slot = slot;
         }
-        for (uint32_t k = 0; k < supers; k++, kk++)
+        __syncwarp ();
+        mbar_wait (b_full, b_loads & 1); b_loads++;
+        cur_slot = slot;
+      }
+      for (uint32_t k = 0; k < supers; k++, kk++)
+      {
+        const int ab = kk & 1, tb = kk & 1;
+        mbar_wait (a_full + ab, (kk >> 1) & 1);
+        TC_STAMP (4);
+        mbar_wait (t_empty + tb, ((kk >> 1) & 1) ^ 1);                       // the epilogue has drained this accumulator buffer
+        TC_STAMP (5);
+        tc_fence_after ();
+        const uint32_t d = tmem + (uint32_t) tb * 256u;
+        const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4), b0 = bBase >> 4;
+        if (elect_one ())
         {
-          const int ab = kk & 1, tb = kk & 1;
-          mbar_wait (a_full + ab, (kk >> 1) & 1);
-          mbar_wait (t_empty + tb, ((kk >> 1) & 1) ^ 1);                       // the epilogue has drained this accumulator buffer
-          tc_fence_after ();
-          const uint32_t d = tmem + (uint32_t) tb * 256u;
-          const uint32_t aHi = aBase + ab * 2 * kPlaneBytes, aLo = aHi + kPlaneBytes;
-#pragma unroll 1
-          for (int ks = 0; ks < kKSteps; ks++)
+          // accumulator columns: [0,48) weight 2^24 = xh h2, [48,96) 2^16 = xh h1 + xl h2, [96,144) 2^8 = xh h0 + xl h1, [144,192) 1 = xl h0.
+          // (Tried: two independent chains, xh * [h2|h1|h0] and xl * [h2|h1|h0] in disjoint columns, added in the epilogue. No faster —
+          // an SS-mode MMA with M = 128 is bound by the fetch of its 4 KB A tile, ~128 clocks whatever N <= 192 is
+          // (tools/microbench/umma_rate.cu) — and it costs the second accumulator buffer.)
+          umma_i8 (d, kDescA | aHi, kDescB | b0, id_ss48, 0u);                                   // xh * h2          -> [0,48)   fresh
+          umma_i8 (d + 48, kDescA | aLo, kDescB | b0, id_us144, 0u);                             // xl * [h2|h1|h0]  -> [48,192) fresh
+          umma_i8 (d + 48, kDescA | aHi, kDescB | (b0 + ((6 * 256) >> 4)), id_ss96, 1u);         // xh * [h1|h0]     -> [48,144) accumulate
+#pragma unroll
+          for (int ks = 1; ks < kKSteps; ks++)
           {
-            // accumulator columns: [0,48) weight 2^24 = xh h2, [48,96) 2^16 = xh h1 + xl h2, [96,144) 2^8 = xh h0 + xl h1, [144,192) 1 = xl h0
-            const uint64_t dHi = umma_desc (aHi + ks * 2 * kChunkBytes, kChunkBytes, 6 * kChunkBytes);
-            const uint64_t dLo = umma_desc (aLo + ks * 2 * kChunkBytes, kChunkBytes, 6 * kChunkBytes);
-            const uint32_t b0 = bBase + ks * kBStep;
-            if (ks == 0)
-            {
-              umma_i8 (d, dHi, umma_desc (b0, 128, 256), id_ss48, 0u);                       // xh * h2            -> [0,48)   fresh
-              umma_i8 (d + 48, dLo, umma_desc (b0, 128, 256), id_us144, 0u);                 // xl * [h2|h1|h0]    -> [48,192) fresh
-              umma_i8 (d + 48, dHi, umma_desc (b0 + 6 * 256, 128, 256), id_ss96, 1u);        // xh * [h1|h0]       -> [48,144) accumulate
-            }
-            else
-            {
-              umma_i8 (d, dHi, umma_desc (b0, 128, 256), id_ss144, 1u);
-              umma_i8 (d + 48, dLo, umma_desc (b0, 128, 256), id_us144, 1u);
-            }
+            const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStep) >> 4;
+            umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss144, 1u);
+            umma_i8 (d + 48, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us144, 1u);
           }
-          umma_commit (t_full + tb);        // accumulators complete -> epilogue
+          umma_commit (t_full + (kk & 3));  // accumulators complete -> epilogue
           umma_commit (a_empty + ab);       // planes read -> converter may overwrite them
         }
+        __syncwarp ();
+        TC_STAMP (6);
       }
     }
-    __syncwarp ();
   }
   else
   {
     // ========================================== epilogue ==========================================
+#if SL_TC_REGSPLIT
+    asm volatile ("setmaxnreg.inc.sync.aligned.u32 152;");
+#endif
     // TMEM lane = 32 w + lane = 8 q + j: thread (q, j) owns firmware block q of channel j of the supertile.
     const int es = warp >> 2, w = warp & 3, a = lane >> 3, j = lane & 7, q = 4 * w + a;
     float *myW = sW + es * (4 * kJ * 4), *myPk = sPk + es * (kQ * kJ);
@@ -377,24 +434,31 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
         const int nblk = (int) (nfr / kBlk);
         const bool last_q = q == nblk - 1;
-        mbar_wait (t_full + tb, (kk >> 1) & 1);
+        mbar_wait (t_full + (kk & 3), (kk >> 2) & 1);
         tc_fence_after ();
-        // ---- accumulators -> float: y = (D24 2^24 + D16 2^16 + D8 2^8 + D0) * 2^-(e+15) (arm_q15_to_float's 1/32768 folded in)
+        if (w == 0) TC_STAMP (7);
+        // ---- accumulators -> float: y = (D24 2^24 + D16 2^16 + D8 2^8 + D0) * unit (arm_q15_to_float's 1/32768 folded in)
         float y[kBlk];
         const uint32_t taddr = tmem + (uint32_t) tb * 256u + ((uint32_t) (32 * w) << 16);
+#ifndef SL_TC_LDW
+#define SL_TC_LDW 16
+#endif
+        constexpr int kW = SL_TC_LDW;                                              // accumulator columns per tcgen05.ld
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+        for (int i = 0; i < kBlk / kW; i++)
         {
-          uint32_t v0[16], v1[16], v2[16], v3[16];
-          tmem_ld16 (taddr + 16 * i, v0); tmem_ld16 (taddr + 48 + 16 * i, v1); tmem_ld16 (taddr + 96 + 16 * i, v2); tmem_ld16 (taddr + 144 + 16 * i, v3);
+          uint32_t v0[kW], v1[kW], v2[kW], v3[kW];
+          if (kW == 16) { tmem_ld16 (taddr + kW * i, v0); tmem_ld16 (taddr + 48 + kW * i, v1); tmem_ld16 (taddr + 96 + kW * i, v2); tmem_ld16 (taddr + 144 + kW * i, v3); }
+          else { tmem_ld8 (taddr + kW * i, v0); tmem_ld8 (taddr + 48 + kW * i, v1); tmem_ld8 (taddr + 96 + kW * i, v2); tmem_ld8 (taddr + 144 + kW * i, v3); }
           tmem_ld_wait ();
 #pragma unroll
-          for (int n = 0; n < 16; n++)
-            y[16 * i + n] = fmaf (__int2float_rn ((int) v0[n]), s24, fmaf (__int2float_rn ((int) v1[n]), s16, fmaf (__int2float_rn ((int) v2[n]), s8, __int2float_rn ((int) v3[n]) * s0)));
+          for (int n = 0; n < kW; n++)
+            y[kW * i + n] = fmaf (__int2float_rn ((int) v0[n]), s24, fmaf (__int2float_rn ((int) v1[n]), s16, fmaf (__int2float_rn ((int) v2[n]), s8, __int2float_rn ((int) v3[n]) * s0)));
         }
         tc_fence_before ();
         __syncwarp ();
         if (lane == 0) mbar_arrive (t_empty + tb);                               // the accumulator buffer now lives in registers
+        if (w == 0) TC_STAMP (8);
 
         // ---- zero-state response of the cascade over the block, per sample as arm_biquad_cascade_df2T_f32.c:551-562:
         //      y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
@@ -411,6 +475,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           z[3] = fmaf (cf[9], y1, cf[7] * y0);
           y[n] = y1;
         }
+        if (w == 0) TC_STAMP (9);
         // ---- level 1: start state of the block inside the warp (zero at the warp's first block): P_{a+1} = M48 P_a + z_a
         float Pst[4] = { 0.f, 0.f, 0.f, 0.f };
 #pragma unroll
@@ -443,7 +508,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           const float4 v = *reinterpret_cast<const float4 *> (sCarryS + (((kk - 1) & 1) * kJ + j) * 4);
           S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
         }
+        if (w == 0) TC_STAMP (10);
         named_bar (1 + 2 * es, 128);
+        if (w == 0) TC_STAMP (11);
         // ---- level 2: state at the warp's first block, then at this block
 #pragma unroll
         for (int ww = 0; ww < 3; ww++)
@@ -489,7 +556,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         myPk[q * kJ + j] = peak;
         if (kk != 0) mbar_wait (e_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
         envc = (k == 0) ? __ldcg (P.state + (size_t) c * 8 + 4) : sCarryE[((kk - 1) & 1) * kJ + j];
+        if (w == 0) TC_STAMP (12);
         named_bar (2 + 2 * es, 128);
+        if (w == 0) TC_STAMP (13);
         // ---- AGC envelope: the oracle's sequential walk env_b = max(peak_b, fl(env_{b-1} * decay)) over the blocks before and including this one
         float e = envc;
 #pragma unroll
@@ -526,6 +595,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           for (int n = 0; n < kBlk; n += 4)
             dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
         }
+        if (w == 0) TC_STAMP (14);
       }
     }
   }
@@ -563,6 +633,31 @@ int launch_rx_ssb_tc (const RxTcLaunch &L, int sm_count, void *stream_)
   uint32_t grid = (uint32_t) sm_count;
   if (grid > L.n_groups) grid = L.n_groups;
   if (const char *gs = std::getenv ("SELENITE_B200_TC_GRID")) { const long v = std::atol (gs); if (v > 0 && (uint32_t) v <= grid) grid = (uint32_t) v; }   // profiling aid
+  P.trace = nullptr;
+#ifdef SL_TC_TRACE
+  if (const char *tf = std::getenv ("SELENITE_B200_TC_TRACE"))
+  {
+    // profiling aid: clock64 stamps of every pipeline role of CTA 0, one row per supertile, dumped as text after the launch
+    const size_t n = (size_t) P.supers * ((L.n_groups + grid - 1) / grid) * 16;
+    long long *d_tr = nullptr;
+    if (cudaMalloc (&d_tr, n * 8) == cudaSuccess)
+    {
+      cudaMemset (d_tr, 0, n * 8);
+      P.trace = d_tr;
+      rx_ssb_tc_kernel<<<grid, kThreads, Smem::bytes, stream>>> (P);
+      cudaDeviceSynchronize ();
+      long long *h = (long long *) std::malloc (n * 8);
+      cudaMemcpy (h, d_tr, n * 8, cudaMemcpyDeviceToHost);
+      if (FILE *f = std::fopen (tf, "w"))
+      {
+        for (size_t r = 0; r < n / 16; r++) { for (int c = 0; c < 16; c++) std::fprintf (f, "%lld ", h[r * 16 + c] ? h[r * 16 + c] - h[0] : -1ll); std::fprintf (f, "\n"); }
+        std::fclose (f);
+      }
+      std::free (h); cudaFree (d_tr);
+      return (int) cudaGetLastError ();
+    }
+  }
+#endif
   rx_ssb_tc_kernel<<<grid, kThreads, Smem::bytes, stream>>> (P);
   return (int) cudaGetLastError ();
 }
