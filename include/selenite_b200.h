@@ -133,6 +133,12 @@ int slb_set_rx_q15_params (slb_ctx *ctx, const slb_rx_q15_params *p);
 int slb_get_rx_q15_params (const slb_ctx *ctx, slb_rx_q15_params *p);
 int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask);   /* host, 2*fft_len floats */
 int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask);
+/* which kernel serves the RX-SSB-f32 chain: SLB_RX_PATH_AUTO = the tensor-core FIR kernel for every channel
+ * whose mask is a 129-tap filter (all the default masks but AM), the FFT kernel for the rest; SLB_RX_PATH_FFT = the FFT
+ * kernel for everything. Both carry the same state, so the path may change between calls. */
+#define SLB_RX_PATH_AUTO 0
+#define SLB_RX_PATH_FFT  1
+int slb_set_rx_path (slb_ctx *ctx, int path);
 
 /* ---- the firmware API, batched (reference: Core/Inc/dsp_if.h:42-51; bodies Core/Src/dsp_if.c) ----
  * pbuf is HOST memory laid out [channels][size]; `size` means what it means in the firmware. */

@@ -47,6 +47,7 @@ struct slb_ctx
   // call) and rebuilt when a mode or a mask changes (mode_version)
   struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
   std::map<uint64_t, TcLists> tc_lists; uint64_t mode_version = 0;
+  bool force_fft = false;              // slb_set_rx_path (SLB_RX_PATH_FFT)
   int16_t *d_ovl[2] = { nullptr, nullptr }; int ovl_parity = 0;
   float *d_state = nullptr; unsigned *d_flag = nullptr;
   unsigned flag_base = 0;
@@ -277,6 +278,12 @@ int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask)
   std::memcpy (ctx->masks_host.data () + (size_t) slot * 2 * ctx->rx.fft_len, mask, (size_t) 2 * ctx->rx.fft_len * sizeof (float));
   return upload_chain_constants (ctx);
 }
+int slb_set_rx_path (slb_ctx *ctx, int path)
+{
+  if (!ctx || (path != SLB_RX_PATH_AUTO && path != SLB_RX_PATH_FFT)) return SLB_ERR_ARG;
+  ctx->force_fft = path == SLB_RX_PATH_FFT;
+  return SLB_OK;
+}
 int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask)
 {
   if (!ctx || !mask) return SLB_ERR_ARG;
@@ -427,7 +434,7 @@ static bool tc_path_enabled ()
 static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
                           float *dbg_audio, float *dbg_gain, cudaStream_t stream)
 {
-  if (ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 || !tc_path_enabled ())
+  if (ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 || !tc_path_enabled () || ctx->force_fft)
     return run_rx_fft_kernel (ctx, d_in, d_out, ch0, nch, frames, dbg_audio, dbg_gain, stream);
   slb_ctx::TcLists &tl = ctx->tc_lists[((uint64_t) ch0 << 32) | nch];
   if (tl.version != ctx->mode_version)

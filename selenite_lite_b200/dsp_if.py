@@ -12,6 +12,7 @@ from . import _lib
 
 CHAIN_PASS, CHAIN_RX_SSB_F32, CHAIN_TX_SSB_F32, CHAIN_CHAN64_F32, CHAIN_RX_SSB_Q15 = 0, 1, 2, 3, 4
 MODE_LSB, MODE_USB, MODE_CW, MODE_CWR, MODE_AM, MODE_FM, MODE_DIG, MODE_PKT = 0x00, 0x01, 0x02, 0x03, 0x04, 0x08, 0x0A, 0x0C
+RX_PATH_AUTO, RX_PATH_FFT = 0, 1
 
 
 class SeleniteError(RuntimeError):
@@ -213,6 +214,10 @@ class DspIf:
         return p
 
     def set_rx_params(self, p): self._ck(self.lib.slb_set_rx_f32_params(self.h, C.byref(p)), "set_rx_f32_params")
+
+    def set_rx_path(self, path):
+        """RX_PATH_AUTO (tensor-core FIR kernel where the mask allows) or RX_PATH_FFT (FFT kernel for every channel)."""
+        self._ck(self.lib.slb_set_rx_path(self.h, int(path)), "set_rx_path")
 
     def mask(self, mode=MODE_USB):
         m = np.zeros(2 * self.rx_params().fft_len, np.float32)

@@ -1,0 +1,127 @@
+"""GPU parity of the tensor-core form of the RX-SSB-f32 chain (sl_rx_ssb_tc.cu), through the C ABI.
+
+The kernel evaluates the overlap-save filter as the exact 129-tap integer FIR it is (tcgen05.mma kind::i8), so against
+the float32-FFT oracle it is held to the same bars as the FFT kernel: audio within 1e-5 * max(|ref|, frame rms), int16
+output within 1 LSB on < 2 % of samples. Extra here: the two kernels against each other, the hand-over of the carried
+state between them, per-channel kernel choice with mixed modes, short groups, the half supertile at the end of a stream."""
+import numpy as np
+import pytest
+
+import selenite_lite_b200 as slb
+from test_golden import audio_tolerance
+from test_gpu_rx_ssb_f32 import check_int16, run_gpu
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def one_lsb(a, b):
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    return d.max() <= 1 and np.mean(d > 0) < 0.02
+
+
+@pytest.mark.parametrize("channels,frames", [(1, 384), (7, 768), (8, 1152), (9, 3840), (150, 1536), (300, 2304)])
+def test_both_kernels_meet_the_oracle_and_each_other(best_oracle, channels, frames):
+    """384 = half a supertile, 1152 = one and a half; 1 / 7 / 9 channels = short groups (rows repeat a channel, unstored);
+    150 / 300 = more groups than one per SM and the smaller-group rule (fewer than 8 channels per SM)."""
+    x = slb.synth_iq(channels, frames)
+    d_tc = slb.DspIf(channels, chain=slb.CHAIN_RX_SSB_F32)
+    d_fft = slb.DspIf(channels, chain=slb.CHAIN_RX_SSB_F32); d_fft.set_rx_path(slb.RX_PATH_FFT)
+    y_tc, a_tc, g_tc = run_gpu(d_tc, x)
+    y_fft, a_fft, g_fft = run_gpu(d_fft, x)
+    assert one_lsb(y_tc, y_fft)
+    worst = 0.0
+    for c in range(0, channels, max(1, channels // 6)):
+        exp, a, g_, _ = best_oracle.rx_ssb_f32(d_tc.oracle_params(), x[c])
+        tol = audio_tolerance(a)
+        e_tc = float(np.max(np.abs(a_tc[c] - a) / tol)); e_fft = float(np.max(np.abs(a_fft[c] - a) / tol))
+        assert e_tc <= 1.0 and e_fft <= 1.0, (c, e_tc, e_fft)
+        worst = max(worst, e_tc)
+        check_int16(y_tc[c], exp)
+        assert np.allclose(g_tc[c], g_, rtol=2e-5)
+    assert worst < 0.5        # the exact FIR sits well inside the tolerance (the oracle's own float32 FFT noise dominates)
+
+
+def test_state_hands_over_between_the_two_kernels(best_oracle):
+    """One stream cut into four calls served alternately by the tensor-core and the FFT kernel: raw tail, biquad state,
+    AGC envelope and the FFT kernel's hand-over counter all cross the switch (DESIGN.md §3.2 carried state)."""
+    C, T = 12, 1536 * 8
+    x = slb.synth_iq(C, T)
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    cuts = [0, 1536 * 2, 1536 * 2 + 384, 1536 * 5, T]
+    xd = torch.from_numpy(x).cuda(); parts = []
+    for i in range(4):
+        d.set_rx_path(slb.RX_PATH_FFT if i % 2 else slb.RX_PATH_AUTO)
+        parts.append(d.rx_process(xd[:, cuts[i]:cuts[i + 1]].contiguous()).cpu().numpy())
+    y = np.concatenate(parts, axis=1)
+    for c in (0, 5, 11):
+        exp, _, _, _ = best_oracle.rx_ssb_f32(d.oracle_params(), x[c])
+        check_int16(y[c], exp)
+    # and a stream cut into calls on the tensor-core kernel alone equals the uncut stream bit for bit
+    d1 = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32); d2 = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    whole = d1.rx_process(xd).cpu().numpy()
+    cut = np.concatenate([d2.rx_process(xd[:, a:b].contiguous()).cpu().numpy() for a, b in ((0, 768 * 3), (768 * 3, 768 * 10), (768 * 10, T))], axis=1)
+    assert np.array_equal(whole, cut)
+
+
+def test_kernel_choice_is_per_channel(best_oracle):
+    """Modes scattered over the channels: every SSB / CW / DIG channel is served by the tensor-core kernel in groups of its
+    own mask, AM channels by the FFT kernel, all in one call; a channel's result does not depend on its neighbours."""
+    C, T = 41, 768 * 5
+    modes = [slb.MODE_USB, slb.MODE_AM, slb.MODE_LSB, slb.MODE_CW, slb.MODE_USB, slb.MODE_DIG, slb.MODE_CWR, slb.MODE_PKT]
+    # a tone inside the pass band of the channel's own mode (an out-of-band tone leaves an output 50 dB below the input,
+    # where the oracle's float32 FFT noise — relative to the INPUT — is larger than 1e-5 of the output)
+    f_in = {slb.MODE_USB: 1000.0, slb.MODE_LSB: -1200.0, slb.MODE_CW: 700.0, slb.MODE_CWR: -650.0, slb.MODE_DIG: 2000.0, slb.MODE_PKT: 1500.0, slb.MODE_AM: 150.0}
+    x = np.concatenate([slb.synth_iq(1, T, f0=abs(f_in[modes[c % len(modes)]]) + 3 * c, sideband=1 if f_in[modes[c % len(modes)]] > 0 else -1,
+                                     first_channel=c) for c in range(C)])
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    for c in range(C):
+        d.DSP_Set_Mode(modes[c % len(modes)], channel=c)
+    y, audio, gain = run_gpu(d, x)
+    for c in range(C):
+        m = modes[c % len(modes)]
+        exp, a, g_, _ = best_oracle.rx_ssb_f32(d.oracle_params(m), x[c])
+        tol = audio_tolerance(a)
+        assert np.all(np.abs(audio[c] - a) <= tol + 1e-12), (c, m)
+        check_int16(y[c], exp)
+    # the same channels alone, one context per mode: bit-identical to the mixed batch
+    for m in (slb.MODE_USB, slb.MODE_CW):
+        idx = [c for c in range(C) if modes[c % len(modes)] == m]
+        ds = slb.DspIf(len(idx), chain=slb.CHAIN_RX_SSB_F32); ds.DSP_Set_Mode(m)
+        ys = run_gpu(ds, np.ascontiguousarray(x[idx]), want_audio=False)[0]
+        assert np.array_equal(ys, y[idx]), m
+
+
+def test_weak_and_full_scale_signals(best_oracle):
+    """The integer FIR is exact, so its error does not depend on the signal level: a -60 dBFS stream and a stream that
+    touches both int16 rails (the byte split's extremes) meet the same relative tolerance."""
+    T = 768 * 6
+    base = slb.synth_iq(2, T).astype(np.int32)
+    weak = (base // 250).astype(np.int16)
+    loud = np.clip(base * 4, -32768, 32767).astype(np.int16)
+    loud[0, 100] = (-32768, 32767); loud[1, 101] = (32767, -32768)
+    for x in (weak, loud):
+        d = slb.DspIf(2, chain=slb.CHAIN_RX_SSB_F32)
+        y, audio, gain = run_gpu(d, x)
+        for c in range(2):
+            exp, a, _, _ = best_oracle.rx_ssb_f32(d.oracle_params(), x[c])
+            assert np.all(np.abs(audio[c] - a) <= audio_tolerance(a) + 1e-12)
+            check_int16(y[c], exp)
+
+
+def test_caller_mask_that_is_no_fir_stays_on_the_fft_kernel(best_oracle):
+    """slb_set_mask with a spectrum that is not the DFT of a 129-tap filter: the channel keeps the FFT kernel (the oracle's
+    circular convolution is reproduced, not approximated by a truncated FIR)."""
+    C, T = 9, 1536 * 3
+    x = slb.synth_iq(C, T)
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    rng = np.random.Generator(np.random.PCG64(11))
+    mask = d.mask(slb.MODE_USB).copy()
+    mask *= (1.0 + 0.05 * rng.standard_normal(mask.shape)).astype(np.float32)     # ragged pass-band: impulse response fills all 512 taps
+    d.set_mask(slb.MODE_USB, mask)
+    y, audio, gain = run_gpu(d, x)
+    prm = d.oracle_params()
+    for c in (0, 8):
+        exp, a, _, _ = best_oracle.rx_ssb_f32(prm, x[c])
+        assert np.all(np.abs(audio[c] - a) <= audio_tolerance(a) + 1e-12)
+        check_int16(y[c], exp)

@@ -8,8 +8,8 @@ mkdir -p gpurun_out
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${R}_launches.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-other > gpurun_out/${R}_launches_bench.log 2>&1
 # 2. the top kernel, full set, at the bench's own configuration (1024 ch x 480000 frames)
-ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:ssb_f32 -c 1 \
-    -o gpurun_out/${R}_rx_ssb_f32_full python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-other > gpurun_out/${R}_full_bench.log 2>&1
+ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:rx_ssb_tc -c 1 \
+    -o gpurun_out/${R}_rx_ssb_tc_full python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-other > gpurun_out/${R}_full_bench.log 2>&1
 # 3. clocks during a plain (unprofiled) bench run + the bench line itself
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap \
     --format=csv -lms 200 > gpurun_out/${R}_clocks.csv &
