@@ -237,7 +237,7 @@ def run_ours(args):
         if dist is not None:
             t = torch.tensor([dt], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
         e2e = {"value": samples_per_step * n_e2e / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": C * T * 4 * world, "d2h_bytes_per_step": C * T * 4 * world,
-               "steps": n_e2e, "path": "slb_rx_process_host: pinned host -> H2D -> rx_ssb_tc_kernel -> D2H, channel chunks (>= 1 channel per SM) on 3 streams"}
+               "steps": n_e2e, "path": "slb_rx_process_host: pinned host -> strided H2D -> rx_ssb_tc_kernel -> strided D2H, 64 MB time slices of all channels, copies and kernels on 3 streams"}
         del xh, yh, d2
 
     # the other chains of the library at the same width, device-resident, for context (not the headline metric)

@@ -68,6 +68,7 @@ struct slb_ctx
   // host bulk path
   int16_t *d_bulk_in[kBulkSlots] = {}; int16_t *d_bulk_out[kBulkSlots] = {}; size_t bulk_bytes = 0;
   cudaStream_t bulk_stream[kBulkSlots] = {}; cudaEvent_t bulk_done[kBulkSlots] = {};
+  cudaEvent_t slice_ev[kBulkSlots][3] = {};   // time-sliced SSB host path: H2D landed / kernel done / D2H done, per staging slot
 };
 
 #define CK(ctx, call)                                                                              \
@@ -231,6 +232,7 @@ void slb_destroy (slb_ctx *ctx)
     cudaFree (ctx->d_bulk_in[s]); cudaFree (ctx->d_bulk_out[s]);
     if (ctx->bulk_stream[s]) cudaStreamDestroy (ctx->bulk_stream[s]);
     if (ctx->bulk_done[s]) cudaEventDestroy (ctx->bulk_done[s]);
+    for (int e = 0; e < 3; e++) if (ctx->slice_ev[s][e]) cudaEventDestroy (ctx->slice_ev[s][e]);
   }
   if (ctx->stream) cudaStreamDestroy (ctx->stream);
   delete ctx;
@@ -868,6 +870,63 @@ static int process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, ui
 int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream) { return process_device (ctx, d_in, d_out, frames, stream, false); }
 int slb_tx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream) { return process_device (ctx, d_in, d_out, frames, stream, true); }
 
+// SSB chains through host buffers: the batch is cut in TIME. Every slice carries all channels (strided 2-D copies
+// straight from / to the caller's [channels][frames] arrays), so each launch is as wide as the batch — the tensor-core
+// kernel wants one channel group per SM — and the slices are small (~64 MB), so the copy that cannot overlap anything (the
+// first H2D, the last D2H) is a few per cent of the call. Slices of one stream depend on each other through the carried
+// state: the kernels run in order on one stream, copies on two others, three staging slots in flight.
+static int process_host_sliced (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames)
+{
+  const uint32_t C = ctx->cfg.channels;
+  // a multiple of 1536 frames = the FFT kernel's tile and two supertiles of the tensor-core kernel: both kernels give the
+  // cut stream bit for bit the result of the uncut one
+  uint32_t slice = (uint32_t) (((size_t) 64 << 20) / ((size_t) C * 4)) / 1536u * 1536u;
+  if (slice < 1536u) slice = 1536u;
+  if (slice > frames) slice = frames;
+  const size_t need = (size_t) C * slice * 4;
+  if (need > ctx->bulk_bytes || !ctx->bulk_stream[0])
+  {
+    for (int s = 0; s < kBulkSlots; s++)
+    {
+      if (ctx->bulk_stream[s]) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
+      if (need > ctx->bulk_bytes)
+      {
+        CK (ctx, cudaFree (ctx->d_bulk_in[s])); CK (ctx, cudaFree (ctx->d_bulk_out[s]));
+        ctx->d_bulk_in[s] = ctx->d_bulk_out[s] = nullptr;
+        CK (ctx, cudaMalloc (&ctx->d_bulk_in[s], need)); CK (ctx, cudaMalloc (&ctx->d_bulk_out[s], need));
+      }
+      if (!ctx->bulk_stream[s]) CK (ctx, cudaStreamCreateWithFlags (&ctx->bulk_stream[s], cudaStreamNonBlocking));
+      if (!ctx->bulk_done[s]) CK (ctx, cudaEventCreateWithFlags (&ctx->bulk_done[s], cudaEventDisableTiming));
+    }
+    if (need > ctx->bulk_bytes) ctx->bulk_bytes = need;
+  }
+  for (int s = 0; s < kBulkSlots; s++)
+    for (int e = 0; e < 3; e++)
+      if (!ctx->slice_ev[s][e]) CK (ctx, cudaEventCreateWithFlags (&ctx->slice_ev[s][e], cudaEventDisableTiming));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  cudaStream_t s_in = ctx->bulk_stream[0], s_k = ctx->bulk_stream[1], s_out = ctx->bulk_stream[2];
+  const size_t pitch = (size_t) frames * 4;
+  uint32_t n_slices = 0;
+  for (uint32_t t0 = 0; t0 < frames; t0 += slice, n_slices++)
+  {
+    const int slot = (int) (n_slices % kBulkSlots);
+    const uint32_t n = (frames - t0 < slice) ? frames - t0 : slice;
+    const size_t row = (size_t) n * 4;
+    if (n_slices >= (uint32_t) kBulkSlots) CK (ctx, cudaStreamWaitEvent (s_in, ctx->slice_ev[slot][2], 0));   // the slot's previous result has left
+    CK (ctx, cudaMemcpy2DAsync (ctx->d_bulk_in[slot], row, reinterpret_cast<const char *> (h_in) + (size_t) t0 * 4, pitch, row, C, cudaMemcpyHostToDevice, s_in));
+    CK (ctx, cudaEventRecord (ctx->slice_ev[slot][0], s_in));
+    CK (ctx, cudaStreamWaitEvent (s_k, ctx->slice_ev[slot][0], 0));
+    { const int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], 0, C, n, nullptr, nullptr, s_k); if (rc) return rc; }
+    rx_advance (ctx, n);                                       // host bookkeeping of the carried state; the launches are stream-ordered
+    CK (ctx, cudaEventRecord (ctx->slice_ev[slot][1], s_k));
+    CK (ctx, cudaStreamWaitEvent (s_out, ctx->slice_ev[slot][1], 0));
+    CK (ctx, cudaMemcpy2DAsync (reinterpret_cast<char *> (h_out) + (size_t) t0 * 4, pitch, ctx->d_bulk_out[slot], row, row, C, cudaMemcpyDeviceToHost, s_out));
+    CK (ctx, cudaEventRecord (ctx->slice_ev[slot][2], s_out));
+  }
+  for (int s = 0; s < kBulkSlots; s++) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
+  return SLB_OK;
+}
+
 static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames, bool want_tx)
 {
   if (!ctx || !h_in || !h_out || frames == 0) return SLB_ERR_ARG;
@@ -879,16 +938,10 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
   if (ctx->q15 && frames % ctx->geo.block_frames != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the 48-frame firmware block");
   const uint32_t C = ctx->cfg.channels;
   const size_t ch_bytes = (size_t) frames * 4;
+  if (chain) return process_host_sliced (ctx, h_in, h_out, frames);
   // channels are independent, so the batch is cut into channel groups and H2D / kernel / D2H of consecutive groups overlap
   uint32_t group = (uint32_t) ((size_t) (48u << 20) / ch_bytes);
   if (group < 1) group = 1;
-  if (ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32 && tc_path_enabled ())
-  {
-    // the tensor-core kernel runs one CTA per group of up to 8 channels: a chunk should bring at least one channel
-    // per SM (staging buffers capped at 1 GB each)
-    const uint32_t want = (uint32_t) ctx->sm_count, cap = (uint32_t) std::max<size_t> (1, ((size_t) 1 << 30) / ch_bytes);
-    if (group < want) group = std::min (want, std::max (group, cap));
-  }
   if (group > C) group = C;
   const size_t need = (size_t) group * ch_bytes;
   if (need > ctx->bulk_bytes)
