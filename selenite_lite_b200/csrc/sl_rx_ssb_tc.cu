@@ -54,6 +54,9 @@ constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_REGSPLIT
 #define SL_TC_REGSPLIT 0
 #endif
+#ifndef SL_TC_BULKOUT
+#define SL_TC_BULKOUT 0
+#endif
 constexpr int kSets = SL_TC_SETS;                 // epilogue warp sets (warpgroups), taking supertiles in turn
 constexpr int kRawStages = SL_TC_RAWSTAGES;            // raw stages: a bulk copy takes ~4400 clocks to land (measured), a supertile ~3000
 constexpr int kEpiWarps = 4 * kSets;
@@ -69,13 +72,14 @@ struct Smem
   static constexpr size_t b = a + 2 * 2 * kPlaneBytes;                  // tap planes of the current mask
   static constexpr size_t raw = b + kTcPlaneBytes;                      // [stages][8 rows]
   static constexpr size_t hist = raw + kRawStages * kJ * kRawRow;       // [stages][8 rows] carried tail of the previous call
-  static constexpr size_t wsum = hist + kRawStages * kJ * kHistRow;              // [sets][4 warps][8][4] floats
+  static constexpr size_t out = hist + kRawStages * kJ * kHistRow;      // [8 rows] packed int16 output of one supertile, stored by bulk copies
+  static constexpr size_t wsum = out + (SL_TC_BULKOUT ? kJ * kRawRow : 0);                    // [sets][4 warps][8][4] floats
   static constexpr size_t pk = wsum + kSets * 4 * kJ * 4 * 4;           // [sets][16][8] floats
   static constexpr size_t carry_s = pk + kSets * kQ * kJ * 4;           // [2][8][4] floats
   static constexpr size_t carry_e = carry_s + 2 * kJ * 4 * 4;           // [2][8] floats
   static constexpr size_t mp = carry_e + 2 * kJ * 4;                    // [4][20] floats: A^(48 a), rows padded to 20 (bank spread)
   static constexpr size_t bars = mp + 4 * 20 * 4;
-  static constexpr int n_bars = 22;
+  static constexpr int n_bars = 26;
   static constexpr size_t tmem_ptr = bars + n_bars * 8;
   static constexpr size_t bytes = tmem_ptr + 16;
 };
@@ -118,6 +122,10 @@ __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned b
 {
   asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                 ::"r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g (void *dst, const void *src, unsigned bytes)
+{
+  asm volatile ("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32 (src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void named_bar (int id, int threads) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
@@ -166,10 +174,22 @@ __device__ __forceinline__ void tmem_ld_wait () { asm volatile ("tcgen05.wait::l
 
 __device__ __forceinline__ uint32_t pack_lr (float x_times_32768)
 {
-  // arm_float_to_q15.c:147 : (q15_t) __SSAT((q31_t)(x * 32768.0f), 16): truncation toward zero, then saturation
+  // arm_float_to_q15.c:147 : (q15_t) __SSAT((q31_t)(x * 32768.0f), 16): truncation toward zero, then saturation.
+#ifdef SL_TC_ABLATE_CVT                                                                // (profiling aid: what the conversions cost)
+  return __float_as_uint (x_times_32768);
+#elif !defined(SL_TC_NOF2I)
   short v;
   asm ("cvt.rzi.sat.s16.f32 %0, %1;" : "=h"(v) : "f"(x_times_32768));
   return __byte_perm ((uint32_t) (uint16_t) v, 0u, 0x1010);   // stereo endpoint, L = R (usbd_audio.c:399-404)
+#else
+  // A/B alternative without the conversion pipe (-DSL_TC_NOF2I): clamp, add |v| to 1.5 * 2^23 rounding TOWARD ZERO — the
+  // sum's low mantissa bits are floor(|v|) — and restore the sign in two's complement. Exact, but 7 instructions instead of 2:
+  // measured 266 vs 291 Gsamples/s, the epilogue is bound by instruction count, not by the F2I rate.
+  const float c = fmaxf (fminf (x_times_32768, 32767.0f), -32768.0f);
+  const int m = __float_as_int (__fadd_rz (fabsf (c), 12582912.0f));
+  const int s = __float_as_int (c) >> 31;
+  return __byte_perm ((uint32_t) ((m ^ s) - s), 0u, 0x1010);   // stereo endpoint, L = R (usbd_audio.c:399-404)
+#endif
 }
 
 // y = M x (4x4 row-major, uniform M) + add
@@ -193,9 +213,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   float *sW = reinterpret_cast<float *> (smem + Smem::wsum), *sPk = reinterpret_cast<float *> (smem + Smem::pk);
   float *sCarryS = reinterpret_cast<float *> (smem + Smem::carry_s), *sCarryE = reinterpret_cast<float *> (smem + Smem::carry_e);
   float *sMp = reinterpret_cast<float *> (smem + Smem::mp);
+  unsigned char *sOut = smem + Smem::out;
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
   uint64_t *raw_full = bars, *raw_empty = bars + 3, *a_full = bars + 6, *a_empty = bars + 8, *t_empty = bars + 10;
-  uint64_t *s_bar = bars + 12, *e_bar = bars + 14, *b_full = bars + 16, *drain = bars + 17, *t_full = bars + 18;
+  uint64_t *s_bar = bars + 12, *e_bar = bars + 14, *b_full = bars + 16, *drain = bars + 17, *t_full = bars + 18, *out_free = bars + 22;
   // t_full has FOUR slots although there are two accumulator buffers: an epilogue set may start waiting for supertile
   // kk + 2 while kk is still in flight, and on a two-slot barrier that wait would alias the phase before kk's and pass at once
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *> (smem + Smem::tmem_ptr);
@@ -210,6 +231,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       mbar_init (t_full + i, 1); mbar_init (t_full + 2 + i, 1); mbar_init (t_empty + i, 4); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
     }
     mbar_init (b_full, 1); mbar_init (drain, 1);
+    for (int i = 0; i < 4; i++) mbar_init (out_free + i, 1);
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 64) sMp[(tid >> 4) * 20 + (tid & 15)] = P.tab.Mp[tid >> 4][tid & 15];
@@ -463,6 +485,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         // ---- zero-state response of the cascade over the block, per sample as arm_biquad_cascade_df2T_f32.c:551-562:
         //      y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
         float z[4] = { 0.f, 0.f, 0.f, 0.f };
+#ifdef SL_TC_ABLATE_ZS                                                              // (profiling aid: what the zero-state pass costs)
+        z[0] = y[0]; z[1] = y[1]; z[2] = y[2]; z[3] = y[3];
+#else
 #pragma unroll
         for (int n = 0; n < kBlk; n++)
         {
@@ -475,6 +500,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           z[3] = fmaf (cf[9], y1, cf[7] * y0);
           y[n] = y1;
         }
+#endif
         if (w == 0) TC_STAMP (9);
         // ---- level 1: start state of the block inside the warp (zero at the warp's first block): P_{a+1} = M48 P_a + z_a
         float Pst[4] = { 0.f, 0.f, 0.f, 0.f };
@@ -509,7 +535,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
         }
         if (w == 0) TC_STAMP (10);
-        named_bar (1 + 2 * es, 128);
+        named_bar (1 + 3 * es, 128);
         if (w == 0) TC_STAMP (11);
         // ---- level 2: state at the warp's first block, then at this block
 #pragma unroll
@@ -557,7 +583,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         if (kk != 0) mbar_wait (e_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
         envc = (k == 0) ? __ldcg (P.state + (size_t) c * 8 + 4) : sCarryE[((kk - 1) & 1) * kJ + j];
         if (w == 0) TC_STAMP (12);
-        named_bar (2 + 2 * es, 128);
+        named_bar (2 + 3 * es, 128);
         if (w == 0) TC_STAMP (13);
         // ---- AGC envelope: the oracle's sequential walk env_b = max(peak_b, fl(env_{b-1} * decay)) over the blocks before and including this one
         float e = envc;
@@ -588,16 +614,58 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
             for (int n = 0; n < kBlk; n += 4) adbg[n / 4] = make_float4 (y[n], y[n + 1], y[n + 2], y[n + 3]);
           }
           if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kBlk) + t0 / kBlk] = gain;
-          // gain (arm_scale_f32), pack (arm_float_to_q15) and store: the block is 192 contiguous bytes
+        }
+#if SL_TC_BULKOUT
+        // ---- gain (arm_scale_f32), pack (arm_float_to_q15), store through a shared-memory image of the supertile's output
+        // (8 channel rows of 3 KB) and one bulk copy per channel. Measured SLOWER than direct stores (245 vs 292 Gsamples/s:
+        // the image is one more hand-over between the two epilogue sets); kept as an A/B option.
+        {
+          if (kk != 0) mbar_wait (out_free + ((kk - 1) & 3), ((kk - 1) >> 2) & 1);   // the previous supertile's copies have read the image
           const float g15 = gain * 32768.0f;                                       // exact: power of two
-          uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + t0);
+          uint4 *dst = reinterpret_cast<uint4 *> (sOut + j * kRawRow + q * (kBlk * 4));
 #pragma unroll
           for (int n = 0; n < kBlk; n += 4)
             dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
+          asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar (3 + 3 * es, 128);
+          if (w == 0 && lane == 0)
+          {
+            const uint32_t gs = P.gstart[g], nv = gi >> 8;
+#pragma unroll 1
+            for (uint32_t jj = 0; jj < nv; jj++)
+              bulk_s2g (P.out + (size_t) P.chan[gs + jj] * P.frames + (size_t) k * kSuper, sOut + jj * kRawRow, nfr * 4u);
+            asm volatile ("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive (out_free + (kk & 3));
+          }
         }
+#else
+        // ---- gain (arm_scale_f32), pack (arm_float_to_q15) and store: the block is 192 contiguous bytes
+        if (q < nblk && jvalid)
+        {
+          const float g15 = gain * 32768.0f;                                       // exact: power of two
+          uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + (size_t) k * kSuper + (size_t) q * kBlk);
+#ifdef SL_TC_ABLATE_ST                                                              // (profiling aid: what the output stores cost)
+          if (g15 == 123.456f)
+#endif
+#pragma unroll
+          for (int n = 0; n < kBlk; n += 8)
+          {
+            // 256-bit stores (sm_100: STG.E.256): the 32 lanes of a store hit 32 different lines whatever its width, so the
+            // L1 wavefronts per block halve
+            asm volatile ("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + n / 4),
+                          "r"(pack_lr (y[n] * g15)), "r"(pack_lr (y[n + 1] * g15)), "r"(pack_lr (y[n + 2] * g15)), "r"(pack_lr (y[n + 3] * g15)),
+                          "r"(pack_lr (y[n + 4] * g15)), "r"(pack_lr (y[n + 5] * g15)), "r"(pack_lr (y[n + 6] * g15)), "r"(pack_lr (y[n + 7] * g15)) : "memory");
+          }
+        }
+#endif
         if (w == 0) TC_STAMP (14);
       }
     }
+#if SL_TC_BULKOUT
+    if (w == 0 && lane == 0) asm volatile ("cp.async.bulk.wait_group 0;" ::: "memory");   // output copies complete before the CTA retires
+    __syncwarp ();
+#endif
   }
 
   tc_fence_before ();
