@@ -282,11 +282,13 @@ uint32_t slb_ring_plan_read (uint32_t ring_frames, int is_out, uint32_t state[3]
 /* tables of the time-parallel 2-stage df2T evaluation for runs of 24 samples: Mpow[6][16] =
  * (A^24)^(2^k), Cresp[24][4] */
 int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp96);
-/* the tensor-core form of the RX-SSB-f32 filter: the 129 complex taps whose DFT the mask [512][2] is,
- * quantised to 24 bits (read back out of the tcgen05 operand planes the kernel uses), and the float value *unit of one
- * unit of the integer FIR output. Returns SLB_ERR_UNSUPPORTED when the mask is no 129-tap filter (the FFT kernel then
- * serves it). mask_default = mode byte: slb_design_mask fills the frozen default mask of that mode. */
-int slb_design_tc_taps (const float *mask_re_im, int32_t taps_re[129], int32_t taps_im[129], float *unit);
+/* the tensor-core form of the RX-SSB-f32 chain. slb_design_tc_taps: the 129 complex taps whose DFT the mask
+ * [512][2] is (SLB_ERR_UNSUPPORTED when the mask is no 129-tap filter: the FFT kernel then serves it).
+ * slb_design_tc_block: builds the kernel's tcgen05 operand planes (taps composed with the zero-state response of the 2-stage
+ * biquad, 24-bit digits) and evaluates them in integers on one raw window int16[176][2] = 128 frames of history + one
+ * 48-frame block: out52[0..47] = the block's biquad output from a zero state, out52[48..51] = the biquad state after it. */
+int slb_design_tc_taps (const float *mask_re_im, double taps_re[129], double taps_im[129]);
+int slb_design_tc_block (const float *mask_re_im, const float coef10[10], const int16_t *window, double out52[52]);
 int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im);
 /* tables of the tensor-core kernel's time-parallel biquad for blocks of 48 samples: Mp[4][16] = A^(48 k), M192[16], Cresp[48][4] */
 int slb_biquad_tc_tables (const float coef10[10], float *Mp64, float *M192, float *Cresp192);

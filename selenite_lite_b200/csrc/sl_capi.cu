@@ -42,7 +42,7 @@ struct slb_ctx
   // device: chain constants + carried state
   float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
   // tensor-core path of the RX-SSB-f32 chain (sl_rx_ssb_tc.cu): tap planes per mask slot, which slots it can serve
-  uint8_t *d_planes = nullptr; bool tc_ok[SLB_MAX_MASKS] = {}; float tc_s0[SLB_MAX_MASKS] = {}; TcBiquadTables tc_tables{};
+  uint8_t *d_planes = nullptr; bool tc_ok[SLB_MAX_MASKS] = {}; float tc_s0[SLB_MAX_MASKS] = {}; float tc_sz[SLB_MAX_MASKS] = {}; TcBiquadTables tc_tables{};
   // channel lists of the tensor-core launches, cached per channel range (the bulk paths cut the batch the same way every
   // call) and rebuilt when a mode or a mask changes (mode_version)
   struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
@@ -118,7 +118,7 @@ static int upload_chain_constants (slb_ctx *ctx)
   {
     std::vector<uint8_t> planes ((size_t) SLB_MAX_MASKS * kTcPlaneBytes, 0);
     for (int m = 0; m < SLB_MAX_MASKS; m++)
-      ctx->tc_ok[m] = N == 512 && m != kAmMaskSlot && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m]);
+      ctx->tc_ok[m] = N == 512 && m != kAmMaskSlot && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, ctx->rx.biquad, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m], &ctx->tc_sz[m]);
     CK (ctx, cudaMemcpyAsync (ctx->d_planes, planes.data (), planes.size (), cudaMemcpyHostToDevice, ctx->stream));
   }
   CK (ctx, cudaStreamSynchronize (ctx->stream));
@@ -484,7 +484,7 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
     L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
     L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
     L.gstart = tl.d; L.ginfo = tl.d + G; L.chan = tl.d + 2 * (size_t) G;
-    L.planes = ctx->d_planes; L.s0 = ctx->tc_s0;
+    L.planes = ctx->d_planes; L.s0 = ctx->tc_s0; L.sz = ctx->tc_sz;
     L.flag_final = ctx->flag_base + rx_ssb_f32_tiles (frames);
     L.n_groups = G; L.frames = frames;
     L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;
@@ -805,24 +805,18 @@ int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp9
   return SLB_OK;
 }
 
-int slb_design_tc_taps (const float *mask_re_im, int32_t taps_re[129], int32_t taps_im[129], float *unit)
+int slb_design_tc_taps (const float *mask_re_im, double taps_re[129], double taps_im[129])
 {
-  if (!mask_re_im || !taps_re || !taps_im || !unit) return SLB_ERR_ARG;
+  if (!mask_re_im || !taps_re || !taps_im) return SLB_ERR_ARG;
+  return tc_design_taps (mask_re_im, taps_re, taps_im) ? SLB_OK : SLB_ERR_UNSUPPORTED;
+}
+int slb_design_tc_block (const float *mask_re_im, const float coef10[10], const int16_t *window, double out52[52])
+{
+  if (!mask_re_im || !coef10 || !window || !out52) return SLB_ERR_ARG;
   std::vector<uint8_t> planes (kTcPlaneBytes);
-  if (!tc_build_planes (mask_re_im, planes.data (), unit)) return SLB_ERR_UNSUPPORTED;
-  // read the taps back out of the operand layout: output n = 0 of the block meets tap d at window frame 128 - d
-  for (int d = 0; d < kTcTaps; d++)
-    for (int rail = 0; rail < 2; rail++)
-    {
-      const int m = 2 * (128 - d) + rail, ks = m / 32, kk = m % 32;
-      int32_t v = 0;
-      for (int g = 0; g < 3; g++)
-      {
-        const int row = g * 48;
-        v = v * 256 + (int8_t) planes[(size_t) ks * 18 * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)];
-      }
-      if (rail) taps_im[d] = -v; else taps_re[d] = v;
-    }
+  float ua = 0.f, uz = 0.f;
+  if (!tc_build_planes (mask_re_im, coef10, planes.data (), &ua, &uz)) return SLB_ERR_UNSUPPORTED;
+  tc_apply_planes (planes.data (), ua, uz, window, out52);
   return SLB_OK;
 }
 int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im)

@@ -219,18 +219,14 @@ void design_biquad_tc_tables (const float *cf, TcBiquadTables *t)
 }
 
 // The mask of a mode is the DFT of a filter of fft_len - hop + 1 = 129 taps, so overlap-save with it IS a 129-tap FIR.
-// Recover the taps (inverse DFT in double, 1/N as arm_cfft_f32.c:604-614), quantise them to 24 bits and lay them out
-// as the B operand of tcgen05.mma kind::i8: for k-step ks and window byte m = 32 ks + kk (frame m / 2 counted from
-// 128 frames before the block, rail m & 1), output n of the block takes tap d = 128 + n - m / 2:
-//   Re y[n] = sum_d hr[d] I[n - d] - hi[d] Q[n - d]   ->   B[n][m] = rail ? -hi[d] : hr[d]
-// split into three balanced base-256 digits (rows digit * 48 + n), K-major no-swizzle core matrices of 8 rows x 16 bytes.
-bool tc_build_planes (const float *mask, uint8_t *planes, float *s0)
+// Recover the taps (inverse DFT in double, 1/N as arm_cfft_f32.c:604-614); false when the impulse response does not fit.
+bool tc_design_taps (const float *mask, double *hr /* kTcTaps */, double *hi)
 {
   const int N = 512;
   const double two_pi = 6.283185307179586476925286766559;
-  std::vector<double> cs (N), sn (N), hr (N), hi (N);
+  std::vector<double> cs (N), sn (N);
   for (int i = 0; i < N; i++) { cs[i] = std::cos (two_pi * i / N); sn[i] = std::sin (two_pi * i / N); }
-  double main_e = 0, tail_e = 0, mx = 0;
+  double main_e = 0, tail_e = 0;
   for (int d = 0; d < N; d++)
   {
     double ar = 0, ai = 0;
@@ -240,41 +236,104 @@ bool tc_build_planes (const float *mask, uint8_t *planes, float *s0)
       const double Hr = mask[2 * k], Hi = mask[2 * k + 1];
       ar += Hr * cs[ph] - Hi * sn[ph]; ai += Hr * sn[ph] + Hi * cs[ph];
     }
-    hr[d] = ar / N; hi[d] = ai / N;
-    const double e = hr[d] * hr[d] + hi[d] * hi[d];
-    if (d < kTcTaps) { main_e += e; mx = std::fmax (mx, std::fmax (std::fabs (hr[d]), std::fabs (hi[d]))); } else tail_e += e;
+    ar /= N; ai /= N;
+    if (d < kTcTaps) { hr[d] = ar; hi[d] = ai; main_e += ar * ar + ai * ai; } else tail_e += ar * ar + ai * ai;
   }
-  if (!(main_e > 0.0) || !std::isfinite (main_e) || tail_e > 1e-13 * main_e) return false;
-  const double lim = 8323071.0;                      // 2^23 - 2^16 - 1: the top balanced digit stays inside int8
-  // scale: the largest tap takes the full 24 bits. The float unit of the integer output is fixed first and the tap
-  // scale derived from it, so that unit * 32768 * scale == 1 holds exactly for the float32 value the kernel multiplies by.
-  const float unit = (float) (mx / (lim * 32768.0));
-  if (!(unit > 0.0f) || !std::isfinite (unit) || unit < 1e-30f) return false;
-  const double scale = 1.0 / ((double) unit * 32768.0);
-  std::vector<int32_t> qr (kTcTaps), qi (kTcTaps);
-  for (int d = 0; d < kTcTaps; d++)
+  return main_e > 0.0 && std::isfinite (main_e) && tail_e <= 1e-13 * main_e;
+}
+
+// B operand of the tensor-core kernel. Per firmware block (48 outputs, zero biquad state at the block start) everything up
+// to and including the biquad's zero-state response is ONE linear map of the 176-frame raw window:
+//   FIR        y[m]  = sum_d hr[d] I[m-d] - hi[d] Q[m-d]                  (m = 0..47 inside the block)
+//   audio      a[n]  = sum_{m<=n} g[n-m] y[m]      g = impulse response of the 2-stage df2T cascade (zero state)
+//   end state  z_i   = sum_m sigma_i[47-m] y[m]    sigma[t] = cascade state t samples after a unit impulse
+// so the taps operand holds W = G T (48 audio rows) and Z = Sigma T (4 state rows) instead of the bare Toeplitz T: the
+// tensor cores deliver the block's zero-state audio and end state, the CUDA cores only chain the states and add the
+// zero-input response (arm_biquad_cascade_df2T_f32.c:551-562 is linear, so the split is exact). Rows are quantised to 24
+// bits (audio and state rows with their own scale), three balanced base-256 digits, rows digit * 64 + r (r < 48 audio,
+// 48..51 state, rest zero), K-major no-swizzle core matrices; window byte m = 32 ks + kk = frame m / 2, rail m & 1.
+bool tc_build_planes (const float *mask, const float *cf, uint8_t *planes, float *unit_a, float *unit_z)
+{
+  double hr[kTcTaps], hi[kTcTaps];
+  if (!tc_design_taps (mask, hr, hi)) return false;
+  // cascade impulse response and state trajectory, in double
+  double g[48], sig[48][4];
   {
-    qr[d] = (int32_t) std::llround (hr[d] * scale); qi[d] = (int32_t) std::llround (hi[d] * scale);
-    if (std::abs (qr[d]) > (int32_t) lim + 1 || std::abs (qi[d]) > (int32_t) lim + 1) return false;
+    double st[4] = { 0, 0, 0, 0 };
+    for (int t = 0; t < 48; t++)
+    {
+      const double x = (t == 0) ? 1.0 : 0.0;
+      const double y0 = (double) cf[0] * x + st[0];
+      const double n0 = ((double) cf[1] * x + (double) cf[3] * y0) + st[1], n1 = (double) cf[2] * x + (double) cf[4] * y0;
+      const double y1 = (double) cf[5] * y0 + st[2];
+      const double n2 = ((double) cf[6] * y0 + (double) cf[8] * y1) + st[3], n3 = (double) cf[7] * y0 + (double) cf[9] * y1;
+      st[0] = n0; st[1] = n1; st[2] = n2; st[3] = n3;
+      g[t] = y1;
+      for (int i = 0; i < 4; i++) sig[t][i] = st[i];
+    }
   }
-  *s0 = unit;                                        // 1/32768 of arm_q15_to_float.c:87 folded in
+  // rows x window (176 frames x 2 rails)
+  const int R = 52, F = 176;
+  std::vector<double> W ((size_t) R * F * 2, 0.0);
+  for (int f = 0; f < F; f++)
+    for (int m = 0; m < 48; m++)
+    {
+      const int d = 128 + m - f;
+      if (d < 0 || d >= kTcTaps) continue;
+      const double tI = hr[d], tQ = -hi[d];
+      for (int n = m; n < 48; n++) { W[((size_t) n * F + f) * 2] += g[n - m] * tI; W[((size_t) n * F + f) * 2 + 1] += g[n - m] * tQ; }
+      for (int i = 0; i < 4; i++) { W[((size_t) (48 + i) * F + f) * 2] += sig[47 - m][i] * tI; W[((size_t) (48 + i) * F + f) * 2 + 1] += sig[47 - m][i] * tQ; }
+    }
+  double mx_a = 0, mx_z = 0;
+  for (int r = 0; r < R; r++) for (int k = 0; k < F * 2; k++) { double &mx = (r < 48) ? mx_a : mx_z; mx = std::fmax (mx, std::fabs (W[(size_t) r * F * 2 + k])); }
+  const double lim = 8323071.0;                      // 2^23 - 2^16 - 1: the top balanced digit stays inside int8
+  // scale: the largest entry takes the full 24 bits. The float unit of the integer output is fixed first and the scale
+  // derived from it, so that unit * 32768 * scale == 1 holds exactly for the float32 value the kernel multiplies by
+  // (the 1/32768 of arm_q15_to_float.c:87 is folded in).
+  const float ua = (float) (mx_a / (lim * 32768.0)), uz = (float) (mx_z / (lim * 32768.0));
+  if (!(ua > 1e-30f) || !std::isfinite (ua) || !(uz > 1e-30f) || !std::isfinite (uz)) return false;
+  const double sc_a = 1.0 / ((double) ua * 32768.0), sc_z = 1.0 / ((double) uz * 32768.0);
+  *unit_a = ua; *unit_z = uz;
   std::memset (planes, 0, kTcPlaneBytes);
-  for (int ks = 0; ks < 11; ks++)
-    for (int n = 0; n < 48; n++)
-      for (int kk = 0; kk < 32; kk++)
+  for (int r = 0; r < R; r++)
+    for (int m = 0; m < F * 2; m++)
+    {
+      const long long q = std::llround (W[(size_t) r * F * 2 + m] * (r < 48 ? sc_a : sc_z));
+      if (q == 0) continue;
+      if (std::llabs (q) > (long long) lim + 1) return false;
+      const int32_t h = (int32_t) q;
+      const int32_t l0 = ((h + 128) & 255) - 128, r1 = (h - l0) >> 8, l1 = ((r1 + 128) & 255) - 128, l2 = (r1 - l1) >> 8;
+      const int32_t dg[3] = { l2, l1, l0 };          // most significant first: accumulator columns 0..63 carry 2^24
+      const int ks = m / 32, kk = m % 32;
+      for (int gdig = 0; gdig < 3; gdig++)
       {
-        const int m = 32 * ks + kk, f = m / 2, rail = m & 1, d = 128 + n - f;
-        if (d < 0 || d >= kTcTaps) continue;
-        const int32_t h = rail ? -qi[d] : qr[d];
-        const int32_t l0 = ((h + 128) & 255) - 128, r1 = (h - l0) >> 8, l1 = ((r1 + 128) & 255) - 128, l2 = (r1 - l1) >> 8;
-        const int32_t dg[3] = { l2, l1, l0 };          // most significant first: accumulator columns 0..47 carry 2^24
-        for (int g = 0; g < 3; g++)
-        {
-          const int row = g * 48 + n;
-          planes[(size_t) ks * 18 * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)] = (uint8_t) (int8_t) dg[g];
-        }
+        const int row = gdig * 64 + r;
+        planes[(size_t) ks * kTcRowGroups * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)] = (uint8_t) (int8_t) dg[gdig];
       }
+    }
   return true;
+}
+
+// host-side evaluation of the planes on one raw window (design check, tests/test_tc_math.py): exactly the integer
+// contraction the kernel runs, out[0..47] = zero-state audio of the block, out[48..51] = its end state
+void tc_apply_planes (const uint8_t *planes, float unit_a, float unit_z, const int16_t *window /* [176][2] */, double *out52)
+{
+  for (int r = 0; r < 52; r++)
+  {
+    long long acc = 0;
+    for (int m = 0; m < 352; m++)
+    {
+      const int ks = m / 32, kk = m % 32;
+      long long h = 0;
+      for (int gdig = 0; gdig < 3; gdig++)
+      {
+        const int row = gdig * 64 + r;
+        h = h * 256 + (int8_t) planes[(size_t) ks * kTcRowGroups * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)];
+      }
+      acc += h * (long long) window[m];
+    }
+    out52[r] = (double) acc * (double) (r < 48 ? unit_a : unit_z);
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------------

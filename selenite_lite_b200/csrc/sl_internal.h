@@ -102,7 +102,8 @@ constexpr size_t kTwiddleFloats = 6 * 32 * 4;
 // is (the mask is the DFT of a 129-tap filter), evaluated by tcgen05.mma kind::i8 on byte planes of samples and taps ----
 constexpr int kTcTaps = 129;                       // fft_len - hop + 1
 constexpr int kTcChannels = 8;                     // channels of one group = the 8 rows of a shared-memory core matrix
-constexpr size_t kTcPlaneBytes = 11 * 18 * 256;    // Toeplitz tap planes of one mask: [k-step][digit*48+n][32 bytes] in UMMA layout
+constexpr int kTcRowGroups = 24;                   // 3 digits x 64 rows (48 audio + 4 state + pad) / 8
+constexpr size_t kTcPlaneBytes = 11 * kTcRowGroups * 256;   // operand planes of one mask: [k-step][digit*64+row][32 bytes] in UMMA layout
 struct TcBiquadTables
 {
   float coef[10];                       // stage 0 {b0,b1,b2,a1,a2}, stage 1 {...}
@@ -111,9 +112,13 @@ struct TcBiquadTables
   float Cresp[48][4];                   // zero-input response of the cascade output at sample n of a block per unit state
 };
 void design_biquad_tc_tables (const float *coef10, TcBiquadTables *t);
-// taps = IDFT of the (unscaled) mask in double; returns false when the impulse response does not fit 129 taps (then the
-// FFT kernel serves the slot). *s0 = 2^-(e+15): the float value of one unit of the integer FIR output.
-bool tc_build_planes (const float *mask_re_im /* [512][2] */, uint8_t *planes /* kTcPlaneBytes */, float *s0);
+// taps = IDFT of the (unscaled) mask in double; false when the impulse response does not fit 129 taps (then the FFT kernel
+// serves the slot)
+bool tc_design_taps (const float *mask_re_im /* [512][2] */, double *hr /* kTcTaps */, double *hi);
+// operand planes: FIR taps composed with the zero-state response of the 2-stage biquad (coef10), see sl_design.cpp.
+// *unit_a / *unit_z: the float value of one unit of the integer audio / state outputs
+bool tc_build_planes (const float *mask_re_im, const float *coef10, uint8_t *planes /* kTcPlaneBytes */, float *unit_a, float *unit_z);
+void tc_apply_planes (const uint8_t *planes, float unit_a, float unit_z, const int16_t *window /* [176][2] */, double *out52);
 struct RxTcLaunch
 {
   const int16_t *in; int16_t *out;         // [C][T][2]
@@ -124,7 +129,7 @@ struct RxTcLaunch
   const uint32_t *gstart;                  // [n_groups] index of the group's first channel in chan[]
   const uint32_t *ginfo;                   // [n_groups] mask slot | channels in the group (1..8) << 8
   const uint8_t *planes;                   // [SLB_MAX_MASKS][kTcPlaneBytes]
-  const float *s0;                         // host, [SLB_MAX_MASKS]
+  const float *s0, *sz;                    // host, [SLB_MAX_MASKS]: units of the audio / state outputs
   unsigned flag_final;
   uint32_t n_groups, frames;
   float agc_target, agc_decay, agc_floor, agc_gmax;

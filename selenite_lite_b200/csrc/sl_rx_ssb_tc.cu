@@ -42,7 +42,8 @@ constexpr int kChunksHist = kHist / 8;   // 16
 constexpr int kChunksNew = kSuper / 8;   // 96
 constexpr int kPlaneBytes = (kChunksHist + kChunksNew) * kChunkBytes;   // 14336
 constexpr int kKSteps = 11;              // (128 + 48) frames * 2 bytes / 32
-constexpr int kBStep = 18 * 256;         // B bytes per K-step: 18 row groups (3 digits x 48 outputs) x 2 chunks x 128 B
+constexpr int kBStep = kTcRowGroups * 256; // B bytes per K-step: 24 row groups (3 digits x 64 rows: 48 audio + 4 state + pad) x 2 chunks x 128 B
+constexpr int kDig = 64;                 // accumulator columns per digit weight
 constexpr int kRawRow = kSuper * 4 + 16; // raw stage row (one channel), padded: conflict-free 16-byte reads across channels
 constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_SETS
@@ -64,7 +65,7 @@ constexpr int kConvWarps = 2;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);   // 16 warps = 4 warpgroups: 3 epilogue sets + {2 converters, MMA issuer, producer}
 static_assert (!SL_TC_REGSPLIT || kThreads == 512, "register split below assumes 4 warpgroups");
-constexpr int kTmemCols = 512;           // two accumulator buffers of 192 columns at 0 and 256
+constexpr int kTmemCols = 512;           // two accumulator buffers of 256 columns
 
 struct Smem
 {
@@ -92,7 +93,7 @@ struct KParams
   float *state; unsigned *flag;
   const uint32_t *chan; const uint32_t *gstart; const uint32_t *ginfo;
   const uint8_t *planes;
-  float s0[SLB_MAX_MASKS];
+  float s0[SLB_MAX_MASKS], sz[SLB_MAX_MASKS];
   long long *trace;                            // profiling aid (SELENITE_B200_TC_TRACE): [supertile][16] clock64 stamps of CTA 0
   unsigned flag_final;
   uint32_t n_groups, frames, supers;
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // The whole warp walks the loop converged and ONE elected lane issues: with `if (lane == 0)` around the loop the
     // compiler cannot keep descriptors in uniform registers and wraps every tcgen05.mma in a vote / broadcast loop —
     // measured 128 clocks of issue per MMA against 72 of execution (N = 144), i.e. the tensor pipe sat idle 2/3 of the time.
-    constexpr uint32_t id_ss48 = umma_idesc (48, 1, 1), id_ss96 = umma_idesc (96, 1, 1), id_ss144 = umma_idesc (144, 1, 1), id_us144 = umma_idesc (144, 0, 1);
+    constexpr uint32_t id_ss64 = umma_idesc (64, 1, 1), id_ss128 = umma_idesc (128, 1, 1), id_ss192 = umma_idesc (192, 1, 1), id_us192 = umma_idesc (192, 0, 1);
     const uint32_t aBase = smem_u32 (sA), bBase = smem_u32 (sB);
     // constant upper halves of the descriptors: LBO = 128 (A and B), SBO = 768 (A, aliased row groups) / 256 (B), version 1
     constexpr uint64_t kDescA = ((uint64_t) (kChunkBytes >> 4) << 16) | ((uint64_t) ((6 * kChunkBytes) >> 4) << 32) | (1ull << 46);
@@ -409,19 +410,20 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4), b0 = bBase >> 4;
         if (elect_one ())
         {
-          // accumulator columns: [0,48) weight 2^24 = xh h2, [48,96) 2^16 = xh h1 + xl h2, [96,144) 2^8 = xh h0 + xl h1, [144,192) 1 = xl h0.
+          // accumulator columns: [0,64) weight 2^24 = xh h2, [64,128) 2^16 = xh h1 + xl h2, [128,192) 2^8 = xh h0 + xl h1, [192,256) 1 = xl h0;
+          // inside each group of 64: 48 audio outputs, 4 end-state outputs, padding.
           // (Tried: two independent chains, xh * [h2|h1|h0] and xl * [h2|h1|h0] in disjoint columns, added in the epilogue. No faster —
           // an SS-mode MMA with M = 128 is bound by the fetch of its 4 KB A tile, ~128 clocks whatever N <= 192 is
           // (tools/microbench/umma_rate.cu) — and it costs the second accumulator buffer.)
-          umma_i8 (d, kDescA | aHi, kDescB | b0, id_ss48, 0u);                                   // xh * h2          -> [0,48)   fresh
-          umma_i8 (d + 48, kDescA | aLo, kDescB | b0, id_us144, 0u);                             // xl * [h2|h1|h0]  -> [48,192) fresh
-          umma_i8 (d + 48, kDescA | aHi, kDescB | (b0 + ((6 * 256) >> 4)), id_ss96, 1u);         // xh * [h1|h0]     -> [48,144) accumulate
+          umma_i8 (d, kDescA | aHi, kDescB | b0, id_ss64, 0u);                                   // xh * h2          -> [0,64)    fresh
+          umma_i8 (d + kDig, kDescA | aLo, kDescB | b0, id_us192, 0u);                           // xl * [h2|h1|h0]  -> [64,256)  fresh
+          umma_i8 (d + kDig, kDescA | aHi, kDescB | (b0 + ((8 * 256) >> 4)), id_ss128, 1u);      // xh * [h1|h0]     -> [64,192)  accumulate
 #pragma unroll
           for (int ks = 1; ks < kKSteps; ks++)
           {
             const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStep) >> 4;
-            umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss144, 1u);
-            umma_i8 (d + 48, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us144, 1u);
+            umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss192, 1u);
+            umma_i8 (d + kDig, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us192, 1u);
           }
           umma_commit (t_full + (kk & 3));  // accumulators complete -> epilogue
           umma_commit (a_empty + ab);       // planes read -> converter may overwrite them
@@ -448,7 +450,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       const uint32_t gi = P.ginfo[g];
       const bool jvalid = (uint32_t) j < (gi >> 8);
       const uint32_t c = P.chan[P.gstart[g] + min ((uint32_t) j, (gi >> 8) - 1u)];
-      const float s0 = P.s0[gi & 0xFFu], s8 = s0 * 256.0f, s16 = s0 * 65536.0f, s24 = s0 * 16777216.0f;
+      const float s0 = P.s0[gi & 0xFFu], s8 = s0 * 256.0f, s16 = s0 * 65536.0f, s24 = s0 * 16777216.0f, z0s = P.sz[gi & 0xFFu];
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         if ((int) (kk % kSets) != es) continue;
@@ -470,37 +472,30 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         for (int i = 0; i < kBlk / kW; i++)
         {
           uint32_t v0[kW], v1[kW], v2[kW], v3[kW];
-          if (kW == 16) { tmem_ld16 (taddr + kW * i, v0); tmem_ld16 (taddr + 48 + kW * i, v1); tmem_ld16 (taddr + 96 + kW * i, v2); tmem_ld16 (taddr + 144 + kW * i, v3); }
-          else { tmem_ld8 (taddr + kW * i, v0); tmem_ld8 (taddr + 48 + kW * i, v1); tmem_ld8 (taddr + 96 + kW * i, v2); tmem_ld8 (taddr + 144 + kW * i, v3); }
+          if (kW == 16) { tmem_ld16 (taddr + kW * i, v0); tmem_ld16 (taddr + kDig + kW * i, v1); tmem_ld16 (taddr + 2 * kDig + kW * i, v2); tmem_ld16 (taddr + 3 * kDig + kW * i, v3); }
+          else { tmem_ld8 (taddr + kW * i, v0); tmem_ld8 (taddr + kDig + kW * i, v1); tmem_ld8 (taddr + 2 * kDig + kW * i, v2); tmem_ld8 (taddr + 3 * kDig + kW * i, v3); }
           tmem_ld_wait ();
 #pragma unroll
           for (int n = 0; n < kW; n++)
             y[kW * i + n] = fmaf (__int2float_rn ((int) v0[n]), s24, fmaf (__int2float_rn ((int) v1[n]), s16, fmaf (__int2float_rn ((int) v2[n]), s8, __int2float_rn ((int) v3[n]) * s0)));
+        }
+        float z[4];
+        {
+          uint32_t v0[8], v1[8], v2[8], v3[8];
+          tmem_ld8 (taddr + 48, v0); tmem_ld8 (taddr + kDig + 48, v1); tmem_ld8 (taddr + 2 * kDig + 48, v2); tmem_ld8 (taddr + 3 * kDig + 48, v3);
+          tmem_ld_wait ();
+          const float z8 = z0s * 256.0f, z16 = z0s * 65536.0f, z24 = z0s * 16777216.0f;
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+            z[r] = fmaf (__int2float_rn ((int) v0[r]), z24, fmaf (__int2float_rn ((int) v1[r]), z16, fmaf (__int2float_rn ((int) v2[r]), z8, __int2float_rn ((int) v3[r]) * z0s)));
         }
         tc_fence_before ();
         __syncwarp ();
         if (lane == 0) mbar_arrive (t_empty + tb);                               // the accumulator buffer now lives in registers
         if (w == 0) TC_STAMP (8);
 
-        // ---- zero-state response of the cascade over the block, per sample as arm_biquad_cascade_df2T_f32.c:551-562:
-        //      y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
-        float z[4] = { 0.f, 0.f, 0.f, 0.f };
-#ifdef SL_TC_ABLATE_ZS                                                              // (profiling aid: what the zero-state pass costs)
-        z[0] = y[0]; z[1] = y[1]; z[2] = y[2]; z[3] = y[3];
-#else
-#pragma unroll
-        for (int n = 0; n < kBlk; n++)
-        {
-          const float x = y[n];
-          const float y0 = fmaf (cf[0], x, z[0]);
-          z[0] = fmaf (cf[3], y0, fmaf (cf[1], x, z[1]));
-          z[1] = fmaf (cf[4], y0, cf[2] * x);
-          const float y1 = fmaf (cf[5], y0, z[2]);
-          z[2] = fmaf (cf[8], y1, fmaf (cf[6], y0, z[3]));
-          z[3] = fmaf (cf[9], y1, cf[7] * y0);
-          y[n] = y1;
-        }
-#endif
+        // (y[] already IS the zero-state response of the biquad cascade over the block — the operand planes hold the FIR
+        //  composed with it — and columns 48..51 of each digit group hold the cascade's end state from a zero start)
         if (w == 0) TC_STAMP (9);
         // ---- level 1: start state of the block inside the warp (zero at the warp's first block): P_{a+1} = M48 P_a + z_a
         float Pst[4] = { 0.f, 0.f, 0.f, 0.f };
@@ -691,7 +686,7 @@ int launch_rx_ssb_tc (const RxTcLaunch &L, int sm_count, void *stream_)
   P.audio_dbg = L.audio_dbg; P.gain_dbg = L.gain_dbg;
   P.ovl_in = reinterpret_cast<const uint32_t *> (L.ovl_in); P.ovl_out = reinterpret_cast<uint32_t *> (L.ovl_out);
   P.state = L.state; P.flag = L.flag; P.chan = L.chan; P.gstart = L.gstart; P.ginfo = L.ginfo; P.planes = L.planes;
-  for (int i = 0; i < SLB_MAX_MASKS; i++) P.s0[i] = L.s0[i];
+  for (int i = 0; i < SLB_MAX_MASKS; i++) { P.s0[i] = L.s0[i]; P.sz[i] = L.sz[i]; }
   P.flag_final = L.flag_final; P.n_groups = L.n_groups; P.frames = L.frames; P.supers = (L.frames + kSuper - 1) / kSuper;
   P.agc_target = L.agc_target; P.agc_decay = L.agc_decay; P.agc_floor = L.agc_floor; P.agc_gmax = L.agc_gmax;
   P.tab = *L.tables;

@@ -1,6 +1,7 @@
 """Host-side logic of the tensor-core RX-SSB-f32 kernel (sl_rx_ssb_tc.cu), checked on the CPU:
- * the 24-bit FIR taps recovered from the tcgen05 operand planes reproduce the overlap-save FFT filter of the oracle
-   chain (arm_cfft_f32 / arm_cmplx_mult_cmplx_f32 / inverse, restated here in float64 numpy) far inside 1e-5;
+ * the 129 taps recovered from a mask reproduce the overlap-save FFT filter of the oracle chain (arm_cfft_f32 /
+   arm_cmplx_mult_cmplx_f32 / inverse, restated here in float64 numpy), and the tcgen05 operand planes built from them
+   (taps composed with the biquad's zero-state response, 24-bit digits) reproduce FIR + biquad far inside 1e-5;
  * a mask that is not the DFT of a 129-tap filter is refused (the FFT kernel keeps serving it);
  * the kernel's time-parallel biquad (zero-state blocks of 48, warp-local walk with A^48, cross-warp walk with A^192,
    zero-input correction) restated in numpy equals the sequential arm_biquad_cascade_df2T_f32 restatement."""
@@ -14,37 +15,73 @@ from selenite_lite_b200 import _lib
 
 
 def tc_taps(mask):
-    hr = np.zeros(129, np.int32); hi = np.zeros(129, np.int32); unit = C.c_float(0)
-    rc = _lib.load().slb_design_tc_taps(mask.ctypes.data, hr.ctypes.data, hi.ctypes.data, C.byref(unit))
-    return rc, hr, hi, unit.value
+    hr = np.zeros(129, np.float64); hi = np.zeros(129, np.float64)
+    rc = _lib.load().slb_design_tc_taps(mask.ctypes.data, hr.ctypes.data, hi.ctypes.data)
+    return rc, hr, hi
+
+
+def default_mask(mode):
+    mask = np.zeros((512, 2), np.float32)
+    assert _lib.load().slb_design_mask(48000, mode, mask.ctypes.data) == 0
+    return mask
+
+
+def biquad_zero_state_f64(coef, x):
+    """arm_biquad_cascade_df2T_f32.c:551-562 in float64, two stages, zero start: output and end state {d1_0,d2_0,d1_1,d2_1}."""
+    c = [float(v) for v in coef]
+    d = [0.0, 0.0, 0.0, 0.0]; y = np.zeros(len(x))
+    for n, xn in enumerate(x):
+        y0 = c[0] * xn + d[0]; d[0] = (c[1] * xn + c[3] * y0) + d[1]; d[1] = c[2] * xn + c[4] * y0
+        y1 = c[5] * y0 + d[2]; d[2] = (c[6] * y0 + c[8] * y1) + d[3]; d[3] = c[7] * y0 + c[9] * y1
+        y[n] = y1
+    return y, np.array(d)
 
 
 @pytest.mark.parametrize("mode", [slb.MODE_USB, slb.MODE_LSB, slb.MODE_CW, slb.MODE_CWR, slb.MODE_DIG])
-def test_integer_fir_equals_overlap_save(mode, rng):
-    mask = np.zeros((512, 2), np.float32)
-    assert _lib.load().slb_design_mask(48000, mode, mask.ctypes.data) == 0
-    rc, hr, hi, unit = tc_taps(mask)
-    assert rc == 0 and 8323000 <= max(np.abs(hr).max(), np.abs(hi).max()) <= 8323072    # the largest tap uses the full 24 bits
+def test_fir_taps_equal_overlap_save(mode, rng):
+    mask = default_mask(mode)
+    rc, hr, hi = tc_taps(mask)
+    assert rc == 0
     T = 384 * 6
     x = rng.integers(-20000, 20000, (T + 128, 2)).astype(np.int16)  # 128 frames of history + the stream
     # oracle filter in float64: 512-point frames hopping by 384, keep the last 384 (1/32768 of arm_q15_to_float folded in)
     H = mask[:, 0].astype(np.float64) + 1j * mask[:, 1].astype(np.float64)
     z = (x[:, 0].astype(np.float64) + 1j * x[:, 1].astype(np.float64)) / 32768.0
     ref = np.concatenate([np.fft.ifft(np.fft.fft(z[f:f + 512]) * H)[128:] for f in range(0, T, 384)]).real
-    # the kernel's form: exact integer FIR, one float scale
-    acc = np.zeros(T, np.int64)
+    got = np.zeros(T)
     for d in range(129):
-        seg = x[128 - d:128 - d + T].astype(np.int64)
-        acc += int(hr[d]) * seg[:, 0] - int(hi[d]) * seg[:, 1]
-    got = acc.astype(np.float64) * unit
-    # white full-band input is the worst case (95 % of its power is rejected): the 2^-24 tap quantisation and the float32
-    # rounding of the mask itself both scale with the INPUT level; measured <= 6e-7 of the output rms, bound 1e-6
-    assert np.max(np.abs(got - ref)) < 1e-6 * np.sqrt(np.mean(ref ** 2))
+        seg = x[128 - d:128 - d + T].astype(np.float64) / 32768.0
+        got += hr[d] * seg[:, 0] - hi[d] * seg[:, 1]
+    # what is left is the part of the mask's impulse response beyond 129 taps (float32 rounding of the mask): ~1e-7 of the INPUT
+    assert np.max(np.abs(got - ref)) < 3e-7 * np.sqrt(np.mean(ref ** 2))
+
+
+@pytest.mark.parametrize("mode", [slb.MODE_USB, slb.MODE_CWR, slb.MODE_DIG])
+def test_operand_planes_equal_fir_plus_biquad(mode, rng):
+    """The kernel's tcgen05 operand planes (taps composed with the biquad's zero-state response, 24-bit digits, UMMA layout),
+    evaluated in integers on raw windows, against the float64 FIR followed by the float64 df2T cascade: audio and end state."""
+    mask = default_mask(mode)
+    rc, hr, hi = tc_taps(mask)
+    coef = np.array(slb.default_rx_f32_params(48000).biquad[:10], np.float32)
+    lib = _lib.load()
+    for trial in range(3):
+        amp = (20000, 300, 32767)[trial]                                  # loud, weak, and rail-to-rail samples
+        w = rng.integers(-amp, amp + 1, (176, 2)).astype(np.int16)
+        if trial == 2:
+            w[::7] = (32767, -32768); w[3::11] = (-32768, 32767)
+        out = np.zeros(52, np.float64)
+        assert lib.slb_design_tc_block(mask.ctypes.data, coef.ctypes.data, w.ctypes.data, out.ctypes.data) == 0
+        xs = w.astype(np.float64) / 32768.0
+        y = np.array([sum(hr[d] * xs[128 + m - d, 0] - hi[d] * xs[128 + m - d, 1] for d in range(129)) for m in range(48)])
+        a, st = biquad_zero_state_f64(coef, y)
+        scale = np.sqrt(np.mean(xs ** 2))                                # 24-bit quantisation error scales with the INPUT level
+        assert np.max(np.abs(out[:48] - a)) < 2e-7 * scale, (trial, np.max(np.abs(out[:48] - a)) / scale)
+        assert np.max(np.abs(out[48:] - st)) < 2e-7 * scale * max(1.0, np.max(np.abs(st)) / max(np.max(np.abs(a)), 1e-12)), trial
 
 
 def test_non_fir_mask_is_refused(rng):
     mask = rng.standard_normal((512, 2)).astype(np.float32)
-    assert tc_taps(mask)[0] == slb.ERR_UNSUPPORTED if hasattr(slb, "ERR_UNSUPPORTED") else tc_taps(mask)[0] != 0
+    assert tc_taps(mask)[0] != 0
     assert tc_taps(np.zeros((512, 2), np.float32))[0] != 0
 
 
