@@ -50,13 +50,16 @@ constexpr int kHistRow = kHist * 4 + 16;
 #define SL_TC_SETS 2
 #endif
 #ifndef SL_TC_RAWSTAGES
-#define SL_TC_RAWSTAGES 3
+#define SL_TC_RAWSTAGES 2
 #endif
 #ifndef SL_TC_REGSPLIT
 #define SL_TC_REGSPLIT 0
 #endif
 #ifndef SL_TC_BULKOUT
 #define SL_TC_BULKOUT 0
+#endif
+#ifndef SL_TC_STHINT
+#define SL_TC_STHINT ".L1::no_allocate"   /* measured: plain 366, .cg 371, .cs 376, .L1::no_allocate 408 Gsamples/s */
 #endif
 constexpr int kSets = SL_TC_SETS;                 // epilogue warp sets (warpgroups), taking supertiles in turn
 constexpr int kRawStages = SL_TC_RAWSTAGES;            // raw stages: a bulk copy takes ~4400 clocks to land (measured), a supertile ~3000
@@ -65,6 +68,8 @@ constexpr int kConvWarps = 2;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);   // 16 warps = 4 warpgroups: 3 epilogue sets + {2 converters, MMA issuer, producer}
 static_assert (!SL_TC_REGSPLIT || kThreads == 512, "register split below assumes 4 warpgroups");
+constexpr int kOutRow = 4 * kBlk * 4 + 16;  // output stage of one epilogue warp: a channel's four blocks (768 B) + pad, ...
+constexpr int kOutStage = 4 * kOutRow;     // ... four channels at a time
 constexpr int kTmemCols = 512;           // two accumulator buffers of 256 columns
 
 struct Smem
@@ -74,7 +79,7 @@ struct Smem
   static constexpr size_t raw = b + kTcPlaneBytes;                      // [stages][8 rows]
   static constexpr size_t hist = raw + kRawStages * kJ * kRawRow;       // [stages][8 rows] carried tail of the previous call
   static constexpr size_t out = hist + kRawStages * kJ * kHistRow;      // [8 rows] packed int16 output of one supertile, stored by bulk copies
-  static constexpr size_t wsum = out + (SL_TC_BULKOUT ? kJ * kRawRow : 0);                    // [sets][4 warps][8][4] floats
+  static constexpr size_t wsum = out + (SL_TC_BULKOUT ? kEpiWarps * kOutStage : 0);                    // [sets][4 warps][8][4] floats
   static constexpr size_t pk = wsum + kSets * 4 * kJ * 4 * 4;           // [sets][16][8] floats
   static constexpr size_t carry_s = pk + kSets * kQ * kJ * 4;           // [2][8][4] floats
   static constexpr size_t carry_e = carry_s + 2 * kJ * 4 * 4;           // [2][8] floats
@@ -611,27 +616,41 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kBlk) + t0 / kBlk] = gain;
         }
 #if SL_TC_BULKOUT
-        // ---- gain (arm_scale_f32), pack (arm_float_to_q15), store through a shared-memory image of the supertile's output
-        // (8 channel rows of 3 KB) and one bulk copy per channel. Measured SLOWER than direct stores (245 vs 292 Gsamples/s:
-        // the image is one more hand-over between the two epilogue sets); kept as an A/B option.
+        // ---- gain (arm_scale_f32), pack (arm_float_to_q15), store. A warp holds 4 consecutive blocks of 8 channels = 768
+        // contiguous bytes per channel, but as direct stores every instruction touches 32 different lines (32 L1 wavefronts; the
+        // output stores alone were 30 % of the kernel, ablation in profiles/r01_summary.md). The warp lays its blocks into a
+        // private shared-memory stage (conflict-free 16-byte stores, 4 wavefronts each) and one lane sends 768-byte bulk
+        // copies, four channels per round. No other warp is involved.
         {
-          if (kk != 0) mbar_wait (out_free + ((kk - 1) & 3), ((kk - 1) >> 2) & 1);   // the previous supertile's copies have read the image
           const float g15 = gain * 32768.0f;                                       // exact: power of two
-          uint4 *dst = reinterpret_cast<uint4 *> (sOut + j * kRawRow + q * (kBlk * 4));
+          unsigned char *stage = sOut + warp * kOutStage;
+          const uint32_t gs = P.gstart[g], nv = gi >> 8;
 #pragma unroll
-          for (int n = 0; n < kBlk; n += 4)
-            dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
-          asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
-          named_bar (3 + 3 * es, 128);
-          if (w == 0 && lane == 0)
+          for (int r = 0; r < 2; r++)
           {
-            const uint32_t gs = P.gstart[g], nv = gi >> 8;
+            if (lane == 0) asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stage's previous copies have been read
+            __syncwarp ();
+            if ((j >> 2) == r)
+            {
+              uint4 *dst = reinterpret_cast<uint4 *> (stage + (j & 3) * kOutRow + a * (kBlk * 4));
+#pragma unroll
+              for (int n = 0; n < kBlk; n += 4)
+                dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
+            }
+            asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp ();
+            if (lane == 0)
+            {
+              // blocks of this warp that exist in a half supertile at the end of a stream: 4 w .. min (4 w + 3, nblk - 1)
+              const int nb = min (4, nblk - 4 * w);
+              if (nb > 0)
+              {
 #pragma unroll 1
-            for (uint32_t jj = 0; jj < nv; jj++)
-              bulk_s2g (P.out + (size_t) P.chan[gs + jj] * P.frames + (size_t) k * kSuper, sOut + jj * kRawRow, nfr * 4u);
-            asm volatile ("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_arrive (out_free + (kk & 3));
+                for (uint32_t jj = 4u * r; jj < min (4u * r + 4u, nv); jj++)
+                  bulk_s2g (P.out + (size_t) P.chan[gs + jj] * P.frames + (size_t) k * kSuper + (size_t) (4 * w) * kBlk, stage + (jj & 3) * kOutRow, (unsigned) nb * kBlk * 4u);
+              }
+              asm volatile ("cp.async.bulk.commit_group;" ::: "memory");
+            }
           }
         }
 #else
@@ -639,7 +658,11 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         if (q < nblk && jvalid)
         {
           const float g15 = gain * 32768.0f;                                       // exact: power of two
+#ifdef SL_TC_ABLATE_STADDR                                                          // (profiling aid: the same stores, but to one L2-resident block per thread)
+          uint4 *dst = reinterpret_cast<uint4 *> (P.out + ((size_t) blockIdx.x * kThreads + tid) * kBlk);
+#else
           uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + (size_t) k * kSuper + (size_t) q * kBlk);
+#endif
 #ifdef SL_TC_ABLATE_ST                                                              // (profiling aid: what the output stores cost)
           if (g15 == 123.456f)
 #endif
@@ -647,8 +670,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           for (int n = 0; n < kBlk; n += 8)
           {
             // 256-bit stores (sm_100: STG.E.256): the 32 lanes of a store hit 32 different lines whatever its width, so the
-            // L1 wavefronts per block halve
-            asm volatile ("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + n / 4),
+            // L1 wavefronts per block halve; and the lines must not allocate in L1 — the shared-memory / L1 data pipe is what the
+            // tensor core fetches its operands through, and the MMAs are the critical path
+            asm volatile ("st.global" SL_TC_STHINT ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + n / 4),
                           "r"(pack_lr (y[n] * g15)), "r"(pack_lr (y[n + 1] * g15)), "r"(pack_lr (y[n + 2] * g15)), "r"(pack_lr (y[n + 3] * g15)),
                           "r"(pack_lr (y[n + 4] * g15)), "r"(pack_lr (y[n + 5] * g15)), "r"(pack_lr (y[n + 6] * g15)), "r"(pack_lr (y[n + 7] * g15)) : "memory");
           }
@@ -658,7 +682,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       }
     }
 #if SL_TC_BULKOUT
-    if (w == 0 && lane == 0) asm volatile ("cp.async.bulk.wait_group 0;" ::: "memory");   // output copies complete before the CTA retires
+    if (lane == 0) asm volatile ("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's output copies complete before the CTA retires
     __syncwarp ();
 #endif
   }
