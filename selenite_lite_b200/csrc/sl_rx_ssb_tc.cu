@@ -1,24 +1,29 @@
 // RX-SSB-f32 on the 5th-generation tensor cores (tcgen05 + TMEM), one kernel, every sample crosses HBM once.
 //
 // The oracle chain filters by overlap-save: arm_q15_to_float -> arm_cfft_f32(512) -> arm_cmplx_mult_cmplx_f32 with the
-// mode's mask -> arm_cfft_f32 inverse -> keep 384. The mask is the DFT of a 129-tap complex filter, so
-// this IS the linear convolution  Re y[n] = sum_{d=0..128} hr[d] I[n-d] - hi[d] Q[n-d]  of int16 samples with fixed taps:
-// a dense contraction with a Toeplitz matrix of taps — the case the north-star reserves the tensor cores for. It is
-// evaluated EXACTLY in integers:  x = 256 xh + xl (signed high byte, unsigned low byte),  h = 2^16 h2 + 2^8 h1 + h0
-// (24-bit taps, balanced signed digits), all six digit products by tcgen05.mma kind::i8 into four int32 TMEM accumulators
-// by weight (2^24, 2^16, 2^8, 1). The only deviation from infinite precision is the 2^-24 quantisation of the taps; the
-// float32 FFTs of the oracle are two orders noisier (tolerance: DESIGN.md §3.5).
+// mode's mask -> arm_cfft_f32 inverse -> keep 384, then arm_biquad_cascade_df2T_f32. The mask is the DFT
+// of a 129-tap complex filter, so the first part IS the linear convolution
+//   Re y[n] = sum_{d=0..128} hr[d] I[n-d] - hi[d] Q[n-d]
+// of int16 samples with fixed taps, and the biquad is linear: inside one firmware block of 48 samples its output is
+// (zero-state response to the block's y) + (zero-input response of the state at the block start). Everything up to and
+// including the zero-state response, and the block's end state from a zero start, is ONE fixed linear map of the 176-frame
+// raw window — a dense contraction, the case the north-star reserves the tensor cores for. It is evaluated in integers:
+// x = 256 xh + xl (signed high byte, unsigned low byte), map entries quantised to 24 bits as three balanced base-256
+// digits, all six digit products by tcgen05.mma kind::i8 into four int32 TMEM accumulators by weight (2^24, 2^16, 2^8, 1).
+// No product is dropped: the only deviation from infinite precision is the 2^-24 quantisation of the map, of the order
+// of one float32 epsilon of the INPUT level like the oracle's own FFT noise (tolerances: DESIGN.md §3.5).
 //
 //   MMA shape: M = 128 rows = 8 channels (the 8 rows of a core matrix) x 16 consecutive firmware blocks (row groups),
-//   N = 48 outputs of a block x 3 tap digits, K = 32 bytes = 16 frames (I, Q bytes) per instruction, 11 K-steps cover the
-//   128 + 48 frame window. The A operand is the byte plane of the channel group's samples, ONCE: row group q is the
-//   same plane 48 frames (6 sixteen-byte chunks) further on, so the descriptor's row-group stride (SBO = 768 B) makes the
-//   16 row groups alias one contiguous buffer — no Toeplitz expansion of the data, only of the (constant) taps.
+//   N = 64 outputs of a block (48 audio + 4 end-state + pad) x 3 digits, K = 32 bytes = 16 frames (I, Q bytes) per
+//   instruction, 11 K-steps cover the 128 + 48 frame window. The A operand is the byte plane of the channel group's samples,
+//   ONCE: row group q is the same plane 48 frames (6 sixteen-byte chunks) further on, so the descriptor's row-group stride
+//   (SBO = 768 B) makes the 16 row groups alias one contiguous buffer — no Toeplitz expansion of the data, only of the
+//   (constant) map. An SS-mode MMA is bound by the fetch of its A tile (~128 clocks for N <= 192), so N = 192 is free.
 //
-//   Roles (warps): 2 x 4 epilogue warps (TMEM lane = (block q, channel j): int32 -> float, time-parallel 2-stage df2T
-//   biquad over the 16 blocks, AGC envelope walk, gain, float -> q15, 192-byte stores), 1 converter warp (raw int16 ->
-//   byte planes, PRMT only), 1 MMA issuer (one thread, 23 tcgen05.mma per supertile), 1 bulk-copy producer. mbarrier
-//   pipelines: raw stage (2), A planes (2), TMEM accumulators (2), biquad / envelope carry between consecutive supertiles.
+//   Roles (warps): 2 x 4 epilogue warps (TMEM lane = (block q, channel j): int32 -> float, chain the 16 block end states,
+//   add the zero-input response, AGC envelope walk, gain, float -> q15, 192-byte stores), 2 converter warps (raw int16 ->
+//   byte planes, PRMT only), 1 MMA issuer (one elected lane, 23 tcgen05.mma per supertile), 1 bulk-copy producer.
+//   mbarrier pipelines: raw stages, A planes (2), TMEM accumulators (2), biquad / envelope carry between supertiles.
 //
 // Oracle stage per box as in sl_rx_ssb_f32.cu; the chain sits where the firmware would call it (Core/Src/dsp_if.c:286-289).
 #include <cuda_runtime.h>
