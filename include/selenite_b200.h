@@ -249,6 +249,9 @@ int slb_st_max_q15 (slb_ctx *ctx, const int16_t *src, uint32_t n, uint32_t block
 int slb_st_rms_q15 (slb_ctx *ctx, const int16_t *src, uint32_t n, uint32_t block, int16_t *out, void *stream);
 /* batched arm_cfft_f32 (bit-reversed output order is not offered): data [channels][count][2*N] floats, in place */
 int slb_st_cfft_f32 (slb_ctx *ctx, float *data, uint32_t N, uint32_t count, int ifft, void *stream);
+/* batched arm_rfft_fast_f32 (arm_rfft_fast_f32.c:288): in / out [channels][count][N] floats, out of place, N = 32..4096;
+ * forward output packed as the reference packs it: out[0] = X[0], out[1] = X[N/2], then (Re, Im) of X[1..N/2-1] */
+int slb_st_rfft_fast_f32 (slb_ctx *ctx, const float *in, float *out, uint32_t N, uint32_t count, int ifft, void *stream);
 
 /* ---- host stream feeder: the stand-in for HAL DMA + UAC1 that replays the firmware's cadence ----
  * One tick = 1 ms = fs/1000 frames per channel, in this order (the I2S completion callback, dsp_if.c:50-67, then the two

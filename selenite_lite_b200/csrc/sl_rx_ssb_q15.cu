@@ -64,6 +64,11 @@ struct KParams
   int32_t target, floor_; uint32_t gmax;
 };
 
+// output stores that do not allocate in L1 (every lane of a fragment store hits its own line)
+__device__ __forceinline__ void st_na_u32 (uint32_t *p, uint32_t v)
+{
+  asm volatile ("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared (p); }
 __device__ __forceinline__ void mbar_init (uint64_t *bar, unsigned count)
 {
@@ -280,8 +285,8 @@ __global__ void __launch_bounds__ (kThreads, 4) rx_ssb_q15_kernel (const __grid_
           {
             const size_t t = t0 + (i >> 1) * 16 + (i & 1) * 8 + g;               // MMA block i >> 1, row g + 8 (i & 1)
             const int y0 = sat16 ((aud0[i] * m0) >> (15 - sh0)), y1 = sat16 ((aud1[i] * m1) >> (15 - sh1));
-            if (ok0) P.out[(size_t) ch_o0 * P.frames + t] = __byte_perm ((uint32_t) y0, 0u, 0x1010);   // L = R
-            if (ok1) P.out[(size_t) ch_o1 * P.frames + t] = __byte_perm ((uint32_t) y1, 0u, 0x1010);
+            if (ok0) st_na_u32 (P.out + (size_t) ch_o0 * P.frames + t, __byte_perm ((uint32_t) y0, 0u, 0x1010));   // L = R
+            if (ok1) st_na_u32 (P.out + (size_t) ch_o1 * P.frames + t, __byte_perm ((uint32_t) y1, 0u, 0x1010));
             if (P.audio_dbg)
             {
               if (ok0) P.audio_dbg[(size_t) ch_o0 * P.frames + t] = (int16_t) aud0[i];

@@ -340,6 +340,70 @@ __global__ void cfft_f32_kernel (float2 *__restrict__ data, int N, int log2n, in
   for (int i = threadIdx.x; i < N; i += blockDim.x) { float2 v = a[i]; x[i] = make_float2 (v.x * sc, inverse ? -v.y * sc : v.y); }
 }
 
+// =====================================================================================================================
+// batched real FFT, N = 32..4096 (arm_rfft_fast_f32.c:288-315 contract). Forward: the N reals are transformed as N/2
+// complex points (arm_cfft_f32 of half length) and split (stage_rfft_f32, :38-141): out[0] = X[0], out[1] = X[N/2] (both
+// real), then (Re, Im) of X[1..N/2-1]. Inverse: merge (merge_rfft_f32, :143-227) then the half-length inverse transform,
+// so that rfft followed by rifft returns the input. One CTA per transform, everything in shared memory.
+// =====================================================================================================================
+__global__ void rfft_fast_f32_kernel (const float *__restrict__ in, float *__restrict__ out, int N, int log2m, int inverse)
+{
+  extern __shared__ float2 sm[];
+  const int M = N / 2;
+  float2 *a = sm, *b = sm + M;
+  const float *x = in + (size_t) blockIdx.x * N;
+  float *y = out + (size_t) blockIdx.x * N;
+  if (!inverse)
+    for (int i = threadIdx.x; i < M; i += blockDim.x) a[i] = make_float2 (x[2 * i], x[2 * i + 1]);
+  else
+  {
+    // Zm[k] = 0.5 [(X[k] + conj X[M-k]) + j e^{+2 pi j k / N} (X[k] - conj X[M-k])], conjugated for the forward engine below
+    for (int k = threadIdx.x; k < M; k += blockDim.x)
+    {
+      const float2 xk = (k == 0) ? make_float2 (x[0], 0.f) : make_float2 (x[2 * k], x[2 * k + 1]);
+      const float2 xm = (k == 0) ? make_float2 (x[1], 0.f) : make_float2 (x[2 * (M - k)], x[2 * (M - k) + 1]);
+      const float sr = xk.x + xm.x, si = xk.y - xm.y, dr = xk.x - xm.x, di = xk.y + xm.y;   // X[k] +/- conj X[M-k]
+      float sn, cs; sincospif (2.0f * (float) k / (float) N, &sn, &cs);
+      // j e^{j t} (dr + j di) = (-sn dr - cs di) + j (cs dr - sn di)
+      const float zr = 0.5f * (sr + (-sn * dr - cs * di)), zi = 0.5f * (si + (cs * dr - sn * di));
+      a[k] = make_float2 (zr, -zi);
+    }
+  }
+  __syncthreads ();
+  for (int s = 0, ns = 1; s < log2m; s++, ns <<= 1)
+  {
+    for (int j = threadIdx.x; j < M / 2; j += blockDim.x)
+    {
+      const int k = j & (ns - 1);
+      float sn, cs; sincospif (-(float) k / (float) ns, &sn, &cs);
+      const float2 u = a[j], t = a[j + M / 2];
+      const float2 w = make_float2 (t.x * cs - t.y * sn, t.x * sn + t.y * cs);
+      const int o = ((j - k) << 1) + k;
+      b[o] = make_float2 (u.x + w.x, u.y + w.y); b[o + ns] = make_float2 (u.x - w.x, u.y - w.y);
+    }
+    __syncthreads ();
+    float2 *t = a; a = b; b = t;
+  }
+  if (inverse)
+  {
+    const float sc = 1.0f / (float) M;                 // arm_cfft_f32.c:604-614
+    for (int i = threadIdx.x; i < M; i += blockDim.x) { y[2 * i] = a[i].x * sc; y[2 * i + 1] = -a[i].y * sc; }
+  }
+  else
+  {
+    // X[k] = 0.5 (Z[k] + conj Z[M-k]) - 0.5 j e^{-2 pi j k / N} (Z[k] - conj Z[M-k])
+    for (int k = threadIdx.x; k < M; k += blockDim.x)
+    {
+      if (k == 0) { y[0] = a[0].x + a[0].y; y[1] = a[0].x - a[0].y; continue; }
+      const float2 zk = a[k], zm = a[M - k];
+      const float sr = zk.x + zm.x, si = zk.y - zm.y, dr = zk.x - zm.x, di = zk.y + zm.y;
+      float sn, cs; sincospif (-2.0f * (float) k / (float) N, &sn, &cs);
+      // -j e^{j t} (dr + j di) = (sn dr + cs di) + j (sn di - cs dr)
+      y[2 * k] = 0.5f * (sr + (sn * dr + cs * di)); y[2 * k + 1] = 0.5f * (si + (sn * di - cs * dr));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // host helpers
 // ---------------------------------------------------------------------------------------------------------------------
@@ -506,6 +570,19 @@ int slb_st_cfft_f32 (slb_ctx *ctx, float *data, uint32_t N, uint32_t count, int 
   if (smem > 48 * 1024) cudaFuncSetAttribute (cfft_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
   const unsigned threads = N / 2 < 256 ? N / 2 : 256;
   cfft_f32_kernel<<<(unsigned) (C * count), threads, smem, st>>> ((float2 *) data, (int) N, lg, ifft ? 1 : 0);
+  ST_END (ctx, (int) cudaGetLastError ());
+}
+
+// ---- batched real FFT: in [channels][count][N] floats -> out [channels][count][N] floats (packed as arm_rfft_fast_f32)
+int slb_st_rfft_fast_f32 (slb_ctx *ctx, const float *in, float *out, uint32_t N, uint32_t count, int ifft, void *stream)
+{
+  ST_BEGIN (ctx);
+  int lg = 0; while ((1u << lg) < N) lg++;
+  if (!in || !out || in == out || N < 32 || N > 4096 || (1u << lg) != N) return ctx_fail (ctx, SLB_ERR_ARG, "N must be a power of two in 32..4096, out of place (arm_rfft_fast_f32.c:288)");
+  const size_t smem = (size_t) N * sizeof (float2);
+  if (smem > 48 * 1024) cudaFuncSetAttribute (rfft_fast_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  const unsigned threads = N / 4 < 256 ? N / 4 : 256;
+  rfft_fast_f32_kernel<<<(unsigned) (C * count), threads, smem, st>>> (in, out, (int) N, lg - 1, ifft ? 1 : 0);
   ST_END (ctx, (int) cudaGetLastError ());
 }
 

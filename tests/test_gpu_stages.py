@@ -210,3 +210,23 @@ def test_batched_cfft(ctx, best_oracle, rng, nfft):
                 exp = best_oracle.cfft_f32(x[c, k], ifft, 1)
                 rms = np.sqrt(np.mean(exp.astype(np.float64) ** 2))
                 assert np.max(np.abs(got[c, k] - exp)) <= 3e-6 * rms, (nfft, ifft)
+
+
+@pytest.mark.parametrize("nfft", [32, 128, 512, 2048, 4096])
+def test_batched_rfft_fast(ctx, best_oracle, rng, nfft):
+    """arm_rfft_fast_f32: forward packing (X[0], X[N/2], then Re/Im pairs) and the inverse, tolerance class of the float FFTs."""
+    cnt = 2
+    x = f32(rng, C, cnt, nfft)
+    out = torch.zeros((C, cnt, nfft), dtype=torch.float32, device="cuda")
+    ctx.st("rfft_fast_f32", dev(x), out, nfft, cnt, 0)
+    spec = out.cpu().numpy()
+    back = torch.zeros_like(out)
+    ctx.st("rfft_fast_f32", out, back, nfft, cnt, 1)
+    back = back.cpu().numpy()
+    for c in range(C):
+        for k in range(cnt):
+            exp = best_oracle.rfft_fast_f32(x[c, k], 0)
+            rms = np.sqrt(np.mean(exp.astype(np.float64) ** 2))
+            assert np.max(np.abs(spec[c, k] - exp)) <= 3e-6 * rms, nfft
+            exp_b = best_oracle.rfft_fast_f32(exp, 1)
+            assert np.max(np.abs(back[c, k] - exp_b)) <= 3e-6 * np.sqrt(np.mean(exp_b.astype(np.float64) ** 2)), nfft
