@@ -125,3 +125,57 @@ def test_caller_mask_that_is_no_fir_stays_on_the_fft_kernel(best_oracle):
         exp, a, _, _ = best_oracle.rx_ssb_f32(prm, x[c])
         assert np.all(np.abs(audio[c] - a) <= audio_tolerance(a) + 1e-12)
         check_int16(y[c], exp)
+
+
+def test_several_groups_per_cta_and_mask_reloads(best_oracle):
+    """More channel groups than CTAs (what 8192 channels per GPU, BASELINE config 5, look like): a CTA walks several groups
+    back to back — pipelines and carry barriers run on across the group boundary, the carried state is re-read at every
+    group start — and reloads the operand planes when the next group has another mask. Forced here with a 3-CTA grid
+    (SELENITE_B200_TC_GRID, a profiling knob of the launcher) so that a few channels suffice; also 2048 channels on the
+    full grid against single-mode contexts."""
+    import os
+    C, T = 44, 768 * 3 + 384
+    modes = [slb.MODE_USB, slb.MODE_LSB, slb.MODE_DIG, slb.MODE_USB, slb.MODE_CW]
+    f_in = {slb.MODE_USB: 1000.0, slb.MODE_LSB: -1200.0, slb.MODE_CW: 700.0, slb.MODE_DIG: 2000.0}
+    x = np.concatenate([slb.synth_iq(1, T, f0=abs(f_in[modes[c % 5]]) + 2 * c, sideband=1 if f_in[modes[c % 5]] > 0 else -1, first_channel=c) for c in range(C)])
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    for c in range(C):
+        d.DSP_Set_Mode(modes[c % 5], channel=c)
+    full = run_gpu(d, x, want_audio=False)[0]
+    os.environ["SELENITE_B200_TC_GRID"] = "3"
+    try:
+        d3 = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+        for c in range(C):
+            d3.DSP_Set_Mode(modes[c % 5], channel=c)
+        y3, audio, gain = run_gpu(d3, x)
+        # two calls: the state written at the end of every group is picked up again
+        d3b = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+        for c in range(C):
+            d3b.DSP_Set_Mode(modes[c % 5], channel=c)
+        xd = torch.from_numpy(x).cuda()
+        y3b = np.concatenate([d3b.rx_process(xd[:, :768].contiguous()).cpu().numpy(), d3b.rx_process(xd[:, 768:].contiguous()).cpu().numpy()], axis=1)
+    finally:
+        del os.environ["SELENITE_B200_TC_GRID"]
+    assert np.array_equal(y3, full) and np.array_equal(y3b, full)
+    for c in range(0, C, 5):
+        exp, a, _, _ = best_oracle.rx_ssb_f32(d.oracle_params(modes[c % 5]), x[c])
+        assert np.all(np.abs(audio[c] - a) <= audio_tolerance(a) + 1e-12), c
+        check_int16(full[c], exp)
+    # full grid, more groups than SMs: 2048 channels = 256 groups of 8, two masks interleaved in blocks of 100 channels
+    C2, T2 = 2048, 768 * 2
+    base = slb.synth_iq(8, T2)
+    x2 = np.ascontiguousarray(base[np.arange(C2) % 8])
+    lsb = (np.arange(C2) // 100) % 2 == 1
+    x2[lsb, :, 1] = -x2[lsb, :, 1]
+    d2 = slb.DspIf(C2, chain=slb.CHAIN_RX_SSB_F32)
+    for c in np.nonzero(lsb)[0]:
+        d2.DSP_Set_Mode(slb.MODE_LSB, channel=int(c))
+    y2 = run_gpu(d2, x2, want_audio=False)[0]
+    for m, sel in ((slb.MODE_USB, ~lsb), (slb.MODE_LSB, lsb)):
+        ds = slb.DspIf(8, chain=slb.CHAIN_RX_SSB_F32); ds.DSP_Set_Mode(m)
+        xs = base.copy()
+        if m == slb.MODE_LSB:
+            xs[:, :, 1] = -xs[:, :, 1]
+        ys = run_gpu(ds, xs, want_audio=False)[0]
+        idx = np.nonzero(sel)[0]
+        assert np.array_equal(y2[idx], ys[idx % 8]), m
