@@ -224,7 +224,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   float *sW = reinterpret_cast<float *> (smem + Smem::wsum), *sPk = reinterpret_cast<float *> (smem + Smem::pk);
   float *sCarryS = reinterpret_cast<float *> (smem + Smem::carry_s), *sCarryE = reinterpret_cast<float *> (smem + Smem::carry_e);
   float *sMp = reinterpret_cast<float *> (smem + Smem::mp);
+#if SL_TC_BULKOUT
   unsigned char *sOut = smem + Smem::out;
+#endif
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
   uint64_t *raw_full = bars, *raw_empty = bars + 3, *a_full = bars + 6, *a_empty = bars + 8, *t_empty = bars + 10;
   uint64_t *s_bar = bars + 12, *e_bar = bars + 14, *b_full = bars + 16, *drain = bars + 17, *t_full = bars + 18, *out_free = bars + 22;
@@ -452,7 +454,6 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // TMEM lane = 32 w + lane = 8 q + j: thread (q, j) owns firmware block q of channel j of the supertile.
     const int es = warp >> 2, w = warp & 3, a = lane >> 3, j = lane & 7, q = 4 * w + a;
     float *myW = sW + es * (4 * kJ * 4), *myPk = sPk + es * (kQ * kJ);
-    const float *cf = P.tab.coef;
     const float decay = P.agc_decay;
     unsigned kk = 0;
     for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
