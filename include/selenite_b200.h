@@ -296,6 +296,12 @@ int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im);
 /* tables of the tensor-core kernel's time-parallel biquad for blocks of 48 samples: Mp[4][16] = A^(48 k), M192[16], Cresp[48][4] */
 int slb_biquad_tc_tables (const float coef10[10], float *Mp64, float *M192, float *Cresp192);
 
+/* ---- spectrum export (the north-star's "gather spectra"): power spectrum of N frames per channel,
+ * d_iq int16 [channels][N][2] -> d_power float [channels][N] (natural bin order, bin k = k fs / N, upper half = negative
+ * frequencies), as arm_q15_to_float -> arm_cfft_f32 (N = 16..4096) -> arm_cmplx_mag_squared_f32. Device pointers, async;
+ * gathering the shards' spectra over NCCL is selenite_lite_b200/shard.py::gather_spectra. */
+int slb_rx_spectrum_device (slb_ctx *ctx, const int16_t *d_iq, float *d_power, uint32_t N, void *stream);
+
 /* ---- accounting ---- */
 uint64_t slb_kernel_launches (const slb_ctx *ctx);   /* kernels this context has launched since create */
 int slb_sync (slb_ctx *ctx);

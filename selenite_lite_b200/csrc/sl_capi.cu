@@ -805,6 +805,17 @@ int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp9
   return SLB_OK;
 }
 
+int slb_rx_spectrum_device (slb_ctx *ctx, const int16_t *d_iq, float *d_power, uint32_t N, void *stream)
+{
+  if (!ctx || !d_iq || !d_power) return SLB_ERR_ARG;
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  float *tmp = static_cast<float *> (sl::ctx_scratch (ctx, (size_t) ctx->cfg.channels * 2 * N * sizeof (float)));
+  if (!tmp) return SLB_ERR_CUDA;
+  int rc = slb_st_q15_to_float (ctx, d_iq, tmp, 2 * N, stream);                 // arm_q15_to_float.c:65
+  if (!rc) rc = slb_st_cfft_f32 (ctx, tmp, N, 1, 0, stream);                      // arm_cfft_f32.c:562, forward
+  if (!rc) rc = slb_st_cmplx_mag_squared_f32 (ctx, tmp, d_power, N, stream);      // arm_cmplx_mag_squared_f32.c:70
+  return rc;
+}
 int slb_design_tc_taps (const float *mask_re_im, double taps_re[129], double taps_im[129])
 {
   if (!mask_re_im || !taps_re || !taps_im) return SLB_ERR_ARG;

@@ -315,6 +315,17 @@ class DspIf:
         self._ck(self.lib.slb_rx_process_host(self.h, x_pinned.data_ptr(), out_pinned.data_ptr(), frames), "rx_process_host")
         return out_pinned
 
+    def spectrum(self, x, out=None, stream=None):
+        """Power spectrum of x = int16 [channels][N][2] (CUDA tensor): float32 [channels][N], natural bin order."""
+        import torch
+        assert x.is_cuda and x.is_contiguous() and x.dtype == torch.int16
+        n = x.shape[1]
+        if out is None:
+            out = torch.empty((x.shape[0], n), dtype=torch.float32, device=x.device)
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        self._ck(self.lib.slb_rx_spectrum_device(self.h, x.data_ptr(), out.data_ptr(), n, st), "rx_spectrum_device")
+        return out
+
     def set_debug_taps(self, audio=None, gain=None):
         self._keep_taps = (audio, gain)
         self._ck(self.lib.slb_rx_set_debug_taps(self.h, audio.data_ptr() if audio is not None else None,

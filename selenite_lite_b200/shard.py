@@ -30,3 +30,18 @@ def gather_audio(local_out, channels, group=None):
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
     return torch.cat([parts[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)], 0).view(torch.int16)
+
+
+def gather_spectra(local_power, channels, group=None):
+    """Optional gather of the shards' power spectra (slb_rx_spectrum_device): local_power is this rank's [hi-lo][N] float32
+    tensor; returns [channels][N] on every rank (NCCL all-gather over NVLink on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    sizes = [shard_range(channels, r, world) for r in range(world)]
+    biggest = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((biggest,) + tuple(local_power.shape[1:]), dtype=local_power.dtype, device=local_power.device)
+    pad[:local_power.shape[0]] = local_power
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([parts[r][:hi - lo] for r, (lo, hi) in enumerate(sizes)], 0)

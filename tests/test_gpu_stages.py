@@ -230,3 +230,18 @@ def test_batched_rfft_fast(ctx, best_oracle, rng, nfft):
             assert np.max(np.abs(spec[c, k] - exp)) <= 3e-6 * rms, nfft
             exp_b = best_oracle.rfft_fast_f32(exp, 1)
             assert np.max(np.abs(back[c, k] - exp_b)) <= 3e-6 * np.sqrt(np.mean(exp_b.astype(np.float64) ** 2)), nfft
+
+
+@pytest.mark.parametrize("nfft", [64, 1024])
+def test_spectrum_export(best_oracle, rng, nfft):
+    """slb_rx_spectrum_device = arm_q15_to_float -> arm_cfft_f32 -> arm_cmplx_mag_squared_f32 per channel."""
+    Cs = 5
+    x = slb.synth_iq(Cs, nfft)
+    d = slb.DspIf(Cs, chain=slb.CHAIN_RX_SSB_F32)
+    got = d.spectrum(torch.from_numpy(x).cuda()).cpu().numpy()
+    o = best_oracle
+    for c in range(Cs):
+        f = o.q15_to_float(x[c].reshape(-1))
+        exp = o.cmplx_mag_squared_f32(o.cfft_f32(f, 0, 1))
+        assert np.max(np.abs(got[c] - exp)) <= 1e-5 * np.max(exp), (nfft, c)
+    assert int(np.argmax(got[0])) == int(round(slb.channel_tone_hz(0) * nfft / 48000.0))     # the tone sits in its bin

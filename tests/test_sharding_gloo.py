@@ -27,8 +27,11 @@ def _worker(rank, world, port, C, T, ret):
     g = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))
     y, _ = orc.rx_ssb_f32_batch(rx_params(g, "usb"), x)
     full = slb.shard.gather_audio(torch.from_numpy(y), C)
+    # spectra of the first 256 frames of the shard's channels (what slb_rx_spectrum_device computes), gathered the same way
+    z = x[:, :256, 0].astype(np.float32) / 32768.0 + 1j * (x[:, :256, 1].astype(np.float32) / 32768.0)
+    spec = slb.shard.gather_spectra(torch.from_numpy((np.abs(np.fft.fft(z, axis=1)) ** 2).astype(np.float32)), C)
     if rank == 0:
-        ret["full"] = full.numpy().copy()
+        ret["full"] = full.numpy().copy(); ret["spec"] = spec.numpy().copy()
     dist.barrier(); dist.destroy_process_group()
 
 
@@ -46,3 +49,6 @@ def test_two_rank_shards_reassemble():
     g = np.load(os.path.join(GOLD, "rx_ssb_f32.npz"))
     whole, _ = oracle_lib.Oracle("port").rx_ssb_f32_batch(rx_params(g, "usb"), slb.synth_iq(C, T))
     assert np.array_equal(ret["full"], whole)
+    xw = slb.synth_iq(C, T)
+    zw = xw[:, :256, 0].astype(np.float32) / 32768.0 + 1j * (xw[:, :256, 1].astype(np.float32) / 32768.0)
+    assert np.array_equal(ret["spec"], (np.abs(np.fft.fft(zw, axis=1)) ** 2).astype(np.float32))
