@@ -134,6 +134,12 @@ __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned b
   asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                 ::"r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
 }
+// the same with an L2 eviction-priority hint: the raw stream is read exactly once
+__device__ __forceinline__ void bulk_g2s_stream (void *dst, const void *src, unsigned bytes, uint64_t *bar, uint64_t policy)
+{
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                ::"r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void bulk_s2g (void *dst, const void *src, unsigned bytes)
 {
   asm volatile ("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32 (src)), "r"(bytes) : "memory");
@@ -272,6 +278,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     if (lane == 0)
     {
       unsigned kk = 0;
+#ifdef SL_TC_L2HINT
+      uint64_t pol;
+      asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
       for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
         for (uint32_t k = 0; k < supers; k++, kk++)
         {
@@ -285,7 +295,11 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           for (int j = 0; j < kJ; j++)
           {
             const uint32_t c = P.chan[gs + min ((uint32_t) j, nv - 1u)];   // short groups repeat their last channel (rows computed, never stored)
+#ifdef SL_TC_L2HINT
+            bulk_g2s_stream (sRaw + (rb * kJ + j) * kRawRow, P.in + (size_t) c * P.frames + (size_t) k * kSuper, nfr * 4u, raw_full + rb, pol);
+#else
             bulk_g2s (sRaw + (rb * kJ + j) * kRawRow, P.in + (size_t) c * P.frames + (size_t) k * kSuper, nfr * 4u, raw_full + rb);
+#endif
             if (k == 0) bulk_g2s (sHist + (rb * kJ + j) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
           }
         }
@@ -672,6 +686,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
 #ifdef SL_TC_ABLATE_ST                                                              // (profiling aid: what the output stores cost)
           if (g15 == 123.456f)
 #endif
+#ifdef SL_TC_ST128
+#pragma unroll
+          for (int n = 0; n < kBlk; n += 4)
+            asm volatile ("st.global" SL_TC_STHINT ".v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(dst + n / 4),
+                          "r"(pack_lr (y[n] * g15)), "r"(pack_lr (y[n + 1] * g15)), "r"(pack_lr (y[n + 2] * g15)), "r"(pack_lr (y[n + 3] * g15)) : "memory");
+#else
 #pragma unroll
           for (int n = 0; n < kBlk; n += 8)
           {
@@ -682,6 +702,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
                           "r"(pack_lr (y[n] * g15)), "r"(pack_lr (y[n + 1] * g15)), "r"(pack_lr (y[n + 2] * g15)), "r"(pack_lr (y[n + 3] * g15)),
                           "r"(pack_lr (y[n + 4] * g15)), "r"(pack_lr (y[n + 5] * g15)), "r"(pack_lr (y[n + 6] * g15)), "r"(pack_lr (y[n + 7] * g15)) : "memory");
           }
+#endif
         }
 #endif
         if (w == 0) TC_STAMP (14);
