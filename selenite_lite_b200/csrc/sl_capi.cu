@@ -885,7 +885,9 @@ static int process_host_sliced (slb_ctx *ctx, const int16_t *h_in, int16_t *h_ou
   const uint32_t C = ctx->cfg.channels;
   // a multiple of 1536 frames = the FFT kernel's tile and two supertiles of the tensor-core kernel: both kernels give the
   // cut stream bit for bit the result of the uncut one
-  uint32_t slice = (uint32_t) (((size_t) 64 << 20) / ((size_t) C * 4)) / 1536u * 1536u;
+  size_t slice_bytes = (size_t) 64 << 20;
+  if (const char *e = std::getenv ("SELENITE_B200_SLICE_BYTES")) { const long long v = std::atoll (e); if (v > 0) slice_bytes = (size_t) v; }   // test / tuning knob
+  uint32_t slice = (uint32_t) (slice_bytes / ((size_t) C * 4)) / 1536u * 1536u;
   if (slice < 1536u) slice = 1536u;
   if (slice > frames) slice = frames;
   const size_t need = (size_t) C * slice * 4;

@@ -179,3 +179,28 @@ def test_several_groups_per_cta_and_mask_reloads(best_oracle):
         ys = run_gpu(ds, xs, want_audio=False)[0]
         idx = np.nonzero(sel)[0]
         assert np.array_equal(y2[idx], ys[idx % 8]), m
+
+
+def test_host_path_cut_into_many_time_slices(best_oracle):
+    """slb_rx_process_host cuts the batch in time (64 MB slices by default); with the slice forced down to 1536 frames a
+    stream of 7 slices (the last one short) must equal the device path bit for bit — carried state across slices, strided
+    copies, three staging slots in flight — for the tensor-core kernel and, with AM channels mixed in, the FFT kernel."""
+    import os
+    C, T = 20, 1536 * 6 + 384
+    x = slb.synth_iq(C, T)
+    def make():
+        d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+        for c in (3, 11):
+            d.DSP_Set_Mode(slb.MODE_AM, channel=c)
+        return d
+    y_dev = run_gpu(make(), x, want_audio=False)[0]
+    os.environ["SELENITE_B200_SLICE_BYTES"] = str(C * 4 * 1536)
+    try:
+        y_host = make().rx_process(x)
+        xp = torch.from_numpy(x).pin_memory(); yp = torch.empty_like(xp).pin_memory()
+        make().rx_process_pinned(xp, yp)
+    finally:
+        del os.environ["SELENITE_B200_SLICE_BYTES"]
+    assert np.array_equal(y_host, y_dev) and np.array_equal(yp.numpy(), y_dev)
+    exp, _, _, _ = best_oracle.rx_ssb_f32(make().oracle_params(), x[0])
+    check_int16(y_host[0], exp)
