@@ -292,6 +292,8 @@ int slb_biquad_scan_tables (const float coef10[10], float *Mpow96, float *Cresp9
  * 48-frame block: out52[0..47] = the block's biquad output from a zero state, out52[48..51] = the biquad state after it. */
 int slb_design_tc_taps (const float *mask_re_im, double taps_re[129], double taps_im[129]);
 int slb_design_tc_block (const float *mask_re_im, const float coef10[10], const int16_t *window, double out52[52]);
+/* the same for TX (sl_tx_ssb_tc.cu): window = int16[192] mic samples from 128 before the block, out = (I, Q) of its 48 samples */
+int slb_design_tc_tx_block (const float *mask_re_im, const int16_t *window, double out_iq[96]);
 int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im);
 /* tables of the tensor-core kernel's time-parallel biquad for blocks of 48 samples: Mp[4][16] = A^(48 k), M192[16], Cresp[48][4] */
 int slb_biquad_tc_tables (const float coef10[10], float *Mp64, float *M192, float *Cresp192);

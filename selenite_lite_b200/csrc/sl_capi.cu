@@ -43,6 +43,7 @@ struct slb_ctx
   float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
   // tensor-core path of the RX-SSB-f32 chain (sl_rx_ssb_tc.cu): tap planes per mask slot, which slots it can serve
   uint8_t *d_planes = nullptr; bool tc_ok[SLB_MAX_MASKS] = {}; float tc_s0[SLB_MAX_MASKS] = {}; float tc_sz[SLB_MAX_MASKS] = {}; TcBiquadTables tc_tables{};
+  uint8_t *d_tx_planes = nullptr; float tx_unit[SLB_MAX_MASKS] = {};   // TX-SSB-f32 contexts: tc_ok[] then refers to these planes
   // channel lists of the tensor-core launches, cached per channel range (the bulk paths cut the batch the same way every
   // call) and rebuilt when a mode or a mask changes (mode_version)
   struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
@@ -117,6 +118,15 @@ static int upload_chain_constants (slb_ctx *ctx)
   // caller-supplied one may not) and the AM slot (two outputs per sample) stay on the FFT kernel
   {
     std::vector<uint8_t> planes ((size_t) SLB_MAX_MASKS * kTcPlaneBytes, 0);
+    if (ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32)
+    {
+      std::vector<uint8_t> txp ((size_t) SLB_MAX_MASKS * kTcTxPlaneBytes, 0);
+      for (int m = 0; m < SLB_MAX_MASKS; m++)
+        ctx->tc_ok[m] = N == 512 && m != kAmMaskSlot && tc_build_tx_planes (ctx->masks_host.data () + (size_t) m * 2 * N, txp.data () + (size_t) m * kTcTxPlaneBytes, &ctx->tx_unit[m]);
+      CK (ctx, cudaMemcpyAsync (ctx->d_tx_planes, txp.data (), txp.size (), cudaMemcpyHostToDevice, ctx->stream));
+      CK (ctx, cudaStreamSynchronize (ctx->stream));
+    }
+    else
     for (int m = 0; m < SLB_MAX_MASKS; m++)
       ctx->tc_ok[m] = N == 512 && m != kAmMaskSlot && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, ctx->rx.biquad, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m], &ctx->tc_sz[m]);
     CK (ctx, cudaMemcpyAsync (ctx->d_planes, planes.data (), planes.size (), cudaMemcpyHostToDevice, ctx->stream));
@@ -188,6 +198,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   CKC (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking));
   CKC (cudaMalloc (&ctx->d_masks, (size_t) SLB_MAX_MASKS * 2 * N * sizeof (float)));
   CKC (cudaMalloc (&ctx->d_planes, (size_t) SLB_MAX_MASKS * kTcPlaneBytes));
+  CKC (cudaMalloc (&ctx->d_tx_planes, (size_t) SLB_MAX_MASKS * kTcTxPlaneBytes));
   CKC (cudaMalloc (&ctx->d_slot, C));
   CKC (cudaMalloc (&ctx->d_twiddle, kTwiddleFloats * sizeof (float)));
   for (int p = 0; p < 2; p++) CKC (cudaMalloc (&ctx->d_ovl[p], (size_t) C * ovl * 4));
@@ -220,7 +231,7 @@ void slb_destroy (slb_ctx *ctx)
   cudaDeviceSynchronize ();
   chan64_destroy (ctx->chan);
   rxq15_destroy (ctx->q15);
-  cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle); cudaFree (ctx->d_planes);
+  cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle); cudaFree (ctx->d_planes); cudaFree (ctx->d_tx_planes);
   for (auto &kv : ctx->tc_lists) cudaFree (kv.second.d);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
@@ -436,7 +447,8 @@ static bool tc_path_enabled ()
 static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
                           float *dbg_audio, float *dbg_gain, cudaStream_t stream)
 {
-  if (ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 || !tc_path_enabled () || ctx->force_fft)
+  const bool is_tx = ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32;
+  if ((ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 && !is_tx) || !tc_path_enabled () || ctx->force_fft)
     return run_rx_fft_kernel (ctx, d_in, d_out, ch0, nch, frames, dbg_audio, dbg_gain, stream);
   slb_ctx::TcLists &tl = ctx->tc_lists[((uint64_t) ch0 << 32) | nch];
   if (tl.version != ctx->mode_version)
@@ -475,7 +487,23 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
     tl.groups = G; tl.version = ctx->mode_version;
   }
   const std::vector<uint8_t> &on_tc = tl.on_tc;
-  if (tl.groups != 0)
+  if (tl.groups != 0 && is_tx)
+  {
+    const uint32_t G = tl.groups;
+    const uint32_t ovl = ctx->rx.fft_len - ctx->rx.hop;
+    TxTcLaunch L{};
+    L.in = d_in; L.out = d_out; L.iq_dbg = dbg_audio; L.gain_dbg = dbg_gain;
+    L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
+    L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
+    L.gstart = tl.d; L.ginfo = tl.d + G; L.chan = tl.d + 2 * (size_t) G;
+    L.planes = ctx->d_tx_planes; L.unit = ctx->tx_unit;
+    L.flag_final = ctx->flag_base + rx_ssb_f32_tiles (frames);
+    L.n_groups = G; L.frames = frames;
+    L.alc_target = ctx->tx.alc_target; L.alc_decay = ctx->tx.alc_decay; L.alc_floor = ctx->tx.alc_floor; L.alc_gmax = ctx->tx.alc_gmax;
+    CK (ctx, launch_tx_ssb_tc (L, ctx->sm_count, stream));
+    ctx->launches++;
+  }
+  else if (tl.groups != 0)
   {
     const uint32_t G = tl.groups;
     const uint32_t ovl = ctx->rx.fft_len - ctx->rx.hop;
@@ -497,7 +525,7 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
     if (on_tc[i]) { i++; continue; }
     uint32_t e = i; while (e < nch && !on_tc[e]) e++;
     const int rc = run_rx_fft_kernel (ctx, d_in + (size_t) i * frames * 2, d_out + (size_t) i * frames * 2, ch0 + i, e - i, frames,
-                                      dbg_audio ? dbg_audio + (size_t) i * frames : nullptr, dbg_gain ? dbg_gain + (size_t) i * (frames / kAgcBlock) : nullptr, stream);
+                                      dbg_audio ? dbg_audio + (size_t) i * frames * (is_tx ? 2 : 1) : nullptr, dbg_gain ? dbg_gain + (size_t) i * (frames / kAgcBlock) : nullptr, stream);
     if (rc) return rc;
     i = e;
   }
@@ -828,6 +856,15 @@ int slb_design_tc_block (const float *mask_re_im, const float coef10[10], const 
   float ua = 0.f, uz = 0.f;
   if (!tc_build_planes (mask_re_im, coef10, planes.data (), &ua, &uz)) return SLB_ERR_UNSUPPORTED;
   tc_apply_planes (planes.data (), ua, uz, window, out52);
+  return SLB_OK;
+}
+int slb_design_tc_tx_block (const float *mask_re_im, const int16_t *window, double out_iq[96])
+{
+  if (!mask_re_im || !window || !out_iq) return SLB_ERR_ARG;
+  std::vector<uint8_t> planes (kTcTxPlaneBytes);
+  float u = 0.f;
+  if (!tc_build_tx_planes (mask_re_im, planes.data (), &u)) return SLB_ERR_UNSUPPORTED;
+  tc_apply_tx_planes (planes.data (), u, window, out_iq);
   return SLB_OK;
 }
 int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im)

@@ -336,6 +336,61 @@ void tc_apply_planes (const uint8_t *planes, float unit_a, float unit_z, const i
   }
 }
 
+// TX: I[n] = sum_d hr[d] m[n-d], Q[n] = sum_d hi[d] m[n-d] on the real mic samples m. Window = 192 samples from 128 before
+// the block (6 K-steps of 32; the last 16 reach past the block and meet zero taps); rows digit * 48 + n per rail.
+bool tc_build_tx_planes (const float *mask, uint8_t *planes, float *unit)
+{
+  double hr[kTcTaps], hi[kTcTaps];
+  if (!tc_design_taps (mask, hr, hi)) return false;
+  double mx = 0;
+  for (int d = 0; d < kTcTaps; d++) mx = std::fmax (mx, std::fmax (std::fabs (hr[d]), std::fabs (hi[d])));
+  const double lim = 8323071.0;
+  const float u = (float) (mx / (lim * 32768.0));
+  if (!(u > 1e-30f) || !std::isfinite (u)) return false;
+  const double sc = 1.0 / ((double) u * 32768.0);
+  *unit = u;
+  std::memset (planes, 0, kTcTxPlaneBytes);
+  for (int rail = 0; rail < 2; rail++)
+    for (int n = 0; n < 48; n++)
+      for (int f = 0; f < 192; f++)
+      {
+        const int d = 128 + n - f;
+        if (d < 0 || d >= kTcTaps) continue;
+        const long long q = std::llround ((rail ? hi[d] : hr[d]) * sc);
+        if (std::llabs (q) > (long long) lim + 1) return false;
+        const int32_t h = (int32_t) q;
+        const int32_t l0 = ((h + 128) & 255) - 128, r1 = (h - l0) >> 8, l1 = ((r1 + 128) & 255) - 128, l2 = (r1 - l1) >> 8;
+        const int32_t dg[3] = { l2, l1, l0 };
+        const int ks = f / 32, kk = f % 32;
+        for (int g = 0; g < 3; g++)
+        {
+          const int row = g * 48 + n;
+          planes[(size_t) (rail * 6 + ks) * 18 * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)] = (uint8_t) (int8_t) dg[g];
+        }
+      }
+  return true;
+}
+void tc_apply_tx_planes (const uint8_t *planes, float unit, const int16_t *window, double *out_iq)
+{
+  for (int rail = 0; rail < 2; rail++)
+    for (int n = 0; n < 48; n++)
+    {
+      long long acc = 0;
+      for (int f = 0; f < 192; f++)
+      {
+        const int ks = f / 32, kk = f % 32;
+        long long h = 0;
+        for (int g = 0; g < 3; g++)
+        {
+          const int row = g * 48 + n;
+          h = h * 256 + (int8_t) planes[(size_t) (rail * 6 + ks) * 18 * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)];
+        }
+        acc += h * (long long) window[f];
+      }
+      out_iq[2 * n + rail] = (double) acc * (double) unit;
+    }
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // Ring index logic — follows Core/Src/dsp_if.c line by line (cited), with the sample stores left to the kernels.
 // -----------------------------------------------------------------------------------------------------------

@@ -137,6 +137,25 @@ struct RxTcLaunch
 };
 int launch_rx_ssb_tc (const RxTcLaunch &L, int sm_count, void *stream);
 
+// ---- TX-SSB-f32 on the tensor cores (sl_tx_ssb_tc.cu): real mic samples x complex taps, two output rails ----
+constexpr size_t kTcTxPlaneBytes = 2 * 6 * 18 * 256;   // [rail I|Q][K-step of 32 samples][digit*48+n][32 bytes]
+bool tc_build_tx_planes (const float *mask_re_im, uint8_t *planes /* kTcTxPlaneBytes */, float *unit);
+void tc_apply_tx_planes (const uint8_t *planes, float unit, const int16_t *window /* [192] mic samples */, double *out_iq /* [48][2] */);
+struct TxTcLaunch
+{
+  const int16_t *in; int16_t *out;         // [C][T][2]: L = R mic frames in, I/Q out
+  float *iq_dbg; float *gain_dbg;
+  const int16_t *ovl_in; int16_t *ovl_out; // [C][128][2] carried raw tail
+  float *state; unsigned *flag;            // envelope at state[c][4]; flag[c] left at flag_final for the FFT kernel
+  const uint32_t *chan, *gstart, *ginfo;   // as RxTcLaunch
+  const uint8_t *planes;                   // [SLB_MAX_MASKS][kTcTxPlaneBytes]
+  const float *unit;                       // host, [SLB_MAX_MASKS]
+  unsigned flag_final;
+  uint32_t n_groups, frames;
+  float alc_target, alc_decay, alc_floor, alc_gmax;
+};
+int launch_tx_ssb_tc (const TxTcLaunch &L, int sm_count, void *stream);
+
 // ---- CHAN-64-f32 (sl_chan64.cu): state object owned by the context ----
 struct Chan64State;
 int design_default_chan (uint32_t fs, slb_chan_params *p);

@@ -1,0 +1,81 @@
+// Device helpers shared by the tensor-core kernels (sl_rx_ssb_tc.cu, sl_tx_ssb_tc.cu): mbarriers, bulk asynchronous copies,
+// tcgen05 descriptors / MMA issue / TMEM loads. Included inside each translation unit's anonymous namespace.
+#pragma once
+__device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared (p); }
+__device__ __forceinline__ void mbar_init (uint64_t *bar, unsigned count)
+{
+  asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32 (bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, unsigned bytes)
+{
+  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32 (bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive (uint64_t *bar)
+{
+  asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32 (bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
+{
+  asm volatile ("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+                ::"r"(smem_u32 (bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)) : "memory");
+}
+// the same with an L2 eviction-priority hint: the raw stream is read exactly once
+__device__ __forceinline__ void bulk_g2s_stream (void *dst, const void *src, unsigned bytes, uint64_t *bar, uint64_t policy)
+{
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                ::"r"(smem_u32 (dst)), "l"(src), "r"(bytes), "r"(smem_u32 (bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g (void *dst, const void *src, unsigned bytes)
+{
+  asm volatile ("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32 (src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void named_bar (int id, int threads) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+// ---- tcgen05 ----
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
+// LBO = distance between the two 16-byte K-chunks of one instruction, SBO = distance between 8-row groups
+// (verified on B200 by tools/microbench/umma_i8_probe.cu, including the aliased SBO used for A)
+__device__ __forceinline__ uint64_t umma_desc (uint32_t addr, uint32_t lbo, uint32_t sbo)
+{
+  return (uint64_t) ((addr & 0x3FFFFu) >> 4) | ((uint64_t) (lbo >> 4) << 16) | ((uint64_t) (sbo >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::i8: D = s32, A / B signedness, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc (int N, int a_signed, int b_signed)
+{
+  return (2u << 4) | ((uint32_t) a_signed << 7) | ((uint32_t) b_signed << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8 (uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+  asm volatile ("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool elect_one ()
+{
+  uint32_t pred;
+  asm volatile ("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_commit (uint64_t *bar)
+{
+  asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32 (bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before () { asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after () { asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16 (uint32_t addr, uint32_t *v)
+{
+  asm volatile ("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                  "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld8 (uint32_t addr, uint32_t *v)
+{
+  asm volatile ("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait () { asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+

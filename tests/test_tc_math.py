@@ -111,3 +111,23 @@ def test_block_parallel_biquad_equals_sequential(port, rng):
     scale = np.sqrt(np.mean(ref_y.astype(np.float64) ** 2))
     assert np.max(np.abs(y.reshape(-1) - ref_y)) < 3e-6 * scale
     assert np.max(np.abs(end - ref_state)) < 3e-6 * max(1.0, np.max(np.abs(ref_state)))
+
+
+@pytest.mark.parametrize("mode", [slb.MODE_USB, slb.MODE_LSB])
+def test_tx_operand_planes_equal_complex_fir(mode, rng):
+    """TX (sl_tx_ssb_tc.cu): real mic samples x complex taps, two rails of tcgen05 operand planes, against the float64 FIR."""
+    mask = default_mask(mode)
+    rc, hr, hi = tc_taps(mask)
+    assert rc == 0
+    lib = _lib.load()
+    for amp in (20000, 200, 32767):
+        w = rng.integers(-amp, amp + 1, 192).astype(np.int16)
+        if amp == 32767:
+            w[::5] = 32767; w[2::7] = -32768
+        out = np.zeros(96, np.float64)
+        assert lib.slb_design_tc_tx_block(mask.ctypes.data, w.ctypes.data, out.ctypes.data) == 0
+        m = w.astype(np.float64) / 32768.0
+        ref_i = np.array([sum(hr[d] * m[128 + n - d] for d in range(129)) for n in range(48)])
+        ref_q = np.array([sum(hi[d] * m[128 + n - d] for d in range(129)) for n in range(48)])
+        scale = np.sqrt(np.mean(m ** 2))
+        assert np.max(np.abs(out[0::2] - ref_i)) < 2e-7 * scale and np.max(np.abs(out[1::2] - ref_q)) < 2e-7 * scale
