@@ -111,3 +111,46 @@ def test_host_path_and_1ms_cadence(best_oracle):
     assert starts, "modulated stream not found behind the ring"
     with pytest.raises(slb.SeleniteError):
         d.rx_process(torch.zeros((C, 384, 2), dtype=torch.int16, device="cuda"))    # wrong direction for this context
+
+
+def test_tensor_core_and_fft_kernels_agree_and_hand_over(best_oracle):
+    """TX on the tensor cores (sl_tx_ssb_tc.cu, the default) against the FFT kernel (slb_set_rx_path FFT) on the same input,
+    a stream cut into calls served alternately by the two (raw tail, ALC envelope and the hand-over counter cross the
+    switch), several channel groups per CTA with mask reloads (forced 3-CTA grid), and the time-sliced host path."""
+    C, T = 44, 1536 * 4 + 384
+    x = slb.synth_mic(C, T)
+    modes = [slb.MODE_USB, slb.MODE_LSB, slb.MODE_DIG, slb.MODE_USB, slb.MODE_CW]
+
+    def make(path=slb.RX_PATH_AUTO):
+        d = slb.DspIf(C, chain=slb.CHAIN_TX_SSB_F32); d.set_rx_path(path)
+        for c in range(C):
+            d.DSP_Set_Mode(modes[c % 5], channel=c)
+        return d
+    y_tc, iq_tc, g_tc = run_gpu(make(), x)
+    y_fft, iq_fft, g_fft = run_gpu(make(slb.RX_PATH_FFT), x)
+    dd = np.abs(y_tc.astype(np.int32) - y_fft.astype(np.int32))
+    assert dd.max() <= 1 and np.mean(dd > 0) < 0.02
+    for c in range(0, C, 7):
+        exp, z, g_, _ = best_oracle.tx_ssb_f32(make().oracle_params(modes[c % 5]), x[c])
+        tol = iq_tolerance(z)
+        assert np.all(np.abs(iq_tc[c] - z) <= tol + 1e-9) and np.all(np.abs(iq_fft[c] - z) <= tol + 1e-9), c
+        assert np.allclose(g_tc[c], g_, rtol=2e-5)
+        check_int16(y_tc[c], exp)
+    # alternate kernels between calls
+    d = make(); xd = torch.from_numpy(x).cuda(); parts = []
+    cuts = [0, 1536, 1536 + 384, 1536 * 3, T]
+    for i in range(4):
+        d.set_rx_path(slb.RX_PATH_FFT if i % 2 else slb.RX_PATH_AUTO)
+        parts.append(d.tx_process(xd[:, cuts[i]:cuts[i + 1]].contiguous()).cpu().numpy())
+    ya = np.concatenate(parts, axis=1)
+    for c in (0, 13, 43):
+        exp, _, _, _ = best_oracle.tx_ssb_f32(make().oracle_params(modes[c % 5]), x[c])
+        check_int16(ya[c], exp)
+    # several groups per CTA, mask reloads; and the host path cut into time slices
+    os.environ["SELENITE_B200_TC_GRID"] = "3"; os.environ["SELENITE_B200_SLICE_BYTES"] = str(C * 4 * 1536)
+    try:
+        y3 = run_gpu(make(), x, want_dbg=False)[0]
+        y_host = make().tx_process(x)
+    finally:
+        del os.environ["SELENITE_B200_TC_GRID"]; del os.environ["SELENITE_B200_SLICE_BYTES"]
+    assert np.array_equal(y3, y_tc) and np.array_equal(y_host, y_tc)
