@@ -189,6 +189,19 @@ size_t rxq15_state_bytes (const RxQ15State *st);
 int rxq15_state_save (RxQ15State *st, char *dst);
 int rxq15_state_load (RxQ15State *st, const char *src);
 
+// ---- RX-SSB-q15 on the tensor cores (sl_rx_q15_tc.cu): same chain, same state, bit-identical results ----
+constexpr size_t kTcQ15PlaneBytes = 7 * 24 * 256;
+bool q15_tc_build_planes (const int16_t *taps_i, const int16_t *taps_q, uint8_t *planes /* kTcQ15PlaneBytes */);
+struct RxQ15TcLaunch
+{
+  const int16_t *in; int16_t *out;
+  const uint32_t *tail_in; uint32_t *tail_out; const int16_t *peaks_in; int16_t *peaks_out;
+  const uint8_t *planes, *lsb; int16_t *audio_dbg; uint32_t *gain_dbg;
+  const int16_t *rel;                      // host, [SLB_Q15_WIN]
+  uint32_t channels, frames, window; int32_t target, floor_; uint32_t gmax;
+};
+int launch_rx_q15_tc (const RxQ15TcLaunch &L, int sm_count, void *stream);
+
 // ---- context accessors for translation units that do not see the struct (sl_stages.cu, sl_chains.cu) ----
 int ctx_device (const slb_ctx *ctx);
 size_t ctx_channels (const slb_ctx *ctx);

@@ -26,6 +26,7 @@
 // window-1 blocks before it (FIR only, nothing stored). No cross-CTA hand-over exists in this kernel.
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "sl_internal.h"
@@ -327,6 +328,7 @@ struct RxQ15State
   slb_rx_q15_params prm{};
   uint32_t *d_tail[2] = { nullptr, nullptr }; int16_t *d_peaks[2] = { nullptr, nullptr }; int parity = 0;
   uint32_t *d_afrag = nullptr; uint8_t *d_lsb = nullptr;
+  uint8_t *d_tc_planes = nullptr; bool tc_ok = false;   // tcgen05 form of the same FIRs (sl_rx_q15_tc.cu)
   int16_t *dbg_audio = nullptr; uint32_t *dbg_gain = nullptr;
 };
 
@@ -368,6 +370,7 @@ int rxq15_create (slb_ctx *ctx, uint32_t channels, uint32_t fs, RxQ15State **out
   }
   ok = ok && cudaMalloc (&st->d_afrag, 4 * 10 * 32 * 4) == cudaSuccess;
   ok = ok && cudaMalloc (&st->d_lsb, channels) == cudaSuccess;
+  ok = ok && cudaMalloc (&st->d_tc_planes, kTcQ15PlaneBytes) == cudaSuccess;
   if (!ok) { rxq15_destroy (st); return ctx_fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state allocation failed"); }
   slb_rx_q15_params p; design_default_rx_q15 (fs, &p);
   int rc = rxq15_set_params (ctx, st, &p);
@@ -382,7 +385,7 @@ void rxq15_destroy (RxQ15State *st)
 {
   if (!st) return;
   for (int p = 0; p < 2; p++) { cudaFree (st->d_tail[p]); cudaFree (st->d_peaks[p]); }
-  cudaFree (st->d_afrag); cudaFree (st->d_lsb);
+  cudaFree (st->d_afrag); cudaFree (st->d_lsb); cudaFree (st->d_tc_planes);
   delete st;
 }
 
@@ -404,6 +407,12 @@ int rxq15_set_params (slb_ctx *ctx, RxQ15State *st, const slb_rx_q15_params *p)
   pack_afrag (p->taps_i, p->ntaps, frag.data (), frag.data () + 320);
   pack_afrag (p->taps_q, p->ntaps, frag.data () + 640, frag.data () + 960);
   if (cudaMemcpy (st->d_afrag, frag.data (), frag.size () * 4, cudaMemcpyHostToDevice) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "tap upload failed");
+  {
+    // the tcgen05 kernel serves the chain when every tap splits into two signed bytes and the AGC window fits the peaks it keeps
+    std::vector<uint8_t> planes (kTcQ15PlaneBytes);
+    st->tc_ok = q15_tc_build_planes (p->taps_i, p->taps_q, planes.data ()) && p->agc_window <= 17;
+    if (st->tc_ok && cudaMemcpy (st->d_tc_planes, planes.data (), planes.size (), cudaMemcpyHostToDevice) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "tap upload failed");
+  }
   st->prm = *p;
   return SLB_OK;
 }
@@ -421,6 +430,22 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
 {
   if (frames == 0 || frames % kBlk != 0) return ctx_fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the 48-frame firmware block");
   if (reinterpret_cast<uintptr_t> (d_in) & 15u) return ctx_fail (ctx, SLB_ERR_ARG, "input must be 16-byte aligned (bulk copies)");
+  static const bool legacy_only = [] { const char *e = std::getenv ("SELENITE_B200_Q15_PATH"); return e && std::strcmp (e, "legacy") == 0; } ();   // A/B knob
+  if (st->tc_ok && !legacy_only)
+  {
+    RxQ15TcLaunch L{};
+    L.in = d_in; L.out = d_out;
+    L.tail_in = st->d_tail[st->parity] + (size_t) ch0 * kTaps; L.tail_out = st->d_tail[st->parity ^ 1] + (size_t) ch0 * kTaps;
+    L.peaks_in = st->d_peaks[st->parity] + (size_t) ch0 * kWin; L.peaks_out = st->d_peaks[st->parity ^ 1] + (size_t) ch0 * kWin;
+    L.planes = st->d_tc_planes; L.lsb = st->d_lsb + ch0;
+    L.audio_dbg = with_debug ? st->dbg_audio : nullptr; L.gain_dbg = with_debug ? st->dbg_gain : nullptr;
+    L.rel = st->prm.rel; L.channels = nch; L.frames = frames; L.window = st->prm.agc_window;
+    L.target = st->prm.agc_target; L.floor_ = st->prm.agc_floor; L.gmax = st->prm.agc_gmax_q15;
+    const int e = launch_rx_q15_tc (L, sm_count, stream);
+    if (e != 0) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString ((cudaError_t) e));
+    ctx_count_launch (ctx);
+    return SLB_OK;
+  }
   KParams P{};
   P.in = reinterpret_cast<const uint32_t *> (d_in); P.out = reinterpret_cast<uint32_t *> (d_out);
   P.tail_in = st->d_tail[st->parity] + (size_t) ch0 * kTaps; P.tail_out = st->d_tail[st->parity ^ 1] + (size_t) ch0 * kTaps;
