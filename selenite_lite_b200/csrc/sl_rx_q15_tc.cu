@@ -169,12 +169,14 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
           }
         }
         {
-          // new chunks: chunk cc = c4 + 4 t, the two warps take alternate t; a stream may end on any block (nfr = 48 b)
-          const int nchunks = (int) nfr / 8;
+          // new chunks: warp 0 takes the first half, warp 1 the second (the chunks it copies as history next time are its
+          // own); a stream may end on any block (nfr = 48 b)
+          const int nchunks = (int) nfr / 8, half = (nchunks / 2) & ~3;
+          const int lo = cw == 0 ? 0 : half, hi = cw == 0 ? half : nchunks;
           const unsigned char *src0 = sRaw + (rb * kJ + j) * kRawRow;
           unsigned char *dst0 = Ahi + kChunksHist * kChunkBytes + j * 16;
 #pragma unroll 3
-          for (int cc = c4 + 4 * cw; cc < nchunks; cc += 4 * kConvWarps)
+          for (int cc = lo + c4; cc < hi; cc += 4)
           {
             const uint4 *src = reinterpret_cast<const uint4 *> (src0 + cc * 32);
             const uint4 v0 = src[0], v1 = src[1];

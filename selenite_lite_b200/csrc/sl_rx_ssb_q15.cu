@@ -430,7 +430,8 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
 {
   if (frames == 0 || frames % kBlk != 0) return ctx_fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the 48-frame firmware block");
   if (reinterpret_cast<uintptr_t> (d_in) & 15u) return ctx_fail (ctx, SLB_ERR_ARG, "input must be 16-byte aligned (bulk copies)");
-  static const bool legacy_only = [] { const char *e = std::getenv ("SELENITE_B200_Q15_PATH"); return e && std::strcmp (e, "legacy") == 0; } ();   // A/B knob
+  const char *path_env = std::getenv ("SELENITE_B200_Q15_PATH");                 // A/B and test knob: "legacy" = the mma.sync kernel below
+  const bool legacy_only = path_env && std::strcmp (path_env, "legacy") == 0;
   if (st->tc_ok && !legacy_only)
   {
     RxQ15TcLaunch L{};

@@ -126,3 +126,54 @@ def test_full_size_properties():
     h = slb.DspIf(C // 2, chain=slb.CHAIN_RX_SSB_Q15)
     yh, _, _ = run_gpu(h, x[C // 2:], want_dbg=False)
     assert np.array_equal(yh, y[C // 2:])
+
+
+def test_tcgen05_kernel_equals_the_mma_sync_kernel_bit_for_bit():
+    """The chain has two kernels: sl_rx_q15_tc.cu (tcgen05, the default when the taps and the AGC window allow it) and the
+    mma.sync kernel of sl_rx_ssb_q15.cu (SELENITE_B200_Q15_PATH=legacy). Same output, audio, gain words AND carried state
+    (raw tail, peak window by age) on ragged shapes: one block, a half supertile, several groups per CTA, both sidebands;
+    and a stream cut into calls that alternate between the two."""
+    import os
+    import torch
+
+    def run(C, x, legacy, cuts=None, grid=None):
+        if legacy:
+            os.environ["SELENITE_B200_Q15_PATH"] = "legacy"
+        if grid:
+            os.environ["SELENITE_B200_TC_GRID"] = str(grid)
+        try:
+            d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+            for c in range(1, C, 3):
+                d.DSP_Set_Mode(slb.MODE_LSB, channel=c)
+            T = x.shape[1]
+            audio = torch.zeros((C, T), dtype=torch.int16, device="cuda"); gain = torch.zeros((C, T // 48), dtype=torch.int32, device="cuda")
+            d.set_q15_debug_taps(audio, gain)
+            xd = torch.from_numpy(x).cuda()
+            if cuts is None:
+                y = d.rx_process(xd).cpu().numpy()
+            else:
+                parts = []
+                for i in range(len(cuts) - 1):
+                    if (i % 2 == 1) != legacy:
+                        os.environ["SELENITE_B200_Q15_PATH"] = "legacy"
+                    else:
+                        os.environ.pop("SELENITE_B200_Q15_PATH", None)
+                    parts.append(d.rx_process(xd[:, cuts[i]:cuts[i + 1]].contiguous()).cpu().numpy())
+                y = np.concatenate(parts, axis=1)
+            torch.cuda.synchronize()
+            return y, audio.cpu().numpy(), gain.cpu().numpy(), bytes(d.state_save())
+        finally:
+            os.environ.pop("SELENITE_B200_Q15_PATH", None); os.environ.pop("SELENITE_B200_TC_GRID", None)
+
+    rng = np.random.Generator(np.random.PCG64(21))
+    for C, T, grid in ((1, 48, None), (5, 48 * 9, None), (19, 768 * 2 + 48 * 5, 2), (300, 768 * 3, None)):
+        x = slb.synth_iq(C, T)
+        x[:, ::97] = rng.integers(-32768, 32768, x[:, ::97].shape)                  # rail-to-rail samples in between
+        a = run(C, x, legacy=False, grid=grid); b = run(C, x, legacy=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]), (C, T)
+        assert a[3] == b[3], (C, T)                                               # tail + peak window + sidebands
+    C, T = 11, 768 * 2 + 48 * 7
+    x = slb.synth_iq(C, T)
+    whole = run(C, x, legacy=True)
+    cut = run(C, x, legacy=False, cuts=[0, 48, 48 * 14, 768 + 48 * 3, T])
+    assert np.array_equal(whole[0], cut[0]) and whole[3] == cut[3]
