@@ -263,7 +263,7 @@ def run_ours(args):
             dd = slb.DspIf(C, fs=FS, chain=chain, device=local)
             ms = timed(lambda: getattr(dd, call)(xi, yo))
             other[name] = {"Msamples_per_s": C * T / (ms * 1e-3) / 1e6, "hbm_frac": C * T * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / peak,
-                           "note": "bit-exact integer chain, FIR on the integer tensor cores" if name == "rx_ssb_q15" else "config 3: tx_ssb_tc_kernel (tcgen05 FIR, two rails)"}
+                           "note": "bit-exact integer chain: rx_q15_tc_kernel (tcgen05 kind::i8 FIRs, integer epilogue)" if name == "rx_ssb_q15" else "config 3: tx_ssb_tc_kernel (tcgen05 FIR, two rails)"}
             del dd
         del xi, yo
         S, Tw = 64, 192000 * args.seconds // 768 * 768
