@@ -28,7 +28,7 @@ FS = 48000
 SECONDS = 10
 FRAMES = FS * SECONDS          # 480 000 = 1250 hops of 384
 BYTES_PER_SAMPLE = 8           # 4 B int16 I/Q in + 4 B int16 L/R out
-WORKLOAD = "configs[1]: 1024 independent 48 kHz I/Q channels x 10 s per GPU, RX-SSB-f32 chain (FFT overlap-save SSB demod + 2-stage biquad + AGC)"
+WORKLOAD = "configs[1]: 1024 independent 48 kHz I/Q channels x 10 s per GPU, RX-SSB-f32 chain (overlap-save SSB demod + 2-stage biquad + AGC; filter and biquad block response evaluated as one exact integer contraction on tcgen05)"
 
 
 def load_peaks():
