@@ -294,6 +294,9 @@ int slb_design_tc_taps (const float *mask_re_im, double taps_re[129], double tap
 int slb_design_tc_block (const float *mask_re_im, const float coef10[10], const int16_t *window, double out52[52]);
 /* the same for TX (sl_tx_ssb_tc.cu): window = int16[192] mic samples from 128 before the block, out = (I, Q) of its 48 samples */
 int slb_design_tc_tx_block (const float *mask_re_im, const int16_t *window, double out_iq[96]);
+/* and for the integer chain (sl_rx_q15_tc.cu): window = int16[112][2] I/Q frames from 64 before the block, out = the 48 arm_fir_q15
+ * results of rail I, then of rail Q; SLB_ERR_UNSUPPORTED when a tap does not split into two signed bytes (|tap| >= 32640) */
+int slb_design_q15_tc_block (const int16_t taps_i[64], const int16_t taps_q[64], const int16_t *window, int32_t out96[96]);
 int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im);
 /* tables of the tensor-core kernel's time-parallel biquad for blocks of 48 samples: Mp[4][16] = A^(48 k), M192[16], Cresp[48][4] */
 int slb_biquad_tc_tables (const float coef10[10], float *Mp64, float *M192, float *Cresp192);

@@ -867,6 +867,14 @@ int slb_design_tc_tx_block (const float *mask_re_im, const int16_t *window, doub
   tc_apply_tx_planes (planes.data (), u, window, out_iq);
   return SLB_OK;
 }
+int slb_design_q15_tc_block (const int16_t taps_i[64], const int16_t taps_q[64], const int16_t *window, int32_t out96[96])
+{
+  if (!taps_i || !taps_q || !window || !out96) return SLB_ERR_ARG;
+  std::vector<uint8_t> planes (kTcQ15PlaneBytes);
+  if (!q15_tc_build_planes (taps_i, taps_q, planes.data ())) return SLB_ERR_UNSUPPORTED;
+  q15_tc_apply_planes (planes.data (), window, out96);
+  return SLB_OK;
+}
 int slb_design_mask (uint32_t fs, uint8_t mode, float *mask_re_im)
 {
   if (!mask_re_im) return SLB_ERR_ARG;

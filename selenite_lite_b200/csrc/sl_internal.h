@@ -192,6 +192,7 @@ int rxq15_state_load (RxQ15State *st, const char *src);
 // ---- RX-SSB-q15 on the tensor cores (sl_rx_q15_tc.cu): same chain, same state, bit-identical results ----
 constexpr size_t kTcQ15PlaneBytes = 7 * 24 * 256;
 bool q15_tc_build_planes (const int16_t *taps_i, const int16_t *taps_q, uint8_t *planes /* kTcQ15PlaneBytes */);
+void q15_tc_apply_planes (const uint8_t *planes, const int16_t *window /* [112][2] */, int32_t *out96);
 struct RxQ15TcLaunch
 {
   const int16_t *in; int16_t *out;

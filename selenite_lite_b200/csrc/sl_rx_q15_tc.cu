@@ -395,6 +395,27 @@ bool q15_tc_build_planes (const int16_t *taps_i, const int16_t *taps_q, uint8_t 
   return true;
 }
 
+// host-side evaluation of the planes on one raw window (design check, tests/test_tc_math.py): the integer contraction the
+// kernel runs and its reconstruction of arm_fir_q15's result; out[0..47] = rail I, out[48..95] = rail Q
+void q15_tc_apply_planes (const uint8_t *planes, const int16_t *window /* [112][2] */, int32_t *out96)
+{
+  for (int rail = 0; rail < 2; rail++)
+    for (int n = 0; n < 48; n++)
+    {
+      long long s2 = 0, s1 = 0, s0 = 0;
+      for (int m = 0; m < 224; m++)
+      {
+        const int ks = m / 32, kk = m % 32, x = window[m], xl = x & 255, xh = (x - xl) >> 8;
+        const int r_hh = rail * 96 + n, r_hl = rail * 96 + 48 + n;
+        const int hh = (int8_t) planes[(size_t) ks * kBStep + (r_hh / 8) * 256 + (kk / 16) * 128 + (r_hh % 8) * 16 + (kk % 16)];
+        const int hl = (int8_t) planes[(size_t) ks * kBStep + (r_hl / 8) * 256 + (kk / 16) * 128 + (r_hl % 8) * 16 + (kk % 16)];
+        s2 += xh * hh; s1 += xh * hl + xl * hh; s0 += xl * hl;
+      }
+      const long long v = 2 * s2 + ((256 * s1 + s0) >> 15);
+      out96[rail * 48 + n] = (int32_t) (v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+    }
+}
+
 int launch_rx_q15_tc (const RxQ15TcLaunch &L, int sm_count, void *stream)
 {
   KParams P{};

@@ -131,3 +131,26 @@ def test_tx_operand_planes_equal_complex_fir(mode, rng):
         ref_q = np.array([sum(hi[d] * m[128 + n - d] for d in range(129)) for n in range(48)])
         scale = np.sqrt(np.mean(m ** 2))
         assert np.max(np.abs(out[0::2] - ref_i)) < 2e-7 * scale and np.max(np.abs(out[1::2] - ref_q)) < 2e-7 * scale
+
+
+def test_q15_operand_planes_equal_arm_fir_q15(port, rng):
+    """sl_rx_q15_tc.cu: the tcgen05 operand planes of the two 64-tap q15 FIRs (balanced byte digits, both rails in one operand)
+    and the reconstruction (acc >> 15) = 2 S2 + ((256 S1 + S0) >> 15), bit for bit against arm_fir_q15 — random taps,
+    full-scale samples, saturating outputs; taps that do not split into two signed bytes are refused."""
+    lib = _lib.load()
+    for trial in range(4):
+        ti = rng.integers(-32639, 32640, 64).astype(np.int16); tq = rng.integers(-32639, 32640, 64).astype(np.int16)
+        if trial == 0:
+            p = slb.default_rx_q15_params(48000); ti = np.array(p.taps_i[:64], np.int16); tq = np.array(p.taps_q[:64], np.int16)
+        w = rng.integers(-32768, 32768, (112, 2)).astype(np.int16)
+        if trial == 3:
+            w[:] = 32767; ti[:] = 32639; tq[:] = -32639                            # both rails saturate
+        out = np.zeros(96, np.int32)
+        assert lib.slb_design_q15_tc_block(ti.ctypes.data, tq.ctypes.data, w.ctypes.data, out.ctypes.data) == 0
+        for rail, taps in ((0, ti), (1, tq)):
+            x = np.ascontiguousarray(w[:, rail])
+            # arm_fir_q15 takes pCoeffs time-reversed (oracle/chains.inc.c does the same); pState: ntaps + block - 1 (+1), zero history
+            y, _ = port.fir_q15(np.ascontiguousarray(taps[::-1]), np.zeros(64 + 16, np.int16), x, 16)
+            assert np.array_equal(out[48 * rail:48 * rail + 48], y[64:].astype(np.int32)), (trial, rail)
+    bad = np.zeros(64, np.int16); bad[5] = 32700
+    assert lib.slb_design_q15_tc_block(bad.ctypes.data, bad.ctypes.data, np.zeros((112, 2), np.int16).ctypes.data, np.zeros(96, np.int32).ctypes.data) != 0
