@@ -33,7 +33,10 @@ constexpr int kPlaneBytes = (kChunksHist + kChunksNew) * kChunkBytes;   // 13312
 constexpr int kKSteps = 7;               // (64 + 48) frames * 2 bytes / 32
 constexpr int kBStep = 24 * 256;         // 192 rows x 32 bytes per K-step
 constexpr int kRawRow = kSuper * 4 + 16, kHistRow = kHist * 4 + 16;
-constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2;
+#ifndef SL_Q15TC_RAWSTAGES
+#define SL_Q15TC_RAWSTAGES 2
+#endif
+constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = SL_Q15TC_RAWSTAGES;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1, kThreads = 32 * (kProdWarp + 1);
 constexpr int kTmemCols = 512;           // xh products in columns [0,192), xl products in [192,384)
 
@@ -42,11 +45,11 @@ struct Smem
   static constexpr size_t a = 0;
   static constexpr size_t b = a + 2 * 2 * kPlaneBytes;
   static constexpr size_t raw = b + kTcQ15PlaneBytes;
-  static constexpr size_t hist = raw + 2 * kJ * kRawRow;
-  static constexpr size_t pk = hist + 2 * kJ * kHistRow;                // [4 tiles][16][8] int: block peaks of the last supertiles
+  static constexpr size_t hist = raw + kRawStages * kJ * kRawRow;
+  static constexpr size_t pk = hist + kRawStages * kJ * kHistRow;                // [4 tiles][16][8] int: block peaks of the last supertiles
   static constexpr size_t pkc = pk + 4 * kQ * kJ * 4;                   // [sets][16][8] int: peaks before the stream start, by 16 - age
   static constexpr size_t bars = pkc + kSets * kQ * kJ * 4;
-  static constexpr int n_bars = 16;
+  static constexpr int n_bars = 20;
   static constexpr size_t tmem_ptr = bars + n_bars * 8;
   static constexpr size_t bytes = tmem_ptr + 16;
 };
@@ -65,7 +68,12 @@ struct KParams
 
 #include "sl_tc_common.cuh"
 
+// (A/B: cvt.sat.s16.s32 is one instruction but runs on the conversion pipe: 403 vs 467 Gsamples/s; a third raw stage: no change)
+#ifdef SL_Q15TC_CVTSAT
+__device__ __forceinline__ int sat16 (int v) { short r; asm ("cvt.sat.s16.s32 %0, %1;" : "=h"(r) : "r"(v)); return (int) r; }
+#else
 __device__ __forceinline__ int sat16 (int v) { return max (-32768, min (32767, v)); }
+#endif
 
 __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_constant__ KParams P)
 {
@@ -73,16 +81,17 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
   unsigned char *sA = smem + Smem::a, *sB = smem + Smem::b, *sRaw = smem + Smem::raw, *sHist = smem + Smem::hist;
   int *sPk = reinterpret_cast<int *> (smem + Smem::pk), *sPkC = reinterpret_cast<int *> (smem + Smem::pkc);
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
-  uint64_t *raw_full = bars, *raw_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 6, *t_empty = bars + 8;
-  uint64_t *p_bar = bars + 9, *b_full = bars + 11, *t_full = bars + 12;
+  uint64_t *raw_full = bars, *raw_empty = bars + 3, *a_full = bars + 6, *a_empty = bars + 8, *t_empty = bars + 10;
+  uint64_t *p_bar = bars + 11, *b_full = bars + 13, *t_full = bars + 14;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *> (smem + Smem::tmem_ptr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0)
   {
+    for (int i = 0; i < kRawStages; i++) { mbar_init (raw_full + i, 1); mbar_init (raw_empty + i, kConvWarps); }
     for (int i = 0; i < 2; i++)
     {
-      mbar_init (raw_full + i, 1); mbar_init (raw_empty + i, kConvWarps); mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
+      mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
       mbar_init (p_bar + i, 4); mbar_init (t_full + i, 1);
     }
     mbar_init (t_empty, 4); mbar_init (b_full, 1);
@@ -112,9 +121,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
       for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
         for (uint32_t k = 0; k < supers; k++, kk++)
         {
-          const int rb = kk & 1;
+          const int rb = kk % kRawStages;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper), nv = group_nv (g);
-          mbar_wait (raw_empty + rb, ((kk >> 1) & 1) ^ 1);
+          mbar_wait (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
           mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
 #pragma unroll 1
           for (int j = 0; j < kJ; j++)
@@ -137,10 +146,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
       const uint32_t nv = group_nv (g);
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
-        const int rb = kk & 1, ab = kk & 1;
+        const int rb = kk % kRawStages, ab = kk & 1;
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
         unsigned char *Ahi = sA + ab * 2 * kPlaneBytes;
-        mbar_wait (raw_full + rb, (kk >> 1) & 1);
+        mbar_wait (raw_full + rb, (kk / kRawStages) & 1);
         mbar_wait (a_empty + ab, ((kk >> 1) & 1) ^ 1);
         if (cw == 0 && k == 0)
         {
