@@ -43,10 +43,11 @@ struct slb_ctx
   float *d_masks = nullptr; uint8_t *d_slot = nullptr; float *d_twiddle = nullptr;
   // tensor-core path of the RX-SSB-f32 chain (sl_rx_ssb_tc.cu): tap planes per mask slot, which slots it can serve
   uint8_t *d_planes = nullptr; bool tc_ok[SLB_MAX_MASKS] = {}; float tc_s0[SLB_MAX_MASKS] = {}; float tc_sz[SLB_MAX_MASKS] = {}; TcBiquadTables tc_tables{};
-  uint8_t *d_tx_planes = nullptr; float tx_unit[SLB_MAX_MASKS] = {};   // TX-SSB-f32 contexts: tc_ok[] then refers to these planes
+  uint8_t *d_tx_planes = nullptr; float tx_unit[SLB_MAX_MASKS] = {};
+  uint8_t *d_am_planes = nullptr; float am_unit[SLB_MAX_MASKS] = {};   // RX contexts: the AM slot's two-rail planes (sl_rx_am_tc.cu)   // TX-SSB-f32 contexts: tc_ok[] then refers to these planes
   // channel lists of the tensor-core launches, cached per channel range (the bulk paths cut the batch the same way every
   // call) and rebuilt when a mode or a mask changes (mode_version)
-  struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
+  struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0, groups_ssb = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
   std::map<uint64_t, TcLists> tc_lists; uint64_t mode_version = 0;
   bool force_fft = false;              // slb_set_rx_path (SLB_RX_PATH_FFT)
   int16_t *d_ovl[2] = { nullptr, nullptr }; int ovl_parity = 0;
@@ -127,8 +128,19 @@ static int upload_chain_constants (slb_ctx *ctx)
       CK (ctx, cudaStreamSynchronize (ctx->stream));
     }
     else
+    {
+      // the AM slot: both rails of the filter on the tensor cores, envelope and biquad in the epilogue (sl_rx_am_tc.cu)
+      std::vector<uint8_t> amp (kTcAmPlaneBytes, 0);
+      // Measured slower than the FFT kernel (135.7 vs 144.8 Gsamples/s at 1024 channels: 46 MMAs per supertile, one accumulator
+      // buffer, and the biquad recurrence back on the CUDA cores), so AM channels take it only on request: SELENITE_B200_AM_PATH=tc
+      const char *am_env = std::getenv ("SELENITE_B200_AM_PATH");
+      ctx->tc_ok[kAmMaskSlot] = am_env && std::strcmp (am_env, "tc") == 0 && N == 512 && tc_build_am_planes (ctx->masks_host.data () + (size_t) kAmMaskSlot * 2 * N, amp.data (), &ctx->am_unit[kAmMaskSlot]);
+      CK (ctx, cudaMemcpyAsync (ctx->d_am_planes + (size_t) kAmMaskSlot * kTcAmPlaneBytes, amp.data (), amp.size (), cudaMemcpyHostToDevice, ctx->stream));
+      CK (ctx, cudaStreamSynchronize (ctx->stream));
+    }
+    if (ctx->cfg.chain != SLB_CHAIN_TX_SSB_F32)
     for (int m = 0; m < SLB_MAX_MASKS; m++)
-      ctx->tc_ok[m] = N == 512 && m != kAmMaskSlot && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, ctx->rx.biquad, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m], &ctx->tc_sz[m]);
+      if (m != kAmMaskSlot) ctx->tc_ok[m] = N == 512 && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, ctx->rx.biquad, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m], &ctx->tc_sz[m]);
     CK (ctx, cudaMemcpyAsync (ctx->d_planes, planes.data (), planes.size (), cudaMemcpyHostToDevice, ctx->stream));
   }
   CK (ctx, cudaStreamSynchronize (ctx->stream));
@@ -199,6 +211,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   CKC (cudaMalloc (&ctx->d_masks, (size_t) SLB_MAX_MASKS * 2 * N * sizeof (float)));
   CKC (cudaMalloc (&ctx->d_planes, (size_t) SLB_MAX_MASKS * kTcPlaneBytes));
   CKC (cudaMalloc (&ctx->d_tx_planes, (size_t) SLB_MAX_MASKS * kTcTxPlaneBytes));
+  CKC (cudaMalloc (&ctx->d_am_planes, (size_t) SLB_MAX_MASKS * kTcAmPlaneBytes));
   CKC (cudaMalloc (&ctx->d_slot, C));
   CKC (cudaMalloc (&ctx->d_twiddle, kTwiddleFloats * sizeof (float)));
   for (int p = 0; p < 2; p++) CKC (cudaMalloc (&ctx->d_ovl[p], (size_t) C * ovl * 4));
@@ -231,7 +244,7 @@ void slb_destroy (slb_ctx *ctx)
   cudaDeviceSynchronize ();
   chan64_destroy (ctx->chan);
   rxq15_destroy (ctx->q15);
-  cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle); cudaFree (ctx->d_planes); cudaFree (ctx->d_tx_planes);
+  cudaFree (ctx->d_masks); cudaFree (ctx->d_slot); cudaFree (ctx->d_twiddle); cudaFree (ctx->d_planes); cudaFree (ctx->d_tx_planes); cudaFree (ctx->d_am_planes);
   for (auto &kv : ctx->tc_lists) cudaFree (kv.second.d);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
@@ -474,6 +487,8 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
         chan.insert (chan.end (), by_slot[slot].begin () + i, by_slot[slot].begin () + i + n);
       }
     const uint32_t G = (uint32_t) gstart.size ();
+    tl.groups_ssb = G;
+    for (uint32_t gi = 0; gi < G; gi++) if ((ginfo[gi] & 0xFFu) == (uint32_t) kAmMaskSlot) { tl.groups_ssb = gi; break; }   // slot-major: AM groups are last
     if (G != 0)
     {
       std::vector<uint32_t> pack (2 * (size_t) G + chan.size ());
@@ -505,20 +520,38 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
   }
   else if (tl.groups != 0)
   {
-    const uint32_t G = tl.groups;
+    const uint32_t G = tl.groups, Gs = tl.groups_ssb;
     const uint32_t ovl = ctx->rx.fft_len - ctx->rx.hop;
-    RxTcLaunch L{};
-    L.in = d_in; L.out = d_out; L.audio_dbg = dbg_audio; L.gain_dbg = dbg_gain;
-    L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
-    L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
-    L.gstart = tl.d; L.ginfo = tl.d + G; L.chan = tl.d + 2 * (size_t) G;
-    L.planes = ctx->d_planes; L.s0 = ctx->tc_s0; L.sz = ctx->tc_sz;
-    L.flag_final = ctx->flag_base + rx_ssb_f32_tiles (frames);
-    L.n_groups = G; L.frames = frames;
-    L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;
-    L.tables = &ctx->tc_tables;
-    CK (ctx, launch_rx_ssb_tc (L, ctx->sm_count, stream));
-    ctx->launches++;
+    if (Gs != 0)
+    {
+      RxTcLaunch L{};
+      L.in = d_in; L.out = d_out; L.audio_dbg = dbg_audio; L.gain_dbg = dbg_gain;
+      L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
+      L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
+      L.gstart = tl.d; L.ginfo = tl.d + G; L.chan = tl.d + 2 * (size_t) G;
+      L.planes = ctx->d_planes; L.s0 = ctx->tc_s0; L.sz = ctx->tc_sz;
+      L.flag_final = ctx->flag_base + rx_ssb_f32_tiles (frames);
+      L.n_groups = Gs; L.frames = frames;
+      L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;
+      L.tables = &ctx->tc_tables;
+      CK (ctx, launch_rx_ssb_tc (L, ctx->sm_count, stream));
+      ctx->launches++;
+    }
+    if (Gs != G)
+    {
+      RxAmTcLaunch L{};
+      L.in = d_in; L.out = d_out; L.audio_dbg = dbg_audio; L.gain_dbg = dbg_gain;
+      L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
+      L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
+      L.gstart = tl.d + Gs; L.ginfo = tl.d + G + Gs; L.chan = tl.d + 2 * (size_t) G;
+      L.planes = ctx->d_am_planes; L.unit = ctx->am_unit;
+      L.flag_final = ctx->flag_base + rx_ssb_f32_tiles (frames);
+      L.n_groups = G - Gs; L.frames = frames;
+      L.agc_target = ctx->rx.agc_target; L.agc_decay = ctx->rx.agc_decay; L.agc_floor = ctx->rx.agc_floor; L.agc_gmax = ctx->rx.agc_gmax;
+      L.tables = &ctx->tc_tables;
+      CK (ctx, launch_rx_am_tc (L, ctx->sm_count, stream));
+      ctx->launches++;
+    }
   }
   for (uint32_t i = 0; i < nch;)
   {

@@ -391,6 +391,42 @@ void tc_apply_tx_planes (const uint8_t *planes, float unit, const int16_t *windo
     }
 }
 
+// AM (complex detector): both rails of z = h * x on the interleaved I/Q byte planes, window byte m = 2 frame + rail:
+//   Re z[n] = sum_d hr[d] I - hi[d] Q,  Im z[n] = sum_d hi[d] I + hr[d] Q;  rows digit * 48 + n per output rail, 11 K-steps.
+bool tc_build_am_planes (const float *mask, uint8_t *planes, float *unit)
+{
+  double hr[kTcTaps], hi[kTcTaps];
+  if (!tc_design_taps (mask, hr, hi)) return false;
+  double mx = 0;
+  for (int d = 0; d < kTcTaps; d++) mx = std::fmax (mx, std::fmax (std::fabs (hr[d]), std::fabs (hi[d])));
+  const double lim = 8323071.0;
+  const float u = (float) (mx / (lim * 32768.0));
+  if (!(u > 1e-30f) || !std::isfinite (u)) return false;
+  const double sc = 1.0 / ((double) u * 32768.0);
+  *unit = u;
+  std::memset (planes, 0, kTcAmPlaneBytes);
+  for (int orail = 0; orail < 2; orail++)
+    for (int n = 0; n < 48; n++)
+      for (int m = 0; m < 352; m++)
+      {
+        const int f = m / 2, irail = m & 1, d = 128 + n - f;
+        if (d < 0 || d >= kTcTaps) continue;
+        const double v = (orail == 0) ? (irail ? -hi[d] : hr[d]) : (irail ? hr[d] : hi[d]);
+        const long long q = std::llround (v * sc);
+        if (std::llabs (q) > (long long) lim + 1) return false;
+        const int32_t h = (int32_t) q;
+        const int32_t l0 = ((h + 128) & 255) - 128, r1 = (h - l0) >> 8, l1 = ((r1 + 128) & 255) - 128, l2 = (r1 - l1) >> 8;
+        const int32_t dg[3] = { l2, l1, l0 };
+        const int ks = m / 32, kk = m % 32;
+        for (int g = 0; g < 3; g++)
+        {
+          const int row = g * 48 + n;
+          planes[(size_t) (orail * 11 + ks) * 18 * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)] = (uint8_t) (int8_t) dg[g];
+        }
+      }
+  return true;
+}
+
 // -----------------------------------------------------------------------------------------------------------
 // Ring index logic — follows Core/Src/dsp_if.c line by line (cited), with the sample stores left to the kernels.
 // -----------------------------------------------------------------------------------------------------------

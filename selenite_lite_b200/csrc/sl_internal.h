@@ -189,6 +189,22 @@ size_t rxq15_state_bytes (const RxQ15State *st);
 int rxq15_state_save (RxQ15State *st, char *dst);
 int rxq15_state_load (RxQ15State *st, const char *src);
 
+// ---- RX-SSB-f32 AM channels on the tensor cores (sl_rx_am_tc.cu): both rails of the complex filter, envelope detector ----
+constexpr size_t kTcAmPlaneBytes = 2 * 11 * 18 * 256;   // [rail Re|Im][K-step][digit*48+n][32 bytes]
+bool tc_build_am_planes (const float *mask_re_im, uint8_t *planes /* kTcAmPlaneBytes */, float *unit);
+struct RxAmTcLaunch
+{
+  const int16_t *in; int16_t *out; float *audio_dbg; float *gain_dbg;
+  const int16_t *ovl_in; int16_t *ovl_out; float *state; unsigned *flag;
+  const uint32_t *chan, *gstart, *ginfo;   // as RxTcLaunch
+  const uint8_t *planes;                   // [SLB_MAX_MASKS][kTcAmPlaneBytes]
+  const float *unit;                       // host, [SLB_MAX_MASKS]
+  unsigned flag_final; uint32_t n_groups, frames;
+  float agc_target, agc_decay, agc_floor, agc_gmax;
+  const TcBiquadTables *tables;
+};
+int launch_rx_am_tc (const RxAmTcLaunch &L, int sm_count, void *stream);
+
 // ---- RX-SSB-q15 on the tensor cores (sl_rx_q15_tc.cu): same chain, same state, bit-identical results ----
 constexpr size_t kTcQ15PlaneBytes = 7 * 24 * 256;
 bool q15_tc_build_planes (const int16_t *taps_i, const int16_t *taps_q, uint8_t *planes /* kTcQ15PlaneBytes */);

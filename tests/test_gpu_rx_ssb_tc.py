@@ -204,3 +204,52 @@ def test_host_path_cut_into_many_time_slices(best_oracle):
     assert np.array_equal(y_host, y_dev) and np.array_equal(yp.numpy(), y_dev)
     exp, _, _, _ = best_oracle.rx_ssb_f32(make().oracle_params(), x[0])
     check_int16(y_host[0], exp)
+
+
+def test_am_channels_on_the_tensor_cores(best_oracle):
+    """AM (FT-817 mode byte 0x04) has its own tensor-core kernel (sl_rx_am_tc.cu: both rails of the channel filter by
+    tcgen05.mma, envelope + biquad in the epilogue; opt-in with SELENITE_B200_AM_PATH=tc because the FFT kernel is faster for
+    AM): an all-AM batch is one launch, meets the oracle, agrees with the FFT
+    kernel, hands its state over to it and back, and several groups per CTA / host slices reproduce it bit for bit."""
+    import os
+    from test_gpu_rx_ssb_f32 import am_signal
+    C, T = 21, 768 * 4 + 384
+    x = am_signal(C, T)
+
+    def make(path=slb.RX_PATH_AUTO):
+        # the AM tensor-core kernel is opt-in (it measures slower than the FFT kernel): the knob is read when a context is created
+        os.environ["SELENITE_B200_AM_PATH"] = "tc"
+        try:
+            d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+        finally:
+            del os.environ["SELENITE_B200_AM_PATH"]
+        d.DSP_Set_Mode(slb.MODE_AM); d.set_rx_path(path)
+        return d
+    d = make(); n0 = d.kernel_launches()
+    y, audio, gain = run_gpu(d, x)
+    assert d.kernel_launches() - n0 == 1
+    y_fft, a_fft, _ = run_gpu(make(slb.RX_PATH_FFT), x)
+    assert one_lsb(y, y_fft)
+    prm = d.oracle_params(slb.MODE_AM)
+    for c in range(0, C, 4):
+        exp, a, g_, _ = best_oracle.rx_ssb_f32(prm, x[c])
+        tol = audio_tolerance(a)
+        assert np.all(np.abs(audio[c] - a) <= tol + 1e-12), (c, float(np.max(np.abs(audio[c] - a) / tol)))
+        assert np.allclose(gain[c], g_, rtol=2e-5)
+        check_int16(y[c], exp)
+    d2 = make(); xd = torch.from_numpy(x).cuda(); parts = []
+    cuts = [0, 768, 768 + 384, 768 * 3, T]
+    for i in range(4):
+        d2.set_rx_path(slb.RX_PATH_FFT if i % 2 else slb.RX_PATH_AUTO)
+        parts.append(d2.rx_process(xd[:, cuts[i]:cuts[i + 1]].contiguous()).cpu().numpy())
+    ya = np.concatenate(parts, axis=1)
+    for c in (0, 20):
+        exp, _, _, _ = best_oracle.rx_ssb_f32(prm, x[c])
+        check_int16(ya[c], exp)
+    os.environ["SELENITE_B200_TC_GRID"] = "2"; os.environ["SELENITE_B200_SLICE_BYTES"] = str(C * 4 * 1536)
+    try:
+        y2 = run_gpu(make(), x, want_audio=False)[0]
+        y_host = make().rx_process(x)
+    finally:
+        del os.environ["SELENITE_B200_TC_GRID"]; del os.environ["SELENITE_B200_SLICE_BYTES"]
+    assert np.array_equal(y2, y) and np.array_equal(y_host, y)
