@@ -953,7 +953,7 @@ static int process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, ui
 int slb_rx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream) { return process_device (ctx, d_in, d_out, frames, stream, false); }
 int slb_tx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uint32_t frames, void *stream) { return process_device (ctx, d_in, d_out, frames, stream, true); }
 
-// SSB chains through host buffers: the batch is cut in TIME. Every slice carries all channels (strided 2-D copies
+// SSB chains (f32 and q15) through host buffers: the batch is cut in TIME. Every slice carries all channels (strided 2-D copies
 // straight from / to the caller's [channels][frames] arrays), so each launch is as wide as the batch — the tensor-core
 // kernel wants one channel group per SM — and the slices are small (~64 MB), so the copy that cannot overlap anything (the
 // first H2D, the last D2H) is a few per cent of the call. Slices of one stream depend on each other through the carried
@@ -1001,8 +1001,16 @@ static int process_host_sliced (slb_ctx *ctx, const int16_t *h_in, int16_t *h_ou
     CK (ctx, cudaMemcpy2DAsync (ctx->d_bulk_in[slot], row, reinterpret_cast<const char *> (h_in) + (size_t) t0 * 4, pitch, row, C, cudaMemcpyHostToDevice, s_in));
     CK (ctx, cudaEventRecord (ctx->slice_ev[slot][0], s_in));
     CK (ctx, cudaStreamWaitEvent (s_k, ctx->slice_ev[slot][0], 0));
-    { const int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], 0, C, n, nullptr, nullptr, s_k); if (rc) return rc; }
-    rx_advance (ctx, n);                                       // host bookkeeping of the carried state; the launches are stream-ordered
+    if (ctx->q15)
+    {
+      const int rc = rxq15_launch (ctx, ctx->q15, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], 0, C, n, ctx->sm_count, s_k, false); if (rc) return rc;
+      rxq15_advance (ctx->q15);
+    }
+    else
+    {
+      const int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], 0, C, n, nullptr, nullptr, s_k); if (rc) return rc;
+      rx_advance (ctx, n);                                     // host bookkeeping of the carried state; the launches are stream-ordered
+    }
     CK (ctx, cudaEventRecord (ctx->slice_ev[slot][1], s_k));
     CK (ctx, cudaStreamWaitEvent (s_out, ctx->slice_ev[slot][1], 0));
     CK (ctx, cudaMemcpy2DAsync (reinterpret_cast<char *> (h_out) + (size_t) t0 * 4, pitch, ctx->d_bulk_out[slot], row, row, C, cudaMemcpyDeviceToHost, s_out));
@@ -1023,7 +1031,7 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
   if (ctx->q15 && frames % ctx->geo.block_frames != 0) return fail (ctx, SLB_ERR_ARG, "frames must be a multiple of the 48-frame firmware block");
   const uint32_t C = ctx->cfg.channels;
   const size_t ch_bytes = (size_t) frames * 4;
-  if (chain) return process_host_sliced (ctx, h_in, h_out, frames);
+  if (chain || ctx->q15) return process_host_sliced (ctx, h_in, h_out, frames);   // (the integer chain is exact, so any cut at a block boundary reproduces the uncut stream)
   // channels are independent, so the batch is cut into channel groups and H2D / kernel / D2H of consecutive groups overlap
   uint32_t group = (uint32_t) ((size_t) (48u << 20) / ch_bytes);
   if (group < 1) group = 1;

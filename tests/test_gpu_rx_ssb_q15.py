@@ -177,3 +177,22 @@ def test_tcgen05_kernel_equals_the_mma_sync_kernel_bit_for_bit():
     whole = run(C, x, legacy=True)
     cut = run(C, x, legacy=False, cuts=[0, 48, 48 * 14, 768 + 48 * 3, T])
     assert np.array_equal(whole[0], cut[0]) and whole[3] == cut[3]
+
+
+def test_host_path_cut_into_time_slices_is_bit_exact():
+    """slb_rx_process_host for the q15 chain cuts the batch in time like the f32 chains: forced down to 1536-frame slices, a stream
+    of 6 slices and a 5-block remainder equals the device path bit for bit, state included."""
+    import os
+    import torch
+    C, T = 13, 1536 * 6 + 48 * 5
+    x = slb.synth_iq(C, T)
+    d_dev = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    y_dev = d_dev.rx_process(torch.from_numpy(x).cuda()).cpu().numpy()
+    os.environ["SELENITE_B200_SLICE_BYTES"] = str(C * 4 * 1536)
+    try:
+        d_host = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+        y_host = d_host.rx_process(x)
+    finally:
+        del os.environ["SELENITE_B200_SLICE_BYTES"]
+    assert np.array_equal(y_host, y_dev)
+    assert bytes(d_host.state_save()) == bytes(d_dev.state_save())
