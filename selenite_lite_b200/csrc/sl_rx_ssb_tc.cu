@@ -18,7 +18,8 @@
 //   instruction, 11 K-steps cover the 128 + 48 frame window. The A operand is the byte plane of the channel group's samples,
 //   ONCE: row group q is the same plane 48 frames (6 sixteen-byte chunks) further on, so the descriptor's row-group stride
 //   (SBO = 768 B) makes the 16 row groups alias one contiguous buffer — no Toeplitz expansion of the data, only of the
-//   (constant) map. An SS-mode MMA is bound by the fetch of its A tile (~128 clocks for N <= 192), so N = 192 is free.
+//   (constant) map. An SS-mode MMA is bound by its operand fetch ((4 KB of A + 32 N bytes of B) at ~74 B/clk, measured): N = 192
+//   instead of 144 costs 24 clocks per MMA and takes the whole per-sample recurrence off the CUDA cores.
 //
 //   Roles (warps): 2 x 4 epilogue warps (TMEM lane = (block q, channel j): int32 -> float, chain the 16 block end states,
 //   add the zero-input response, AGC envelope walk, gain, float -> q15, 192-byte stores), 2 converter warps (raw int16 ->
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // ========================================== MMA issuer ==========================================
     // The whole warp walks the loop converged and ONE elected lane issues: with `if (lane == 0)` around the loop the
     // compiler cannot keep descriptors in uniform registers and wraps every tcgen05.mma in a vote / broadcast loop —
-    // measured 128 clocks of issue per MMA against 72 of execution (N = 144), i.e. the tensor pipe sat idle 2/3 of the time.
+    // measured 128 clocks of issue per MMA against 116 of execution (N = 144).
     constexpr uint32_t id_ss64 = umma_idesc (64, 1, 1), id_ss128 = umma_idesc (128, 1, 1), id_ss192 = umma_idesc (192, 1, 1), id_us192 = umma_idesc (192, 0, 1);
     const uint32_t aBase = smem_u32 (sA), bBase = smem_u32 (sB);
     // constant upper halves of the descriptors: LBO = 128 (A and B), SBO = 768 (A, aliased row groups) / 256 (B), version 1
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           // accumulator columns: [0,64) weight 2^24 = xh h2, [64,128) 2^16 = xh h1 + xl h2, [128,192) 2^8 = xh h0 + xl h1, [192,256) 1 = xl h0;
           // inside each group of 64: 48 audio outputs, 4 end-state outputs, padding.
           // (Tried: two independent chains, xh * [h2|h1|h0] and xl * [h2|h1|h0] in disjoint columns, added in the epilogue. No faster —
-          // an SS-mode MMA with M = 128 is bound by the fetch of its 4 KB A tile, ~128 clocks whatever N <= 192 is
+          // an SS-mode MMA is bound by the fetch of its operands from shared memory, dependent or not
           // (tools/microbench/umma_rate.cu) — and it costs the second accumulator buffer.)
           umma_i8 (d, kDescA | aHi, kDescB | b0, id_ss64, 0u);                                   // xh * h2          -> [0,64)    fresh
           umma_i8 (d + kDig, kDescA | aLo, kDescB | b0, id_us192, 0u);                           // xl * [h2|h1|h0]  -> [64,256)  fresh

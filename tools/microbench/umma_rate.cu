@@ -8,7 +8,7 @@
 #include <cuda_runtime.h>
 
 __device__ __forceinline__ uint32_t smem_u32 (const void *p) { return (uint32_t) __cvta_generic_to_shared (p); }
-struct Cfg { uint32_t layout, a_lbo, a_sbo, b_lbo, b_sbo, n, f16, iters, a_step, b_step, ksteps; };
+struct Cfg { uint32_t layout, a_lbo, a_sbo, b_lbo, b_sbo, n, f16, iters, a_step, b_step, ksteps, alt; };
 
 __global__ void __launch_bounds__ (128, 1) rate (Cfg c, long long *out)
 {
@@ -31,26 +31,35 @@ __global__ void __launch_bounds__ (128, 1) rate (Cfg c, long long *out)
   __syncthreads ();
   asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_s;
-  if (threadIdx.x == 0)
+  if (threadIdx.x < 32)
   {
+    // the warp stays converged and ONE elected lane issues (descriptors in uniform registers): under `if (threadIdx.x == 0)`
+    // the compiler wraps every tcgen05.mma in a vote / broadcast loop and the ISSUE, not the tensor pipe, sets the pace
     const uint32_t idesc = c.f16 ? ((1u << 4) | ((c.n >> 3) << 17) | (8u << 24))                    // f16 x f16 -> f32
                                  : ((2u << 4) | (1u << 7) | (1u << 10) | ((c.n >> 3) << 17) | (8u << 24));   // s8 x s8 -> s32
     const uint64_t hi = ((uint64_t) (c.layout & 7) << 61) | (1ull << 46);
     const uint32_t a0 = smem_u32 (smem), b0 = smem_u32 (smem) + 96 * 1024;
     const long long t0 = clock64 ();
-    for (uint32_t it = 0; it < c.iters; it++)
-      for (uint32_t ks = 0; ks < c.ksteps; ks++)
-      {
-        const uint64_t da = hi | (uint64_t) (((a0 + ks * c.a_step) & 0x3FFFF) >> 4) | ((uint64_t) (c.a_lbo >> 4) << 16) | ((uint64_t) (c.a_sbo >> 4) << 32);
-        const uint64_t db = hi | (uint64_t) (((b0 + ks * c.b_step) & 0x3FFFF) >> 4) | ((uint64_t) (c.b_lbo >> 4) << 16) | ((uint64_t) (c.b_sbo >> 4) << 32);
-        if (c.f16)
-          asm volatile ("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
-        else
-          asm volatile ("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
-      }
-    asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32 (&bar)) : "memory");
+    uint32_t elected;
+    asm volatile ("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(elected));
+    if (elected)
+    {
+      for (uint32_t it = 0; it < c.iters; it++)
+        for (uint32_t ks = 0; ks < c.ksteps; ks++)
+        {
+          const uint64_t da = hi | (uint64_t) (((a0 + ks * c.a_step) & 0x3FFFF) >> 4) | ((uint64_t) (c.a_lbo >> 4) << 16) | ((uint64_t) (c.a_sbo >> 4) << 32);
+          const uint64_t db = hi | (uint64_t) (((b0 + ks * c.b_step) & 0x3FFFF) >> 4) | ((uint64_t) (c.b_lbo >> 4) << 16) | ((uint64_t) (c.b_sbo >> 4) << 32);
+          const uint32_t d = tmem + ((c.alt && (ks & 1)) ? 256u : 0u);              // alt: two independent accumulators, alternately
+          if (c.f16)
+            asm volatile ("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+          else
+            asm volatile ("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+        }
+      asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32 (&bar)) : "memory");
+    }
+    __syncwarp ();
     asm volatile ("{\n .reg .pred p;\n W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n @p bra D;\n bra W;\n D:\n}\n" ::"r"(smem_u32 (&bar)) : "memory");
-    out[blockIdx.x] = clock64 () - t0;
+    if (threadIdx.x == 0) out[blockIdx.x] = clock64 () - t0;
   }
   asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads ();
@@ -78,8 +87,9 @@ int main ()
   // K per instruction = 32 bytes for both kinds. Operand tiles: A 128 rows, B n rows.
   for (int ctas : { 1, 148 })
   {
-    for (uint32_t n : { 48u, 144u, 256u })
+    for (uint32_t n : { 48u, 96u, 144u, 192u, 256u })
     {
+      run ("no swizzle, A aliased, two independent accumulators alternately", Cfg{ 0, 128, 768, 128, 256, n, 0, 0, 256, 4608, 11, 1 }, ctas);
       // no swizzle: core matrix 8 rows x 16 B; LBO = 128 between the two K chunks, SBO = 256 between row groups; K-step advances by 4608 (B) / 256 (A, as the kernel's aliased plane)
       run ("no swizzle, A aliased (SBO 768), step as in the kernel", Cfg{ 0, 128, 768, 128, 256, n, 0, 0, 256, 4608, 11 }, ctas);
       run ("no swizzle, A plain (SBO 256)", Cfg{ 0, 128, 256, 128, 256, n, 0, 0, 4096, 8192, 8 }, ctas);
