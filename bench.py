@@ -2,12 +2,15 @@
 """bench.py — headline metric of BASELINE.json: complex Msamples/s of the fused RX chain, whole box, + HBM roofline.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-  (N > 1: launched by torchrun, one rank per GPU; channels shard with no data-path collective -> weak scaling)
 
-A step = one pass of the hot path (slb_rx_process_device, RX-SSB-f32 chain) over one batch of synthetic I/Q:
-BASELINE configs[1], 1024 independent 48 kHz channels per GPU x 10 s (480 000 frames) = 1.97 GB in + 1.97 GB out per
-GPU per step, far larger than the 126 MB L2. `value` has inputs resident in HBM; `e2e` is the same batch through the
-host-buffer C-ABI call (slb_rx_process_host: pinned host memory -> H2D -> kernel -> D2H, chunked and overlapped).
+A step = one pass of the hot path (slb_rx_process_device, RX-SSB-f32 chain) over one batch of synthetic I/Q.
+  N = 1: BASELINE configs[1], 1024 independent 48 kHz channels x 10 s (480 000 frames) = 1.97 GB in + 1.97 GB out per step.
+  N > 1 (torchrun, one rank per GPU): BASELINE configs[4], 65 536 channels x 1 s sharded as contiguous ranges of 65 536 / N
+         channels per GPU with NO data-path collective ("scaling": "strong"); after the timed compute the optional NCCL
+         all-gather of the decoded audio (shard.gather_audio) is timed on its own and reported under "gather".
+Both are far larger than the 126 MB L2. `value` has inputs resident in HBM; `e2e` is the same batch through the host-buffer
+C-ABI call (slb_rx_process_host: pinned host memory -> H2D -> kernel -> D2H, sliced and overlapped) with the plain pinned
+cudaMemcpyAsync duplex ceiling of the same bytes measured beside it on every rank at once (`e2e.pcie_ceiling_gbs`).
 """
 import argparse
 import json
@@ -28,7 +31,19 @@ FS = 48000
 SECONDS = 10
 FRAMES = FS * SECONDS          # 480 000 = 1250 hops of 384
 BYTES_PER_SAMPLE = 8           # 4 B int16 I/Q in + 4 B int16 L/R out
-WORKLOAD = "configs[1]: 1024 independent 48 kHz I/Q channels x 10 s per GPU, RX-SSB-f32 chain (overlap-save SSB demod + 2-stage biquad + AGC; filter and biquad block response evaluated as one exact integer contraction on tcgen05)"
+CHAIN_NOTE = "RX-SSB-f32 chain (overlap-save SSB demod + 2-stage biquad + AGC; filter and biquad block response evaluated as one exact integer contraction on tcgen05: int8 digit planes x int8 digit planes -> int32, then float32)"
+WORKLOAD = "configs[1]: 1024 independent 48 kHz I/Q channels x 10 s on one GPU, " + CHAIN_NOTE
+CONFIG5_CHANNELS = 65536       # BASELINE configs[4]: "65536-channel RX chain sharded across 2/4/8 B200, optional NCCL gather of decoded audio"
+CONFIG5_SECONDS = 1
+WORKLOAD5 = "configs[4]: 65536 independent 48 kHz I/Q channels x 1 s sharded over %d GPUs (%d channels per GPU, contiguous ranges, no data-path collective), " + CHAIN_NOTE
+
+
+def workload_for(world, seconds):
+    """(channels per GPU, frames per step, workload string, scaling)."""
+    if world == 1:
+        return CHANNELS_PER_GPU, FS * seconds, WORKLOAD, "weak"
+    c = CONFIG5_CHANNELS // world
+    return c, FS * CONFIG5_SECONDS, WORKLOAD5 % (world, c), "strong"
 
 
 def load_peaks():
@@ -143,12 +158,69 @@ def run_reference(args):
     tot_s = sum(t for _, t in times); tot_n = sum(n for n, _ in times)
     v = tot_n / tot_s / 1e6
     base["value"] = v
+    world = max(1, int(os.environ.get("WORLD_SIZE", args.gpus)))
+    _, _, workload, scaling = workload_for(world, SECONDS)
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(times), "higher_is_better": True, "scaling": "weak",
+                      "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(times), "higher_is_better": True, "scaling": scaling,
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample (%s)" % base["sample"]},
+                      "config": {"workload": workload, "note": "CPU arm: each step is a bounded sample (%s)" % base["sample"]},
                       "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}))
+
+
+def measure_traffic(args):
+    """DRAM bytes of ONE launch of the dominant kernel at the bench configuration, measured now, on this box: a short ncu pass
+    over this very script (--traffic-probe: build the same batch, launch the kernel a few times) that collects only
+    dram__bytes_read.sum and dram__bytes_write.sum. Returns (bytes, note)."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found on this box"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:rx_ssb_tc", "-s", "2", "-c", "1",
+           "--csv", sys.executable, os.path.abspath(__file__), "--traffic-probe", "--seconds", str(args.seconds)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, BENCH_NO_SAMPLER="1")).stdout
+        tot, seen = 0.0, 0
+        rows = [r for r in csv.reader(io.StringIO(out[out.index('"ID"'):]))]
+        hdr = rows[0]
+        for r in rows[1:]:
+            d = dict(zip(hdr, r))
+            if d.get("Metric Name") in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[d["Metric Unit"]]
+                tot += float(d["Metric Value"].replace(",", "")) * mult; seen += 1
+        if seen != 2:
+            return None, "ncu pass returned %d of 2 counters" % seen
+        return tot, "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu pass inside this bench run"
+    except Exception as exc:  # noqa: BLE001  (a profiler failure must not take the bench line down)
+        return None, "ncu pass failed: %s" % (str(exc)[:120])
+
+
+def traffic_probe(args):
+    """Child of measure_traffic(): the bench batch, a few launches, nothing else."""
+    import torch
+    import selenite_lite_b200 as slb
+    dev = torch.device("cuda", 0)
+    C, T, _, _ = workload_for(1, args.seconds)
+    d = slb.DspIf(C, fs=FS, chain=slb.CHAIN_RX_SSB_F32, device=0)
+    x = synth_on_gpu(torch, C, T, dev, first_channel=0)
+    y = torch.empty_like(x)
+    for _ in range(4):
+        d.rx_process(x, y)
+    torch.cuda.synchronize()
+
+
+def pin_rank_to_cores(local, world):
+    """Every rank gets its own slice of the host cores (the staging threads of 8 ranks otherwise migrate over one NUMA node)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(1, world))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return None
 
 
 def run_ours(args):
@@ -163,10 +235,12 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+    cores_per_rank = pin_rank_to_cores(local, world) if world > 1 else None
 
-    C, T = CHANNELS_PER_GPU, FS * args.seconds
+    C, T, workload, scaling = workload_for(world, args.seconds)
+    lo = rank * C                                             # this rank's contiguous channel range [lo, lo + C)
     d = slb.DspIf(C, fs=FS, chain=slb.CHAIN_RX_SSB_F32, device=local)
-    x = synth_on_gpu(torch, C, T, dev, first_channel=rank * C)
+    x = synth_on_gpu(torch, C, T, dev, first_channel=lo)
     y = torch.empty_like(x)
     torch.cuda.synchronize()
 
@@ -174,6 +248,13 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         d.rx_process(x, y)
@@ -197,10 +278,8 @@ def run_ours(args):
     step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     if os.environ.get("BENCH_DEBUG"):
         print("step_ms", [round(v, 3) for v in step_ms], file=sys.stderr)
-    total_ms = evs[0].elapsed_time(evs[-1])
+    total_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]))
     if dist is not None:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); total_ms = float(t.item())
         ln = torch.tensor([launches], device=dev, dtype=torch.int64); dist.all_reduce(ln); launches = int(ln.item())
     samples_per_step = C * T * world
     value = samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
@@ -211,15 +290,32 @@ def run_ours(args):
     achieved = C * T * BYTES_PER_SAMPLE / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "kernel": "rx_ssb_tc_kernel (sl_rx_ssb_tc.cu: tcgen05.mma kind::i8 FIR + biquad/AGC epilogue)", "algorithmic_bytes_per_launch": C * T * BYTES_PER_SAMPLE,
-                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f; bound by the A-operand fetch of the SS-mode MMAs and by the epilogue's FP32 work, not by HBM (DESIGN.md §4A)" % (achieved / 8000.0)}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
-    if os.path.exists(traffic_file):
-        try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch_bench")
-        except Exception:
-            pass
+                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f; the kernel is bound by the SM's L1 / shared-memory data pipe (tensor-core operand fetch + epilogue and converter traffic, ncu: 82 %% busy), not by HBM (DESIGN.md §4A)" % (achieved / 8000.0)}
 
-    # end to end through the host-buffer C-ABI call
+    # optional gather of the decoded audio over NCCL / NVLink (configs[4]), timed on its own AFTER the timed compute
+    gather = None
+    if dist is not None:
+        full = torch.empty((C * world, T, 2), dtype=torch.int16, device=dev)
+        for _ in range(2):
+            slb.shard.gather_audio(y, C * world, out=full)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_g = 3
+        g0.record()
+        for _ in range(n_g):
+            slb.shard.gather_audio(y, C * world, out=full)
+        g1.record()
+        barrier()
+        g_ms = max_over_ranks(g0.elapsed_time(g1) / n_g)
+        ok = bool(torch.equal(full[lo:lo + C], y))           # this rank's own shard sits where it belongs
+        recv = (world - 1) * C * T * 4                       # bytes every GPU receives over NVLink per gather
+        gather = {"op": "ncclAllGather of int16 audio [channels][frames][2] (one frame = one int32 word), every rank ends with all %d channels" % (C * world),
+                  "bytes_per_rank_in": C * T * 4, "bytes_per_rank_received": recv, "ms": g_ms, "recv_GBps_per_gpu": recv / (g_ms * 1e-3) / 1e9,
+                  "algbw_GBps": C * world * T * 4 / (g_ms * 1e-3) / 1e9, "own_shard_in_place": ok,
+                  "note": "after the timed compute, not part of `value`; NVLink peer-copy reference on this pool 770 GB/s per direction per GPU"}
+        del full
+
+    # end to end through the host-buffer C-ABI call, and the plain-copy ceiling of the same bytes beside it
     e2e = None
     if not args.no_e2e:
         xh = torch.empty((C, T, 2), dtype=torch.int16).pin_memory(); yh = torch.empty((C, T, 2), dtype=torch.int16).pin_memory()
@@ -233,11 +329,29 @@ def run_ours(args):
         for _ in range(n_e2e):
             d2.rx_process_pinned(xh, yh)                     # returns after the D2H copy of the result has landed
         barrier()
-        dt = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
-        e2e = {"value": samples_per_step * n_e2e / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": C * T * 4 * world, "d2h_bytes_per_step": C * T * 4 * world,
-               "steps": n_e2e, "path": "slb_rx_process_host: pinned host -> strided H2D -> rx_ssb_tc_kernel -> strided D2H, 64 MB time slices of all channels, copies and kernels on 3 streams"}
+        dt = max_over_ranks(time.perf_counter() - t0)
+        # ceiling: the same bytes as ONE contiguous pinned cudaMemcpyAsync each way, both directions at once, all ranks at once
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def duplex():
+            with torch.cuda.stream(s_in):
+                x.copy_(xh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh.copy_(y, non_blocking=True)
+        duplex(); barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            duplex()
+        barrier()
+        dt_c = max_over_ranks(time.perf_counter() - t0)
+        ceil_gbs = C * T * 4 * n_e2e / dt_c / 1e9            # per GPU, each way
+        e2e_val = samples_per_step * n_e2e / dt / 1e6
+        ceil_val = samples_per_step * n_e2e / dt_c / 1e6
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": C * T * 4 * world, "d2h_bytes_per_step": C * T * 4 * world,
+               "steps": n_e2e, "pcie_ceiling_gbs": ceil_gbs, "pcie_ceiling_msamples": ceil_val, "frac_of_ceiling": e2e_val / ceil_val,
+               "ceiling_how": "same bytes as one contiguous pinned cudaMemcpyAsync H2D + one D2H per step on two streams, every rank at once, GB/s per GPU each way",
+               "host_cores_per_rank": cores_per_rank,
+               "path": "slb_rx_process_host: pinned host -> strided H2D -> rx_ssb_tc_kernel -> strided D2H, time slices of all channels, copies and kernels on 3 streams"}
         del xh, yh, d2
 
     # the other chains of the library at the same width, device-resident, for context (not the headline metric)
@@ -274,21 +388,25 @@ def run_ours(args):
         other["chan64_f32"] = {"Msamples_per_s": S * Tw / (ms * 1e-3) / 1e6, "hbm_frac": S * Tw * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9 / peak,
                                "note": "config 4: 64 x 192 kHz wideband streams -> 4096 narrowband channels"}
         del dd, xw, yw
+        torch.cuda.empty_cache()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu_baseline = cpu_reference_run(os.cpu_count() or 1, budget_s=12.0)[0]
+    if rank == 0 and world == 1 and not args.no_traffic:
+        roofline["traffic"], roofline["traffic_how"] = measure_traffic(args)
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
     if rank != 0:
         return
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "channels_per_gpu": C, "frames_per_step": T, "fs": FS, "chain": "rx_ssb_f32",
-                   "l2_policy": "inputs larger than L2 (3.9 GB touched per step per GPU vs 126 MB L2)", "parallelism": "channels sharded, no collective"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "other_chains": other}))
+        "config": {"workload": workload, "channels_per_gpu": C, "channels_total": C * world, "frames_per_step": T, "fs": FS, "chain": "rx_ssb_f32",
+                   "arithmetic": "filter + biquad block response: int8 x int8 -> int32 digit products of int16 samples and a 24-bit-quantised map (exact for that map); state chain, AGC, pack: float32",
+                   "l2_policy": "inputs larger than L2 (%.1f GB touched per step per GPU vs 126 MB L2)" % (C * T * 8 / 1e9), "parallelism": "channels sharded, no collective"},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gather": gather, "gpu_launches": launches, "clocks": clocks, "other_chains": other}))
 
 
 def main():
@@ -300,9 +418,13 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-other", action="store_true", help="skip the context measurements of the other chains")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu pass that measures the kernel's DRAM traffic")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--seconds", type=int, default=SECONDS, help="signal seconds per channel per step (profiling runs only; the headline uses the default)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.traffic_probe:
+        traffic_probe(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -326,7 +326,21 @@ void DSP_Out_Buff_Read (uint16_t *pbuf, uint16_t size);
 void DSP_Out_Buff_Mute (void);
 /* the rest of the firmware's sample-path surface, single channel: the I2S DMA double buffer and its two completion
  * callbacks (dsp_if.c:32, :50-67; hi2s is ignored) and the USB class dispatcher (usbd_audio_if.c:179-202) */
-typedef struct { uint16_t rx[768]; uint16_t tx[768]; } SLB_I2S_Buff_TypeDef;   /* I2S_BUFF_SIZE = 4 fs/1000 entries are used */
+/* i2s_buff has the layout of the firmware's I2S_Buff_TypeDef (dsp_if.h:75-79): rx[I2S_BUFF_SIZE]; tx[I2S_BUFF_SIZE] with
+ * I2S_BUFF_SIZE = 2 * (2 * USBD_AUDIO_FREQ / 1000) half-words (dsp_if.h:69-73) — 192 at 48 kHz, 384 at 96 kHz, 768 at 192 kHz. As in
+ * the firmware the size is compile-time: build the consumer with the same -DUSBD_AUDIO_FREQ as dsp_if.h would see (default 48000,
+ * dsp_if.h:55-57) and run the library with the same rate (SELENITE_B200_FS): the library places tx at
+ * I2S_BUFF_SIZE of ITS rate. The object the
+ * library exports is storage for the largest geometry, so every rate's struct is a prefix-compatible view of it. */
+#ifndef USBD_AUDIO_FREQ
+#define USBD_AUDIO_FREQ 48000U
+#endif
+#define SLB_I2S_BUFF_SIZE (2U * ((USBD_AUDIO_FREQ * 2U) / 1000U))
+#ifdef SLB_BUILDING_LIBRARY
+typedef struct { uint16_t words[2 * 768]; } SLB_I2S_Buff_TypeDef;                /* rx = words, tx = words + I2S_BUFF_SIZE of the run-time rate */
+#else
+typedef struct { uint16_t rx[SLB_I2S_BUFF_SIZE]; uint16_t tx[SLB_I2S_BUFF_SIZE]; } SLB_I2S_Buff_TypeDef;
+#endif
 extern SLB_I2S_Buff_TypeDef i2s_buff;
 void HAL_I2SEx_TxRxHalfCpltCallback (void *hi2s);
 void HAL_I2SEx_TxRxCpltCallback (void *hi2s);

@@ -194,10 +194,10 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   slb_ctx *ctx = new slb_ctx ();
   ctx->cfg = *cfg; ctx->geo = Geometry (cfg->fs);
   cudaDeviceGetAttribute (&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  // the float chains keep 48-frame AGC / ALC blocks at every rate (the kernels' block; the release time is kept by scaling the
+  // decay with fs in design_default_*): 1 ms at 48 kHz, half a firmware block at 96 kHz, a quarter at 192 kHz
   design_default_rx_f32 (cfg->fs, &ctx->rx);
-  ctx->rx.agc_block = ctx->geo.block_frames;
   design_default_tx_f32 (cfg->fs, &ctx->tx);
-  ctx->tx.alc_block = ctx->geo.block_frames;
   const uint32_t C = cfg->channels, N = ctx->rx.fft_len, hop = ctx->rx.hop, ovl = N - hop, R = ctx->geo.ring_frames;
 
   ctx->masks_host.assign ((size_t) SLB_MAX_MASKS * 2 * N, 0.0f);
@@ -1032,7 +1032,8 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
   const uint32_t C = ctx->cfg.channels;
   const size_t ch_bytes = (size_t) frames * 4;
   if (chain || ctx->q15) return process_host_sliced (ctx, h_in, h_out, frames);   // (the integer chain is exact, so any cut at a block boundary reproduces the uncut stream)
-  // channels are independent, so the batch is cut into channel groups and H2D / kernel / D2H of consecutive groups overlap
+  // PASS (the firmware as shipped): channels are independent, so the batch is cut into channel groups and H2D / copy kernel / D2H of
+  // consecutive groups overlap
   uint32_t group = (uint32_t) ((size_t) (48u << 20) / ch_bytes);
   if (group < 1) group = 1;
   if (group > C) group = C;
@@ -1058,26 +1059,11 @@ static int process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint
     cudaStream_t st = ctx->bulk_stream[slot];
     const size_t bytes = (size_t) n * ch_bytes;
     CK (ctx, cudaMemcpyAsync (ctx->d_bulk_in[slot], reinterpret_cast<const char *> (h_in) + (size_t) c0 * ch_bytes, bytes, cudaMemcpyHostToDevice, st));
-    if (chain)
-    {
-      int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], c0, n, frames, nullptr, nullptr, st);
-      if (rc) return rc;
-    }
-    else if (ctx->q15)
-    {
-      int rc = rxq15_launch (ctx, ctx->q15, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], c0, n, frames, ctx->sm_count, st, false);
-      if (rc) return rc;
-    }
-    else
-    {
-      CK (ctx, launch_copy_iq (ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], (size_t) n * frames, st));
-      ctx->launches++;
-    }
+    CK (ctx, launch_copy_iq (ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], (size_t) n * frames, st));
+    ctx->launches++;
     CK (ctx, cudaMemcpyAsync (reinterpret_cast<char *> (h_out) + (size_t) c0 * ch_bytes, ctx->d_bulk_out[slot], bytes, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < kBulkSlots; s++) if (ctx->bulk_stream[s]) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
-  if (chain) rx_advance (ctx, frames);
-  if (ctx->q15) rxq15_advance (ctx->q15);
   return SLB_OK;
 }
 int slb_rx_process_host (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames) { return process_host (ctx, h_in, h_out, frames, false); }
@@ -1279,20 +1265,22 @@ void DSP_Out_Buff_Read (uint16_t *pbuf, uint16_t size) { DROPIN (SLB_DSP_Out_Buf
 void DSP_Out_Buff_Mute (void) { DROPIN (SLB_DSP_Out_Buff_Mute (c_)); }
 
 // the I2S DMA double buffer and its completion callbacks (dsp_if.c:32, :50-67) and the USB class dispatcher
-SLB_I2S_Buff_TypeDef i2s_buff;
+SLB_I2S_Buff_TypeDef i2s_buff;   // storage for the largest geometry; rx at 0, tx at I2S_BUFF_SIZE of the context's rate (dsp_if.h:75-79)
 void HAL_I2SEx_TxRxHalfCpltCallback (void *)
 {
   slb_ctx *c = dropin (); if (!c) return;
   const uint16_t half = (uint16_t) c->geo.i2s_half_hw;
-  DSP_Out_Buff_Read (i2s_buff.tx, half);
-  DSP_In_Buff_Write (i2s_buff.rx, half);
+  uint16_t *rx = i2s_buff.words, *tx = i2s_buff.words + 2u * half;
+  DSP_Out_Buff_Read (tx, half);
+  DSP_In_Buff_Write (rx, half);
 }
 void HAL_I2SEx_TxRxCpltCallback (void *)
 {
   slb_ctx *c = dropin (); if (!c) return;
   const uint16_t half = (uint16_t) c->geo.i2s_half_hw;
-  DSP_Out_Buff_Read (&i2s_buff.tx[half], half);
-  DSP_In_Buff_Write (&i2s_buff.rx[half], half);
+  uint16_t *rx = i2s_buff.words, *tx = i2s_buff.words + 2u * half;
+  DSP_Out_Buff_Read (&tx[half], half);
+  DSP_In_Buff_Write (&rx[half], half);
 }
 int8_t AUDIO_AudioCmd_FS (uint8_t *pbuf, uint32_t size, uint8_t cmd) { DROPIN (SLB_AUDIO_AudioCmd (c_, pbuf, size, cmd)); return 0; /* USBD_OK, unconditionally (usbd_audio_if.c:200) */ }
 

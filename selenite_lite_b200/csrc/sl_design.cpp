@@ -32,7 +32,7 @@ int design_default_rx_f32 (uint32_t fs, slb_rx_f32_params *p)
   biquad_lp (3000.0, 0.54119610014619698, (double) fs, p->biquad);
   biquad_lp (3000.0, 1.30656296487637653, (double) fs, p->biquad + 5);
   p->agc_target = 0.25f;                                                 // -12 dBFS
-  p->agc_decay = (float) std::exp (-1.0 / 300.0);                        // 300 ms release at the 1 ms block cadence
+  p->agc_decay = (float) std::exp (-(48.0 / (double) fs) / 0.300);       // 300 ms release; one step per 48-frame block (1 ms at 48 kHz)
   p->agc_floor = 1.0e-4f;
   p->agc_gmax = 100.0f;                                                  // +40 dB
   return SLB_OK;
@@ -45,7 +45,7 @@ int design_default_tx_f32 (uint32_t fs, slb_tx_f32_params *p)
   std::memset (p, 0, sizeof *p);
   p->fft_len = 512; p->hop = 384; p->alc_block = 48;
   p->alc_target = 0.5f;                                                  // -6 dBFS peak envelope of I + jQ
-  p->alc_decay = (float) std::exp (-1.0 / 100.0);                        // 100 ms release at the 1 ms block cadence
+  p->alc_decay = (float) std::exp (-(48.0 / (double) fs) / 0.100);       // 100 ms release; one step per 48-frame block (1 ms at 48 kHz)
   p->alc_floor = 1.0e-3f;
   p->alc_gmax = 16.0f;                                                   // +24 dB
   return SLB_OK;
@@ -250,8 +250,8 @@ bool tc_design_taps (const float *mask, double *hr /* kTcTaps */, double *hi)
 // so the taps operand holds W = G T (48 audio rows) and Z = Sigma T (4 state rows) instead of the bare Toeplitz T: the
 // tensor cores deliver the block's zero-state audio and end state, the CUDA cores only chain the states and add the
 // zero-input response (arm_biquad_cascade_df2T_f32.c:551-562 is linear, so the split is exact). Rows are quantised to 24
-// bits (audio and state rows with their own scale), three balanced base-256 digits, rows digit * 64 + r (r < 48 audio,
-// 48..51 state, rest zero), K-major no-swizzle core matrices; window byte m = 32 ks + kk = frame m / 2, rail m & 1.
+// bits (audio and state rows with their own scale), three balanced base-256 digits, rows digit * 52 + r (r < 48 audio,
+// 48..51 state; rows 156..159 zero), K-major no-swizzle core matrices; window byte m = 32 ks + kk = frame m / 2, rail m & 1.
 bool tc_build_planes (const float *mask, const float *cf, uint8_t *planes, float *unit_a, float *unit_z)
 {
   double hr[kTcTaps], hi[kTcTaps];
@@ -303,11 +303,11 @@ bool tc_build_planes (const float *mask, const float *cf, uint8_t *planes, float
       if (std::llabs (q) > (long long) lim + 1) return false;
       const int32_t h = (int32_t) q;
       const int32_t l0 = ((h + 128) & 255) - 128, r1 = (h - l0) >> 8, l1 = ((r1 + 128) & 255) - 128, l2 = (r1 - l1) >> 8;
-      const int32_t dg[3] = { l2, l1, l0 };          // most significant first: accumulator columns 0..63 carry 2^24
+      const int32_t dg[3] = { l2, l1, l0 };          // most significant first: accumulator columns 0..51 carry 2^24
       const int ks = m / 32, kk = m % 32;
       for (int gdig = 0; gdig < 3; gdig++)
       {
-        const int row = gdig * 64 + r;
+        const int row = gdig * kTcDigit + r;
         planes[(size_t) ks * kTcRowGroups * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)] = (uint8_t) (int8_t) dg[gdig];
       }
     }
@@ -327,7 +327,7 @@ void tc_apply_planes (const uint8_t *planes, float unit_a, float unit_z, const i
       long long h = 0;
       for (int gdig = 0; gdig < 3; gdig++)
       {
-        const int row = gdig * 64 + r;
+        const int row = gdig * kTcDigit + r;
         h = h * 256 + (int8_t) planes[(size_t) ks * kTcRowGroups * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)];
       }
       acc += h * (long long) window[m];

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <string>
 #include <vector>
+#define SLB_BUILDING_LIBRARY 1   /* i2s_buff is declared as raw storage inside the library (include/selenite_b200.h) */
 #include "../../include/selenite_b200.h"
 
 namespace sl {
@@ -102,8 +103,9 @@ constexpr size_t kTwiddleFloats = 6 * 32 * 4;
 // is (the mask is the DFT of a 129-tap filter), evaluated by tcgen05.mma kind::i8 on byte planes of samples and taps ----
 constexpr int kTcTaps = 129;                       // fft_len - hop + 1
 constexpr int kTcChannels = 8;                     // channels of one group = the 8 rows of a shared-memory core matrix
-constexpr int kTcRowGroups = 24;                   // 3 digits x 64 rows (48 audio + 4 state + pad) / 8
-constexpr size_t kTcPlaneBytes = 11 * kTcRowGroups * 256;   // operand planes of one mask: [k-step][digit*64+row][32 bytes] in UMMA layout
+constexpr int kTcDigit = 52;                       // rows of one digit: 48 audio + 4 end-state outputs of a block
+constexpr int kTcRowGroups = 20;                   // 3 digits x 52 rows, padded to N = 160 (a multiple of 16), / 8
+constexpr size_t kTcPlaneBytes = 11 * kTcRowGroups * 256;   // operand planes of one mask: [k-step][digit*52+row][32 bytes] in UMMA layout
 struct TcBiquadTables
 {
   float coef[10];                       // stage 0 {b0,b1,b2,a1,a2}, stage 1 {...}

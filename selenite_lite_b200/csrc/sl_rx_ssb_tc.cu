@@ -14,16 +14,16 @@
 // of one float32 epsilon of the INPUT level like the oracle's own FFT noise (tolerances: DESIGN.md §3.5).
 //
 //   MMA shape: M = 128 rows = 8 channels (the 8 rows of a core matrix) x 16 consecutive firmware blocks (row groups),
-//   N = 64 outputs of a block (48 audio + 4 end-state + pad) x 3 digits, K = 32 bytes = 16 frames (I, Q bytes) per
+//   N = 160 = 52 outputs of a block (48 audio + 4 end-state) x 3 digits + 4 rows of padding, K = 32 bytes = 16 frames (I, Q bytes) per
 //   instruction, 11 K-steps cover the 128 + 48 frame window. The A operand is the byte plane of the channel group's samples,
 //   ONCE: row group q is the same plane 48 frames (6 sixteen-byte chunks) further on, so the descriptor's row-group stride
 //   (SBO = 768 B) makes the 16 row groups alias one contiguous buffer — no Toeplitz expansion of the data, only of the
-//   (constant) map. An SS-mode MMA is bound by its operand fetch ((4 KB of A + 32 N bytes of B) at ~74 B/clk, measured): N = 192
-//   instead of 144 costs 24 clocks per MMA and takes the whole per-sample recurrence off the CUDA cores.
+//   (constant) map. An SS-mode MMA is bound by its operand fetch ((4 KB of A + 32 N bytes of B) at ~74 B/clk, measured): N = 160
+//   instead of 144 costs 8 clocks per MMA and takes the whole per-sample recurrence off the CUDA cores.
 //
 //   Roles (warps): 2 x 4 epilogue warps (TMEM lane = (block q, channel j): int32 -> float, chain the 16 block end states,
 //   add the zero-input response, AGC envelope walk, gain, float -> q15, 192-byte stores), 2 converter warps (raw int16 ->
-//   byte planes, PRMT only), 1 MMA issuer (one elected lane, 23 tcgen05.mma per supertile), 1 bulk-copy producer.
+//   byte planes, PRMT only), 1 MMA issuer (one elected lane, 22 tcgen05.mma per supertile), 1 bulk-copy producer.
 //   mbarrier pipelines: raw stages, A planes (2), TMEM accumulators (2), biquad / envelope carry between supertiles.
 //
 // Oracle stage per box as in sl_rx_ssb_f32.cu; the chain sits where the firmware would call it (Core/Src/dsp_if.c:286-289).
@@ -48,15 +48,16 @@ constexpr int kChunksHist = kHist / 8;   // 16
 constexpr int kChunksNew = kSuper / 8;   // 96
 constexpr int kPlaneBytes = (kChunksHist + kChunksNew) * kChunkBytes;   // 14336
 constexpr int kKSteps = 11;              // (128 + 48) frames * 2 bytes / 32
-constexpr int kBStep = kTcRowGroups * 256; // B bytes per K-step: 24 row groups (3 digits x 64 rows: 48 audio + 4 state + pad) x 2 chunks x 128 B
-constexpr int kDig = 64;                 // accumulator columns per digit weight
+constexpr int kBStep = kTcRowGroups * 256; // B bytes per K-step: 20 row groups (3 digits x 52 rows: 48 audio + 4 state; 4 rows of padding) x 2 chunks x 128 B
+constexpr int kDig = kTcDigit;           // accumulator columns per digit weight (52)
+constexpr int kN = kTcRowGroups * 8;     // 160 = the N of every MMA
 constexpr int kRawRow = kSuper * 4 + 16; // raw stage row (one channel), padded: conflict-free 16-byte reads across channels
 constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_SETS
 #define SL_TC_SETS 2
 #endif
 #ifndef SL_TC_RAWSTAGES
-#define SL_TC_RAWSTAGES 2
+#define SL_TC_RAWSTAGES 3
 #endif
 #ifndef SL_TC_REGSPLIT
 #define SL_TC_REGSPLIT 0
@@ -64,15 +65,20 @@ constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_BULKOUT
 #define SL_TC_BULKOUT 0
 #endif
+#ifndef SL_TC_MMA_UNROLL
+#define SL_TC_MMA_UNROLL 1
+#endif
 #ifndef SL_TC_STHINT
 #define SL_TC_STHINT ".L1::no_allocate"   /* measured: plain 366, .cg 371, .cs 376, .L1::no_allocate 408 Gsamples/s */
 #endif
+constexpr int kMmaUnroll = SL_TC_MMA_UNROLL;
 constexpr int kSets = SL_TC_SETS;                 // epilogue warp sets (warpgroups), taking supertiles in turn
 constexpr int kRawStages = SL_TC_RAWSTAGES;            // raw stages: a bulk copy takes ~4400 clocks to land (measured), a supertile ~3000
 constexpr int kEpiWarps = 4 * kSets;
 constexpr int kConvWarps = 2;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);   // 16 warps = 4 warpgroups: 3 epilogue sets + {2 converters, MMA issuer, producer}
+static_assert (kSets == 2, "an epilogue set owns one accumulator buffer (it zeroes the buffer's top-digit columns)");
 static_assert (!SL_TC_REGSPLIT || kThreads == 512, "register split below assumes 4 warpgroups");
 constexpr int kOutRow = 4 * kBlk * 4 + 16;  // output stage of one epilogue warp: a channel's four blocks (768 B) + pad, ...
 constexpr int kOutStage = 4 * kOutRow;     // ... four channels at a time
@@ -189,6 +195,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   tc_fence_after ();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t supers = P.supers;
+  // Columns [0,52) of both accumulator buffers start at zero: the xh MMAs accumulate into them (see the MMA issuer); afterwards
+  // the epilogue set that drains a buffer zeroes them again.
+  if (warp < kEpiWarps) tmem_zero<kDig> (tmem + (uint32_t) (warp >> 2) * 256u + ((uint32_t) (32 * (warp & 3)) << 16));
+  tc_fence_before ();
+  __syncthreads ();
+  tc_fence_after ();
   // register split between the warpgroups (the launch gives every thread 128): the epilogue holds a 48-sample block plus
   // 64 accumulator words per thread, the copy / convert / issue roles need little
   // (the whole warpgroup executes ONE setmaxnreg: the three small roles share warpgroup 3 and release together, as a
@@ -212,7 +224,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         {
           const int rb = kk % kRawStages;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
-          mbar_wait (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
+          mbar_wait_long (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
           TC_STAMP (0);
           mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
@@ -247,9 +259,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         const int rb = kk % kRawStages, ab = kk & 1;
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
         unsigned char *Ahi = sA + ab * 2 * kPlaneBytes;
-        mbar_wait (raw_full + rb, (kk / kRawStages) & 1);
+        mbar_wait_long (raw_full + rb, (kk / kRawStages) & 1);
         if (cw == 0) TC_STAMP (1);
-        mbar_wait (a_empty + ab, ((kk >> 1) & 1) ^ 1);                         // the MMAs of supertile kk - 2 have read this buffer
+        mbar_wait_long (a_empty + ab, ((kk >> 1) & 1) ^ 1);                         // the MMAs of supertile kk - 2 have read this buffer
         if (cw == 0) TC_STAMP (2);
         if (cw == 0 && k == 0)
         {
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // The whole warp walks the loop converged and ONE elected lane issues: with `if (lane == 0)` around the loop the
     // compiler cannot keep descriptors in uniform registers and wraps every tcgen05.mma in a vote / broadcast loop —
     // measured 128 clocks of issue per MMA against 116 of execution (N = 144).
-    constexpr uint32_t id_ss64 = umma_idesc (64, 1, 1), id_ss128 = umma_idesc (128, 1, 1), id_ss192 = umma_idesc (192, 1, 1), id_us192 = umma_idesc (192, 0, 1);
+    constexpr uint32_t id_ss = umma_idesc (kN, 1, 1), id_us = umma_idesc (kN, 0, 1);
     const uint32_t aBase = smem_u32 (sA), bBase = smem_u32 (sB);
     // constant upper halves of the descriptors: LBO = 128 (A and B), SBO = 768 (A, aliased row groups) / 256 (B), version 1
     constexpr uint64_t kDescA = ((uint64_t) (kChunkBytes >> 4) << 16) | ((uint64_t) ((6 * kChunkBytes) >> 4) << 32) | (1ull << 46);
@@ -352,29 +364,32 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         const int ab = kk & 1, tb = kk & 1;
-        mbar_wait (a_full + ab, (kk >> 1) & 1);
+        mbar_wait_long (a_full + ab, (kk >> 1) & 1);
         TC_STAMP (4);
-        mbar_wait (t_empty + tb, ((kk >> 1) & 1) ^ 1);                       // the epilogue has drained this accumulator buffer
+        mbar_wait_long (t_empty + tb, ((kk >> 1) & 1) ^ 1);                       // the epilogue has drained this accumulator buffer and zeroed its columns [0,52)
         TC_STAMP (5);
         tc_fence_after ();
         const uint32_t d = tmem + (uint32_t) tb * 256u;
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4), b0 = bBase >> 4;
         if (elect_one ())
         {
-          // accumulator columns: [0,64) weight 2^24 = xh h2, [64,128) 2^16 = xh h1 + xl h2, [128,192) 2^8 = xh h0 + xl h1, [192,256) 1 = xl h0;
-          // inside each group of 64: 48 audio outputs, 4 end-state outputs, padding.
+          // accumulator columns: [0,52) weight 2^24 = xh h2, [52,104) 2^16 = xh h1 + xl h2, [104,156) 2^8 = xh h0 + xl h1, [156,208) 1 = xl h0;
+          // inside each group of 52: 48 audio outputs, 4 end-state outputs. Both planes meet the SAME operand [h2|h1|h0] (N = 160,
+          // rows 156..159 zero), xl one digit to the right of xh. The first xl MMA starts columns [52,212) afresh; columns [0,52)
+          // were zeroed by the epilogue set that drained the buffer (N must be a multiple of 16: there is no MMA that could
+          // start exactly these 52 columns), so every xh MMA accumulates.
           // (Tried: two independent chains, xh * [h2|h1|h0] and xl * [h2|h1|h0] in disjoint columns, added in the epilogue. No faster —
           // an SS-mode MMA is bound by the fetch of its operands from shared memory, dependent or not
           // (tools/microbench/umma_rate.cu) — and it costs the second accumulator buffer.)
-          umma_i8 (d, kDescA | aHi, kDescB | b0, id_ss64, 0u);                                   // xh * h2          -> [0,64)    fresh
-          umma_i8 (d + kDig, kDescA | aLo, kDescB | b0, id_us192, 0u);                           // xl * [h2|h1|h0]  -> [64,256)  fresh
-          umma_i8 (d + kDig, kDescA | aHi, kDescB | (b0 + ((8 * 256) >> 4)), id_ss128, 1u);      // xh * [h1|h0]     -> [64,192)  accumulate
-#pragma unroll
-          for (int ks = 1; ks < kKSteps; ks++)
+#pragma unroll kMmaUnroll
+          for (int ks = 0; ks < kKSteps; ks++)
           {
+#ifdef SL_TC_ABLATE_MMA                                                             // (profiling aid: what the MMAs cost)
+            if (ks > 0) break;
+#endif
             const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStep) >> 4;
-            umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss192, 1u);
-            umma_i8 (d + kDig, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us192, 1u);
+            umma_i8 (d + kDig, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us, ks ? 1u : 0u);
+            umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss, 1u);
           }
           umma_commit (t_full + (kk & 3));  // accumulators complete -> epilogue
           umma_commit (a_empty + ab);       // planes read -> converter may overwrite them
@@ -408,7 +423,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
         const int nblk = (int) (nfr / kBlk);
         const bool last_q = q == nblk - 1;
-        mbar_wait (t_full + (kk & 3), (kk >> 2) & 1);
+        mbar_wait_long (t_full + (kk & 3), (kk >> 2) & 1);
         tc_fence_after ();
         if (w == 0) TC_STAMP (7);
         // ---- accumulators -> float: y = (D24 2^24 + D16 2^16 + D8 2^8 + D0) * unit (arm_q15_to_float's 1/32768 folded in)
@@ -431,18 +446,22 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         }
         float z[4];
         {
-          uint32_t v0[8], v1[8], v2[8], v3[8];
-          tmem_ld8 (taddr + 48, v0); tmem_ld8 (taddr + kDig + 48, v1); tmem_ld8 (taddr + 2 * kDig + 48, v2); tmem_ld8 (taddr + 3 * kDig + 48, v3);
+          uint32_t v0[4], v1[4], v2[4], v3[4];
+          tmem_ld4 (taddr + 48, v0); tmem_ld4 (taddr + kDig + 48, v1); tmem_ld4 (taddr + 2 * kDig + 48, v2); tmem_ld4 (taddr + 3 * kDig + 48, v3);
           tmem_ld_wait ();
           const float z8 = z0s * 256.0f, z16 = z0s * 65536.0f, z24 = z0s * 16777216.0f;
 #pragma unroll
           for (int r = 0; r < 4; r++)
             z[r] = fmaf (__int2float_rn ((int) v0[r]), z24, fmaf (__int2float_rn ((int) v1[r]), z16, fmaf (__int2float_rn ((int) v2[r]), z8, __int2float_rn ((int) v3[r]) * z0s)));
         }
+        tmem_zero<kDig> (taddr);                                                   // the next supertile's xh MMAs accumulate into these columns
         tc_fence_before ();
         __syncwarp ();
         if (lane == 0) mbar_arrive (t_empty + tb);                               // the accumulator buffer now lives in registers
         if (w == 0) TC_STAMP (8);
+#ifdef SL_TC_ABLATE_EPI                                                             // (profiling aid: the kernel without the epilogue's arithmetic and stores)
+        if (y[0] != 123.456f || z[0] != 1.0f) continue;
+#endif
 
         // (y[] already IS the zero-state response of the biquad cascade over the block — the operand planes hold the FIR
         //  composed with it — and columns 48..51 of each digit group hold the cascade's end state from a zero start)
@@ -524,6 +543,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           y[n] = fmaf (C[0], st[0], fmaf (C[1], st[1], fmaf (C[2], st[2], fmaf (C[3], st[3], y[n]))));
           peak = fmaxf (peak, fabsf (y[n]));
         }
+#ifndef SL_TC_ENVSCAN                                                              // (default: the sequential walk; -DSL_TC_ENVSCAN: A/B alternative below)
         myPk[q * kJ + j] = peak;
         if (kk != 0) mbar_wait (e_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
         envc = (k == 0) ? __ldcg (P.state + (size_t) c * 8 + 4) : sCarryE[((kk - 1) & 1) * kJ + j];
@@ -538,6 +558,37 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           const float p = myPk[qq * kJ + j];
           if (qq <= q) e = fmaxf (p, e * decay);
         }
+#else
+        // ---- AGC envelope: the oracle's sequential walk env_b = max(peak_b, fl(env_{b-1} * decay)) over the blocks before and
+        // including this one. x -> fl(x * decay) is monotonic, so fl(max(a, b) * decay) = max(fl(a * decay), fl(b * decay)) and the
+        // walk equals a max-scan whose step of distance d applies the rounded multiply d times — bit for bit (the FFT kernel's
+        // env_scan, sl_rx_ssb_f32.cu). Inside the warp: its four blocks of channel j sit in lanes j, j + 8, j + 16, j + 24.
+        float e = peak;
+        {
+          const float t1 = __shfl_up_sync (0xffffffffu, e, 8) * decay;
+          if (a >= 1) e = fmaxf (e, t1);
+          const float t2 = (__shfl_up_sync (0xffffffffu, e, 16) * decay) * decay;
+          if (a >= 2) e = fmaxf (e, t2);
+        }
+        if (a == 3) myPk[w * kJ + j] = e;                                          // the warp's four blocks from a zero envelope
+        if (kk != 0) mbar_wait (e_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
+        envc = (k == 0) ? __ldcg (P.state + (size_t) c * 8 + 4) : sCarryE[((kk - 1) & 1) * kJ + j];
+        if (w == 0) TC_STAMP (12);
+        named_bar (2 + 3 * es, 128);
+        if (w == 0) TC_STAMP (13);
+        {
+          // envelope at the end of the block before the warp's first one, then decayed to this block
+          float cin = envc;
+#pragma unroll
+          for (int ww = 0; ww < 3; ww++)
+            if (ww < w) cin = fmaxf (myPk[ww * kJ + j], (((cin * decay) * decay) * decay) * decay);
+          float t = cin * decay;
+          if (a >= 1) t *= decay;
+          if (a >= 2) t *= decay;
+          if (a >= 3) t *= decay;
+          e = fmaxf (e, t);
+        }
+#endif
         if (last_q)
         {
           sCarryE[(kk & 1) * kJ + j] = e;

@@ -55,29 +55,28 @@ struct OpMagSqF32 { const float2 *a; float *d; __device__ void operator() (size_
 struct OpMagF32 { const float2 *a; float *d; __device__ void operator() (size_t i) const {                                                          // arm_cmplx_mag_f32.c:72 via arm_sqrt_f32 (arm_math.h:5726)
   float2 x = a[i]; float v = __fadd_rn (__fmul_rn (x.x, x.x), __fmul_rn (x.y, x.y)); d[i] = v >= 0.0f ? __fsqrt_rn (v) : 0.0f; } };
 
-// arm_sqrt_q15.c:50-140 : float-bit-trick seed, three q15 Newton steps, multiply back. Every cast is the reference's.
-__device__ __forceinline__ int16_t sqrt_q15 (int16_t in)
+// q15 square root with the exact integer results of arm_sqrt_q15.c:50-140: normalise by an even shift so the mantissa m lies in
+// [0.25, 1), seed r ~ 1/sqrt(m) from the float bit pattern, refine r three times in q15 (every intermediate truncated to 16 bits
+// where the reference truncates), sqrt = m * r, then undo half the normalisation shift.
+__device__ __forceinline__ int16_t trunc16 (int v) { return (int16_t) v; }
+__device__ __forceinline__ int16_t sqrt_q15 (int16_t x)
 {
-  int16_t number = in, temp1, var1, signBits1, half;
-  if (number <= 0) return 0;
-  signBits1 = (int16_t) (__clz ((int) number) - 17);
-  number = (int16_t) (((signBits1 % 2) == 0) ? (number << signBits1) : (number << (signBits1 - 1)));
-  half = (int16_t) (number >> 1);
-  temp1 = number;
-  float tf = __fmul_rn ((float) number, 3.051757812500000e-005f);
-  int bits = 0x5f3759df - (__float_as_int (tf) >> 1);
-  tf = __int_as_float (bits);
-  var1 = (int16_t) (int) __float2int_rz (__fmul_rn (tf, 16384.0f));
+  if (x <= 0) return 0;
+  const int lead = __clz ((int) x) - 17;                 // redundant sign bits of the 16-bit value
+  const int even_shift = lead & ~1;                      // the reference shifts by lead or lead - 1, whichever is even
+  const int16_t m = trunc16 ((int) x << even_shift);
+  const int16_t m_half = trunc16 (m >> 1);
+  const float seed = __int_as_float (0x5f3759df - (__float_as_int (__fmul_rn ((float) m, 1.0f / 32768.0f)) >> 1));
+  int16_t r = trunc16 (__float2int_rz (__fmul_rn (seed, 16384.0f)));
 #pragma unroll
-  for (int it = 0; it < 3; it++)
+  for (int step = 0; step < 3; step++)
   {
-    int16_t sq = (int16_t) (((int) var1 * var1) >> 15);
-    int16_t hs = (int16_t) (((int) sq * (int) half) >> 15);
-    var1 = (int16_t) (((int16_t) (((int) var1 * (0x3000 - hs)) >> 15)) << 2);
+    const int16_t r2 = trunc16 (((int) r * r) >> 15);
+    const int16_t t = trunc16 (((int) r2 * m_half) >> 15);
+    r = trunc16 ((int) trunc16 (((int) r * (0x3000 - t)) >> 15) << 2);
   }
-  var1 = (int16_t) (((int16_t) (((int) temp1 * var1) >> 15)) << 1);
-  var1 = (int16_t) (((signBits1 % 2) == 0) ? (var1 >> (signBits1 / 2)) : (var1 >> ((signBits1 - 1) / 2)));
-  return var1;
+  const int16_t root = trunc16 ((int) trunc16 (((int) m * r) >> 15) << 1);
+  return trunc16 (root >> (even_shift >> 1));
 }
 struct OpMagQ15 { const short2 *a; int16_t *d; __device__ void operator() (size_t i) const {                                                         // arm_cmplx_mag_q15.c:120-130, result in 2.14
   short2 x = a[i]; long long acc = (long long) ((int) x.x * x.x) + (long long) ((int) x.y * x.y); d[i] = sqrt_q15 ((int16_t) (acc >> 17)); } };

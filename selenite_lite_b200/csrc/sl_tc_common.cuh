@@ -19,6 +19,32 @@ __device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
   asm volatile ("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
                 ::"r"(smem_u32 (bar)), "r"(parity) : "memory");
 }
+// The same for the roles that wait long (producer, converters, MMA issuer, an epilogue set waiting for its accumulators): a
+// plain try_wait loop polls every ~20 clocks, and every poll is a shared-memory wavefront on the L1 data pipe the tensor core
+// fetches its operands through (ncu, round 2: 411 polls per supertile = 10 % of that pipe). Here the try_wait carries a
+// suspend-time hint and a failed poll backs off with nanosleep.
+#ifndef SL_TC_WAIT_HINT_NS
+#define SL_TC_WAIT_HINT_NS 2000
+#endif
+#ifndef SL_TC_WAIT_SLEEP_NS
+#define SL_TC_WAIT_SLEEP_NS 64
+#endif
+__device__ __forceinline__ void mbar_wait_long (uint64_t *bar, unsigned parity)
+{
+#if SL_TC_WAIT_SLEEP_NS == 0 && SL_TC_WAIT_HINT_NS == 0
+  mbar_wait (bar, parity);
+#else
+  uint32_t done;
+  do
+  {
+    asm volatile ("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+                  : "=r"(done) : "r"(smem_u32 (bar)), "r"(parity), "r"((unsigned) SL_TC_WAIT_HINT_NS) : "memory");
+#if SL_TC_WAIT_SLEEP_NS > 0
+    if (!done) __nanosleep (SL_TC_WAIT_SLEEP_NS);
+#endif
+  } while (!done);
+#endif
+}
 __device__ __forceinline__ void bulk_g2s (void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {
   asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -76,6 +102,23 @@ __device__ __forceinline__ void tmem_ld8 (uint32_t addr, uint32_t *v)
 {
   asm volatile ("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld4 (uint32_t addr, uint32_t *v)
+{
+  asm volatile ("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+// zero `cols` (a multiple of 4) accumulator columns of the calling thread's TMEM lane
+template <int cols> __device__ __forceinline__ void tmem_zero (uint32_t addr)
+{
+  const uint32_t z = 0u;
+#pragma unroll
+  for (int c = 0; c + 16 <= cols; c += 16)
+    asm volatile ("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(addr + c), "r"(z) : "memory");
+  if (cols % 16 >= 8)
+    asm volatile ("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(addr + cols / 16 * 16), "r"(z) : "memory");
+  if (cols % 8 >= 4)
+    asm volatile ("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%1,%1,%1};" ::"r"(addr + cols / 8 * 8), "r"(z) : "memory");
+  asm volatile ("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait () { asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

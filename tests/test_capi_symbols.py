@@ -84,3 +84,16 @@ def test_default_design_is_sane():
     # time response is 129 taps: overlap-save with 128 carried frames is exact linear filtering
     h = np.fft.ifft(usb.astype(np.complex128))
     assert np.max(abs(h[129:])) < 1e-6
+
+
+def test_i2s_buff_has_the_firmware_layout(tmp_path):
+    """i2s_buff must look to a dsp_if.h consumer like the firmware's I2S_Buff_TypeDef (dsp_if.h:69-79): rx[I2S_BUFF_SIZE];
+    tx[I2S_BUFF_SIZE] with I2S_BUFF_SIZE = 2 * (2 fs / 1000) half-words — compile-time, from USBD_AUDIO_FREQ, default 48000."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include "selenite_b200.h"\n'
+                   '_Static_assert (offsetof (SLB_I2S_Buff_TypeDef, tx) == 2 * WANT, "tx offset");\n'
+                   '_Static_assert (sizeof (SLB_I2S_Buff_TypeDef) == 4 * WANT, "size");\n'
+                   'int main (void) { return (int) sizeof (i2s_buff.rx) != 2 * WANT; }\n')
+    for flags, want in (([], 192), (["-DUSBD_AUDIO_FREQ=48000U"], 192), (["-DUSBD_AUDIO_FREQ=96000U"], 384), (["-DUSBD_AUDIO_FREQ=192000U"], 768)):
+        subprocess.run(["gcc", "-std=c11", "-fsyntax-only", "-DWANT=%d" % want, "-I", os.path.join(ROOT, "include")] + flags + [str(src)], check=True)

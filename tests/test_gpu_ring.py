@@ -182,7 +182,8 @@ def test_firmware_names_i2s_callbacks_and_audiocmd():
     and AUDIO_AudioCmd_FS (usbd_audio_if.c:179-202) drive the same global context as DSP_*."""
     lib = _lib.load()
     lib.DSP_Init()
-    buf_t = (C.c_uint16 * 768) * 2
+    # I2S_Buff_TypeDef at 48 kHz (dsp_if.h:69-79): rx[192]; tx[192] — the layout a dsp_if.h consumer compiled for this rate sees
+    buf_t = (C.c_uint16 * 192) * 2
     i2s = buf_t.in_dll(lib, "i2s_buff")
     ring, fns = oracle_ring(48000)
     in_write, in_read, out_write, out_read, ptrs, mute = fns

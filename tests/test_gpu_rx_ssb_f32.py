@@ -223,3 +223,30 @@ def test_am_envelope_detector(best_oracle):
     # the demodulated AM audio carries the modulating tone: envelope swing ~ depth around the carrier level
     a = audio[0][1536:]
     assert 0.5 < (a.max() - a.min()) / (2 * a.mean()) < 0.7
+
+
+@pytest.mark.parametrize("fs", [96000, 192000])
+@pytest.mark.parametrize("path", [slb.RX_PATH_AUTO, slb.RX_PATH_FFT])
+def test_shipped_sample_rate(best_oracle, fs, path):
+    """The firmware ships at 96 kHz (USB_DEVICE/Class/usbd_audio.h:46; geometry dsp_if.h:69-85), config 4 runs at 192 kHz. The
+    float chain keeps its 48-frame AGC block at every rate (slb_get_rx_f32_params says so and the oracle is fed from it),
+    masks and biquads are designed for fs, the AGC release time is kept by scaling the decay with fs."""
+    C, T = 6, 1536 * 3
+    d = slb.DspIf(C, fs=fs, chain=slb.CHAIN_RX_SSB_F32); d.set_rx_path(path)
+    p = d.rx_params()
+    assert p.agc_block == 48 and abs(p.agc_decay - np.exp(-(48.0 / fs) / 0.3)) < 1e-7
+    d.set_rx_params(p)                                                    # a get-modify-set round trip is accepted
+    x = slb.synth_iq(C, T, fs=fs)
+    modes = [slb.MODE_USB, slb.MODE_LSB, slb.MODE_DIG]
+    for c in range(C):
+        d.DSP_Set_Mode(modes[c % 3], channel=c)
+        if modes[c % 3] == slb.MODE_LSB:
+            x[c, :, 1] = -x[c, :, 1]
+    y, audio, gain = run_gpu(d, x)
+    for c in range(C):
+        exp, a, g_, _ = best_oracle.rx_ssb_f32(d.oracle_params(modes[c % 3]), x[c])
+        assert np.sqrt(np.mean(a.astype(np.float64) ** 2)) > 0.1          # the tone is inside the pass band at this rate too
+        err = np.abs(audio[c] - a); tol = audio_tolerance(a)
+        assert np.all(err <= tol + 1e-9), (c, float(np.max(err / (tol + 1e-9))))
+        assert np.allclose(gain[c], g_, rtol=2e-5)
+        check_int16(y[c], exp)

@@ -154,3 +154,24 @@ def test_tensor_core_and_fft_kernels_agree_and_hand_over(best_oracle):
     finally:
         del os.environ["SELENITE_B200_TC_GRID"]; del os.environ["SELENITE_B200_SLICE_BYTES"]
     assert np.array_equal(y3, y_tc) and np.array_equal(y_host, y_tc)
+
+
+@pytest.mark.parametrize("fs", [96000, 192000])
+def test_shipped_sample_rate(best_oracle, fs):
+    """96 kHz is what the firmware ships with (usbd_audio.h:46); the TX chain keeps its 48-frame ALC block at every rate."""
+    C, T = 5, 1536 * 2
+    d = slb.DspIf(C, fs=fs, chain=slb.CHAIN_TX_SSB_F32)
+    p = d.tx_params()
+    assert p.alc_block == 48 and abs(p.alc_decay - np.exp(-(48.0 / fs) / 0.1)) < 1e-7
+    d.set_tx_params(p)
+    x = slb.synth_mic(C, T, fs=fs)
+    modes = [slb.MODE_USB, slb.MODE_LSB]
+    for c in range(C):
+        d.DSP_Set_Mode(modes[c % 2], channel=c)
+    y, iq, gain = run_gpu(d, x)
+    for c in range(C):
+        exp, z, g_, _ = best_oracle.tx_ssb_f32(d.oracle_params(modes[c % 2]), x[c])
+        err = np.abs(iq[c] - z); tol = iq_tolerance(z)
+        assert np.all(err <= tol + 1e-9), (c, float(np.max(err / (tol + 1e-9))))
+        assert np.allclose(gain[c], g_, rtol=2e-5)
+        check_int16(y[c], exp)

@@ -35,13 +35,14 @@ def _worker(rank, world, port, C, T, ret):
     dist.barrier(); dist.destroy_process_group()
 
 
-def test_two_rank_shards_reassemble():
+@pytest.mark.parametrize("C", [5, 6])      # 5: shards of 2 and 3 (padded gather); 6: equal shards (one all-gather into the result)
+def test_two_rank_shards_reassemble(C):
     sys.path.insert(0, HERE)
     import oracle_lib
     import selenite_lite_b200 as slb
     from test_golden import GOLD, rx_params
-    C, T = 5, 384 * 3                                              # odd channel count: shards of 2 and 3
-    assert [slb.shard.shard_range(C, r, 2) for r in range(2)] == [(0, 2), (2, 5)]
+    T = 384 * 3
+    assert [slb.shard.shard_range(5, r, 2) for r in range(2)] == [(0, 2), (2, 5)]
     assert [slb.shard.shard_range(65536, r, 8) for r in range(8)][-1] == (57344, 65536)
     oracle_lib.build_oracles(want_ref=False)
     mgr = mp.Manager(); ret = mgr.dict()
