@@ -113,7 +113,8 @@ typedef struct
   float biquad[5 * SLO_MAX_STAGES];
   float agc_target, agc_decay, agc_floor, agc_gmax;
   const float *mask;  /* 2*fft_len, interleaved re/im, unscaled */
-  uint32_t envelope;  /* 0: product detector (real part), 1: AM envelope detector [cmplx_mag_f32] */
+  uint32_t envelope;  /* detector: 0: product detector (real part), 1: AM envelope detector [cmplx_mag_f32],
+                         2: FM limiter-discriminator [cmplx_conj, cmplx_mult_cmplx, cmplx_mag; see chains.inc.c] */
 } slo_rx_f32_params;
 
 typedef struct
@@ -121,7 +122,9 @@ typedef struct
   int16_t ovl[2 * SLO_MAX_FFT];       /* last (fft_len-hop) raw input frames, interleaved I,Q */
   float bq[2 * SLO_MAX_STAGES];       /* df2T d1,d2 per stage */
   float env;                          /* AGC envelope */
+  float zlast[2];                     /* FM: the last filtered baseband sample of the previous super-block (re, im) */
 } slo_rx_f32_state;
+#define SLO_FM_FLOOR 1.0e-8f          /* FM soft squelch: |z[n] conj z[n-1]| below this (|z| < 1e-4: no carrier, filter start-up) divides by this instead */
 
 /* frames % hop == 0. audio_dbg (optional) receives the post-biquad, pre-AGC float audio;
  * gain_dbg (optional) the per-agc_block gain. */

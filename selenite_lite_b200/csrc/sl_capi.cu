@@ -47,7 +47,7 @@ struct slb_ctx
   uint8_t *d_am_planes = nullptr; float am_unit[SLB_MAX_MASKS] = {};   // RX contexts: the AM slot's two-rail planes (sl_rx_am_tc.cu)   // TX-SSB-f32 contexts: tc_ok[] then refers to these planes
   // channel lists of the tensor-core launches, cached per channel range (the bulk paths cut the batch the same way every
   // call) and rebuilt when a mode or a mask changes (mode_version)
-  struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0, groups_ssb = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
+  struct TcLists { uint32_t *d = nullptr; size_t cap = 0; uint32_t groups = 0, groups_ssb = 0, n_chan = 0, n_pairs = 0; uint64_t version = ~0ull; std::vector<uint8_t> on_tc; };
   std::map<uint64_t, TcLists> tc_lists; uint64_t mode_version = 0;
   bool force_fft = false;              // slb_set_rx_path (SLB_RX_PATH_FFT)
   int16_t *d_ovl[2] = { nullptr, nullptr }; int ovl_parity = 0;
@@ -123,7 +123,7 @@ static int upload_chain_constants (slb_ctx *ctx)
     {
       std::vector<uint8_t> txp ((size_t) SLB_MAX_MASKS * kTcTxPlaneBytes, 0);
       for (int m = 0; m < SLB_MAX_MASKS; m++)
-        ctx->tc_ok[m] = N == 512 && m != kAmMaskSlot && tc_build_tx_planes (ctx->masks_host.data () + (size_t) m * 2 * N, txp.data () + (size_t) m * kTcTxPlaneBytes, &ctx->tx_unit[m]);
+        ctx->tc_ok[m] = N == 512 && m < kAmMaskSlot && tc_build_tx_planes (ctx->masks_host.data () + (size_t) m * 2 * N, txp.data () + (size_t) m * kTcTxPlaneBytes, &ctx->tx_unit[m]);
       CK (ctx, cudaMemcpyAsync (ctx->d_tx_planes, txp.data (), txp.size (), cudaMemcpyHostToDevice, ctx->stream));
       CK (ctx, cudaStreamSynchronize (ctx->stream));
     }
@@ -137,10 +137,16 @@ static int upload_chain_constants (slb_ctx *ctx)
       ctx->tc_ok[kAmMaskSlot] = am_env && std::strcmp (am_env, "tc") == 0 && N == 512 && tc_build_am_planes (ctx->masks_host.data () + (size_t) kAmMaskSlot * 2 * N, amp.data (), &ctx->am_unit[kAmMaskSlot]);
       CK (ctx, cudaMemcpyAsync (ctx->d_am_planes + (size_t) kAmMaskSlot * kTcAmPlaneBytes, amp.data (), amp.size (), cudaMemcpyHostToDevice, ctx->stream));
       CK (ctx, cudaStreamSynchronize (ctx->stream));
+      // the FM slot: the same two-rail planes; the limiter-discriminator exists on the complex-detector tensor-core kernel only
+      // (sl_rx_am_tc.cu), so an FM mask must be a 129-tap FIR (slb_set_mask refuses others)
+      std::fill (amp.begin (), amp.end (), (uint8_t) 0);
+      ctx->tc_ok[kFmMaskSlot] = N == 512 && tc_build_am_planes (ctx->masks_host.data () + (size_t) kFmMaskSlot * 2 * N, amp.data (), &ctx->am_unit[kFmMaskSlot]);
+      CK (ctx, cudaMemcpyAsync (ctx->d_am_planes + (size_t) kFmMaskSlot * kTcAmPlaneBytes, amp.data (), amp.size (), cudaMemcpyHostToDevice, ctx->stream));
+      CK (ctx, cudaStreamSynchronize (ctx->stream));
     }
     if (ctx->cfg.chain != SLB_CHAIN_TX_SSB_F32)
     for (int m = 0; m < SLB_MAX_MASKS; m++)
-      if (m != kAmMaskSlot) ctx->tc_ok[m] = N == 512 && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, ctx->rx.biquad, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m], &ctx->tc_sz[m]);
+      if (m < kAmMaskSlot) ctx->tc_ok[m] = N == 512 && tc_build_planes (ctx->masks_host.data () + (size_t) m * 2 * N, ctx->rx.biquad, planes.data () + (size_t) m * kTcPlaneBytes, &ctx->tc_s0[m], &ctx->tc_sz[m]);
     CK (ctx, cudaMemcpyAsync (ctx->d_planes, planes.data (), planes.size (), cudaMemcpyHostToDevice, ctx->stream));
   }
   CK (ctx, cudaStreamSynchronize (ctx->stream));
@@ -201,7 +207,7 @@ int slb_create (const slb_config *cfg, slb_ctx **out)
   const uint32_t C = cfg->channels, N = ctx->rx.fft_len, hop = ctx->rx.hop, ovl = N - hop, R = ctx->geo.ring_frames;
 
   ctx->masks_host.assign ((size_t) SLB_MAX_MASKS * 2 * N, 0.0f);
-  const uint8_t modes[7] = { SLB_MODE_LSB, SLB_MODE_USB, SLB_MODE_CW, SLB_MODE_CWR, SLB_MODE_DIG, SLB_MODE_PKT, SLB_MODE_AM };
+  const uint8_t modes[8] = { SLB_MODE_LSB, SLB_MODE_USB, SLB_MODE_CW, SLB_MODE_CWR, SLB_MODE_DIG, SLB_MODE_PKT, SLB_MODE_AM, SLB_MODE_FM };
   for (uint8_t m : modes) design_default_mask (cfg->fs, N, m, ctx->masks_host.data () + (size_t) mode_to_mask_slot (m) * 2 * N);
   ctx->mode_host.assign (C, SLB_MODE_USB);
   ctx->slot_host.assign (C, (uint8_t) mode_to_mask_slot (SLB_MODE_USB));
@@ -299,15 +305,26 @@ int slb_set_mask (slb_ctx *ctx, uint8_t mode, const float *mask)
 {
   if (!ctx || !mask) return SLB_ERR_ARG;
   const int slot = mode_to_mask_slot (mode);
-  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "mode has no spectral mask (FM)");
+  if (slot < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "not an FT-817 mode byte");
   CK (ctx, cudaSetDevice (ctx->cfg.device));
-  std::memcpy (ctx->masks_host.data () + (size_t) slot * 2 * ctx->rx.fft_len, mask, (size_t) 2 * ctx->rx.fft_len * sizeof (float));
-  return upload_chain_constants (ctx);
+  float *dst = ctx->masks_host.data () + (size_t) slot * 2 * ctx->rx.fft_len;
+  const std::vector<float> before (dst, dst + (size_t) 2 * ctx->rx.fft_len);
+  std::memcpy (dst, mask, (size_t) 2 * ctx->rx.fft_len * sizeof (float));
+  int rc = upload_chain_constants (ctx);
+  if (rc == SLB_OK && slot == kFmMaskSlot && ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32 && !ctx->tc_ok[kFmMaskSlot])
+  {
+    // the discriminator runs on the complex-detector tensor-core kernel only: the FM mask must be the DFT of a 129-tap filter
+    std::memcpy (dst, before.data (), before.size () * sizeof (float));
+    rc = upload_chain_constants (ctx);
+    return rc ? rc : fail (ctx, SLB_ERR_UNSUPPORTED, "an FM mask must be the DFT of a filter of at most 129 taps (the discriminator runs on the tensor-core kernel)");
+  }
+  return rc;
 }
 int slb_set_rx_path (slb_ctx *ctx, int path)
 {
   if (!ctx || (path != SLB_RX_PATH_AUTO && path != SLB_RX_PATH_FFT)) return SLB_ERR_ARG;
   ctx->force_fft = path == SLB_RX_PATH_FFT;
+  ctx->mode_version++;                 // the channel lists of run_rx_kernel depend on it
   return SLB_OK;
 }
 int slb_get_mask (const slb_ctx *ctx, uint8_t mode, float *mask)
@@ -376,9 +393,13 @@ int SLB_DSP_Set_TX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; ctx->tx_mode =
 // which FT-817 mode bytes (rxtx_if.h:33-43) a chain has a demodulator / modulator for
 static int check_mode (slb_ctx *ctx, uint8_t mode)
 {
-  if (mode_to_mask_slot (mode) < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "no FM discriminator in this build (AM, LSB, USB, CW, CW-R, DIG, PKT are served)");
+  if (mode_to_mask_slot (mode) < 0) return fail (ctx, SLB_ERR_UNSUPPORTED, "not an FT-817 mode byte (LSB, USB, CW, CW-R, AM, FM, DIG, PKT are served; rxtx_if.h:33-43)");
   if (mode == SLB_MODE_AM && ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 && ctx->cfg.chain != SLB_CHAIN_PASS)
     return fail (ctx, SLB_ERR_UNSUPPORTED, "AM is served by the RX-SSB-f32 chain (envelope detector) and the channelizer only");
+  if (mode == SLB_MODE_FM && ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 && ctx->cfg.chain != SLB_CHAIN_PASS)
+    return fail (ctx, SLB_ERR_UNSUPPORTED, "FM is served by the RX-SSB-f32 chain (limiter-discriminator) only");
+  if (mode == SLB_MODE_FM && ctx->cfg.chain == SLB_CHAIN_RX_SSB_F32 && !ctx->tc_ok[kFmMaskSlot])
+    return fail (ctx, SLB_ERR_UNSUPPORTED, "the FM slot has no tensor-core planes (fft_len must be 512 and the FM mask a 129-tap FIR)");
   return SLB_OK;
 }
 
@@ -461,8 +482,11 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
                           float *dbg_audio, float *dbg_gain, cudaStream_t stream)
 {
   const bool is_tx = ctx->cfg.chain == SLB_CHAIN_TX_SSB_F32;
-  if ((ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 && !is_tx) || !tc_path_enabled () || ctx->force_fft)
+  if (ctx->cfg.chain != SLB_CHAIN_RX_SSB_F32 && !is_tx)
     return run_rx_fft_kernel (ctx, d_in, d_out, ch0, nch, frames, dbg_audio, dbg_gain, stream);
+  // slb_set_rx_path (SLB_RX_PATH_FFT) / SELENITE_B200_RX_PATH=fft keep every channel on the FFT kernel — except FM, whose
+  // discriminator exists on the complex-detector tensor-core kernel only
+  const bool fft_only = !tc_path_enabled () || ctx->force_fft;
   slb_ctx::TcLists &tl = ctx->tc_lists[((uint64_t) ch0 << 32) | nch];
   if (tl.version != ctx->mode_version)
   {
@@ -472,7 +496,7 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
     for (uint32_t i = 0; i < nch; i++)
     {
       const uint8_t slot = ctx->slot_host[ch0 + i];
-      if (slot < SLB_MAX_MASKS && ctx->tc_ok[slot]) { by_slot[slot].push_back (i); tl.on_tc[i] = 1; n_tc++; }
+      if (slot < SLB_MAX_MASKS && ctx->tc_ok[slot] && (!fft_only || slot == kFmMaskSlot)) { by_slot[slot].push_back (i); tl.on_tc[i] = 1; n_tc++; }
     }
     std::vector<uint32_t> chan, gstart, ginfo;
     chan.reserve (n_tc);
@@ -488,12 +512,23 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
       }
     const uint32_t G = (uint32_t) gstart.size ();
     tl.groups_ssb = G;
-    for (uint32_t gi = 0; gi < G; gi++) if ((ginfo[gi] & 0xFFu) == (uint32_t) kAmMaskSlot) { tl.groups_ssb = gi; break; }   // slot-major: AM groups are last
+    for (uint32_t gi = 0; gi < G; gi++) if ((ginfo[gi] & 0xFFu) >= (uint32_t) kAmMaskSlot) { tl.groups_ssb = gi; break; }   // slot-major: AM and FM groups (complex detector) are last
+    // the RX-SSB kernel runs on CTA pairs (tcgen05.mma.cta_group::2 shares the map operand between two SMs): consecutive groups
+    // of one mask slot pair up, a slot's odd group gets a partner that only runs along (0xFFFFFFFF)
+    std::vector<uint32_t> pairs;
+    for (uint32_t gi = 0; gi < tl.groups_ssb;)
+    {
+      const bool two = gi + 1 < tl.groups_ssb && (ginfo[gi + 1] & 0xFFu) == (ginfo[gi] & 0xFFu);
+      pairs.push_back (gi); pairs.push_back (two ? gi + 1 : 0xFFFFFFFFu);
+      gi += two ? 2 : 1;
+    }
+    tl.n_chan = (uint32_t) chan.size (); tl.n_pairs = (uint32_t) (pairs.size () / 2);
     if (G != 0)
     {
-      std::vector<uint32_t> pack (2 * (size_t) G + chan.size ());
+      std::vector<uint32_t> pack (2 * (size_t) G + chan.size () + pairs.size ());
       std::memcpy (pack.data (), gstart.data (), G * 4); std::memcpy (pack.data () + G, ginfo.data (), G * 4);
       std::memcpy (pack.data () + 2 * (size_t) G, chan.data (), chan.size () * 4);
+      if (!pairs.empty ()) std::memcpy (pack.data () + 2 * (size_t) G + chan.size (), pairs.data (), pairs.size () * 4);
       // a kernel of an earlier call may still be reading the old lists (any stream): modes change rarely, so wait
       CK (ctx, cudaDeviceSynchronize ());
       if (pack.size () > tl.cap) { CK (ctx, cudaFree (tl.d)); tl.d = nullptr; CK (ctx, cudaMalloc (&tl.d, pack.size () * 4)); tl.cap = pack.size (); }
@@ -529,6 +564,7 @@ static int run_rx_kernel (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, uin
       L.ovl_in = ctx->d_ovl[ctx->ovl_parity] + (size_t) ch0 * ovl * 2; L.ovl_out = ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) ch0 * ovl * 2;
       L.state = ctx->d_state + (size_t) ch0 * 8; L.flag = ctx->d_flag + ch0;
       L.gstart = tl.d; L.ginfo = tl.d + G; L.chan = tl.d + 2 * (size_t) G;
+      L.pairs = tl.d + 2 * (size_t) G + tl.n_chan; L.n_pairs = tl.n_pairs;
       L.planes = ctx->d_planes; L.s0 = ctx->tc_s0; L.sz = ctx->tc_sz;
       L.flag_final = ctx->flag_base + rx_ssb_f32_tiles (frames);
       L.n_groups = Gs; L.frames = frames;

@@ -58,7 +58,8 @@ int mode_to_mask_slot (uint8_t mode)
     case SLB_MODE_LSB: return 0; case SLB_MODE_USB: return 1; case SLB_MODE_CW: return 2; case SLB_MODE_CWR: return 3;
     case SLB_MODE_DIG: return 4; case SLB_MODE_PKT: return 5;
     case SLB_MODE_AM: return kAmMaskSlot;                                // two-sided channel filter + envelope detector
-    default: return -1;                                                  // FM needs a discriminator (not built)
+    case SLB_MODE_FM: return kFmMaskSlot;                                // two-sided channel filter + limiter-discriminator
+    default: return -1;
   }
 }
 
@@ -83,6 +84,7 @@ int design_default_mask (uint32_t fs, uint32_t N, uint8_t mode, float *out)
     case SLB_MODE_CWR: lo = -950.0; hi = -450.0; break;
     case SLB_MODE_DIG: case SLB_MODE_PKT: lo = 300.0; hi = 3300.0; break;
     case SLB_MODE_AM: lo = -3000.0; hi = 3000.0; break;                  // carrier and both sidebands
+    case SLB_MODE_FM: lo = -7500.0; hi = 7500.0; break;                  // narrow-band FM channel: +-5 kHz deviation + 2.5 kHz audio (Carson)
     default: return SLB_ERR_UNSUPPORTED;
   }
   const int taps = (int) N / 4 + 1, mid = (taps - 1) / 2;

@@ -42,8 +42,10 @@ struct RingPtrs
 int design_default_rx_f32 (uint32_t fs, slb_rx_f32_params *out);
 int design_default_tx_f32 (uint32_t fs, slb_tx_f32_params *out);
 int design_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mask_out);
-int mode_to_mask_slot (uint8_t mode);   // -1 when the mode has no spectral mask (FM)
+int mode_to_mask_slot (uint8_t mode);   // -1 for a byte that is no FT-817 mode
 constexpr int kAmMaskSlot = 6;          // channels on this slot use the envelope detector (arm_cmplx_mag_f32) instead of Re
+constexpr int kFmMaskSlot = 7;          // channels on this slot use the limiter-discriminator (complex-detector tensor-core kernel only)
+constexpr float kFmFloor = 1.0e-8f;     // FM soft squelch: |z[n] conj z[n-1]| below this (no carrier, filter start-up) divides by this instead (oracle: SLO_FM_FLOOR)
 
 // Tables the time-parallel biquad needs, derived in double from the 2-stage df2T coefficients (sl_design.cpp).
 constexpr int kRun = 24;                // samples per run; a lane of the recurrence warp carries two runs = one AGC block
@@ -130,6 +132,7 @@ struct RxTcLaunch
   const uint32_t *chan;                    // channels served by this launch, grouped by mask slot
   const uint32_t *gstart;                  // [n_groups] index of the group's first channel in chan[]
   const uint32_t *ginfo;                   // [n_groups] mask slot | channels in the group (1..8) << 8
+  const uint32_t *pairs; uint32_t n_pairs; // [n_pairs][2]: the two groups (same mask slot) served by a CTA pair; second = 0xFFFFFFFF when the slot has an odd group
   const uint8_t *planes;                   // [SLB_MAX_MASKS][kTcPlaneBytes]
   const float *s0, *sz;                    // host, [SLB_MAX_MASKS]: units of the audio / state outputs
   unsigned flag_final;

@@ -48,7 +48,9 @@ struct Smem
   static constexpr size_t carry_s = pk + kSets * kQ * kJ * 4;           // [2][8][4] floats
   static constexpr size_t carry_e = carry_s + 2 * kJ * 4 * 4;           // [2][8] floats
   static constexpr size_t mp = carry_e + 2 * kJ * 4;                    // [4][20] floats: A^(48 a)
-  static constexpr size_t bars = mp + 4 * 20 * 4;
+  static constexpr size_t zl = mp + 4 * 20 * 4;                         // FM: [sets][4 warps][8] float2, last baseband sample of each warp's four blocks
+  static constexpr size_t carry_z = zl + kSets * 4 * kJ * 8;            // FM: [2][8] float2, last baseband sample of a supertile
+  static constexpr size_t bars = carry_z + 2 * kJ * 8;
   static constexpr int n_bars = 18;
   static constexpr size_t tmem_ptr = bars + n_bars * 8;
   static constexpr size_t bytes = tmem_ptr + 16;
@@ -83,6 +85,17 @@ __device__ __forceinline__ void matvec4 (const float *M, const float *x, const f
 {
 #pragma unroll
   for (int r = 0; r < 4; r++) y[r] = add[r] + (M[4 * r] * x[0] + M[4 * r + 1] * x[1] + M[4 * r + 2] * x[2] + M[4 * r + 3] * x[3]);
+}
+
+// FM limiter-discriminator, operation by operation as the oracle chain composes it: prev' = conj (prev) (arm_cmplx_conj_f32.c:71),
+// w = z * prev' (arm_cmplx_mult_cmplx_f32.c:72: re = a c - b d, im = a d + b c with every product and sum rounded — the
+// oracle build does not contract), m = |w| (arm_cmplx_mag_f32.c:72), d = Im w / max (m, floor).
+__device__ __forceinline__ float fm_discriminator (float a, float b, float pr, float pi)
+{
+  const float c = pr, d = -pi;
+  const float re = __fsub_rn (__fmul_rn (a, c), __fmul_rn (b, d)), im = __fadd_rn (__fmul_rn (a, d), __fmul_rn (b, c));
+  const float m = __fsqrt_rn (__fadd_rn (__fmul_rn (re, re), __fmul_rn (im, im)));
+  return __fdiv_rn (im, fmaxf (m, kFmFloor));
 }
 
 __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_constant__ KParams P)
@@ -282,6 +295,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
     // ========================================== epilogue ==========================================
     const int es = warp >> 2, w = warp & 3, a = lane >> 3, j = lane & 7, q = 4 * w + a;
     float *myW = sW + es * (4 * kJ * 4), *myPk = sPk + es * (kQ * kJ);
+    float2 *myZ = reinterpret_cast<float2 *> (smem + Smem::zl) + es * (4 * kJ), *sCarryZ = reinterpret_cast<float2 *> (smem + Smem::carry_z);
     const float *cf = P.tab.coef;
     const float decay = P.agc_decay;
     unsigned kk = 0;
@@ -291,6 +305,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
       const bool jvalid = (uint32_t) j < (gi >> 8);
       const uint32_t c = P.chan[P.gstart[g] + min ((uint32_t) j, (gi >> 8) - 1u)];
       const float s0 = P.unit[gi & 0xFFu], s8 = s0 * 256.0f, s16 = s0 * 65536.0f, s24 = s0 * 16777216.0f;
+      const bool fm = (gi & 0xFFu) == (uint32_t) kFmMaskSlot;                 // the group's detector: envelope (AM) or limiter-discriminator (FM)
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         if ((int) (kk % kSets) != es) continue;
@@ -299,8 +314,14 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
         const bool last_q = q == nblk - 1;
         mbar_wait (t_full + (kk & 1), (kk >> 1) & 1);
         tc_fence_after ();
-        // ---- accumulators -> float Re z, Im z -> envelope |z| (arm_cmplx_mag_f32.c:72: sqrt (re re + im im), each product rounded)
+        // ---- accumulators -> float Re z, Im z -> detector.
+        //   AM: envelope |z| (arm_cmplx_mag_f32.c:72: sqrt (re re + im im), each product rounded).
+        //   FM: w[n] = z[n] conj (z[n-1]) (arm_cmplx_conj_f32.c:71, arm_cmplx_mult_cmplx_f32.c:72: (ac - bd, ad + bc), products rounded),
+        //       d[n] = Im w[n] / max (|w[n]|, floor) (arm_cmplx_mag_f32 + one division): the sine of the carrier's phase step, amplitude
+        //       divided out. The oracle chain has no arctangent either (CMSIS-DSP V1.5.3 has none; oracle/chains.inc.c).
+        //       z[-1] of the block is the neighbouring thread's last sample: fetched below, d[0] is completed there.
         float y[kBlk];
+        float pr = 0.f, pi = 0.f, z0r = 0.f, z0i = 0.f;                            // FM: previous sample inside the block; the block's first sample
         const uint32_t taddr = tmem + ((uint32_t) (32 * w) << 16);
 #pragma unroll
         for (int i = 0; i < kBlk / 8; i++)
@@ -318,12 +339,39 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
           for (int n = 0; n < 8; n++)
           {
             const float zi = fmaf (__int2float_rn ((int) v0[n]), s24, fmaf (__int2float_rn ((int) v1[n]), s16, fmaf (__int2float_rn ((int) v2[n]), s8, __int2float_rn ((int) v3[n]) * s0)));
-            y[8 * i + n] = __fsqrt_rn (__fadd_rn (__fmul_rn (zr[n], zr[n]), __fmul_rn (zi, zi)));
+            if (!fm) y[8 * i + n] = __fsqrt_rn (__fadd_rn (__fmul_rn (zr[n], zr[n]), __fmul_rn (zi, zi)));
+            else
+            {
+              if (i == 0 && n == 0) { z0r = zr[0]; z0i = zi; y[0] = 0.f; }
+              else y[8 * i + n] = fm_discriminator (zr[n], zi, pr, pi);
+              pr = zr[n]; pi = zi;
+            }
           }
         }
         tc_fence_before ();
         __syncwarp ();
         if (lane == 0) mbar_arrive (t_empty);
+        bool carry_waited = false;
+        if (fm)
+        {
+          // ---- FM: the sample before the block. Blocks 1..3 of the warp: the thread 8 lanes down; the warp's first block: the
+          // previous warp's last thread through shared memory; the supertile's first block: the previous supertile's last sample
+          // (two-slot carry, handed over with the biquad state) or, at the start of a call, the carried state of the channel.
+          float qr = __shfl_up_sync (0xffffffffu, pr, 8), qi = __shfl_up_sync (0xffffffffu, pi, 8);
+          if (a == 3) myZ[w * kJ + j] = make_float2 (pr, pi);
+          if (kk != 0) mbar_wait (s_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
+          carry_waited = true;
+          named_bar (5 + es, 128);
+          if (a == 0)
+          {
+            float2 v;
+            if (w > 0) v = myZ[(w - 1) * kJ + j];
+            else if (k == 0) v = make_float2 (__ldcg (P.state + (size_t) c * 8 + 5), __ldcg (P.state + (size_t) c * 8 + 6));
+            else v = sCarryZ[((kk - 1) & 1) * kJ + j];
+            qr = v.x; qi = v.y;
+          }
+          y[0] = fm_discriminator (z0r, z0i, qr, qi);
+        }
         // ---- zero-state response of the cascade over the block, per sample as arm_biquad_cascade_df2T_f32.c:551-562:
         //      y = b0 x + d1;  d1 = (b1 x + a1 y) + d2;  d2 = b2 x + a2 y
         float z[4] = { 0.f, 0.f, 0.f, 0.f };
@@ -358,7 +406,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
         }
         // ---- carried state: from the previous call (first supertile) or the previous supertile (no carry-barrier phase is skipped)
         float S[4], envc;
-        if (kk != 0) mbar_wait (s_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
+        if (kk != 0 && !carry_waited) mbar_wait (s_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
         if (k == 0)
         {
           const float *stc = P.state + (size_t) c * 8;
@@ -395,10 +443,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
           float en[4];
           matvec4 (P.tab.Mp[1], st, z, en);
           *reinterpret_cast<float4 *> (sCarryS + ((kk & 1) * kJ + j) * 4) = make_float4 (en[0], en[1], en[2], en[3]);
+          if (fm) sCarryZ[(kk & 1) * kJ + j] = make_float2 (pr, pi);             // FM: this block's last baseband sample, for the next supertile
           if (k + 1 == supers && jvalid)
           {
             float *stw = P.state + (size_t) c * 8;
             __stcg (stw + 0, en[0]); __stcg (stw + 1, en[1]); __stcg (stw + 2, en[2]); __stcg (stw + 3, en[3]);
+            if (fm) { __stcg (stw + 5, pr); __stcg (stw + 6, pi); }
           }
           mbar_arrive (s_bar + (kk & 1));
         }

@@ -56,6 +56,9 @@ constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_SETS
 #define SL_TC_SETS 2
 #endif
+#ifndef SL_TC_PAIR
+#define SL_TC_PAIR 0                      /* 1: CTA pairs, tcgen05.mma.cta_group::2 (M = 256, each CTA fetches half of the map operand); 0: single CTAs */
+#endif
 #ifndef SL_TC_RAWSTAGES
 #define SL_TC_RAWSTAGES 3
 #endif
@@ -71,6 +74,7 @@ constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_STHINT
 #define SL_TC_STHINT ".L1::no_allocate"   /* measured: plain 366, .cg 371, .cs 376, .L1::no_allocate 408 Gsamples/s */
 #endif
+constexpr bool kPair = SL_TC_PAIR != 0;
 constexpr int kMmaUnroll = SL_TC_MMA_UNROLL;
 constexpr int kSets = SL_TC_SETS;                 // epilogue warp sets (warpgroups), taking supertiles in turn
 constexpr int kRawStages = SL_TC_RAWSTAGES;            // raw stages: a bulk copy takes ~4400 clocks to land (measured), a supertile ~3000
@@ -78,7 +82,6 @@ constexpr int kEpiWarps = 4 * kSets;
 constexpr int kConvWarps = 2;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);   // 16 warps = 4 warpgroups: 3 epilogue sets + {2 converters, MMA issuer, producer}
-static_assert (kSets == 2, "an epilogue set owns one accumulator buffer (it zeroes the buffer's top-digit columns)");
 static_assert (!SL_TC_REGSPLIT || kThreads == 512, "register split below assumes 4 warpgroups");
 constexpr int kOutRow = 4 * kBlk * 4 + 16;  // output stage of one epilogue warp: a channel's four blocks (768 B) + pad, ...
 constexpr int kOutStage = 4 * kOutRow;     // ... four channels at a time
@@ -88,7 +91,8 @@ struct Smem
 {
   static constexpr size_t a = 0;                                        // [2 buffers][hi plane | lo plane]
   static constexpr size_t b = a + 2 * 2 * kPlaneBytes;                  // tap planes of the current mask
-  static constexpr size_t raw = b + kTcPlaneBytes;                      // [stages][8 rows]
+  static constexpr size_t b_bytes = kPair ? kTcPlaneBytes / 2 : kTcPlaneBytes;   // pair: this CTA's half of the rows of every K-step
+  static constexpr size_t raw = b + b_bytes;                            // [stages][8 rows]
   static constexpr size_t hist = raw + kRawStages * kJ * kRawRow;       // [stages][8 rows] carried tail of the previous call
   static constexpr size_t out = hist + kRawStages * kJ * kHistRow;      // [8 rows] packed int16 output of one supertile, stored by bulk copies
   static constexpr size_t wsum = out + (SL_TC_BULKOUT ? kEpiWarps * kOutStage : 0);                    // [sets][4 warps][8][4] floats
@@ -97,7 +101,7 @@ struct Smem
   static constexpr size_t carry_e = carry_s + 2 * kJ * 4 * 4;           // [2][8] floats
   static constexpr size_t mp = carry_e + 2 * kJ * 4;                    // [4][20] floats: A^(48 a), rows padded to 20 (bank spread)
   static constexpr size_t bars = mp + 4 * 20 * 4;
-  static constexpr int n_bars = 26;
+  static constexpr int n_bars = 28;
   static constexpr size_t tmem_ptr = bars + n_bars * 8;
   static constexpr size_t bytes = tmem_ptr + 16;
 };
@@ -109,11 +113,12 @@ struct KParams
   const uint32_t *ovl_in; uint32_t *ovl_out;
   float *state; unsigned *flag;
   const uint32_t *chan; const uint32_t *gstart; const uint32_t *ginfo;
+  const uint32_t *pairs;                       // [n_items][2] groups of a CTA pair (same mask slot); 0xFFFFFFFF = none (the CTA idles along on the partner's data)
   const uint8_t *planes;
   float s0[SLB_MAX_MASKS], sz[SLB_MAX_MASKS];
   long long *trace;                            // profiling aid (SELENITE_B200_TC_TRACE): [supertile][16] clock64 stamps of CTA 0
   unsigned flag_final;
-  uint32_t n_groups, frames, supers;
+  uint32_t n_groups, n_items, frames, supers;   // n_items: work items of the launch = groups (single CTAs) or pairs of groups
   float agc_target, agc_decay, agc_floor, agc_gmax;
   TcBiquadTables tab;
 };
@@ -154,6 +159,19 @@ __device__ __forceinline__ void matvec4 (const float *M, const float *x, const f
 #define TC_STAMP(slot) do { if (P.trace && blockIdx.x == 0 && lane == 0) P.trace[(size_t) kk * 16 + (slot)] = clock64 (); } while (0)
 #endif
 
+// work item -> the channel group this CTA serves. Single CTAs: item = group. CTA pairs: item = two groups of one mask slot, one per
+// CTA; a pair with one group only lets its second CTA run along on the partner's channels without storing anything (the MMAs of a
+// pair are issued for both CTAs at once, so both must present operands and drain accumulators for every supertile).
+struct Item { uint32_t g; bool idle; };
+__device__ __forceinline__ Item item_group (const KParams &P, uint32_t it, uint32_t rank)
+{
+  if (!kPair) return Item{ it, false };
+  uint32_t g = P.pairs[2 * it + rank];
+  const bool idle = g == 0xFFFFFFFFu;
+  if (idle) g = P.pairs[2 * it + (rank ^ 1u)];
+  return Item{ g, idle };
+}
+
 __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_constant__ KParams P)
 {
   extern __shared__ __align__ (1024) unsigned char smem[];
@@ -166,38 +184,53 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
 #endif
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
   uint64_t *raw_full = bars, *raw_empty = bars + 3, *a_full = bars + 6, *a_empty = bars + 8, *t_empty = bars + 10;
-  uint64_t *s_bar = bars + 12, *e_bar = bars + 14, *b_full = bars + 16, *drain = bars + 17, *t_full = bars + 18, *out_free = bars + 22;
+  uint64_t *s_bar = bars + 12, *e_bar = bars + 14, *b_full = bars + 16, *drain = bars + 17, *t_full = bars + 18, *out_free = bars + 22, *b_ready = bars + 26;
   // t_full has FOUR slots although there are two accumulator buffers: an epilogue set may start waiting for supertile
   // kk + 2 while kk is still in flight, and on a two-slot barrier that wait would alias the phase before kk's and pass at once
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *> (smem + Smem::tmem_ptr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // pair mode: rank 0 of the cluster is the leader (issues the MMAs of both CTAs); a_full, t_empty and b_ready of the LEADER collect
+  // arrivals from both CTAs, t_full / a_empty / drain of each CTA are reached by the leader's multicast commits
+  const uint32_t rank = kPair ? cluster_ctarank () : 0u;
+  const uint32_t item0 = kPair ? cluster_id_x () : blockIdx.x, istride = kPair ? cluster_n_x () : gridDim.x;
   if (tid == 0)
   {
     for (int i = 0; i < kRawStages; i++) { mbar_init (raw_full + i, 1); mbar_init (raw_empty + i, kConvWarps); }
     for (int i = 0; i < 2; i++)
     {
-      mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
-      mbar_init (t_full + i, 1); mbar_init (t_full + 2 + i, 1); mbar_init (t_empty + i, 4); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
+      mbar_init (a_full + i, (kPair ? 2 : 1) * kConvWarps); mbar_init (a_empty + i, 1);
+      mbar_init (t_full + i, 1); mbar_init (t_full + 2 + i, 1); mbar_init (t_empty + i, (kPair ? 2 : 1) * 4); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
     }
-    mbar_init (b_full, 1); mbar_init (drain, 1);
+    mbar_init (b_full, 1); mbar_init (drain, 1); mbar_init (b_ready, 1);
     for (int i = 0; i < 4; i++) mbar_init (out_free + i, 1);
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 64) sMp[(tid >> 4) * 20 + (tid & 15)] = P.tab.Mp[tid >> 4][tid & 15];
   if (warp == kMmaWarp)
   {
-    asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32 (tmem_ptr)), "n"(kTmemCols) : "memory");
-    asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair)
+    {
+      // the same warp of both CTAs allocates the same columns in both tensor memories
+      asm volatile ("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32 (tmem_ptr)), "n"(kTmemCols) : "memory");
+      asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    else
+    {
+      asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32 (tmem_ptr)), "n"(kTmemCols) : "memory");
+      asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before ();
   __syncthreads ();
+  if (kPair) cluster_sync_all ();                  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after ();
   const uint32_t tmem = *tmem_ptr;
+  const uint32_t a_full_ldr = mapa_u32 (smem_u32 (a_full), 0u), t_empty_ldr = mapa_u32 (smem_u32 (t_empty), 0u), b_ready_ldr = mapa_u32 (smem_u32 (b_ready), 0u);
   const uint32_t supers = P.supers;
   // Columns [0,52) of both accumulator buffers start at zero: the xh MMAs accumulate into them (see the MMA issuer); afterwards
   // the epilogue set that drains a buffer zeroes them again.
-  if (warp < kEpiWarps) tmem_zero<kDig> (tmem + (uint32_t) (warp >> 2) * 256u + ((uint32_t) (32 * (warp & 3)) << 16));
+  if (warp < 8) tmem_zero<kDig> (tmem + (uint32_t) (warp >> 2) * 256u + ((uint32_t) (32 * (warp & 3)) << 16));
   tc_fence_before ();
   __syncthreads ();
   tc_fence_after ();
@@ -219,7 +252,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       uint64_t pol;
       asm volatile ("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 #endif
-      for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
+      for (uint32_t it = item0; it < P.n_items; it += istride)
+      {
+        const uint32_t g = item_group (P, it, rank).g;
         for (uint32_t k = 0; k < supers; k++, kk++)
         {
           const int rb = kk % kRawStages;
@@ -240,6 +275,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
             if (k == 0) bulk_g2s (sHist + (rb * kJ + j) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
           }
         }
+      }
     }
     __syncwarp ();
   }
@@ -251,9 +287,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // channel (lane & 7) and walks the chunks lane >> 3, + 4, + 8, ...: constant strides, three chunks in flight (the role runs on 56 registers).
     const int cw = warp - kEpiWarps, j = lane & 7, c4 = lane >> 3;
     unsigned kk = 0;
-    for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
+    for (uint32_t it = item0; it < P.n_items; it += istride)
     {
-      const uint32_t nvalid = P.ginfo[g] >> 8, gs = P.gstart[g];
+      const Item item = item_group (P, it, rank);
+      const uint32_t g = item.g, nvalid = item.idle ? 0u : P.ginfo[g] >> 8, gs = P.gstart[g];
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         const int rb = kk % kRawStages, ab = kk & 1;
@@ -328,7 +365,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp ();
         if (cw == 0) TC_STAMP (3);
-        if (lane == 0) { mbar_arrive (a_full + ab); mbar_arrive (raw_empty + rb); }
+        if (lane == 0) { if (kPair) mbar_arrive_cluster (a_full_ldr + ab * 8u); else mbar_arrive (a_full + ab); mbar_arrive (raw_empty + rb); }
       }
     }
   }
@@ -338,35 +375,60 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // The whole warp walks the loop converged and ONE elected lane issues: with `if (lane == 0)` around the loop the
     // compiler cannot keep descriptors in uniform registers and wraps every tcgen05.mma in a vote / broadcast loop —
     // measured 128 clocks of issue per MMA against 116 of execution (N = 144).
-    constexpr uint32_t id_ss = umma_idesc (kN, 1, 1), id_us = umma_idesc (kN, 0, 1);
+    constexpr uint32_t id_ss = kPair ? umma_idesc_pair (kN, 1, 1) : umma_idesc (kN, 1, 1), id_us = kPair ? umma_idesc_pair (kN, 0, 1) : umma_idesc (kN, 0, 1);
     const uint32_t aBase = smem_u32 (sA), bBase = smem_u32 (sB);
     // constant upper halves of the descriptors: LBO = 128 (A and B), SBO = 768 (A, aliased row groups) / 256 (B), version 1
     constexpr uint64_t kDescA = ((uint64_t) (kChunkBytes >> 4) << 16) | ((uint64_t) ((6 * kChunkBytes) >> 4) << 32) | (1ull << 46);
     constexpr uint64_t kDescB = ((uint64_t) (128 >> 4) << 16) | ((uint64_t) (256 >> 4) << 32) | (1ull << 46);
+    // pair mode: every CTA holds HALF of the map's rows of each K-step (rows [80 rank, 80 rank + 80) of the 160, the split
+    // tcgen05.mma.cta_group::2 expects: tools/microbench/umma_cta2.cu), at the same shared-memory offsets in both CTAs
+    constexpr uint32_t kBStepS = kPair ? kBStep / 2 : kBStep;            // K-step stride of the planes in shared memory
     unsigned kk = 0, b_loads = 0, drains = 0;
     int cur_slot = -1;
-    for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
+    for (uint32_t it = item0; it < P.n_items; it += istride)
     {
-      const int slot = (int) (P.ginfo[g] & 0xFFu);
+      const uint32_t g = item_group (P, it, rank).g;
+      const int slot = (int) (P.ginfo[g] & 0xFFu);                             // (both groups of a pair have the same slot)
       if (slot != cur_slot)
       {
-        // (re)load the tap planes of this mask; earlier MMAs may still be reading the old ones
-        if (kk != 0) { if (elect_one ()) umma_commit (drain); __syncwarp (); mbar_wait (drain, drains & 1); drains++; }
+        // (re)load the tap planes of this mask; earlier MMAs may still be reading the old ones (in pair mode: in BOTH CTAs — the
+        // leader's commit reaches the drain barrier of both)
+        if (kk != 0)
+        {
+          if (rank == 0 && elect_one ()) { if (kPair) umma_commit_pair (drain); else umma_commit (drain); }
+          __syncwarp ();
+          mbar_wait (drain, drains & 1); drains++;
+        }
         if (elect_one ())
         {
-          mbar_expect_tx (b_full, (unsigned) kTcPlaneBytes);
-          bulk_g2s (sB, P.planes + (size_t) slot * kTcPlaneBytes, (unsigned) kTcPlaneBytes, b_full);
+          mbar_expect_tx (b_full, (unsigned) Smem::b_bytes);
+          if (kPair)
+          {
+#pragma unroll 1
+            for (int ks = 0; ks < kKSteps; ks++)
+              bulk_g2s (sB + ks * kBStepS, P.planes + (size_t) slot * kTcPlaneBytes + (size_t) ks * kBStep + (size_t) rank * kBStepS, kBStepS, b_full);
+          }
+          else bulk_g2s (sB, P.planes + (size_t) slot * kTcPlaneBytes, (unsigned) kTcPlaneBytes, b_full);
         }
         __syncwarp ();
-        mbar_wait (b_full, b_loads & 1); b_loads++;
+        mbar_wait (b_full, b_loads & 1);
+        if (kPair)
+        {
+          // the leader may issue only when the follower's half has landed too
+          if (rank != 0) { if (lane == 0) mbar_arrive_cluster (b_ready_ldr); }
+          else mbar_wait_cluster (b_ready, b_loads & 1);
+        }
+        b_loads++;
         cur_slot = slot;
       }
+      if (rank != 0) { kk += supers; continue; }                               // the follower's MMAs are issued by the leader
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         const int ab = kk & 1, tb = kk & 1;
-        mbar_wait_long (a_full + ab, (kk >> 1) & 1);
+        if (kPair) mbar_wait_cluster (a_full + ab, (kk >> 1) & 1); else mbar_wait_long (a_full + ab, (kk >> 1) & 1);
         TC_STAMP (4);
-        mbar_wait_long (t_empty + tb, ((kk >> 1) & 1) ^ 1);                       // the epilogue has drained this accumulator buffer and zeroed its columns [0,52)
+        // the epilogue (of both CTAs) has drained this accumulator buffer and zeroed its columns [0,52)
+        if (kPair) mbar_wait_cluster (t_empty + tb, ((kk >> 1) & 1) ^ 1); else mbar_wait_long (t_empty + tb, ((kk >> 1) & 1) ^ 1);
         TC_STAMP (5);
         tc_fence_after ();
         const uint32_t d = tmem + (uint32_t) tb * 256u;
@@ -378,21 +440,29 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           // rows 156..159 zero), xl one digit to the right of xh. The first xl MMA starts columns [52,212) afresh; columns [0,52)
           // were zeroed by the epilogue set that drained the buffer (N must be a multiple of 16: there is no MMA that could
           // start exactly these 52 columns), so every xh MMA accumulates.
-          // (Tried: two independent chains, xh * [h2|h1|h0] and xl * [h2|h1|h0] in disjoint columns, added in the epilogue. No faster —
-          // an SS-mode MMA is bound by the fetch of its operands from shared memory, dependent or not
-          // (tools/microbench/umma_rate.cu) — and it costs the second accumulator buffer.)
+          // (Tried: two independent chains, xh * [h2|h1|h0] and xl * [h2|h1|h0] in disjoint columns, added in the epilogue. No faster,
+          // and it costs the second accumulator buffer.)
 #pragma unroll kMmaUnroll
           for (int ks = 0; ks < kKSteps; ks++)
           {
 #ifdef SL_TC_ABLATE_MMA                                                             // (profiling aid: what the MMAs cost)
             if (ks > 0) break;
 #endif
-            const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStep) >> 4;
-            umma_i8 (d + kDig, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us, ks ? 1u : 0u);
-            umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss, 1u);
+            const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStepS) >> 4;
+            if (kPair)
+            {
+              umma_i8_pair (d + kDig, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us, ks ? 1u : 0u);
+              umma_i8_pair (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss, 1u);
+            }
+            else
+            {
+              umma_i8 (d + kDig, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us, ks ? 1u : 0u);
+              umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss, 1u);
+            }
           }
-          umma_commit (t_full + (kk & 3));  // accumulators complete -> epilogue
-          umma_commit (a_empty + ab);       // planes read -> converter may overwrite them
+          // accumulators complete -> epilogue; planes read -> converter may overwrite them (pair mode: in both CTAs)
+          if (kPair) { umma_commit_pair (t_full + (kk & 3)); umma_commit_pair (a_empty + ab); }
+          else { umma_commit (t_full + (kk & 3)); umma_commit (a_empty + ab); }
         }
         __syncwarp ();
         TC_STAMP (6);
@@ -410,10 +480,11 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     float *myW = sW + es * (4 * kJ * 4), *myPk = sPk + es * (kQ * kJ);
     const float decay = P.agc_decay;
     unsigned kk = 0;
-    for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
+    for (uint32_t it = item0; it < P.n_items; it += istride)
     {
-      const uint32_t gi = P.ginfo[g];
-      const bool jvalid = (uint32_t) j < (gi >> 8);
+      const Item item = item_group (P, it, rank);
+      const uint32_t g = item.g, gi = P.ginfo[g];
+      const bool jvalid = !item.idle && (uint32_t) j < (gi >> 8);
       const uint32_t c = P.chan[P.gstart[g] + min ((uint32_t) j, (gi >> 8) - 1u)];
       const float s0 = P.s0[gi & 0xFFu], s8 = s0 * 256.0f, s16 = s0 * 65536.0f, s24 = s0 * 16777216.0f, z0s = P.sz[gi & 0xFFu];
       for (uint32_t k = 0; k < supers; k++, kk++)
@@ -457,7 +528,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         tmem_zero<kDig> (taddr);                                                   // the next supertile's xh MMAs accumulate into these columns
         tc_fence_before ();
         __syncwarp ();
-        if (lane == 0) mbar_arrive (t_empty + tb);                               // the accumulator buffer now lives in registers
+        if (lane == 0) { if (kPair) mbar_arrive_cluster (t_empty_ldr + tb * 8u); else mbar_arrive (t_empty + tb); }   // the accumulator buffer now lives in registers
         if (w == 0) TC_STAMP (8);
 #ifdef SL_TC_ABLATE_EPI                                                             // (profiling aid: the kernel without the epilogue's arithmetic and stores)
         if (y[0] != 123.456f || z[0] != 1.0f) continue;
@@ -692,10 +763,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
 
   tc_fence_before ();
   __syncthreads ();
+  if (kPair) cluster_sync_all ();                  // neither CTA retires (shared memory, barriers, TMEM) while the peer may still reach into it
   if (warp == kMmaWarp)
   {
     tc_fence_after ();
-    asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    if (kPair) asm volatile ("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    else asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -708,33 +781,41 @@ int launch_rx_ssb_tc (const RxTcLaunch &L, int sm_count, void *stream_)
   if ((reinterpret_cast<uintptr_t> (L.in) | reinterpret_cast<uintptr_t> (L.ovl_in) | reinterpret_cast<uintptr_t> (L.ovl_out) | reinterpret_cast<uintptr_t> (L.out) |
        reinterpret_cast<uintptr_t> (L.planes)) & 15u)
     return (int) cudaErrorMisalignedAddress;
+  if (kPair && (L.pairs == nullptr || L.n_pairs == 0)) return (int) cudaErrorInvalidValue;
   KParams P;
   P.in = reinterpret_cast<const uint32_t *> (L.in); P.out = reinterpret_cast<uint32_t *> (L.out);
   P.audio_dbg = L.audio_dbg; P.gain_dbg = L.gain_dbg;
   P.ovl_in = reinterpret_cast<const uint32_t *> (L.ovl_in); P.ovl_out = reinterpret_cast<uint32_t *> (L.ovl_out);
-  P.state = L.state; P.flag = L.flag; P.chan = L.chan; P.gstart = L.gstart; P.ginfo = L.ginfo; P.planes = L.planes;
+  P.state = L.state; P.flag = L.flag; P.chan = L.chan; P.gstart = L.gstart; P.ginfo = L.ginfo; P.pairs = L.pairs; P.planes = L.planes;
   for (int i = 0; i < SLB_MAX_MASKS; i++) { P.s0[i] = L.s0[i]; P.sz[i] = L.sz[i]; }
-  P.flag_final = L.flag_final; P.n_groups = L.n_groups; P.frames = L.frames; P.supers = (L.frames + kSuper - 1) / kSuper;
+  P.flag_final = L.flag_final; P.n_groups = L.n_groups; P.n_items = kPair ? L.n_pairs : L.n_groups; P.frames = L.frames; P.supers = (L.frames + kSuper - 1) / kSuper;
   P.agc_target = L.agc_target; P.agc_decay = L.agc_decay; P.agc_floor = L.agc_floor; P.agc_gmax = L.agc_gmax;
   P.tab = *L.tables;
   static_assert (sizeof (KParams) <= 4000, "kernel parameter block");
   cudaError_t e = cudaFuncSetAttribute (rx_ssb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Smem::bytes);
   if (e != cudaSuccess) return (int) e;
-  uint32_t grid = (uint32_t) sm_count;
-  if (grid > L.n_groups) grid = L.n_groups;
-  if (const char *gs = std::getenv ("SELENITE_B200_TC_GRID")) { const long v = std::atol (gs); if (v > 0 && (uint32_t) v <= grid) grid = (uint32_t) v; }   // profiling aid
+  // one CTA per SM; pair mode: one cluster of two CTAs per work item (a TPC), at most sm_count / 2 clusters
+  uint32_t ctas_per_item = kPair ? 2u : 1u;
+  uint32_t grid_items = (uint32_t) sm_count / ctas_per_item;
+  if (grid_items > P.n_items) grid_items = P.n_items;
+  if (const char *gs = std::getenv ("SELENITE_B200_TC_GRID")) { const long v = std::atol (gs); if (v > 0 && (uint32_t) v <= grid_items) grid_items = (uint32_t) v; }   // profiling aid
   P.trace = nullptr;
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3 (grid_items * ctas_per_item); lc.blockDim = dim3 (kThreads); lc.dynamicSmemBytes = Smem::bytes; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = ctas_per_item; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
 #ifdef SL_TC_TRACE
   if (const char *tf = std::getenv ("SELENITE_B200_TC_TRACE"))
   {
     // profiling aid: clock64 stamps of every pipeline role of CTA 0, one row per supertile, dumped as text after the launch
-    const size_t n = (size_t) P.supers * ((L.n_groups + grid - 1) / grid) * 16;
+    const size_t n = (size_t) P.supers * ((P.n_items + grid_items - 1) / grid_items) * 16;
     long long *d_tr = nullptr;
     if (cudaMalloc (&d_tr, n * 8) == cudaSuccess)
     {
       cudaMemset (d_tr, 0, n * 8);
       P.trace = d_tr;
-      rx_ssb_tc_kernel<<<grid, kThreads, Smem::bytes, stream>>> (P);
+      cudaLaunchKernelEx (&lc, rx_ssb_tc_kernel, P);
       cudaDeviceSynchronize ();
       long long *h = (long long *) std::malloc (n * 8);
       cudaMemcpy (h, d_tr, n * 8, cudaMemcpyDeviceToHost);
@@ -748,8 +829,8 @@ int launch_rx_ssb_tc (const RxTcLaunch &L, int sm_count, void *stream_)
     }
   }
 #endif
-  rx_ssb_tc_kernel<<<grid, kThreads, Smem::bytes, stream>>> (P);
-  return (int) cudaGetLastError ();
+  e = cudaLaunchKernelEx (&lc, rx_ssb_tc_kernel, P);
+  return (int) (e != cudaSuccess ? e : cudaGetLastError ());
 }
 
 }  // namespace sl

@@ -263,7 +263,7 @@ class DspIf:
         if self.chain == CHAIN_TX_SSB_F32:
             return tx_params_to_dict(self.tx_params(), self.mask(mode))
         prm = params_to_dict(self.rx_params(), self.mask(mode))
-        prm["envelope"] = int(mode == MODE_AM)
+        prm["envelope"] = 1 if mode == MODE_AM else 2 if mode == MODE_FM else 0   # the oracle chain's detector: Re, |z| (AM), limiter-discriminator (FM)
         return prm
 
     # ---- bulk path ----

@@ -63,3 +63,20 @@ def synth_wideband(streams, frames, fs=192000, bins=64, amp=0.02, sigma=0.01, of
         out[k, :, 0] = np.clip(np.rint(z.real * 32768.0), -32768, 32767).astype(np.int16)
         out[k, :, 1] = np.clip(np.rint(z.imag * 32768.0), -32768, 32767).astype(np.int16)
     return out
+
+
+def synth_fm(channels, frames, fs=48000, audio_hz=1000.0, deviation_hz=2500.0, carrier_hz=0.0, amp=0.25, sigma=0.002, seed=SEED, first_channel=0):
+    """FM test input (mode byte 0x08): int16[channels][frames][2], a carrier at `carrier_hz` frequency-modulated by a tone of
+    `audio_hz` (channel c detunes it by c Hz) with peak deviation `deviation_hz`, plus complex white noise."""
+    out = np.empty((channels, frames, 2), np.int16)
+    n = np.arange(frames, dtype=np.float64)
+    for k in range(channels):
+        c = first_channel + k
+        rng = np.random.Generator(np.random.PCG64(seed + 0xF3 + c))
+        fa = audio_hz + (c % 89)
+        ph = 2.0 * np.pi * carrier_hz * n / fs + (deviation_hz / fa) * np.sin(2.0 * np.pi * fa * n / fs + 0.3 * c)
+        i = amp * np.cos(ph) + sigma * rng.standard_normal(frames)
+        q = amp * np.sin(ph) + sigma * rng.standard_normal(frames)
+        out[k, :, 0] = np.clip(np.rint(i * 32768.0), -32768, 32767).astype(np.int16)
+        out[k, :, 1] = np.clip(np.rint(q * 32768.0), -32768, 32767).astype(np.int16)
+    return out

@@ -34,11 +34,28 @@ def golden_q15(ref):
     print("rx_ssb_q15.npz", os.path.getsize(os.path.join(HERE, "rx_ssb_q15.npz")), "bytes")
 
 
+def golden_fm(ref):
+    """RX-SSB-f32 chain with the FM detector (mode byte 0x08): a carrier frequency-modulated by a 1 kHz tone, +-2.5 kHz deviation,
+    once centred and once 1.5 kHz off the channel centre (a constant offset in the discriminator output), 20 hops each."""
+    p = slb.default_rx_f32_params(48000)
+    mask = slb.default_mask(48000, p.fft_len, slb.MODE_FM)
+    out = {"fm_mask": mask, "fm_biquad": np.array(p.biquad[:10], np.float32), "fm_agc": np.array([p.agc_target, p.agc_decay, p.agc_floor, p.agc_gmax], np.float32)}
+    for name, fc in (("centre", 0.0), ("offset", 1500.0)):
+        x = slb.synth_fm(1, 20 * 384, carrier_hz=fc)[0]
+        prm = params_to_dict(p, mask); prm["envelope"] = 2
+        y, audio, gain, _ = ref.rx_ssb_f32(prm, x)
+        out["fm_%s_in" % name] = x; out["fm_%s_out" % name] = y; out["fm_%s_audio" % name] = audio; out["fm_%s_gain" % name] = gain
+    np.savez_compressed(os.path.join(HERE, "rx_fm_f32.npz"), **out)
+    print("rx_fm_f32.npz", os.path.getsize(os.path.join(HERE, "rx_fm_f32.npz")), "bytes")
+
+
 def main():
     oracle_lib.build_oracles()
     ref = oracle_lib.Oracle("ref")
     if len(sys.argv) > 1 and sys.argv[1] == "q15":      # later additions regenerate alone: the older fixtures stay untouched
         return golden_q15(ref)
+    if len(sys.argv) > 1 and sys.argv[1] == "fm":
+        return golden_fm(ref)
     rng = np.random.Generator(np.random.PCG64(slb.signals.SEED))
 
     # ---- RX-SSB-f32, config-1 style: one channel, tone +1000 Hz + noise, 20 hops; and an LSB tone at -1700 Hz

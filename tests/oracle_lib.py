@@ -32,7 +32,7 @@ class RxF32Params(C.Structure):
 
 
 class RxF32State(C.Structure):
-    _fields_ = [("ovl", C.c_int16 * (2 * MAX_FFT)), ("bq", C.c_float * (2 * MAX_STAGES)), ("env", C.c_float)]
+    _fields_ = [("ovl", C.c_int16 * (2 * MAX_FFT)), ("bq", C.c_float * (2 * MAX_STAGES)), ("env", C.c_float), ("zlast", C.c_float * 2)]
 
 
 class TxF32Params(C.Structure):

@@ -230,3 +230,52 @@ def test_am_chain_port_vs_ref(port, ref):
     assert np.all(a_r >= 0) and np.all(np.abs(a_p - a_r) <= audio_tolerance(a_r) + 1e-12)
     d = np.abs(y_p.astype(np.int32) - y_r.astype(np.int32))
     assert d.max() <= 1 and np.mean(d > 0) < 0.02
+
+
+def fm_params(g):
+    return dict(fft_len=512, hop=384, agc_block=48, biquad=g["fm_biquad"].reshape(2, 5), agc_target=g["fm_agc"][0], agc_decay=g["fm_agc"][1],
+                agc_floor=g["fm_agc"][2], agc_gmax=g["fm_agc"][3], mask=g["fm_mask"], envelope=2)
+
+
+def fm_audio_ok(audio, ref_audio):
+    """FM discriminator output: the usual 1e-5 bar from the second super-block on; inside the first one the channel filter
+    is still filling and the limiter divides by a baseband amplitude that starts at ~1e-7, so float32 rounding of the
+    filter (1e-7 of the INPUT) shows through magnified — the reference against its own restatement differs by 4e-5 there."""
+    err = np.abs(audio - ref_audio)
+    return bool(np.all(err[384:] <= audio_tolerance(ref_audio)[384:] + 1e-9) and np.all(err[:384] <= 2e-4))
+
+
+def fm_int16_ok(out, ref_out):
+    """int16 result of the FM chain: nothing but single-LSB flips of the truncating pack (arm_float_to_q15.c:147). The SHARE of
+    flipped samples is not held to the 2 % of the other chains: the AGC envelope of a stream that starts inside the filter's
+    fill-up holds that first block's peak for 300 ms, so the start-up difference above becomes a 2e-5 .. 4e-5 relative GAIN
+    difference over the whole fixture (checked separately, rtol 1e-4) = 0.15 .. 0.3 LSB of scaling difference per sample
+    (measured shares: reference vs its restatement 6 %, GPU vs reference 11 %). What IS held: the float audio to 1e-5 after the
+    first super-block, and no sample off by more than one LSB."""
+    d = np.abs(out.astype(np.int32) - ref_out.astype(np.int32))
+    return bool(d.max() <= 1 and np.mean(d > 0) < 0.25)
+
+
+@pytest.mark.parametrize("name", ["centre", "offset"])
+def test_port_fm_chain_vs_golden(port, name):
+    """The FM detector of the chain (limiter-discriminator composed from arm_cmplx_conj_f32, arm_cmplx_mult_cmplx_f32,
+    arm_cmplx_mag_f32; oracle/chains.inc.c): port vs the outputs of the reference build."""
+    g = np.load(os.path.join(GOLD, "rx_fm_f32.npz"))
+    out, audio, gain, _ = port.rx_ssb_f32(fm_params(g), g["fm_%s_in" % name])
+    assert fm_audio_ok(audio, g["fm_%s_audio" % name])
+    assert np.allclose(gain, g["fm_%s_gain" % name], rtol=1e-4)
+    assert fm_int16_ok(out, g["fm_%s_out" % name])
+    # what the discriminator is: the sine of the carrier's phase step — a 1 kHz tone of amplitude sin (2 pi 2500 / 48000), offset by
+    # sin (2 pi fc / 48000) when the carrier sits fc off the channel centre (the biquad passes both)
+    a = g["fm_%s_audio" % name][3000:7000].astype(np.float64); n = np.arange(3000, 7000)
+    basis = np.stack([np.cos(2 * np.pi * 1000.0 * n / 48000.0), np.sin(2 * np.pi * 1000.0 * n / 48000.0), np.ones(n.size)], 1)
+    c, *_ = np.linalg.lstsq(basis, a, rcond=None)
+    assert abs(np.hypot(c[0], c[1]) - np.sin(2 * np.pi * 2500.0 / 48000.0)) < 0.02
+    assert abs(c[2] - (np.sin(2 * np.pi * 1500.0 / 48000.0) if name == "offset" else 0.0)) < 0.02
+
+
+@pytest.mark.parametrize("name", ["centre", "offset"])
+def test_ref_fm_chain_reproduces_golden(ref, name):
+    g = np.load(os.path.join(GOLD, "rx_fm_f32.npz"))
+    out, audio, gain, _ = ref.rx_ssb_f32(fm_params(g), g["fm_%s_in" % name])
+    assert np.array_equal(out, g["fm_%s_out" % name]) and np.array_equal(audio, g["fm_%s_audio" % name])
