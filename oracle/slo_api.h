@@ -124,7 +124,9 @@ typedef struct
   float env;                          /* AGC envelope */
   float zlast[2];                     /* FM: the last filtered baseband sample of the previous super-block (re, im) */
 } slo_rx_f32_state;
-#define SLO_FM_FLOOR 1.0e-8f          /* FM soft squelch: |z[n] conj z[n-1]| below this (|z| < 1e-4: no carrier, filter start-up) divides by this instead */
+#define SLO_FM_FLOOR 9.765625e-4f     /* = 2^-10. FM soft squelch: |z[n] conj z[n-1]| below this (|z| < 2^-5 = -30 dBFS: weak or no carrier, filter start-up)
+                                         divides by this instead, so the limiter never magnifies float32 rounding of the filter: with the floor at 1e-8 the
+                                         reference build and the port disagreed by 85x the 1e-5 bar inside the first super-block, at 2^-10 by 0.23x */
 
 /* frames % hop == 0. audio_dbg (optional) receives the post-biquad, pre-AGC float audio;
  * gain_dbg (optional) the per-agc_block gain. */

@@ -45,7 +45,7 @@ int design_default_mask (uint32_t fs, uint32_t fft_len, uint8_t mode, float *mas
 int mode_to_mask_slot (uint8_t mode);   // -1 for a byte that is no FT-817 mode
 constexpr int kAmMaskSlot = 6;          // channels on this slot use the envelope detector (arm_cmplx_mag_f32) instead of Re
 constexpr int kFmMaskSlot = 7;          // channels on this slot use the limiter-discriminator (complex-detector tensor-core kernel only)
-constexpr float kFmFloor = 1.0e-8f;     // FM soft squelch: |z[n] conj z[n-1]| below this (no carrier, filter start-up) divides by this instead (oracle: SLO_FM_FLOOR)
+constexpr float kFmFloor = 9.765625e-4f;     // FM soft squelch: |z[n] conj z[n-1]| below this (no carrier, filter start-up) divides by this instead (oracle: SLO_FM_FLOOR)
 
 // Tables the time-parallel biquad needs, derived in double from the 2-stage df2T coefficients (sl_design.cpp).
 constexpr int kRun = 24;                // samples per run; a lane of the recurrence warp carries two runs = one AGC block
