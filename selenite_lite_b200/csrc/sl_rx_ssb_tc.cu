@@ -56,6 +56,12 @@ constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_SETS
 #define SL_TC_SETS 2
 #endif
+#ifndef SL_TC_HALVES
+#define SL_TC_HALVES 1                    /* warps per TMEM lane quadrant and epilogue set. 2 = a block's 48 samples are split between two warps (columns [0,24) / [24,48)):
+                                             16 epilogue warps of 80 registers instead of 8 of 168. Measured equal (416 vs 423 Gsamples/s at 1024 channels, 461 vs 460 at
+                                             8192): the kernel is bound by the L1 / shared-memory data pipe (tensor-core operand reads + LSU wavefronts), not by the
+                                             latency of an epilogue set, so more epilogue warps buy nothing; kept as an A/B option */
+#endif
 #ifndef SL_TC_PAIR
 #define SL_TC_PAIR 0                      /* 1: CTA pairs, tcgen05.mma.cta_group::2 (M = 256, each CTA fetches half of the map operand); 0: single CTAs */
 #endif
@@ -78,8 +84,16 @@ constexpr bool kPair = SL_TC_PAIR != 0;
 constexpr int kMmaUnroll = SL_TC_MMA_UNROLL;
 constexpr int kSets = SL_TC_SETS;                 // epilogue warp sets (warpgroups), taking supertiles in turn
 constexpr int kRawStages = SL_TC_RAWSTAGES;            // raw stages: a bulk copy takes ~4400 clocks to land (measured), a supertile ~3000
-constexpr int kEpiWarps = 4 * kSets;
-constexpr int kConvWarps = 2;
+constexpr int kHalves = SL_TC_HALVES;
+constexpr int kHalf = kBlk / kHalves;              // samples of a block per epilogue thread
+constexpr int kEpiWarps = 4 * kSets * kHalves;
+static_assert (kHalves == 1 || (kHalves == 2 && !SL_TC_PAIR && !SL_TC_BULKOUT && !SL_TC_REGSPLIT), "the split epilogue has no CTA-pair / bulk-store / register-split variant");
+#ifndef SL_TC_CONVWARPS
+#define SL_TC_CONVWARPS 2
+#endif
+constexpr int kConvWarps = SL_TC_CONVWARPS;        // 2, 3 or 4: the converters' shared-memory accesses queue behind the tensor core's operand reads (latency-bound role)
+constexpr int kGroups = kChunksNew / 4;            // groups of 4 chunks (32 frames) of a supertile: 24; warp cw converts the groups t = cw (mod kConvWarps)
+static_assert ((kGroups / 2) % kConvWarps == 0, "a half supertile splits evenly too");
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);   // 16 warps = 4 warpgroups: 3 epilogue sets + {2 converters, MMA issuer, producer}
 static_assert (!SL_TC_REGSPLIT || kThreads == 512, "register split below assumes 4 warpgroups");
@@ -96,8 +110,8 @@ struct Smem
   static constexpr size_t hist = raw + kRawStages * kJ * kRawRow;       // [stages][8 rows] carried tail of the previous call
   static constexpr size_t out = hist + kRawStages * kJ * kHistRow;      // [8 rows] packed int16 output of one supertile, stored by bulk copies
   static constexpr size_t wsum = out + (SL_TC_BULKOUT ? kEpiWarps * kOutStage : 0);                    // [sets][4 warps][8][4] floats
-  static constexpr size_t pk = wsum + kSets * 4 * kJ * 4 * 4;           // [sets][16][8] floats
-  static constexpr size_t carry_s = pk + kSets * kQ * kJ * 4;           // [2][8][4] floats
+  static constexpr size_t pk = wsum + kSets * 4 * kJ * 4 * 4;           // [sets][halves][16][8] floats
+  static constexpr size_t carry_s = pk + kSets * kHalves * kQ * kJ * 4; // [2][8][4] floats
   static constexpr size_t carry_e = carry_s + 2 * kJ * 4 * 4;           // [2][8] floats
   static constexpr size_t mp = carry_e + 2 * kJ * 4;                    // [4][20] floats: A^(48 a), rows padded to 20 (bank spread)
   static constexpr size_t bars = mp + 4 * 20 * 4;
@@ -152,7 +166,26 @@ __device__ __forceinline__ void matvec4 (const float *M, const float *x, const f
   for (int r = 0; r < 4; r++) y[r] = add[r] + (M[4 * r] * x[0] + M[4 * r + 1] * x[1] + M[4 * r + 2] * x[2] + M[4 * r + 3] * x[3]);
 }
 
+// split epilogue: the zero-input response of the block's start state added to one half's samples (4 FMA per sample, the only
+// biquad arithmetic left on the CUDA cores) and the half's peak (arm_abs_f32 + arm_max_f32). The half is a template parameter so
+// that the response table stays an immediate constant-bank operand.
+template <int H> __device__ __forceinline__ float corr_half (const KParams &P, float (&y)[kHalf], const float (&st)[4])
+{
+  float peak = 0.f;
+#pragma unroll
+  for (int n = 0; n < kHalf; n++)
+  {
+    const float *C = P.tab.Cresp[H * kHalf + n];
+    y[n] = fmaf (C[0], st[0], fmaf (C[1], st[1], fmaf (C[2], st[2], fmaf (C[3], st[3], y[n]))));
+    peak = fmaxf (peak, fabsf (y[n]));
+  }
+  return peak;
+}
+
 // pipeline trace (tools/tc_trace.py): build with -DSL_TC_TRACE; the stamps cost 7 % even when no buffer is attached
+#ifndef SL_TC_TRACE_CW
+#define SL_TC_TRACE_CW 0                  /* which converter warp writes the converter stamps */
+#endif
 #ifndef SL_TC_TRACE
 #define TC_STAMP(slot) do { } while (0)
 #else
@@ -200,7 +233,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     for (int i = 0; i < 2; i++)
     {
       mbar_init (a_full + i, (kPair ? 2 : 1) * kConvWarps); mbar_init (a_empty + i, 1);
-      mbar_init (t_full + i, 1); mbar_init (t_full + 2 + i, 1); mbar_init (t_empty + i, (kPair ? 2 : 1) * 4); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
+      mbar_init (t_full + i, 1); mbar_init (t_full + 2 + i, 1); mbar_init (t_empty + i, (kPair ? 2 : 1) * 4 * kHalves); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
     }
     mbar_init (b_full, 1); mbar_init (drain, 1); mbar_init (b_ready, 1);
     for (int i = 0; i < 4; i++) mbar_init (out_free + i, 1);
@@ -245,7 +278,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   if (warp == kProdWarp)
   {
     // ======================================= bulk-copy producer =======================================
-    if (lane == 0)
+    // Lane j < 8 owns row j of the group: it reads its channel index ONCE per work item and issues that row's bulk copy for
+    // every supertile. (Until round 2 one lane walked the eight rows and read the index from global memory for every row of every
+    // supertile — eight dependent L2 round trips of ~400 clocks under load: the producer, not the epilogue or the MMAs, set the
+    // kernel's pace of ~3500 clocks per supertile, which is why no epilogue or MMA variant ever moved it.)
     {
       unsigned kk = 0;
 #ifdef SL_TC_L2HINT
@@ -255,29 +291,33 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       for (uint32_t it = item0; it < P.n_items; it += istride)
       {
         const uint32_t g = item_group (P, it, rank).g;
+        const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
+        const uint32_t c = P.chan[gs + min ((uint32_t) (lane & 7), nv - 1u)];    // short groups repeat their last channel (rows computed, never stored)
+        const uint32_t *src = P.in + (size_t) c * P.frames;
         for (uint32_t k = 0; k < supers; k++, kk++)
         {
           const int rb = kk % kRawStages;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
-          mbar_wait_long (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
-          TC_STAMP (0);
-          mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
-          const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
-#pragma unroll 1
-          for (int j = 0; j < kJ; j++)
+          if (lane == 0)
           {
-            const uint32_t c = P.chan[gs + min ((uint32_t) j, nv - 1u)];   // short groups repeat their last channel (rows computed, never stored)
-#ifdef SL_TC_L2HINT
-            bulk_g2s_stream (sRaw + (rb * kJ + j) * kRawRow, P.in + (size_t) c * P.frames + (size_t) k * kSuper, nfr * 4u, raw_full + rb, pol);
-#else
-            bulk_g2s (sRaw + (rb * kJ + j) * kRawRow, P.in + (size_t) c * P.frames + (size_t) k * kSuper, nfr * 4u, raw_full + rb);
-#endif
-            if (k == 0) bulk_g2s (sHist + (rb * kJ + j) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
+            mbar_wait_long (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
+            TC_STAMP (0);
+            mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           }
+          __syncwarp ();
+          if (lane < kJ)
+          {
+#ifdef SL_TC_L2HINT
+            bulk_g2s_stream (sRaw + (rb * kJ + lane) * kRawRow, src + (size_t) k * kSuper, nfr * 4u, raw_full + rb, pol);
+#else
+            bulk_g2s (sRaw + (rb * kJ + lane) * kRawRow, src + (size_t) k * kSuper, nfr * 4u, raw_full + rb);
+#endif
+            if (k == 0) bulk_g2s (sHist + (rb * kJ + lane) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
+          }
+          __syncwarp ();
         }
       }
     }
-    __syncwarp ();
   }
   else if (warp >= kEpiWarps && warp < kEpiWarps + kConvWarps)
   {
@@ -297,9 +337,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
         unsigned char *Ahi = sA + ab * 2 * kPlaneBytes;
         mbar_wait_long (raw_full + rb, (kk / kRawStages) & 1);
-        if (cw == 0) TC_STAMP (1);
+        if (cw == SL_TC_TRACE_CW) TC_STAMP (1);
         mbar_wait_long (a_empty + ab, ((kk >> 1) & 1) ^ 1);                         // the MMAs of supertile kk - 2 have read this buffer
-        if (cw == 0) TC_STAMP (2);
+        if (cw == SL_TC_TRACE_CW) TC_STAMP (2);
         if (cw == 0 && k == 0)
         {
           // history = the carried raw tail of the previous call (this launch reads ovl_in and writes ovl_out)
@@ -315,35 +355,39 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
                 make_uint4 (__byte_perm (v0.x, v0.y, 0x6420), __byte_perm (v0.z, v0.w, 0x6420), __byte_perm (v1.x, v1.y, 0x6420), __byte_perm (v1.z, v1.w, 0x6420));
           }
         }
-        if (cw == kConvWarps - 1 && k != 0)
+        if (k != 0)
         {
-          // history = the last 16 chunks of the previous supertile's planes (the other buffer; this warp wrote them)
-          const unsigned char *prev = sA + (ab ^ 1) * 2 * kPlaneBytes + kChunksNew * kChunkBytes;
+          // history = the last 16 chunks of the previous supertile's planes (the other buffer). Every warp moves the groups it
+          // wrote itself (program order is all the synchronisation that takes): group kGroups - 4 + hg -> history group hg
 #pragma unroll
-          for (int i = 0; i < 2 * kChunksHist * kJ / 32; i++)
-          {
-            const int e = lane + 32 * i, plane = e >> 7, o = (e & 127) * 16;
-            *reinterpret_cast<uint4 *> (Ahi + plane * kPlaneBytes + o) = *reinterpret_cast<const uint4 *> (prev + plane * kPlaneBytes + o);
-          }
+          for (int hg = 0; hg < 4; hg++)
+            if ((kGroups - 4 + hg) % kConvWarps == cw)
+            {
+              const unsigned char *prev = sA + (ab ^ 1) * 2 * kPlaneBytes + (kChunksNew + 4 * hg) * kChunkBytes + lane * 16;
+              unsigned char *cur = Ahi + 4 * hg * kChunkBytes + lane * 16;
+              const uint4 v0 = *reinterpret_cast<const uint4 *> (prev), v1 = *reinterpret_cast<const uint4 *> (prev + kPlaneBytes);
+              *reinterpret_cast<uint4 *> (cur) = v0; *reinterpret_cast<uint4 *> (cur + kPlaneBytes) = v1;
+            }
         }
         {
-          // this warp's share of the new chunks: t in [cw * per, (cw + 1) * per), chunk = c4 + 4 t
-          const int per = (int) (nfr / 32) / kConvWarps;                          // 12 (or 6 for the half supertile at the end of a stream)
-          const unsigned char *src = sRaw + (rb * kJ + j) * kRawRow + (c4 + 4 * cw * per) * 32;
-          unsigned char *dst = Ahi + (kChunksHist + c4 + 4 * cw * per) * kChunkBytes + j * 16;
-          constexpr int kB = SL_TC_REGSPLIT ? 3 : 6;                             // chunks in flight (the role runs on 56 registers under the split)
+          // this warp's share of the new chunks: groups t = cw + kConvWarps * i, chunk = c4 + 4 t
+          const int per = (int) (nfr / 32) / kConvWarps;                          // groups per warp (half of it for the half supertile at the end of a stream)
+          const unsigned char *src = sRaw + (rb * kJ + j) * kRawRow + (c4 + 4 * cw) * 32;
+          unsigned char *dst = Ahi + (kChunksHist + c4 + 4 * cw) * kChunkBytes + j * 16;
+          constexpr int kB = kGroups / 2 / kConvWarps;                            // groups in flight
+          constexpr int kS = kConvWarps * 128, kD = kConvWarps * 4 * kChunkBytes;  // strides from one of the warp's groups to the next
           for (int t0 = 0; t0 < per; t0 += kB)
           {
             uint4 v[2 * kB];
 #pragma unroll
-            for (int t = 0; t < kB; t++) { v[2 * t] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * 128); v[2 * t + 1] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * 128 + 16); }
+            for (int t = 0; t < kB; t++) { v[2 * t] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * kS); v[2 * t + 1] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * kS + 16); }
 #pragma unroll
             for (int t = 0; t < kB; t++)
             {
               const uint4 v0 = v[2 * t], v1 = v[2 * t + 1];
-              *reinterpret_cast<uint4 *> (dst + (t0 + t) * 4 * kChunkBytes) =
+              *reinterpret_cast<uint4 *> (dst + (t0 + t) * kD) =
                   make_uint4 (__byte_perm (v0.x, v0.y, 0x7531), __byte_perm (v0.z, v0.w, 0x7531), __byte_perm (v1.x, v1.y, 0x7531), __byte_perm (v1.z, v1.w, 0x7531));
-              *reinterpret_cast<uint4 *> (dst + kPlaneBytes + (t0 + t) * 4 * kChunkBytes) =
+              *reinterpret_cast<uint4 *> (dst + kPlaneBytes + (t0 + t) * kD) =
                   make_uint4 (__byte_perm (v0.x, v0.y, 0x6420), __byte_perm (v0.z, v0.w, 0x6420), __byte_perm (v1.x, v1.y, 0x6420), __byte_perm (v1.z, v1.w, 0x6420));
             }
           }
@@ -364,7 +408,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         }
         asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp ();
-        if (cw == 0) TC_STAMP (3);
+        if (cw == SL_TC_TRACE_CW) TC_STAMP (3);
         if (lane == 0) { if (kPair) mbar_arrive_cluster (a_full_ldr + ab * 8u); else mbar_arrive (a_full + ab); mbar_arrive (raw_empty + rb); }
       }
     }
@@ -472,6 +516,191 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
   else
   {
     // ========================================== epilogue ==========================================
+#if SL_TC_HALVES == 2
+    // TMEM lane = 32 w + lane = 8 q + j: the two threads (q, j) of a set — one in each of the two warps that may read lane quadrant
+    // w — own firmware block q of channel j of the supertile, half h its samples [24 h, 24 h + 24). Both run the (short) state chain
+    // of the block; half 0 hands state and envelope on to the next supertile.
+    const int es = warp >> 3, h = (warp >> 2) & 1, w = warp & 3, a = lane >> 3, j = lane & 7, q = 4 * w + a;
+    const bool tracer = (w == 0 && h == 0);
+    float *myW = sW + es * (4 * kJ * 4), *myPk = sPk + es * (kHalves * kQ * kJ);
+    const float decay = P.agc_decay;
+    unsigned kk = 0;
+    for (uint32_t it = item0; it < P.n_items; it += istride)
+    {
+      const uint32_t g = it, gi = P.ginfo[g];
+      const bool jvalid = (uint32_t) j < (gi >> 8);
+      const uint32_t c = P.chan[P.gstart[g] + min ((uint32_t) j, (gi >> 8) - 1u)];
+      const float s0 = P.s0[gi & 0xFFu], s8 = s0 * 256.0f, s16 = s0 * 65536.0f, s24 = s0 * 16777216.0f, z0s = P.sz[gi & 0xFFu];
+      for (uint32_t k = 0; k < supers; k++, kk++)
+      {
+        if ((int) (kk % kSets) != es) continue;
+        const int tb = kk & 1;
+        const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
+        const int nblk = (int) (nfr / kBlk);
+        const bool last_q = q == nblk - 1;
+        mbar_wait_long (t_full + (kk & 3), (kk >> 2) & 1);
+        tc_fence_after ();
+        if (tracer) TC_STAMP (7);
+        // ---- accumulators -> float: y = (D24 2^24 + D16 2^16 + D8 2^8 + D0) * unit (arm_q15_to_float's 1/32768 folded in)
+        float y[kHalf];
+        const uint32_t taddr = tmem + (uint32_t) tb * 256u + ((uint32_t) (32 * w) << 16);
+        const uint32_t tcol = taddr + (uint32_t) (h * kHalf);
+#pragma unroll
+        for (int i = 0; i < kHalf / 8; i++)
+        {
+          uint32_t v0[8], v1[8], v2[8], v3[8];
+          tmem_ld8 (tcol + 8 * i, v0); tmem_ld8 (tcol + kDig + 8 * i, v1); tmem_ld8 (tcol + 2 * kDig + 8 * i, v2); tmem_ld8 (tcol + 3 * kDig + 8 * i, v3);
+          tmem_ld_wait ();
+#pragma unroll
+          for (int n = 0; n < 8; n++)
+            y[8 * i + n] = fmaf (__int2float_rn ((int) v0[n]), s24, fmaf (__int2float_rn ((int) v1[n]), s16, fmaf (__int2float_rn ((int) v2[n]), s8, __int2float_rn ((int) v3[n]) * s0)));
+        }
+        float z[4];
+        {
+          uint32_t v0[4], v1[4], v2[4], v3[4];
+          tmem_ld4 (taddr + 48, v0); tmem_ld4 (taddr + kDig + 48, v1); tmem_ld4 (taddr + 2 * kDig + 48, v2); tmem_ld4 (taddr + 3 * kDig + 48, v3);
+          tmem_ld_wait ();
+          const float z8 = z0s * 256.0f, z16 = z0s * 65536.0f, z24 = z0s * 16777216.0f;
+#pragma unroll
+          for (int r = 0; r < 4; r++)
+            z[r] = fmaf (__int2float_rn ((int) v0[r]), z24, fmaf (__int2float_rn ((int) v1[r]), z16, fmaf (__int2float_rn ((int) v2[r]), z8, __int2float_rn ((int) v3[r]) * z0s)));
+        }
+        // both warps of the quadrant have read (the state columns are read by both): columns [0,52) are zeroed for the next
+        // supertile's xh MMAs, each warp its own audio columns, half 1 the state columns too
+        tc_fence_before ();
+        named_bar (7 + 4 * es + w, 64);
+        tc_fence_after ();
+        if (h == 0) tmem_zero<kHalf> (taddr); else tmem_zero<kHalf + 4> (taddr + kHalf);
+        tc_fence_before ();
+        __syncwarp ();
+        if (lane == 0) mbar_arrive (t_empty + tb);                                 // the accumulator buffer now lives in registers
+        if (tracer) TC_STAMP (8);
+        // ---- level 1: start state of the block inside the warp (zero at the warp's first block): P_{a+1} = M48 P_a + z_a
+        float Pst[4] = { 0.f, 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int kq = 0; kq < 3; kq++)
+        {
+          float t[4], nx[4];
+#pragma unroll
+          for (int r = 0; r < 4; r++) t[r] = __shfl_sync (0xffffffffu, z[r], kq * 8 + j);
+          matvec4 (P.tab.Mp[1], Pst, t, nx);
+          if (kq < a) { Pst[0] = nx[0]; Pst[1] = nx[1]; Pst[2] = nx[2]; Pst[3] = nx[3]; }
+        }
+        if (a == 3 && h == 0)
+        {
+          float We[4];
+          matvec4 (P.tab.Mp[1], Pst, z, We);                                      // the warp's four blocks from a zero start
+          *reinterpret_cast<float4 *> (myW + (w * kJ + j) * 4) = make_float4 (We[0], We[1], We[2], We[3]);
+        }
+        // ---- carried state of the channel: from the previous call (first supertile) or the previous supertile
+        // (every supertile but the CTA's first waits for its predecessor's hand-over, also across items where the value is
+        // not used: no phase of the two-slot carry barriers is ever skipped, so a parity can never be mistaken for an older one)
+        float S[4], envc;
+        if (kk != 0) mbar_wait (s_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
+        if (k == 0)
+        {
+          const float *stc = P.state + (size_t) c * 8;
+          S[0] = __ldcg (stc + 0); S[1] = __ldcg (stc + 1); S[2] = __ldcg (stc + 2); S[3] = __ldcg (stc + 3);
+        }
+        else
+        {
+          const float4 v = *reinterpret_cast<const float4 *> (sCarryS + (((kk - 1) & 1) * kJ + j) * 4);
+          S[0] = v.x; S[1] = v.y; S[2] = v.z; S[3] = v.w;
+        }
+        if (tracer) TC_STAMP (10);
+        named_bar (1 + 3 * es, 128 * kHalves);
+        if (tracer) TC_STAMP (11);
+        // ---- level 2: state at the warp's first block, then at this block
+#pragma unroll
+        for (int ww = 0; ww < 3; ww++)
+          if (ww < w)
+          {
+            const float4 v = *reinterpret_cast<const float4 *> (myW + (ww * kJ + j) * 4);
+            const float add[4] = { v.x, v.y, v.z, v.w };
+            float nx[4];
+            matvec4 (P.tab.M192, S, add, nx);
+            S[0] = nx[0]; S[1] = nx[1]; S[2] = nx[2]; S[3] = nx[3];
+          }
+        float st[4];
+        {
+          const float4 m0 = *reinterpret_cast<const float4 *> (sMp + a * 20), m1 = *reinterpret_cast<const float4 *> (sMp + a * 20 + 4);
+          const float4 m2 = *reinterpret_cast<const float4 *> (sMp + a * 20 + 8), m3 = *reinterpret_cast<const float4 *> (sMp + a * 20 + 12);
+          st[0] = Pst[0] + (m0.x * S[0] + m0.y * S[1] + m0.z * S[2] + m0.w * S[3]);
+          st[1] = Pst[1] + (m1.x * S[0] + m1.y * S[1] + m1.z * S[2] + m1.w * S[3]);
+          st[2] = Pst[2] + (m2.x * S[0] + m2.y * S[1] + m2.z * S[2] + m2.w * S[3]);
+          st[3] = Pst[3] + (m3.x * S[0] + m3.y * S[1] + m3.z * S[2] + m3.w * S[3]);
+        }
+        if (last_q && h == 0)
+        {
+          // end state of the last block = carried state of the next supertile / the next call
+          float en[4];
+          matvec4 (P.tab.Mp[1], st, z, en);
+          *reinterpret_cast<float4 *> (sCarryS + ((kk & 1) * kJ + j) * 4) = make_float4 (en[0], en[1], en[2], en[3]);
+          if (k + 1 == supers && jvalid)
+          {
+            float *stw = P.state + (size_t) c * 8;
+            __stcg (stw + 0, en[0]); __stcg (stw + 1, en[1]); __stcg (stw + 2, en[2]); __stcg (stw + 3, en[3]);
+          }
+          mbar_arrive (s_bar + (kk & 1));
+        }
+        // ---- add the zero-input response of the true start state; the half's peak
+        const float peak = (h == 0) ? corr_half<0> (P, y, st) : corr_half<1> (P, y, st);
+        myPk[(h * kQ + q) * kJ + j] = peak;
+        if (kk != 0) mbar_wait (e_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
+        envc = (k == 0) ? __ldcg (P.state + (size_t) c * 8 + 4) : sCarryE[((kk - 1) & 1) * kJ + j];
+        if (tracer) TC_STAMP (12);
+        named_bar (2 + 3 * es, 128 * kHalves);
+        if (tracer) TC_STAMP (13);
+        // ---- AGC envelope: the oracle's sequential walk env_b = max(peak_b, fl(env_{b-1} * decay)) over the blocks before and
+        // including this one; a block's peak (arm_max_f32 over its 48 samples) is the larger of its halves' peaks
+        // (a [half][channel][block] layout read as 16-byte words was measured slower: 396 vs 416 Gsamples/s)
+        float e = envc;
+#pragma unroll
+        for (int qq = 0; qq < kQ; qq++)
+        {
+          const float p = fmaxf (myPk[qq * kJ + j], myPk[(kQ + qq) * kJ + j]);
+          if (qq <= q) e = fmaxf (p, e * decay);
+        }
+        if (last_q && h == 0)
+        {
+          sCarryE[(kk & 1) * kJ + j] = e;
+          if (k + 1 == supers && jvalid)
+          {
+            __stcg (P.state + (size_t) c * 8 + 4, e);
+            P.flag[c] = P.flag_final;                                              // the FFT kernel's hand-over counter stays consistent
+          }
+          mbar_arrive (e_bar + (kk & 1));
+        }
+        const float gain = fminf (__fdiv_rn (P.agc_target, fmaxf (e, P.agc_floor)), P.agc_gmax);
+        if (tracer) TC_STAMP (9);
+        if (q < nblk && jvalid)
+        {
+          const size_t t0 = (size_t) k * kSuper + (size_t) q * kBlk + (size_t) (h * kHalf);
+          if (P.audio_dbg)
+          {
+            float4 *adbg = reinterpret_cast<float4 *> (P.audio_dbg + (size_t) c * P.frames + t0);
+#pragma unroll
+            for (int n = 0; n < kHalf; n += 4) adbg[n / 4] = make_float4 (y[n], y[n + 1], y[n + 2], y[n + 3]);
+          }
+          if (P.gain_dbg && h == 0) P.gain_dbg[(size_t) c * (P.frames / kBlk) + t0 / kBlk] = gain;
+          // ---- gain (arm_scale_f32), pack (arm_float_to_q15) and store: the half block is 96 contiguous bytes. 256-bit stores
+          // (sm_100: STG.E.256) that do not allocate in L1 — the shared-memory / L1 data pipe is what the tensor core fetches its
+          // operands through
+          const float g15 = gain * 32768.0f;                                       // exact: power of two
+          uint4 *dst = reinterpret_cast<uint4 *> (P.out + (size_t) c * P.frames + t0);
+#ifdef SL_TC_ABLATE_ST                                                              // (profiling aid: what the output stores cost)
+          if (g15 == 123.456f)
+#endif
+#pragma unroll
+          for (int n = 0; n < kHalf; n += 8)
+            asm volatile ("st.global" SL_TC_STHINT ".v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + n / 4),
+                          "r"(pack_lr (y[n] * g15)), "r"(pack_lr (y[n + 1] * g15)), "r"(pack_lr (y[n + 2] * g15)), "r"(pack_lr (y[n + 3] * g15)),
+                          "r"(pack_lr (y[n + 4] * g15)), "r"(pack_lr (y[n + 5] * g15)), "r"(pack_lr (y[n + 6] * g15)), "r"(pack_lr (y[n + 7] * g15)) : "memory");
+        }
+        if (tracer) TC_STAMP (14);
+      }
+    }
+#else
 #if SL_TC_REGSPLIT
     asm volatile ("setmaxnreg.inc.sync.aligned.u32 152;");
 #endif
@@ -758,6 +987,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
 #if SL_TC_BULKOUT
     if (lane == 0) asm volatile ("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's output copies complete before the CTA retires
     __syncwarp ();
+#endif
 #endif
   }
 

@@ -26,4 +26,7 @@ def d_(a, b): return np.mean(t[mid, a] - t[mid, b])
 print("period (epi done to done): %.0f" % np.mean(np.diff(t[mid, 14])))
 print("conv: wait raw %.0f  wait a_empty %.0f  work %.0f" % (d_(1, 0), d_(2, 1), d_(3, 2)))
 print("mma: a_full after conv done %.0f  wait t_empty %.0f  issue %.0f ; t_full seen by epi after issue %.0f" % (d_(4, 3), d_(5, 4), d_(6, 5), d_(7, 6)))
-print("epi: tmem %.0f zero-state %.0f wait s_bar %.0f BAR1 %.0f corr+wait e_bar %.0f BAR2 %.0f tail %.0f total %.0f" % (d_(8, 7), d_(9, 8), d_(10, 9), d_(11, 10), d_(12, 11), d_(13, 12), d_(14, 13), d_(14, 7)))
+if np.mean(t[mid, 9]) > np.mean(t[mid, 13]):   # split epilogue: stamp 9 sits after the envelope walk and the gain
+    print("epi: tmem %.0f level1+wait s_bar %.0f BAR1 %.0f corr+wait e_bar %.0f BAR2 %.0f walk+gain %.0f pack+store %.0f total %.0f" % (d_(8, 7), d_(10, 8), d_(11, 10), d_(12, 11), d_(13, 12), d_(9, 13), d_(14, 9), d_(14, 7)))
+else:
+    print("epi: tmem %.0f zero-state %.0f wait s_bar %.0f BAR1 %.0f corr+wait e_bar %.0f BAR2 %.0f tail %.0f total %.0f" % (d_(8, 7), d_(9, 8), d_(10, 9), d_(11, 10), d_(12, 11), d_(13, 12), d_(14, 13), d_(14, 7)))
