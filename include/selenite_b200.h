@@ -235,6 +235,11 @@ int slb_st_fir_decimate_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ntaps, 
 int slb_st_fir_decimate_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, uint32_t M, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream);
 int slb_st_fir_interpolate_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ntaps, uint32_t L, float *hist, const float *src, float *dst, uint32_t n, void *stream);
 int slb_st_fir_interpolate_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, uint32_t L, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream);
+int slb_st_fir_decimate_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t ntaps, uint32_t M, int32_t *hist, const int32_t *src, int32_t *dst, uint32_t n, void *stream);      /* arm_fir_decimate_q31.c:60 */
+int slb_st_fir_interpolate_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t ntaps, uint32_t L, int32_t *hist, const int32_t *src, int32_t *dst, uint32_t n, void *stream);   /* arm_fir_interpolate_q31.c:62 */
+/* normalised LMS adaptive FIR (arm_lms_norm_f32.c:161): noise reduction (out) / auto-notch (err) when src is a delayed copy of ref.
+ * coeffs: device [channels][ntaps], state: device [channels][ntaps + 1] = ntaps - 1 previous samples, energy, x0; both updated in place. */
+int slb_st_lms_norm_f32 (slb_ctx *ctx, float *coeffs, uint32_t ntaps, float mu, float *state, const float *src, const float *ref, float *out, float *err, uint32_t n, void *stream);
 int slb_st_biquad_df2T_f32 (slb_ctx *ctx, const float *coeffs, uint32_t n_stages, float *state, const float *src, float *dst, uint32_t n, void *stream);
 int slb_st_biquad_stereo_df2T_f32 (slb_ctx *ctx, const float *coeffs, uint32_t n_stages, float *state, const float *src, float *dst, uint32_t nframes, void *stream);
 int slb_st_biquad_df1_f32 (slb_ctx *ctx, const float *coeffs, uint32_t n_stages, float *state, const float *src, float *dst, uint32_t n, void *stream);

@@ -49,6 +49,23 @@ void ref_fir_interpolate_f32 (const float *c, uint32_t nt, uint32_t L, float *st
   arm_fir_interpolate_instance_f32 S = { (uint8_t) L, (uint16_t) (nt / L), (float *) c, st };
   for (uint32_t o = 0; o < n; o += block) arm_fir_interpolate_f32 (&S, (float *) src + o, dst + o * L, block);
 }
+void ref_lms_norm_f32 (float *coeffs, uint32_t nt, float mu, float *st, float *en_x0, const float *src, const float *ref,
+                        float *out, float *err, uint32_t n, uint32_t block)
+{
+  arm_lms_norm_instance_f32 S = { (uint16_t) nt, st, coeffs, mu, en_x0[0], en_x0[1] };
+  for (uint32_t o = 0; o < n; o += block) arm_lms_norm_f32 (&S, (float *) src + o, (float *) ref + o, out + o, err + o, block);
+  en_x0[0] = S.energy; en_x0[1] = S.x0;
+}
+void ref_fir_decimate_q31 (const int32_t *c, uint32_t nt, uint32_t M, int32_t *st, const int32_t *src, int32_t *dst, uint32_t n, uint32_t block)
+{
+  arm_fir_decimate_instance_q31 S = { (uint8_t) M, (uint16_t) nt, (q31_t *) c, st };
+  for (uint32_t o = 0; o < n; o += block) arm_fir_decimate_q31 (&S, (q31_t *) src + o, dst + o / M, block);
+}
+void ref_fir_interpolate_q31 (const int32_t *c, uint32_t nt, uint32_t L, int32_t *st, const int32_t *src, int32_t *dst, uint32_t n, uint32_t block)
+{
+  arm_fir_interpolate_instance_q31 S = { (uint8_t) L, (uint16_t) (nt / L), (q31_t *) c, st };
+  for (uint32_t o = 0; o < n; o += block) arm_fir_interpolate_q31 (&S, (q31_t *) src + o, dst + o * L, block);
+}
 void ref_fir_interpolate_q15 (const int16_t *c, uint32_t nt, uint32_t L, int16_t *st, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block)
 {
   arm_fir_interpolate_instance_q15 S = { (uint8_t) L, (uint16_t) (nt / L), (q15_t *) c, st };

@@ -45,6 +45,14 @@ void SLO (fir_decimate_q15) (const int16_t *coeffs, uint32_t ntaps, uint32_t M, 
 /* interpolator: ntaps % L == 0, state block+ntaps/L-1, L outputs per input (arm_fir_interpolate_f32.c:470) */
 void SLO (fir_interpolate_f32) (const float *coeffs, uint32_t ntaps, uint32_t L, float *state, const float *src, float *dst, uint32_t n, uint32_t block);
 void SLO (fir_interpolate_q15) (const int16_t *coeffs, uint32_t ntaps, uint32_t L, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block);
+/* normalised LMS adaptive FIR (arm_lms_norm_f32.c:161): per sample y = sum state*coeffs (oldest first), e = ref - y,
+ * coeffs += (e mu / (energy + 1.19e-7)) * state; energy is the running sum of squares over the tap window. coeffs[ntaps] and
+ * en_x0[2] = {energy, x0} are updated in place; state = ntaps-1 previous samples + block (as arm_lms_norm_init_f32 lays it out). */
+void SLO (lms_norm_f32) (float *coeffs, uint32_t ntaps, float mu, float *state, float *en_x0, const float *src, const float *ref,
+                         float *out, float *err, uint32_t n, uint32_t block);
+/* q31 polyphase stages (arm_fir_decimate_q31.c:60, arm_fir_interpolate_q31.c:62): q63 accumulator, result (q31) (acc >> 31) */
+void SLO (fir_decimate_q31) (const int32_t *coeffs, uint32_t ntaps, uint32_t M, int32_t *state, const int32_t *src, int32_t *dst, uint32_t n, uint32_t block);
+void SLO (fir_interpolate_q31) (const int32_t *coeffs, uint32_t ntaps, uint32_t L, int32_t *state, const int32_t *src, int32_t *dst, uint32_t n, uint32_t block);
 
 /* ---- biquad cascades: coeffs {b0,b1,b2,a1,a2} per stage, feedback sign +a1,+a2
  * (arm_biquad_cascade_df1_f32.c:52). df2T state 2/stage, stereo df2T 4/stage, df1 4/stage.

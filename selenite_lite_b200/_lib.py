@@ -92,6 +92,12 @@ def load():
             if not os.path.exists(path):
                 raise RuntimeError("selenite_lite_b200: CUDA library missing and cannot be built (%s); "
                                    "there is no CPU fallback" % exc)
+            # a prebuilt library older than the sources: say so — the argument types below come from the CURRENT header, and a
+            # silent ABI drift would be memory corruption rather than an error (set SELENITE_B200_ALLOW_STALE=1 to keep going quietly)
+            if not os.environ.get("SELENITE_B200_ALLOW_STALE"):
+                import warnings
+                warnings.warn("selenite_lite_b200: %s is older than its sources and could not be rebuilt (%s); loading the stale "
+                              "library" % (path, exc), RuntimeWarning)
     if not os.path.exists(path):
         raise RuntimeError("selenite_lite_b200: %s not found; run __graft_entry__.build(). There is no CPU fallback." % path)
     lib = C.CDLL(path)

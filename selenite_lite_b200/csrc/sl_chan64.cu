@@ -626,8 +626,14 @@ int chan64_launch (slb_ctx *ctx, Chan64State *st, const int16_t *d_in, int16_t *
   const uint64_t items = (uint64_t) ns * P.tiles;
   uint64_t grid = (uint64_t) sm_count * per_sm;          // co-resident: the look-back may spin on a predecessor
   if (grid > items) grid = items;
-  chan64_f32_kernel<<<(unsigned) grid, kThreads, kSmemBytes, stream>>> (P);
-  e = cudaGetLastError ();
+  // cooperative launch (gang-scheduled grid): the look-back polls predecessors, see launch_rx_ssb_f32
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3 ((unsigned) grid); lc.blockDim = dim3 (kThreads); lc.dynamicSmemBytes = kSmemBytes; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  e = cudaLaunchKernelEx (&lc, chan64_f32_kernel, P);
+  if (e == cudaSuccess) e = cudaGetLastError ();
   if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));
   ctx_count_launch (ctx, 1);
   return SLB_OK;

@@ -831,9 +831,17 @@ int launch_rx_ssb_f32 (const RxF32Launch &L, int sm_count, void *stream_)
   // 448: 117 Gsamples/s — i.e. every CTA is an internally latency-bound pipeline; shrinking the grid to make the segment
   // hand-over trivially satisfied costs more than the polling it removes.)
   if (const char *g = std::getenv ("SELENITE_B200_RX_GRID")) { const long v = std::atol (g); if (v > 0 && (uint64_t) v <= (uint64_t) sm_count * per_sm) grid = (uint64_t) v; }   // profiling aid
-  if (L.tx) ssb_f32_kernel<true><<<(unsigned) grid, kThreads, smem, stream>>> (P);
-  else ssb_f32_kernel<false><<<(unsigned) grid, kThreads, smem, stream>>> (P);
-  return (int) cudaGetLastError ();
+  // Cooperative launch: consecutive segments of a channel hand over through a flag the successor polls, so every CTA of the
+  // grid must be resident at once. The cooperative attribute makes the driver schedule the grid as a gang — next to other
+  // work on the device (a second stream of this library, another context, MPS) the launch waits for room or fails with
+  // cudaErrorCooperativeLaunchTooLarge, where a plain launch could leave resident CTAs spinning on one that never starts.
+  cudaLaunchConfig_t lc{};
+  lc.gridDim = dim3 ((unsigned) grid); lc.blockDim = dim3 (kThreads); lc.dynamicSmemBytes = smem; lc.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  e = L.tx ? cudaLaunchKernelEx (&lc, ssb_f32_kernel<true>, P) : cudaLaunchKernelEx (&lc, ssb_f32_kernel<false>, P);
+  return (int) (e != cudaSuccess ? e : cudaGetLastError ());
 }
 
 }  // namespace sl

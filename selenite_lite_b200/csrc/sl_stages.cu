@@ -153,6 +153,83 @@ __global__ void fir_kernel (const T *__restrict__ coeffs, int ntaps, int M, int 
 }
 
 // =====================================================================================================================
+// normalised LMS (arm_lms_norm_f32.c:161) — the adaptive stage behind noise reduction (take `out`: the predictable part of the
+// audio) and the auto-notch (take `err`: the audio minus its predictable, tonal part) when src is a delayed copy of ref.
+// The coefficients change with every sample, so a channel is strictly sequential: one thread per channel, a warp = 32 channels.
+// Window and coefficients live in shared memory ([tap][lane]: conflict-free); the window is kept twice, ntaps apart, so that
+// the oldest-first walk of the reference (:359-366) is a contiguous run without index wrapping. Samples travel through
+// 32 x 32 tiles (coalesced global accesses, padded rows). Every operation is rounded separately in the reference's order
+// (the oracle build has no FMA contraction), so output, error, coefficients and state agree bit for bit.
+// =====================================================================================================================
+constexpr int kLmsTile = 32;
+__global__ void __launch_bounds__ (32) lms_norm_f32_kernel (float *__restrict__ coeffs, int ntaps, float mu, float *__restrict__ state,
+                                                            const float *__restrict__ src, const float *__restrict__ ref,
+                                                            float *__restrict__ out, float *__restrict__ err, uint32_t channels, uint32_t n)
+{
+  extern __shared__ float lms_smem[];
+  float *win = lms_smem;                                  // [2 ntaps][32]
+  float *cf = win + 2 * ntaps * 32;                       // [ntaps][32]
+  float *tx = cf + ntaps * 32;                            // four tiles [32][33]: src, ref, out, err
+  float *tr = tx + 32 * 33, *to = tr + 32 * 33, *te = to + 32 * 33;
+  const int lane = threadIdx.x;
+  const uint32_t c0 = blockIdx.x * 32u, c = c0 + lane;
+  const bool valid = c < channels;
+  const uint32_t nch = min (32u, channels - c0);
+  float energy = 0.f, x0 = 0.f;
+  if (valid)
+  {
+    const float *st = state + (size_t) c * (ntaps + 1);
+    for (int k = 0; k + 1 < ntaps; k++) { const float v = st[k]; win[(1 + k) * 32 + lane] = v; win[(1 + k + ntaps) * 32 + lane] = v; }
+    energy = st[ntaps - 1]; x0 = st[ntaps];
+    for (int k = 0; k < ntaps; k++) cf[k * 32 + lane] = coeffs[(size_t) c * ntaps + k];
+  }
+  int p = 0;
+  for (uint32_t t0 = 0; t0 < n; t0 += kLmsTile)
+  {
+    const uint32_t tn = min ((uint32_t) kLmsTile, n - t0);
+    __syncwarp ();
+    for (uint32_t r = 0; r < nch; r++)
+      if ((uint32_t) lane < tn)
+      {
+        tx[r * 33 + lane] = src[(size_t) (c0 + r) * n + t0 + lane];
+        tr[r * 33 + lane] = ref[(size_t) (c0 + r) * n + t0 + lane];
+      }
+    __syncwarp ();
+    if (valid)
+      for (uint32_t i = 0; i < tn; i++)
+      {
+        const float in = tx[lane * 33 + i];
+        win[p * 32 + lane] = in; win[(p + ntaps) * 32 + lane] = in;
+        energy = __fsub_rn (energy, __fmul_rn (x0, x0));
+        energy = __fadd_rn (energy, __fmul_rn (in, in));
+        const float *w0 = win + (p + 1) * 32 + lane;     // the window, oldest first
+        float sum = 0.0f;
+        for (int k = 0; k < ntaps; k++) sum = __fadd_rn (sum, __fmul_rn (w0[k * 32], cf[k * 32 + lane]));
+        const float e = __fsub_rn (tr[lane * 33 + i], sum);
+        to[lane * 33 + i] = sum; te[lane * 33 + i] = e;
+        const float w = __fdiv_rn (__fmul_rn (e, mu), __fadd_rn (energy, 0.000000119209289f));
+        for (int k = 0; k < ntaps; k++) cf[k * 32 + lane] = __fadd_rn (cf[k * 32 + lane], __fmul_rn (w, w0[k * 32]));
+        x0 = w0[0];
+        p = (p + 1 == ntaps) ? 0 : p + 1;
+      }
+    __syncwarp ();
+    for (uint32_t r = 0; r < nch; r++)
+      if ((uint32_t) lane < tn)
+      {
+        out[(size_t) (c0 + r) * n + t0 + lane] = to[r * 33 + lane];
+        err[(size_t) (c0 + r) * n + t0 + lane] = te[r * 33 + lane];
+      }
+  }
+  if (valid)
+  {
+    float *st = state + (size_t) c * (ntaps + 1);
+    for (int k = 0; k + 1 < ntaps; k++) st[k] = win[(p + 1 + k) * 32 + lane];
+    st[ntaps - 1] = energy; st[ntaps] = x0;
+    for (int k = 0; k < ntaps; k++) coeffs[(size_t) c * ntaps + k] = cf[k * 32 + lane];
+  }
+}
+
+// =====================================================================================================================
 // biquad cascades — channel-parallel: one thread per (channel [, stereo rail]), sample-sequential, stage-major order
 // is irrelevant for a causal cascade so the cascade runs sample-major with the state in registers.
 // =====================================================================================================================
@@ -502,6 +579,23 @@ int slb_st_fir_decimate_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ntaps, 
 int slb_st_fir_decimate_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, uint32_t M, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream) { return fir_common<int16_t, 1> (ctx, coeffs, ntaps, M, 1, hist, src, dst, n, stream); }
 int slb_st_fir_interpolate_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ntaps, uint32_t L, float *hist, const float *src, float *dst, uint32_t n, void *stream) { return fir_common<float, 0> (ctx, coeffs, ntaps, 1, L, hist, src, dst, n, stream); }
 int slb_st_fir_interpolate_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t ntaps, uint32_t L, int16_t *hist, const int16_t *src, int16_t *dst, uint32_t n, void *stream) { return fir_common<int16_t, 1> (ctx, coeffs, ntaps, 1, L, hist, src, dst, n, stream); }
+// arm_fir_decimate_q31.c:60 / arm_fir_interpolate_q31.c:62: q63 accumulator of q31 x q31 products, result (q31) (acc >> 31), no saturation
+int slb_st_fir_decimate_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t ntaps, uint32_t M, int32_t *hist, const int32_t *src, int32_t *dst, uint32_t n, void *stream) { return fir_common<int32_t, 3> (ctx, coeffs, ntaps, M, 1, hist, src, dst, n, stream); }
+int slb_st_fir_interpolate_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t ntaps, uint32_t L, int32_t *hist, const int32_t *src, int32_t *dst, uint32_t n, void *stream) { return fir_common<int32_t, 3> (ctx, coeffs, ntaps, 1, L, hist, src, dst, n, stream); }
+
+// ---- normalised LMS. coeffs: device [channels][ntaps] (every channel adapts its own), state: device [channels][ntaps + 1] =
+// the ntaps - 1 previous samples oldest first (the head of the CMSIS state buffer), then energy and x0 of the instance; both in place
+int slb_st_lms_norm_f32 (slb_ctx *ctx, float *coeffs, uint32_t ntaps, float mu, float *state, const float *src, const float *ref,
+                         float *out, float *err, uint32_t n, void *stream)
+{
+  ST_BEGIN (ctx);
+  if (!coeffs || !state || !src || !ref || !out || !err || ntaps < 2 || ntaps > 128 || n == 0) return ctx_fail (ctx, SLB_ERR_ARG, "lms_norm: 2..128 taps");
+  const size_t smem = ((size_t) 3 * ntaps * 32 + 4 * 32 * 33) * sizeof (float);
+  cudaError_t e = cudaFuncSetAttribute (lms_norm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));
+  lms_norm_f32_kernel<<<(unsigned) ((C + 31) / 32), 32, smem, st>>> (coeffs, (int) ntaps, mu, state, src, ref, out, err, (uint32_t) C, n);
+  ST_END (ctx, (int) cudaGetLastError ());
+}
 
 // ---- biquads. state: device, CMSIS layout per channel (df2T 2/stage, stereo df2T 4/stage, df1 4/stage)
 static int bq_f32 (slb_ctx *ctx, const float *coeffs, uint32_t ns, float *state, const float *src, float *dst, uint32_t n, void *stream, int kind)

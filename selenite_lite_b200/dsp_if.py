@@ -183,7 +183,15 @@ class DspIf:
             io.adc, io.usb_in = adc.ctypes.data, usb_in.ctypes.data; ticks = adc.shape[1] // self.block_frames
         if usb_out is not None:
             usb_out = np.ascontiguousarray(usb_out, np.int16); dac = np.zeros_like(usb_out); keep += [usb_out, dac]
-            io.usb_out, io.dac = usb_out.ctypes.data, dac.ctypes.data; ticks = usb_out.shape[1] // self.block_frames
+            io.usb_out, io.dac = usb_out.ctypes.data, dac.ctypes.data
+            if ticks is not None and usb_out.shape[1] // self.block_frames != ticks:
+                raise ValueError("feeder_run: adc and usb_out must cover the same number of ticks")
+            ticks = usb_out.shape[1] // self.block_frames
+        for a in (adc, usb_out):
+            if a is not None and (a.shape[0] != self.channels or a.shape[1] % self.block_frames != 0 or a.shape[2] != 2):
+                raise ValueError("feeder_run: streams are int16 [channels][ticks * block_frames][2]")
+        if ticks is None:
+            raise ValueError("feeder_run: no stream given")
         self._ck(self.lib.slb_feeder_run(self.h, C.byref(io), ticks), "feeder_run")
         return usb_in, dac
 

@@ -116,6 +116,8 @@ class Oracle:
     def fir_decimate_q15(self, c, M, st, x, block): return self._fir("fir_decimate_q15", np.int16, i16p, c, st, x, block, (M,), len(x) // M)
     def fir_interpolate_f32(self, c, L, st, x, block): return self._fir("fir_interpolate_f32", np.float32, f32p, c, st, x, block, (L,), len(x) * L)
     def fir_interpolate_q15(self, c, L, st, x, block): return self._fir("fir_interpolate_q15", np.int16, i16p, c, st, x, block, (L,), len(x) * L)
+    def fir_decimate_q31(self, c, M, st, x, block): return self._fir("fir_decimate_q31", np.int32, i32p, c, st, x, block, (M,), len(x) // M)
+    def fir_interpolate_q31(self, c, L, st, x, block): return self._fir("fir_interpolate_q31", np.int32, i32p, c, st, x, block, (L,), len(x) * L)
 
     # ---- biquads: returns (out, state)
     def _bq(self, name, dt, ptr, coeffs, nstages, state, x, block, n, extra=()):
@@ -130,6 +132,15 @@ class Oracle:
     def biquad_df1_f32(self, c, ns, st, x, block): return self._bq("biquad_df1_f32", np.float32, f32p, c, ns, st, x, block, len(x))
     def biquad_df1_q15(self, c, ns, ps, st, x, block): return self._bq("biquad_df1_q15", np.int16, i16p, c, ns, st, x, block, len(x), (ps,))
     def biquad_df1_q31(self, c, ns, ps, st, x, block): return self._bq("biquad_df1_q31", np.int32, i32p, c, ns, st, x, block, len(x), (ps,))
+
+    def lms_norm_f32(self, coeffs, mu, st, en_x0, x, ref, block):
+        """arm_lms_norm_f32: returns (out, err, coeffs, state, en_x0) — copies, the inputs are not modified."""
+        c = np.ascontiguousarray(coeffs, np.float32).copy(); s_ = np.ascontiguousarray(st, np.float32).copy()
+        ex = np.ascontiguousarray(en_x0, np.float32).copy()
+        x = np.ascontiguousarray(x, np.float32); ref = np.ascontiguousarray(ref, np.float32)
+        out = np.zeros_like(x); err = np.zeros_like(x)
+        self._f("lms_norm_f32", [f32p, u32, C.c_float, f32p, f32p, f32p, f32p, f32p, f32p, u32, u32])(c, c.size, mu, s_, ex, x, ref, out, err, x.size, block)
+        return out, err, c, s_, ex
 
     # ---- transforms (interleaved re/im in, copy out)
     def cfft_f32(self, x, ifft=0, bitrev=1):

@@ -141,6 +141,50 @@ def test_fir_decimate_interpolate(ctx, best_oracle, rng):
             assert np.array_equal(got[ch], getattr(best_oracle, "fir_interpolate_" + name)(cc, 4, np.zeros(64 + B, dt), xx[ch], B)[0]), ("int", name, ch)
 
 
+def test_fir_decimate_interpolate_q31(ctx, best_oracle, rng):
+    """arm_fir_decimate_q31.c:60 / arm_fir_interpolate_q31.c:62, bit-exact with the history carried across two calls."""
+    c31 = rng.integers(-2**27, 2**27, 64).astype(np.int32); xx = rng.integers(-2**31, 2**31 - 1, (C, 2 * N)).astype(np.int32)
+    for M in (2, 4):
+        hist = torch.zeros((C, 63), dtype=torch.int32, device="cuda"); outs = []
+        for part in (xx[:, :N], xx[:, N:]):
+            d = torch.zeros((C, N // M), dtype=torch.int32, device="cuda")
+            ctx.st("fir_decimate_q31", c31, 64, M, hist, dev(part), d, N); outs.append(d.cpu().numpy())
+        got = np.concatenate(outs, 1)
+        for ch in range(C):
+            assert np.array_equal(got[ch], best_oracle.fir_decimate_q31(c31, M, np.zeros(64 + B, np.int32), xx[ch], B)[0]), ("dec", M, ch)
+        hist = torch.zeros((C, 64 // M - 1), dtype=torch.int32, device="cuda"); outs = []
+        for part in (xx[:, :N], xx[:, N:]):
+            d = torch.zeros((C, N * M), dtype=torch.int32, device="cuda")
+            ctx.st("fir_interpolate_q31", c31, 64, M, hist, dev(part), d, N); outs.append(d.cpu().numpy())
+        got = np.concatenate(outs, 1)
+        for ch in range(C):
+            assert np.array_equal(got[ch], best_oracle.fir_interpolate_q31(c31, M, np.zeros(64 + B, np.int32), xx[ch], B)[0]), ("int", M, ch)
+
+
+@pytest.mark.parametrize("ntaps", [8, 32, 64])
+def test_lms_norm_f32_bit_exact_with_carried_state(ctx, best_oracle, rng, ntaps):
+    """arm_lms_norm_f32.c:161 per channel (every channel adapts its own coefficients): output, error, coefficients and the carried
+    instance (history, energy, x0) bit for bit, over two calls of ragged length; and the auto-notch it is for."""
+    n1, n2 = 48 * 30 + 17, 48 * 20
+    t = np.arange(n1 + n2)
+    d = np.stack([(0.3 * np.sin(2 * np.pi * (700.0 + 90.0 * ch) * t / 48000.0) + 0.05 * rng.standard_normal(t.size)) for ch in range(C)]).astype(np.float32)
+    x = np.concatenate([np.zeros((C, 3), np.float32), d[:, :-3]], 1)
+    coeffs = torch.zeros((C, ntaps), dtype=torch.float32, device="cuda"); state = torch.zeros((C, ntaps + 1), dtype=torch.float32, device="cuda")
+    outs, errs = [], []
+    for a, b in ((0, n1), (n1, n1 + n2)):
+        o = torch.zeros((C, b - a), dtype=torch.float32, device="cuda"); e = torch.zeros_like(o)
+        ctx.st("lms_norm_f32", coeffs, ntaps, 0.05, state, dev(x[:, a:b]), dev(d[:, a:b]), o, e, b - a)
+        outs.append(o.cpu().numpy()); errs.append(e.cpu().numpy())
+    got_o, got_e = np.concatenate(outs, 1), np.concatenate(errs, 1)
+    cf, stt = coeffs.cpu().numpy(), state.cpu().numpy()
+    for ch in range(C):
+        eo, ee, ec, es, ex = best_oracle.lms_norm_f32(np.zeros(ntaps, np.float32), 0.05, np.zeros(ntaps + 1, np.float32), np.zeros(2, np.float32), x[ch], d[ch], 1)
+        assert np.array_equal(got_o[ch], eo) and np.array_equal(got_e[ch], ee), ch
+        assert np.array_equal(cf[ch], ec) and np.array_equal(stt[ch, :ntaps - 1], es[:ntaps - 1]) and np.array_equal(stt[ch, ntaps - 1:], ex), ch
+    if ntaps >= 32:
+        assert np.std(got_e[:, -2000:]) < 0.5 * np.std(d[:, -2000:])
+
+
 def test_biquads_bit_exact_with_carried_state(ctx, best_oracle, rng):
     p = slb.default_rx_f32_params(48000)
     cf = np.array(p.biquad[:10], np.float32)

@@ -61,6 +61,33 @@ def test_fir_decimate_interpolate(ref, port, rng):
     cq = q15(rng, 64, 4000); xq = q15(rng, BLOCK * 8); sq = np.zeros(64 + BLOCK, np.int16)
     assert np.array_equal(ref.fir_decimate_q15(cq, 4, sq, xq, BLOCK)[0], port.fir_decimate_q15(cq, 4, sq, xq, BLOCK)[0])
     assert np.array_equal(ref.fir_interpolate_q15(cq, 4, sq, xq, BLOCK)[0], port.fir_interpolate_q15(cq, 4, sq, xq, BLOCK)[0])
+    # q31 (arm_fir_decimate_q31.c:60, arm_fir_interpolate_q31.c:62): full-range samples, q63 accumulator >> 31, no saturation
+    c31 = rng.integers(-2**27, 2**27, 64).astype(np.int32); x31 = rng.integers(-2**31, 2**31 - 1, BLOCK * 8).astype(np.int32)
+    s31 = np.zeros(64 + BLOCK, np.int32)
+    for M in (2, 4):
+        assert np.array_equal(ref.fir_decimate_q31(c31, M, s31, x31, BLOCK)[0], port.fir_decimate_q31(c31, M, s31, x31, BLOCK)[0])
+        assert np.array_equal(ref.fir_interpolate_q31(c31, M, s31, x31, BLOCK)[0], port.fir_interpolate_q31(c31, M, s31, x31, BLOCK)[0])
+
+
+@pytest.mark.parametrize("ntaps", [8, 32])
+def test_lms_norm_f32_bit_exact(ref, port, rng, ntaps):
+    """arm_lms_norm_f32.c:161: output, error, adapted coefficients, state buffer head, energy and x0 — reference vs port, with the
+    instance carried over two calls."""
+    n = BLOCK * 40
+    t = np.arange(n)
+    d = (0.3 * np.sin(2 * np.pi * 1000.0 * t / 48000.0) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    x = np.concatenate([np.zeros(3, np.float32), d[:-3]])                        # the decorrelation delay of a line enhancer
+    c0 = np.zeros(ntaps, np.float32); st0 = np.zeros(ntaps + BLOCK, np.float32); ex0 = np.zeros(2, np.float32)
+    h = n // 2
+    for orc_a, orc_b in ((ref, port),):
+        ra = orc_a.lms_norm_f32(c0, 0.05, st0, ex0, x[:h], d[:h], BLOCK); rb = orc_b.lms_norm_f32(c0, 0.05, st0, ex0, x[:h], d[:h], BLOCK)
+        for u, v in zip(ra, rb):
+            assert np.array_equal(u[:ntaps - 1] if u.size == ntaps + BLOCK else u, v[:ntaps - 1] if v.size == ntaps + BLOCK else v)
+        ra2 = orc_a.lms_norm_f32(ra[2], 0.05, ra[3], ra[4], x[h:], d[h:], BLOCK); rb2 = orc_b.lms_norm_f32(rb[2], 0.05, rb[3], rb[4], x[h:], d[h:], BLOCK)
+        assert np.array_equal(ra2[0], rb2[0]) and np.array_equal(ra2[1], rb2[1]) and np.array_equal(ra2[2], rb2[2]) and np.array_equal(ra2[4], rb2[4])
+    # what it is for: the error output is the audio with the tone notched out (auto-notch), the filter output is the tone (noise reduction)
+    tail = slice(n // 2 - 2000, n // 2)
+    assert np.std(ra[1][tail]) < 0.5 * np.std(d[tail]) and np.std(ra[0][tail]) > 0.6 * np.std(d[tail])
 
 
 def _sos_cmsis(order=4, fc=300.0, fs=48000.0):
