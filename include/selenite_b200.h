@@ -146,6 +146,16 @@ int SLB_DSP_Init (slb_ctx *ctx);                                                
 int SLB_DSP_Set_RX (slb_ctx *ctx);                                                 /* dsp_if.c:347 */
 int SLB_DSP_Set_TX (slb_ctx *ctx);                                                 /* dsp_if.c:357 */
 int SLB_DSP_Set_Mode (slb_ctx *ctx, uint8_t mode);                                 /* dsp_if.c:367, all channels */
+/* SLB_DSP_Set_RX / _TX act on a CHANGE of direction (as ptt_set_rx / ptt_set_tx do, rxtx_if.c:255-317): the codec's mute-reroute-unmute
+ * (codec_if.c:230-345) becomes: the samples of both rings are flushed (pointers untouched, as DSP_Out_Buff_Mute) and the chain's carried
+ * state is cleared, so nothing captured or queued under the old routing comes out under the new one. slb_get_direction: 0 = RX, 1 = TX. */
+int slb_get_direction (const slb_ctx *ctx);
+/* CW side-tone, mixed at the hook the firmware marks ("mix CW tone to speaker signal here", dsp_if.c:218): SLB_DSP_Out_Buff_Read[_Ch]
+ * adds the tone to L and R of every keyed channel. Composition (ours) of reference stages: arm_sin_f32 (k 2 pi / fs) -> arm_scale_f32
+ * (level) -> arm_float_to_q15 -> arm_add_q15 (saturating); the phase counter k = (k + freq) mod fs restarts at 0 with every key-down.
+ * key_down: host [channels] bytes (NULL = all keys up). freq_hz = 0 switches the tone off. */
+int SLB_DSP_Set_Sidetone (slb_ctx *ctx, uint32_t freq_hz, float level);
+int SLB_DSP_Key (slb_ctx *ctx, const uint8_t *key_down);
 int SLB_DSP_Set_Mode_Channel (slb_ctx *ctx, uint32_t channel, uint8_t mode);
 int SLB_DSP_In_Buff_Write (slb_ctx *ctx, const uint16_t *pbuf, uint16_t size);     /* dsp_if.c:250, size = half-words */
 int SLB_DSP_In_Buff_Read (slb_ctx *ctx, uint8_t *pbuf, uint32_t size);             /* dsp_if.c:310, size = bytes */

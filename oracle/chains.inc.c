@@ -256,3 +256,27 @@ void SLO (rx_ssb_q15) (const slo_rx_q15_params *p, slo_rx_q15_state *st, const i
     for (uint32_t k = 0; k < B; k++) { out_lr[2 * (size_t) (o + k)] = y[k]; out_lr[2 * (size_t) (o + k) + 1] = y[k]; }   /* L = R */
   }
 }
+
+
+/* CW side-tone at the firmware's hook (dsp_if.c:218 "mix CW tone to speaker signal here"): see slo_api.h. */
+void SLO (sidetone_mix) (int16_t *lr, uint32_t frames, uint32_t *counter, int key_down, uint32_t freq_hz, uint32_t fs, float level)
+{
+  if (!key_down) { *counter = 0; return; }
+  const float w = (float) (6.283185307179586 / (double) fs);
+  float *x = (float *) malloc (sizeof (float) * frames), *s = (float *) malloc (sizeof (float) * frames), *sc = (float *) malloc (sizeof (float) * frames);
+  int16_t *t = (int16_t *) malloc (sizeof (int16_t) * frames), *l = (int16_t *) malloc (sizeof (int16_t) * frames), *r = (int16_t *) malloc (sizeof (int16_t) * frames);
+  for (uint32_t n = 0; n < frames; n++)
+  {
+    const uint32_t k = (uint32_t) (((uint64_t) *counter + (uint64_t) n * freq_hz) % fs);
+    x[n] = (float) k * w;
+    l[n] = lr[2 * n]; r[n] = lr[2 * n + 1];
+  }
+  SLO (sin_f32) (x, s, frames);
+  SLO (scale_f32) (s, level, sc, frames);
+  SLO (float_to_q15) (sc, t, frames);
+  SLO (add_q15) (l, t, l, frames);
+  SLO (add_q15) (r, t, r, frames);
+  for (uint32_t n = 0; n < frames; n++) { lr[2 * n] = l[n]; lr[2 * n + 1] = r[n]; }
+  *counter = (uint32_t) (((uint64_t) *counter + (uint64_t) frames * freq_hz) % fs);
+  free (x); free (s); free (sc); free (t); free (l); free (r);
+}

@@ -45,6 +45,10 @@ void SLO (fir_decimate_q15) (const int16_t *coeffs, uint32_t ntaps, uint32_t M, 
 /* interpolator: ntaps % L == 0, state block+ntaps/L-1, L outputs per input (arm_fir_interpolate_f32.c:470) */
 void SLO (fir_interpolate_f32) (const float *coeffs, uint32_t ntaps, uint32_t L, float *state, const float *src, float *dst, uint32_t n, uint32_t block);
 void SLO (fir_interpolate_q15) (const int16_t *coeffs, uint32_t ntaps, uint32_t L, int16_t *state, const int16_t *src, int16_t *dst, uint32_t n, uint32_t block);
+/* CW side-tone mixed into one call's worth of DAC frames (the hook of dsp_if.c:218). OUR composition: k = (*counter + n f) mod fs,
+ * arm_sin_f32 ((float) k * (float) (2 pi / fs)) -> arm_scale_f32 (level) -> arm_float_to_q15 -> arm_add_q15 onto L and R (saturating);
+ * key up: nothing is mixed and the counter returns to 0. lr = int16 [frames][2] in place. */
+void SLO (sidetone_mix) (int16_t *lr, uint32_t frames, uint32_t *counter, int key_down, uint32_t freq_hz, uint32_t fs, float level);
 /* normalised LMS adaptive FIR (arm_lms_norm_f32.c:161): per sample y = sum state*coeffs (oldest first), e = ref - y,
  * coeffs += (e mu / (energy + 1.19e-7)) * state; energy is the running sum of squares over the tap window. coeffs[ntaps] and
  * en_x0[2] = {energy, x0} are updated in place; state = ntaps-1 previous samples + block (as arm_lms_norm_init_f32 lays it out). */

@@ -64,6 +64,10 @@ struct slb_ctx
   // chain at the 1 ms cadence: accumulate `hop` frames, process, feed the ring from the previous super-block
   int16_t *d_acc = nullptr; int16_t *d_proc[2] = { nullptr, nullptr }; uint32_t acc_fill = 0; int proc_cur = 0;
 
+  // CW side-tone (dsp_if.c:218): one second of the tone as q15, key state and phase counter per channel
+  uint32_t tone_hz = 0; float tone_level = 0.f; int16_t *d_tone = nullptr; float *d_sin513 = nullptr; uint8_t *d_key = nullptr; uint32_t *d_tone_cnt = nullptr;
+  bool any_key = false;
+
   // scratch for the stage library (coefficients, FIR history double buffer)
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
 
@@ -168,6 +172,7 @@ static int reset_state (slb_ctx *ctx)
   ctx->flag_base = 0; ctx->ovl_parity = 0; ctx->acc_fill = 0; ctx->proc_cur = 0;
   ctx->ring_in.reset (R); ctx->ring_out.reset (R);
   ctx->ring_pc = false;
+  if (ctx->d_key) { CK (ctx, cudaMemset (ctx->d_key, 0, C)); CK (ctx, cudaMemset (ctx->d_tone_cnt, 0, (size_t) C * 4)); ctx->any_key = false; }
   if (ctx->chan) return chan64_reset (ctx, ctx->chan);
   if (ctx->q15) return rxq15_reset (ctx, ctx->q15);
   return SLB_OK;
@@ -254,6 +259,7 @@ void slb_destroy (slb_ctx *ctx)
   for (auto &kv : ctx->tc_lists) cudaFree (kv.second.d);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
+  cudaFree (ctx->d_tone); cudaFree (ctx->d_sin513); cudaFree (ctx->d_key); cudaFree (ctx->d_tone_cnt);
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
   cudaFree (ctx->d_blk); cudaFree (ctx->d_acc); cudaFree (ctx->d_scratch);
   cudaFree (ctx->d_rptr[0]); cudaFree (ctx->d_rptr[1]); cudaFree (ctx->d_active);
@@ -387,8 +393,69 @@ int SLB_DSP_Init (slb_ctx *ctx)                       // dsp_if.c:377-383 (+ i2s
   ctx->tx_mode = false;
   return reset_state (ctx);
 }
-int SLB_DSP_Set_RX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; ctx->tx_mode = false; return SLB_OK; }   // dsp_if.c:347 (codec routing is out of scope)
-int SLB_DSP_Set_TX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; ctx->tx_mode = true; return SLB_OK; }    // dsp_if.c:357
+// DSP_Set_RX / DSP_Set_TX (dsp_if.c:347 / :357, called from ptt_set_rx / ptt_set_tx, rxtx_if.c:306 / :269). The firmware hands the switch to
+// the codec, which mutes every path, re-routes ADC and DAC (I/Q <-> microphone, headphones <-> exciter) and unmutes (codec_if.c:230-345).
+// The codec itself is out of scope; what its mute means for the sample path is: nothing that was captured or queued under the OLD
+// routing may come out under the new one. So a real switch of direction flushes the samples of BOTH rings (as DSP_Out_Buff_Mute does for
+// one, dsp_if.c:188-195: samples to zero, pointers untouched — the cadence on both sides goes on), and the chain forgets the signal it was
+// following (filter history, biquad state, AGC / ALC envelope, the pending super-block), like a context that has just been created.
+static int switch_direction (slb_ctx *ctx, bool tx)
+{
+  if (ctx->tx_mode == tx) return SLB_OK;                                                   // ptt_set_tx / ptt_set_rx act on a change only
+  ctx->tx_mode = tx;
+  if (ctx->chan) return SLB_OK;                                                            // the channelizer has no firmware rings
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames, ovl = ctx->rx.fft_len - ctx->rx.hop, hop = ctx->rx.hop;
+  for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) CK (ctx, cudaMemsetAsync (ctx->d_ring[w][k], 0, (size_t) C * R * 2, ctx->stream));
+  for (int p = 0; p < 2; p++) CK (ctx, cudaMemsetAsync (ctx->d_ovl[p], 0, (size_t) C * ovl * 4, ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_state, 0, (size_t) C * 8 * sizeof (float), ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_flag, 0, (size_t) C * sizeof (unsigned), ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_acc, 0, (size_t) C * hop * 4, ctx->stream));
+  for (int p = 0; p < 2; p++) CK (ctx, cudaMemsetAsync (ctx->d_proc[p], 0, (size_t) C * hop * 4, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  ctx->flag_base = 0; ctx->ovl_parity = 0; ctx->acc_fill = 0; ctx->proc_cur = 0;
+  if (ctx->q15) return rxq15_reset (ctx, ctx->q15);
+  return SLB_OK;
+}
+int SLB_DSP_Set_RX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; return switch_direction (ctx, false); }
+int SLB_DSP_Set_TX (slb_ctx *ctx) { if (!ctx) return SLB_ERR_ARG; return switch_direction (ctx, true); }
+int slb_get_direction (const slb_ctx *ctx) { return ctx ? (ctx->tx_mode ? 1 : 0) : SLB_ERR_ARG; }
+
+// ---- CW side-tone at the hook the firmware marks (dsp_if.c:218) ----
+int SLB_DSP_Set_Sidetone (slb_ctx *ctx, uint32_t freq_hz, float level)
+{
+  if (!ctx) return SLB_ERR_ARG;
+  if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
+  if (freq_hz >= ctx->cfg.fs / 2 || !(level >= 0.f) || !(level < 1.0f)) return fail (ctx, SLB_ERR_ARG, "side-tone: 0 <= freq < fs / 2, 0 <= level < 1");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const uint32_t C = ctx->cfg.channels, fs = ctx->cfg.fs;
+  if (!ctx->d_tone)
+  {
+    CK (ctx, cudaMalloc (&ctx->d_tone, (size_t) fs * 2)); CK (ctx, cudaMalloc (&ctx->d_sin513, 513 * sizeof (float)));
+    CK (ctx, cudaMalloc (&ctx->d_key, C)); CK (ctx, cudaMalloc (&ctx->d_tone_cnt, (size_t) C * 4));
+    CK (ctx, cudaMemset (ctx->d_key, 0, C)); CK (ctx, cudaMemset (ctx->d_tone_cnt, 0, (size_t) C * 4));
+    CK (ctx, cudaMemcpy (ctx->d_sin513, host_sin_table (), 513 * sizeof (float), cudaMemcpyHostToDevice));
+  }
+  ctx->tone_hz = freq_hz; ctx->tone_level = level;
+  CK (ctx, launch_tone_table (ctx->d_tone, fs, level, ctx->d_sin513, ctx->stream));
+  CK (ctx, cudaMemsetAsync (ctx->d_tone_cnt, 0, (size_t) C * 4, ctx->stream));
+  CK (ctx, cudaStreamSynchronize (ctx->stream));
+  ctx->launches++;
+  return SLB_OK;
+}
+int SLB_DSP_Key (slb_ctx *ctx, const uint8_t *key_down)
+{
+  if (!ctx) return SLB_ERR_ARG;
+  if (!ctx->d_tone) return fail (ctx, SLB_ERR_STATE, "SLB_DSP_Set_Sidetone first");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  const uint32_t C = ctx->cfg.channels;
+  if (key_down) CK (ctx, cudaMemcpy (ctx->d_key, key_down, C, cudaMemcpyHostToDevice)); else CK (ctx, cudaMemset (ctx->d_key, 0, C));
+  // any_key stays set for one more read after the last key-up so that the released channels' phase counters are reset
+  bool any = false; if (key_down) for (uint32_t c = 0; c < C; c++) any = any || key_down[c] != 0;
+  ctx->any_key = ctx->any_key || any;
+  if (!any) { CK (ctx, cudaMemset (ctx->d_tone_cnt, 0, (size_t) C * 4)); ctx->any_key = false; }
+  return SLB_OK;
+}
 
 // which FT-817 mode bytes (rxtx_if.h:33-43) a chain has a demodulator / modulator for
 static int check_mode (slb_ctx *ctx, uint8_t mode)
@@ -731,6 +798,8 @@ static int ring_read_common (slb_ctx *ctx, int which, void *pbuf, uint32_t frame
     CK (ctx, launch_ring_plan (ctx->d_rptr[which], d_act, C, R, false, which != 0, frames, ctx->stream));
     CK (ctx, launch_ring_read_pc (ctx->d_blk, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, ctx->d_rptr[which], frames, ctx->stream));
     ctx->launches += 2;
+    if (which == 1 && ctx->any_key && ctx->tone_hz)                                                      // "mix CW tone to speaker signal here" (dsp_if.c:218)
+    { CK (ctx, launch_sidetone_mix (ctx->d_blk, C, frames, ctx->d_key, ctx->d_tone_cnt, ctx->d_rptr[1], ctx->d_tone, ctx->tone_hz, ctx->cfg.fs, ctx->stream)); ctx->launches++; }
     CK (ctx, cudaMemcpyAsync (pbuf, ctx->d_blk, (size_t) C * frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK (ctx, cudaStreamSynchronize (ctx->stream));
     return SLB_OK;
@@ -739,6 +808,8 @@ static int ring_read_common (slb_ctx *ctx, int which, void *pbuf, uint32_t frame
   const uint32_t rd0 = rp.plan_read (which != 0, frames);
   CK (ctx, launch_ring_read (ctx->d_blk, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, rd0, frames, ctx->stream));
   ctx->launches++;
+  if (which == 1 && ctx->any_key && ctx->tone_hz)                                                        // "mix CW tone to speaker signal here" (dsp_if.c:218)
+  { CK (ctx, launch_sidetone_mix (ctx->d_blk, C, frames, ctx->d_key, ctx->d_tone_cnt, nullptr, ctx->d_tone, ctx->tone_hz, ctx->cfg.fs, ctx->stream)); ctx->launches++; }
   CK (ctx, cudaMemcpyAsync (pbuf, ctx->d_blk, (size_t) C * frames * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   return SLB_OK;
@@ -813,6 +884,8 @@ int slb_feeder_run (slb_ctx *ctx, const slb_feeder_io *io, uint32_t ticks)
     CK (ctx, cudaMemcpyAsync (d_raw, io->usb_out, bytes, cudaMemcpyHostToDevice, st));
     CK (ctx, launch_ring_replay (false, nullptr, 0, 0, d_raw, (uint32_t) frames, d_out, ctx->d_ring[1][0], ctx->d_ring[1][1], C, R, d_plan, ticks, B, st));
     ctx->launches++;
+    if (ctx->any_key && ctx->tone_hz)                                                  // the side-tone of all `ticks` reads at once (keys constant over the run)
+    { CK (ctx, launch_sidetone_mix (d_out, C, (uint32_t) frames, ctx->d_key, ctx->d_tone_cnt, nullptr, ctx->d_tone, ctx->tone_hz, ctx->cfg.fs, st)); ctx->launches++; }
     CK (ctx, cudaMemcpyAsync (io->dac, d_out, bytes, cudaMemcpyDeviceToHost, st));
     CK (ctx, cudaStreamSynchronize (st));
   }

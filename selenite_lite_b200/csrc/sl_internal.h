@@ -78,6 +78,16 @@ int launch_ring_write_pc (const int16_t *d_blocks, uint32_t block_stride_frames,
 int launch_ring_read_pc (int16_t *d_blocks, const int16_t *d_ring_i, const int16_t *d_ring_q, uint32_t channels, uint32_t ring_frames,
                          const uint32_t *d_ptr, uint32_t frames, void *stream);
 
+// CW side-tone (the hook "mix CW tone to speaker signal here", dsp_if.c:218). d_tone = one second of the tone as q15
+// ([fs] samples: arm_sin_f32 (k * 2 pi / fs) -> arm_scale_f32 (level) -> arm_float_to_q15), built once by launch_tone_table;
+// launch_sidetone_mix adds tone[(cnt + n f) mod fs] to both words of frame n of every keyed channel (arm_add_q15, saturating)
+// and advances the channel's phase counter; a channel whose key is up has its counter reset (every element starts at phase 0).
+// d_first (per-channel cadence, may be null) = the [C][4] pointer words whose 4th entry is 0xFFFFFFFF for a channel skipped this call.
+int launch_tone_table (int16_t *d_tone, uint32_t fs, float level, const float *d_sin513, void *stream);
+int launch_sidetone_mix (int16_t *d_blocks, uint32_t channels, uint32_t frames, const uint8_t *d_key, uint32_t *d_cnt, const uint32_t *d_first,
+                         const int16_t *d_tone, uint32_t freq_hz, uint32_t fs, void *stream);
+const float *host_sin_table ();
+
 struct RxF32Launch
 {
   const int16_t *in; int16_t *out;         // [C][T][2]

@@ -218,4 +218,62 @@ int launch_copy_iq (const int16_t *d_in, int16_t *d_out, size_t n_frames, void *
   return (int) cudaGetLastError ();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// CW side-tone, mixed where the firmware marks it (dsp_if.c:218, end of DSP_Out_Buff_Read). OUR composition of reference
+// stages: arm_sin_f32 (FastMathFunctions/arm_sin_f32.c:72, table + linear interpolation) -> arm_scale_f32 -> arm_float_to_q15
+// (truncating, :147) -> arm_add_q15 (saturating, :115) onto L and R. The phase is an integer counter k = (k0 + n f) mod fs, so
+// the tone is a pure function of k: one second of it is tabulated once per setting and the mix is one add per word.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void tone_table_kernel (int16_t *__restrict__ tone, uint32_t fs, float w, float level, const float *__restrict__ tab)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= fs) return;
+  // arm_sin_f32.c:72-119 for x = k w >= 0
+  const float x = __fmul_rn ((float) k, w);
+  float in = __fmul_rn (x, 0.159154943092f);
+  const int n = (int) in;
+  in = __fsub_rn (in, (float) n);
+  const float findex = __fmul_rn (512.0f, in);
+  const unsigned idx = ((unsigned) (uint16_t) (int) findex) & 0x1ffu;
+  const float fract = __fsub_rn (findex, (float) idx);
+  const float sv = __fadd_rn (__fmul_rn (__fsub_rn (1.0f, fract), tab[idx]), __fmul_rn (fract, tab[idx + 1]));
+  const float sc = __fmul_rn (sv, level);                                                    // arm_scale_f32.c:77
+  const int q = __float2int_rz (__fmul_rn (sc, 32768.0f));                                   // arm_float_to_q15.c:147
+  tone[k] = (int16_t) max (-32768, min (32767, q));
+}
+__global__ void sidetone_mix_kernel (int16_t *__restrict__ blk, uint32_t channels, uint32_t frames, const uint8_t *__restrict__ key,
+                                     uint32_t *__restrict__ cnt, const uint32_t *__restrict__ first, const int16_t *__restrict__ tone, uint32_t f, uint32_t fs)
+{
+  const uint32_t c = blockIdx.x;
+  if (first && first[4 * c + 3] == 0xFFFFFFFFu) return;                                      // channel skipped this call (per-channel cadence)
+  const uint32_t k0 = cnt[c];
+  const bool down = key[c] != 0;
+  if (down)
+    for (uint32_t n = threadIdx.x; n < frames; n += blockDim.x)
+    {
+      const int t = tone[(uint32_t) (((uint64_t) k0 + (uint64_t) n * f) % fs)];
+      int16_t *p = blk + ((size_t) c * frames + n) * 2;
+      p[0] = (int16_t) max (-32768, min (32767, (int) p[0] + t));                             // arm_add_q15.c:115
+      p[1] = (int16_t) max (-32768, min (32767, (int) p[1] + t));
+    }
+  __syncthreads ();
+  if (threadIdx.x == 0) cnt[c] = down ? (uint32_t) (((uint64_t) k0 + (uint64_t) frames * f) % fs) : 0u;
+}
+}  // namespace
+
+int launch_tone_table (int16_t *d_tone, uint32_t fs, float level, const float *d_sin513, void *stream)
+{
+  const float w = (float) (6.283185307179586 / (double) fs);
+  tone_table_kernel<<<(fs + 255) / 256, 256, 0, (cudaStream_t) stream>>> (d_tone, fs, w, level, d_sin513);
+  return (int) cudaGetLastError ();
+}
+int launch_sidetone_mix (int16_t *d_blocks, uint32_t channels, uint32_t frames, const uint8_t *d_key, uint32_t *d_cnt, const uint32_t *d_first,
+                         const int16_t *d_tone, uint32_t freq_hz, uint32_t fs, void *stream)
+{
+  sidetone_mix_kernel<<<channels, 64, 0, (cudaStream_t) stream>>> (d_blocks, channels, frames, d_key, d_cnt, d_first, d_tone, freq_hz, fs);
+  return (int) cudaGetLastError ();
+}
+
 }  // namespace sl

@@ -172,6 +172,19 @@ class DspIf:
         self._ck(self.lib.SLB_DSP_Out_Buff_Read_Ch(self.h, out.ctypes.data, size, m), "DSP_Out_Buff_Read_Ch")
         return out
 
+    def DSP_Set_Sidetone(self, freq_hz, level):
+        self._ck(self.lib.SLB_DSP_Set_Sidetone(self.h, int(freq_hz), float(level)), "DSP_Set_Sidetone")
+
+    def DSP_Key(self, key_down=None):
+        """key_down: per-channel booleans (None = all keys up)."""
+        if key_down is None:
+            self._ck(self.lib.SLB_DSP_Key(self.h, None), "DSP_Key"); return
+        k = np.ascontiguousarray(np.asarray(key_down).astype(np.uint8)); assert k.size == self.channels
+        self._ck(self.lib.SLB_DSP_Key(self.h, k.ctypes.data), "DSP_Key")
+
+    def direction(self):
+        return self.lib.slb_get_direction(self.h)
+
     def feeder_run(self, adc=None, usb_out=None):
         """Replay `ticks` firmware milliseconds in one call (slb_feeder_run): adc / usb_out int16 [channels][ticks*block][2]
         host streams (either may be None). Returns (usb_in, dac) of the same shape (None for a skipped direction)."""

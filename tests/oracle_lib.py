@@ -133,6 +133,12 @@ class Oracle:
     def biquad_df1_q15(self, c, ns, ps, st, x, block): return self._bq("biquad_df1_q15", np.int16, i16p, c, ns, st, x, block, len(x), (ps,))
     def biquad_df1_q31(self, c, ns, ps, st, x, block): return self._bq("biquad_df1_q31", np.int32, i32p, c, ns, st, x, block, len(x), (ps,))
 
+    def sidetone_mix(self, lr, counter, key_down, freq_hz, fs, level):
+        """One DAC read's worth of frames int16 [frames][2]; returns (mixed copy, new counter)."""
+        d = np.ascontiguousarray(lr, np.int16).copy(); cnt = C.c_uint32(counter)
+        self._f("sidetone_mix", [i16p, u32, C.POINTER(C.c_uint32), C.c_int, u32, u32, C.c_float])(d.reshape(-1), d.shape[0], C.byref(cnt), int(key_down), freq_hz, fs, level)
+        return d, cnt.value
+
     def lms_norm_f32(self, coeffs, mu, st, en_x0, x, ref, block):
         """arm_lms_norm_f32: returns (out, err, coeffs, state, en_x0) — copies, the inputs are not modified."""
         c = np.ascontiguousarray(coeffs, np.float32).copy(); s_ = np.ascontiguousarray(st, np.float32).copy()

@@ -200,3 +200,72 @@ def test_firmware_names_i2s_callbacks_and_audiocmd():
         got = np.zeros(96, np.int16); lib.AUDIO_AudioCmd_FS(got.ctypes.data, 192, 4)
         assert np.array_equal(got, in_read(192)), t
     assert lib.slb_dropin_status() == 0
+
+
+@pytest.mark.parametrize("fs", [48000, 96000])
+def test_cw_sidetone_at_the_firmware_hook(best_oracle, rng, fs):
+    """'mix CW tone to speaker signal here' (dsp_if.c:218): DSP_Out_Buff_Read adds the side-tone to L and R of every keyed channel.
+    Against the oracle composition (arm_sin_f32 -> arm_scale_f32 -> arm_float_to_q15 -> arm_add_q15) applied to the oracle ring's
+    output, bit for bit, through key-down / key-up sequences, with samples near the rails (the add saturates)."""
+    Cn = 6; B = fs // 1000; hw = 2 * B
+    d = slb.DspIf(Cn, fs=fs, chain=slb.CHAIN_PASS); d.DSP_Init()
+    d.DSP_Set_Sidetone(700, 0.3)
+    rings = [oracle_ring(fs)[1] for _ in range(Cn)]
+    cnt = [0] * Cn
+    keys = np.zeros(Cn, bool)
+    for step in range(60):
+        if step % 7 == 0:
+            keys = rng.random(Cn) < 0.5
+            if step == 28: keys[:] = False
+            d.DSP_Key(keys if keys.any() else None)
+        blk = rng.integers(-32768, 32768, (Cn, hw)).astype(np.int16)
+        d.DSP_Out_Buff_Write(blk, hw * 2)
+        got = d.DSP_Out_Buff_Read(hw)
+        for c in range(Cn):
+            rings[c][2](blk[c])
+            e = rings[c][3](hw).reshape(B, 2)
+            e, cnt[c] = best_oracle.sidetone_mix(e, cnt[c], bool(keys[c]), 700, fs, 0.3)
+            assert np.array_equal(got[c].reshape(B, 2), e), (step, c)
+    # the feeder mixes the same tone over a whole run
+    a = slb.DspIf(Cn, fs=fs, chain=slb.CHAIN_PASS); b = slb.DspIf(Cn, fs=fs, chain=slb.CHAIN_PASS)
+    ticks = 16
+    pc = rng.integers(-20000, 20000, (Cn, ticks * B, 2)).astype(np.int16)
+    keys = np.array([1, 0, 1, 1, 0, 0], bool)
+    for x in (a, b):
+        x.DSP_Set_Sidetone(650, 0.2); x.DSP_Key(keys)
+    exp = []
+    for t in range(ticks):
+        exp.append(a.DSP_Out_Buff_Read(2 * B)); a.DSP_Out_Buff_Write(pc[:, t * B:(t + 1) * B].reshape(Cn, -1))
+    _, dac = b.feeder_run(None, pc)
+    assert np.array_equal(dac, np.stack(exp, 1).reshape(Cn, -1, 2))
+    assert np.array_equal(a.DSP_Out_Buff_Read(2 * B), b.DSP_Out_Buff_Read(2 * B))
+
+
+@pytest.mark.parametrize("chain", [slb.CHAIN_RX_SSB_F32, slb.CHAIN_RX_SSB_Q15])
+def test_rx_tx_switch_flushes_rings_and_chain_state(chain):
+    """DSP_Set_TX / DSP_Set_RX as ptt_set_tx / ptt_set_rx use them (rxtx_if.c:255-317): a change of direction flushes the samples of
+    both rings (pointers keep running, as DSP_Out_Buff_Mute, dsp_if.c:188-195) and the chain's carried state — after the switch the
+    context behaves like a fresh one that has seen the same number of ticks; repeating the current direction changes nothing."""
+    Cn, B = 4, 48
+    x = slb.synth_iq(Cn, 64 * B)
+    a = slb.DspIf(Cn, chain=chain); a.DSP_Init()
+    fresh = slb.DspIf(Cn, chain=chain); fresh.DSP_Init()
+    zeros = np.zeros((Cn, 2 * B), np.int16)
+    for t in range(24):                                               # 24 ticks of signal on `a`, 24 ticks of silence on `fresh`: same pointers
+        a.DSP_In_Buff_Write(x[:, t * B:(t + 1) * B].reshape(Cn, -1)); a.DSP_In_Buff_Read(4 * B)
+        a.DSP_Out_Buff_Write(x[:, t * B:(t + 1) * B].reshape(Cn, -1)); a.DSP_Out_Buff_Read(2 * B)
+        fresh.DSP_In_Buff_Write(zeros); fresh.DSP_In_Buff_Read(4 * B)
+        fresh.DSP_Out_Buff_Write(zeros); fresh.DSP_Out_Buff_Read(2 * B)
+    assert a.direction() == 0
+    a.DSP_Set_RX()                                                    # no change of direction: nothing is flushed
+    assert np.any(a.ring_iq(0)[0] != 0)
+    a.DSP_Set_TX(); fresh.DSP_Set_TX()
+    assert a.direction() == 1
+    assert a.ring_ptrs(0) == fresh.ring_ptrs(0) and a.ring_ptrs(1) == fresh.ring_ptrs(1)
+    for w in (0, 1):
+        assert not np.any(a.ring_iq(w)[0]) and not np.any(a.ring_iq(w)[1])
+    for t in range(24, 64):                                           # from here on the two contexts are indistinguishable
+        for d in (a, fresh):
+            d.DSP_In_Buff_Write(x[:, t * B:(t + 1) * B].reshape(Cn, -1)); d.DSP_Out_Buff_Write(x[:, t * B:(t + 1) * B].reshape(Cn, -1))
+        assert np.array_equal(a.DSP_In_Buff_Read(4 * B), fresh.DSP_In_Buff_Read(4 * B)), t
+        assert np.array_equal(a.DSP_Out_Buff_Read(2 * B), fresh.DSP_Out_Buff_Read(2 * B)), t
