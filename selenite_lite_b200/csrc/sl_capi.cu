@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -59,6 +60,8 @@ struct slb_ctx
   RingPtrs ring_in, ring_out;
   // per-channel cadence (SLB_DSP_*_Ch): once switched on, the pointers of every channel live on the device
   bool ring_pc = false; uint32_t *d_rptr[2] = { nullptr, nullptr }; uint8_t *d_active = nullptr;
+  // ... and with a super-block chain behind the RX ring every channel fills its own super-block (frames accumulated so far)
+  std::vector<uint32_t> acc_fill_pc; uint32_t *d_acc_off = nullptr;
   int16_t *d_ring[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };   // [which][i|q]
   int16_t *d_blk = nullptr; size_t blk_frames = 0;                           // [C][blk_frames][2]
   // chain at the 1 ms cadence: accumulate `hop` frames, process, feed the ring from the previous super-block
@@ -259,6 +262,7 @@ void slb_destroy (slb_ctx *ctx)
   for (auto &kv : ctx->tc_lists) cudaFree (kv.second.d);
   for (int p = 0; p < 2; p++) { cudaFree (ctx->d_ovl[p]); cudaFree (ctx->d_proc[p]); }
   cudaFree (ctx->d_state); cudaFree (ctx->d_flag);
+  cudaFree (ctx->d_acc_off);
   cudaFree (ctx->d_tone); cudaFree (ctx->d_sin513); cudaFree (ctx->d_key); cudaFree (ctx->d_tone_cnt);
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
   cudaFree (ctx->d_blk); cudaFree (ctx->d_acc); cudaFree (ctx->d_scratch);
@@ -695,8 +699,30 @@ static int ring_pc_enable (slb_ctx *ctx)
     CK (ctx, cudaMemcpyAsync (ctx->d_rptr[w], h.data (), h.size () * sizeof (uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK (ctx, cudaStreamSynchronize (ctx->stream));
   }
+  if (is_ssb_chain (ctx->cfg.chain))
+  {
+    // from here on d_proc[0] alone holds every channel's previously processed super-block (a channel's row is rewritten only after
+    // its eight blocks have gone into the ring), and every channel counts its own accumulated frames
+    const uint32_t hop = ctx->rx.hop;
+    if (ctx->proc_cur == 1) { CK (ctx, cudaMemcpyAsync (ctx->d_proc[0], ctx->d_proc[1], (size_t) C * hop * 4, cudaMemcpyDeviceToDevice, ctx->stream)); ctx->proc_cur = 0; }
+    if (!ctx->d_acc_off) CK (ctx, cudaMalloc (&ctx->d_acc_off, (size_t) C * 4));
+    ctx->acc_fill_pc.assign (C, 0u);
+    CK (ctx, cudaStreamSynchronize (ctx->stream));
+  }
   ctx->ring_pc = true;
   return SLB_OK;
+}
+// maximal runs [first, first + count) of channels for which pred holds
+static std::vector<std::pair<uint32_t, uint32_t>> channel_runs (uint32_t C, const std::function<bool (uint32_t)> &pred)
+{
+  std::vector<std::pair<uint32_t, uint32_t>> r;
+  for (uint32_t c = 0; c < C;)
+  {
+    if (!pred (c)) { c++; continue; }
+    uint32_t e = c; while (e < C && pred (e)) e++;
+    r.emplace_back (c, e - c); c = e;
+  }
+  return r;
 }
 // device copy of the activity mask of this call (nullptr = all channels)
 static int ring_pc_mask (slb_ctx *ctx, const uint8_t *active, const uint8_t **d_out)
@@ -720,16 +746,71 @@ static int ring_write_common (slb_ctx *ctx, int which, const void *pbuf, uint32_
   const bool chain = (which == 0 && is_ssb_chain (ctx->cfg.chain));
   if (per_channel || ctx->ring_pc)
   {
-    if (which == 0 && ctx->cfg.chain != SLB_CHAIN_PASS)
-      return fail (ctx, SLB_ERR_UNSUPPORTED, "per-channel cadence with a chain behind the RX ring is not built: use the PASS chain or the bulk calls");
+    if (which == 0 && !ctx->ring_pc && is_ssb_chain (ctx->cfg.chain) && ctx->acc_fill != 0)
+      return fail (ctx, SLB_ERR_STATE, "switch to per-channel cadence on a super-block boundary");
     int rc = ring_pc_enable (ctx); if (rc) return rc;
     const uint8_t *d_act = nullptr;
     rc = ring_pc_mask (ctx, active, &d_act); if (rc) return rc;
     rc = ensure_blk (ctx, frames); if (rc) return rc;
     CK (ctx, cudaMemcpyAsync (ctx->d_blk, pbuf, (size_t) C * frames * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK (ctx, launch_ring_plan (ctx->d_rptr[which], d_act, C, R, true, which != 0, frames, ctx->stream));
-    CK (ctx, launch_ring_write_pc (ctx->d_blk, frames, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, ctx->d_rptr[which], frames, ctx->stream));
-    ctx->launches += 2;
+    auto is_on = [&] (uint32_t c) { return !active || active[c] != 0; };
+    if (which == 0 && ctx->q15)
+    {
+      // the integer chain demodulates a block in the call that delivers it (dsp_if.c:286-289): the channels that fired run through the
+      // kernel (one launch per run of neighbours), the others carry their state over unchanged
+      if (frames % ctx->geo.block_frames != 0) return fail (ctx, SLB_ERR_ARG, "with the RX-SSB-q15 chain the block must be a whole number of 48-frame firmware blocks");
+      for (auto &r : channel_runs (C, is_on))
+      {
+        rc = rxq15_launch (ctx, ctx->q15, ctx->d_blk + (size_t) r.first * frames * 2, ctx->d_proc[0] + (size_t) r.first * frames * 2, r.first, r.second, frames, ctx->sm_count, ctx->stream, false);
+        if (rc) return rc;
+      }
+      for (auto &r : channel_runs (C, [&] (uint32_t c) { return !is_on (c); })) CK (ctx, rxq15_carry_idle (ctx->q15, r.first, r.second, ctx->stream));
+      rxq15_advance (ctx->q15);
+      CK (ctx, launch_ring_write_pc (ctx->d_proc[0], frames, ctx->d_ring[0][0], ctx->d_ring[0][1], C, R, ctx->d_rptr[0], frames, ctx->stream));
+      ctx->launches += 2;
+    }
+    else if (which == 0 && is_ssb_chain (ctx->cfg.chain))
+    {
+      // dsp_if.c:252-300 per channel with the demodulator in front: the block joins the channel's own super-block, the ring takes the
+      // block at the same position of the channel's previously processed super-block (384 frames of latency, as under the shared
+      // cadence), and the channels whose super-block is now complete run through the fused chain
+      const uint32_t hop = ctx->rx.hop;
+      if (hop % frames != 0) return fail (ctx, SLB_ERR_ARG, "with a chain the block size must divide the hop (384)");
+      for (uint32_t c = 0; c < C; c++) if (is_on (c) && ctx->acc_fill_pc[c] % frames != 0) return fail (ctx, SLB_ERR_ARG, "with a chain the block size must divide the hop (384)");
+      CK (ctx, cudaMemcpyAsync (ctx->d_acc_off, ctx->acc_fill_pc.data (), (size_t) C * 4, cudaMemcpyHostToDevice, ctx->stream));
+      CK (ctx, launch_acc_store_pc (ctx->d_acc, hop, ctx->d_blk, C, frames, ctx->d_acc_off, ctx->d_rptr[0], ctx->stream));
+      CK (ctx, launch_ring_write_pc (ctx->d_proc[0], hop, ctx->d_ring[0][0], ctx->d_ring[0][1], C, R, ctx->d_rptr[0], frames, ctx->stream, ctx->d_acc_off));
+      ctx->launches += 3;
+      CK (ctx, cudaStreamSynchronize (ctx->stream));                       // (acc_fill_pc is host memory the copy above reads)
+      for (uint32_t c = 0; c < C; c++) if (is_on (c)) ctx->acc_fill_pc[c] += frames;
+      auto ready = [&] (uint32_t c) { return ctx->acc_fill_pc[c] == hop; };
+      const auto runs = channel_runs (C, ready);
+      if (!runs.empty ())
+      {
+        if (ctx->tc_lists.size () > 64) { for (auto &kv : ctx->tc_lists) cudaFree (kv.second.d); ctx->tc_lists.clear (); }   // (lists are cached per channel range)
+        const uint32_t ovl = ctx->rx.fft_len - hop;
+        for (auto &r : runs)
+        {
+          rc = run_rx_kernel (ctx, ctx->d_acc + (size_t) r.first * hop * 2, ctx->d_proc[0] + (size_t) r.first * hop * 2, r.first, r.second, hop, nullptr, nullptr, ctx->stream);
+          if (rc) return rc;
+        }
+        // the other channels sit this launch out: their raw tail and hand-over counter move on unchanged
+        for (auto &r : channel_runs (C, [&] (uint32_t c) { return !ready (c); }))
+        {
+          CK (ctx, cudaMemcpyAsync (ctx->d_ovl[ctx->ovl_parity ^ 1] + (size_t) r.first * ovl * 2, ctx->d_ovl[ctx->ovl_parity] + (size_t) r.first * ovl * 2, (size_t) r.second * ovl * 4,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+          CK (ctx, launch_fill_u32 (ctx->d_flag + r.first, r.second, ctx->flag_base + rx_ssb_f32_tiles (hop), ctx->stream));
+        }
+        rx_advance (ctx, hop);
+        for (uint32_t c = 0; c < C; c++) if (ready (c)) ctx->acc_fill_pc[c] = 0;
+      }
+    }
+    else
+    {
+      CK (ctx, launch_ring_write_pc (ctx->d_blk, frames, ctx->d_ring[which][0], ctx->d_ring[which][1], C, R, ctx->d_rptr[which], frames, ctx->stream));
+      ctx->launches += 2;
+    }
     CK (ctx, cudaStreamSynchronize (ctx->stream));
     return SLB_OK;
   }
@@ -1293,6 +1374,9 @@ int slb_state_save (slb_ctx *ctx, void *buf, size_t bytes)
   {
     if (ctx->ring_pc) CK (ctx, cudaMemcpy (p, ctx->d_rptr[w], C * 4 * sizeof (uint32_t), cudaMemcpyDeviceToHost));
     else std::memset (p, 0, C * 4 * sizeof (uint32_t));
+    // (the 4th word of a pointer record is per-call scratch: in the checkpoint it carries the channel's own super-block fill level)
+    if (w == 0 && ctx->ring_pc && ctx->acc_fill_pc.size () == C)
+      for (size_t c = 0; c < C; c++) std::memcpy (p + (4 * c + 3) * sizeof (uint32_t), &ctx->acc_fill_pc[c], sizeof (uint32_t));
     p += C * 4 * sizeof (uint32_t);
   }
   return SLB_OK;
@@ -1324,7 +1408,13 @@ int slb_state_load (slb_ctx *ctx, const void *buf, size_t bytes)
   if (h.ring_pc)
   {
     int rc = ring_pc_enable (ctx); if (rc) return rc;
-    for (int w = 0; w < 2; w++) { CK (ctx, cudaMemcpy (ctx->d_rptr[w], p, C * 4 * sizeof (uint32_t), cudaMemcpyHostToDevice)); p += C * 4 * sizeof (uint32_t); }
+    for (int w = 0; w < 2; w++)
+    {
+      CK (ctx, cudaMemcpy (ctx->d_rptr[w], p, C * 4 * sizeof (uint32_t), cudaMemcpyHostToDevice));
+      if (w == 0 && ctx->acc_fill_pc.size () == C)
+        for (size_t c = 0; c < C; c++) std::memcpy (&ctx->acc_fill_pc[c], p + (4 * c + 3) * sizeof (uint32_t), sizeof (uint32_t));
+      p += C * 4 * sizeof (uint32_t);
+    }
   }
   // per-channel tile counters restart from zero on this context
   CK (ctx, cudaMemset (ctx->d_flag, 0, C * sizeof (unsigned)));

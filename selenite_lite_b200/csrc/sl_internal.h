@@ -74,7 +74,10 @@ int launch_ring_replay (bool write_first, const int16_t *src_a, uint32_t stride_
 int launch_ring_plan (uint32_t *d_ptr, const uint8_t *d_active, uint32_t channels, uint32_t ring_frames, bool is_write, bool is_out,
                       uint32_t frames, void *stream);
 int launch_ring_write_pc (const int16_t *d_blocks, uint32_t block_stride_frames, int16_t *d_ring_i, int16_t *d_ring_q, uint32_t channels,
-                          uint32_t ring_frames, const uint32_t *d_ptr, uint32_t frames, void *stream);
+                          uint32_t ring_frames, const uint32_t *d_ptr, uint32_t frames, void *stream, const uint32_t *d_src_off = nullptr);
+int launch_acc_store_pc (int16_t *d_acc, uint32_t acc_stride_frames, const int16_t *d_blocks, uint32_t channels, uint32_t frames, const uint32_t *d_off,
+                         const uint32_t *d_ptr, void *stream);
+int launch_fill_u32 (uint32_t *d, uint32_t n, uint32_t v, void *stream);
 int launch_ring_read_pc (int16_t *d_blocks, const int16_t *d_ring_i, const int16_t *d_ring_q, uint32_t channels, uint32_t ring_frames,
                          const uint32_t *d_ptr, uint32_t frames, void *stream);
 
@@ -200,6 +203,7 @@ int rxq15_set_sideband (slb_ctx *ctx, RxQ15State *st, uint32_t ch0, uint32_t n, 
 int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_out, uint32_t ch0, uint32_t nch, uint32_t frames,
                   int sm_count, void *stream, bool with_debug);
 void rxq15_advance (RxQ15State *st);
+int rxq15_carry_idle (RxQ15State *st, uint32_t ch0, uint32_t nch, void *stream);
 size_t rxq15_state_bytes (const RxQ15State *st);
 int rxq15_state_save (RxQ15State *st, char *dst);
 int rxq15_state_load (RxQ15State *st, const char *src);

@@ -75,13 +75,14 @@ __global__ void ring_plan_kernel (uint32_t *__restrict__ ptr /* [C][4] */, const
 }
 
 __global__ void ring_write_pc_kernel (const int16_t *__restrict__ blocks, uint32_t block_stride_frames, int16_t *__restrict__ ring_i,
-                                      int16_t *__restrict__ ring_q, uint32_t ring_frames, const uint32_t *__restrict__ ptr, uint32_t frames)
+                                      int16_t *__restrict__ ring_q, uint32_t ring_frames, const uint32_t *__restrict__ ptr, uint32_t frames,
+                                      const uint32_t *__restrict__ src_off)
 {
   const uint32_t c = blockIdx.y;
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t wr0 = ptr[4 * (size_t) c + 3];
   if (k > frames || wr0 == kRingSkip) return;
-  const uint32_t src = (k < frames) ? k : frames - 1u;
+  const uint32_t src = ((k < frames) ? k : frames - 1u) + (src_off ? src_off[c] : 0u);     // src_off: where this channel's block starts in its source row
   const uint32_t iq = reinterpret_cast<const uint32_t *> (blocks)[(size_t) c * block_stride_frames + src];
   const uint32_t slot = (wr0 + k) % ring_frames;
   ring_i[(size_t) c * ring_frames + slot] = (int16_t) (iq & 0xFFFFu);
@@ -111,10 +112,35 @@ int launch_ring_plan (uint32_t *d_ptr, const uint8_t *d_active, uint32_t channel
   return (int) cudaGetLastError ();
 }
 int launch_ring_write_pc (const int16_t *d_blocks, uint32_t stride, int16_t *ri, int16_t *rq, uint32_t channels, uint32_t ring_frames,
-                          const uint32_t *d_ptr, uint32_t frames, void *stream)
+                          const uint32_t *d_ptr, uint32_t frames, void *stream, const uint32_t *d_src_off)
 {
   dim3 grid ((frames + 1 + 127) / 128, channels);
-  ring_write_pc_kernel<<<grid, 128, 0, (cudaStream_t) stream>>> (d_blocks, stride, ri, rq, ring_frames, d_ptr, frames);
+  ring_write_pc_kernel<<<grid, 128, 0, (cudaStream_t) stream>>> (d_blocks, stride, ri, rq, ring_frames, d_ptr, frames, d_src_off);
+  return (int) cudaGetLastError ();
+}
+
+// per-channel cadence with a super-block chain behind the RX ring: an active channel's block joins ITS super-block at ITS fill level
+namespace {
+__global__ void acc_store_pc_kernel (uint32_t *__restrict__ acc, uint32_t acc_stride_frames, const uint32_t *__restrict__ blocks, uint32_t frames,
+                                     const uint32_t *__restrict__ off, const uint32_t *__restrict__ ptr)
+{
+  const uint32_t c = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= frames || ptr[4 * (size_t) c + 3] == kRingSkip) return;
+  acc[(size_t) c * acc_stride_frames + off[c] + k] = blocks[(size_t) c * frames + k];
+}
+__global__ void fill_u32_kernel (uint32_t *p, uint32_t n, uint32_t v) { const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+}  // namespace
+int launch_acc_store_pc (int16_t *d_acc, uint32_t acc_stride_frames, const int16_t *d_blocks, uint32_t channels, uint32_t frames, const uint32_t *d_off,
+                         const uint32_t *d_ptr, void *stream)
+{
+  dim3 grid ((frames + 127) / 128, channels);
+  acc_store_pc_kernel<<<grid, 128, 0, (cudaStream_t) stream>>> (reinterpret_cast<uint32_t *> (d_acc), acc_stride_frames, reinterpret_cast<const uint32_t *> (d_blocks), frames, d_off, d_ptr);
+  return (int) cudaGetLastError ();
+}
+int launch_fill_u32 (uint32_t *d, uint32_t n, uint32_t v, void *stream)
+{
+  if (n == 0) return 0;
+  fill_u32_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t) stream>>> (d, n, v);
   return (int) cudaGetLastError ();
 }
 int launch_ring_read_pc (int16_t *d_blocks, const int16_t *ri, const int16_t *rq, uint32_t channels, uint32_t ring_frames,

@@ -481,6 +481,16 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
   return SLB_OK;
 }
 void rxq15_advance (RxQ15State *st) { st->parity ^= 1; }
+// per-channel cadence: channels [ch0, ch0 + nch) sat this call out — their carried state moves to the buffers the next call reads
+int rxq15_carry_idle (RxQ15State *st, uint32_t ch0, uint32_t nch, void *stream)
+{
+  cudaError_t e = cudaMemcpyAsync (st->d_tail[st->parity ^ 1] + (size_t) ch0 * kTaps, st->d_tail[st->parity] + (size_t) ch0 * kTaps, (size_t) nch * kTaps * sizeof (*st->d_tail[0]),
+                                   cudaMemcpyDeviceToDevice, (cudaStream_t) stream);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync (st->d_peaks[st->parity ^ 1] + (size_t) ch0 * kWin, st->d_peaks[st->parity] + (size_t) ch0 * kWin, (size_t) nch * kWin * sizeof (*st->d_peaks[0]),
+                         cudaMemcpyDeviceToDevice, (cudaStream_t) stream);
+  return (int) e;
+}
 
 size_t rxq15_state_bytes (const RxQ15State *st) { return (size_t) st->channels * (kTaps * 4 + kWin * 2 + 1); }
 int rxq15_state_save (RxQ15State *st, char *dst)

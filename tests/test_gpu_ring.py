@@ -269,3 +269,40 @@ def test_rx_tx_switch_flushes_rings_and_chain_state(chain):
             d.DSP_In_Buff_Write(x[:, t * B:(t + 1) * B].reshape(Cn, -1)); d.DSP_Out_Buff_Write(x[:, t * B:(t + 1) * B].reshape(Cn, -1))
         assert np.array_equal(a.DSP_In_Buff_Read(4 * B), fresh.DSP_In_Buff_Read(4 * B)), t
         assert np.array_equal(a.DSP_Out_Buff_Read(2 * B), fresh.DSP_Out_Buff_Read(2 * B)), t
+
+
+@pytest.mark.parametrize("chain", [slb.CHAIN_RX_SSB_Q15, slb.CHAIN_RX_SSB_F32, slb.CHAIN_TX_SSB_F32])
+def test_chain_behind_the_ring_under_per_channel_cadence(chain):
+    """dsp_if.c:252-300 per channel with a demodulator in front (SURVEY §8f.2 + §8f.3): channels whose producers and consumers tick at
+    different rates each follow their own ring AND their own chain state / super-block fill. Every channel of the batched context
+    must equal, bit for bit, a one-channel context that sees only that channel's events (that path is held to the oracle by
+    test_chain_behind_the_1ms_cadence); a checkpoint taken while the channels are at different fill levels carries on the same way."""
+    C, ticks, B = 7, 150, 48
+    modes = [slb.MODE_USB, slb.MODE_LSB, slb.MODE_USB, slb.MODE_CW, slb.MODE_USB, slb.MODE_LSB, slb.MODE_USB]
+    if chain == slb.CHAIN_RX_SSB_F32:
+        modes[4] = slb.MODE_AM; modes[2] = slb.MODE_FM                # the FFT kernel and the complex-detector kernel serve their channels next to the SSB ones
+    x = slb.synth_iq(C, ticks * B)
+    d = slb.DspIf(C, chain=chain); single = [slb.DspIf(1, chain=chain) for _ in range(C)]
+    for c in range(C):
+        d.DSP_Set_Mode(modes[c], channel=c); single[c].DSP_Set_Mode(modes[c])
+    rng = np.random.Generator(np.random.PCG64(5))
+    def fires(c, t):
+        w = not ((c == 1 and t % 13 == 12) or (c == 3 and t % 5 == 4) or (c == 5 and rng.random() < 0.1))
+        r = not ((c == 2 and t % 17 == 16) or (c == 4 and t % 7 == 6) or (c == 5 and rng.random() < 0.1))
+        return w, r
+    pos = [0] * C                                                       # every producer walks its own stream
+    for t in range(ticks):
+        if t == 70:                                                     # checkpoint in mid-stream into a fresh context
+            snap = d.state_save(); d = slb.DspIf(C, chain=chain); d.state_load(snap)
+        act = np.array([fires(c, t) for c in range(C)])
+        blk = np.zeros((C, 2 * B), np.int16)
+        for c in range(C):
+            if act[c, 0]:
+                blk[c] = x[c, pos[c]:pos[c] + B].reshape(-1); pos[c] += B
+        d.DSP_In_Buff_Write_Ch(blk, act[:, 0].astype(np.uint8))
+        got = d.DSP_In_Buff_Read_Ch(4 * B, act[:, 1].astype(np.uint8))
+        for c in range(C):
+            if act[c, 0]: single[c].DSP_In_Buff_Write(blk[c:c + 1])
+            exp = single[c].DSP_In_Buff_Read(4 * B)[0] if act[c, 1] else np.zeros(2 * B, np.int16)
+            assert np.array_equal(got[c], exp), (t, c)
+            assert d.ring_ptrs_channel(c, 0) == single[c].ring_ptrs(0), (t, c)
