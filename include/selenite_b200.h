@@ -287,6 +287,22 @@ typedef struct
   int16_t *dac;             /* TX out: what the I2S TX half carries to the codec DAC */
 } slb_feeder_io;
 int slb_feeder_run (slb_ctx *ctx, const slb_feeder_io *io, uint32_t ticks);
+
+/* ---- LIVE feeder: the same four calls per tick, as a pipeline over chunks of `ticks_per_chunk` ms ----
+ * What replaces the double-buffered I2S DMA (dsp_if.c:50-67: one half is processed while the other fills) and the USB isochronous
+ * endpoints (usbd_audio.c:707-745, :844-879) on a host: slb_live_push() takes the chunk that has just filled (host buffers, copied
+ * into pinned staging), and returns at once; the chunk's host->device copy, its kernels (chain + ring replay) and its device->host
+ * copy run on three streams, so chunk n is copied in while chunk n-1 computes and chunk n-2 is copied out. slb_live_pop() hands
+ * out the oldest finished chunk (blocks until it is there; SLB_ERR_STATE when nothing is in flight). At most `depth` chunks
+ * (2..8) are in flight; push with all slots taken returns SLB_ERR_STATE (pop first). Results are bit-identical to slb_feeder_run
+ * and to the per-tick calls. latency_us (may be NULL) receives the time from the chunk's push to the moment its results were in
+ * host memory. Directions as in slb_feeder_io: give adc to get usb_in, usb_out to get dac; which ones is fixed at open time. */
+typedef struct slb_live slb_live;
+int slb_live_open (slb_ctx *ctx, uint32_t ticks_per_chunk, uint32_t depth, int with_rx, int with_tx, slb_live **out);
+int slb_live_push (slb_live *lv, const int16_t *adc, const int16_t *usb_out);
+int slb_live_pop (slb_live *lv, int16_t *usb_in, int16_t *dac, float *latency_us);
+int slb_live_in_flight (const slb_live *lv);
+void slb_live_close (slb_live *lv);
 /* USBD_AUDIO_ItfTypeDef.AudioCmd, batched (usbd_audio_if.c:179-202): cmd = 1 START (no-op), 2 PLAY -> DSP_Out_Buff_Write,
  * 3 STOP -> DSP_Out_Buff_Mute, 4 RECORD -> DSP_In_Buff_Read; pbuf is [channels][size] host memory, size in bytes */
 int SLB_AUDIO_AudioCmd (slb_ctx *ctx, uint8_t *pbuf, uint32_t size, uint8_t cmd);

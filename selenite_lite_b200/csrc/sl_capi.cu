@@ -2,6 +2,7 @@
 // same argument meaning, ring index arithmetic identical; the sample movement and the inserted chain run on the GPU.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1003,6 +1004,173 @@ int slb_feeder_run (slb_ctx *ctx, const slb_feeder_io *io, uint32_t ticks)
     CK (ctx, cudaMemcpyAsync (io->usb_in, d_out, bytes, cudaMemcpyDeviceToHost, st));
     CK (ctx, cudaStreamSynchronize (st));
   }
+  return SLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Live feeder: chunks of ticks through a three-stream pipeline (H2D | chain + ring replay | D2H) with pinned staging
+// ------------------------------------------------------------------------------------------------------------------
+struct slb_live
+{
+  slb_ctx *ctx = nullptr;
+  uint32_t ticks = 0, depth = 0; bool rx = false, tx = false;
+  size_t frames = 0, bytes = 0;
+  struct Slot
+  {
+    int16_t *h_adc = nullptr, *h_usb_out = nullptr, *h_usb_in = nullptr, *h_dac = nullptr;   // pinned
+    uint32_t *h_plan = nullptr;                                                               // pinned, [2 rings][ticks][2]
+    int16_t *d_adc = nullptr, *d_usb_out = nullptr, *d_prc = nullptr, *d_usb_in = nullptr, *d_dac = nullptr; uint32_t *d_plan = nullptr;
+    cudaEvent_t in_done = nullptr, work_done = nullptr, out_done = nullptr;
+    std::chrono::steady_clock::time_point pushed;
+  };
+  std::vector<Slot> slots;
+  cudaStream_t s_in = nullptr, s_work = nullptr, s_out = nullptr;
+  uint64_t n_pushed = 0, n_popped = 0;
+};
+
+int slb_live_open (slb_ctx *ctx, uint32_t ticks_per_chunk, uint32_t depth, int with_rx, int with_tx, slb_live **out)
+{
+  if (!ctx || !out || ticks_per_chunk == 0 || depth < 2 || depth > 8 || (!with_rx && !with_tx)) return SLB_ERR_ARG;
+  *out = nullptr;
+  if (ctx->chan) return fail (ctx, SLB_ERR_UNSUPPORTED, "the channelizer chain has no firmware ring (bulk calls only)");
+  if (ctx->ring_pc) return fail (ctx, SLB_ERR_STATE, "the feeder replays one shared cadence; per-channel cadence is on");
+  const uint32_t B = ctx->geo.block_frames, per_hop = ctx->rx.hop / B;
+  if (with_rx && is_ssb_chain (ctx->cfg.chain) && (ticks_per_chunk % per_hop != 0 || ctx->acc_fill != 0))
+    return fail (ctx, SLB_ERR_ARG, "with an FFT chain the feeder moves whole 384-frame super-blocks (ticks % 8 == 0)");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  slb_live *lv = new slb_live ();
+  lv->ctx = ctx; lv->ticks = ticks_per_chunk; lv->depth = depth; lv->rx = with_rx != 0; lv->tx = with_tx != 0;
+  lv->frames = (size_t) ticks_per_chunk * B; lv->bytes = (size_t) ctx->cfg.channels * lv->frames * 4;
+  lv->slots.resize (depth);
+  bool ok = cudaStreamCreateWithFlags (&lv->s_in, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags (&lv->s_work, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags (&lv->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  const size_t plan_bytes = (size_t) ticks_per_chunk * 2 * 2 * sizeof (uint32_t);
+  for (auto &sl : lv->slots)
+  {
+    if (!ok) break;
+    if (lv->rx) ok = ok && cudaHostAlloc (&sl.h_adc, lv->bytes, cudaHostAllocDefault) == cudaSuccess && cudaHostAlloc (&sl.h_usb_in, lv->bytes, cudaHostAllocDefault) == cudaSuccess &&
+                     cudaMalloc (&sl.d_adc, lv->bytes) == cudaSuccess && cudaMalloc (&sl.d_prc, lv->bytes) == cudaSuccess && cudaMalloc (&sl.d_usb_in, lv->bytes) == cudaSuccess;
+    if (lv->tx) ok = ok && cudaHostAlloc (&sl.h_usb_out, lv->bytes, cudaHostAllocDefault) == cudaSuccess && cudaHostAlloc (&sl.h_dac, lv->bytes, cudaHostAllocDefault) == cudaSuccess &&
+                     cudaMalloc (&sl.d_usb_out, lv->bytes) == cudaSuccess && cudaMalloc (&sl.d_dac, lv->bytes) == cudaSuccess;
+    ok = ok && cudaHostAlloc (&sl.h_plan, plan_bytes, cudaHostAllocDefault) == cudaSuccess && cudaMalloc (&sl.d_plan, plan_bytes) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags (&sl.in_done, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags (&sl.work_done, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags (&sl.out_done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) { slb_live_close (lv); return fail (ctx, SLB_ERR_CUDA, "live feeder: allocation failed"); }
+  CK (ctx, cudaStreamSynchronize (ctx->stream));                  // whatever the per-call API left running is ordered before the first chunk
+  *out = lv;
+  return SLB_OK;
+}
+
+void slb_live_close (slb_live *lv)
+{
+  if (!lv) return;
+  cudaSetDevice (lv->ctx->cfg.device);
+  if (lv->s_in) cudaStreamSynchronize (lv->s_in);
+  if (lv->s_work) cudaStreamSynchronize (lv->s_work);
+  if (lv->s_out) cudaStreamSynchronize (lv->s_out);
+  for (auto &sl : lv->slots)
+  {
+    cudaFreeHost (sl.h_adc); cudaFreeHost (sl.h_usb_out); cudaFreeHost (sl.h_usb_in); cudaFreeHost (sl.h_dac); cudaFreeHost (sl.h_plan);
+    cudaFree (sl.d_adc); cudaFree (sl.d_usb_out); cudaFree (sl.d_prc); cudaFree (sl.d_usb_in); cudaFree (sl.d_dac); cudaFree (sl.d_plan);
+    if (sl.in_done) cudaEventDestroy (sl.in_done);
+    if (sl.work_done) cudaEventDestroy (sl.work_done);
+    if (sl.out_done) cudaEventDestroy (sl.out_done);
+  }
+  if (lv->s_in) cudaStreamDestroy (lv->s_in);
+  if (lv->s_work) cudaStreamDestroy (lv->s_work);
+  if (lv->s_out) cudaStreamDestroy (lv->s_out);
+  delete lv;
+}
+
+int slb_live_in_flight (const slb_live *lv) { return lv ? (int) (lv->n_pushed - lv->n_popped) : SLB_ERR_ARG; }
+
+int slb_live_push (slb_live *lv, const int16_t *adc, const int16_t *usb_out)
+{
+  if (!lv || (lv->rx && !adc) || (lv->tx && !usb_out)) return SLB_ERR_ARG;
+  slb_ctx *ctx = lv->ctx;
+  if (lv->n_pushed - lv->n_popped >= lv->depth) return fail (ctx, SLB_ERR_STATE, "live feeder: every slot is in flight (pop first)");
+  if (ctx->ring_pc) return fail (ctx, SLB_ERR_STATE, "the feeder replays one shared cadence; per-channel cadence is on");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  slb_live::Slot &sl = lv->slots[lv->n_pushed % lv->depth];
+  const uint32_t C = ctx->cfg.channels, R = ctx->geo.ring_frames, B = ctx->geo.block_frames, hop = ctx->rx.hop, per_hop = hop / B, ticks = lv->ticks;
+  const bool f32 = is_ssb_chain (ctx->cfg.chain);
+  sl.pushed = std::chrono::steady_clock::now ();
+  // 1. staging (pinned) and the pointer plan of every tick of the chunk — the firmware's arithmetic, on the host, in call order
+  uint32_t *plan_tx = sl.h_plan, *plan_rx = sl.h_plan + (size_t) ticks * 2;
+  if (lv->tx)
+  {
+    std::memcpy (sl.h_usb_out, usb_out, lv->bytes);
+    for (uint32_t t = 0; t < ticks; t++) { plan_tx[2 * t + 1] = ctx->ring_out.plan_read (true, B); plan_tx[2 * t] = ctx->ring_out.plan_write (true, B); }
+  }
+  if (lv->rx)
+  {
+    std::memcpy (sl.h_adc, adc, lv->bytes);
+    for (uint32_t t = 0; t < ticks; t++) { plan_rx[2 * t] = ctx->ring_in.plan_write (false, B); plan_rx[2 * t + 1] = ctx->ring_in.plan_read (false, B); }
+  }
+  // 2. copy in (stream s_in)
+  CK (ctx, cudaMemcpyAsync (sl.d_plan, sl.h_plan, (size_t) ticks * 4 * sizeof (uint32_t), cudaMemcpyHostToDevice, lv->s_in));
+  if (lv->tx) CK (ctx, cudaMemcpyAsync (sl.d_usb_out, sl.h_usb_out, lv->bytes, cudaMemcpyHostToDevice, lv->s_in));
+  if (lv->rx) CK (ctx, cudaMemcpyAsync (sl.d_adc, sl.h_adc, lv->bytes, cudaMemcpyHostToDevice, lv->s_in));
+  CK (ctx, cudaEventRecord (sl.in_done, lv->s_in));
+  // 3. the chunk's kernels (stream s_work: chunks in order — chain state and rings carry from one to the next)
+  CK (ctx, cudaStreamWaitEvent (lv->s_work, sl.in_done, 0));
+  cudaStream_t st = lv->s_work;
+  if (lv->tx)
+  {
+    CK (ctx, launch_ring_replay (false, nullptr, 0, 0, sl.d_usb_out, (uint32_t) lv->frames, sl.d_dac, ctx->d_ring[1][0], ctx->d_ring[1][1], C, R, sl.d_plan, ticks, B, st));
+    ctx->launches++;
+    if (ctx->any_key && ctx->tone_hz)
+    { CK (ctx, launch_sidetone_mix (sl.d_dac, C, (uint32_t) lv->frames, ctx->d_key, ctx->d_tone_cnt, nullptr, ctx->d_tone, ctx->tone_hz, ctx->cfg.fs, st)); ctx->launches++; }
+  }
+  if (lv->rx)
+  {
+    const int16_t *src_a = nullptr, *src_b = sl.d_adc; uint32_t stride_a = 0, ticks_a = 0;
+    if (ctx->q15)
+    {
+      int rc = rxq15_launch (ctx, ctx->q15, sl.d_adc, sl.d_prc, 0, C, (uint32_t) lv->frames, ctx->sm_count, st, false);
+      if (rc) return rc;
+      rxq15_advance (ctx->q15);
+      src_b = sl.d_prc;
+    }
+    else if (f32)
+    {
+      int rc = run_rx_kernel (ctx, sl.d_adc, sl.d_prc, 0, C, (uint32_t) lv->frames, nullptr, nullptr, st);
+      if (rc) return rc;
+      rx_advance (ctx, (uint32_t) lv->frames);
+      src_a = ctx->d_proc[ctx->proc_cur]; stride_a = hop; ticks_a = per_hop; src_b = sl.d_prc;
+    }
+    CK (ctx, launch_ring_replay (true, src_a, stride_a, ticks_a, src_b, (uint32_t) lv->frames, sl.d_usb_in, ctx->d_ring[0][0], ctx->d_ring[0][1], C, R, sl.d_plan + (size_t) ticks * 2, ticks, B, st));
+    ctx->launches++;
+    if (f32)
+    {
+      CK (ctx, cudaMemcpy2DAsync (ctx->d_proc[ctx->proc_cur ^ 1], (size_t) hop * 4, reinterpret_cast<const char *> (sl.d_prc) + (lv->frames - hop) * 4, lv->frames * 4,
+                                  (size_t) hop * 4, C, cudaMemcpyDeviceToDevice, st));
+      ctx->proc_cur ^= 1;
+    }
+  }
+  CK (ctx, cudaEventRecord (sl.work_done, st));
+  // 4. copy out (stream s_out)
+  CK (ctx, cudaStreamWaitEvent (lv->s_out, sl.work_done, 0));
+  if (lv->tx) CK (ctx, cudaMemcpyAsync (sl.h_dac, sl.d_dac, lv->bytes, cudaMemcpyDeviceToHost, lv->s_out));
+  if (lv->rx) CK (ctx, cudaMemcpyAsync (sl.h_usb_in, sl.d_usb_in, lv->bytes, cudaMemcpyDeviceToHost, lv->s_out));
+  CK (ctx, cudaEventRecord (sl.out_done, lv->s_out));
+  lv->n_pushed++;
+  return SLB_OK;
+}
+
+int slb_live_pop (slb_live *lv, int16_t *usb_in, int16_t *dac, float *latency_us)
+{
+  if (!lv || (lv->rx && !usb_in) || (lv->tx && !dac)) return SLB_ERR_ARG;
+  slb_ctx *ctx = lv->ctx;
+  if (lv->n_pushed == lv->n_popped) return fail (ctx, SLB_ERR_STATE, "live feeder: nothing in flight");
+  CK (ctx, cudaSetDevice (ctx->cfg.device));
+  slb_live::Slot &sl = lv->slots[lv->n_popped % lv->depth];
+  CK (ctx, cudaEventSynchronize (sl.out_done));
+  if (latency_us) *latency_us = std::chrono::duration<float, std::micro> (std::chrono::steady_clock::now () - sl.pushed).count ();
+  if (lv->rx) std::memcpy (usb_in, sl.h_usb_in, lv->bytes);
+  if (lv->tx) std::memcpy (dac, sl.h_dac, lv->bytes);
+  lv->n_popped++;
   return SLB_OK;
 }
 

@@ -83,6 +83,45 @@ def params_to_dict(p, mask):
                 agc_target=p.agc_target, agc_decay=p.agc_decay, agc_floor=p.agc_floor, agc_gmax=p.agc_gmax, mask=mask)
 
 
+class LiveFeeder:
+    """slb_live_*: chunks of `ticks_per_chunk` ms through a three-stream pipeline (copy in | chain + ring replay | copy out)."""
+
+    def __init__(self, dsp, ticks_per_chunk, depth, rx, tx):
+        self.dsp, self.rx, self.tx = dsp, bool(rx), bool(tx)
+        self.frames = ticks_per_chunk * dsp.block_frames
+        self.h = C.c_void_p()
+        dsp._ck(dsp.lib.slb_live_open(dsp.h, ticks_per_chunk, depth, int(rx), int(tx), C.byref(self.h)), "live_open")
+
+    def push(self, adc=None, usb_out=None):
+        keep = []
+        def ptr(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, np.int16); assert a.shape == (self.dsp.channels, self.frames, 2); keep.append(a); return a.ctypes.data
+        self.dsp._ck(self.dsp.lib.slb_live_push(self.h, ptr(adc), ptr(usb_out)), "live_push")
+
+    def pop(self):
+        """Returns (usb_in, dac, latency_us) of the oldest chunk in flight."""
+        shape = (self.dsp.channels, self.frames, 2)
+        usb_in = np.zeros(shape, np.int16) if self.rx else None; dac = np.zeros(shape, np.int16) if self.tx else None
+        lat = C.c_float()
+        self.dsp._ck(self.dsp.lib.slb_live_pop(self.h, usb_in.ctypes.data if self.rx else None, dac.ctypes.data if self.tx else None, C.byref(lat)), "live_pop")
+        return usb_in, dac, lat.value
+
+    def in_flight(self):
+        return self.dsp.lib.slb_live_in_flight(self.h)
+
+    def close(self):
+        if self.h:
+            self.dsp.lib.slb_live_close(self.h); self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class DspIf:
     """One context = one GPU's shard of channels."""
 
@@ -207,6 +246,10 @@ class DspIf:
             raise ValueError("feeder_run: no stream given")
         self._ck(self.lib.slb_feeder_run(self.h, C.byref(io), ticks), "feeder_run")
         return usb_in, dac
+
+    def live_open(self, ticks_per_chunk, depth=3, rx=True, tx=True):
+        """Live feeder (slb_live_*): returns a LiveFeeder bound to this context."""
+        return LiveFeeder(self, ticks_per_chunk, depth, rx, tx)
 
     def AUDIO_AudioCmd(self, pbuf, size, cmd):
         a = np.ascontiguousarray(pbuf)

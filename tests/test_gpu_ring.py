@@ -306,3 +306,51 @@ def test_chain_behind_the_ring_under_per_channel_cadence(chain):
             exp = single[c].DSP_In_Buff_Read(4 * B)[0] if act[c, 1] else np.zeros(2 * B, np.int16)
             assert np.array_equal(got[c], exp), (t, c)
             assert d.ring_ptrs_channel(c, 0) == single[c].ring_ptrs(0), (t, c)
+
+
+@pytest.mark.parametrize("chain,ticks", [(slb.CHAIN_PASS, 5), (slb.CHAIN_RX_SSB_Q15, 10), (slb.CHAIN_RX_SSB_F32, 16), (slb.CHAIN_TX_SSB_F32, 8)])
+def test_live_feeder_pipeline_equals_the_per_tick_calls(chain, ticks, rng):
+    """SURVEY.md §8f.1, the live form: chunks pushed into a three-stream pipeline (pinned staging; chunk n is copied in while n-1
+    computes and n-2 is copied out) and popped in order give, bit for bit, what the per-tick calls give — with several chunks in
+    flight at once, a side-tone keyed in between, and the per-tick API carrying on from the same state afterwards."""
+    C, B, chunks, depth = 5, 48, 9, 3
+    n = ticks * B
+    adc = slb.synth_iq(C, (chunks * ticks + 8) * B)
+    pc = rng.integers(-20000, 20000, (C, (chunks * ticks + 8) * B, 2)).astype(np.int16)
+    a = slb.DspIf(C, chain=chain); b = slb.DspIf(C, chain=chain)
+    for x in (a, b):
+        x.DSP_Set_Sidetone(800, 0.1)
+    exp_in, exp_dac = [], []
+    for t in range(chunks * ticks):
+        if t == 4 * ticks:
+            a.DSP_Key(np.array([1, 0, 0, 1, 0], bool))
+        blk = slice(t * B, (t + 1) * B)
+        exp_dac.append(a.DSP_Out_Buff_Read(2 * B))
+        a.DSP_In_Buff_Write(adc[:, blk].reshape(C, -1))
+        a.DSP_Out_Buff_Write(pc[:, blk].reshape(C, -1))
+        exp_in.append(a.DSP_In_Buff_Read(4 * B))
+    exp_in = np.stack(exp_in, 1).reshape(C, -1, 2); exp_dac = np.stack(exp_dac, 1).reshape(C, -1, 2)
+    lv = b.live_open(ticks, depth)
+    got_in, got_dac, pushed = [], [], 0
+    with pytest.raises(slb.SeleniteError):
+        lv.pop()                                                                                # nothing in flight
+    for k in range(chunks):
+        if k == 4:
+            while lv.in_flight():                                                               # the key changes between chunks: drain, as the per-tick run did at tick 4 * ticks
+                u, v, _ = lv.pop(); got_in.append(u); got_dac.append(v)
+            b.DSP_Key(np.array([1, 0, 0, 1, 0], bool))
+        if lv.in_flight() == depth:
+            u, v, lat = lv.pop(); got_in.append(u); got_dac.append(v); assert lat > 0
+        lv.push(adc[:, k * n:(k + 1) * n], pc[:, k * n:(k + 1) * n]); pushed += 1
+    assert lv.in_flight() > 1                                                                   # the pipeline really held several chunks
+    while lv.in_flight():
+        u, v, _ = lv.pop(); got_in.append(u); got_dac.append(v)
+    lv.close()
+    assert np.array_equal(np.concatenate(got_dac, 1), exp_dac)
+    assert np.array_equal(np.concatenate(got_in, 1), exp_in)
+    assert a.ring_ptrs(0) == b.ring_ptrs(0) and a.ring_ptrs(1) == b.ring_ptrs(1)
+    for t in range(chunks * ticks, chunks * ticks + 8):                                          # and the per-tick API carries on from the same state
+        blk = slice(t * B, (t + 1) * B)
+        for d in (a, b):
+            d.DSP_In_Buff_Write(adc[:, blk].reshape(C, -1))
+        assert np.array_equal(a.DSP_In_Buff_Read(4 * B), b.DSP_In_Buff_Read(4 * B))
