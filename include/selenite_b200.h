@@ -264,6 +264,14 @@ int slb_st_max_q15 (slb_ctx *ctx, const int16_t *src, uint32_t n, uint32_t block
 int slb_st_rms_q15 (slb_ctx *ctx, const int16_t *src, uint32_t n, uint32_t block, int16_t *out, void *stream);
 /* batched arm_cfft_f32 (bit-reversed output order is not offered): data [channels][count][2*N] floats, in place */
 int slb_st_cfft_f32 (slb_ctx *ctx, float *data, uint32_t N, uint32_t count, int ifft, void *stream);
+/* batched arm_cfft_q15 (arm_cfft_q15.c:77, in the ARM_MATH_DSP branch the firmware's ARM_MATH_CM4 build compiles) and arm_cfft_q31
+ * (arm_cfft_q31.c:77): data [channels][count][2*N] q15 / q31, in place, N = 16..4096, natural output order, bit-exact; the output
+ * scaling is the reference's (forward: 1/N for N = 4^m ... see arm_cfft_radix4_q15.c:94-104). slb_design_twiddle_*: the regenerated
+ * twiddle tables (3 N / 4 (cos, sin) pairs), exported for the design check against arm_common_tables.c. */
+int slb_st_cfft_q15 (slb_ctx *ctx, int16_t *data, uint32_t N, uint32_t count, int ifft, void *stream);
+int slb_st_cfft_q31 (slb_ctx *ctx, int32_t *data, uint32_t N, uint32_t count, int ifft, void *stream);
+int slb_design_twiddle_q15 (uint32_t N, int16_t *out);
+int slb_design_twiddle_q31 (uint32_t N, int32_t *out);
 /* batched arm_rfft_fast_f32 (arm_rfft_fast_f32.c:288): in / out [channels][count][N] floats, out of place, N = 32..4096;
  * forward output packed as the reference packs it: out[0] = X[0], out[1] = X[N/2], then (Re, Im) of X[1..N/2-1] */
 int slb_st_rfft_fast_f32 (slb_ctx *ctx, const float *in, float *out, uint32_t N, uint32_t count, int ifft, void *stream);

@@ -90,6 +90,11 @@ int launch_tone_table (int16_t *d_tone, uint32_t fs, float level, const float *d
 int launch_sidetone_mix (int16_t *d_blocks, uint32_t channels, uint32_t frames, const uint8_t *d_key, uint32_t *d_cnt, const uint32_t *d_first,
                          const int16_t *d_tone, uint32_t freq_hz, uint32_t fs, void *stream);
 const float *host_sin_table ();
+// fixed-point FFTs (sl_fft_fixed.cu): regenerated twiddle tables (host, cached) and the batched transforms
+const int16_t *fft_twiddle_q15 (uint32_t N);
+const int32_t *fft_twiddle_q31 (uint32_t N);
+int launch_cfft_q15 (int16_t *d_data, uint32_t N, size_t transforms, int ifft, const int16_t *d_tw, void *stream);
+int launch_cfft_q31 (int32_t *d_data, uint32_t N, size_t transforms, int ifft, const int32_t *d_tw, void *stream);
 
 struct RxF32Launch
 {

@@ -583,6 +583,33 @@ int slb_st_fir_interpolate_q15 (slb_ctx *ctx, const int16_t *coeffs, uint32_t nt
 int slb_st_fir_decimate_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t ntaps, uint32_t M, int32_t *hist, const int32_t *src, int32_t *dst, uint32_t n, void *stream) { return fir_common<int32_t, 3> (ctx, coeffs, ntaps, M, 1, hist, src, dst, n, stream); }
 int slb_st_fir_interpolate_q31 (slb_ctx *ctx, const int32_t *coeffs, uint32_t ntaps, uint32_t L, int32_t *hist, const int32_t *src, int32_t *dst, uint32_t n, void *stream) { return fir_common<int32_t, 3> (ctx, coeffs, ntaps, 1, L, hist, src, dst, n, stream); }
 
+// ---- fixed-point FFTs (sl_fft_fixed.cu): data [channels][count][2 N], in place, natural output order
+int slb_st_cfft_q15 (slb_ctx *ctx, int16_t *data, uint32_t N, uint32_t count, int ifft, void *stream)
+{
+  ST_BEGIN (ctx);
+  if (!data || count == 0 || N < 16 || N > 4096 || (N & (N - 1))) return ctx_fail (ctx, SLB_ERR_ARG, "cfft_q15: N = 16 .. 4096, a power of two");
+  const size_t tw_bytes = (size_t) 3 * N / 4 * 2 * sizeof (int16_t);
+  int16_t *d_tw = (int16_t *) ctx_scratch (ctx, tw_bytes);
+  if (!d_tw) return SLB_ERR_CUDA;
+  cudaError_t e = cudaMemcpyAsync (d_tw, fft_twiddle_q15 (N), tw_bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));
+  ST_END (ctx, launch_cfft_q15 (data, N, C * count, ifft, d_tw, st));
+}
+int slb_st_cfft_q31 (slb_ctx *ctx, int32_t *data, uint32_t N, uint32_t count, int ifft, void *stream)
+{
+  ST_BEGIN (ctx);
+  if (!data || count == 0 || N < 16 || N > 4096 || (N & (N - 1))) return ctx_fail (ctx, SLB_ERR_ARG, "cfft_q31: N = 16 .. 4096, a power of two");
+  const size_t tw_bytes = (size_t) 3 * N / 4 * 2 * sizeof (int32_t);
+  int32_t *d_tw = (int32_t *) ctx_scratch (ctx, tw_bytes);
+  if (!d_tw) return SLB_ERR_CUDA;
+  cudaError_t e = cudaMemcpyAsync (d_tw, fft_twiddle_q31 (N), tw_bytes, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));
+  ST_END (ctx, launch_cfft_q31 (data, N, C * count, ifft, d_tw, st));
+}
+// design check (tests/test_fft_fixed_tables.py): the regenerated twiddle tables, 3 N / 4 (cos, sin) pairs
+int slb_design_twiddle_q15 (uint32_t N, int16_t *out) { if (!out || N < 16 || N > 4096 || (N & (N - 1))) return SLB_ERR_ARG; std::memcpy (out, fft_twiddle_q15 (N), (size_t) 3 * N / 4 * 2 * sizeof (int16_t)); return SLB_OK; }
+int slb_design_twiddle_q31 (uint32_t N, int32_t *out) { if (!out || N < 16 || N > 4096 || (N & (N - 1))) return SLB_ERR_ARG; std::memcpy (out, fft_twiddle_q31 (N), (size_t) 3 * N / 4 * 2 * sizeof (int32_t)); return SLB_OK; }
+
 // ---- normalised LMS. coeffs: device [channels][ntaps] (every channel adapts its own), state: device [channels][ntaps + 1] =
 // the ntaps - 1 previous samples oldest first (the head of the CMSIS state buffer), then energy and x0 of the instance; both in place
 int slb_st_lms_norm_f32 (slb_ctx *ctx, float *coeffs, uint32_t ntaps, float mu, float *state, const float *src, const float *ref,

@@ -49,9 +49,28 @@ def golden_fm(ref):
     print("rx_fm_f32.npz", os.path.getsize(os.path.join(HERE, "rx_fm_f32.npz")), "bytes")
 
 
+def golden_fft_fixed(ref):
+    """arm_cfft_q15 (in the ARM_MATH_DSP branch of the firmware's ARM_MATH_CM4 build: oracle/ref_glue/cm4_fft_q15.c) and arm_cfft_q31
+    of the reference build on frozen inputs: N = 64 (4^3), 128 (2 * 4^3), 1024, 2048; forward and inverse; moderate and full-scale."""
+    rng = np.random.Generator(np.random.PCG64(slb.signals.SEED + 0xFF7))
+    out = {}
+    for N in (16, 64, 128, 1024, 2048):
+        for amp, tag in ((6000, "m"), (32767, "f")):
+            x15 = rng.integers(-amp, amp + 1, 2 * N).astype(np.int16)
+            x31 = rng.integers(-(amp << 16), (amp << 16) + 1, 2 * N).astype(np.int32)
+            out["q15_%d_%s_in" % (N, tag)] = x15; out["q31_%d_%s_in" % (N, tag)] = x31
+            for ifft in (0, 1):
+                out["q15_%d_%s_%d" % (N, tag, ifft)] = ref.cfft_q15_cm4(x15, ifft)
+                out["q31_%d_%s_%d" % (N, tag, ifft)] = ref.cfft_q31(x31, ifft)
+    np.savez_compressed(os.path.join(HERE, "cfft_fixed.npz"), **out)
+    print("cfft_fixed.npz", os.path.getsize(os.path.join(HERE, "cfft_fixed.npz")), "bytes")
+
+
 def main():
     oracle_lib.build_oracles()
     ref = oracle_lib.Oracle("ref")
+    if len(sys.argv) > 1 and sys.argv[1] == "fft_fixed":
+        return golden_fft_fixed(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "q15":      # later additions regenerate alone: the older fixtures stay untouched
         return golden_q15(ref)
     if len(sys.argv) > 1 and sys.argv[1] == "fm":

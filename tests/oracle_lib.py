@@ -153,6 +153,11 @@ class Oracle:
         d = np.ascontiguousarray(x, np.float32).copy()
         self._f("cfft_f32", [f32p, u32, C.c_int, C.c_int])(d, d.size // 2, ifft, bitrev); return d
 
+    def cfft_q15_cm4(self, x, ifft=0, bitrev=1):
+        """arm_cfft_q15 in the branch the firmware's ARM_MATH_CM4 build compiles (reference build only; the authority for the q15 FFT)."""
+        d = np.ascontiguousarray(x, np.int16).copy()
+        self._f("cfft_q15_cm4", [i16p, u32, C.c_int, C.c_int])(d, d.size // 2, ifft, bitrev); return d
+
     def cfft_q15(self, x, ifft=0, bitrev=1):
         d = np.ascontiguousarray(x, np.int16).copy()
         self._f("cfft_q15", [i16p, u32, C.c_int, C.c_int])(d, d.size // 2, ifft, bitrev); return d

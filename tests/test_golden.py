@@ -274,3 +274,20 @@ def test_ref_fm_chain_reproduces_golden(ref, name):
     g = np.load(os.path.join(GOLD, "rx_fm_f32.npz"))
     out, audio, gain, _ = ref.rx_ssb_f32(fm_params(g), g["fm_%s_in" % name])
     assert np.array_equal(out, g["fm_%s_out" % name]) and np.array_equal(audio, g["fm_%s_audio" % name])
+
+
+def test_ref_fixed_point_ffts_reproduce_golden(ref):
+    """tests/golden/cfft_fixed.npz = arm_cfft_q15 (ARM_MATH_DSP branch, oracle/ref_glue/cm4_fft_q15.c) and arm_cfft_q31 of the reference build."""
+    g = np.load(os.path.join(GOLD, "cfft_fixed.npz"))
+    n = 0
+    for key in g.files:
+        if key.endswith("_in"):
+            kind, N, tag, _ = key.split("_")
+            for ifft in (0, 1):
+                fn = ref.cfft_q15_cm4 if kind == "q15" else ref.cfft_q31
+                assert np.array_equal(fn(g[key], ifft), g["%s_%s_%s_%d" % (kind, N, tag, ifft)]); n += 1
+    assert n == 40
+    # and the reason the CM4-path build exists: the C branch of the same routine is NOT the firmware's arithmetic (SURVEY.md §8c.3)
+    x = g["q15_1024_m_in"]
+    assert not np.array_equal(ref.cfft_q15(x, 0), ref.cfft_q15_cm4(x, 0))
+    assert np.max(np.abs(ref.cfft_q15(x, 0).astype(np.int32) - ref.cfft_q15_cm4(x, 0))) <= 8

@@ -3,6 +3,7 @@ Integer routines and the sequential float routines: bit-exact. FFT: 2e-6 of outp
 import numpy as np
 import pytest
 
+import oracle_lib
 import selenite_lite_b200 as slb
 
 torch = pytest.importorskip("torch")
@@ -159,6 +160,45 @@ def test_fir_decimate_interpolate_q31(ctx, best_oracle, rng):
         got = np.concatenate(outs, 1)
         for ch in range(C):
             assert np.array_equal(got[ch], best_oracle.fir_interpolate_q31(c31, M, np.zeros(64 + B, np.int32), xx[ch], B)[0]), ("int", M, ch)
+
+
+@pytest.mark.parametrize("N", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("ifft", [0, 1])
+def test_cfft_q15_q31_bit_exact(ctx, rng, N, ifft):
+    """arm_cfft_q15 (arm_cfft_q15.c:77, the ARM_MATH_DSP branch of the firmware's Cortex-M4 build) and arm_cfft_q31 (arm_cfft_q31.c:77),
+    batched [channels][count][2 N] in place: bit for bit against the reference build (every size: both the pure radix-4 and the
+    radix-4-by-2 decompositions), moderate and rail-to-rail inputs (the q15 lane sums saturate)."""
+    try:
+        ref = oracle_lib.Oracle("ref")
+    except (FileNotFoundError, OSError):
+        pytest.skip("reference build absent: the committed vectors (test_cfft_fixed_golden_vectors) are the check")
+    count = 3
+    for amp in (5000, 32767):
+        x15 = rng.integers(-amp, amp + 1, (C, count, 2 * N)).astype(np.int16)
+        x31 = rng.integers(-(amp << 16), (amp << 16) + 1, (C, count, 2 * N)).astype(np.int32)
+        d15 = dev(x15); d31 = dev(x31)
+        ctx.st("cfft_q15", d15, N, count, ifft); ctx.st("cfft_q31", d31, N, count, ifft)
+        g15, g31 = d15.cpu().numpy(), d31.cpu().numpy()
+        for ch in range(C):
+            for k in range(count):
+                assert np.array_equal(g15[ch, k], ref.cfft_q15_cm4(x15[ch, k], ifft)), ("q15", N, amp, ch, k)
+                assert np.array_equal(g31[ch, k], ref.cfft_q31(x31[ch, k], ifft)), ("q31", N, amp, ch, k)
+
+
+def test_cfft_fixed_golden_vectors(ctx):
+    """The same transforms against vectors committed from the reference build (tests/golden/make_golden.py fft_fixed)."""
+    import os
+    from test_golden import GOLD
+    g = np.load(os.path.join(GOLD, "cfft_fixed.npz"))
+    for key in g.files:
+        if not key.endswith("_in"):
+            continue
+        kind, N, tag, _ = key.split("_"); N = int(N)
+        x = np.tile(g[key], (C, 1, 1))
+        for ifft in (0, 1):
+            d = dev(x)
+            ctx.st("cfft_" + kind, d, N, 1, ifft)
+            assert np.array_equal(d.cpu().numpy()[C - 1, 0], g["%s_%d_%s_%d" % (kind, N, tag, ifft)]), (key, ifft)
 
 
 @pytest.mark.parametrize("ntaps", [8, 32, 64])
