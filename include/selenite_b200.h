@@ -111,6 +111,11 @@ typedef struct
   int16_t  rel[SLB_Q15_WIN];             /* q15 release weight of a block peak by age in blocks; rel[0] unused */
   int16_t  agc_target, agc_floor;        /* q15 */
   uint32_t agc_gmax_q15;                 /* gain limit in Q15 (1.0 = 32768) [arm_scale_q15 scaleFract << shift] */
+  /* optional audio filter between the mixer and the AGC detector [arm_biquad_cascade_df1_q15.c:62]: bq_stages = 0
+   * (default) leaves it out and the chain runs as ONE fused tensor-core kernel; 1..4 stages run the chain as three kernels — fused FIR +
+   * mixer, the integer biquad (one thread per channel: it truncates after every sample, so it cannot be evaluated time-parallel exactly),
+   * AGC + scale — bit-exact all the same. Coefficients {b0, 0, b1, b2, a1, a2} per stage (arm_biquad_cascade_df1_init_q15). */
+  uint32_t bq_stages; int32_t bq_postshift; int16_t bq_coeffs[6 * SLB_MAX_STAGES];
 } slb_rx_q15_params;
 
 /* ---- life cycle ---- */

@@ -234,6 +234,7 @@ void SLO (rx_ssb_q15) (const slo_rx_q15_params *p, slo_rx_q15_state *st, const i
     SLO (fir_q15) (ci, T, st->fir_i, xi, fi, B, B);
     SLO (fir_q15) (cq, T, st->fir_q, xq, fq, B, B);
     if (p->lsb) SLO (sub_q15) (fi, fq, a, B); else SLO (add_q15) (fi, fq, a, B);
+    if (p->bq_stages) SLO (biquad_df1_q15) (p->bq_coeffs, p->bq_stages, p->bq_postshift, st->bq, a, a, B, B);   /* optional audio filter (Appendix B) */
     if (audio_dbg) memcpy (audio_dbg + o, a, sizeof (int16_t) * B);
     SLO (abs_q15) (a, ab, B);
     const int32_t peak = SLO (max_q15) (ab, B, 0);

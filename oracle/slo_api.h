@@ -214,12 +214,16 @@ typedef struct
   int16_t rel[SLO_Q15_WIN];                              /* q15 release weight by block age; rel[0] unused */
   int16_t agc_target, agc_floor;                         /* q15; floor >= 1 */
   uint32_t agc_gmax_q15;                                 /* gain limit in Q15 (1.0 = 32768) */
+  /* optional audio filter between the mixer and the AGC detector: arm_biquad_cascade_df1_q15 on the mixed audio,
+   * bq_stages = 0 switches it off; coefficients {b0, 0, b1, b2, a1, a2} per stage as arm_biquad_cascade_df1_init_q15 lays them out */
+  uint32_t bq_stages; int32_t bq_postshift; int16_t bq_coeffs[6 * 4];
 } slo_rx_q15_params;
 
 typedef struct
 {
   int16_t fir_i[SLO_Q15_TAPS + SLO_Q15_MAX_BLOCK], fir_q[SLO_Q15_TAPS + SLO_Q15_MAX_BLOCK];   /* arm_fir_q15 pState */
   int16_t peaks[SLO_Q15_WIN];                            /* peaks[j] = block peak j+1 blocks ago */
+  int16_t bq[4 * 4];                                     /* arm_biquad_cascade_df1_q15 pState: {x[n-1], x[n-2], y[n-1], y[n-2]} per stage */
 } slo_rx_q15_state;
 
 /* frames % agc_block == 0. audio_dbg (optional): the pre-AGC q15 audio [frames]; gain_dbg (optional): q per block. */

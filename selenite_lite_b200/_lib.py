@@ -27,7 +27,8 @@ class TxF32Params(C.Structure):
 class RxQ15Params(C.Structure):
     _fields_ = [("ntaps", C.c_uint32), ("agc_block", C.c_uint32), ("agc_window", C.c_uint32),
                 ("taps_i", C.c_int16 * 64), ("taps_q", C.c_int16 * 64), ("rel", C.c_int16 * 32),
-                ("agc_target", C.c_int16), ("agc_floor", C.c_int16), ("agc_gmax_q15", C.c_uint32)]
+                ("agc_target", C.c_int16), ("agc_floor", C.c_int16), ("agc_gmax_q15", C.c_uint32),
+                ("bq_stages", C.c_uint32), ("bq_postshift", C.c_int32), ("bq_coeffs", C.c_int16 * 24)]
 
 
 class FeederIo(C.Structure):

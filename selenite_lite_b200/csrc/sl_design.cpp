@@ -288,13 +288,15 @@ bool tc_build_planes (const float *mask, const float *cf, uint8_t *planes, float
     }
   double mx_a = 0, mx_z = 0;
   for (int r = 0; r < R; r++) for (int k = 0; k < F * 2; k++) { double &mx = (r < 48) ? mx_a : mx_z; mx = std::fmax (mx, std::fabs (W[(size_t) r * F * 2 + k])); }
-  const double lim = 8323071.0;                      // 2^23 - 2^16 - 1: the top balanced digit stays inside int8
-  // scale: the largest entry takes the full 24 bits. The float unit of the integer output is fixed first and the scale
-  // derived from it, so that unit * 32768 * scale == 1 holds exactly for the float32 value the kernel multiplies by
-  // (the 1/32768 of arm_q15_to_float.c:87 is folded in).
-  const float ua = (float) (mx_a / (lim * 32768.0)), uz = (float) (mx_z / (lim * 32768.0));
+  // 32-bit map, four balanced base-256 digits: 127 (2^24 + 2^16 + 2^8 + 1) is the largest value they hold
+  const double lim = 2139062143.0 - 16843009.0;
+  // scale: the largest entry takes the full range. The float unit of the integer output is fixed first and the scale derived
+  // from it, so that unit * 32768 * scale == 1 holds exactly for the float32 value the kernel multiplies by (the 1/32768 of
+  // arm_q15_to_float.c:87 is folded in). The kernel drops the one product class below 2^8 (low data byte x lowest digit), so
+  // the unit it is handed belongs to the 2^8 class: 256 map LSBs.
+  const float ua = (float) (256.0 * mx_a / (lim * 32768.0)), uz = (float) (256.0 * mx_z / (lim * 32768.0));
   if (!(ua > 1e-30f) || !std::isfinite (ua) || !(uz > 1e-30f) || !std::isfinite (uz)) return false;
-  const double sc_a = 1.0 / ((double) ua * 32768.0), sc_z = 1.0 / ((double) uz * 32768.0);
+  const double sc_a = 256.0 / ((double) ua * 32768.0), sc_z = 256.0 / ((double) uz * 32768.0);
   *unit_a = ua; *unit_z = uz;
   std::memset (planes, 0, kTcPlaneBytes);
   for (int r = 0; r < R; r++)
@@ -302,12 +304,17 @@ bool tc_build_planes (const float *mask, const float *cf, uint8_t *planes, float
     {
       const long long q = std::llround (W[(size_t) r * F * 2 + m] * (r < 48 ? sc_a : sc_z));
       if (q == 0) continue;
-      if (std::llabs (q) > (long long) lim + 1) return false;
-      const int32_t h = (int32_t) q;
-      const int32_t l0 = ((h + 128) & 255) - 128, r1 = (h - l0) >> 8, l1 = ((r1 + 128) & 255) - 128, l2 = (r1 - l1) >> 8;
-      const int32_t dg[3] = { l2, l1, l0 };          // most significant first: accumulator columns 0..51 carry 2^24
+      if (std::llabs (q) > 2139062143ll) return false;          // (lim keeps 0.8 % of headroom under this: the float32 unit moves the scale by up to 6e-8)
+      long long h = q;
+      int32_t dg[kTcMapDigits];                      // most significant first: accumulator columns 0..51 carry 2^32 (x 2^8 of the high data byte)
+      for (int gdig = kTcMapDigits - 1; gdig >= 0; gdig--)
+      {
+        const long long lo = ((h + 128) & 255) - 128;
+        dg[gdig] = (int32_t) lo; h = (h - lo) >> 8;
+      }
+      if (h != 0) return false;
       const int ks = m / 32, kk = m % 32;
-      for (int gdig = 0; gdig < 3; gdig++)
+      for (int gdig = 0; gdig < kTcMapDigits; gdig++)
       {
         const int row = gdig * kTcDigit + r;
         planes[(size_t) ks * kTcRowGroups * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)] = (uint8_t) (int8_t) dg[gdig];
@@ -317,22 +324,25 @@ bool tc_build_planes (const float *mask, const float *cf, uint8_t *planes, float
 }
 
 // host-side evaluation of the planes on one raw window (design check, tests/test_tc_math.py): exactly the integer
-// contraction the kernel runs, out[0..47] = zero-state audio of the block, out[48..51] = its end state
+// contraction the kernel runs — the high data byte against all four digits, the low one against the top three (the class
+// below 2^8 is not computed) — out[0..47] = zero-state audio of the block, out[48..51] = its end state
 void tc_apply_planes (const uint8_t *planes, float unit_a, float unit_z, const int16_t *window /* [176][2] */, double *out52)
 {
   for (int r = 0; r < 52; r++)
   {
-    long long acc = 0;
+    long long acc = 0;                                // in units of the 2^8 class
     for (int m = 0; m < 352; m++)
     {
       const int ks = m / 32, kk = m % 32;
-      long long h = 0;
-      for (int gdig = 0; gdig < 3; gdig++)
+      long long dg[kTcMapDigits];
+      for (int gdig = 0; gdig < kTcMapDigits; gdig++)
       {
         const int row = gdig * kTcDigit + r;
-        h = h * 256 + (int8_t) planes[(size_t) ks * kTcRowGroups * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)];
+        dg[gdig] = (int8_t) planes[(size_t) ks * kTcRowGroups * 256 + (row / 8) * 256 + (kk / 16) * 128 + (row % 8) * 16 + (kk % 16)];
       }
-      acc += h * (long long) window[m];
+      const int x = window[m], xl = x & 255, xh = (x - xl) >> 8;
+      // x h / 2^8 = xh (h3 2^24 + h2 2^16 + h1 2^8 + h0) + xl (h3 2^16 + h2 2^8 + h1) [+ xl h0 / 2^8, dropped]
+      acc += (long long) xh * (((dg[0] * 256 + dg[1]) * 256 + dg[2]) * 256 + dg[3]) + (long long) xl * ((dg[0] * 256 + dg[1]) * 256 + dg[2]);
     }
     out52[r] = (double) acc * (double) (r < 48 ? unit_a : unit_z);
   }

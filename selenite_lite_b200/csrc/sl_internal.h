@@ -124,7 +124,8 @@ constexpr size_t kTwiddleFloats = 6 * 32 * 4;
 constexpr int kTcTaps = 129;                       // fft_len - hop + 1
 constexpr int kTcChannels = 8;                     // channels of one group = the 8 rows of a shared-memory core matrix
 constexpr int kTcDigit = 52;                       // rows of one digit: 48 audio + 4 end-state outputs of a block
-constexpr int kTcRowGroups = 20;                   // 3 digits x 52 rows, padded to N = 160 (a multiple of 16), / 8
+constexpr int kTcMapDigits = 4;                    // base-256 digits of a map entry: a 32-bit map. The high data byte meets all four, the low one the top three
+constexpr int kTcRowGroups = 26;                   // 4 digits x 52 rows = 208 rows (N = 208 for the xh MMAs; the xl MMAs read the first 160), / 8
 constexpr size_t kTcPlaneBytes = 11 * kTcRowGroups * 256;   // operand planes of one mask: [k-step][digit*52+row][32 bytes] in UMMA layout
 struct TcBiquadTables
 {
@@ -209,6 +210,7 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
                   int sm_count, void *stream, bool with_debug);
 void rxq15_advance (RxQ15State *st);
 int rxq15_carry_idle (RxQ15State *st, uint32_t ch0, uint32_t nch, void *stream);
+int launch_biquad_df1_q15 (const int16_t *coeffs6, uint32_t ns, int32_t postshift, int16_t *d_state, const int16_t *d_src, int16_t *d_dst, uint32_t channels, uint32_t n, void *stream);
 size_t rxq15_state_bytes (const RxQ15State *st);
 int rxq15_state_save (RxQ15State *st, char *dst);
 int rxq15_state_load (RxQ15State *st, const char *src);

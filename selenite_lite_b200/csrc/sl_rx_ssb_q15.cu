@@ -330,7 +330,57 @@ struct RxQ15State
   uint32_t *d_afrag = nullptr; uint8_t *d_lsb = nullptr;
   uint8_t *d_tc_planes = nullptr; bool tc_ok = false;   // tcgen05 form of the same FIRs (sl_rx_q15_tc.cu)
   int16_t *dbg_audio = nullptr; uint32_t *dbg_gain = nullptr;
+  // optional integer biquad between mixer and AGC (prm.bq_stages > 0): state [C][4 x stages], and the staging of the three-kernel path
+  int16_t *d_bq = nullptr; int16_t *d_aud = nullptr; int16_t *d_blkpk = nullptr; int16_t *d_pk_dummy = nullptr; int16_t *d_rel = nullptr; size_t aud_cap = 0, blk_cap = 0;
 };
+
+// AGC + scale of the three-kernel path (the chain with the optional biquad): block peaks of the filtered audio (arm_abs_q15 + arm_max_q15),
+// the finite-window envelope and gain word exactly as in the fused kernels, arm_scale_q15, L = R. One CTA per channel.
+__global__ void __launch_bounds__ (128) q15_agc_kernel (const int16_t *__restrict__ aud, uint32_t *__restrict__ out, const int16_t *__restrict__ peaks_in,
+                                                        int16_t *__restrict__ peaks_out, int16_t *__restrict__ blkpk, uint32_t frames, uint32_t window,
+                                                        int target, int floor_, uint32_t gmax, const int16_t *__restrict__ rel, uint32_t *__restrict__ gain_dbg)
+{
+  const uint32_t c = blockIdx.x, blocks = frames / kBlk;
+  const int16_t *a = aud + (size_t) c * frames;
+  int16_t *pk = blkpk + (size_t) c * blocks;
+  const int16_t *pin = peaks_in + (size_t) c * kWin;
+  __shared__ int16_t s_rel[kWin];
+  if (threadIdx.x < kWin) s_rel[threadIdx.x] = rel[threadIdx.x];
+  for (uint32_t b = threadIdx.x; b < blocks; b += blockDim.x)
+  {
+    int m = 0;
+    for (int n = 0; n < kBlk; n++) m = max (m, min (abs ((int) a[(size_t) b * kBlk + n]), 32767));
+    pk[b] = (int16_t) m;
+  }
+  __syncthreads ();
+  for (uint32_t b = threadIdx.x; b < blocks; b += blockDim.x)
+  {
+    int e = pk[b];
+    for (uint32_t age = 1; age < window; age++)
+    {
+      const int p = (b >= age) ? (int) pk[b - age] : (int) pin[age - b - 1];
+      e = max (e, (p * (int) s_rel[age]) >> 15);
+    }
+    const unsigned gq = min ((unsigned) (target << 15) / (unsigned) max (e, floor_), gmax);
+    const int sh = max (0, 17 - __clz (gq)), m = (int) (gq >> sh);
+    if (gain_dbg) gain_dbg[(size_t) c * blocks + b] = gq;
+    uint32_t *o = out + (size_t) c * frames + (size_t) b * kBlk;
+    for (int n = 0; n < kBlk; n++)
+    {
+      const int v = max (-32768, min (32767, ((int) a[(size_t) b * kBlk + n] * m) >> (15 - sh)));
+      o[n] = __byte_perm ((uint32_t) v, 0u, 0x1010);
+    }
+  }
+  // the peak window by age for the next call
+  for (uint32_t age = 1 + threadIdx.x; age < (uint32_t) kWin; age += blockDim.x)
+  {
+    int v;
+    if (blocks >= age) v = pk[blocks - age];
+    else v = (age - blocks <= (uint32_t) kWin - 1) ? (int) pin[age - blocks - 1] : 0;
+    peaks_out[(size_t) c * kWin + age - 1] = (int16_t) v;
+  }
+  if (threadIdx.x == 0) peaks_out[(size_t) c * kWin + kWin - 1] = 0;
+}
 
 // A[m][k] = h[m + 64 - k] (0 outside 0..ntaps-1), k-steps 0, 1 (32 wide) and 2 (16 wide), split into the signed high
 // byte and the unsigned low byte, in the per-lane register layout of mma.sync m16n8k32 / m16n8k16 (row-major A):
@@ -371,6 +421,7 @@ int rxq15_create (slb_ctx *ctx, uint32_t channels, uint32_t fs, RxQ15State **out
   ok = ok && cudaMalloc (&st->d_afrag, 4 * 10 * 32 * 4) == cudaSuccess;
   ok = ok && cudaMalloc (&st->d_lsb, channels) == cudaSuccess;
   ok = ok && cudaMalloc (&st->d_tc_planes, kTcQ15PlaneBytes) == cudaSuccess;
+  ok = ok && cudaMalloc (&st->d_bq, (size_t) channels * 16 * 2) == cudaSuccess && cudaMalloc (&st->d_pk_dummy, (size_t) channels * kWin * 2) == cudaSuccess && cudaMalloc (&st->d_rel, kWin * 2) == cudaSuccess;
   if (!ok) { rxq15_destroy (st); return ctx_fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state allocation failed"); }
   slb_rx_q15_params p; design_default_rx_q15 (fs, &p);
   int rc = rxq15_set_params (ctx, st, &p);
@@ -386,6 +437,7 @@ void rxq15_destroy (RxQ15State *st)
   if (!st) return;
   for (int p = 0; p < 2; p++) { cudaFree (st->d_tail[p]); cudaFree (st->d_peaks[p]); }
   cudaFree (st->d_afrag); cudaFree (st->d_lsb); cudaFree (st->d_tc_planes);
+  cudaFree (st->d_bq); cudaFree (st->d_aud); cudaFree (st->d_blkpk); cudaFree (st->d_pk_dummy); cudaFree (st->d_rel);
   delete st;
 }
 
@@ -394,6 +446,7 @@ int rxq15_reset (slb_ctx *ctx, RxQ15State *st)
   for (int p = 0; p < 2; p++)
     if (cudaMemset (st->d_tail[p], 0, (size_t) st->channels * kTaps * 4) != cudaSuccess || cudaMemset (st->d_peaks[p], 0, (size_t) st->channels * kWin * 2) != cudaSuccess)
       return ctx_fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state reset failed");
+  if (cudaMemset (st->d_bq, 0, (size_t) st->channels * 16 * 2) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state reset failed");
   st->parity = 0;
   return SLB_OK;
 }
@@ -403,6 +456,10 @@ int rxq15_set_params (slb_ctx *ctx, RxQ15State *st, const slb_rx_q15_params *p)
   if (p->ntaps != (uint32_t) kTaps || p->agc_block != (uint32_t) kBlk) return ctx_fail (ctx, SLB_ERR_UNSUPPORTED, "this build has a kernel for ntaps=64, agc_block=48 only");
   if (p->agc_window < 1 || p->agc_window > (uint32_t) kWin || p->agc_floor < 1 || p->agc_target < 1 || p->agc_gmax_q15 < 1 || p->agc_gmax_q15 > (255u << 15))
     return ctx_fail (ctx, SLB_ERR_ARG, "AGC constants out of range");
+  if (p->bq_stages > (uint32_t) SLB_MAX_STAGES || p->bq_postshift < 0 || p->bq_postshift > 14) return ctx_fail (ctx, SLB_ERR_ARG, "optional biquad: 0..4 stages, postshift 0..14");
+  if (p->bq_stages != st->prm.bq_stages || std::memcmp (p->bq_coeffs, st->prm.bq_coeffs, sizeof p->bq_coeffs) != 0)
+    if (cudaMemset (st->d_bq, 0, (size_t) st->channels * 16 * 2) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15 state reset failed");   // a new filter starts from rest
+  if (cudaMemcpy (st->d_rel, p->rel, kWin * 2, cudaMemcpyHostToDevice) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "release table upload failed");
   std::vector<uint32_t> frag (4 * 10 * 32);
   pack_afrag (p->taps_i, p->ntaps, frag.data (), frag.data () + 320);
   pack_afrag (p->taps_q, p->ntaps, frag.data () + 640, frag.data () + 960);
@@ -432,27 +489,59 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
   if (reinterpret_cast<uintptr_t> (d_in) & 15u) return ctx_fail (ctx, SLB_ERR_ARG, "input must be 16-byte aligned (bulk copies)");
   const char *path_env = std::getenv ("SELENITE_B200_Q15_PATH");                 // A/B and test knob: "legacy" = the mma.sync kernel below
   const bool legacy_only = path_env && std::strcmp (path_env, "legacy") == 0;
+  // With the optional biquad the chain runs as three kernels: (1) the fused kernel for FIRs + mixer, its audio tap as the product and
+  // its own AGC output / peak window discarded, (2) arm_biquad_cascade_df1_q15 per channel, (3) AGC + scale on the filtered audio.
+  const bool with_bq = st->prm.bq_stages != 0;
+  int16_t *aud_tap = with_debug ? st->dbg_audio : nullptr; uint32_t *gain_tap = with_debug ? st->dbg_gain : nullptr;
+  int16_t *pk_out = st->d_peaks[st->parity ^ 1] + (size_t) ch0 * kWin;
+  if (with_bq)
+  {
+    const size_t need_a = (size_t) nch * frames, need_b = (size_t) nch * (frames / kBlk);
+    if (need_a > st->aud_cap || need_b > st->blk_cap)
+    {
+      cudaStreamSynchronize ((cudaStream_t) stream);
+      cudaFree (st->d_aud); cudaFree (st->d_blkpk); st->d_aud = st->d_blkpk = nullptr; st->aud_cap = st->blk_cap = 0;
+      if (cudaMalloc (&st->d_aud, need_a * 2) != cudaSuccess || cudaMalloc (&st->d_blkpk, need_b * 2) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "RX-SSB-q15: staging allocation failed");
+      st->aud_cap = need_a; st->blk_cap = need_b;
+    }
+    aud_tap = st->d_aud; gain_tap = nullptr; pk_out = st->d_pk_dummy + (size_t) ch0 * kWin;
+  }
+  auto finish_bq = [&] () -> int
+  {
+    if (!with_bq) return SLB_OK;
+    cudaStream_t s_ = (cudaStream_t) stream;
+    int e = launch_biquad_df1_q15 (st->prm.bq_coeffs, st->prm.bq_stages, st->prm.bq_postshift, st->d_bq + (size_t) ch0 * 4 * st->prm.bq_stages, st->d_aud, st->d_aud, nch, frames, stream);
+    if (e != 0) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString ((cudaError_t) e));
+    q15_agc_kernel<<<nch, 128, 0, s_>>> (st->d_aud, reinterpret_cast<uint32_t *> (d_out), st->d_peaks[st->parity] + (size_t) ch0 * kWin,
+                                          st->d_peaks[st->parity ^ 1] + (size_t) ch0 * kWin, st->d_blkpk, frames, st->prm.agc_window, st->prm.agc_target, st->prm.agc_floor,
+                                          st->prm.agc_gmax_q15, st->d_rel, with_debug ? st->dbg_gain : nullptr);
+    cudaError_t ce = cudaGetLastError ();
+    if (ce == cudaSuccess && with_debug && st->dbg_audio) ce = cudaMemcpyAsync (st->dbg_audio, st->d_aud, (size_t) nch * frames * 2, cudaMemcpyDeviceToDevice, s_);
+    if (ce != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (ce));
+    ctx_count_launch (ctx, 2);
+    return SLB_OK;
+  };
   if (st->tc_ok && !legacy_only)
   {
     RxQ15TcLaunch L{};
     L.in = d_in; L.out = d_out;
     L.tail_in = st->d_tail[st->parity] + (size_t) ch0 * kTaps; L.tail_out = st->d_tail[st->parity ^ 1] + (size_t) ch0 * kTaps;
-    L.peaks_in = st->d_peaks[st->parity] + (size_t) ch0 * kWin; L.peaks_out = st->d_peaks[st->parity ^ 1] + (size_t) ch0 * kWin;
+    L.peaks_in = st->d_peaks[st->parity] + (size_t) ch0 * kWin; L.peaks_out = pk_out;
     L.planes = st->d_tc_planes; L.lsb = st->d_lsb + ch0;
-    L.audio_dbg = with_debug ? st->dbg_audio : nullptr; L.gain_dbg = with_debug ? st->dbg_gain : nullptr;
+    L.audio_dbg = aud_tap; L.gain_dbg = gain_tap;
     L.rel = st->prm.rel; L.channels = nch; L.frames = frames; L.window = st->prm.agc_window;
     L.target = st->prm.agc_target; L.floor_ = st->prm.agc_floor; L.gmax = st->prm.agc_gmax_q15;
     const int e = launch_rx_q15_tc (L, sm_count, stream);
     if (e != 0) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString ((cudaError_t) e));
     ctx_count_launch (ctx);
-    return SLB_OK;
+    return finish_bq ();
   }
   KParams P{};
   P.in = reinterpret_cast<const uint32_t *> (d_in); P.out = reinterpret_cast<uint32_t *> (d_out);
   P.tail_in = st->d_tail[st->parity] + (size_t) ch0 * kTaps; P.tail_out = st->d_tail[st->parity ^ 1] + (size_t) ch0 * kTaps;
-  P.peaks_in = st->d_peaks[st->parity] + (size_t) ch0 * kWin; P.peaks_out = st->d_peaks[st->parity ^ 1] + (size_t) ch0 * kWin;
+  P.peaks_in = st->d_peaks[st->parity] + (size_t) ch0 * kWin; P.peaks_out = pk_out;
   P.afrag = st->d_afrag; P.lsb = st->d_lsb + ch0;
-  P.audio_dbg = with_debug ? st->dbg_audio : nullptr; P.gain_dbg = with_debug ? st->dbg_gain : nullptr;
+  P.audio_dbg = aud_tap; P.gain_dbg = gain_tap;
   std::memcpy (P.rel, st->prm.rel, sizeof P.rel);
   P.channels = nch; P.frames = frames; P.blocks = frames / kBlk; P.groups = (nch + 7) / 8; P.window = st->prm.agc_window;
   P.target = st->prm.agc_target; P.floor_ = st->prm.agc_floor; P.gmax = st->prm.agc_gmax_q15;
@@ -478,7 +567,7 @@ int rxq15_launch (slb_ctx *ctx, RxQ15State *st, const int16_t *d_in, int16_t *d_
   cudaError_t e = cudaGetLastError ();
   if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));
   ctx_count_launch (ctx);
-  return SLB_OK;
+  return finish_bq ();
 }
 void rxq15_advance (RxQ15State *st) { st->parity ^= 1; }
 // per-channel cadence: channels [ch0, ch0 + nch) sat this call out — their carried state moves to the buffers the next call reads
@@ -492,13 +581,14 @@ int rxq15_carry_idle (RxQ15State *st, uint32_t ch0, uint32_t nch, void *stream)
   return (int) e;
 }
 
-size_t rxq15_state_bytes (const RxQ15State *st) { return (size_t) st->channels * (kTaps * 4 + kWin * 2 + 1); }
+size_t rxq15_state_bytes (const RxQ15State *st) { return (size_t) st->channels * (kTaps * 4 + kWin * 2 + 1 + 16 * 2); }
 int rxq15_state_save (RxQ15State *st, char *dst)
 {
   const size_t C = st->channels;
   if (cudaMemcpy (dst, st->d_tail[st->parity], C * kTaps * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
   if (cudaMemcpy (dst + C * kTaps * 4, st->d_peaks[st->parity], C * kWin * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
   if (cudaMemcpy (dst + C * (kTaps * 4 + kWin * 2), st->d_lsb, C, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  if (cudaMemcpy (dst + C * (kTaps * 4 + kWin * 2 + 1), st->d_bq, C * 16 * 2, cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
   return 0;
 }
 int rxq15_state_load (RxQ15State *st, const char *src)
@@ -507,6 +597,7 @@ int rxq15_state_load (RxQ15State *st, const char *src)
   if (cudaMemcpy (st->d_tail[st->parity], src, C * kTaps * 4, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
   if (cudaMemcpy (st->d_peaks[st->parity], src + C * kTaps * 4, C * kWin * 2, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
   if (cudaMemcpy (st->d_lsb, src + C * (kTaps * 4 + kWin * 2), C, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+  if (cudaMemcpy (st->d_bq, src + C * (kTaps * 4 + kWin * 2 + 1), C * 16 * 2, cudaMemcpyHostToDevice) != cudaSuccess) return 1;
   return 0;
 }
 

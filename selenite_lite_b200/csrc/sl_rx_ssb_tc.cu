@@ -14,7 +14,7 @@
 // of one float32 epsilon of the INPUT level like the oracle's own FFT noise (tolerances: DESIGN.md §3.5).
 //
 //   MMA shape: M = 128 rows = 8 channels (the 8 rows of a core matrix) x 16 consecutive firmware blocks (row groups),
-//   N = 160 = 52 outputs of a block (48 audio + 4 end-state) x 3 digits + 4 rows of padding, K = 32 bytes = 16 frames (I, Q bytes) per
+//   N = 208 (high data byte: 52 outputs of a block = 48 audio + 4 end-state, x 4 map digits) or 160 (low data byte: the top 3 digits + 4 rows), K = 32 bytes = 16 frames (I, Q bytes) per
 //   instruction, 11 K-steps cover the 128 + 48 frame window. The A operand is the byte plane of the channel group's samples,
 //   ONCE: row group q is the same plane 48 frames (6 sixteen-byte chunks) further on, so the descriptor's row-group stride
 //   (SBO = 768 B) makes the 16 row groups alias one contiguous buffer — no Toeplitz expansion of the data, only of the
@@ -48,9 +48,11 @@ constexpr int kChunksHist = kHist / 8;   // 16
 constexpr int kChunksNew = kSuper / 8;   // 96
 constexpr int kPlaneBytes = (kChunksHist + kChunksNew) * kChunkBytes;   // 14336
 constexpr int kKSteps = 11;              // (128 + 48) frames * 2 bytes / 32
-constexpr int kBStep = kTcRowGroups * 256; // B bytes per K-step: 20 row groups (3 digits x 52 rows: 48 audio + 4 state; 4 rows of padding) x 2 chunks x 128 B
+constexpr int kBStep = kTcRowGroups * 256; // B bytes per K-step: 26 row groups (4 digits x 52 rows: 48 audio + 4 state) x 2 chunks x 128 B
 constexpr int kDig = kTcDigit;           // accumulator columns per digit weight (52)
-constexpr int kN = kTcRowGroups * 8;     // 160 = the N of every MMA
+constexpr int kNhi = kTcRowGroups * 8;   // 208 = N of the xh MMAs: the high data byte meets all four digits of the 32-bit map
+constexpr int kN = 160;                  // N of the xl MMAs: the low data byte meets the top three digits (3 x 52 rows + 4: a multiple of 16; the
+                                         // four extra rows are the first rows of the lowest digit and land in columns 208..211, which nobody reads)
 constexpr int kRawRow = kSuper * 4 + 16; // raw stage row (one channel), padded: conflict-free 16-byte reads across channels
 constexpr int kHistRow = kHist * 4 + 16;
 #ifndef SL_TC_SETS
@@ -81,6 +83,8 @@ constexpr int kHistRow = kHist * 4 + 16;
 #define SL_TC_STHINT ".L1::no_allocate"   /* measured: plain 366, .cg 371, .cs 376, .L1::no_allocate 408 Gsamples/s */
 #endif
 constexpr bool kPair = SL_TC_PAIR != 0;
+static_assert (!SL_TC_PAIR, "the CTA-pair variant (tcgen05.mma.cta_group::2, measured slower: 315 vs 403 Gsamples/s at 1024 channels, 370 vs 445 at 8192, "
+                            "gpurun_out/s4_*) predates the 32-bit map: its split of the map rows between the two CTAs assumes one N for both data bytes");
 constexpr int kMmaUnroll = SL_TC_MMA_UNROLL;
 constexpr int kSets = SL_TC_SETS;                 // epilogue warp sets (warpgroups), taking supertiles in turn
 constexpr int kRawStages = SL_TC_RAWSTAGES;            // raw stages: a bulk copy takes ~4400 clocks to land (measured), a supertile ~3000
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
     // The whole warp walks the loop converged and ONE elected lane issues: with `if (lane == 0)` around the loop the
     // compiler cannot keep descriptors in uniform registers and wraps every tcgen05.mma in a vote / broadcast loop —
     // measured 128 clocks of issue per MMA against 116 of execution (N = 144).
-    constexpr uint32_t id_ss = kPair ? umma_idesc_pair (kN, 1, 1) : umma_idesc (kN, 1, 1), id_us = kPair ? umma_idesc_pair (kN, 0, 1) : umma_idesc (kN, 0, 1);
+    constexpr uint32_t id_ss = kPair ? umma_idesc_pair (kNhi, 1, 1) : umma_idesc (kNhi, 1, 1), id_us = kPair ? umma_idesc_pair (kN, 0, 1) : umma_idesc (kN, 0, 1);
     const uint32_t aBase = smem_u32 (sA), bBase = smem_u32 (sB);
     // constant upper halves of the descriptors: LBO = 128 (A and B), SBO = 768 (A, aliased row groups) / 256 (B), version 1
     constexpr uint64_t kDescA = ((uint64_t) (kChunkBytes >> 4) << 16) | ((uint64_t) ((6 * kChunkBytes) >> 4) << 32) | (1ull << 46);
@@ -479,8 +483,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4), b0 = bBase >> 4;
         if (elect_one ())
         {
-          // accumulator columns: [0,52) weight 2^24 = xh h2, [52,104) 2^16 = xh h1 + xl h2, [104,156) 2^8 = xh h0 + xl h1, [156,208) 1 = xl h0;
-          // inside each group of 52: 48 audio outputs, 4 end-state outputs. Both planes meet the SAME operand [h2|h1|h0] (N = 160,
+          // the map is 32 bits wide, h = h3 2^24 + h2 2^16 + h1 2^8 + h0 (balanced digits). Accumulator columns, in units of the 2^8 class:
+          // [0,52) weight 2^24 = xh h3, [52,104) 2^16 = xh h2 + xl h3, [104,156) 2^8 = xh h1 + xl h2, [156,208) 1 = xh h0 + xl h1; the class
+          // below (xl h0, 2^-32 of full scale) is not computed. (Round 1's 24-bit map missed the 1e-5 bar by 1.1 .. 2.0 x on outputs dominated by a
+          // REJECTED tone, for every mode: its quantisation error scales with the input. The fourth digit for the high data byte costs 24 clocks
+          // per xh MMA and removes the special bar that case needed.)
+          // inside each group of 52: 48 audio outputs, 4 end-state outputs. Both planes meet the SAME operand [h3|h2|h1|h0] (xh: N = 208, xl: the first 160 rows,
           // rows 156..159 zero), xl one digit to the right of xh. The first xl MMA starts columns [52,212) afresh; columns [0,52)
           // were zeroed by the epilogue set that drained the buffer (N must be a multiple of 16: there is no MMA that could
           // start exactly these 52 columns), so every xh MMA accumulates.

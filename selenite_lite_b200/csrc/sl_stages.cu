@@ -610,6 +610,18 @@ int slb_st_cfft_q31 (slb_ctx *ctx, int32_t *data, uint32_t N, uint32_t count, in
 int slb_design_twiddle_q15 (uint32_t N, int16_t *out) { if (!out || N < 16 || N > 4096 || (N & (N - 1))) return SLB_ERR_ARG; std::memcpy (out, fft_twiddle_q15 (N), (size_t) 3 * N / 4 * 2 * sizeof (int16_t)); return SLB_OK; }
 int slb_design_twiddle_q31 (uint32_t N, int32_t *out) { if (!out || N < 16 || N > 4096 || (N & (N - 1))) return SLB_ERR_ARG; std::memcpy (out, fft_twiddle_q31 (N), (size_t) 3 * N / 4 * 2 * sizeof (int32_t)); return SLB_OK; }
 
+}  // extern "C"
+namespace sl {
+// arm_biquad_cascade_df1_q15 on [channels][n] for the RX-SSB-q15 chain's optional audio filter (sl_rx_ssb_q15.cu)
+int launch_biquad_df1_q15 (const int16_t *coeffs6, uint32_t ns, int32_t postshift, int16_t *d_state, const int16_t *d_src, int16_t *d_dst, uint32_t channels, uint32_t n, void *stream)
+{
+  if (ns == 0 || ns > (uint32_t) kMaxSt) return (int) cudaErrorInvalidValue;
+  BqCoefQ15 K; K.ns = (int) ns; K.shift = 15 - postshift; std::memcpy (K.c, coeffs6, 6 * ns * sizeof (int16_t));
+  biquad_df1_q15_kernel<<<(channels + 63) / 64, 64, 0, (cudaStream_t) stream>>> (K, d_state, d_src, d_dst, channels, n);
+  return (int) cudaGetLastError ();
+}
+}  // namespace sl
+extern "C" {
 // ---- normalised LMS. coeffs: device [channels][ntaps] (every channel adapts its own), state: device [channels][ntaps + 1] =
 // the ntaps - 1 previous samples oldest first (the head of the CMSIS state buffer), then energy and x0 of the instance; both in place
 int slb_st_lms_norm_f32 (slb_ctx *ctx, float *coeffs, uint32_t ntaps, float mu, float *state, const float *src, const float *ref,

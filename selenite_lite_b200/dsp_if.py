@@ -65,7 +65,8 @@ def default_rx_q15_params(fs=48000):
 def q15_params_to_dict(p, lsb=0):
     return dict(ntaps=p.ntaps, agc_block=p.agc_block, agc_window=p.agc_window, lsb=int(lsb),
                 taps_i=np.array(p.taps_i[:], np.int16), taps_q=np.array(p.taps_q[:], np.int16), rel=np.array(p.rel[:], np.int16),
-                agc_target=p.agc_target, agc_floor=p.agc_floor, agc_gmax_q15=p.agc_gmax_q15)
+                agc_target=p.agc_target, agc_floor=p.agc_floor, agc_gmax_q15=p.agc_gmax_q15,
+                bq_stages=p.bq_stages, bq_postshift=p.bq_postshift, bq_coeffs=np.array(p.bq_coeffs[:], np.int16))
 
 
 def default_mask(fs=48000, fft_len=512, mode=MODE_USB):

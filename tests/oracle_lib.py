@@ -58,11 +58,12 @@ class ChanState(C.Structure):
 class RxQ15Params(C.Structure):
     _fields_ = [("ntaps", u32), ("agc_block", u32), ("agc_window", u32), ("lsb", u32),
                 ("taps_i", C.c_int16 * 64), ("taps_q", C.c_int16 * 64), ("rel", C.c_int16 * 32),
-                ("agc_target", C.c_int16), ("agc_floor", C.c_int16), ("agc_gmax_q15", u32)]
+                ("agc_target", C.c_int16), ("agc_floor", C.c_int16), ("agc_gmax_q15", u32),
+                ("bq_stages", u32), ("bq_postshift", i32), ("bq_coeffs", C.c_int16 * 24)]
 
 
 class RxQ15State(C.Structure):
-    _fields_ = [("fir_i", C.c_int16 * (64 + 192)), ("fir_q", C.c_int16 * (64 + 192)), ("peaks", C.c_int16 * 32)]
+    _fields_ = [("fir_i", C.c_int16 * (64 + 192)), ("fir_q", C.c_int16 * (64 + 192)), ("peaks", C.c_int16 * 32), ("bq", C.c_int16 * 16)]
 
 
 def build_oracles(want_ref=True):
@@ -327,6 +328,9 @@ class Oracle:
         for k in range(32):
             p.rel[k] = int(prm["rel"][k])
         p.agc_target, p.agc_floor, p.agc_gmax_q15 = int(prm["agc_target"]), int(prm["agc_floor"]), int(prm["agc_gmax_q15"])
+        p.bq_stages, p.bq_postshift = int(prm.get("bq_stages", 0)), int(prm.get("bq_postshift", 0))
+        for k in range(6 * p.bq_stages):
+            p.bq_coeffs[k] = int(prm["bq_coeffs"][k])
         st = state if state is not None else RxQ15State()
         x = np.ascontiguousarray(in_iq, np.int16).reshape(-1)
         frames = x.size // 2

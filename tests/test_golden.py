@@ -13,7 +13,7 @@ def rx_params(g, name):
                 agc_decay=g["rx_agc"][1], agc_floor=g["rx_agc"][2], agc_gmax=g["rx_agc"][3], mask=g["rx_%s_mask" % name])
 
 
-def audio_tolerance(ref_audio, block=384):
+def audio_tolerance(ref_audio, block=int(os.environ.get("SLB_TOL_BLOCK", "384"))):
     """1e-5 relative per sample, made well-defined at zero crossings: 1e-5 * max(|ref[n]|, rms of ref over
     the 384-frame super-block holding n). The super-block is one overlap-save frame: float32 FFT rounding noise scales
     with the energy of the whole frame, so a quieter stretch inside a loud frame (filter start-up) cannot be held to

@@ -196,3 +196,65 @@ def test_host_path_cut_into_time_slices_is_bit_exact():
         del os.environ["SELENITE_B200_SLICE_BYTES"]
     assert np.array_equal(y_host, y_dev)
     assert bytes(d_host.state_save()) == bytes(d_dev.state_save())
+
+
+def _q15_audio_biquad():
+    """Two df1 sections in q15, postShift 1: a 150 Hz high-pass and a 2.6 kHz low-pass (arm_biquad_cascade_df1_init_q15 layout
+    {b0, 0, b1, b2, a1, a2}, feedback signs as CMSIS stores them)."""
+    from scipy import signal
+    secs = []
+    for kind, fc in (("highpass", 150.0), ("lowpass", 2600.0)):
+        b, a = signal.butter(2, fc, kind, fs=48000)
+        c = np.round(np.array([b[0], b[1], b[2], -a[1], -a[2]]) / 2 * 32768).astype(np.int64)
+        secs += [c[0], 0, c[1], c[2], c[3], c[4]]
+    return np.clip(np.array(secs), -32768, 32767).astype(np.int16), 1
+
+
+@pytest.mark.parametrize("legacy", [False, True])
+def test_optional_integer_biquad_stage(best_oracle, rng, legacy, monkeypatch):
+    """SURVEY Appendix B's arm_biquad_cascade_df1_q15 between mixer and AGC, switched on through the chain parameters: the chain then
+    runs as three kernels (fused FIR + mixer, the channel-parallel integer biquad, AGC + scale) and stays BIT-EXACT — filtered audio,
+    gain words, output, over calls of ragged length (carried filter state and peak window), through the 1 ms firmware API and a
+    checkpoint, for both FIR kernels; hot input makes the biquad's own saturation fire."""
+    if legacy:
+        monkeypatch.setenv("SELENITE_B200_Q15_PATH", "legacy")
+    C, T = 11, 48 * 90
+    x = slb.synth_iq(C, T)
+    x[3] = np.clip(x[3].astype(np.int32) * 5, -32768, 32767).astype(np.int16)          # saturating channel
+    coeffs, ps = _q15_audio_biquad()
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    p = d.rx_q15_params(); p.bq_stages, p.bq_postshift = 2, ps
+    for k in range(12):
+        p.bq_coeffs[k] = int(coeffs[k])
+    d.set_rx_q15_params(p)
+    modes = [slb.MODE_USB, slb.MODE_LSB, slb.MODE_CW]
+    for c in range(C):
+        d.DSP_Set_Mode(modes[c % 3], channel=c)
+    outs, auds, gains = [], [], []
+    for a, b in ((0, 48 * 7), (48 * 7, 48 * 40), (48 * 40, T)):                      # ragged cuts: filter state and peak window carry
+        y, au, g = run_gpu(d, np.ascontiguousarray(x[:, a:b])); outs.append(y); auds.append(au); gains.append(g)
+    y, au, g = np.concatenate(outs, 1), np.concatenate(auds, 1), np.concatenate(gains, 1)
+    for c in range(C):
+        prm = d.oracle_params(modes[c % 3])
+        assert prm["bq_stages"] == 2
+        exp, a_, g_, _ = best_oracle.rx_ssb_q15(prm, x[c])
+        assert np.array_equal(au[c], a_), (c, int(np.argmax(au[c] != a_)))
+        assert np.array_equal(g[c], g_), c
+        assert np.array_equal(y[c], exp), c
+    # the filter does something: 50 Hz hum that the FIR pair lets through is attenuated in the filtered audio
+    plain = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    _, au_plain, _ = run_gpu(plain, x)
+    assert not np.array_equal(au_plain[0], au[0])
+    # 1 ms API + checkpoint: the same stream block by block, saved and restored half way
+    e = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15); e.set_rx_q15_params(p)
+    for c in range(C):
+        e.DSP_Set_Mode(modes[c % 3], channel=c)
+    ring_in = []
+    for t in range(40):
+        if t == 20:
+            snap = e.state_save(); e = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15); e.set_rx_q15_params(p); e.state_load(snap)
+        e.DSP_In_Buff_Write(x[:, 48 * t:48 * t + 48].reshape(C, -1)); ring_in.append(e.DSP_In_Buff_Read(192))
+    f = slb.DspIf(C, chain=slb.CHAIN_PASS)                                            # the ring alone, fed with the oracle chain's output
+    for t in range(40):
+        f.DSP_In_Buff_Write(y[:, 48 * t:48 * t + 48].reshape(C, -1))
+        assert np.array_equal(f.DSP_In_Buff_Read(192), ring_in[t]), t

@@ -69,11 +69,15 @@ def test_kernel_choice_is_per_channel(best_oracle):
     own mask, AM channels by the FFT kernel, all in one call; a channel's result does not depend on its neighbours."""
     C, T = 41, 768 * 5
     modes = [slb.MODE_USB, slb.MODE_AM, slb.MODE_LSB, slb.MODE_CW, slb.MODE_USB, slb.MODE_DIG, slb.MODE_CWR, slb.MODE_PKT]
-    # a tone inside the pass band of the channel's own mode (an out-of-band tone leaves an output 50 dB below the input,
-    # where the oracle's float32 FFT noise — relative to the INPUT — is larger than 1e-5 of the output, DESIGN.md §3.5)
+    # most channels get a tone inside the pass band of their own mode, every fifth one a tone its mode REJECTS (the other sideband):
+    # the same plain 1e-5 bar holds for both (test_output_dominated_by_a_rejected_tone)
     f_in = {slb.MODE_USB: 1000.0, slb.MODE_LSB: -1200.0, slb.MODE_CW: 700.0, slb.MODE_CWR: -650.0, slb.MODE_DIG: 2000.0, slb.MODE_PKT: 1500.0, slb.MODE_AM: 150.0}
-    x = np.concatenate([slb.synth_iq(1, T, f0=abs(f_in[modes[c % len(modes)]]) + 3 * c, sideband=1 if f_in[modes[c % len(modes)]] > 0 else -1,
-                                     first_channel=c) for c in range(C)])
+    def tone_of(c):
+        f = f_in[modes[c % len(modes)]]
+        if c % 5 == 4 and modes[c % len(modes)] != slb.MODE_AM:
+            f = -f                                                        # out of band: the opposite sideband
+        return f
+    x = np.concatenate([slb.synth_iq(1, T, f0=abs(tone_of(c)) + 3 * c, sideband=1 if tone_of(c) > 0 else -1, first_channel=c) for c in range(C)])
     d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
     for c in range(C):
         d.DSP_Set_Mode(modes[c % len(modes)], channel=c)

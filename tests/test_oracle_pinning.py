@@ -179,3 +179,21 @@ def test_sin_cos_table(ref, port, rng):
     # (the last element also pins a quirk: x = -2*pi maps to table index 512 & 0x1ff = 0 with fract = 512 -> 6.283)
     assert ref.sin_f32(x)[-1] > 6.0
     assert 1e-6 < np.max(np.abs(ref.sin_f32(x[:-1]) - np.sin(x[:-1].astype(np.float64)))) < 4e-5
+
+
+def test_q15_chain_with_the_optional_biquad_bit_exact(ref, port, rng):
+    """oracle/chains.inc.c rx_ssb_q15 with arm_biquad_cascade_df1_q15 between mixer and AGC: reference build vs port."""
+    import selenite_lite_b200 as slb
+    from test_golden import GOLD, q15_params
+    import os
+    g = np.load(os.path.join(GOLD, "rx_ssb_q15.npz"))
+    prm = q15_params(g, 0)
+    from scipy import signal
+    b, a = signal.butter(2, 2600.0, "lowpass", fs=48000)
+    c = np.round(np.array([b[0], b[1], b[2], -a[1], -a[2]]) / 2 * 32768).astype(np.int16)
+    prm.update(bq_stages=1, bq_postshift=1, bq_coeffs=np.array([c[0], 0, c[1], c[2], c[3], c[4]], np.int16))
+    x = slb.synth_iq(1, 48 * 60)[0]
+    o_r, a_r, g_r, _ = ref.rx_ssb_q15(prm, x); o_p, a_p, g_p, _ = port.rx_ssb_q15(prm, x)
+    assert np.array_equal(o_r, o_p) and np.array_equal(a_r, a_p) and np.array_equal(g_r, g_p)
+    prm0 = q15_params(g, 0)
+    assert not np.array_equal(ref.rx_ssb_q15(prm0, x)[1], a_r)
