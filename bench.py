@@ -290,7 +290,7 @@ def run_ours(args):
     achieved = C * T * BYTES_PER_SAMPLE / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "kernel": "rx_ssb_tc_kernel (sl_rx_ssb_tc.cu: tcgen05.mma kind::i8 FIR + biquad/AGC epilogue)", "algorithmic_bytes_per_launch": C * T * BYTES_PER_SAMPLE,
-                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f; the kernel is bound by the SM's L1 / shared-memory data pipe (tensor-core operand fetch + epilogue and converter traffic, ncu: 82 %% busy), not by HBM (DESIGN.md §4A)" % (achieved / 8000.0)}
+                "note": "1 launch per step; frac vs the nominal 8 TB/s = %.3f; the kernel is bound by the SM's L1 / shared-memory data pipe (tensor-core operand reads ~50 %% of its cycles + LSU wavefronts of converters, epilogue and output stores ~40 %%: profiles/r02_summary.md), not by HBM (DESIGN.md §4A)" % (achieved / 8000.0)}
 
     # optional gather of the decoded audio over NCCL / NVLink (configs[4]), timed on its own AFTER the timed compute
     gather = None
@@ -404,7 +404,7 @@ def run_ours(args):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload, "channels_per_gpu": C, "channels_total": C * world, "frames_per_step": T, "fs": FS, "chain": "rx_ssb_f32",
-                   "arithmetic": "filter + biquad block response: int8 x int8 -> int32 digit products of int16 samples and a 24-bit-quantised map (exact for that map); state chain, AGC, pack: float32",
+                   "arithmetic": "filter + biquad block response: int8 x int8 -> int32 digit products of int16 samples and a 32-bit-quantised map (exact for that map; the high data byte meets all four map digits); state chain, AGC, pack: float32",
                    "l2_policy": "inputs larger than L2 (%.1f GB touched per step per GPU vs 126 MB L2)" % (C * T * 8 / 1e9), "parallelism": "channels sharded, no collective"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gather": gather, "gpu_launches": launches, "clocks": clocks, "other_chains": other}))
 
