@@ -39,7 +39,11 @@ constexpr int kKSteps = 6;               // ceil ((128 + 48) / 32)
 constexpr int kBStep = 18 * 256;         // B bytes per K-step and rail: 18 row groups (3 digits x 48) x 2 chunks x 128 B
 constexpr int kRawRow = kSuper * 4 + 16;
 constexpr int kHistRow = kHist * 4 + 16;
-constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = 2;
+#ifndef SL_TXTC_RAWSTAGES
+#define SL_TXTC_RAWSTAGES 3
+#endif
+constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = SL_TXTC_RAWSTAGES;   // raw stages: a bulk copy lands ~4000 clocks after it is issued
+constexpr int kGroups = kChunksNew / 4;  // groups of 4 chunks (64 samples) of a supertile: 12; converter warp cw takes the groups t = cw (mod kConvWarps)
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);
 constexpr int kTmemCols = 512;           // I accumulators in columns [0,192), Q in [192,384)
@@ -53,7 +57,7 @@ struct Smem
   static constexpr size_t pk = hist + kRawStages * kJ * kHistRow;       // [sets][16][8] floats
   static constexpr size_t carry_e = pk + kSets * kQ * kJ * 4;           // [2][8] floats
   static constexpr size_t bars = carry_e + 2 * kJ * 4;
-  static constexpr int n_bars = 16;
+  static constexpr int n_bars = 24;
   static constexpr size_t tmem_ptr = bars + n_bars * 8;
   static constexpr size_t bytes = tmem_ptr + 16;
 };
@@ -92,19 +96,25 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
   unsigned char *sA = smem + Smem::a, *sB = smem + Smem::b, *sRaw = smem + Smem::raw, *sHist = smem + Smem::hist;
   float *sPk = reinterpret_cast<float *> (smem + Smem::pk), *sCarryE = reinterpret_cast<float *> (smem + Smem::carry_e);
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
-  uint64_t *raw_full = bars, *raw_empty = bars + 2, *a_full = bars + 4, *a_empty = bars + 6, *t_empty = bars + 8;
-  uint64_t *e_bar = bars + 9, *b_full = bars + 11, *drain = bars + 12, *t_full = bars + 13;       // t_full: two slots (one accumulator buffer)
+  uint64_t *raw_full = bars, *raw_empty = bars + 4, *a_full = bars + 8, *a_empty = bars + 10, *t_empty = bars + 12;
+  uint64_t *e_bar = bars + 13, *b_full = bars + 15, *drain = bars + 16, *t_full = bars + 17;      // t_full: two slots (one accumulator buffer)
+  // the two rails have their own hand-over (rail Q: t_full_q / t_empty_q): the epilogue frees the I columns while the Q MMAs still
+  // run, so the next supertile's I MMAs start at once and the tensor pipe never waits for a whole accumulator drain
+  uint64_t *t_full_q = bars + 19, *t_empty_q = bars + 21;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *> (smem + Smem::tmem_ptr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0)
   {
+    static_assert (kRawStages >= 2 && kRawStages <= 4, "barrier layout");
+    for (int i = 0; i < kRawStages; i++) { mbar_init (raw_full + i, 1); mbar_init (raw_empty + i, kConvWarps); }
     for (int i = 0; i < 2; i++)
     {
-      mbar_init (raw_full + i, 1); mbar_init (raw_empty + i, kConvWarps); mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
+      mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
       mbar_init (e_bar + i, kJ); mbar_init (t_full + i, 1);
     }
     mbar_init (t_empty, 4); mbar_init (b_full, 1); mbar_init (drain, 1);
+    mbar_init (t_full_q, 1); mbar_init (t_full_q + 1, 1); mbar_init (t_empty_q, 4);
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // the pad chunk of every plane is read (times zero taps) but never written by the converters: keep it finite
@@ -125,27 +135,33 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
   if (warp == kProdWarp)
   {
     // ======================================= bulk-copy producer =======================================
-    if (lane == 0)
+    // lane j < 8 owns row j of the group: its channel index is read once per group, its bulk copy issued per supertile (as sl_rx_ssb_tc.cu)
     {
       unsigned kk = 0;
       for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
+      {
+        const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
+        const uint32_t c = P.chan[gs + min ((uint32_t) (lane & 7), nv - 1u)];
+        const uint32_t *src = P.in + (size_t) c * P.frames;
         for (uint32_t k = 0; k < supers; k++, kk++)
         {
-          const int rb = kk & 1;
+          const int rb = kk % kRawStages;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
-          mbar_wait (raw_empty + rb, ((kk >> 1) & 1) ^ 1);
-          mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
-          const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
-#pragma unroll 1
-          for (int j = 0; j < kJ; j++)
+          if (lane == 0)
           {
-            const uint32_t c = P.chan[gs + min ((uint32_t) j, nv - 1u)];
-            bulk_g2s (sRaw + (rb * kJ + j) * kRawRow, P.in + (size_t) c * P.frames + (size_t) k * kSuper, nfr * 4u, raw_full + rb);
-            if (k == 0) bulk_g2s (sHist + (rb * kJ + j) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
+            mbar_wait (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
+            mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           }
+          __syncwarp ();
+          if (lane < kJ)
+          {
+            bulk_g2s (sRaw + (rb * kJ + lane) * kRawRow, src + (size_t) k * kSuper, nfr * 4u, raw_full + rb);
+            if (k == 0) bulk_g2s (sHist + (rb * kJ + lane) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
+          }
+          __syncwarp ();
         }
+      }
     }
-    __syncwarp ();
   }
   else if (warp >= kEpiWarps && warp < kEpiWarps + kConvWarps)
   {
@@ -158,10 +174,10 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
       const uint32_t nvalid = P.ginfo[g] >> 8, gs = P.gstart[g];
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
-        const int rb = kk & 1, ab = kk & 1;
+        const int rb = kk % kRawStages, ab = kk & 1;
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
         unsigned char *Ahi = sA + ab * 2 * kPlaneBytes;
-        mbar_wait (raw_full + rb, (kk >> 1) & 1);
+        mbar_wait (raw_full + rb, (kk / kRawStages) & 1);
         mbar_wait (a_empty + ab, ((kk >> 1) & 1) ^ 1);
         if (cw == 0 && k == 0)
         {
@@ -177,34 +193,37 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
             *reinterpret_cast<uint4 *> (dst + kPlaneBytes + t * 4 * kChunkBytes) = make_uint4 (lo4 (v0), lo4 (v1), lo4 (v2), lo4 (v3));
           }
         }
-        if (cw == kConvWarps - 1 && k != 0)
+        if (k != 0)
         {
-          // history = the last 8 chunks of the previous supertile's planes (the other buffer; this warp wrote them)
-          const unsigned char *prev = sA + (ab ^ 1) * 2 * kPlaneBytes + kChunksNew * kChunkBytes;
+          // history = the last 8 chunks of the previous supertile's planes (the other buffer): every warp moves the group it wrote itself
 #pragma unroll
-          for (int i = 0; i < 2 * kChunksHist * kJ / 32; i++)
-          {
-            const int e = lane + 32 * i, plane = e >> 6, o = (e & 63) * 16;
-            *reinterpret_cast<uint4 *> (Ahi + plane * kPlaneBytes + o) = *reinterpret_cast<const uint4 *> (prev + plane * kPlaneBytes + o);
-          }
+          for (int hg = 0; hg < kChunksHist / 4; hg++)
+            if ((kGroups - kChunksHist / 4 + hg) % kConvWarps == cw)
+            {
+              const unsigned char *prev = sA + (ab ^ 1) * 2 * kPlaneBytes + (kChunksNew + 4 * hg) * kChunkBytes + lane * 16;
+              unsigned char *cur = Ahi + 4 * hg * kChunkBytes + lane * 16;
+              const uint4 v0 = *reinterpret_cast<const uint4 *> (prev), v1 = *reinterpret_cast<const uint4 *> (prev + kPlaneBytes);
+              *reinterpret_cast<uint4 *> (cur) = v0; *reinterpret_cast<uint4 *> (cur + kPlaneBytes) = v1;
+            }
         }
         {
-          // this warp's share of the new chunks: t in [cw * per, (cw + 1) * per), chunk = c4 + 4 t
+          // this warp's share of the new chunks: groups t = cw + kConvWarps i (4 chunks = 64 samples each), chunk = c4 + 4 t
           const int per = (int) (nfr / 64) / kConvWarps;                          // 6 (3 for the half supertile at the end of a stream)
-          const unsigned char *src = sRaw + (rb * kJ + j) * kRawRow + (c4 + 4 * cw * per) * 64;
-          unsigned char *dst = Ahi + (kChunksHist + c4 + 4 * cw * per) * kChunkBytes + j * 16;
+          const unsigned char *src = sRaw + (rb * kJ + j) * kRawRow + (c4 + 4 * cw) * 64;
+          unsigned char *dst = Ahi + (kChunksHist + c4 + 4 * cw) * kChunkBytes + j * 16;
+          constexpr int kS = kConvWarps * 256, kD = kConvWarps * 4 * kChunkBytes;
           for (int t0 = 0; t0 < per; t0 += 3)
           {
             uint4 v[12];
 #pragma unroll
             for (int t = 0; t < 3; t++)
 #pragma unroll
-              for (int u = 0; u < 4; u++) v[4 * t + u] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * 256 + u * 16);
+              for (int u = 0; u < 4; u++) v[4 * t + u] = *reinterpret_cast<const uint4 *> (src + (t0 + t) * kS + u * 16);
 #pragma unroll
             for (int t = 0; t < 3; t++)
             {
-              *reinterpret_cast<uint4 *> (dst + (t0 + t) * 4 * kChunkBytes) = make_uint4 (hi4 (v[4 * t]), hi4 (v[4 * t + 1]), hi4 (v[4 * t + 2]), hi4 (v[4 * t + 3]));
-              *reinterpret_cast<uint4 *> (dst + kPlaneBytes + (t0 + t) * 4 * kChunkBytes) = make_uint4 (lo4 (v[4 * t]), lo4 (v[4 * t + 1]), lo4 (v[4 * t + 2]), lo4 (v[4 * t + 3]));
+              *reinterpret_cast<uint4 *> (dst + (t0 + t) * kD) = make_uint4 (hi4 (v[4 * t]), hi4 (v[4 * t + 1]), hi4 (v[4 * t + 2]), hi4 (v[4 * t + 3]));
+              *reinterpret_cast<uint4 *> (dst + kPlaneBytes + (t0 + t) * kD) = make_uint4 (lo4 (v[4 * t]), lo4 (v[4 * t + 1]), lo4 (v[4 * t + 2]), lo4 (v[4 * t + 3]));
             }
           }
         }
@@ -254,13 +273,13 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
       {
         const int ab = kk & 1;
         mbar_wait (a_full + ab, (kk >> 1) & 1);
-        mbar_wait (t_empty, (kk & 1) ^ 1);                                     // the epilogue has read the accumulators of supertile kk - 1
-        tc_fence_after ();
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4);
-        if (elect_one ())
-        {
 #pragma unroll
-          for (int rail = 0; rail < 2; rail++)
+        for (int rail = 0; rail < 2; rail++)
+        {
+          mbar_wait (rail ? t_empty_q : t_empty, (kk & 1) ^ 1);                // the epilogue has read this rail's accumulators of supertile kk - 1
+          tc_fence_after ();
+          if (elect_one ())
           {
             // per rail: columns [0,48) weight 2^24 = mh h2, [48,96) 2^16 = mh h1 + ml h2, [96,144) 2^8 = mh h0 + ml h1, [144,192) 1 = ml h0
             const uint32_t d = tmem + 192u * rail, b0 = (bBase + rail * kKSteps * kBStep) >> 4;
@@ -274,11 +293,11 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
               umma_i8 (d, kDescA | (aHi + ao), kDescB | (b0 + bo), id_ss144, 1u);
               umma_i8 (d + 48, kDescA | (aLo + ao), kDescB | (b0 + bo), id_us144, 1u);
             }
+            umma_commit ((rail ? t_full_q : t_full) + (kk & 1));
+            if (rail) umma_commit (a_empty + ab);
           }
-          umma_commit (t_full + (kk & 1));
-          umma_commit (a_empty + ab);
+          __syncwarp ();
         }
-        __syncwarp ();
       }
     }
   }
@@ -301,11 +320,11 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
         const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
         const int nblk = (int) (nfr / kBlk);
         const bool last_q = q == nblk - 1;
-        mbar_wait (t_full + (kk & 1), (kk >> 1) & 1);
-        tc_fence_after ();
-        // ---- accumulators -> float I, Q
+        // ---- accumulators -> float I, Q: rail by rail, each rail's columns handed back to the MMA issuer as soon as they are in registers
         float zi[kBlk], zq[kBlk];
         const uint32_t taddr = tmem + ((uint32_t) (32 * w) << 16);
+        mbar_wait (t_full + (kk & 1), (kk >> 1) & 1);
+        tc_fence_after ();
 #pragma unroll
         for (int i = 0; i < kBlk / 8; i++)
         {
@@ -315,6 +334,16 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
 #pragma unroll
           for (int n = 0; n < 8; n++)
             zi[8 * i + n] = fmaf (__int2float_rn ((int) v0[n]), s24, fmaf (__int2float_rn ((int) v1[n]), s16, fmaf (__int2float_rn ((int) v2[n]), s8, __int2float_rn ((int) v3[n]) * s0)));
+        }
+        tc_fence_before ();
+        __syncwarp ();
+        if (lane == 0) mbar_arrive (t_empty);
+        mbar_wait (t_full_q + (kk & 1), (kk >> 1) & 1);
+        tc_fence_after ();
+#pragma unroll
+        for (int i = 0; i < kBlk / 8; i++)
+        {
+          uint32_t v0[8], v1[8], v2[8], v3[8];
           tmem_ld8 (taddr + 192 + 8 * i, v0); tmem_ld8 (taddr + 240 + 8 * i, v1); tmem_ld8 (taddr + 288 + 8 * i, v2); tmem_ld8 (taddr + 336 + 8 * i, v3);
           tmem_ld_wait ();
 #pragma unroll
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
         }
         tc_fence_before ();
         __syncwarp ();
-        if (lane == 0) mbar_arrive (t_empty);
+        if (lane == 0) mbar_arrive (t_empty_q);
         // ---- block peak of |I + jQ|: arm_cmplx_mag_f32.c:72 sqrt (re re + im im), each product rounded; sqrt is monotonic and
         //      correctly rounded, so max (sqrt) = sqrt (max)
         float m2 = 0.f;
