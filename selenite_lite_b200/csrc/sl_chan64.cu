@@ -155,6 +155,14 @@ __device__ __forceinline__ unsigned ld_relaxed (const unsigned *p)
   unsigned v; asm volatile ("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 __device__ __forceinline__ void st_release (unsigned *p, unsigned v) { asm volatile ("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_look (const unsigned long long *p)
+{
+  unsigned long long v; asm volatile ("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_look (unsigned long long *p, unsigned status, float v)
+{
+  asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long) status << 32) | (unsigned long long) __float_as_uint (v)) : "memory");
+}
 // named barriers (like the RX kernel): 1,2 = audio buffer 0/1 full; 3,4 = audio buffer 0/1 empty (all 160 threads take
 // part in each, one side syncs, the other arrives); 5 = the FFT warps among themselves; 6 = the AGC warps
 __device__ __forceinline__ void bar_sync (int id, int n) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -166,7 +174,8 @@ struct KParams
   const uint32_t *hist_in; uint32_t *hist_out;  // [S][7*64] raw frames carried between calls (ping-pong)
   const float *env_in; float *env_out;          // [S][64] carried envelope (ping-pong: a late tile may finish before an
                                                 // early one has read its carry-in)
-  float *agg, *incl; unsigned *status;          // look-back: [S][tiles][64], [S][tiles][64], [S][tiles]
+  unsigned long long *look;                     // look-back words [S][tiles][64]: status (0 = none, 1 = zero-start aggregate, 2 = inclusive) << 32 | float bits.
+                                                // One 8-byte word carries flag AND value, so a reader needs no fence and one round trip.
   const float *coef;                            // [64][8]: e_r[p] = h[64 p + 63 - r] / 32768
   const float2 *tw;                             // [8][8]: W_64^(k1*b)
   float *audio_dbg, *gain_dbg;                  // optional: [S][64][hops], [S][64][hops/3]
@@ -240,7 +249,11 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
       if (seq >= 2) bar_sync (3 + buf, kThreads);                    // the AGC warps have drained this audio buffer
 
       const int h_base = warp * kHopsPerWarp;                        // first hop of this warp inside the tile
+#ifdef SL_CHAN_ABLATE_FFT                                            // (profiling aid: the kernel without polyphase filter and FFTs)
+      if (false)
+#else
       if ((uint32_t) h_base < hops_here)
+#endif
       {
         // sliding windows: at hop m the oldest sample x_r[m-7] sits in slot (m+1)&7, the newest in slot m&7
         float w0r[kTaps], w0i[kTaps], w1r[kTaps], w1i[kTaps];
@@ -368,51 +381,44 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
 #pragma unroll
       for (int q = 0; q < kTileBlocks; q++) if (q < nblk) e0 = fmaxf (pkv[q], e0 * decay);
       const size_t slot = ((size_t) s * P.tiles + tile) * kBins + k;
-      __stcg (P.agg + slot, e0);
-      // publish: the CTA-scope barrier orders the 64 stores before thread 0's release at GPU scope (release is cumulative),
-      // so no per-thread __threadfence (MEMBAR.SC + L1 invalidate) is needed
-      bar_sync (6, kAgcThreads);
-      if (k == 0) st_release (P.status + (size_t) s * P.tiles + tile, 1u);
+      st_look (P.look + slot, 1u, e0);
 
-      // carry-in by look-back over the predecessors of this stream. The statuses of the last kLookBackMax tiles are
-      // polled TOGETHER and the values then fetched together, so a look-back costs two global round trips whatever its
-      // depth. Virtual tile -1 is the call's carried state (always inclusive).
+      // carry-in by look-back over the predecessors of this stream: the words of the last kLookBackMax tiles of this bin are
+      // fetched TOGETHER (one round trip whatever the depth) and re-fetched until the nearest inclusive one and every
+      // aggregate after it are there. Virtual tile -1 is the call's carried state (always inclusive).
       float env;
+#ifdef SL_CHAN_ABLATE_LOOKBACK                                       // (profiling aid: no carry-in from other CTAs — WRONG results, timing only)
+      env = 0.f;
+      if (false)
+#endif
       {
-        const unsigned *stp = P.status + (size_t) s * P.tiles;
+        const unsigned long long *lk = P.look + (size_t) s * P.tiles * kBins + k;
+        unsigned long long wd[kLookBackMax];
         int dstar;
         for (;;)
         {
-          unsigned st[kLookBackMax];
 #pragma unroll
-          for (int d = 0; d < kLookBackMax; d++) { const int j = (int) tile - 1 - d; st[d] = (j >= 0) ? ld_relaxed (stp + j) : 2u; }
+          for (int d = 0; d < kLookBackMax; d++) { const int j = (int) tile - 1 - d; wd[d] = (j >= 0) ? ld_look (lk + (size_t) j * kBins) : (2ull << 32); }
           dstar = -1;
           bool ok = true;
 #pragma unroll
-          for (int d = kLookBackMax - 1; d >= 0; d--) { if (st[d] >= 2u) dstar = d; }      // nearest inclusive predecessor
+          for (int d = kLookBackMax - 1; d >= 0; d--) { if ((unsigned) (wd[d] >> 32) >= 2u) dstar = d; }      // nearest inclusive predecessor
           if (dstar < 0) ok = false;
 #pragma unroll
-          for (int d = 0; d < kLookBackMax; d++) if (d < dstar && st[d] < 1u) ok = false;   // everything nearer has an aggregate
+          for (int d = 0; d < kLookBackMax; d++) if (d < dstar && (unsigned) (wd[d] >> 32) < 1u) ok = false;   // everything nearer has an aggregate
           if (ok) break;
-          __nanosleep (64);
-        }
-        asm volatile ("fence.acq_rel.gpu;" ::: "memory");
-        float val[kLookBackMax];
-#pragma unroll
-        for (int d = 0; d < kLookBackMax; d++)
-        {
-          const int j = (int) tile - 1 - d;
-          val[d] = 0.f;
-          if (d <= dstar)
-            val[d] = (j < 0) ? __ldcg (P.env_in + (size_t) s * kBins + k)
-                             : __ldcg ((d == dstar ? P.incl : P.agg) + ((size_t) s * P.tiles + j) * kBins + k);
+          __nanosleep (40);
         }
         // fold forward: env_end(i) = max(E0(i), decay^16(env_end(i-1))), every predecessor tile is a full one
         env = 0.f;
 #pragma unroll
         for (int d = kLookBackMax - 1; d >= 0; d--)
-          if (d == dstar) env = val[d];
-          else if (d < dstar) env = fmaxf (val[d], decay_n (env, decay, kTileBlocks));
+        {
+          const int j = (int) tile - 1 - d;
+          const float v = (j < 0) ? __ldcg (P.env_in + (size_t) s * kBins + k) : __uint_as_float ((unsigned) wd[d]);
+          if (d == dstar) env = v;
+          else if (d < dstar) env = fmaxf (v, decay_n (env, decay, kTileBlocks));
+        }
       }
       // the real walk (oracle order), gains per block
       float gain[kTileBlocks];
@@ -429,10 +435,8 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
           const float gq = P.target * rc;
           gain[q] = fminf (fmaf (rc, fmaf (-den, gq, P.target), gq), P.gmax);
         }
-      __stcg (P.incl + slot, env);
+      st_look (P.look + slot, 2u, env);
       if (tile == P.tiles - 1) __stcg (P.env_out + (size_t) s * kBins + k, env);
-      bar_sync (6, kAgcThreads);
-      if (k == 0) st_release (P.status + (size_t) s * P.tiles + tile, 2u);
 
       // scale (arm_scale_f32), pack (arm_float_to_q15), store channel-major: 12 samples = 3 float4 in, 3 uint4 out
       const size_t orow = ((size_t) s * kBins + k) * P.hops + (size_t) tile * kTileHops;
@@ -598,13 +602,12 @@ int chan64_launch (slb_ctx *ctx, Chan64State *st, const int16_t *d_in, int16_t *
   KParams P{};
   P.streams = ns; P.hops = frames / kBins; P.tiles = (P.hops + kTileHops - 1) / kTileHops;
   // look-back scratch of this launch (per stream group: concurrent launches of one context use disjoint regions)
-  const size_t per_stream = (size_t) P.tiles * (2 * kBins * 4 + 4);
+  const size_t per_stream = (size_t) P.tiles * kBins * 8;
   char *scr = static_cast<char *> (ctx_scratch (ctx, (size_t) st->streams * per_stream + 256));
   if (!scr) return SLB_ERR_CUDA;
   scr += (size_t) s0 * per_stream;
-  P.agg = reinterpret_cast<float *> (scr); P.incl = P.agg + (size_t) ns * P.tiles * kBins;
-  P.status = reinterpret_cast<unsigned *> (P.incl + (size_t) ns * P.tiles * kBins);
-  if (cudaMemsetAsync (P.status, 0, (size_t) ns * P.tiles * 4, stream) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "chan64: status reset failed");
+  P.look = reinterpret_cast<unsigned long long *> (scr);
+  if (cudaMemsetAsync (P.look, 0, (size_t) ns * P.tiles * kBins * 8, stream) != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, "chan64: look-back reset failed");
   P.in = reinterpret_cast<const uint32_t *> (d_in); P.out = reinterpret_cast<uint32_t *> (d_out);
   P.hist_in = st->d_hist[st->parity] + (size_t) s0 * kHistHops * kBins; P.hist_out = st->d_hist[st->parity ^ 1] + (size_t) s0 * kHistHops * kBins;
   P.env_in = st->d_env[st->parity] + (size_t) s0 * kBins; P.env_out = st->d_env[st->parity ^ 1] + (size_t) s0 * kBins;
