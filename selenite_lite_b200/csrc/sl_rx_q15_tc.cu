@@ -39,9 +39,12 @@ constexpr int kRawRow = kSuper * 4 + 16, kHistRow = kHist * 4 + 16;
                                            // all eight warps per supertile puts the sets in lockstep)
 #endif
 #ifndef SL_Q15TC_RAWSTAGES
-#define SL_Q15TC_RAWSTAGES 2
+#define SL_Q15TC_RAWSTAGES 4
 #endif
-constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = SL_Q15TC_RAWSTAGES;
+#ifndef SL_Q15TC_MMA_UNROLL
+#define SL_Q15TC_MMA_UNROLL 1                   /* rolled: 489 vs 470 Gsamples/s (the unrolled issue loop costs instruction fetch: gcc requests at 78 % of peak) */
+#endif
+constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = SL_Q15TC_RAWSTAGES, kMmaUnroll = SL_Q15TC_MMA_UNROLL;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1, kThreads = 32 * (kProdWarp + 1);
 constexpr int kTmemCols = 512;           // xh products in columns [0,192), xl products in [192,384)
 
@@ -73,7 +76,7 @@ struct KParams
 
 #include "sl_tc_common.cuh"
 
-// (A/B: cvt.sat.s16.s32 is one instruction but runs on the conversion pipe: 403 vs 467 Gsamples/s; a third raw stage: no change)
+// (A/B: cvt.sat.s16.s32 is one instruction but runs on the conversion pipe: 403 vs 467 Gsamples/s. Raw stages with the MMA issue loop rolled: 2 -> 475, 3 -> 486, 4 -> 489 Gsamples/s; with it unrolled 468 .. 470 whatever the stages)
 #ifdef SL_Q15TC_CVTSAT
 __device__ __forceinline__ int sat16 (int v) { short r; asm ("cvt.sat.s16.s32 %0, %1;" : "=h"(r) : "r"(v)); return (int) r; }
 #else
@@ -86,8 +89,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
   unsigned char *sA = smem + Smem::a, *sB = smem + Smem::b, *sRaw = smem + Smem::raw, *sHist = smem + Smem::hist;
   int *sPk = reinterpret_cast<int *> (smem + Smem::pk), *sPkC = reinterpret_cast<int *> (smem + Smem::pkc);
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
-  uint64_t *raw_full = bars, *raw_empty = bars + 3, *a_full = bars + 6, *a_empty = bars + 8, *t_empty = bars + 10;
-  uint64_t *p_bar = bars + 11, *b_full = bars + 13, *t_full = bars + 14;
+  static_assert (kRawStages >= 2 && kRawStages <= 4, "barrier layout");
+  uint64_t *raw_full = bars, *raw_empty = bars + 4, *a_full = bars + 8, *a_empty = bars + 10, *t_empty = bars + 12;
+  uint64_t *p_bar = bars + 13, *b_full = bars + 15, *t_full = bars + 16;
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *> (smem + Smem::tmem_ptr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4);
         if (elect_one ())
         {
-#pragma unroll
+#pragma unroll kMmaUnroll
           for (int ks = 0; ks < kKSteps; ks++)
           {
             const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStep) >> 4;

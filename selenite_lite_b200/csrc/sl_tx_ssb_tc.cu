@@ -39,8 +39,15 @@ constexpr int kKSteps = 6;               // ceil ((128 + 48) / 32)
 constexpr int kBStep = 18 * 256;         // B bytes per K-step and rail: 18 row groups (3 digits x 48) x 2 chunks x 128 B
 constexpr int kRawRow = kSuper * 4 + 16;
 constexpr int kHistRow = kHist * 4 + 16;
+#ifndef SL_TXTC_RAIL_UNROLL
+#define SL_TXTC_RAIL_UNROLL 1
+#endif
+#ifndef SL_TXTC_MMA_UNROLL
+#define SL_TXTC_MMA_UNROLL 1                 /* rolled MMA loops: the kernel's instruction fetch sat at 88 % of the GPC cache's request rate (icc hit 84.6 %) */
+#endif
+constexpr int kMmaUnroll = SL_TXTC_MMA_UNROLL, kRailUnroll = SL_TXTC_RAIL_UNROLL;
 #ifndef SL_TXTC_RAWSTAGES
-#define SL_TXTC_RAWSTAGES 3
+#define SL_TXTC_RAWSTAGES 4
 #endif
 constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = SL_TXTC_RAWSTAGES;   // raw stages: a bulk copy lands ~4000 clocks after it is issued
 constexpr int kGroups = kChunksNew / 4;  // groups of 4 chunks (64 samples) of a supertile: 12; converter warp cw takes the groups t = cw (mod kConvWarps)
@@ -274,7 +281,7 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
         const int ab = kk & 1;
         mbar_wait (a_full + ab, (kk >> 1) & 1);
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4);
-#pragma unroll
+#pragma unroll kRailUnroll
         for (int rail = 0; rail < 2; rail++)
         {
           mbar_wait (rail ? t_empty_q : t_empty, (kk & 1) ^ 1);                // the epilogue has read this rail's accumulators of supertile kk - 1
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
             umma_i8 (d, kDescA | aHi, kDescB | b0, id_ss48, 0u);
             umma_i8 (d + 48, kDescA | aLo, kDescB | b0, id_us144, 0u);
             umma_i8 (d + 48, kDescA | aHi, kDescB | (b0 + ((6 * 256) >> 4)), id_ss96, 1u);
-#pragma unroll
+#pragma unroll kMmaUnroll
             for (int ks = 1; ks < kKSteps; ks++)
             {
               const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStep) >> 4;
