@@ -144,7 +144,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
         {
           const int rb = kk & 1;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
-          mbar_wait (raw_empty + rb, ((kk >> 1) & 1) ^ 1);
+          mbar_wait_guarded (raw_empty + rb, ((kk >> 1) & 1) ^ 1);
           mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
 #pragma unroll 1
@@ -261,8 +261,8 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         const int ab = kk & 1;
-        mbar_wait (a_full + ab, (kk >> 1) & 1);
-        mbar_wait (t_empty, (kk & 1) ^ 1);                                     // the epilogue has read the accumulators of supertile kk - 1
+        mbar_wait_guarded (a_full + ab, (kk >> 1) & 1);
+        mbar_wait_guarded (t_empty, (kk & 1) ^ 1);                                     // the epilogue has read the accumulators of supertile kk - 1
         tc_fence_after ();
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4);
         if (elect_one ())

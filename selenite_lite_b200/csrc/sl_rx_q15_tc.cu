@@ -46,6 +46,14 @@ constexpr int kRawRow = kSuper * 4 + 16, kHistRow = kHist * 4 + 16;
 #endif
 constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = SL_Q15TC_RAWSTAGES, kMmaUnroll = SL_Q15TC_MMA_UNROLL;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1, kThreads = 32 * (kProdWarp + 1);
+#ifndef SL_Q15TC_PSLOTS
+#define SL_Q15TC_PSLOTS 4
+#endif
+#ifndef SL_Q15TC_HOIST
+#define SL_Q15TC_HOIST 0                    /* 1: the carried peak of a group's first supertile is loaded at the group's start instead of between read-out and hand-over:
+                                             one more live register in the epilogue, 430 vs 492 Gsamples/s */
+#endif
+constexpr unsigned kPSlots = SL_Q15TC_PSLOTS;
 constexpr int kTmemCols = 512;           // xh products in columns [0,192), xl products in [192,384)
 
 struct Smem
@@ -57,7 +65,7 @@ struct Smem
   static constexpr size_t pk = hist + kRawStages * kJ * kHistRow;                // [4 tiles][16][8] int: block peaks of the last supertiles
   static constexpr size_t pkc = pk + (SL_Q15TC_SPLIT ? 2 : 1) * 4 * kQ * kJ * 4;                   // [sets][16][8] int: peaks before the stream start, by 16 - age
   static constexpr size_t bars = pkc + kSets * kQ * kJ * 4;
-  static constexpr int n_bars = 20;
+  static constexpr int n_bars = 24;
   static constexpr size_t tmem_ptr = bars + n_bars * 8;
   static constexpr size_t bytes = tmem_ptr + 16;
 };
@@ -91,7 +99,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
   static_assert (kRawStages >= 2 && kRawStages <= 4, "barrier layout");
   uint64_t *raw_full = bars, *raw_empty = bars + 4, *a_full = bars + 8, *a_empty = bars + 10, *t_empty = bars + 12;
-  uint64_t *p_bar = bars + 13, *b_full = bars + 15, *t_full = bars + 16;
+  uint64_t *b_full = bars + 15, *t_full = bars + 16, *p_bar = bars + 18;
+  // p_bar has FOUR slots: a set arrives for supertile kk BEFORE it waits for its predecessor's peaks, so the other set can arrive for
+  // kk + 1 while a warp of this one has not yet looked at kk - 1 (it does whenever the global load at the start of a group takes longer
+  // than the MMAs of kk + 1: seen as a hang at 8192 channels). On two slots kk + 1 completes the phase after kk - 1's on the same
+  // barrier and the late wait never returns; on four the next arrival on kk - 1's slot is kk + 3, which needs this set's read-out
+  // of kk + 2.
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *> (smem + Smem::tmem_ptr);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,8 +114,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
     for (int i = 0; i < 2; i++)
     {
       mbar_init (a_full + i, kConvWarps); mbar_init (a_empty + i, 1);
-      mbar_init (p_bar + i, 4); mbar_init (t_full + i, 1);
+      mbar_init (t_full + i, 1);
     }
+    for (int i = 0; i < kPSlots; i++) mbar_init (p_bar + i, 4);
     mbar_init (t_empty, SL_Q15TC_SPLIT ? 4 * kSets : 4); mbar_init (b_full, 1);
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
         {
           const int rb = kk % kRawStages;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper), nv = group_nv (g);
-          mbar_wait (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
+          mbar_wait_guarded (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
           mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
 #pragma unroll 1
           for (int j = 0; j < kJ; j++)
@@ -142,6 +156,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
             if (k == 0) bulk_g2s (sHist + (rb * kJ + j) * kHistRow, P.tail_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
           }
         }
+      // Watchdog (sl_tc_common.cuh): in this kernel only the producer counts its failed polls (the counter in the MMA issuer's waits cost
+      // 5 %: 466 vs 492 Gsamples/s) — a deadlock reaches it through the raw stages — and it stays until the last supertile's MMAs have
+      // completed, so the tail after its last copy is covered too.
+      // (From supertile kk - 1 - kRawStages on: its stage was free for the last copy, so its planes were written, so the MMAs two before
+      // it on the same t_full slot had completed — the parity waits below cannot mistake an older phase for theirs.)
+      for (unsigned i = kk > (unsigned) kRawStages ? kk - 1u - kRawStages : 0u; i < kk; i++) mbar_wait_guarded (t_full + (i & 1), (i >> 1) & 1);
     }
     __syncwarp ();
   }
@@ -276,6 +296,9 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
       const bool jvalid = (uint32_t) j < nv;
       const uint32_t c = g * P.gsz + min ((uint32_t) j, nv - 1u);
       const bool sub = P.lsb[c] != 0;
+#if !SL_Q15TC_SPLIT && SL_Q15TC_HOIST
+      const int carried_pk = (16 - q <= kWin - 1) ? (int) P.peaks_in[(size_t) c * kWin + (16 - q) - 1] : 0;   // loaded here, not between read-out and hand-over
+#endif
 #if SL_Q15TC_SPLIT
       // Both sets work on EVERY supertile: set es takes samples [24 es, 24 es + 24) of each block. The accumulators are read
       // out in half the time — with one accumulator buffer the next supertile's MMAs wait for exactly that — and a block's
@@ -413,11 +436,15 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
         // ---- block peaks: this supertile's into tile kk & 3; at a stream start the peaks before it (carried by age) into
         //      this set's carry tile, laid out like a previous supertile (block 16 - age)
         sPk[((kk & 3) * kQ + q) * kJ + j] = pk;
+#if SL_Q15TC_HOIST
+        if (k == 0) myC[q * kJ + j] = carried_pk;
+#else
         if (k == 0) myC[q * kJ + j] = (16 - q <= kWin - 1) ? (int) P.peaks_in[(size_t) c * kWin + (16 - q) - 1] : 0;
+#endif
         __syncwarp ();
-        if (lane == 0) mbar_arrive (p_bar + (kk & 1));
+        if (lane == 0) mbar_arrive (p_bar + (kk % kPSlots));
         // (every supertile but the CTA's first waits for its predecessor's peaks, also across groups where they are not used)
-        if (kk != 0) mbar_wait (p_bar + ((kk - 1) & 1), ((kk - 1) >> 1) & 1);
+        if (kk != 0) mbar_wait (p_bar + ((kk - 1) % kPSlots), ((kk - 1) / kPSlots) & 1);
         named_bar (1 + es, 128);
         const int *own = sPk + (kk & 3) * kQ * kJ, *prev = (k == 0) ? myC : sPk + ((kk - 1) & 3) * kQ * kJ;
         // ---- envelope over the peak window (ours): max over ages 1 .. window-1 of (peak * rel[age]) >> 15

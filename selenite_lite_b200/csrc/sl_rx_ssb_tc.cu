@@ -101,8 +101,8 @@ static_assert ((kGroups / 2) % kConvWarps == 0, "a half supertile splits evenly 
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);   // 16 warps = 4 warpgroups: 3 epilogue sets + {2 converters, MMA issuer, producer}
 static_assert (!SL_TC_REGSPLIT || kThreads == 512, "register split below assumes 4 warpgroups");
-constexpr int kOutRow = 4 * kBlk * 4 + 16;  // output stage of one epilogue warp: a channel's four blocks (768 B) + pad, ...
-constexpr int kOutStage = 4 * kOutRow;     // ... four channels at a time
+constexpr int kOutRow = 2 * kBlk * 4 + 16;  // output stage of one epilogue warp (SL_TC_BULKOUT): two blocks of a channel (384 B) + pad, ...
+constexpr int kOutStage = kJ * kOutRow;    // ... of all eight channels
 constexpr int kTmemCols = 512;           // two accumulator buffers of 256 columns
 
 struct Smem
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
           if (lane == 0)
           {
-            mbar_wait_long (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
+            mbar_wait_guarded (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
             TC_STAMP (0);
             mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           }
@@ -473,10 +473,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         const int ab = kk & 1, tb = kk & 1;
-        if (kPair) mbar_wait_cluster (a_full + ab, (kk >> 1) & 1); else mbar_wait_long (a_full + ab, (kk >> 1) & 1);
+        if (kPair) mbar_wait_cluster (a_full + ab, (kk >> 1) & 1); else mbar_wait_guarded (a_full + ab, (kk >> 1) & 1);
         TC_STAMP (4);
         // the epilogue (of both CTAs) has drained this accumulator buffer and zeroed its columns [0,52)
-        if (kPair) mbar_wait_cluster (t_empty + tb, ((kk >> 1) & 1) ^ 1); else mbar_wait_long (t_empty + tb, ((kk >> 1) & 1) ^ 1);
+        if (kPair) mbar_wait_cluster (t_empty + tb, ((kk >> 1) & 1) ^ 1); else mbar_wait_guarded (t_empty + tb, ((kk >> 1) & 1) ^ 1);
         TC_STAMP (5);
         tc_fence_after ();
         const uint32_t d = tmem + (uint32_t) tb * 256u;
@@ -920,39 +920,34 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kBlk) + t0 / kBlk] = gain;
         }
 #if SL_TC_BULKOUT
-        // ---- gain (arm_scale_f32), pack (arm_float_to_q15), store. A warp holds 4 consecutive blocks of 8 channels = 768
-        // contiguous bytes per channel, but as direct stores every instruction touches 32 different lines (32 L1 wavefronts; the
-        // output stores alone were 30 % of the kernel, ablation in profiles/r01_summary.md). The warp lays its blocks into a
-        // private shared-memory stage (conflict-free 16-byte stores, 4 wavefronts each) and one lane sends 768-byte bulk
-        // copies, four channels per round. No other warp is involved.
+        // ---- gain (arm_scale_f32), pack (arm_float_to_q15), store through a shared-memory stage. A warp holds 4 consecutive blocks of
+        // 8 channels = 768 contiguous bytes per channel, but as direct stores every instruction touches 32 different lines (32 L1
+        // wavefronts). Here the warp lays two blocks of all eight channels at a time into its private stage (rows of 384 + 16 bytes:
+        // the eight lanes of a quarter warp hit eight different 16-byte bank groups, so a 16-byte store of 16 lanes is its two ideal
+        // wavefronts) and lanes 0..7 send one 384-byte bulk copy each. No other warp is involved.
         {
           const float g15 = gain * 32768.0f;                                       // exact: power of two
           unsigned char *stage = sOut + warp * kOutStage;
-          const uint32_t gs = P.gstart[g], nv = gi >> 8;
 #pragma unroll
           for (int r = 0; r < 2; r++)
           {
-            if (lane == 0) asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stage's previous copies have been read
+            if (lane < 8) asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stage's previous copies have been read
             __syncwarp ();
-            if ((j >> 2) == r)
+            if ((a >> 1) == r)
             {
-              uint4 *dst = reinterpret_cast<uint4 *> (stage + (j & 3) * kOutRow + a * (kBlk * 4));
+              uint4 *dst = reinterpret_cast<uint4 *> (stage + j * kOutRow + (a & 1) * (kBlk * 4));
 #pragma unroll
               for (int n = 0; n < kBlk; n += 4)
                 dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
             }
             asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp ();
-            if (lane == 0)
+            if (lane < 8)
             {
-              // blocks of this warp that exist in a half supertile at the end of a stream: 4 w .. min (4 w + 3, nblk - 1)
-              const int nb = min (4, nblk - 4 * w);
-              if (nb > 0)
-              {
-#pragma unroll 1
-                for (uint32_t jj = 4u * r; jj < min (4u * r + 4u, nv); jj++)
-                  bulk_s2g (P.out + (size_t) P.chan[gs + jj] * P.frames + (size_t) k * kSuper + (size_t) (4 * w) * kBlk, stage + (jj & 3) * kOutRow, (unsigned) nb * kBlk * 4u);
-              }
+              // blocks of this round that exist in a short supertile at the end of a stream: 4 w + 2 r .. min (4 w + 2 r + 1, nblk - 1)
+              const int q0 = 4 * w + 2 * r, nb = min (2, nblk - q0);
+              if (nb > 0 && jvalid)
+                bulk_s2g (P.out + (size_t) c * P.frames + (size_t) k * kSuper + (size_t) q0 * kBlk, stage + j * kOutRow, (unsigned) nb * kBlk * 4u);
               asm volatile ("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
@@ -993,7 +988,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       }
     }
 #if SL_TC_BULKOUT
-    if (lane == 0) asm volatile ("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's output copies complete before the CTA retires
+    if (lane < 8) asm volatile ("cp.async.bulk.wait_group 0;" ::: "memory");    // this warp's output copies complete before the CTA retires
     __syncwarp ();
 #endif
 #endif

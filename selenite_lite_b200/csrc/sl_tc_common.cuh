@@ -19,6 +19,24 @@ __device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
   asm volatile ("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
                 ::"r"(smem_u32 (bar)), "r"(parity) : "memory");
 }
+// Watchdog. Every wait in these kernels is bounded by one pipeline step (microseconds); a wait that fails 2^26 polls in a row
+// (seconds) is a broken hand-over protocol. The two single-lane roles every supertile passes through — the producer (waits for a
+// free raw stage) and the MMA issuer (waits for operands and a free accumulator) — count their failed polls and trap, so a
+// deadlock anywhere in the pipeline ends the launch with an error the host reports instead of hanging the GPU. The other roles
+// poll without the counter: with it in every wait the kernels lost 2 .. 4 % (s30_*: TX 431 vs 450, RX 408 vs 415 Gsamples/s).
+#ifndef SL_TC_WAIT_LIMIT
+#define SL_TC_WAIT_LIMIT 67108864
+#endif
+__device__ __forceinline__ void mbar_wait_guarded (uint64_t *bar, unsigned parity)
+{
+#if SL_TC_WAIT_LIMIT > 0
+  asm volatile ("{\n .reg .pred p;\n .reg .u32 n;\n mov.u32 n, 0;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n"
+                " add.u32 n, n, 1;\n setp.lt.u32 p, n, %2;\n @p bra WAIT_%=;\n trap;\n DONE_%=:\n}\n"
+                ::"r"(smem_u32 (bar)), "r"(parity), "n"(SL_TC_WAIT_LIMIT) : "memory");
+#else
+  mbar_wait (bar, parity);
+#endif
+}
 // The same for the roles that wait long (producer, converters, MMA issuer, an epilogue set waiting for its accumulators): a
 // plain try_wait loop polls every ~20 clocks, and every poll is a shared-memory wavefront on the L1 data pipe the tensor core
 // fetches its operands through (ncu, round 2: 411 polls per supertile). A/B option: the try_wait carries a suspend-time hint

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
           if (lane == 0)
           {
-            mbar_wait (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
+            mbar_wait_guarded (raw_empty + rb, ((kk / kRawStages) & 1) ^ 1);
             mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           }
           __syncwarp ();
@@ -279,12 +279,12 @@ __global__ void __launch_bounds__ (kThreads, 1) tx_ssb_tc_kernel (const __grid_c
       for (uint32_t k = 0; k < supers; k++, kk++)
       {
         const int ab = kk & 1;
-        mbar_wait (a_full + ab, (kk >> 1) & 1);
+        mbar_wait_guarded (a_full + ab, (kk >> 1) & 1);
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4);
 #pragma unroll kRailUnroll
         for (int rail = 0; rail < 2; rail++)
         {
-          mbar_wait (rail ? t_empty_q : t_empty, (kk & 1) ^ 1);                // the epilogue has read this rail's accumulators of supertile kk - 1
+          mbar_wait_guarded (rail ? t_empty_q : t_empty, (kk & 1) ^ 1);                // the epilogue has read this rail's accumulators of supertile kk - 1
           tc_fence_after ();
           if (elect_one ())
           {

@@ -179,6 +179,34 @@ def test_tcgen05_kernel_equals_the_mma_sync_kernel_bit_for_bit():
     assert np.array_equal(whole[0], cut[0]) and whole[3] == cut[3]
 
 
+def test_config5_width_many_groups_per_cta_under_memory_load():
+    """8192 channels (config 5's shard per GPU) x 2 s: 1024 groups on 148 CTAs = seven groups per CTA with the memory system saturated.
+    The tcgen05 kernel once hung here (a set's wait on the two-slot peak hand-over barrier could be overtaken by the other set whenever
+    the load at a group's start outlasted a supertile's MMAs; tests at small widths never saw it). Output and carried state must equal
+    the mma.sync kernel's, compared on the device; a broken hand-over now traps instead of hanging (sl_tc_common.cuh)."""
+    import os
+    import torch
+    C, T = 8192, 96000
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    x = torch.randint(-20000, 20000, (C, T, 2), dtype=torch.int16, device="cuda", generator=g)
+    outs = []
+    for legacy in (False, True):
+        if legacy:
+            os.environ["SELENITE_B200_Q15_PATH"] = "legacy"
+        try:
+            d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+            for rep in range(3 if not legacy else 1):                              # the race needed a few launches
+                y = d.rx_process(x)
+            torch.cuda.synchronize()
+            if not legacy:                                                         # same stream position for the comparison
+                d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15); y = d.rx_process(x); torch.cuda.synchronize()
+            outs.append((y, bytes(d.state_save())))
+        finally:
+            os.environ.pop("SELENITE_B200_Q15_PATH", None)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1]
+
+
 def test_host_path_cut_into_time_slices_is_bit_exact():
     """slb_rx_process_host for the q15 chain cuts the batch in time like the f32 chains: forced down to 1536-frame slices, a stream
     of 6 slices and a 5-block remainder equals the device path bit for bit, state included."""
