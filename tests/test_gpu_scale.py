@@ -1,0 +1,105 @@
+"""The chains at config 5's width (8192 channels per GPU: 1024 channel groups on 148 persistent CTAs, the memory system saturated).
+Parity proper lives in the per-chain test files at sizes the oracle finishes in seconds; this file is about what only shows at scale:
+hand-over protocols between the roles of a CTA that can be overtaken when a load is slow (the RX-SSB-q15 kernel once hung here,
+tests/test_gpu_rx_ssb_q15.py::test_config5_width_many_groups_per_cta_under_memory_load), 32-bit index overflow, groups of mixed
+masks dealt to many CTAs. Each case compares two independent kernels of the library on the device (tensor-core kernel against the
+FFT kernel) or the wide batch against a narrow one, and runs under a hard timeout."""
+import numpy as np
+import pytest
+
+import selenite_lite_b200 as slb
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _int16_close(a, b):
+    d = (a.to(torch.int32) - b.to(torch.int32)).abs()
+    return int(d.max()), float((d > 0).float().mean())
+
+
+@pytest.mark.timeout(240, method="thread")
+def test_rx_ssb_f32_8192_channels_tensor_core_against_fft_kernel():
+    C, T = 8192, 96000
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    x = torch.randint(-12000, 12000, (C, T, 2), dtype=torch.int16, device="cuda", generator=g)
+    modes = [slb.MODE_USB, slb.MODE_LSB, slb.MODE_CW, slb.MODE_DIG, slb.MODE_USB, slb.MODE_AM, slb.MODE_FM]
+    outs = []
+    for path in (slb.RX_PATH_AUTO, slb.RX_PATH_FFT):
+        d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32); d.set_rx_path(path)
+        for m in range(1, len(modes)):
+            for c in range(m, C, 64 * len(modes)):                                 # a sprinkle of every mode: mixed groups, mask reloads
+                d.DSP_Set_Mode(modes[m], channel=c)
+        y = None
+        for rep in range(3):                                                        # a race needs a few launches
+            y = d.rx_process(x, y)
+        torch.cuda.synchronize()
+        d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32); d.set_rx_path(path)
+        for m in range(1, len(modes)):
+            for c in range(m, C, 64 * len(modes)):
+                d.DSP_Set_Mode(modes[m], channel=c)
+        outs.append(d.rx_process(x)); torch.cuda.synchronize()
+    fm = torch.zeros(C, dtype=torch.bool, device="cuda"); fm[6::64 * len(modes)] = True       # FM has one kernel: the same on both paths
+    mx, frac = _int16_close(outs[0][~fm], outs[1][~fm])
+    assert mx <= 1 and frac < 0.02, (mx, frac)
+    assert torch.equal(outs[0][fm], outs[1][fm])
+    assert int(outs[0].abs().max()) > 1000                                          # the chains did run
+
+
+@pytest.mark.timeout(240, method="thread")
+def test_tx_ssb_f32_8192_channels_tensor_core_against_fft_kernel():
+    C, T = 8192, 96000
+    g = torch.Generator(device="cuda"); g.manual_seed(12)
+    m = torch.randint(-8000, 8000, (C, T, 1), dtype=torch.int16, device="cuda", generator=g).expand(C, T, 2).contiguous()
+    outs = []
+    for path in (slb.RX_PATH_AUTO, slb.RX_PATH_FFT):
+        d = slb.DspIf(C, chain=slb.CHAIN_TX_SSB_F32); d.set_rx_path(path)
+        for c in range(1, C, 3):
+            d.DSP_Set_Mode(slb.MODE_LSB, channel=c)
+        for rep in range(3):
+            d.tx_process(m)
+        torch.cuda.synchronize()
+        d = slb.DspIf(C, chain=slb.CHAIN_TX_SSB_F32); d.set_rx_path(path)
+        for c in range(1, C, 3):
+            d.DSP_Set_Mode(slb.MODE_LSB, channel=c)
+        outs.append(d.tx_process(m)); torch.cuda.synchronize()
+    mx, frac = _int16_close(outs[0], outs[1])
+    assert mx <= 1 and frac < 0.02, (mx, frac)
+    assert int(outs[0].abs().max()) > 1000
+
+
+@pytest.mark.timeout(240, method="thread")
+def test_chan64_512_streams_equal_the_same_streams_alone():
+    S, T = 512, 192000 // 768 * 768
+    g = torch.Generator(device="cuda"); g.manual_seed(13)
+    x = torch.randint(-3000, 3000, (S, T, 2), dtype=torch.int16, device="cuda", generator=g)
+    d = slb.DspIf(S, fs=192000, chain=slb.CHAIN_CHAN64_F32)
+    y = torch.empty((S, 64, T // 64, 2), dtype=torch.int16, device="cuda")
+    for rep in range(3):
+        d.chan_process(x, y)
+    torch.cuda.synchronize()
+    d = slb.DspIf(S, fs=192000, chain=slb.CHAIN_CHAN64_F32); d.chan_process(x, y); torch.cuda.synchronize()
+    for s0 in (0, 509):
+        n = 3
+        dn = slb.DspIf(n, fs=192000, chain=slb.CHAIN_CHAN64_F32)
+        yn = torch.empty((n, 64, T // 64, 2), dtype=torch.int16, device="cuda")
+        dn.chan_process(x[s0:s0 + n].contiguous(), yn); torch.cuda.synchronize()
+        assert torch.equal(yn, y[s0:s0 + n]), s0
+
+
+@pytest.mark.timeout(240, method="thread")
+def test_firmware_api_at_8192_channels_equals_a_16_channel_context():
+    """64 firmware milliseconds through the feeder (rings, 8-tick accumulation, chain, ring again) at 8192 channels: every channel hears
+    what the same stream hears in a 16-channel context."""
+    C, ticks = 8192, 64
+    x16 = slb.synth_iq(16, 48 * ticks)
+    x = np.ascontiguousarray(np.tile(x16, (C // 16, 1, 1)))
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    d.DSP_Init(); d.DSP_Set_RX()
+    got, _ = d.feeder_run(adc=x)
+    ref = slb.DspIf(16, chain=slb.CHAIN_RX_SSB_F32)
+    ref.DSP_Init(); ref.DSP_Set_RX()
+    exp, _ = ref.feeder_run(adc=x16)
+    assert got.shape == x.shape
+    assert np.array_equal(got[:16], exp) and np.array_equal(got[-16:], exp) and np.array_equal(got[4096:4112], exp)
+    assert np.abs(exp).max() > 100
