@@ -1321,7 +1321,10 @@ static int process_host_sliced (slb_ctx *ctx, const int16_t *h_in, int16_t *h_ou
   const uint32_t C = ctx->cfg.channels;
   // a multiple of 1536 frames = the FFT kernel's tile and two supertiles of the tensor-core kernel: both kernels give the
   // cut stream bit for bit the result of the uncut one
-  size_t slice_bytes = (size_t) 64 << 20;
+  // slice size: the pipeline's fill and drain (one slice's H2D before, one slice's D2H after) are what separates this path from the plain
+  // duplex copy of the same bytes; measured at 1024 channels x 10 s (tools/bench_e2e_slices.py, profiles/r02_e2e_slices.json): 4 / 8 MiB
+  // 0.975 of that ceiling, 32 MiB 0.957, 64 MiB 0.921, 256 MiB 0.888
+  size_t slice_bytes = (size_t) 8 << 20;
   if (const char *e = std::getenv ("SELENITE_B200_SLICE_BYTES")) { const long long v = std::atoll (e); if (v > 0) slice_bytes = (size_t) v; }   // test / tuning knob
   uint32_t slice = (uint32_t) (slice_bytes / ((size_t) C * 4)) / 1536u * 1536u;
   if (slice < 1536u) slice = 1536u;
