@@ -1319,17 +1319,23 @@ int slb_tx_process_device (slb_ctx *ctx, const int16_t *d_in, int16_t *d_out, ui
 static int process_host_sliced (slb_ctx *ctx, const int16_t *h_in, int16_t *h_out, uint32_t frames)
 {
   const uint32_t C = ctx->cfg.channels;
-  // a multiple of 1536 frames = the FFT kernel's tile and two supertiles of the tensor-core kernel: both kernels give the
-  // cut stream bit for bit the result of the uncut one
-  // slice size: the pipeline's fill and drain (one slice's H2D before, one slice's D2H after) are what separates this path from the plain
-  // duplex copy of the same bytes; measured at 1024 channels x 10 s (tools/bench_e2e_slices.py, profiles/r02_e2e_slices.json): 4 / 8 MiB
-  // 0.975 of that ceiling, 32 MiB 0.957, 64 MiB 0.921, 256 MiB 0.888
-  size_t slice_bytes = (size_t) 8 << 20;
-  if (const char *e = std::getenv ("SELENITE_B200_SLICE_BYTES")) { const long long v = std::atoll (e); if (v > 0) slice_bytes = (size_t) v; }   // test / tuning knob
-  uint32_t slice = (uint32_t) (slice_bytes / ((size_t) C * 4)) / 1536u * 1536u;
+  // The batch is cut into tiles = (block of channels) x (slice of time) that go through a three-stream pipeline: H2D of tile i + 1,
+  // kernel of tile i and D2H of tile i - 1 overlap. Time cuts are multiples of 1536 frames = the FFT kernel's tile and two
+  // supertiles of the tensor-core kernel: both kernels give the cut stream bit for bit the result of the uncut one (the carried
+  // state lives per channel on the device). Tile size: the pipeline's fill and drain (one tile's H2D before, one tile's D2H after)
+  // are what separates this path from the plain duplex copy of the same bytes; measured at 1024 channels x 10 s
+  // (tools/bench_e2e_slices.py, profiles/r02_e2e_slices.json): 4 / 8 MiB 0.975 of that ceiling, 32 MiB 0.957, 64 MiB 0.921,
+  // 256 MiB 0.888. Wide batches (config 5: 32 768 channels per GPU, where the shortest time slice of ALL channels is 201 MB) are
+  // cut into blocks of 1024 channels as well; the kernels take a channel range like under per-channel cadence.
+  size_t tile_bytes = (size_t) 8 << 20;
+  if (const char *e = std::getenv ("SELENITE_B200_SLICE_BYTES")) { const long long v = std::atoll (e); if (v > 0) tile_bytes = (size_t) v; }   // test / tuning knob
+  uint32_t block = C;
+  if (C > 1024u && (size_t) C * 1536u * 4u > tile_bytes) block = 1024u;
+  if (const char *e = std::getenv ("SELENITE_B200_SLICE_CHANNELS")) { const long v = std::atol (e); if (v > 0 && (uint32_t) v < C) block = (uint32_t) v; }   // test knob
+  uint32_t slice = (uint32_t) std::min<size_t> (tile_bytes / ((size_t) block * 4), 0xFFFFFFFFu) / 1536u * 1536u;
   if (slice < 1536u) slice = 1536u;
   if (slice > frames) slice = frames;
-  const size_t need = (size_t) C * slice * 4;
+  const size_t need = (size_t) block * slice * 4;
   if (need > ctx->bulk_bytes || !ctx->bulk_stream[0])
   {
     for (int s = 0; s < kBulkSlots; s++)
@@ -1352,30 +1358,35 @@ static int process_host_sliced (slb_ctx *ctx, const int16_t *h_in, int16_t *h_ou
   CK (ctx, cudaStreamSynchronize (ctx->stream));
   cudaStream_t s_in = ctx->bulk_stream[0], s_k = ctx->bulk_stream[1], s_out = ctx->bulk_stream[2];
   const size_t pitch = (size_t) frames * 4;
-  uint32_t n_slices = 0;
-  for (uint32_t t0 = 0; t0 < frames; t0 += slice, n_slices++)
+  uint32_t n_tiles = 0;
+  for (uint32_t t0 = 0; t0 < frames; t0 += slice)
   {
-    const int slot = (int) (n_slices % kBulkSlots);
     const uint32_t n = (frames - t0 < slice) ? frames - t0 : slice;
     const size_t row = (size_t) n * 4;
-    if (n_slices >= (uint32_t) kBulkSlots) CK (ctx, cudaStreamWaitEvent (s_in, ctx->slice_ev[slot][2], 0));   // the slot's previous result has left
-    CK (ctx, cudaMemcpy2DAsync (ctx->d_bulk_in[slot], row, reinterpret_cast<const char *> (h_in) + (size_t) t0 * 4, pitch, row, C, cudaMemcpyHostToDevice, s_in));
-    CK (ctx, cudaEventRecord (ctx->slice_ev[slot][0], s_in));
-    CK (ctx, cudaStreamWaitEvent (s_k, ctx->slice_ev[slot][0], 0));
-    if (ctx->q15)
+    for (uint32_t c0 = 0; c0 < C; c0 += block, n_tiles++)
     {
-      const int rc = rxq15_launch (ctx, ctx->q15, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], 0, C, n, ctx->sm_count, s_k, false); if (rc) return rc;
-      rxq15_advance (ctx->q15);
+      const int slot = (int) (n_tiles % kBulkSlots);
+      const uint32_t nc = (C - c0 < block) ? C - c0 : block;
+      const size_t host_off = ((size_t) c0 * frames + t0) * 4;
+      if (n_tiles >= (uint32_t) kBulkSlots) CK (ctx, cudaStreamWaitEvent (s_in, ctx->slice_ev[slot][2], 0));   // the slot's previous result has left
+      CK (ctx, cudaMemcpy2DAsync (ctx->d_bulk_in[slot], row, reinterpret_cast<const char *> (h_in) + host_off, pitch, row, nc, cudaMemcpyHostToDevice, s_in));
+      CK (ctx, cudaEventRecord (ctx->slice_ev[slot][0], s_in));
+      CK (ctx, cudaStreamWaitEvent (s_k, ctx->slice_ev[slot][0], 0));
+      if (ctx->q15)
+      {
+        const int rc = rxq15_launch (ctx, ctx->q15, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], c0, nc, n, ctx->sm_count, s_k, false); if (rc) return rc;
+      }
+      else
+      {
+        const int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], c0, nc, n, nullptr, nullptr, s_k); if (rc) return rc;
+      }
+      CK (ctx, cudaEventRecord (ctx->slice_ev[slot][1], s_k));
+      CK (ctx, cudaStreamWaitEvent (s_out, ctx->slice_ev[slot][1], 0));
+      CK (ctx, cudaMemcpy2DAsync (reinterpret_cast<char *> (h_out) + host_off, pitch, ctx->d_bulk_out[slot], row, row, nc, cudaMemcpyDeviceToHost, s_out));
+      CK (ctx, cudaEventRecord (ctx->slice_ev[slot][2], s_out));
     }
-    else
-    {
-      const int rc = run_rx_kernel (ctx, ctx->d_bulk_in[slot], ctx->d_bulk_out[slot], 0, C, n, nullptr, nullptr, s_k); if (rc) return rc;
-      rx_advance (ctx, n);                                     // host bookkeeping of the carried state; the launches are stream-ordered
-    }
-    CK (ctx, cudaEventRecord (ctx->slice_ev[slot][1], s_k));
-    CK (ctx, cudaStreamWaitEvent (s_out, ctx->slice_ev[slot][1], 0));
-    CK (ctx, cudaMemcpy2DAsync (reinterpret_cast<char *> (h_out) + (size_t) t0 * 4, pitch, ctx->d_bulk_out[slot], row, row, C, cudaMemcpyDeviceToHost, s_out));
-    CK (ctx, cudaEventRecord (ctx->slice_ev[slot][2], s_out));
+    // every channel has taken this time slice: host bookkeeping of the carried state (the launches are stream-ordered)
+    if (ctx->q15) rxq15_advance (ctx->q15); else rx_advance (ctx, n);
   }
   for (int s = 0; s < kBulkSlots; s++) CK (ctx, cudaStreamSynchronize (ctx->bulk_stream[s]));
   return SLB_OK;

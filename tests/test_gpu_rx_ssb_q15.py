@@ -224,6 +224,15 @@ def test_host_path_cut_into_time_slices_is_bit_exact():
         del os.environ["SELENITE_B200_SLICE_BYTES"]
     assert np.array_equal(y_host, y_dev)
     assert bytes(d_host.state_save()) == bytes(d_dev.state_save())
+    # channel blocks x time slices (the cut of wide batches): blocks of 5 channels (5 + 5 + 3)
+    os.environ["SELENITE_B200_SLICE_BYTES"] = str(5 * 4 * 1536); os.environ["SELENITE_B200_SLICE_CHANNELS"] = "5"
+    try:
+        d_tiles = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+        y_tiles = d_tiles.rx_process(x)
+    finally:
+        del os.environ["SELENITE_B200_SLICE_BYTES"]; del os.environ["SELENITE_B200_SLICE_CHANNELS"]
+    assert np.array_equal(y_tiles, y_dev)
+    assert bytes(d_tiles.state_save()) == bytes(d_dev.state_save())
 
 
 def _q15_audio_biquad():

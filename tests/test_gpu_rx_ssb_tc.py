@@ -186,7 +186,7 @@ def test_several_groups_per_cta_and_mask_reloads(best_oracle):
 
 
 def test_host_path_cut_into_many_time_slices(best_oracle):
-    """slb_rx_process_host cuts the batch in time (64 MB slices by default); with the slice forced down to 1536 frames a
+    """slb_rx_process_host cuts the batch in time (8 MiB tiles by default); with the slice forced down to 1536 frames a
     stream of 7 slices (the last one short) must equal the device path bit for bit — carried state across slices, strided
     copies, three staging slots in flight — for the tensor-core kernel and, with AM channels mixed in, the FFT kernel."""
     import os
@@ -208,6 +208,18 @@ def test_host_path_cut_into_many_time_slices(best_oracle):
     assert np.array_equal(y_host, y_dev) and np.array_equal(yp.numpy(), y_dev)
     exp, _, _, _ = best_oracle.rx_ssb_f32(make().oracle_params(), x[0])
     check_int16(y_host[0], exp)
+    # wide batches are cut into channel blocks as well (config 5: blocks of 1024 channels): forced down to blocks of 7 channels
+    # (three blocks, the last of 6; AM channels in two of them) x 1536-frame slices = 21 tiles, state per channel across them
+    os.environ["SELENITE_B200_SLICE_BYTES"] = str(7 * 4 * 1536); os.environ["SELENITE_B200_SLICE_CHANNELS"] = "7"
+    try:
+        d = make()
+        y_tiles = d.rx_process(x)
+        y_next = d.rx_process(x)                                                  # and the context carries on from there
+    finally:
+        del os.environ["SELENITE_B200_SLICE_BYTES"]; del os.environ["SELENITE_B200_SLICE_CHANNELS"]
+    assert np.array_equal(y_tiles, y_dev)
+    d = make(); xd = torch.from_numpy(x).cuda(); d.rx_process(xd)
+    assert np.array_equal(y_next, d.rx_process(xd).cpu().numpy())
 
 
 def test_am_channels_on_the_tensor_cores(best_oracle):

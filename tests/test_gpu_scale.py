@@ -103,3 +103,24 @@ def test_firmware_api_at_8192_channels_equals_a_16_channel_context():
     assert got.shape == x.shape
     assert np.array_equal(got[:16], exp) and np.array_equal(got[-16:], exp) and np.array_equal(got[4096:4112], exp)
     assert np.abs(exp).max() > 100
+
+
+@pytest.mark.timeout(240, method="thread")
+def test_host_path_of_a_wide_batch_is_cut_into_channel_blocks_and_equals_the_device_path():
+    """4096 channels x 9216 frames through slb_rx_process_host with the default tile size: four blocks of 1024 channels x six slices
+    of 1536 frames, against one device-resident call."""
+    C, T = 4096, 1536 * 6
+    g = torch.Generator(device="cuda"); g.manual_seed(14)
+    xd = torch.randint(-12000, 12000, (C, T, 2), dtype=torch.int16, device="cuda", generator=g)
+    for chain in (slb.CHAIN_RX_SSB_F32, slb.CHAIN_RX_SSB_Q15):
+        d = slb.DspIf(C, chain=chain)
+        y_dev = d.rx_process(xd); torch.cuda.synchronize()
+        xp = xd.cpu().pin_memory(); yp = torch.empty_like(xp).pin_memory()
+        h = slb.DspIf(C, chain=chain)
+        h.rx_process_pinned(xp, yp)
+        assert torch.equal(yp, y_dev.cpu()), chain
+        if chain == slb.CHAIN_RX_SSB_Q15:
+            assert bytes(h.state_save()) == bytes(d.state_save())                 # (the f32 header counts calls: six slices vs one)
+        y_dev2 = d.rx_process(xd); torch.cuda.synchronize()                       # both contexts carry on alike
+        h.rx_process_pinned(xp, yp)
+        assert torch.equal(yp, y_dev2.cpu()), chain

@@ -154,6 +154,13 @@ def test_tensor_core_and_fft_kernels_agree_and_hand_over(best_oracle):
     finally:
         del os.environ["SELENITE_B200_TC_GRID"]; del os.environ["SELENITE_B200_SLICE_BYTES"]
     assert np.array_equal(y3, y_tc) and np.array_equal(y_host, y_tc)
+    # channel blocks x time slices (the cut of wide batches): blocks of 16 channels (16 + 16 + 12)
+    os.environ["SELENITE_B200_SLICE_BYTES"] = str(16 * 4 * 1536); os.environ["SELENITE_B200_SLICE_CHANNELS"] = "16"
+    try:
+        y_tiles = make().tx_process(x)
+    finally:
+        del os.environ["SELENITE_B200_SLICE_BYTES"]; del os.environ["SELENITE_B200_SLICE_CHANNELS"]
+    assert np.array_equal(y_tiles, y_tc)
 
 
 @pytest.mark.parametrize("fs", [96000, 192000])
