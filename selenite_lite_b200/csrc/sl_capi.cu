@@ -74,6 +74,7 @@ struct slb_ctx
 
   // scratch for the stage library (coefficients, FIR history double buffer)
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
+  cudaStream_t scratch_stream = nullptr; bool scratch_used = false; cudaEvent_t scratch_ev = nullptr;   // last stream that staged data in d_scratch
 
   // host bulk path
   int16_t *d_bulk_in[kBulkSlots] = {}; int16_t *d_bulk_out[kBulkSlots] = {}; size_t bulk_bytes = 0;
@@ -108,6 +109,21 @@ void *ctx_scratch (slb_ctx *ctx, size_t bytes)
   if (cudaMalloc (&ctx->d_scratch, want) != cudaSuccess) { ctx->err = "scratch allocation failed"; return nullptr; }
   ctx->scratch_bytes = want;
   return ctx->d_scratch;
+}
+// The same for callers that stage per-call data at the start of the buffer (coefficients, tables, temporaries) and consume it on
+// `stream`: a call on another stream than the previous one first waits for everything queued there, so two stage calls of one
+// context on different streams cannot overwrite each other's staged data (calls on one stream are ordered anyway).
+void *ctx_scratch_on (slb_ctx *ctx, size_t bytes, void *stream_)
+{
+  cudaStream_t stream = (cudaStream_t) stream_;
+  if (ctx->scratch_used && ctx->scratch_stream != stream)
+  {
+    if (!ctx->scratch_ev && cudaEventCreateWithFlags (&ctx->scratch_ev, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event creation failed"; return nullptr; }
+    if (cudaEventRecord (ctx->scratch_ev, ctx->scratch_stream) != cudaSuccess || cudaStreamWaitEvent (stream, ctx->scratch_ev, 0) != cudaSuccess)
+    { ctx->err = "scratch hand-over between streams failed"; return nullptr; }
+  }
+  ctx->scratch_stream = stream; ctx->scratch_used = true;
+  return ctx_scratch (ctx, bytes);
 }
 }  // namespace sl
 
@@ -266,7 +282,7 @@ void slb_destroy (slb_ctx *ctx)
   cudaFree (ctx->d_acc_off);
   cudaFree (ctx->d_tone); cudaFree (ctx->d_sin513); cudaFree (ctx->d_key); cudaFree (ctx->d_tone_cnt);
   for (int w = 0; w < 2; w++) for (int k = 0; k < 2; k++) cudaFree (ctx->d_ring[w][k]);
-  cudaFree (ctx->d_blk); cudaFree (ctx->d_acc); cudaFree (ctx->d_scratch);
+  cudaFree (ctx->d_blk); cudaFree (ctx->d_acc); cudaFree (ctx->d_scratch); if (ctx->scratch_ev) cudaEventDestroy (ctx->scratch_ev);
   cudaFree (ctx->d_rptr[0]); cudaFree (ctx->d_rptr[1]); cudaFree (ctx->d_active);
   for (int s = 0; s < kBulkSlots; s++)
   {
@@ -952,7 +968,7 @@ int slb_feeder_run (slb_ctx *ctx, const slb_feeder_io *io, uint32_t ticks)
   CK (ctx, cudaSetDevice (ctx->cfg.device));
   const size_t frames = (size_t) ticks * B, bytes = (size_t) C * frames * 4;
   // scratch: raw stream, processed stream, ring output, plan
-  char *scr = static_cast<char *> (ctx_scratch (ctx, 3 * bytes + (size_t) ticks * 8 + 256));
+  char *scr = static_cast<char *> (ctx_scratch_on (ctx, 3 * bytes + (size_t) ticks * 8 + 256, ctx->stream));
   if (!scr) return SLB_ERR_CUDA;
   int16_t *d_raw = reinterpret_cast<int16_t *> (scr), *d_prc = reinterpret_cast<int16_t *> (scr + bytes), *d_out = reinterpret_cast<int16_t *> (scr + 2 * bytes);
   uint32_t *d_plan = reinterpret_cast<uint32_t *> (scr + 3 * bytes);
@@ -1228,7 +1244,7 @@ int slb_rx_spectrum_device (slb_ctx *ctx, const int16_t *d_iq, float *d_power, u
 {
   if (!ctx || !d_iq || !d_power) return SLB_ERR_ARG;
   CK (ctx, cudaSetDevice (ctx->cfg.device));
-  float *tmp = static_cast<float *> (sl::ctx_scratch (ctx, (size_t) ctx->cfg.channels * 2 * N * sizeof (float)));
+  float *tmp = static_cast<float *> (sl::ctx_scratch_on (ctx, (size_t) ctx->cfg.channels * 2 * N * sizeof (float), stream));
   if (!tmp) return SLB_ERR_CUDA;
   int rc = slb_st_q15_to_float (ctx, d_iq, tmp, 2 * N, stream);                 // arm_q15_to_float.c:65
   if (!rc) rc = slb_st_cfft_f32 (ctx, tmp, N, 1, 0, stream);                      // arm_cfft_f32.c:562, forward

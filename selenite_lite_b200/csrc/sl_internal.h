@@ -250,6 +250,7 @@ int ctx_device (const slb_ctx *ctx);
 size_t ctx_channels (const slb_ctx *ctx);
 int ctx_fail (slb_ctx *ctx, int code, const char *msg);
 void ctx_count_launch (slb_ctx *ctx, unsigned n = 1);
+void *ctx_scratch_on (slb_ctx *ctx, size_t bytes, void *stream);   // the same, ordered after the previous user's stream (per-call staging)
 void *ctx_scratch (slb_ctx *ctx, size_t bytes);     // device scratch owned by the context, grown on demand (nullptr + error on failure)
 
 }  // namespace sl

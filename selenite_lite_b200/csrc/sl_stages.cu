@@ -539,7 +539,7 @@ int slb_st_cmplx_mag_q15 (slb_ctx *ctx, const int16_t *a, int16_t *dst, uint32_t
 static int sincos_common (slb_ctx *ctx, const float *x, float *dst, uint32_t n, void *stream, int is_cos)
 {
   ST_BEGIN (ctx);
-  float *tab = (float *) ctx_scratch (ctx, 513 * sizeof (float));
+  float *tab = (float *) ctx_scratch_on (ctx, 513 * sizeof (float), st);
   if (!tab) return SLB_ERR_CUDA;
   cudaError_t e = cudaMemcpyAsync (tab, host_sin_table (), 513 * sizeof (float), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));
@@ -557,7 +557,7 @@ static int fir_common (slb_ctx *ctx, const T *h_coeffs, uint32_t ntaps, uint32_t
   ST_BEGIN (ctx);
   if (!h_coeffs || !hist || !src || !dst || ntaps == 0 || M == 0 || L == 0 || n % M != 0 || ntaps % L != 0) return ctx_fail (ctx, SLB_ERR_ARG, "bad FIR arguments");
   const size_t hist_len = ntaps / L - 1;
-  char *scr = (char *) ctx_scratch (ctx, ntaps * sizeof (T) + C * hist_len * sizeof (T) + 64);
+  char *scr = (char *) ctx_scratch_on (ctx, ntaps * sizeof (T) + C * hist_len * sizeof (T) + 64, st);
   if (!scr) return SLB_ERR_CUDA;
   T *d_coeffs = (T *) scr; T *hist_new = (T *) (scr + ((ntaps * sizeof (T) + 63) / 64) * 64);
   cudaError_t e = cudaMemcpyAsync (d_coeffs, h_coeffs, ntaps * sizeof (T), cudaMemcpyHostToDevice, st);
@@ -589,7 +589,7 @@ int slb_st_cfft_q15 (slb_ctx *ctx, int16_t *data, uint32_t N, uint32_t count, in
   ST_BEGIN (ctx);
   if (!data || count == 0 || N < 16 || N > 4096 || (N & (N - 1))) return ctx_fail (ctx, SLB_ERR_ARG, "cfft_q15: N = 16 .. 4096, a power of two");
   const size_t tw_bytes = (size_t) 3 * N / 4 * 2 * sizeof (int16_t);
-  int16_t *d_tw = (int16_t *) ctx_scratch (ctx, tw_bytes);
+  int16_t *d_tw = (int16_t *) ctx_scratch_on (ctx, tw_bytes, st);
   if (!d_tw) return SLB_ERR_CUDA;
   cudaError_t e = cudaMemcpyAsync (d_tw, fft_twiddle_q15 (N), tw_bytes, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));
@@ -600,7 +600,7 @@ int slb_st_cfft_q31 (slb_ctx *ctx, int32_t *data, uint32_t N, uint32_t count, in
   ST_BEGIN (ctx);
   if (!data || count == 0 || N < 16 || N > 4096 || (N & (N - 1))) return ctx_fail (ctx, SLB_ERR_ARG, "cfft_q31: N = 16 .. 4096, a power of two");
   const size_t tw_bytes = (size_t) 3 * N / 4 * 2 * sizeof (int32_t);
-  int32_t *d_tw = (int32_t *) ctx_scratch (ctx, tw_bytes);
+  int32_t *d_tw = (int32_t *) ctx_scratch_on (ctx, tw_bytes, st);
   if (!d_tw) return SLB_ERR_CUDA;
   cudaError_t e = cudaMemcpyAsync (d_tw, fft_twiddle_q31 (N), tw_bytes, cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return ctx_fail (ctx, SLB_ERR_CUDA, cudaGetErrorString (e));

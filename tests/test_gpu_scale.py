@@ -124,3 +124,31 @@ def test_host_path_of_a_wide_batch_is_cut_into_channel_blocks_and_equals_the_dev
         y_dev2 = d.rx_process(xd); torch.cuda.synchronize()                       # both contexts carry on alike
         h.rx_process_pinned(xp, yp)
         assert torch.equal(yp, y_dev2.cpu()), chain
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_bench_shape_1024_channels_x_10_s_against_the_oracle_and_its_own_cuts(best_oracle):
+    """The bench line's workload at full size (configs[1]: 1024 channels x 10 s = 480 000 frames per channel, one launch). Four
+    channels spread over the batch are run through the oracle for the whole 10 s (int16 within 1 LSB on < 2 % of samples: no drift of
+    the AGC / biquad state over 625 supertiles); channels that carry the same stream give the same bytes wherever they sit in the
+    batch; and the stream cut into two calls at a 384-frame boundary that is NOT a supertile boundary equals the one call."""
+    from test_gpu_rx_ssb_f32 import check_int16
+    C, T = 1024, 480000
+    base = slb.synth_iq(8, T)                                                       # eight different streams (tone + noise, PCG64 per channel)
+    xd = torch.from_numpy(base).cuda().repeat(C // 8, 1, 1).contiguous()            # channel c carries stream c % 8
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    for c in range(1, C, 2):
+        d.DSP_Set_Mode(slb.MODE_LSB, channel=c)                                    # odd streams demodulate the lower sideband
+    y = d.rx_process(xd); torch.cuda.synchronize()
+    y8 = y[:8]
+    assert torch.equal(y.reshape(C // 8, 8, T, 2), y8.unsqueeze(0).expand(C // 8, 8, T, 2))
+    yh = y8.cpu().numpy()
+    for c in (0, 3, 5, 6):
+        exp, _, _, _ = best_oracle.rx_ssb_f32(d.oracle_params(slb.MODE_LSB if c % 2 else slb.MODE_USB), base[c])
+        check_int16(yh[c], exp)
+    d2 = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32)
+    for c in range(1, C, 2):
+        d2.DSP_Set_Mode(slb.MODE_LSB, channel=c)
+    cut = 384 * 601                                                                 # 300.5 supertiles
+    ya = d2.rx_process(xd[:, :cut].contiguous()); yb = d2.rx_process(xd[:, cut:].contiguous()); torch.cuda.synchronize()
+    assert torch.equal(ya, y[:, :cut]) and torch.equal(yb, y[:, cut:])

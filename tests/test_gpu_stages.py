@@ -122,6 +122,28 @@ def test_fir_family_bit_exact_with_carried_state(ctx, best_oracle, rng, name, dt
         assert np.array_equal(got[ch], exp), (name, ch)
 
 
+def test_stage_calls_on_two_streams_do_not_share_staged_coefficients(ctx, best_oracle, rng):
+    """The stage library stages a call's coefficients in the context's scratch buffer and consumes them on the caller's stream.
+    Calls of one context on DIFFERENT streams are ordered through that buffer (ctx_scratch_on), so a second filter's
+    coefficients cannot replace the first's before its kernel has read them: 40 alternating calls with two tap sets on two
+    streams, every result bit-exact."""
+    ca, cb = f32(rng, 64, amp=0.1), f32(rng, 64, amp=0.1)
+    x = f32(rng, C, 16 * N)
+    xd = dev(x)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for i in range(40):
+        c, s = (ca, sa) if i % 2 == 0 else (cb, sb)
+        hist = torch.zeros((C, 63), dtype=torch.float32, device="cuda"); d = torch.zeros((C, 16 * N), dtype=torch.float32, device="cuda")
+        ctx.st("fir_f32", c, 64, hist, xd, d, 16 * N, stream=s.cuda_stream)
+        outs.append(d)
+    torch.cuda.synchronize()
+    exp = [np.stack([best_oracle.fir_f32(c, np.zeros(64 + B, np.float32), x[ch], B)[0] for ch in range(C)]) for c in (ca, cb)]
+    for i, d in enumerate(outs):
+        assert np.array_equal(d.cpu().numpy(), exp[i % 2]), i
+
+
 def test_fir_decimate_interpolate(ctx, best_oracle, rng):
     c, x = f32(rng, 64, amp=0.1), f32(rng, C, 2 * N)
     cq, xq = q15(rng, 64, amp=4000), q15(rng, C, 2 * N)
