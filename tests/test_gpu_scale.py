@@ -152,3 +152,53 @@ def test_bench_shape_1024_channels_x_10_s_against_the_oracle_and_its_own_cuts(be
     cut = 384 * 601                                                                 # 300.5 supertiles
     ya = d2.rx_process(xd[:, :cut].contiguous()); yb = d2.rx_process(xd[:, cut:].contiguous()); torch.cuda.synchronize()
     assert torch.equal(ya, y[:, :cut]) and torch.equal(yb, y[:, cut:])
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_config3_shape_1024_mic_channels_x_10_s_against_the_oracle(best_oracle):
+    """TX-SSB-f32 at full size: 1024 mic channels x 10 s, four channels against the oracle for the whole stream, placement invariance."""
+    from test_gpu_tx_ssb_f32 import check_int16
+    C, T = 1024, 480000
+    base = slb.synth_mic(8, T)
+    xd = torch.from_numpy(base).cuda().repeat(C // 8, 1, 1).contiguous()
+    d = slb.DspIf(C, chain=slb.CHAIN_TX_SSB_F32)
+    for c in range(1, C, 2):
+        d.DSP_Set_Mode(slb.MODE_LSB, channel=c)
+    y = d.tx_process(xd); torch.cuda.synchronize()
+    assert torch.equal(y.reshape(C // 8, 8, T, 2), y[:8].unsqueeze(0).expand(C // 8, 8, T, 2))
+    yh = y[:8].cpu().numpy()
+    for c in (0, 3, 5, 6):
+        exp, _, _, _ = best_oracle.tx_ssb_f32(d.oracle_params(slb.MODE_LSB if c % 2 else slb.MODE_USB), base[c])
+        check_int16(yh[c], exp)
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_config4_shape_64_streams_x_10_s_against_the_oracle(best_oracle):
+    """CHAN-64-f32 at full size: 64 wideband streams x 10 s at 192 kHz (625 tiles per stream chained by the look-back), two streams
+    against the oracle for the whole 10 s, placement invariance."""
+    from test_gpu_chan64_f32 import check_int16
+    S, T = 64, 192000 * 10 // 768 * 768
+    base = slb.synth_wideband(4, T)
+    xd = torch.from_numpy(base).cuda().repeat(S // 4, 1, 1).contiguous()
+    d = slb.DspIf(S, fs=192000, chain=slb.CHAIN_CHAN64_F32)
+    y = d.chan_process(xd); torch.cuda.synchronize()
+    assert torch.equal(y.reshape(S // 4, 4, 64, T // 64, 2), y[:4].unsqueeze(0).expand(S // 4, 4, 64, T // 64, 2))
+    yh = y[:4].cpu().numpy()
+    for s in (1, 2):
+        exp, _, _, _ = best_oracle.chan_f32(d.oracle_params(), base[s])
+        check_int16(yh[s], exp)
+
+
+@pytest.mark.timeout(300, method="thread")
+def test_q15_chain_1024_channels_x_10_s_bit_exact(best_oracle):
+    """RX-SSB-q15 at the bench width and length: bit-exact against the oracle on four channels over the whole 10 s, placement invariance."""
+    C, T = 1024, 480000
+    base = slb.synth_iq(8, T)
+    xd = torch.from_numpy(base).cuda().repeat(C // 8, 1, 1).contiguous()
+    d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15)
+    y = d.rx_process(xd); torch.cuda.synchronize()
+    assert torch.equal(y.reshape(C // 8, 8, T, 2), y[:8].unsqueeze(0).expand(C // 8, 8, T, 2))
+    yh = y[:8].cpu().numpy()
+    for c in (0, 2, 5, 7):
+        exp = best_oracle.rx_ssb_q15(d.oracle_params(slb.MODE_USB), base[c])[0]
+        assert np.array_equal(yh[c], exp), c
