@@ -49,7 +49,11 @@ constexpr int kHistHops = kTaps - 1;             // hops of input history a tile
 constexpr int kTileHops = 48;                    // hops per tile = 16 AGC blocks of 3
 constexpr int kBlk = 3;                          // AGC block: 1 ms = 192 wideband frames = 3 narrowband samples
 constexpr int kTileBlocks = kTileHops / kBlk;
-constexpr int kFftWarps = 3, kAgcWarps = 2;
+#ifndef SL_CHAN_FFTWARPS
+#define SL_CHAN_FFTWARPS 3                          /* producer warps per CTA: 3 (16 hops each, 3 CTAs per SM) or 6 (8 hops each, 2 CTAs per SM) */
+#endif
+constexpr int kFftWarps = SL_CHAN_FFTWARPS, kAgcWarps = 2;
+static_assert (kFftWarps == 3 || kFftWarps == 6, "48 hops split into rounds of 8");
 constexpr int kFftThreads = 32 * kFftWarps, kAgcThreads = 32 * kAgcWarps, kThreads = kFftThreads + kAgcThreads;
 constexpr int kHopsPerWarp = kTileHops / kFftWarps;  // 16 = two rounds of 8
 constexpr int kRowUnits = 72;                    // 64-bit units per hop-pair row of the FFT scratch (64 + 8: rows of the two
@@ -63,7 +67,20 @@ constexpr size_t kRawBytes = 2 * kRawWords * 4;                                 
 constexpr size_t kScratchBytes = (size_t) kFftWarps * 2 * 4 * kRowUnits * 8;
 constexpr size_t kAudioWords = (size_t) kBins * kAudioStride;
 constexpr size_t kAudioBytes = 2 * kAudioWords * 4;                              // double-buffered
-constexpr size_t kSmemBytes = kRawBytes + kScratchBytes + kAudioBytes + 64 * 8 /* twiddles */ + 32 /* mbarriers */;
+#ifndef SL_CHAN_FIR_X2
+#define SL_CHAN_FIR_X2 0                          /* 1: the polyphase FIR on FP32x2, one fma.rn.f32x2 per tap for (re, im): bit-identical, measured equal (288.6 vs 290.5 Gsamples/s) */
+#endif
+#ifndef SL_CHAN_PACK
+#define SL_CHAN_PACK 1                            /* who scales, packs and stores a tile. 0: the AGC thread of each channel row (every store instruction touches 32 lines);
+                                                     1: the three producer warps after the FFTs of the next tile, gains handed over through shared memory, consecutive lanes
+                                                     on consecutive 16-byte pieces of a row; 2: the AGC warps, same lane mapping as 1.
+                                                     Measured (Gsamples/s): 0 -> 283, 1 -> 290 (and then the PRODUCER side is the limit: 305 with the AGC ablated, the AGC
+                                                     side alone 566), 2 -> 237 (one more barrier and a shared-memory round trip on the AGC warps' critical path) */
+#endif
+#define SL_CHAN_PACK_FFT (SL_CHAN_PACK == 1)
+constexpr int kGainStride = 20;                  // floats per row of the gain tile: 16 block gains + pad (80-byte rows: conflict-free 16-byte stores of 8 lanes)
+constexpr size_t kGainBytes = SL_CHAN_PACK != 0 ? (size_t) kBins * kGainStride * 4 : 0;
+constexpr size_t kSmemBytes = kRawBytes + kScratchBytes + kAudioBytes + 64 * 8 /* twiddles */ + 32 /* mbarriers */ + kGainBytes;
 
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk (float lo, float hi) { u64 r; asm ("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -190,7 +207,7 @@ __device__ __forceinline__ float decay_n (float x, float decay, int n)
   return x;
 }
 
-__global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_constant__ KParams P)
+__global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_kernel (const __grid_constant__ KParams P)
 {
   extern __shared__ __align__ (128) unsigned char smem[];
   uint32_t *sRaw = reinterpret_cast<uint32_t *> (smem);
@@ -198,6 +215,9 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
   float *sAudio = reinterpret_cast<float *> (smem + kRawBytes + kScratchBytes);
   float2 *sTw = reinterpret_cast<float2 *> (smem + kRawBytes + kScratchBytes + kAudioBytes);
   uint64_t *sBar = reinterpret_cast<uint64_t *> (smem + kRawBytes + kScratchBytes + kAudioBytes + 64 * 8);   // [2]: raw buffer full
+#if SL_CHAN_PACK != 0
+  float *sGain = reinterpret_cast<float *> (smem + kRawBytes + kScratchBytes + kAudioBytes + 64 * 8 + 32);     // [64][kGainStride]: gains x 32768 of the tile being packed
+#endif
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned total = P.streams * P.tiles;
@@ -237,6 +257,35 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
     u64 *scr_re = sScr + (size_t) warp * 2 * 4 * kRowUnits, *scr_im = scr_re + 4 * kRowUnits;
     const int g = lane >> 3, b = lane & 7;
     unsigned seq = 0;
+#if SL_CHAN_PACK_FFT
+    // scale (arm_scale_f32), pack (arm_float_to_q15), store of a finished tile by the 96 producer threads: the tile is 64 rows x 12
+    // float4, thread t takes the float4 t, t + 96, ... — consecutive lanes store consecutive 16-byte pieces of a channel row (192
+    // contiguous bytes per row and tile), where one thread per row made every store instruction touch 32 different lines. A
+    // float4 q4 of a row holds samples 4 q4 .. 4 q4 + 3 of blocks (4 q4) / 3 and the next one: (g0 g0 g0 g1), (g0 g0 g1 g1) or
+    // (g0 g1 g1 g1) by q4 mod 3.
+    auto pack_item = [&] (unsigned pitem, int pb) {
+      const uint32_t ptile = pitem / P.streams, ps = pitem % P.streams;
+      const int nq4 = (int) (min ((uint32_t) kTileHops, P.hops - ptile * kTileHops) / 4);
+      const float *aud = sAudio + (size_t) pb * kAudioWords;
+      uint32_t *orow0 = P.out + (size_t) ps * kBins * P.hops + (size_t) ptile * kTileHops;
+      bar_sync (3 + pb, kThreads);                                   // the AGC warps have written this tile's gains
+#pragma unroll
+      for (int i = 0; i < kBins * (kTileHops / 4) / kFftThreads; i++)
+      {
+        const int idx = tid + kFftThreads * i, row = idx / (kTileHops / 4), q4 = idx - row * (kTileHops / 4);
+        if (q4 < nq4)
+        {
+          const float4 v = *reinterpret_cast<const float4 *> (aud + row * kAudioStride + 4 * q4);
+          const int ga = (4 * q4) / 3, m = q4 - 3 * (q4 / 3);
+          const float g0 = sGain[row * kGainStride + ga], g1 = sGain[row * kGainStride + ga + 1];
+          st_na (reinterpret_cast<uint4 *> (orow0 + (size_t) row * P.hops) + q4,
+                 make_uint4 (pack_lr (v.x * g0), pack_lr (v.y * (m == 2 ? g1 : g0)), pack_lr (v.z * (m == 0 ? g0 : g1)), pack_lr (v.w * g1)));
+        }
+      }
+      bar_arrive (6 + pb, kThreads);                                 // the gain tile may be overwritten
+    };
+    static_assert (kBins * (kTileHops / 4) % kFftThreads == 0, "the pack loop covers the tile evenly");
+#endif
 
     for (unsigned item = blockIdx.x; item < total; item += gridDim.x, seq++)
     {
@@ -246,7 +295,9 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
       const uint32_t *raw = sRaw + (size_t) buf * kRawWords;
       float *audio = sAudio + (size_t) buf * kAudioWords;
       mbar_wait (sBar + buf, (seq >> 1) & 1);                        // raw tile has landed
+#if !SL_CHAN_PACK_FFT
       if (seq >= 2) bar_sync (3 + buf, kThreads);                    // the AGC warps have drained this audio buffer
+#endif                                                               // (else: these warps packed tile seq - 2 out of it themselves, after the AGC warps were done with it)
 
       const int h_base = warp * kHopsPerWarp;                        // first hop of this warp inside the tile
 #ifdef SL_CHAN_ABLATE_FFT                                            // (profiling aid: the kernel without polyphase filter and FFTs)
@@ -255,6 +306,50 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
       if ((uint32_t) h_base < hops_here)
 #endif
       {
+#if SL_CHAN_FIR_X2
+        // sliding windows: at hop m the oldest sample x_r[m-7] sits in slot (m+1)&7, the newest in slot m&7; a slot holds (re, im) as
+        // one FP32x2 register pair, so a tap is ONE fma.rn.f32x2 for both rails (each lane IEEE-identical to the scalar fmaf)
+        u64 w0[kTaps], w1[kTaps];
+        const uint32_t *rawp = raw + (size_t) h_base * kBins + lane;  // row (hop_local + 7) holds hop hop_local
+#pragma unroll
+        for (int j = 0; j < kHistHops; j++)
+        {
+          float re, im;
+          unpack_iq (rawp[j * kBins], re, im); w0[j + 1] = pk (re, im);
+          unpack_iq (rawp[j * kBins + 32], re, im); w1[j + 1] = pk (re, im);
+        }
+#pragma unroll 1
+        for (int rd = 0; rd < kHopsPerWarp / 8; rd++)
+        {
+          const int h0 = h_base + 8 * rd;
+          // ---- polyphase branch FIRs (arm_fir_f32.c: acc = sum_k state[n+k] * pCoeffs[k], oldest sample first,
+          //      pCoeffs[k] = e_r[7-k]) for 8 hops; the two hops of a pair are stored together
+#pragma unroll
+          for (int m = 0; m < 8; m += 2)
+          {
+            u64 a0[2], a1[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+            {
+              const int mm = m + e;
+              float re, im;
+              unpack_iq (rawp[(8 * rd + mm + kHistHops) * kBins], re, im); w0[mm & 7] = pk (re, im);
+              unpack_iq (rawp[(8 * rd + mm + kHistHops) * kBins + 32], re, im); w1[mm & 7] = pk (re, im);
+              u64 p0 = pk (0.f, 0.f), p1 = pk (0.f, 0.f);
+#pragma unroll
+              for (int k = 0; k < kTaps; k++)
+              {
+                const int slot = (mm + 1 + k) & 7;                   // x_r[m - 7 + k]
+                p0 = fma2 (w0[slot], pk (c0[kTaps - 1 - k], c0[kTaps - 1 - k]), p0);
+                p1 = fma2 (w1[slot], pk (c1[kTaps - 1 - k], c1[kTaps - 1 - k]), p1);
+              }
+              a0[e] = p0; a1[e] = p1;
+            }
+            // scratch row = hop pair, unit = branch; lo/hi = even/odd hop of the pair
+            scr_re[(m >> 1) * kRowUnits + lane] = pk (lo_of (a0[0]), lo_of (a0[1])); scr_im[(m >> 1) * kRowUnits + lane] = pk (hi_of (a0[0]), hi_of (a0[1]));
+            scr_re[(m >> 1) * kRowUnits + lane + 32] = pk (lo_of (a1[0]), lo_of (a1[1])); scr_im[(m >> 1) * kRowUnits + lane + 32] = pk (hi_of (a1[0]), hi_of (a1[1]));
+          }
+#else
         // sliding windows: at hop m the oldest sample x_r[m-7] sits in slot (m+1)&7, the newest in slot m&7
         float w0r[kTaps], w0i[kTaps], w1r[kTaps], w1i[kTaps];
         const uint32_t *rawp = raw + (size_t) h_base * kBins + lane;  // row (hop_local + 7) holds hop hop_local
@@ -265,7 +360,7 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
           unpack_iq (rawp[j * kBins + 32], w1r[j + 1], w1i[j + 1]);
         }
 #pragma unroll 1
-        for (int rd = 0; rd < 2; rd++)
+        for (int rd = 0; rd < kHopsPerWarp / 8; rd++)
         {
           const int h0 = h_base + 8 * rd;
           // ---- polyphase branch FIRs (arm_fir_f32.c: acc = sum_k state[n+k] * pCoeffs[k], oldest sample first,
@@ -294,6 +389,7 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
             scr_re[(m >> 1) * kRowUnits + lane] = pk (a0r[0], a0r[1]); scr_im[(m >> 1) * kRowUnits + lane] = pk (a0i[0], a0i[1]);
             scr_re[(m >> 1) * kRowUnits + lane + 32] = pk (a1r[0], a1r[1]); scr_im[(m >> 1) * kRowUnits + lane + 32] = pk (a1i[0], a1i[1]);
           }
+#endif
           __syncwarp ();
           // ---- 64-point FFT (arm_cfft_f32 len 64, forward) of 8 hops: lane (g, b) = hop pair g, column b
           u64 xr[8], xi[8];
@@ -348,7 +444,13 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
       const unsigned refill = item + 2 * gridDim.x;
       if (tid == 0 && refill < total) { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); issue_load (refill, buf); }
       bar_arrive (1 + buf, kThreads);
+#if SL_CHAN_PACK_FFT
+      if (seq >= 1) pack_item (item - gridDim.x, buf ^ 1);           // the previous tile, while the AGC warps work on this one
+#endif
     }
+#if SL_CHAN_PACK_FFT
+    if (seq >= 1) pack_item (blockIdx.x + (seq - 1) * gridDim.x, (int) ((seq - 1) & 1));
+#endif
   }
   else
   {
@@ -366,6 +468,11 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
       bar_sync (1 + buf, kThreads);                                  // audio tile complete
       // block peaks (arm_abs_f32 + arm_max_f32 over 3 samples); 4 blocks = 12 samples = 3 float4
       float pkv[kTileBlocks];
+#ifdef SL_CHAN_ABLATE_AGC                                             // (profiling aid: no peak detection — WRONG results, timing only)
+#pragma unroll
+      for (int q = 0; q < kTileBlocks; q++) pkv[q] = 1.0f;
+      if (false)
+#endif
 #pragma unroll
       for (int q = 0; q < kTileBlocks / 4; q++)
       {
@@ -438,8 +545,90 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
       st_look (P.look + slot, 2u, env);
       if (tile == P.tiles - 1) __stcg (P.env_out + (size_t) s * kBins + k, env);
 
-      // scale (arm_scale_f32), pack (arm_float_to_q15), store channel-major: 12 samples = 3 float4 in, 3 uint4 out
       const size_t orow = ((size_t) s * kBins + k) * P.hops + (size_t) tile * kTileHops;
+#if SL_CHAN_PACK == 2
+      // scale (arm_scale_f32), pack (arm_float_to_q15), store, by the 64 AGC threads together: the gains (x 32768: exact) go through
+      // shared memory, then thread t takes the float4 t, t + 64, ... of the 64 x 12 float4 tile — consecutive lanes store consecutive
+      // 16-byte pieces of a channel row (192 contiguous bytes per row and tile) instead of 32 different lines per instruction. A
+      // float4 q4 of a row holds samples 4 q4 .. 4 q4 + 3 of blocks (4 q4) / 3 and the next one: (g0 g0 g0 g1), (g0 g0 g1 g1) or
+      // (g0 g1 g1 g1) by q4 mod 3. (One gain tile: every AGC thread has passed the next tile's audio barrier before any writes it again.)
+      {
+        float4 *gr = reinterpret_cast<float4 *> (sGain + k * kGainStride);
+#pragma unroll
+        for (int q = 0; q < kTileBlocks / 4; q++)
+          gr[q] = make_float4 (4 * q < nblk ? gain[4 * q] * 32768.0f : 0.f, 4 * q + 1 < nblk ? gain[4 * q + 1] * 32768.0f : 0.f,
+                               4 * q + 2 < nblk ? gain[4 * q + 2] * 32768.0f : 0.f, 4 * q + 3 < nblk ? gain[4 * q + 3] * 32768.0f : 0.f);
+      }
+      if (P.gain_dbg || P.audio_dbg)
+      {
+#pragma unroll
+        for (int q = 0; q < kTileBlocks / 4; q++)
+          if (4 * q < nblk)
+          {
+            if (P.gain_dbg)
+            {
+              float *gd = P.gain_dbg + ((size_t) s * kBins + k) * (P.hops / kBlk) + (size_t) tile * kTileBlocks + 4 * q;
+              gd[0] = gain[4 * q]; gd[1] = gain[4 * q + 1]; gd[2] = gain[4 * q + 2]; gd[3] = gain[4 * q + 3];
+            }
+            if (P.audio_dbg)
+            {
+              float4 *ad = reinterpret_cast<float4 *> (P.audio_dbg + orow) + 3 * q;
+              ad[0] = row[3 * q]; ad[1] = row[3 * q + 1]; ad[2] = row[3 * q + 2];
+            }
+          }
+      }
+      bar_sync (6, kAgcThreads);                                      // every row's gains are in shared memory
+      {
+        const int nq4 = (int) hops_here / 4;
+        const float *aud = sAudio + (size_t) buf * kAudioWords;
+        uint32_t *orow0 = P.out + (size_t) s * kBins * P.hops + (size_t) tile * kTileHops;
+#pragma unroll
+        for (int i = 0; i < kBins * (kTileHops / 4) / kAgcThreads; i++)
+        {
+          const int idx = k + kAgcThreads * i, r = idx / (kTileHops / 4), q4 = idx - r * (kTileHops / 4);
+          if (q4 < nq4)
+          {
+            const float4 v = *reinterpret_cast<const float4 *> (aud + r * kAudioStride + 4 * q4);
+            const int ga = (4 * q4) / 3, m = q4 - 3 * (q4 / 3);
+            const float g0 = sGain[r * kGainStride + ga], g1 = sGain[r * kGainStride + ga + 1];
+            st_na (reinterpret_cast<uint4 *> (orow0 + (size_t) r * P.hops) + q4,
+                   make_uint4 (pack_lr (v.x * g0), pack_lr (v.y * (m == 2 ? g1 : g0)), pack_lr (v.z * (m == 0 ? g0 : g1)), pack_lr (v.w * g1)));
+          }
+        }
+      }
+      bar_arrive (3 + buf, kThreads);                                // audio buffer drained
+#elif SL_CHAN_PACK_FFT
+      // hand the gains (x 32768: exact) to the producer warps, which scale, pack and store the tile; the gain tile has one buffer,
+      // free once the previous tile is packed — long ago: that started when this tile's audio was complete
+      if (seq >= 1) bar_sync (6 + (buf ^ 1), kThreads);
+      {
+        float4 *gr = reinterpret_cast<float4 *> (sGain + k * kGainStride);
+#pragma unroll
+        for (int q = 0; q < kTileBlocks / 4; q++)
+          gr[q] = make_float4 (4 * q < nblk ? gain[4 * q] * 32768.0f : 0.f, 4 * q + 1 < nblk ? gain[4 * q + 1] * 32768.0f : 0.f,
+                               4 * q + 2 < nblk ? gain[4 * q + 2] * 32768.0f : 0.f, 4 * q + 3 < nblk ? gain[4 * q + 3] * 32768.0f : 0.f);
+      }
+      if (P.gain_dbg || P.audio_dbg)
+      {
+#pragma unroll
+        for (int q = 0; q < kTileBlocks / 4; q++)
+          if (4 * q < nblk)
+          {
+            if (P.gain_dbg)
+            {
+              float *gd = P.gain_dbg + ((size_t) s * kBins + k) * (P.hops / kBlk) + (size_t) tile * kTileBlocks + 4 * q;
+              gd[0] = gain[4 * q]; gd[1] = gain[4 * q + 1]; gd[2] = gain[4 * q + 2]; gd[3] = gain[4 * q + 3];
+            }
+            if (P.audio_dbg)
+            {
+              float4 *ad = reinterpret_cast<float4 *> (P.audio_dbg + orow) + 3 * q;
+              ad[0] = row[3 * q]; ad[1] = row[3 * q + 1]; ad[2] = row[3 * q + 2];
+            }
+          }
+      }
+      bar_arrive (3 + buf, kThreads);                                // (after the debug taps: they read the audio row once more)
+#else
+      // scale (arm_scale_f32), pack (arm_float_to_q15), store channel-major: 12 samples = 3 float4 in, 3 uint4 out
       uint4 *dst = reinterpret_cast<uint4 *> (P.out + orow);
 #pragma unroll
       for (int q = 0; q < kTileBlocks / 4; q++)
@@ -462,6 +651,7 @@ __global__ void __launch_bounds__ (kThreads, 3) chan64_f32_kernel (const __grid_
           }
         }
       bar_arrive (3 + buf, kThreads);                                // audio buffer drained
+#endif
     }
   }
 }
