@@ -32,6 +32,10 @@ constexpr int kKSteps = 11;              // (128 + 48) frames * 2 bytes / 32
 constexpr int kBStep = 18 * 256;         // B bytes per K-step and rail: 18 row groups (3 digits x 48) x 2 chunks x 128 B
 constexpr int kRawRow = kSuper * 4 + 16;
 constexpr int kHistRow = kHist * 4 + 16;
+#ifndef SL_AMTC_MMA_UNROLL
+#define SL_AMTC_MMA_UNROLL 1                     /* 1: rolled MMA issue loops (instruction fetch, as in the TX / q15 kernels); 10: unrolled */
+#endif
+constexpr int kMmaUnroll = SL_AMTC_MMA_UNROLL, kRailUnroll = SL_AMTC_MMA_UNROLL > 1 ? 2 : 1;
 constexpr int kSets = 2, kEpiWarps = 4 * kSets, kConvWarps = 2, kRawStages = 2;
 constexpr int kMmaWarp = kEpiWarps + kConvWarps, kProdWarp = kMmaWarp + 1;
 constexpr int kThreads = 32 * (kProdWarp + 1);
@@ -135,28 +139,35 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
 
   if (warp == kProdWarp)
   {
-    // ======================================= bulk-copy producer =======================================
-    if (lane == 0)
+    // ======================================= bulk-copy producer (as sl_rx_ssb_tc.cu) =======================================
+    // lane j < 8 owns row j of the group: it reads its channel index once per group and issues the row's copies, so the eight
+    // copies of a supertile go out together instead of behind eight dependent index loads of one lane
     {
       unsigned kk = 0;
       for (uint32_t g = blockIdx.x; g < P.n_groups; g += gridDim.x)
+      {
+        const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
+        const uint32_t c = P.chan[gs + min ((uint32_t) (lane & 7), nv - 1u)];
+        const uint32_t *src = P.in + (size_t) c * P.frames;
         for (uint32_t k = 0; k < supers; k++, kk++)
         {
           const int rb = kk & 1;
           const uint32_t nfr = min ((uint32_t) kSuper, P.frames - k * kSuper);
-          mbar_wait_guarded (raw_empty + rb, ((kk >> 1) & 1) ^ 1);
-          mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
-          const uint32_t gs = P.gstart[g], nv = P.ginfo[g] >> 8;
-#pragma unroll 1
-          for (int j = 0; j < kJ; j++)
+          if (lane == 0)
           {
-            const uint32_t c = P.chan[gs + min ((uint32_t) j, nv - 1u)];
-            bulk_g2s (sRaw + (rb * kJ + j) * kRawRow, P.in + (size_t) c * P.frames + (size_t) k * kSuper, nfr * 4u, raw_full + rb);
-            if (k == 0) bulk_g2s (sHist + (rb * kJ + j) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
+            mbar_wait_guarded (raw_empty + rb, ((kk >> 1) & 1) ^ 1);
+            mbar_expect_tx (raw_full + rb, kJ * nfr * 4u + (k == 0 ? kJ * kHist * 4u : 0u));
           }
+          __syncwarp ();
+          if (lane < kJ)
+          {
+            bulk_g2s (sRaw + (rb * kJ + lane) * kRawRow, src + (size_t) k * kSuper, nfr * 4u, raw_full + rb);
+            if (k == 0) bulk_g2s (sHist + (rb * kJ + lane) * kHistRow, P.ovl_in + (size_t) c * kHist, kHist * 4u, raw_full + rb);
+          }
+          __syncwarp ();
         }
+      }
     }
-    __syncwarp ();
   }
   else if (warp >= kEpiWarps && warp < kEpiWarps + kConvWarps)
   {
@@ -267,7 +278,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
         const uint32_t aHi = (aBase + ab * 2 * kPlaneBytes) >> 4, aLo = aHi + (kPlaneBytes >> 4);
         if (elect_one ())
         {
-#pragma unroll
+#pragma unroll kRailUnroll
           for (int rail = 0; rail < 2; rail++)
           {
             // per rail: columns [0,48) weight 2^24 = mh h2, [48,96) 2^16 = mh h1 + ml h2, [96,144) 2^8 = mh h0 + ml h1, [144,192) 1 = ml h0
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_am_tc_kernel (const __grid_co
             umma_i8 (d, kDescA | aHi, kDescB | b0, id_ss48, 0u);
             umma_i8 (d + 48, kDescA | aLo, kDescB | b0, id_us144, 0u);
             umma_i8 (d + 48, kDescA | aHi, kDescB | (b0 + ((6 * 256) >> 4)), id_ss96, 1u);
-#pragma unroll
+#pragma unroll kMmaUnroll
             for (int ks = 1; ks < kKSteps; ks++)
             {
               const uint32_t ao = (uint32_t) (ks * 2 * kChunkBytes) >> 4, bo = (uint32_t) (ks * kBStep) >> 4;
