@@ -99,7 +99,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
   uint64_t *bars = reinterpret_cast<uint64_t *> (smem + Smem::bars);
   static_assert (kRawStages >= 2 && kRawStages <= 4, "barrier layout");
   uint64_t *raw_full = bars, *raw_empty = bars + 4, *a_full = bars + 8, *a_empty = bars + 10, *t_empty = bars + 12;
-  uint64_t *done_bar = bars + 13, *b_full = bars + 15, *t_full = bars + 16, *p_bar = bars + 18;
+  uint64_t *b_full = bars + 15, *t_full = bars + 16, *p_bar = bars + 18;
   // p_bar has FOUR slots: a set arrives for supertile kk BEFORE it waits for its predecessor's peaks, so the other set can arrive for
   // kk + 1 while a warp of this one has not yet looked at kk - 1 (it does whenever the global load at the start of a group takes longer
   // than the MMAs of kk + 1: seen as a hang at 8192 channels). On two slots kk + 1 completes the phase after kk - 1's on the same
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
       mbar_init (t_full + i, 1);
     }
     for (int i = 0; i < kPSlots; i++) mbar_init (p_bar + i, 4);
-    mbar_init (t_empty, SL_Q15TC_SPLIT ? 4 * kSets : 4); mbar_init (b_full, 1); mbar_init (done_bar, 1);
+    mbar_init (t_empty, SL_Q15TC_SPLIT ? 4 * kSets : 4); mbar_init (b_full, 1);
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp)
@@ -157,11 +157,12 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
           }
         }
       // Watchdog (sl_tc_common.cuh): in this kernel only the producer counts its failed polls (the counter in the MMA issuer's waits cost
-      // 5 %: 466 vs 492 Gsamples/s) — a deadlock reaches it through the raw stages — and it stays until the MMAs of the CTA's last
-      // supertile have completed, so the tail after its last copy is covered too. That is a barrier of its own, committed once: a parity
-      // wait on a t_full slot is only safe for a thread that follows the slot phase by phase (a late observer cannot tell phase n from
-      // phase n + 2 — compute-sanitizer's timing showed exactly that).
-      mbar_wait_guarded (done_bar, 0);
+      // 5 %: 466 vs 492 Gsamples/s, and so did one more commit of the MMA issuer to a completion barrier) — a deadlock reaches it
+      // through the raw stages. After its last copy it goes on waiting for the stages as if it had more to load, which covers the
+      // pipeline up to the MMAs of the CTA's third-last supertile (a stage is freed once its planes are written, and that needs the
+      // MMAs two supertiles back). Only a barrier the producer follows phase by phase will do here: a late parity wait on a t_full
+      // slot cannot tell phase n from phase n + 2 (compute-sanitizer's timing showed exactly that).
+      for (unsigned i = kk; i < kk + kRawStages; i++) mbar_wait_guarded (raw_empty + i % kRawStages, ((i / kRawStages) & 1) ^ 1);
     }
     __syncwarp ();
   }
@@ -280,8 +281,6 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
         }
         __syncwarp ();
       }
-    if (elect_one ()) umma_commit (done_bar);                                  // every MMA of this CTA has completed (the producer's watchdog waits here)
-    __syncwarp ();
   }
   else
   {
@@ -505,6 +504,10 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_q15_tc_kernel (const __grid_c
             }
           }
         }
+        // The window above may reach back to tile kk - 2 (a short last supertile), which this set's NEXT supertile kk + 2 overwrites
+        // — a warp that is through here could be there before a slower one has read it (inside a group only tiles kk and kk - 1
+        // are read, and kk + 2 cannot touch those). Found under compute-sanitizer's timing; one barrier per group closes it.
+        if (k + 1 == supers) named_bar (1 + es, 128);
       }
 #endif
     }
