@@ -42,6 +42,7 @@
 namespace sl {
 
 namespace {
+#include "sl_stress.cuh"
 
 constexpr int kBins = 64;                        // branches = FFT length = decimation
 constexpr int kTaps = 8;                         // taps per branch (prototype = 512 taps)
@@ -153,6 +154,7 @@ __device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, unsigned bytes)
 }
 __device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
 {
+  sl_jitter ();
   asm volatile (
       "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
       ::"r"(smem_u32 (bar)), "r"(parity) : "memory");
@@ -178,12 +180,13 @@ __device__ __forceinline__ unsigned long long ld_look (const unsigned long long 
 }
 __device__ __forceinline__ void st_look (unsigned long long *p, unsigned status, float v)
 {
+  sl_jitter ();
   asm volatile ("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long) status << 32) | (unsigned long long) __float_as_uint (v)) : "memory");
 }
 // named barriers (like the RX kernel): 1,2 = audio buffer 0/1 full; 3,4 = audio buffer 0/1 empty (all 160 threads take
 // part in each, one side syncs, the other arrives); 5 = the FFT warps among themselves; 6 = the AGC warps
-__device__ __forceinline__ void bar_sync (int id, int n) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive (int id, int n) { asm volatile ("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync (int id, int n) { sl_jitter (); asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive (int id, int n) { sl_jitter (); asm volatile ("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct KParams
 {

@@ -32,6 +32,7 @@
 namespace sl {
 
 namespace {
+#include "sl_stress.cuh"
 
 constexpr int kN = 512;                          // FFT length
 constexpr int kHop = 384;                        // new frames per FFT frame
@@ -196,10 +197,12 @@ __device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, unsigned bytes)
 }
 __device__ __forceinline__ void mbar_arrive (uint64_t *bar)
 {
+  sl_jitter ();
   asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32 (bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
 {
+  sl_jitter ();
   asm volatile (
 #ifdef SL_RX_WAIT_HINT
       // the time hint lets the hardware park the warp until the phase flips instead of spinning through issue slots

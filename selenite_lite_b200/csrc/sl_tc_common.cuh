@@ -10,28 +10,15 @@ __device__ __forceinline__ void mbar_expect_tx (uint64_t *bar, unsigned bytes)
 {
   asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32 (bar)), "r"(bytes) : "memory");
 }
-// Stress build (-DSL_TC_STRESS, tools/ab_build.sh): every hand-over point (arrive, wait) first sleeps a pseudo-random time of up to
-// ~16 us in about one call out of four, per warp — roles and warps of one role drift apart by several supertiles' worth of time, which
-// is what it takes to show a hand-over that only holds for the usual timing (the two faults compute-sanitizer's timing found in the
-// q15 kernel). The GPU tests must pass unchanged on that build.
-#ifdef SL_TC_STRESS
-__device__ __forceinline__ void tc_jitter ()
-{
-  unsigned t; asm volatile ("mov.u32 %0, %%clock;" : "=r"(t));
-  unsigned h = (t ^ (threadIdx.x >> 5) * 2654435761u) * 2246822519u;
-  if ((h >> 28) < 4u) __nanosleep ((h >> 8) & 0x3FFFu);
-}
-#else
-__device__ __forceinline__ void tc_jitter () {}
-#endif
+#include "sl_stress.cuh"
 __device__ __forceinline__ void mbar_arrive (uint64_t *bar)
 {
-  tc_jitter ();
+  sl_jitter ();
   asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32 (bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
 {
-  tc_jitter ();
+  sl_jitter ();
   asm volatile ("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
                 ::"r"(smem_u32 (bar)), "r"(parity) : "memory");
 }
@@ -46,7 +33,7 @@ __device__ __forceinline__ void mbar_wait (uint64_t *bar, unsigned parity)
 __device__ __forceinline__ void mbar_wait_guarded (uint64_t *bar, unsigned parity)
 {
 #if SL_TC_WAIT_LIMIT > 0
-  tc_jitter ();
+  sl_jitter ();
   asm volatile ("{\n .reg .pred p;\n .reg .u32 n;\n mov.u32 n, 0;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n"
                 " add.u32 n, n, 1;\n setp.lt.u32 p, n, %2;\n @p bra WAIT_%=;\n trap;\n DONE_%=:\n}\n"
                 ::"r"(smem_u32 (bar)), "r"(parity), "n"(SL_TC_WAIT_LIMIT) : "memory");
@@ -96,7 +83,7 @@ __device__ __forceinline__ void bulk_s2g (void *dst, const void *src, unsigned b
 {
   asm volatile ("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32 (src)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void named_bar (int id, int threads) { tc_jitter (); asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar (int id, int threads) { sl_jitter (); asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // ---- tcgen05 ----
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes);
