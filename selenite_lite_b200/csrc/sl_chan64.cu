@@ -71,6 +71,12 @@ constexpr size_t kAudioBytes = 2 * kAudioWords * 4;                             
 #ifndef SL_CHAN_FIR_X2
 #define SL_CHAN_FIR_X2 0                          /* 1: the polyphase FIR on FP32x2, one fma.rn.f32x2 per tap for (re, im): bit-identical, measured equal (288.6 vs 290.5 Gsamples/s) */
 #endif
+#ifndef SL_CHAN_EARLY_LOOK
+#define SL_CHAN_EARLY_LOOK 0                      /* 1: look-back words fetched before the wait for the tile's audio: measured slower (283 vs 290 Gsamples/s) */
+#endif
+#ifndef SL_CHAN_LAST_REFILLS
+#define SL_CHAN_LAST_REFILLS 0                    /* 1: no barrier among the producer warps, the last one done with a raw buffer refills it: measured slower (284 vs 290) */
+#endif
 #ifndef SL_CHAN_PACK
 #define SL_CHAN_PACK 1                            /* who scales, packs and stores a tile. 0: the AGC thread of each channel row (every store instruction touches 32 lines);
                                                      1: the three producer warps after the FFTs of the next tile, gains handed over through shared memory, consecutive lanes
@@ -218,6 +224,7 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
   float *sAudio = reinterpret_cast<float *> (smem + kRawBytes + kScratchBytes);
   float2 *sTw = reinterpret_cast<float2 *> (smem + kRawBytes + kScratchBytes + kAudioBytes);
   uint64_t *sBar = reinterpret_cast<uint64_t *> (smem + kRawBytes + kScratchBytes + kAudioBytes + 64 * 8);   // [2]: raw buffer full
+  unsigned *sCnt = reinterpret_cast<unsigned *> (smem + kRawBytes + kScratchBytes + kAudioBytes + 64 * 8 + 16);   // [2]: producer warps done with a raw buffer
 #if SL_CHAN_PACK != 0
   float *sGain = reinterpret_cast<float *> (smem + kRawBytes + kScratchBytes + kAudioBytes + 64 * 8 + 32);     // [64][kGainStride]: gains x 32768 of the tile being packed
 #endif
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned total = P.streams * P.tiles;
 
-  if (tid == 0) { mbar_init (sBar, 1); mbar_init (sBar + 1, 1); }
+  if (tid == 0) { mbar_init (sBar, 1); mbar_init (sBar + 1, 1); sCnt[0] = sCnt[1] = 0u; }
   if (tid < 64) sTw[tid] = P.tw[tid];
   __syncthreads ();
 
@@ -443,9 +450,24 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
       // carried FIR history for the next call: the last 7 hops of the stream (rows hops_here .. hops_here + 6)
       if (tile == P.tiles - 1)
         for (int i = tid; i < kHistHops * kBins; i += kFftThreads) P.hist_out[(size_t) s * kHistHops * kBins + i] = raw[hops_here * kBins + i];
-      bar_sync (5, kFftThreads);                                     // every FFT warp is done with raw[buf]; audio[buf] complete
       const unsigned refill = item + 2 * gridDim.x;
+#if SL_CHAN_LAST_REFILLS
+      // the warp that is LAST done with raw[buf] (a shared-memory counter) issues the refill: nobody waits for the slowest warp
+      __syncwarp ();
+      if (lane == 0)
+      {
+        __threadfence_block ();
+        if (atomicAdd (sCnt + buf, 1u) == (unsigned) kFftWarps - 1u)
+        {
+          sCnt[buf] = 0u;
+          __threadfence_block ();
+          if (refill < total) { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); issue_load (refill, buf); }
+        }
+      }
+#else
+      bar_sync (5, kFftThreads);                                     // every FFT warp is done with raw[buf]; audio[buf] complete
       if (tid == 0 && refill < total) { asm volatile ("fence.proxy.async.shared::cta;" ::: "memory"); issue_load (refill, buf); }
+#endif
       bar_arrive (1 + buf, kThreads);
 #if SL_CHAN_PACK_FFT
       if (seq >= 1) pack_item (item - gridDim.x, buf ^ 1);           // the previous tile, while the AGC warps work on this one
@@ -468,6 +490,14 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
       const uint32_t hops_here = min ((uint32_t) kTileHops, P.hops - tile * kTileHops);
       const int nblk = hops_here / kBlk;
       const float4 *row = reinterpret_cast<const float4 *> (sAudio + (size_t) buf * kAudioWords + k * kAudioStride);
+#if SL_CHAN_EARLY_LOOK
+      // the look-back words of the predecessors do not depend on this tile: fetched before the wait for its audio, so the round trip
+      // to L2 runs behind the barrier, the peak detection and the zero-start walk (re-fetched below if they do not suffice yet)
+      const unsigned long long *lk = P.look + (size_t) s * P.tiles * kBins + k;
+      unsigned long long wd[kLookBackMax];
+#pragma unroll
+      for (int d = 0; d < kLookBackMax; d++) { const int j = (int) tile - 1 - d; wd[d] = (j >= 0) ? ld_look (lk + (size_t) j * kBins) : (2ull << 32); }
+#endif
       bar_sync (1 + buf, kThreads);                                  // audio tile complete
       // block peaks (arm_abs_f32 + arm_max_f32 over 3 samples); 4 blocks = 12 samples = 3 float4
       float pkv[kTileBlocks];
@@ -502,13 +532,18 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
       if (false)
 #endif
       {
+#if !SL_CHAN_EARLY_LOOK
         const unsigned long long *lk = P.look + (size_t) s * P.tiles * kBins + k;
         unsigned long long wd[kLookBackMax];
+#endif
         int dstar;
-        for (;;)
+        for (bool first = true;; first = false)
         {
+          if (!SL_CHAN_EARLY_LOOK || !first)
+          {
 #pragma unroll
-          for (int d = 0; d < kLookBackMax; d++) { const int j = (int) tile - 1 - d; wd[d] = (j >= 0) ? ld_look (lk + (size_t) j * kBins) : (2ull << 32); }
+            for (int d = 0; d < kLookBackMax; d++) { const int j = (int) tile - 1 - d; wd[d] = (j >= 0) ? ld_look (lk + (size_t) j * kBins) : (2ull << 32); }
+          }
           dstar = -1;
           bool ok = true;
 #pragma unroll
