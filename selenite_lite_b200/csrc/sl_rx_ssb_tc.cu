@@ -113,7 +113,7 @@ struct Smem
   static constexpr size_t raw = b + b_bytes;                            // [stages][8 rows]
   static constexpr size_t hist = raw + kRawStages * kJ * kRawRow;       // [stages][8 rows] carried tail of the previous call
   static constexpr size_t out = hist + kRawStages * kJ * kHistRow;      // [8 rows] packed int16 output of one supertile, stored by bulk copies
-  static constexpr size_t wsum = out + (SL_TC_BULKOUT ? kEpiWarps * kOutStage : 0);                    // [sets][4 warps][8][4] floats
+  static constexpr size_t wsum = out + (SL_TC_BULKOUT == 2 ? kJ * kRawRow : SL_TC_BULKOUT ? kEpiWarps * kOutStage : 0);                    // [sets][4 warps][8][4] floats
   static constexpr size_t pk = wsum + kSets * 4 * kJ * 4 * 4;           // [sets][halves][16][8] floats
   static constexpr size_t carry_s = pk + kSets * kHalves * kQ * kJ * 4; // [2][8][4] floats
   static constexpr size_t carry_e = carry_s + 2 * kJ * 4 * 4;           // [2][8] floats
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
       mbar_init (t_full + i, 1); mbar_init (t_full + 2 + i, 1); mbar_init (t_empty + i, (kPair ? 2 : 1) * 4 * kHalves); mbar_init (s_bar + i, kJ); mbar_init (e_bar + i, kJ);
     }
     mbar_init (b_full, 1); mbar_init (drain, 1); mbar_init (b_ready, 1);
-    for (int i = 0; i < 4; i++) mbar_init (out_free + i, 1);
+    for (int i = 0; i < 4; i++) mbar_init (out_free + i, 1);                        // (slot 0 in use: SL_TC_BULKOUT == 2)
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 64) sMp[(tid >> 4) * 20 + (tid & 15)] = P.tab.Mp[tid >> 4][tid & 15];
@@ -919,7 +919,36 @@ __global__ void __launch_bounds__ (kThreads, 1) rx_ssb_tc_kernel (const __grid_c
           }
           if (P.gain_dbg) P.gain_dbg[(size_t) c * (P.frames / kBlk) + t0 / kBlk] = gain;
         }
-#if SL_TC_BULKOUT
+#if SL_TC_BULKOUT == 2
+        // ---- gain (arm_scale_f32), pack (arm_float_to_q15), store through ONE shared-memory stage of a whole supertile ([8 channels][768
+        // frames], rows padded like the raw stage: a 16-byte store of the 8 lanes of a quarter warp hits 8 different bank groups) that the
+        // two epilogue sets use in turn: supertile kk takes it when kk - 1's bulk copies have read it (out_free, one phase per
+        // supertile), the set's 128 threads lay their blocks in, and lanes 0..7 of the set's first warp send ONE 3072-byte bulk copy
+        // per channel — 8 copies per supertile instead of 768 line-sized store wavefronts.
+        {
+          const float g15 = gain * 32768.0f;                                       // exact: power of two
+          if (kk != 0) mbar_wait (out_free, (kk - 1) & 1);
+          {
+            uint4 *dst = reinterpret_cast<uint4 *> (sOut + j * kRawRow + q * (kBlk * 4));
+#pragma unroll
+            for (int n = 0; n < kBlk; n += 4)
+              dst[n / 4] = make_uint4 (pack_lr (y[n] * g15), pack_lr (y[n + 1] * g15), pack_lr (y[n + 2] * g15), pack_lr (y[n + 3] * g15));
+          }
+          asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+          named_bar (9 + es, 128);
+          if (w == 0)
+          {
+            if (lane < kJ)
+            {
+              if (jvalid) bulk_s2g (P.out + (size_t) c * P.frames + (size_t) k * kSuper, sOut + j * kRawRow, nfr * 4u);
+              asm volatile ("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile ("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            __syncwarp ();
+            if (lane == 0) mbar_arrive (out_free);
+          }
+        }
+#elif SL_TC_BULKOUT
         // ---- gain (arm_scale_f32), pack (arm_float_to_q15), store through a shared-memory stage. A warp holds 4 consecutive blocks of
         // 8 channels = 768 contiguous bytes per channel, but as direct stores every instruction touches 32 different lines (32 L1
         // wavefronts). Here the warp lays two blocks of all eight channels at a time into its private stage (rows of 384 + 16 bytes:
