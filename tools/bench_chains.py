@@ -54,6 +54,12 @@ def main():
             x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
             d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15); y = torch.empty_like(x)
             ms = timeit(lambda: d.rx_process(x, y), args.steps); n = C * T; name = "rx_ssb_q15 (%d channels x %d s)" % (C, args.seconds)
+        elif which == "am":
+            C, T = args.rx_channels, 48000 * args.seconds // 384 * 384
+            x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
+            d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32); d.DSP_Set_Mode(slb.MODE_AM); y = torch.empty_like(x)
+            ms = timeit(lambda: d.rx_process(x, y), args.steps); n = C * T
+            name = "rx am (%s, %d channels x %d s)" % ("complex-detector tensor-core kernel" if os.environ.get("SELENITE_B200_AM_PATH") == "tc" else "FFT kernel", C, args.seconds)
         elif which == "fm":
             C, T = args.rx_channels, 48000 * args.seconds // 384 * 384
             x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
