@@ -326,10 +326,18 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         n_e2e = max(3, min(args.steps, 5))
+        e2e_steps = []
         for _ in range(n_e2e):
+            t1 = time.perf_counter()
             d2.rx_process_pinned(xh, yh)                     # returns after the D2H copy of the result has landed
+            e2e_steps.append(time.perf_counter() - t1)
         barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
+        # per-step wall times of this rank; the reported figure uses the MEDIAN step (max over ranks), so that one step hit by another
+        # tenant of the host (seen once: 62 ms instead of 42) does not decide the number; the mean is kept beside it
+        dt_mean = max_over_ranks(time.perf_counter() - t0)
+        dt = max_over_ranks(sorted(e2e_steps)[len(e2e_steps) // 2]) * n_e2e
+        if os.environ.get("BENCH_DEBUG"):
+            print("e2e step ms", [round(v * 1e3, 2) for v in e2e_steps], file=sys.stderr)
         # ceiling: the same bytes as ONE contiguous pinned cudaMemcpyAsync each way, both directions at once, all ranks at once
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
 
@@ -339,17 +347,21 @@ def run_ours(args):
             with torch.cuda.stream(s_out):
                 yh.copy_(y, non_blocking=True)
         duplex(); barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            duplex()
-        barrier()
-        dt_c = max_over_ranks(time.perf_counter() - t0)
+        dt_c = None
+        for _ in range(3):                                   # a ceiling is the best the link does: best of three rounds (a round disturbed by
+            t0 = time.perf_counter()                         # another process's driver call once read 33 GB/s next to an e2e of 44)
+            for _ in range(n_e2e):
+                duplex()
+            barrier()
+            r = max_over_ranks(time.perf_counter() - t0)
+            dt_c = r if dt_c is None else min(dt_c, r)
         ceil_gbs = C * T * 4 * n_e2e / dt_c / 1e9            # per GPU, each way
         e2e_val = samples_per_step * n_e2e / dt / 1e6
         ceil_val = samples_per_step * n_e2e / dt_c / 1e6
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": C * T * 4 * world, "d2h_bytes_per_step": C * T * 4 * world,
-               "steps": n_e2e, "pcie_ceiling_gbs": ceil_gbs, "pcie_ceiling_msamples": ceil_val, "frac_of_ceiling": e2e_val / ceil_val,
-               "ceiling_how": "same bytes as one contiguous pinned cudaMemcpyAsync H2D + one D2H per step on two streams, every rank at once, GB/s per GPU each way",
+               "steps": n_e2e, "statistic": "median step (max over ranks); mean-based value in value_mean", "value_mean": samples_per_step * n_e2e / dt_mean / 1e6,
+               "pcie_ceiling_gbs": ceil_gbs, "pcie_ceiling_msamples": ceil_val, "frac_of_ceiling": e2e_val / ceil_val,
+               "ceiling_how": "same bytes as one contiguous pinned cudaMemcpyAsync H2D + one D2H per step on two streams, every rank at once, GB/s per GPU each way, best of three rounds",
                "host_cores_per_rank": cores_per_rank,
                "path": "slb_rx_process_host: pinned host -> strided H2D -> rx_ssb_tc_kernel -> strided D2H, time slices of all channels, copies and kernels on 3 streams"}
         del xh, yh, d2
