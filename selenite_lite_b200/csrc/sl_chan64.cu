@@ -537,6 +537,7 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
         unsigned long long wd[kLookBackMax];
 #endif
         int dstar;
+        unsigned spins = 0;
         for (bool first = true;; first = false)
         {
           if (!SL_CHAN_EARLY_LOOK || !first)
@@ -552,6 +553,7 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
 #pragma unroll
           for (int d = 0; d < kLookBackMax; d++) if (d < dstar && (unsigned) (wd[d] >> 32) < 1u) ok = false;   // everything nearer has an aggregate
           if (ok) break;
+          if (++spins > (1u << 23)) __trap ();                                // (seconds: a predecessor tile never published — an error, not a hung GPU)
           __nanosleep (40);
         }
         // fold forward: env_end(i) = max(E0(i), decay^16(env_end(i-1))), every predecessor tile is a full one

@@ -147,6 +147,9 @@ __device__ __forceinline__ unsigned ld_acquire (const unsigned *p)
 }
 // polling load for the hand-over spin: coherent at GPU scope but WITHOUT acquire semantics, so the loop does not
 // invalidate the SM's L1 on every iteration (ld.acquire compiles to LDG.STRONG + CCTL.IVALL); one acquire follows.
+// watchdog of the inter-CTA hand-over polls: a tile's predecessor is published within microseconds (the grid is launched cooperatively,
+// so it is resident); 2^23 polls of >= 32 ns + an L2 round trip are several seconds
+constexpr unsigned kSpinLimit = 1u << 23;
 __device__ __forceinline__ unsigned ld_relaxed (const unsigned *p)
 {
   unsigned v;
@@ -574,7 +577,8 @@ __global__ void __launch_bounds__ (kThreads, SL_RX_CTAS) ssb_f32_kernel
         if (lane == 0)
         {
           const unsigned want = P.flag_base + it.seg ();
-          while (ld_relaxed (P.flag + c) != want) __nanosleep (32);
+          for (unsigned spins = 0; ld_relaxed (P.flag + c) != want; __nanosleep (32))
+            if (++spins > kSpinLimit) __trap ();                                   // (seconds: the predecessor tile never arrived — an error, not a hung GPU)
           (void) ld_acquire (P.flag + c);
         }
         __syncwarp ();
@@ -657,7 +661,8 @@ __global__ void __launch_bounds__ (kThreads, SL_RX_CTAS) ssb_f32_kernel
         if (lane == 0)
         {
           const unsigned want = P.flag_base + it.seg ();
-          while (ld_relaxed (P.flag + c) != want) __nanosleep (32);
+          for (unsigned spins = 0; ld_relaxed (P.flag + c) != want; __nanosleep (32))
+            if (++spins > kSpinLimit) __trap ();                                   // (seconds: the predecessor tile never arrived — an error, not a hung GPU)
           (void) ld_acquire (P.flag + c);
         }
         __syncwarp ();
