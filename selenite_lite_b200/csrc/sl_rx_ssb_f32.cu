@@ -80,13 +80,13 @@ template <bool kTx> struct Smem
 // l1tex__data_pipe_lsu_wavefronts 84 % before this swizzle, half of all store wavefronts were bank conflicts), so the
 // layout is chosen to make every access pattern of the three passes conflict-free with 64-bit accesses: bits [4:1]
 // of the word index are XORed with bits [7:4]. Pairs (2k, 2k+1) stay adjacent and 8-byte aligned.
-__device__ __forceinline__ int phys (int i) { return i ^ (((i >> 4) & 15) << 1); }
+[[maybe_unused]] __device__ __forceinline__ int phys (int i) { return i ^ (((i >> 4) & 15) << 1); }   // (the definition of record: call sites fold it)
 
 // ---- packed FP32x2: one 64-bit register pair holds the same quantity for butterfly A (lo) and butterfly B (hi) ----
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pk (float lo, float hi) { u64 r; asm ("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float lo_of (u64 a) { float x, y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return x; }
-__device__ __forceinline__ float hi_of (u64 a) { float x, y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return y; }
+__device__ __forceinline__ float lo_of (u64 a) { float x; [[maybe_unused]] float y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return x; }
+__device__ __forceinline__ float hi_of (u64 a) { [[maybe_unused]] float x; float y; asm ("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a)); return y; }
 __device__ __forceinline__ u64 pair_lo (u64 a, u64 b) { return pk (lo_of (a), lo_of (b)); }   // 2x2 transpose helpers
 __device__ __forceinline__ u64 pair_hi (u64 a, u64 b) { return pk (hi_of (a), hi_of (b)); }
 __device__ __forceinline__ u64 add2 (u64 a, u64 b) { u64 r; asm ("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -165,10 +165,6 @@ __device__ __forceinline__ void st_release (unsigned *p, unsigned v)
 __device__ __forceinline__ void st_na (uint4 *p, uint4 v)
 {
   asm volatile ("st.global.L1::no_allocate.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void st_na (uint32_t *p, uint32_t v)
-{
-  asm volatile ("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_lr (float x_times_32768)
 {
