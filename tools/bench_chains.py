@@ -54,6 +54,11 @@ def main():
             x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
             d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_Q15); y = torch.empty_like(x)
             ms = timeit(lambda: d.rx_process(x, y), args.steps); n = C * T; name = "rx_ssb_q15 (%d channels x %d s)" % (C, args.seconds)
+        elif which == "pass":
+            C, T = args.rx_channels, 48000 * args.seconds // 384 * 384
+            x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
+            d = slb.DspIf(C, chain=slb.CHAIN_PASS); y = torch.empty_like(x)
+            ms = timeit(lambda: d.rx_process(x, y), args.steps); n = C * T; name = "pass (the firmware as shipped: bit-exact copy, %d channels x %d s)" % (C, args.seconds)
         elif which == "am":
             C, T = args.rx_channels, 48000 * args.seconds // 384 * 384
             x = torch.randint(-8000, 8000, (C, T, 2), dtype=torch.int16, device=dev, generator=g)
