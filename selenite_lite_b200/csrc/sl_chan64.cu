@@ -77,6 +77,10 @@ constexpr size_t kAudioBytes = 2 * kAudioWords * 4;                             
 #ifndef SL_CHAN_LAST_REFILLS
 #define SL_CHAN_LAST_REFILLS 0                    /* 1: no barrier among the producer warps, the last one done with a raw buffer refills it: measured slower (284 vs 290) */
 #endif
+#ifndef SL_CHAN_RD_UNROLL
+#define SL_CHAN_RD_UNROLL 1
+#endif
+constexpr int kRdUnroll = SL_CHAN_RD_UNROLL;
 #ifndef SL_CHAN_PACK
 #define SL_CHAN_PACK 1                            /* who scales, packs and stores a tile. 0: the AGC thread of each channel row (every store instruction touches 32 lines);
                                                      1: the three producer warps after the FFTs of the next tile, gains handed over through shared memory, consecutive lanes
@@ -315,7 +319,7 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
           unpack_iq (rawp[j * kBins], re, im); w0[j + 1] = pk (re, im);
           unpack_iq (rawp[j * kBins + 32], re, im); w1[j + 1] = pk (re, im);
         }
-#pragma unroll 1
+#pragma unroll kRdUnroll
         for (int rd = 0; rd < kHopsPerWarp / 8; rd++)
         {
           const int h0 = h_base + 8 * rd;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__ (kThreads, kFftWarps == 3 ? 3 : 2) chan64_f32_
           unpack_iq (rawp[j * kBins], w0r[j + 1], w0i[j + 1]);
           unpack_iq (rawp[j * kBins + 32], w1r[j + 1], w1i[j + 1]);
         }
-#pragma unroll 1
+#pragma unroll kRdUnroll
         for (int rd = 0; rd < kHopsPerWarp / 8; rd++)
         {
           const int h0 = h_base + 8 * rd;
