@@ -113,6 +113,42 @@ def test_weak_and_full_scale_signals(best_oracle):
             check_int16(y[c], exp)
 
 
+def test_worst_case_inputs_for_the_integer_accumulators(best_oracle):
+    """Inputs that drive the int32 accumulators of the digit products as far as int16 data can: both rails held at -32768 (every
+    high byte -128, every low byte 0), at +32767 (high 127, low 255: the unsigned low-byte operand at its maximum), a full-scale
+    complex tone inside the pass-band (the filter's gain on top), and full-scale alternation at the band edge. Both kernels against
+    the oracle at the plain bars, all default masks."""
+    T = 768 * 4
+    n = np.arange(T)
+    pats = []
+    pats.append(np.full((T, 2), -32768, np.int16))
+    pats.append(np.full((T, 2), 32767, np.int16))
+    tone = np.exp(2j * np.pi * 1000.0 * n / 48000.0)
+    pats.append(np.stack([np.clip(np.rint(tone.real * 32767), -32768, 32767), np.clip(np.rint(tone.imag * 32767), -32768, 32767)], axis=1).astype(np.int16))
+    sq = np.where((n // 8) % 2 == 0, 32767, -32768).astype(np.int16)              # 3 kHz square wave, rail to rail, on both rails
+    pats.append(np.stack([sq, np.roll(sq, 4)], axis=1))
+    x = np.stack(pats)
+    C = len(pats)
+    for mode in (slb.MODE_USB, slb.MODE_LSB, slb.MODE_CW, slb.MODE_DIG):
+        for path in (slb.RX_PATH_AUTO, slb.RX_PATH_FFT):
+            d = slb.DspIf(C, chain=slb.CHAIN_RX_SSB_F32); d.set_rx_path(path); d.DSP_Set_Mode(mode)
+            y, audio, gain = run_gpu(d, x)
+            for c in range(C):
+                exp, a, _, _ = best_oracle.rx_ssb_f32(d.oracle_params(mode), x[c])
+                if float(np.max(np.abs(a[384:]))) < 1e-4:                             # (after the filter has filled)
+                    # a full-scale input the mode's filter rejects by > 80 dB (DC; the tone in the other sideband; the square wave outside a
+                    # narrow filter): what is left of it in the oracle is its own float32 rounding noise, and a bar
+                    # relative to THAT output means nothing (a 512-point float32 FFT of a full-scale signal carries ~ log2 (512) * 2^-24 =
+                    # 5e-7 of it; the integer FIR's own DC leak is the 32-bit map's, 3.6e-9). Held to -120 dB of the input instead.
+                    assert np.max(np.abs(audio[c] - a)) <= 1e-6, (mode, path, c, float(np.max(np.abs(audio[c] - a))), float(np.max(np.abs(a))))
+                else:
+                    assert np.all(np.abs(audio[c] - a) <= audio_tolerance(a) + 1e-12), (mode, path, c, float(np.max(np.abs(audio[c] - a) / (audio_tolerance(a) + 1e-12))))
+                # (constant-envelope inputs park the AGC output on the target, 0.25 * 32768 = an integer: the truncating pack then turns
+                # float differences of 1e-7 into +-1 LSB on more samples than the 2 % of a noisy signal — the LSB bound itself holds)
+                dd = np.abs(y[c].astype(np.int32) - exp.astype(np.int32))
+                assert dd.max() <= 1 and np.mean(dd > 0) < 0.10, (mode, path, c, int(dd.max()), float(np.mean(dd > 0)))
+
+
 def test_caller_mask_that_is_no_fir_stays_on_the_fft_kernel(best_oracle):
     """slb_set_mask with a spectrum that is not the DFT of a 129-tap filter: the channel keeps the FFT kernel (the oracle's
     circular convolution is reproduced, not approximated by a truncated FIR)."""
