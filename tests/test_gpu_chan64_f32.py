@@ -61,6 +61,25 @@ def test_vs_oracle_ragged_shapes(best_oracle, streams, frames):
         check_int16(y[s], exp)
 
 
+def test_worst_case_inputs(best_oracle):
+    """Wideband streams at the rails: both rails held at -32768, at +32767 (DC lands in bin 0), and a full-scale complex tone at the
+    centre of bin 5 — product and envelope detector, against the oracle."""
+    T = 6144 * 2
+    n = np.arange(T)
+    tone = np.exp(2j * np.pi * (5 * 3000.0 + 400.0) * n / 192000.0)
+    x = np.stack([np.full((T, 2), -32768, np.int16), np.full((T, 2), 32767, np.int16),
+                  np.stack([np.clip(np.rint(tone.real * 32767), -32768, 32767), np.clip(np.rint(tone.imag * 32767), -32768, 32767)], axis=1).astype(np.int16)])
+    for mode in (slb.MODE_USB, slb.MODE_AM):
+        d = slb.DspIf(3, fs=192000, chain=slb.CHAIN_CHAN64_F32); d.DSP_Set_Mode(mode)
+        y, audio, gain = run_gpu(d, x)
+        for s_ in range(3):
+            exp, a, g_, _ = best_oracle.chan_f32(d.oracle_params(mode), x[s_])
+            err = np.abs(audio[s_] - a); tol = chan_tolerance(a)
+            assert np.all(err <= tol + 1e-9), (mode, s_, float(np.max(err / (tol + 1e-9))))
+            dd = np.abs(y[s_].astype(np.int32) - exp.astype(np.int32))
+            assert dd.max() <= 1 and np.mean(dd > 0) < 0.10, (mode, s_, int(dd.max()), float(np.mean(dd > 0)))
+
+
 def test_release_walk_across_many_tiles_is_exact(best_oracle):
     """The AGC release is a long sequential recurrence: a burst followed by near silence makes every later tile's
     envelope depend on a carry-in that is many tiles old. The look-back must reproduce the oracle's gains exactly."""

@@ -61,6 +61,33 @@ def test_vs_oracle_ragged_shapes(best_oracle, channels, frames):
         check_int16(y[c], exp)
 
 
+def test_worst_case_inputs_for_the_integer_accumulators(best_oracle):
+    """Mic streams that drive the int32 accumulators of the digit products as far as int16 data can — the rail at -32768, at +32767,
+    a full-scale tone in the pass-band, a rail-to-rail square wave — through both TX kernels, all default masks. A full-scale input
+    the mode's filter rejects by > 80 dB (DC) leaves only the oracle's own float32 rounding noise: held to -120 dB of the input there."""
+    T = 768 * 4
+    n = np.arange(T)
+    pats = [np.full(T, -32768, np.int16), np.full(T, 32767, np.int16),
+            np.clip(np.rint(np.sin(2 * np.pi * 1200.0 * n / 48000.0) * 32767), -32768, 32767).astype(np.int16),
+            np.where((n // 16) % 2 == 0, 32767, -32768).astype(np.int16)]
+    x = np.stack([np.stack([p_, p_], axis=1) for p_ in pats])
+    C = len(pats)
+    for mode in (slb.MODE_USB, slb.MODE_LSB, slb.MODE_CW, slb.MODE_DIG):
+        for path in (slb.RX_PATH_AUTO, slb.RX_PATH_FFT):
+            d = slb.DspIf(C, chain=slb.CHAIN_TX_SSB_F32); d.set_rx_path(path); d.DSP_Set_Mode(mode)
+            y, iq, gain = run_gpu(d, x)
+            for c in range(C):
+                exp, z, g_, _ = best_oracle.tx_ssb_f32(d.oracle_params(mode), x[c])
+                err = np.abs(iq[c] - z)
+                if float(np.max(np.abs(z[384:]))) < 1e-4:
+                    assert np.max(err) <= 1e-6, (mode, path, c, float(np.max(err)))
+                else:
+                    tol = iq_tolerance(z)
+                    assert np.all(err <= tol + 1e-9), (mode, path, c, float(np.max(err / (tol + 1e-9))))
+                dd = np.abs(y[c].astype(np.int32) - exp.astype(np.int32))
+                assert dd.max() <= 1 and np.mean(dd > 0) < 0.10, (mode, path, c, int(dd.max()), float(np.mean(dd > 0)))
+
+
 def test_only_the_left_channel_is_used(best_oracle):
     """The codec routes the microphone to both ADC channels in TX (codec_if.c:304-306); the chain reads L."""
     x = slb.synth_mic(2, 1536)
