@@ -40,10 +40,10 @@ def main():
     g = torch.Generator(device=dev); g.manual_seed(1)
     for which in args.which.split(","):
         if which == "tx":
-            C, T = 1024, 48000 * args.seconds
+            C, T = args.rx_channels, 48000 * args.seconds
             m = torch.randint(-8000, 8000, (C, T, 1), dtype=torch.int16, device=dev, generator=g).expand(C, T, 2).contiguous()
             d = slb.DspIf(C, chain=slb.CHAIN_TX_SSB_F32); y = torch.empty_like(m)
-            ms = timeit(lambda: d.tx_process(m, y), args.steps); n = C * T; name = "tx_ssb_f32 (config 3: 1024 mic channels x %d s)" % args.seconds
+            ms = timeit(lambda: d.tx_process(m, y), args.steps); n = C * T; name = "tx_ssb_f32 (config 3: %d mic channels x %d s)" % (C, args.seconds)
         elif which == "chan":
             S, T = 64, 192000 * args.seconds // 768 * 768
             x = torch.randint(-3000, 3000, (S, T, 2), dtype=torch.int16, device=dev, generator=g)
